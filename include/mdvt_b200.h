@@ -1,0 +1,162 @@
+/*
+ * mdvt_b200.h -- C ABI of libmdvt_b200.so: the dense per-frame path of
+ * calledit/metric_depth_video_toolbox (RGB-encoded depth decode -> pinhole unproject -> pose ->
+ * perspective re-divide -> z-buffered forward splat + hole mask) as sm_100a CUDA kernels.
+ *
+ * The reference has no FFI of its own: its boundary for this path is the Python module surface
+ * of depth_frames_helper.py / depth_map_tools.py and the per-frame loops of stereo_rerender.py,
+ * 3d_view_depthfile.py and convert_metric_depth_video_to_other_format.py.  Each
+ * entry point below names the reference lines it replaces; INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; nothing is allocated,
+ *     freed or retained; all work is enqueued asynchronously on `stream` (a cudaStream_t passed
+ *     as void*, NULL = legacy default stream); entry points are re-entrant.
+ *   - frames are dense row-major u8x3 in RGB order, exactly what the reference holds after
+ *     cv2.cvtColor(BGR2RGB) (stereo_rerender.py:493); pixel index = row * W + col.
+ *   - return value: MDVT_OK or a negative mdvt_status; mdvt_last_error() gives the text for the
+ *     calling thread.
+ *   - float32 arithmetic is IEEE round-to-nearest, one rounding per written operation, no FMA
+ *     contraction (oracle/kernel_model.py restates the op order); the depth decode is bit-exact
+ *     with the reference (integer code, one float32 multiply or divide).
+ */
+#ifndef MDVT_B200_H_
+#define MDVT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDVT_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define MDVT_API __attribute__((visibility("default")))
+#else
+#define MDVT_API
+#endif
+
+typedef enum mdvt_status {
+    MDVT_OK = 0,
+    MDVT_ERR_INVALID_ARGUMENT = -1,
+    MDVT_ERR_UNSUPPORTED = -2,   /* shape / alignment the requested kernel cannot take */
+    MDVT_ERR_CUDA = -3,          /* a CUDA runtime call failed; see mdvt_last_error() */
+    MDVT_ERR_NO_DEVICE = -4      /* no sm_100 device visible */
+} mdvt_status;
+
+/* Which of the reference's three (non-identical) depth decoders to reproduce. */
+typedef enum mdvt_decoder {
+    MDVT_DECODE_D1 = 0, /* depth_frames_helper.py:13-24,63-75,99-103  hi=R lo=B, code * fl32(max/255^4) */
+    MDVT_DECODE_D2 = 1, /* convert_metric_depth_video_to_other_format.py:646-652  hi=(R+G)>>1, code / fl32(255^4/max) */
+    MDVT_DECODE_D3 = 2  /* find_convergence_depth.py:56-60  hi=R lo=B, code / fl32(255^4/max) */
+} mdvt_decoder;
+
+/* Empty z-buffer slot: all ones.  A filled slot is (float_bits(z') << 32) | source_pixel_index. */
+#define MDVT_ZBUF_EMPTY 0xFFFFFFFFFFFFFFFFull
+
+/* Source-frame description shared by the unproject / splat entry points. */
+typedef struct mdvt_source {
+    int32_t width, height;
+    int32_t decoder;      /* mdvt_decoder */
+    int32_t bit16;        /* 1: 16-bit wire format (the only one the scripts use); 0: 24-bit (D1 only) */
+    float dec_const;      /* D1: fl32(max_depth / 255^4) (multiplier); D2/D3: fl32(255^4 / max_depth) (divisor) */
+    float depth_scale;    /* stereo_rerender.py:537-541 master-FOV scale as fl32; 1.0f = none */
+    float fx, fy, cx, cy; /* depth_map_tools.py:902-934, rounded to float32 */
+    float grid_sx, grid_sy; /* of_by_one stretch fl32((W+1)/W), fl32((H+1)/H); 1.0f = exact pixel grid
+                               (depth_map_tools.py:1118-1123) */
+} mdvt_source;
+
+/* One virtual camera: p_view = M * [p_src; 1] (3x4 row-major), then u = fx X/Z + cx, v = fy Y/Z + cy. */
+typedef struct mdvt_view {
+    float M[12];
+    float fx, fy, cx, cy;
+} mdvt_view;
+
+/* Per-frame constants of the row-local stereo fast path (no pose file, no convergence:
+ * v' == v and u' = u +- fx*(ipd/2)/z, stereo_rerender.py:458-459,704-725,831-836). */
+typedef struct mdvt_stereo_frame {
+    float dec_const;    /* as mdvt_source.dec_const (decoder D1) */
+    float depth_scale;  /* as mdvt_source.depth_scale */
+    float fx_half_ipd;  /* fl32(fx * ipd / 2), ipd in metres */
+    float near_plane;   /* cull z' <= near (depth_map_tools.py:1520: 1e-4) */
+} mdvt_stereo_frame;
+
+/* resolve / stereo flags */
+#define MDVT_FLAG_BG_COLLIDE   0x1u /* a rendered colour equal to `bg_rgb` counts as a hole (stereo_rerender.py:740,854) */
+#define MDVT_FLAG_RESET_ZBUF   0x2u /* resolve leaves the z-buffer empty for the next frame */
+#define MDVT_FLAG_MASK_RGB     0x4u /* hole mask written as u8x3 (bg_rgb at holes, black elsewhere, :787-793) instead of u8 {0,255} */
+
+/* ---- library -------------------------------------------------------------------------------- */
+MDVT_API int mdvt_abi_version(void);
+MDVT_API const char *mdvt_version(void);
+MDVT_API const char *mdvt_last_error(void);
+/* SM count, L2 bytes, shared memory per block (opt-in) of the current device; any pointer may be NULL. */
+MDVT_API int mdvt_device_info(int *sm_count, int *l2_bytes, int *smem_optin_bytes, int *cc_major, int *cc_minor);
+
+/* ---- wire-format codec ---------------------------------------------------------------------- */
+/* depth_frames_helper.decode_rgb_depth_frame / decode_rgb_as_data / decode_uint32_as_depth
+ * (depth_frames_helper.py:13-24,63-75,99-103) and the inline D2/D3 variants.
+ * rgb: n_pixels*3 u8.  out_codes (u32) and out_depth (f32) may each be NULL. */
+MDVT_API int mdvt_decode_depth(const uint8_t *rgb, int64_t n_pixels, int decoder, int bit16, float dec_const,
+                      uint32_t *out_codes, float *out_depth, void *stream);
+
+/* depth_frames_helper.encode_depth_as_uint32 + encode_data_as_BGR (depth_frames_helper.py:5-11,48-61):
+ * clip to [0,max_depth], (255^4/max_depth * double(depth)) truncated to u32, bytes -> u8x3.
+ * `bgr_order` = 1 writes B,G,R (what the reference returns for cv2), 0 writes R,G,B.
+ * out_codes may be NULL; out_pix may be NULL. */
+MDVT_API int mdvt_encode_depth(const float *depth, int64_t n_pixels, double max_depth, int bit16, int bgr_order,
+                      uint32_t *out_codes, uint8_t *out_pix, void *stream);
+
+/* ---- decode + unproject (+ pose) -> point cloud --------------------------------------------- */
+/* decode -> depth_scale -> depth_map_tools.create_point_cloud_from_depth (depth_map_tools.py:1112-1133)
+ * -> optional 3x4 pose (transform_points, depth_map_tools.py:977-1004).  pose_host: 12 floats on
+ * the HOST (row-major 3x4) or NULL.  out_xyz: n*3 f32. */
+MDVT_API int mdvt_unproject_f32(const uint8_t *depth_rgb, const mdvt_source *src_host, const float *pose_host,
+                       float *out_xyz, void *stream);
+/* Same in float64 with the reference's own operation order (K and pose given as doubles): xyz is
+ * bit-identical to NumPy for the unprojection.  K_host: fx, fy, cx, cy; pose_host: 12 doubles or NULL.
+ * out_xyz: n*3 f64 -- the .ply export path (convert_metric_depth_video_to_other_format.py:692-749). */
+MDVT_API int mdvt_unproject_f64(const uint8_t *depth_rgb, const mdvt_source *src_host, const double *K_host,
+                       const double *pose_host, double *out_xyz, void *stream);
+
+/* ---- generic novel-view path: fused decode/unproject/pose/project + z-buffered splat, then resolve */
+MDVT_API int mdvt_zbuf_clear(uint64_t *zbuf, int64_t n_slots, void *stream);
+
+/* K1+K2.  For each of n_views cameras (views_host: HOST array, n_views <= 4) every source pixel is
+ * decoded, unprojected, moved by M, culled if z' <= near, projected, rounded half-to-even, bounds
+ * checked against out_w x out_h and merged into zbuf[view] with one 64-bit atomicMin
+ * (nearest z' wins, ties -> lowest source index; stereo_rerender.py:746-755,814 and the GL depth
+ * test of depth_map_tools.py:1563-1572).  zbuf: n_views * out_w*out_h u64, pre-cleared.
+ * out_uvz (optional, n_views * n_pixels * 3 f32) receives (u', v', z') per source pixel for parity checks. */
+MDVT_API int mdvt_project_splat(const uint8_t *depth_rgb, const mdvt_source *src_host, const mdvt_view *views_host,
+                       int n_views, float near_plane, int out_w, int out_h, uint64_t *zbuf, float *out_uvz,
+                       void *stream);
+
+/* K3.  zbuf (one view, out_w*out_h) + source colours -> image / hole mask / depth plane.
+ * out_rgb: row r starts at out_rgb + r*rgb_pitch (bytes), so a view can be written straight into its
+ * half of a side-by-side frame (cv2.hconcat, stereo_rerender.py:918); same for out_mask / mask_pitch.
+ * out_depth (f32, dense out_w*out_h; 0 where nothing was drawn), out_ids (int32, -1 = hole) optional.
+ * bg_rgb / fill_rgb: 0x00BBGGRR packed (R in the low byte). */
+MDVT_API int mdvt_resolve(uint64_t *zbuf, const uint8_t *colour_rgb, int out_w, int out_h, uint32_t bg_rgb,
+                 uint32_t fill_rgb, uint32_t flags, uint8_t *out_rgb, int64_t rgb_pitch, uint8_t *out_mask,
+                 int64_t mask_pitch, float *out_depth, int32_t *out_ids, void *stream);
+
+/* ---- row-local stereo fast path: ONE fused kernel, frames batched ---------------------------- */
+/* Whole stereo_rerender.py frame loop body (:512-541 decode+scale, :583 unproject, :723-738,:831-852 eye
+ * poses + render, :740,:787-793,:854 hole mask, :918 hconcat) for a batch of frames when there is no
+ * pose file and no convergence rotation.  depth_rgb / colour_rgb: n_frames*H*W*3 u8;
+ * frames_dev: DEVICE array of mdvt_stereo_frame, n_frames entries (or 1 entry if per_frame == 0);
+ * out_sbs: n_frames * H * 2W * 3 u8 (left | right); out_mask: n_frames * H * 2W u8 {0,255}
+ * (or u8x3 with MDVT_FLAG_MASK_RGB), may be NULL.  z-buffers live in shared memory; nothing else
+ * touches HBM.  Requires W <= 65535. */
+MDVT_API int mdvt_stereo_rows(const uint8_t *depth_rgb, const uint8_t *colour_rgb, int n_frames, int width, int height,
+                     const mdvt_stereo_frame *frames_dev, int per_frame, uint32_t bg_rgb, uint32_t fill_rgb,
+                     uint32_t flags, uint8_t *out_sbs, uint8_t *out_mask, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDVT_B200_H_ */

@@ -1,0 +1,228 @@
+// Generic novel-view path: K1+K2 (decode -> unproject -> pose -> project -> 64-bit atomicMin splat) and
+// K3 (resolve: gather colour by winning source index, hole mask, depth plane, z-buffer reset).
+//
+// The z-buffer is a u64 plane per view: (float_bits(z') << 32) | source_index.  z' > near > 0, so the
+// float bit pattern orders like the value and one unsigned atomicMin implements "nearest wins, ties ->
+// lowest source index" deterministically.  1080p stereo = 33 MB, 4K single view = 66 MB: both stay
+// resident in the 126 MB L2, so the RED traffic does not reach HBM.
+#include "mdvt_common.cuh"
+
+namespace mdvt {
+
+constexpr int kThreads = 256;
+constexpr int kMaxViews = 4;
+
+struct ViewPack {
+    mdvt_view v[kMaxViews];
+    int n;
+};
+
+template <int DECODER, bool BIT16>
+__global__ void __launch_bounds__(kThreads)
+    project_splat_kernel(const uint8_t *__restrict__ rgb, int width, int64_t n, float dec_const, float depth_scale, SourceCam cam,
+                         ViewPack views, float near_plane, int out_w, int out_h, unsigned long long *__restrict__ zbuf,
+                         float *__restrict__ out_uvz) {
+    const int64_t out_n = (int64_t)out_w * out_h;
+    const float u_max = (float)(out_w - 1), v_max = (float)(out_h - 1);
+    for (int64_t p = blockIdx.x * (int64_t)kThreads + threadIdx.x; p < n; p += (int64_t)gridDim.x * kThreads) {
+        const uint32_t r = rgb[p * 3], g = rgb[p * 3 + 1], b = rgb[p * 3 + 2];
+        const float z = __fmul_rn(depth_of<DECODER>(code_of<DECODER, BIT16>(r, g, b), dec_const), depth_scale);
+        const int row = (int)(p / width), col = (int)(p - (int64_t)row * width);
+        float X, Y;
+        unproject_px(cam, col, row, z, X, Y);
+#pragma unroll
+        for (int k = 0; k < kMaxViews; ++k) {
+            if (k < views.n) {
+                const mdvt_view &vw = views.v[k];
+                const float Xv = affine_row(vw.M, X, Y, z);
+                const float Yv = affine_row(vw.M + 4, X, Y, z);
+                const float Zv = affine_row(vw.M + 8, X, Y, z);
+                const float u = __fadd_rn(__fdiv_rn(__fmul_rn(vw.fx, Xv), Zv), vw.cx);
+                const float v = __fadd_rn(__fdiv_rn(__fmul_rn(vw.fy, Yv), Zv), vw.cy);
+                if (out_uvz) {
+                    float *o = out_uvz + ((int64_t)k * n + p) * 3;
+                    o[0] = u; o[1] = v; o[2] = Zv;
+                }
+                const float ur = rintf(u), vr = rintf(v);  // round half to even, like np.round
+                // comparisons are false for NaN, so non-finite projections are culled too
+                if (Zv > near_plane && ur >= 0.0f && ur <= u_max && vr >= 0.0f && vr <= v_max) {
+                    const int64_t t = (int64_t)(int)vr * out_w + (int)ur;
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(Zv) << 32) | (uint32_t)p;
+                    atomicMin(zbuf + (int64_t)k * out_n + t, key);
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) zbuf_clear_kernel(unsigned long long *__restrict__ zbuf, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+        zbuf[i] = MDVT_ZBUF_EMPTY;
+}
+
+__device__ __forceinline__ uint32_t gather_rgb(const uint8_t *__restrict__ colour, uint32_t id) {
+    const uint8_t *c = colour + (int64_t)id * 3;
+    return (uint32_t)__ldg(c) | ((uint32_t)__ldg(c + 1) << 8) | ((uint32_t)__ldg(c + 2) << 16);
+}
+
+// One thread per target pixel (scalar stores): used when widths / pitches are not multiples of 4.
+// VEC = 4: one thread per 4 consecutive target pixels of a row, word stores.
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+    resolve_kernel(unsigned long long *__restrict__ zbuf, const uint8_t *__restrict__ colour, int out_w, int out_h, uint32_t bg_rgb,
+                   uint32_t fill_rgb, uint32_t flags, uint8_t *__restrict__ out_rgb, int64_t rgb_pitch, uint8_t *__restrict__ out_mask,
+                   int64_t mask_pitch, float *__restrict__ out_depth, int32_t *__restrict__ out_ids) {
+    const int groups_per_row = out_w / VEC;
+    const int64_t n_groups = (int64_t)groups_per_row * out_h;
+    const bool collide = flags & MDVT_FLAG_BG_COLLIDE, reset = flags & MDVT_FLAG_RESET_ZBUF, mask_rgb = flags & MDVT_FLAG_MASK_RGB;
+    for (int64_t gidx = blockIdx.x * (int64_t)kThreads + threadIdx.x; gidx < n_groups; gidx += (int64_t)gridDim.x * kThreads) {
+        const int row = (int)(gidx / groups_per_row), col0 = (int)(gidx - (int64_t)row * groups_per_row) * VEC;
+        const int64_t t0 = (int64_t)row * out_w + col0;
+        unsigned long long key[4];
+        if (VEC == 4) {
+            const ulonglong2 a = reinterpret_cast<const ulonglong2 *>(zbuf + t0)[0];
+            const ulonglong2 b = reinterpret_cast<const ulonglong2 *>(zbuf + t0)[1];
+            key[0] = a.x; key[1] = a.y; key[2] = b.x; key[3] = b.y;
+        } else {
+            key[0] = zbuf[t0];
+        }
+        uint32_t px[4], mk[4];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            bool hole = key[k] == MDVT_ZBUF_EMPTY;
+            uint32_t c = fill_rgb;
+            if (!hole) {
+                c = gather_rgb(colour, (uint32_t)key[k]);
+                if (collide && c == bg_rgb) hole = true;
+                if (hole) c = fill_rgb;
+            }
+            px[k] = c;
+            mk[k] = hole ? 1u : 0u;
+            if (out_depth) out_depth[t0 + k] = (key[k] == MDVT_ZBUF_EMPTY) ? 0.0f : __uint_as_float((uint32_t)(key[k] >> 32));
+            if (out_ids) out_ids[t0 + k] = (key[k] == MDVT_ZBUF_EMPTY) ? -1 : (int32_t)(uint32_t)key[k];
+        }
+        if (reset) {
+            if (VEC == 4) {
+                const ulonglong2 e = make_ulonglong2(MDVT_ZBUF_EMPTY, MDVT_ZBUF_EMPTY);
+                reinterpret_cast<ulonglong2 *>(zbuf + t0)[0] = e;
+                reinterpret_cast<ulonglong2 *>(zbuf + t0)[1] = e;
+            } else {
+                zbuf[t0] = MDVT_ZBUF_EMPTY;
+            }
+        }
+        if (out_rgb) {
+            uint8_t *o = out_rgb + row * rgb_pitch + (int64_t)col0 * 3;
+            if (VEC == 4) {
+                uint32_t *ow = reinterpret_cast<uint32_t *>(o);
+                ow[0] = px[0] | (px[1] << 24);
+                ow[1] = (px[1] >> 8) | (px[2] << 16);
+                ow[2] = (px[2] >> 16) | (px[3] << 8);
+            } else {
+                o[0] = (uint8_t)px[0]; o[1] = (uint8_t)(px[0] >> 8); o[2] = (uint8_t)(px[0] >> 16);
+            }
+        }
+        if (out_mask) {
+            if (mask_rgb) {
+                uint8_t *o = out_mask + row * mask_pitch + (int64_t)col0 * 3;
+                uint32_t m[4];
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) m[k] = mk[k] ? bg_rgb : 0u;
+                if (VEC == 4) {
+                    uint32_t *ow = reinterpret_cast<uint32_t *>(o);
+                    ow[0] = m[0] | (m[1] << 24);
+                    ow[1] = (m[1] >> 8) | (m[2] << 16);
+                    ow[2] = (m[2] >> 16) | (m[3] << 8);
+                } else {
+                    o[0] = (uint8_t)m[0]; o[1] = (uint8_t)(m[0] >> 8); o[2] = (uint8_t)(m[0] >> 16);
+                }
+            } else {
+                uint8_t *o = out_mask + row * mask_pitch + col0;
+                if (VEC == 4) {
+                    *reinterpret_cast<uint32_t *>(o) =
+                        (mk[0] * 0xFFu) | ((mk[1] * 0xFFu) << 8) | ((mk[2] * 0xFFu) << 16) | ((mk[3] * 0xFFu) << 24);
+                } else {
+                    o[0] = mk[0] ? 255 : 0;
+                }
+            }
+        }
+    }
+}
+
+static int grid_for(int64_t work_items) {
+    const int64_t blocks = (work_items + kThreads - 1) / kThreads;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    return (int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
+}
+
+}  // namespace mdvt
+
+using namespace mdvt;
+
+extern "C" int mdvt_zbuf_clear(uint64_t *zbuf, int64_t n_slots, void *stream) {
+    MDVT_REQUIRE(n_slots >= 0, "negative slot count");
+    if (n_slots == 0) return MDVT_OK;
+    MDVT_REQUIRE(zbuf != nullptr, "zbuf is NULL");
+    zbuf_clear_kernel<<<grid_for(n_slots), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<unsigned long long *>(zbuf), n_slots);
+    MDVT_CUDA_TRY(cudaGetLastError());
+    return MDVT_OK;
+}
+
+extern "C" int mdvt_project_splat(const uint8_t *depth_rgb, const mdvt_source *src, const mdvt_view *views_host, int n_views,
+                                  float near_plane, int out_w, int out_h, uint64_t *zbuf, float *out_uvz, void *stream) {
+    MDVT_REQUIRE(src != nullptr, "mdvt_source is NULL");
+    MDVT_REQUIRE(src->width > 0 && src->height > 0, "bad frame size %dx%d", src->width, src->height);
+    MDVT_REQUIRE(src->decoder >= MDVT_DECODE_D1 && src->decoder <= MDVT_DECODE_D3, "unknown decoder %d", src->decoder);
+    if (!src->bit16 && src->decoder != MDVT_DECODE_D1) {
+        set_error("the 24-bit wire format exists for decoder D1 only");
+        return MDVT_ERR_UNSUPPORTED;
+    }
+    MDVT_REQUIRE(n_views >= 1 && n_views <= kMaxViews, "n_views must be 1..%d", kMaxViews);
+    MDVT_REQUIRE(views_host && depth_rgb && zbuf, "NULL buffer");
+    MDVT_REQUIRE(out_w > 0 && out_h > 0, "bad output size %dx%d", out_w, out_h);
+    const int64_t n = (int64_t)src->width * src->height;
+    MDVT_REQUIRE(n <= 0xFFFFFFFFll, "source frame has more than 2^32 pixels");
+    ViewPack pack{};
+    pack.n = n_views;
+    for (int k = 0; k < n_views; ++k) pack.v[k] = views_host[k];
+    SourceCam cam{src->fx, src->fy, src->cx, src->cy, src->grid_sx, src->grid_sy};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned long long *zb = reinterpret_cast<unsigned long long *>(zbuf);
+    const int grid = grid_for(n);
+#define CALL(D, B)                                                                                                          \
+    project_splat_kernel<D, B><<<grid, kThreads, 0, st>>>(depth_rgb, src->width, n, src->dec_const, src->depth_scale, cam, pack, \
+                                                          near_plane, out_w, out_h, zb, out_uvz)
+    if (src->decoder == MDVT_DECODE_D1 && src->bit16) { CALL(MDVT_DECODE_D1, true); }
+    else if (src->decoder == MDVT_DECODE_D1) { CALL(MDVT_DECODE_D1, false); }
+    else if (src->decoder == MDVT_DECODE_D2) { CALL(MDVT_DECODE_D2, true); }
+    else { CALL(MDVT_DECODE_D3, true); }
+#undef CALL
+    MDVT_CUDA_TRY(cudaGetLastError());
+    return MDVT_OK;
+}
+
+extern "C" int mdvt_resolve(uint64_t *zbuf, const uint8_t *colour_rgb, int out_w, int out_h, uint32_t bg_rgb, uint32_t fill_rgb,
+                            uint32_t flags, uint8_t *out_rgb, int64_t rgb_pitch, uint8_t *out_mask, int64_t mask_pitch,
+                            float *out_depth, int32_t *out_ids, void *stream) {
+    MDVT_REQUIRE(zbuf && colour_rgb, "NULL buffer");
+    MDVT_REQUIRE(out_w > 0 && out_h > 0, "bad output size %dx%d", out_w, out_h);
+    const int mask_bpp = (flags & MDVT_FLAG_MASK_RGB) ? 3 : 1;
+    MDVT_REQUIRE(!out_rgb || rgb_pitch >= (int64_t)out_w * 3, "rgb_pitch %lld too small", (long long)rgb_pitch);
+    MDVT_REQUIRE(!out_mask || mask_pitch >= (int64_t)out_w * mask_bpp, "mask_pitch %lld too small", (long long)mask_pitch);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned long long *zb = reinterpret_cast<unsigned long long *>(zbuf);
+    const bool vec4 = (out_w % 4 == 0) && (reinterpret_cast<uintptr_t>(zbuf) % 16 == 0) &&
+                      (!out_rgb || (reinterpret_cast<uintptr_t>(out_rgb) % 4 == 0 && rgb_pitch % 4 == 0)) &&
+                      (!out_mask || (reinterpret_cast<uintptr_t>(out_mask) % 4 == 0 && mask_pitch % 4 == 0));
+    bg_rgb &= 0xFFFFFF;
+    fill_rgb &= 0xFFFFFF;
+    if (vec4) {
+        resolve_kernel<4><<<grid_for((int64_t)out_w / 4 * out_h), kThreads, 0, st>>>(
+            zb, colour_rgb, out_w, out_h, bg_rgb, fill_rgb, flags, out_rgb, rgb_pitch, out_mask, mask_pitch, out_depth, out_ids);
+    } else {
+        resolve_kernel<1><<<grid_for((int64_t)out_w * out_h), kThreads, 0, st>>>(
+            zb, colour_rgb, out_w, out_h, bg_rgb, fill_rgb, flags, out_rgb, rgb_pitch, out_mask, mask_pitch, out_depth, out_ids);
+    }
+    MDVT_CUDA_TRY(cudaGetLastError());
+    return MDVT_OK;
+}

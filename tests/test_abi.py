@@ -1,0 +1,87 @@
+"""CPU: the C-ABI library builds, loads, exports every symbol include/mdvt_b200.h declares, and its
+argument validation (which runs before any CUDA call) reports errors the documented way.
+No compute call is made here."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from metric_depth_video_toolbox_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "mdvt_b200.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    return sorted(set(re.findall(r"MDVT_API\s+[\w\s\*]+?\b(mdvt_\w+)\s*\(", text)))
+
+
+def test_library_builds_and_loads():
+    path = build.build()
+    assert os.path.isfile(path)
+    lib = _lib.load()
+    assert lib.mdvt_abi_version() == _lib.ABI_VERSION
+    assert b"sm_100a" in lib.mdvt_version()
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    declared = declared_symbols()
+    assert len(declared) >= 12
+    out = subprocess.run(["nm", "-D", "--defined-only", build.build()], capture_output=True, text=True, check=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    missing = [s for s in declared if s not in exported]
+    assert not missing, f"declared in the header but not exported: {missing}"
+    stray = sorted(s for s in exported if s.startswith("mdvt_") and s not in declared)
+    assert not stray, f"exported but not declared: {stray}"
+    assert sorted(_lib.exported_names()) == declared  # the Python binding covers the whole header
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(_lib.Source) == 4 * 4 + 8 * 4
+    assert C.sizeof(_lib.View) == 16 * 4
+    assert C.sizeof(_lib.StereoFrame) == 16
+
+
+def test_sass_contains_tma_and_atomics():
+    """The built library really holds the Blackwell paths the design names: 1-D TMA bulk copies
+    (UBLKCP), mbarrier transactions (SYNCS), shared-memory and 64-bit global atomic min."""
+    sass = subprocess.run(["cuobjdump", "-sass", build.build()], capture_output=True, text=True)
+    if sass.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    for mnemonic in ("UBLKCP", "SYNCS", "ATOMS", "MIN.64"):
+        assert mnemonic in sass.stdout, mnemonic
+    assert "sm_100a" in sass.stdout
+    # --fmad=false: the parity contract forbids contraction in the geometry kernels
+    body = sass.stdout.split("stereo_rows_kernel")[1]
+    assert "FMUL" in body
+
+
+def test_argument_validation_without_a_device():
+    lib = _lib.load()
+    assert lib.mdvt_decode_depth(None, -1, 0, 1, 1.0, None, None, None) == -1
+    assert b"negative" in lib.mdvt_last_error()
+    assert lib.mdvt_decode_depth(None, 16, 7, 1, 1.0, None, None, None) == -1  # unknown decoder
+    assert lib.mdvt_decode_depth(None, 16, _lib.DECODE_D2, 0, 1.0, None, None, None) == -2  # 24-bit is D1-only
+    assert lib.mdvt_decode_depth(None, 0, 0, 1, 1.0, None, None, None) == 0  # empty input is a no-op
+    assert lib.mdvt_encode_depth(None, 4, 0.0, 1, 1, None, None, None) == -1
+    assert lib.mdvt_stereo_rows(None, None, 1, 70000, 4, None, 0, 0, 0, 0, None, None, None) == -2
+    assert b"65535" in lib.mdvt_last_error()
+    assert lib.mdvt_stereo_rows(None, None, 0, 64, 4, None, 0, 0, 0, 0, None, None, None) == 0
+    assert lib.mdvt_zbuf_clear(None, 0, None) == 0
+    src = _lib.Source()
+    assert lib.mdvt_project_splat(None, C.byref(src), None, 1, 1e-4, 4, 4, None, None, None) == -1  # 0x0 frame
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+
+    from metric_depth_video_toolbox_b200 import ops
+
+    with pytest.raises(TypeError, match="no CPU path"):
+        ops.decode_depth(torch.zeros((4, 3), dtype=torch.uint8), 100)
+    with pytest.raises(TypeError, match="no CPU path"):
+        ops.stereo_rows(torch.zeros((1, 2, 16, 3), dtype=torch.uint8), torch.zeros((1, 2, 16, 3), dtype=torch.uint8),
+                        torch.zeros((1, 4)))

@@ -1,0 +1,101 @@
+"""CPU: the float32 kernel model (what the CUDA kernels compute, bit for bit) against the float64
+oracle (what the reference computes).  Tolerance from BASELINE.json: 1e-4 relative on the float
+unproject / reproject; winners identical except near rounding boundaries / z ties (counted)."""
+import numpy as np
+import pytest
+
+from oracle import kernel_model as km
+from oracle import mdvt_oracle as orc
+from metric_depth_video_toolbox_b200.synth import SyntheticClip
+
+REL_TOL = 1e-4  # BASELINE.json north_star: "within 1e-4 relative on the float unproject/reproject"
+
+
+def rel_err(a, b, floor):
+    return np.abs(a.astype(np.float64) - b) / np.maximum(np.abs(b), floor)
+
+
+def boundary_explained(u64, v64, z64, ids_a, ids_b, w, h):
+    """Every target pixel where two id buffers disagree must involve a source whose float64
+    (u', v') lies within 1e-3 px of a .5 rounding boundary, or two candidates whose z' differ by
+    less than 1e-5 relative."""
+    diff = np.argwhere(ids_a != ids_b)
+    near_half = (np.abs((u64 - np.floor(u64)) - 0.5) < 1e-3) | (np.abs((v64 - np.floor(v64)) - 0.5) < 1e-3)
+    unexplained = 0
+    for r, c in diff:
+        cands = [i for i in (ids_a[r, c], ids_b[r, c]) if i >= 0]
+        ok = any(near_half[i] for i in cands)
+        if not ok and len(cands) == 2:
+            za, zb = z64[cands[0]], z64[cands[1]]
+            ok = abs(za - zb) <= 1e-5 * max(abs(za), abs(zb))
+        if not ok:
+            # a hole on one side: some source rounding into / out of (r, c) must sit on a boundary
+            ur, vr = np.rint(u64), np.rint(v64)
+            near = near_half & (np.abs(ur - c) <= 1) & (np.abs(vr - r) <= 1)
+            ok = bool(near.any())
+        unexplained += 0 if ok else 1
+    return len(diff), unexplained
+
+
+@pytest.mark.parametrize("size", [(64, 48), (640, 480)])
+@pytest.mark.parametrize("posed", [False, True])
+def test_generic_view_model_vs_oracle(size, posed):
+    w, h = size
+    depth_rgb, colour = SyntheticClip(w, h, 4, zero_fraction=0.005).frame(2)
+    K = orc.camera_matrix(60.0, None, w, h)
+    scale = orc.master_fov_depth_scale(45.0, 60.0)
+    M = orc.eye_pose("left", 0.063, 0.008 if posed else None)
+    if posed:
+        T = np.eye(4)
+        T[:3, :3] = orc.rot_y(0.01)
+        T[:3, 3] = (0.05, -0.02, 0.1)
+        M = M @ T
+    u64, v64, z64 = orc.view_uvz(depth_rgb, 100, K, M, depth_scale=scale)
+    src = km.source_constants(w, h, K, 100, depth_scale=scale)
+    u32, v32, z32 = km.view_uvz_f32(depth_rgb, src, M, (K[0, 0], K[1, 1], K[0, 2], K[1, 2]))
+    ok = z64 > orc.NEAR_PLANE
+    assert rel_err(z32[ok], z64[ok], 1e-6).max() < REL_TOL
+    # u, v are pixel coordinates: relative to the coordinate with a 1 px floor
+    assert rel_err(u32[ok], u64[ok], 1.0).max() < REL_TOL
+    assert rel_err(v32[ok], v64[ok], 1.0).max() < REL_TOL
+    ids64 = orc.splat_ids(u64, v64, z64, w, h)
+    ids32 = km.splat_ids_f32(u32, v32, z32, w, h)
+    n_diff, unexplained = boundary_explained(u64, v64, z64, ids32, ids64, w, h)
+    assert unexplained == 0
+    assert n_diff <= max(4, int(2e-3 * w * h)), n_diff
+
+
+@pytest.mark.parametrize("size", [(64, 48), (640, 480)])
+def test_stereo_rows_model_vs_oracle(size):
+    w, h = size
+    from metric_depth_video_toolbox_b200.ops import stereo_frame_constants
+
+    depth_rgb, colour = SyntheticClip(w, h, 4, zero_fraction=0.005).frame(1)
+    colour[3, 5] = (0, 255, 0)  # planted pure green: must read as a hole with infill_mask on
+    consts = stereo_frame_constants(60.0, w, 100, 63, 45.0)
+    sbs32, mask32, ids32 = km.stereo_rows_f32(depth_rgb, colour, consts, bg_rgb=(0, 255, 0), bg_collide=True)
+    sbs64, mask64, ids64 = orc.stereo_frame(depth_rgb, colour, 60.0, infill_mask=True)
+    K = orc.camera_matrix(60.0, None, w, h)
+    scale = orc.master_fov_depth_scale(45.0, 60.0)
+    total_diff = 0
+    for eye, a, b in (("left", ids32[0], ids64[0]), ("right", ids32[1], ids64[1])):
+        u64, v64, z64 = orc.view_uvz(depth_rgb, 100, K, orc.eye_pose(eye, 0.063, None), depth_scale=scale)
+        n_diff, unexplained = boundary_explained(u64, v64, z64, a, b, w, h)
+        assert unexplained == 0
+        total_diff += n_diff
+    assert total_diff <= max(4, int(2e-3 * w * h))
+    same = (np.concatenate(ids32, axis=1) == np.concatenate(ids64, axis=1))
+    assert np.array_equal(sbs32[same], sbs64[same]) and np.array_equal(mask32[same], mask64[same])
+    assert (mask64 == 255).mean() > 0.001  # the clip really has disocclusion holes
+
+
+def test_stereo_rows_key_order_equals_z_order():
+    """z is strictly increasing in the 16-bit code for any positive constants, so ordering by
+    (code16, column) == ordering by (z', source index): the row kernel's 32-bit key is exact."""
+    from metric_depth_video_toolbox_b200.ops import stereo_frame_constants
+
+    for xfov, md in ((60.0, 100), (33.0, 20), (110.0, 7)):
+        dec, scale, _, _ = stereo_frame_constants(xfov, 1920, md, 63, 45.0)
+        c16 = np.arange(65536, dtype=np.uint32)
+        z = ((c16 << 16).astype(np.float32) * np.float32(dec)) * np.float32(scale)
+        assert np.all(np.diff(z.astype(np.float64)) > 0)
