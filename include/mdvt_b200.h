@@ -87,6 +87,7 @@ typedef struct mdvt_stereo_frame {
 /* resolve / stereo flags */
 #define MDVT_FLAG_BG_COLLIDE   0x1u /* a rendered colour equal to `bg_rgb` counts as a hole (stereo_rerender.py:740,854) */
 #define MDVT_FLAG_RESET_ZBUF   0x2u /* resolve leaves the z-buffer empty for the next frame */
+#define MDVT_FLAG_ANYWIDTH      0x8u /* mdvt_stereo_rows: force the any-width kernel even when W % 32 == 0 (test aid; same results) */
 #define MDVT_FLAG_MASK_RGB     0x4u /* hole mask written as u8x3 (bg_rgb at holes, black elsewhere, :787-793) instead of u8 {0,255} */
 
 /* ---- library -------------------------------------------------------------------------------- */

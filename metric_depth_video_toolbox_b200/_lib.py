@@ -15,7 +15,7 @@ from . import build as _build
 OK = 0
 DECODE_D1, DECODE_D2, DECODE_D3 = 0, 1, 2
 DECODERS = {"D1": DECODE_D1, "D2": DECODE_D2, "D3": DECODE_D3}
-FLAG_BG_COLLIDE, FLAG_RESET_ZBUF, FLAG_MASK_RGB = 0x1, 0x2, 0x4
+FLAG_BG_COLLIDE, FLAG_RESET_ZBUF, FLAG_MASK_RGB, FLAG_ANYWIDTH = 0x1, 0x2, 0x4, 0x8
 ZBUF_EMPTY = 0xFFFFFFFFFFFFFFFF
 ABI_VERSION = 1
 

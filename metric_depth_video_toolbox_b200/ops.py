@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import DECODERS, FLAG_BG_COLLIDE, FLAG_MASK_RGB, FLAG_RESET_ZBUF, MdvtError  # noqa: F401
+from ._lib import DECODERS, FLAG_ANYWIDTH, FLAG_BG_COLLIDE, FLAG_MASK_RGB, FLAG_RESET_ZBUF, MdvtError  # noqa: F401
 
 FULL_SCALE = 255 ** 4
 NEAR_PLANE = 1e-4  # depth_map_tools.py:1520

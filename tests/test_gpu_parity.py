@@ -190,7 +190,7 @@ def test_resolve_mask_rgb_and_white_background():
 # ---------------------------------------------------------------------------------------------
 # fused row-local stereo kernel
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("size", [(64, 48), (640, 480), (70, 33), (1920, 8)])
+@pytest.mark.parametrize("size", [(64, 48), (640, 480), (70, 33), (48, 16), (1920, 8)])  # fast W%32, any-width, bulk W%16
 @pytest.mark.parametrize("mask_rgb", [False, True])
 def test_stereo_rows_bit_exact_vs_model(size, mask_rgb):
     w, h = size
