@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- stereo-reprojected frames/s at 1920x1080 (BASELINE.json metric, configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path over one 300-frame 1920x1080 synthetic clip per GPU
+(decode + master-FOV scale + unproject + eye poses + re-projection + z-buffered splat + hole masks,
+side-by-side output): ONE launch of the fused row kernel.  Frames shard across ranks with no data-path
+collective (weak scaling: 300 frames per GPU; rank 0 broadcasts the per-frame constant block only).
+
+  value     whole-job frames/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e       same clip through the public host API (StereoRerenderer.render_host): pinned host buffers,
+            H2D + kernel + D2H inside the timed region
+  roofline  algorithmic bytes (14 B/px: 6 in, 8 out) / mean launch time vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the NumPy oracle port of the reference path on a bounded sample (rank 0, N=1)
+
+--impl reference times the reference's CPU path (NumPy oracle port; the reference itself needs
+open3d + a Windows-only render()) on all host cores, a bounded sample per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WIDTH, HEIGHT, CLIP_FRAMES = 1920, 1080, 300
+XFOV, MAX_DEPTH, IPD_MM, MASTER_XFOV = 60.0, 100, 63, 45.0
+BYTES_PER_PX = 14  # depth u8x3 + colour u8x3 in; 2 x RGB u8x3 + 2 x mask u8 out
+METRIC = "stereo-reprojected frames/sec at 1920x1080"
+WORKLOAD = "configs[1]: 1920x1080 x 300-frame synthetic clip, stereo_rerender left/right warp + hole masks"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--frames", type=int, default=CLIP_FRAMES, help="frames per GPU per step")
+    ap.add_argument("--distinct-frames", type=int, default=30, help="distinct synthetic frames generated per rank (tiled to --frames)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-frames", type=int, default=24, help="frames of the bounded CPU-baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.samples, self.proc, self.gpu = [], None, gpu_index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.12)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, sm_max, reasons = [], 0, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.samples:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                sm_max = max(sm_max, float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": sm_max or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arms (the only places that touch oracle/)
+# ------------------------------------------------------------------------------------------------
+_CPU_FRAMES = {}  # pre-generated synthetic frames (inherited by forked workers): generation is never timed
+
+
+def _prepare_cpu_frames(count: int):
+    from metric_depth_video_toolbox_b200.synth import SyntheticClip
+
+    clip = SyntheticClip(WIDTH, HEIGHT, CLIP_FRAMES)
+    for k in range(count):
+        if k not in _CPU_FRAMES:
+            _CPU_FRAMES[k] = clip.frame(k)
+
+
+def _oracle_stereo_frame(idx):
+    from oracle import mdvt_oracle as orc
+
+    depth_rgb, colour = _CPU_FRAMES[idx % len(_CPU_FRAMES)]
+    t0 = time.perf_counter()
+    sbs, mask, _ = orc.stereo_frame(depth_rgb, colour, XFOV, None, MAX_DEPTH, IPD_MM, MASTER_XFOV, infill_mask=True)
+    return time.perf_counter() - t0, int(sbs[::97, ::89].sum()) + int(mask.sum() // 255)
+
+
+def cpu_baseline(n_frames: int):
+    """Oracle port, one core, frames already in RAM (generation is outside the timed part)."""
+    _prepare_cpu_frames(n_frames)
+    times = [_oracle_stereo_frame(i)[0] for i in range(n_frames)]
+    total = sum(times)
+    return {"value": n_frames / total, "unit": "frames/s", "cores": 1, "kind": "port",
+            "sample": f"{n_frames} frames of the same 1920x1080 clip through oracle/mdvt_oracle.stereo_frame (NumPy float64, both eyes + masks), "
+                      f"{total:.1f} s of CPU work"}
+
+
+def run_reference(args):
+    """The reference's CPU path (NumPy oracle port) on all host cores: frames are independent, so they are
+    fanned over a process pool exactly like movie_2_3D.py --parallel fans scenes (movie_2_3D.py:422-452)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    per_step = cores  # one frame per core per step
+    _prepare_cpu_frames(min(cores, 16))
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for _ in range(args.warmup):
+            pool.map(_oracle_stereo_frame, range(per_step), chunksize=1)
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            pool.map(_oracle_stereo_frame, [s * per_step + k for k in range(per_step)], chunksize=1)
+        elapsed = time.perf_counter() - t0
+    value = args.steps * per_step / elapsed
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "xfov": XFOV, "max_depth": MAX_DEPTH,
+                       "pupillary_distance_mm": IPD_MM, "master_xfov": MASTER_XFOV, "frames_per_step": per_step},
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": f"{per_step} frames per step ({args.steps} steps) of the same clip, one frame per core, NumPy float64 oracle port"},
+            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic_per_frame():
+    """DRAM bytes per frame of the fused kernel from the committed ncu capture (profiles/), if any."""
+    path = os.path.join(ROOT, "profiles", "stereo_rows_traffic.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh)
+    return None
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from metric_depth_video_toolbox_b200 import ops
+    from metric_depth_video_toolbox_b200.stereo import StereoParams, StereoRerenderer
+    from metric_depth_video_toolbox_b200.synth import SyntheticClip
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device: there is no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_frames = args.frames
+
+    # ---- the clip shard of this rank (frames [rank*n, (rank+1)*n) of the whole job) -----------------------
+    # `distinct` different synthetic frames are generated into a pinned host ring and tiled to n_frames on
+    # the device: same bytes moved and same work per pixel as n_frames distinct frames, bounded host memory.
+    distinct = max(1, min(args.distinct_frames, n_frames))
+    clip = SyntheticClip(WIDTH, HEIGHT, world * n_frames)
+    host_d = torch.empty((distinct, HEIGHT, WIDTH, 3), dtype=torch.uint8, pin_memory=True)
+    host_c = torch.empty((distinct, HEIGHT, WIDTH, 3), dtype=torch.uint8, pin_memory=True)
+    first = rank * n_frames
+    for k in range(distinct):
+        d, c = clip.frame(first + k)
+        host_d[k] = torch.from_numpy(d)
+        host_c[k] = torch.from_numpy(c)
+    reps = (n_frames + distinct - 1) // distinct
+    dev_d = host_d.to(dev).repeat(reps, 1, 1, 1)[:n_frames].contiguous()
+    dev_c = host_c.to(dev).repeat(reps, 1, 1, 1)[:n_frames].contiguous()
+
+    # ---- parameter block: built on rank 0, broadcast (the only collective of the path) --------------------
+    params = StereoParams(WIDTH, HEIGHT, xfov=XFOV, max_depth=MAX_DEPTH, pupillary_distance=IPD_MM, master_xfov=MASTER_XFOV,
+                          infill_mask=True)
+    rr = StereoRerenderer(params, dev)
+    consts = torch.from_numpy(rr.frame_constants(0, n_frames)).to(dev) if rank == 0 else torch.empty((1, 4), dtype=torch.float32, device=dev)
+    if world > 1:
+        dist.broadcast(consts, src=0)
+    out_sbs = torch.empty((n_frames, HEIGHT, 2 * WIDTH, 3), dtype=torch.uint8, device=dev)
+    out_mask = torch.empty((n_frames, HEIGHT, 2 * WIDTH), dtype=torch.uint8, device=dev)
+    flags = ops.FLAG_BG_COLLIDE
+
+    def step():
+        ops.stereo_rows(dev_d, dev_c, consts, params.bg_rgb, (0, 0, 0), flags, out_sbs, out_mask)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    sync_all()
+    # ---- device-resident throughput ----------------------------------------------------------------------
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with ClockSampler(local_rank) as clocks:
+        sync_all()
+        ev[0].record()
+        for s in range(args.steps):
+            step()
+            ev[s + 1].record()
+        sync_all()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    launch_ms = [ev[s].elapsed_time(ev[s + 1]) for s in range(args.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * n_frames * args.steps / (total_ms_max / 1e3)
+
+    # ---- end to end through the host API -------------------------------------------------------------------
+    # One e2e step = the same n_frames clip, streamed from the pinned host ring in `distinct`-frame segments
+    # (like a reader filling a ring buffer) through StereoRerenderer.render_host: H2D, kernel and D2H are all
+    # inside the timed region; bytes are counted from the tensors actually copied.
+    e2e = None
+    if not args.no_e2e:
+        host_sbs = torch.empty((distinct, HEIGHT, 2 * WIDTH, 3), dtype=torch.uint8, pin_memory=True)
+        host_mask = torch.empty((distinct, HEIGHT, 2 * WIDTH), dtype=torch.uint8, pin_memory=True)
+        segments = [(f0, min(distinct, n_frames - f0)) for f0 in range(0, n_frames, distinct)]
+
+        def e2e_step():
+            for f0, cnt in segments:
+                rr.render_host(host_d[:cnt], host_c[:cnt], host_sbs[:cnt], host_mask[:cnt], start_frame=f0)
+
+        e2e_step()  # warm-up: allocates the device staging buffers
+        sync_all()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        e1.record()
+        sync_all()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        t = torch.tensor([max(e0.elapsed_time(e1), wall_ms)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_value = world * n_frames * args.e2e_steps / (float(t.item()) / 1e3)
+        checksum = int(host_mask[::17].sum().item())  # the step's result is read on the host
+        per_frame_in = 2 * HEIGHT * WIDTH * 3
+        per_frame_out = HEIGHT * 2 * WIDTH * 4
+        e2e = {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(per_frame_in * n_frames),
+               "d2h_bytes_per_step": int(per_frame_out * n_frames), "steps": args.e2e_steps,
+               "api": "StereoRerenderer.render_host (pinned host ring, 2-stream chunked H2D/kernel/D2H)", "mask_checksum": checksum}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_kind = measured_peak()
+    mean_launch_ms = sum(launch_ms) / len(launch_ms)
+    algorithmic = BYTES_PER_PX * WIDTH * HEIGHT * n_frames
+    achieved = algorithmic / (mean_launch_ms / 1e3) / 1e9
+    traffic = ncu_traffic_per_frame()
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": (traffic["dram_bytes_per_frame"] * n_frames) if traffic else None,
+                "kernel": "mdvt::stereo_rows_w32_kernel<1,true>", "algorithmic_bytes_per_launch": algorithmic,
+                "launch_ms": mean_launch_ms, "peak_source": peak_kind,
+                "traffic_source": traffic.get("source") if traffic else None}
+    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "frames_per_gpu_per_step": n_frames,
+                       "distinct_frames_per_gpu": distinct, "xfov": XFOV, "max_depth": MAX_DEPTH, "pupillary_distance_mm": IPD_MM,
+                       "master_xfov": MASTER_XFOV, "sharding": f"frames, {world} rank(s), no data-path collective",
+                       "l2": f"inputs {(dev_d.numel() + dev_c.numel()) / 1e9:.2f} GB + outputs {(out_sbs.numel() + out_mask.numel()) / 1e9:.2f} GB per step >> 126 MB L2 (no flush needed)"},
+            "roofline": roofline, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks.summary()}
+    if not args.no_cpu and world == 1:
+        line["cpu_baseline"] = cpu_baseline(args.cpu_frames)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

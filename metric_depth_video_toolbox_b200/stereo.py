@@ -1,0 +1,189 @@
+"""Stereo re-render of a clip: the body of stereo_rerender.py's frame loop (:471-941) for whole batches
+of frames, on the GPU.
+
+`StereoRerenderer` is the public host API: it turns the script-level parameters (xfov / per-frame xfov
+list, max_depth, pupillary distance, master FOV, optional smoothed convergence list, optional per-frame
+camera poses) into per-frame constant blocks, picks the kernel path per clip
+
+  * row-local fused kernel (`ops.stereo_rows`)      -- no pose file, no convergence rotation
+  * generic path (`ops.project_splat` + `ops.resolve`) -- anything else
+
+and runs it either on device-resident tensors (`render_device`) or on host arrays through a chunked,
+double-buffered H2D -> kernel -> D2H pipeline (`render_host`).  There is no CPU implementation.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import geometry as geo
+from . import ops
+
+
+@dataclass
+class StereoParams:
+    """Mirrors the stereo_rerender.py CLI values that reach the per-pixel path (:279-312)."""
+    width: int
+    height: int
+    xfov: Optional[float] = None          # --xfov
+    yfov: Optional[float] = None          # --yfov
+    xfovs: Optional[Sequence[float]] = None  # --xfov_file (one value per frame; yfov then unused, :515-517)
+    max_depth: float = 100                # --max_depth
+    pupillary_distance: float = 63        # --pupillary_distance [mm]
+    master_xfov: float = 45.0             # --master_xfov
+    convergence_depths: Optional[Sequence[float]] = None  # already fill_nan + curve_fit'ed (:343-349)
+    transformations: Optional[Sequence] = None            # per-frame 4x4, already re-based (:369-373)
+    infill_mask: bool = True              # --infill_mask: green background, hole mask written
+    mask_rgb: bool = False                # mask as the reference's green/black u8x3 image instead of u8
+    near: float = geo.NEAR_PLANE
+
+    def __post_init__(self):
+        if self.xfov is None and self.yfov is None and self.xfovs is None:
+            raise ValueError("Error: Either --xfov_file, --xfov or --yfov must be provided.")  # stereo_rerender.py:319-320
+
+    @property
+    def bg_rgb(self):
+        return (0, 255, 0) if self.infill_mask else (0, 0, 0)  # stereo_rerender.py:554-556
+
+    def xfov_of(self, frame: int) -> float:
+        xf = self.xfovs[frame] if self.xfovs is not None else self.xfov
+        if xf is None:
+            # the reference dereferences xf / 2 with xf = None here (stereo_rerender.py:537): --yfov alone fails
+            raise TypeError("unsupported operand: --xfov or --xfov_file is required by the master-FOV scaling")
+        return float(xf)
+
+    def row_local(self) -> bool:
+        """True when every frame is a pure +-ipd/2 shift: v' == v, one fused kernel does it all."""
+        return self.transformations is None and self.convergence_depths is None
+
+
+class StereoRerenderer:
+    def __init__(self, params: StereoParams, device: Optional[torch.device] = None):
+        self.p = params
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._consts_cache = {}
+        self._zbufs = {}  # one 2-view z-buffer per CUDA stream (render_host runs two streams)
+
+    # ---- per-frame constants ---------------------------------------------------------------------
+    def frame_constants(self, start: int, count: int) -> np.ndarray:
+        """(count, 4) float32 rows of mdvt_stereo_frame for frames start .. start+count-1."""
+        p = self.p
+        if p.xfovs is None:
+            row = ops.stereo_frame_constants(p.xfov_of(0), p.width, p.max_depth, p.pupillary_distance, p.master_xfov, p.near)
+            return np.repeat(row[None], 1, axis=0)
+        return np.stack([ops.stereo_frame_constants(p.xfov_of(f), p.width, p.max_depth, p.pupillary_distance, p.master_xfov, p.near)
+                         for f in range(start, start + count)])
+
+    def _device_constants(self, start: int, count: int) -> torch.Tensor:
+        key = (start, count) if self.p.xfovs is not None else None
+        if key not in self._consts_cache:
+            if len(self._consts_cache) > 64:
+                self._consts_cache.clear()
+            self._consts_cache[key] = torch.from_numpy(self.frame_constants(start, count)).to(self.device)
+        return self._consts_cache[key]
+
+    def views_of(self, frame: int) -> List[ops.ViewSpec]:
+        """Both eye cameras of one frame for the generic path (stereo_rerender.py:525,537-541,615-619,704-725,831-836)."""
+        p = self.p
+        xf = p.xfov_of(frame)
+        K = geo.compute_camera_matrix(xf, None if p.xfovs is not None else p.yfov, p.width, p.height)
+        scale = geo.master_fov_depth_scale(p.master_xfov, xf)
+        ipd = p.pupillary_distance / 1000
+        theta = None
+        if p.convergence_depths is not None:
+            conv = float(p.convergence_depths[frame])
+            if conv != 0:  # "Convergence distance is zero, skipping convergence" (:711-713)
+                theta = geo.convergence_angle(conv * scale, ipd)
+        T = np.eye(4) if p.transformations is None else np.asarray(p.transformations[frame], dtype=np.float64)
+        return [ops.ViewSpec(geo.stereo_eye_pose(eye, ipd, theta) @ T, K[0, 0], K[1, 1], K[0, 2], K[1, 2]) for eye in ("left", "right")]
+
+    # ---- device-resident ------------------------------------------------------------------------------
+    def render_device(self, depth_rgb: torch.Tensor, colour: torch.Tensor, start_frame: int = 0,
+                      out_sbs: Optional[torch.Tensor] = None, out_mask: Optional[torch.Tensor] = None):
+        """depth_rgb / colour: (n, H, W, 3) u8 CUDA.  Returns (sbs (n, H, 2W, 3), mask (n, H, 2W[, 3]) or None)."""
+        p = self.p
+        n, h, w, _ = depth_rgb.shape
+        if (w, h) != (p.width, p.height):
+            raise ValueError(f"frames are {w}x{h}, parameters say {p.width}x{p.height}")
+        flags = (ops.FLAG_BG_COLLIDE if p.infill_mask else 0) | (ops.FLAG_MASK_RGB if p.mask_rgb else 0)
+        if p.row_local():
+            return ops.stereo_rows(depth_rgb, colour, self._device_constants(start_frame, n), p.bg_rgb, (0, 0, 0), flags,
+                                   out_sbs, out_mask, want_mask=p.infill_mask)
+        # generic path: per frame K1+K2 into a persistent 2-view z-buffer, K3 per eye straight into the SBS halves
+        if out_sbs is None:
+            out_sbs = torch.empty((n, h, 2 * w, 3), dtype=torch.uint8, device=depth_rgb.device)
+        if out_mask is None and p.infill_mask:
+            out_mask = torch.empty((n, h, 2 * w) + ((3,) if p.mask_rgb else ()), dtype=torch.uint8, device=depth_rgb.device)
+        zkey = torch.cuda.current_stream(depth_rgb.device).cuda_stream
+        zbuf = self._zbufs.get(zkey)
+        if zbuf is None or tuple(zbuf.shape) != (2, h, w) or zbuf.device != depth_rgb.device:
+            zbuf = self._zbufs[zkey] = ops.new_zbuf(2, w, h, depth_rgb.device)
+        scratch_mask = None
+        for k in range(n):
+            f = start_frame + k
+            xf = p.xfov_of(f)
+            K = geo.compute_camera_matrix(xf, None if p.xfovs is not None else p.yfov, w, h)
+            src = ops.make_source(w, h, K, p.max_depth, "D1", True, geo.master_fov_depth_scale(p.master_xfov, xf), False)
+            ops.project_splat(depth_rgb[k], src, self.views_of(f), w, h, zbuf, p.near)
+            for e in range(2):
+                if out_mask is not None:
+                    m = out_mask[k, :, e * w:(e + 1) * w]
+                else:
+                    if scratch_mask is None:
+                        scratch_mask = torch.empty((h, w), dtype=torch.uint8, device=depth_rgb.device)
+                    m = scratch_mask
+                ops.resolve(zbuf[e], colour[k], p.bg_rgb, (0, 0, 0), flags | ops.FLAG_RESET_ZBUF,
+                            out_rgb=out_sbs[k, :, e * w:(e + 1) * w], out_mask=m)
+        return out_sbs, out_mask
+
+    # ---- host arrays, pipelined -----------------------------------------------------------------------
+    def render_host(self, depth_rgb, colour, out_sbs=None, out_mask=None, start_frame: int = 0, chunk_frames: int = 8):
+        """depth_rgb / colour: (n, H, W, 3) u8 host arrays (NumPy or CPU tensors; pinned memory makes the
+        copies asynchronous).  Frames stream through `chunk_frames`-sized device staging buffers on two
+        CUDA streams so H2D, the kernels and D2H overlap.  Returns host tensors (sbs, mask)."""
+        p = self.p
+        d_host = torch.as_tensor(depth_rgb)
+        c_host = torch.as_tensor(colour)
+        n, h, w, _ = d_host.shape
+        if out_sbs is None:
+            out_sbs = torch.empty((n, h, 2 * w, 3), dtype=torch.uint8, pin_memory=True)
+        if out_mask is None and p.infill_mask:
+            out_mask = torch.empty((n, h, 2 * w) + ((3,) if p.mask_rgb else ()), dtype=torch.uint8, pin_memory=True)
+        out_sbs_t, out_mask_t = torch.as_tensor(out_sbs), (None if out_mask is None else torch.as_tensor(out_mask))
+        chunk = max(1, min(chunk_frames, n))
+        n_slots = 2
+        slots = self._host_pipeline_slots(n_slots, chunk, h, w)
+        caller = torch.cuda.current_stream(self.device)
+        for s in slots:
+            s["stream"].wait_stream(caller)
+        for i, f0 in enumerate(range(0, n, chunk)):
+            s = slots[i % n_slots]
+            cnt = min(chunk, n - f0)
+            with torch.cuda.stream(s["stream"]):
+                s["d"][:cnt].copy_(d_host[f0:f0 + cnt], non_blocking=True)
+                s["c"][:cnt].copy_(c_host[f0:f0 + cnt], non_blocking=True)
+                self.render_device(s["d"][:cnt], s["c"][:cnt], start_frame + f0, s["sbs"][:cnt],
+                                   None if s["mask"] is None else s["mask"][:cnt])
+                out_sbs_t[f0:f0 + cnt].copy_(s["sbs"][:cnt], non_blocking=True)
+                if out_mask_t is not None:
+                    out_mask_t[f0:f0 + cnt].copy_(s["mask"][:cnt], non_blocking=True)
+        for s in slots:
+            caller.wait_stream(s["stream"])
+        return out_sbs, out_mask
+
+    def _host_pipeline_slots(self, n_slots, chunk, h, w):
+        key = (n_slots, chunk, h, w, self.p.mask_rgb, self.p.infill_mask)
+        if getattr(self, "_slots_key", None) != key:
+            dev = self.device
+            mask_shape = (chunk, h, 2 * w) + ((3,) if self.p.mask_rgb else ())
+            self._slots = [dict(stream=torch.cuda.Stream(device=dev),
+                                d=torch.empty((chunk, h, w, 3), dtype=torch.uint8, device=dev),
+                                c=torch.empty((chunk, h, w, 3), dtype=torch.uint8, device=dev),
+                                sbs=torch.empty((chunk, h, 2 * w, 3), dtype=torch.uint8, device=dev),
+                                mask=torch.empty(mask_shape, dtype=torch.uint8, device=dev) if self.p.infill_mask else None)
+                           for _ in range(n_slots)]
+            self._slots_key = key
+        return self._slots
