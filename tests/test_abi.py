@@ -55,8 +55,8 @@ def test_sass_contains_tma_and_atomics():
         assert mnemonic in sass.stdout, mnemonic
     assert "sm_100a" in sass.stdout
     # --fmad=false: the parity contract forbids contraction in the geometry kernels
-    body = sass.stdout.split("stereo_rows_kernel")[1]
-    assert "FMUL" in body
+    body = sass.stdout.split("stereo_rows_w32_kernel")[1]
+    assert "FMUL" in body and "ATOMS.MIN" in body and "UBLKCP" in body
 
 
 def test_argument_validation_without_a_device():
