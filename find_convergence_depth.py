@@ -1,0 +1,5 @@
+"""Launcher with the reference script's name and command line (see metric_depth_video_toolbox_b200/cli/find_convergence_depth.py)."""
+from metric_depth_video_toolbox_b200.cli.find_convergence_depth import main
+
+if __name__ == "__main__":
+    raise SystemExit(main())

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MDVT_ABI_VERSION 1
+#define MDVT_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define MDVT_API __attribute__((visibility("default")))
@@ -51,7 +51,10 @@ typedef enum mdvt_status {
 typedef enum mdvt_decoder {
     MDVT_DECODE_D1 = 0, /* depth_frames_helper.py:13-24,63-75,99-103  hi=R lo=B, code * fl32(max/255^4) */
     MDVT_DECODE_D2 = 1, /* convert_metric_depth_video_to_other_format.py:646-652  hi=(R+G)>>1, code / fl32(255^4/max) */
-    MDVT_DECODE_D3 = 2  /* find_convergence_depth.py:56-60  hi=R lo=B, code / fl32(255^4/max) */
+    MDVT_DECODE_D3 = 2, /* find_convergence_depth.py:56-60  hi=R lo=B, code / fl32(255^4/max) */
+    MDVT_SOURCE_F32 = 3 /* not a decoder: the source buffer is a plane of float32 depths the caller already holds
+                           (the `depth_map` argument of depth_map_tools.get_mesh_from_depth_map /
+                           create_point_cloud_from_depth, depth_map_tools.py:1104-1133); dec_const / bit16 unused */
 } mdvt_decoder;
 
 /* Empty z-buffer slot: all ones.  A filled slot is (float_bits(z') << 32) | source_pixel_index. */
@@ -111,17 +114,52 @@ MDVT_API int mdvt_decode_depth(const uint8_t *rgb, int64_t n_pixels, int decoder
 MDVT_API int mdvt_encode_depth(const float *depth, int64_t n_pixels, double max_depth, int bit16, int bgr_order,
                       uint32_t *out_codes, uint8_t *out_pix, void *stream);
 
+/* decode_uint32_as_depth (depth_frames_helper.py:13-24) on a plane of codes the caller holds: D1 multiplies by
+ * dec_const, D2/D3 divide by it. */
+MDVT_API int mdvt_codes_to_depth(const uint32_t *codes, int64_t n_pixels, int decoder, float dec_const, float *out_depth,
+                        void *stream);
+/* encode_data_as_BGR (depth_frames_helper.py:48-61): bytes of a u32 plane -> u8x3 (16-bit: R=G=byte3, B=byte2;
+ * 24-bit: R=byte2, G=byte1, B=byte0); bgr_order as in mdvt_encode_depth. */
+MDVT_API int mdvt_codes_to_pixels(const uint32_t *codes, int64_t n_pixels, int bit16, int bgr_order, uint8_t *out_pix,
+                         void *stream);
+
+/* ---- other depth export formats ---------------------------------------------------------------- */
+/* `depth_src`: n*3 u8 wire-format pixels, or n float32 depths with decoder == MDVT_SOURCE_F32.
+ * Grey depth video frames (convert_metric_depth_video_to_other_format.py:752-760):
+ * out = astype(rint(depth * factor)) with factor = fl32(255^2 / max_depth) -> u16 x1 (--bit16) or
+ * fl32(255 / max_depth) -> u8 replicated to 3 channels (--bit8).  out_bits 8|16, channels 1|3 (16-bit: 1). */
+MDVT_API int mdvt_depth_to_grey(const void *depth_src, int64_t n_pixels, int decoder, int bit16, float dec_const,
+                       float factor, int out_bits, int channels, void *out, void *stream);
+/* Touchly reverse-depth plane (stereo_rerender.py:548-552; rendered-depth variant :687-690,:826-829 with
+ * zero_is_far = 1): 255 - rint(max(0, min(depth*depth_scale, tmax) - tmin) * gain), gain = fl32(255/(tmax-tmin))
+ * evaluated by the caller in double like the script does; u8 x3, row r at out_rgb + r*out_pitch so it can be
+ * written into its slot of the stacked output frame. */
+MDVT_API int mdvt_touchly_depth(const void *depth_src, int width, int height, int decoder, int bit16, float dec_const,
+                       float depth_scale, float touchly_min, float touchly_max, float gain, int zero_is_far,
+                       uint8_t *out_rgb, int64_t out_pitch, void *stream);
+
 /* ---- decode + unproject (+ pose) -> point cloud --------------------------------------------- */
-/* decode -> depth_scale -> depth_map_tools.create_point_cloud_from_depth (depth_map_tools.py:1112-1133)
+/* `depth_src` below is the u8x3 wire-format frame (n*3 bytes), or n float32 depths when
+ * src->decoder == MDVT_SOURCE_F32.
+ * decode -> depth_scale -> depth_map_tools.create_point_cloud_from_depth (depth_map_tools.py:1112-1133)
  * -> optional 3x4 pose (transform_points, depth_map_tools.py:977-1004).  pose_host: 12 floats on
  * the HOST (row-major 3x4) or NULL.  out_xyz: n*3 f32. */
-MDVT_API int mdvt_unproject_f32(const uint8_t *depth_rgb, const mdvt_source *src_host, const float *pose_host,
+MDVT_API int mdvt_unproject_f32(const void *depth_src, const mdvt_source *src_host, const float *pose_host,
                        float *out_xyz, void *stream);
 /* Same in float64 with the reference's own operation order (K and pose given as doubles): xyz is
  * bit-identical to NumPy for the unprojection.  K_host: fx, fy, cx, cy; pose_host: 12 doubles or NULL.
  * out_xyz: n*3 f64 -- the .ply export path (convert_metric_depth_video_to_other_format.py:692-749). */
-MDVT_API int mdvt_unproject_f64(const uint8_t *depth_rgb, const mdvt_source *src_host, const double *K_host,
+MDVT_API int mdvt_unproject_f64(const void *depth_src, const mdvt_source *src_host, const double *K_host,
                        const double *pose_host, double *out_xyz, void *stream);
+
+/* depth_map_tools.transform_points (depth_map_tools.py:977-1004): out = [xyz 1] @ T.T without the w divide.
+ * pose_host: upper 3x4 of T, 12 doubles row-major, on the HOST.  In place (out_xyz == xyz) is allowed. */
+MDVT_API int mdvt_transform_points_f64(const double *xyz, int64_t n_points, const double *pose_host, double *out_xyz,
+                              void *stream);
+/* depth_map_tools.project_3d_points_to_2d (depth_map_tools.py:1057-1060; cv2.projectPoints with zero
+ * rvec/tvec/distortion): out_uv = (fx X/Z + cx, fy Y/Z + cy), n*2 f64.  K_host: fx, fy, cx, cy. */
+MDVT_API int mdvt_project_points_f64(const double *xyz, int64_t n_points, const double *K_host, double *out_uv,
+                            void *stream);
 
 /* ---- generic novel-view path: fused decode/unproject/pose/project + z-buffered splat, then resolve */
 MDVT_API int mdvt_zbuf_clear(uint64_t *zbuf, int64_t n_slots, void *stream);
@@ -131,10 +169,17 @@ MDVT_API int mdvt_zbuf_clear(uint64_t *zbuf, int64_t n_slots, void *stream);
  * checked against out_w x out_h and merged into zbuf[view] with one 64-bit atomicMin
  * (nearest z' wins, ties -> lowest source index; stereo_rerender.py:746-755,814 and the GL depth
  * test of depth_map_tools.py:1563-1572).  zbuf: n_views * out_w*out_h u64, pre-cleared.
+ * The payload written is id_offset + source pixel index, so several objects can share one z-buffer and one
+ * concatenated colour table (render() takes a list of objects, depth_map_tools.py:1422).
  * out_uvz (optional, n_views * n_pixels * 3 f32) receives (u', v', z') per source pixel for parity checks. */
-MDVT_API int mdvt_project_splat(const uint8_t *depth_rgb, const mdvt_source *src_host, const mdvt_view *views_host,
-                       int n_views, float near_plane, int out_w, int out_h, uint64_t *zbuf, float *out_uvz,
-                       void *stream);
+MDVT_API int mdvt_project_splat(const void *depth_src, const mdvt_source *src_host, const mdvt_view *views_host,
+                       int n_views, float near_plane, int out_w, int out_h, uint32_t id_offset, uint64_t *zbuf,
+                       float *out_uvz, void *stream);
+
+/* Same visibility rule for explicit points (n_points x 3 float32, in the space the views' M maps from): the
+ * reference's point painter (stereo_rerender.py:746-755,814) and render() of point clouds. */
+MDVT_API int mdvt_splat_points(const float *xyz, int64_t n_points, const mdvt_view *views_host, int n_views,
+                      float near_plane, int out_w, int out_h, uint32_t id_offset, uint64_t *zbuf, void *stream);
 
 /* K3.  zbuf (one view, out_w*out_h) + source colours -> image / hole mask / depth plane.
  * out_rgb: row r starts at out_rgb + r*rgb_pitch (bytes), so a view can be written straight into its
@@ -144,6 +189,21 @@ MDVT_API int mdvt_project_splat(const uint8_t *depth_rgb, const mdvt_source *src
 MDVT_API int mdvt_resolve(uint64_t *zbuf, const uint8_t *colour_rgb, int out_w, int out_h, uint32_t bg_rgb,
                  uint32_t fill_rgb, uint32_t flags, uint8_t *out_rgb, int64_t rgb_pitch, uint8_t *out_mask,
                  int64_t mask_pitch, float *out_depth, int32_t *out_ids, void *stream);
+
+/* ---- per-frame reductions (fixed summation order: reproducible) -------------------------------- */
+/* Result buffers hold 4 doubles of result followed by MDVT_REDUCE_SCRATCH_DOUBLES doubles of scratch. */
+#define MDVT_REDUCE_SCRATCH_DOUBLES 4096
+
+/* Sum of the unprojected (+posed) vertices in float64 with the reference's evaluation order
+ * (create_point_cloud_from_depth, then Open3D get_center() = mean of vertices, 3d_view_depthfile.py:231):
+ * out_sums = {sum X, sum Y, sum Z, n}.  K_host: fx, fy, cx, cy doubles; pose_host: 12 doubles or NULL. */
+MDVT_API int mdvt_centroid(const void *depth_src, const mdvt_source *src_host, const double *K_host,
+                  const double *pose_host, double *out_sums, void *stream);
+
+/* find_convergence_depth.py:56-80: sum / count (/ sum of squares) of the decoded depth over the pixels whose
+ * mask byte is > mask_gt (mask NULL: all pixels).  out_sums = {sum, count, sum of squares, 0}. */
+MDVT_API int mdvt_depth_sum(const void *depth_src, int64_t n_pixels, int decoder, int bit16, float dec_const,
+                   const uint8_t *mask, int mask_gt, double *out_sums, void *stream);
 
 /* ---- row-local stereo fast path: ONE fused kernel, frames batched ---------------------------- */
 /* Whole stereo_rerender.py frame loop body (:512-541 decode+scale, :583 unproject, :723-738,:831-852 eye

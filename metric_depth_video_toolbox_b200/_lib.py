@@ -13,11 +13,12 @@ import threading
 from . import build as _build
 
 OK = 0
-DECODE_D1, DECODE_D2, DECODE_D3 = 0, 1, 2
-DECODERS = {"D1": DECODE_D1, "D2": DECODE_D2, "D3": DECODE_D3}
+DECODE_D1, DECODE_D2, DECODE_D3, SOURCE_F32 = 0, 1, 2, 3
+DECODERS = {"D1": DECODE_D1, "D2": DECODE_D2, "D3": DECODE_D3, "F32": SOURCE_F32}
+REDUCE_SCRATCH_DOUBLES = 4096
 FLAG_BG_COLLIDE, FLAG_RESET_ZBUF, FLAG_MASK_RGB, FLAG_ANYWIDTH = 0x1, 0x2, 0x4, 0x8
 ZBUF_EMPTY = 0xFFFFFFFFFFFFFFFF
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class MdvtError(RuntimeError):
@@ -57,9 +58,20 @@ _PROTOTYPES = {
     "mdvt_encode_depth": (C.c_int, [_f32p, C.c_int64, C.c_double, C.c_int, C.c_int, _u32p, _u8p, _stream]),
     "mdvt_unproject_f32": (C.c_int, [_u8p, C.POINTER(Source), C.POINTER(C.c_float), _f32p, _stream]),
     "mdvt_unproject_f64": (C.c_int, [_u8p, C.POINTER(Source), C.POINTER(C.c_double), C.POINTER(C.c_double), _f64p, _stream]),
+    "mdvt_depth_to_grey": (C.c_int, [_u8p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, _stream]),
+    "mdvt_touchly_depth": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                     C.c_int, _u8p, C.c_int64, _stream]),
+    "mdvt_transform_points_f64": (C.c_int, [_f64p, C.c_int64, C.POINTER(C.c_double), _f64p, _stream]),
+    "mdvt_project_points_f64": (C.c_int, [_f64p, C.c_int64, C.POINTER(C.c_double), _f64p, _stream]),
     "mdvt_zbuf_clear": (C.c_int, [_u64p, C.c_int64, _stream]),
+    "mdvt_codes_to_depth": (C.c_int, [_u32p, C.c_int64, C.c_int, C.c_float, _f32p, _stream]),
+    "mdvt_codes_to_pixels": (C.c_int, [_u32p, C.c_int64, C.c_int, C.c_int, _u8p, _stream]),
     "mdvt_project_splat": (C.c_int, [_u8p, C.POINTER(Source), C.POINTER(View), C.c_int, C.c_float, C.c_int, C.c_int,
-                                     _u64p, _f32p, _stream]),
+                                     C.c_uint32, _u64p, _f32p, _stream]),
+    "mdvt_splat_points": (C.c_int, [_f32p, C.c_int64, C.POINTER(View), C.c_int, C.c_float, C.c_int, C.c_int, C.c_uint32,
+                                    _u64p, _stream]),
+    "mdvt_centroid": (C.c_int, [_u8p, C.POINTER(Source), C.POINTER(C.c_double), C.POINTER(C.c_double), _f64p, _stream]),
+    "mdvt_depth_sum": (C.c_int, [_u8p, C.c_int64, C.c_int, C.c_int, C.c_float, _u8p, C.c_int, _f64p, _stream]),
     "mdvt_resolve": (C.c_int, [_u64p, _u8p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, _u8p, C.c_int64,
                                _u8p, C.c_int64, _f32p, _i32p, _stream]),
     "mdvt_stereo_rows": (C.c_int, [_u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32,

@@ -1,0 +1,202 @@
+"""stereo_rerender.py front end: same flags, defaults, validation messages and output file names as the
+reference script (stereo_rerender.py:270-968); the frame loop body runs on the GPU in chunks through
+`StereoRerenderer` while OpenCV decodes / encodes on background threads.
+
+    python stereo_rerender.py --depth_video D.mkv --color_video C.mkv --xfov 60 [--infill_mask ...]
+    torchrun --nproc-per-node 8 --master-addr 127.0.0.1 stereo_rerender.py ...    # frames sharded over 8 GPUs
+
+Deviations from the reference, all deliberate:
+  * rendering is a point splat (the reference's own --render_as_pointcloud visibility rule), so
+    --render_as_pointcloud / --remove_edges / --dont_remove_edges change nothing;
+  * --max_frames N renders exactly N frames (the reference renders N+1 and then fails its own frame-count
+    check, stereo_rerender.py:468,943,952);
+  * under torchrun each rank renders a contiguous frame range into a segment file and rank 0 joins them.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from .. import depth_frames_helper, sharding, video_io
+from ..geometry import convergence_angle, curve_fit, fill_nan_with_closest, rebase_transformations  # noqa: F401
+from ..stereo import StereoParams, StereoRerenderer
+
+UNSUPPORTED = {
+    "mask_video": "--mask_video (background accumulation) is sequential host state outside the per-frame GPU path",
+    "save_background": "--save_background belongs to the --mask_video background accumulation",
+    "load_background": "--load_background belongs to the --mask_video background accumulation",
+}
+
+
+def build_parser() -> argparse.ArgumentParser:
+    p = argparse.ArgumentParser(description="Convert an RGB-encoded depth video and optional color video into a stereoscopic 3D "
+                                            "side-by-side output for VR/3D TVs.")
+    add = p.add_argument
+    add("--master_xfov", type=float, default=45.0, help="Intended master FOV: how large the screen is from the viewer's point of view.")
+    add("--depth_video", type=str, required=True, help="Path to input depth-encoded video file")
+    add("--color_video", type=str, help="Path to input color video file")
+    add("--xfov", type=float, help="Horizontal FOV in degrees")
+    add("--yfov", type=float, help="Vertical FOV in degrees, calculated from aspect ratio and xfov if not given")
+    add("--xfov_file", type=str, help="JSON file specifying xfov per frame")
+    add("--max_depth", default=100, type=int, help="Maximum depth encoded in video")
+    add("--transformation_file", type=str, help="file with scene transformations from the aligner")
+    add("--transformation_lock_frame", default=0, type=int, help="the frame that the transformation will use as a base")
+    add("--pupillary_distance", default=63, type=int, help="pupillary distance in mm")
+    add("--max_frames", default=-1, type=int, help="Stop after processing this many frames")
+    add("--touchly0", action="store_true", help="Render in touchly0 format (stereo 3D)")
+    add("--vr180", action="store_true", help="Render in VR180 180 degree side-by-side")
+    add("--render_as_pointcloud", action="store_true", help="Render output as point cloud (always the case here)")
+    add("--convergence_file", type=str, help="json file with convergence data for each frame.")
+    add("--dont_place_points_in_edges", action="store_true", help="Skip adding edge points for infill")
+    add("--dont_remove_edges", action="store_true", help="Skip removing edges")
+    add("--do_basic_infill", action="store_true", help="Use basic in-house infill algorithm.")
+    add("--touchly1", action="store_true", help="Render in touchly1 format (mono+depth)")
+    add("--touchly_max_depth", default=5, type=float, help="the max depth that touchly is clipped to.")
+    add("--touchly_min_depth", default=0, type=float, help="the min depth that touchly is clipped to.")
+    add("--compressed", action="store_true", help="Compress output video (lower quality)")
+    add("--infill_mask", action="store_true", help="Save infill masks alongside output")
+    add("--green_and_black_infill_mask", action="store_true", help="Dont generate normals for the infill mask.")
+    add("--remove_edges", action="store_true", help="Remove mesh edges not visible in input frames")
+    add("--mask_video", type=str, help="mask video used to build a background-only model")
+    add("--save_background", action="store_true", help="Save the compound background as a file.")
+    add("--load_background", help="Load the compound background from a file.")
+    add("--create_sbs_depth_video", action="store_true", help="Save a depth version of the final sbs video")
+    # additions (not in the reference)
+    add("--chunk_frames", default=8, type=int, help="frames per GPU batch")
+    return p
+
+
+def _require_file(path: Optional[str], what: str, exc=FileNotFoundError):
+    if path and not os.path.isfile(path):
+        raise exc(f"{what} not found: {path}")
+
+
+def load_clip_parameters(args, frame_width: int, frame_height: int, n_frames: int) -> StereoParams:
+    """Everything of stereo_rerender.py:343-373,402-404 that spans the whole clip (rank 0 only under torchrun)."""
+    convergence = None
+    if args.convergence_file:
+        _require_file(args.convergence_file, "Convergence file")
+        with open(args.convergence_file) as fh:
+            convergence = curve_fit(fill_nan_with_closest(json.load(fh)))
+    xfovs = None
+    if args.xfov_file:
+        _require_file(args.xfov_file, "XFOV file")
+        with open(args.xfov_file) as fh:
+            xfovs = json.load(fh)
+        if not isinstance(xfovs, list) or not all(isinstance(x, (int, float)) for x in xfovs):
+            raise ValueError("XFOV file must contain a list of numbers.")
+        if len(xfovs) != n_frames:
+            raise ValueError(f"XFOV file must have the same number of frames as the input video ({n_frames} vs xfov={len(xfovs)}).")
+    transformations = None
+    if args.transformation_file is not None:
+        if not os.path.isfile(args.transformation_file):
+            raise Exception("input transformation_file does not exist")
+        with open(args.transformation_file) as fh:
+            transformations = rebase_transformations(json.load(fh), args.transformation_lock_frame)
+    for name, seq in (("convergence", convergence), ("transformation", transformations)):
+        if seq is not None and len(seq) < n_frames:
+            raise ValueError(f"{name} file has {len(seq)} entries, the clip has {n_frames} frames")
+    return StereoParams(frame_width, frame_height, xfov=args.xfov, yfov=args.yfov, xfovs=xfovs, max_depth=args.max_depth,
+                        pupillary_distance=args.pupillary_distance, master_xfov=args.master_xfov,
+                        convergence_depths=None if convergence is None else list(convergence)[:n_frames],
+                        transformations=None if transformations is None else transformations[:n_frames],
+                        infill_mask=bool(args.infill_mask), mask_rgb=True)
+
+
+def output_names(args):
+    """stereo_rerender.py:409-435."""
+    kind = "Touchly1" if args.touchly1 else ("Touchly0" if args.touchly0 else "stereo")
+    ext, fourcc = ("mp4", "avc1") if args.compressed else ("mkv", "FFV1")
+    return f"{args.depth_video}_{kind}.{ext}", f"{args.depth_video}_tmp_{kind}.{ext}", fourcc
+
+
+def main(argv: Optional[List[str]] = None) -> int:
+    args = build_parser().parse_args(argv)
+    if args.xfov is None and args.yfov is None and args.xfov_file is None:
+        raise ValueError("Error: Either --xfov_file, --xfov or --yfov must be provided.")
+    if args.green_and_black_infill_mask and args.do_basic_infill:
+        raise ValueError("Error: --green_and_black_infill_mask and --do_basic_infill are not compatible with eachother.")
+    for flag, why in UNSUPPORTED.items():
+        if getattr(args, flag):
+            raise NotImplementedError(why)
+    _require_file(args.depth_video, "Depth video")
+    _require_file(args.color_video, "Color video")
+
+    rank, world_size, local_rank = sharding.init_from_env()
+    device = torch.device("cuda", local_rank)
+
+    frame_width, frame_height, frame_rate, total = video_io.video_info(args.depth_video)
+    if args.color_video:
+        cw, ch, cfps, _ = video_io.video_info(args.color_video)
+        if (frame_width, frame_height) != (cw, ch):
+            raise ValueError(f"Depth video and Color video must have the same dimensions (Depth: {frame_width}x{frame_height} vs Color {cw}x{ch}).")
+        if round(frame_rate, 2) != round(cfps, 2):
+            raise ValueError(f"Color video and depth video must have the same frame rate (Depth={frame_rate} vs Color={round(cfps, 2)}).")
+    total_frames = total if args.max_frames < 0 else min(total, args.max_frames)
+
+    # whole-clip parameters: built once on rank 0, broadcast (the only inter-GPU traffic of the job)
+    params = load_clip_parameters(args, frame_width, frame_height, total) if rank == 0 else None
+    params, _ = sharding.broadcast_params(params, total)
+    start, stop = sharding.frame_range(total_frames, rank, world_size)
+
+    from . import stereo_modes
+
+    job = stereo_modes.StereoJob(args, params, device, frame_width, frame_height)
+    output_file, output_tmp_file, fourcc = output_names(args)
+    seg = (lambda p: p) if world_size == 1 else (lambda p: f"{p}.rank{rank:02d}.mkv")
+    seg_fourcc = fourcc if world_size == 1 else "FFV1"
+    writers = {"main": video_io.ChunkWriter(seg(output_tmp_file), seg_fourcc, frame_rate, job.out_size)}
+    if args.infill_mask:
+        writers["mask"] = video_io.ChunkWriter(seg(output_tmp_file + "_infillmask.mkv"), "FFV1", frame_rate, job.out_size)
+    if args.create_sbs_depth_video and job.has_depth_output:
+        writers["depth"] = video_io.ChunkWriter(seg(output_tmp_file + "_depth.mkv"), "FFV1", frame_rate, job.out_size)
+
+    reader = video_io.ChunkReader([args.depth_video, args.color_video], start, stop, chunk=args.chunk_frames)
+    t0 = time.time()
+    done = 0
+    for n, (depth_rgb, colour) in reader:
+        outputs = job.render_chunk(depth_rgb, depth_rgb if colour is None else colour, start + done)
+        torch.cuda.synchronize(device)  # results are on the host, the reader may recycle its buffers
+        for key, w in writers.items():
+            w.write(outputs[key], rgb=(key != "depth"))
+        done += n
+        if rank == 0:
+            pct = 100.0 * done / max(1, stop - start)
+            print(f"[{pct:5.1f}%] Frame #{done:4d}/{stop - start}  {done / max(1e-9, time.time() - t0):7.1f} frames/s", end="\r", file=sys.stderr)
+    for w in writers.values():
+        w.close()
+    total_done = sharding.gather_counts(done)
+
+    if world_size > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        if rank == 0:
+            for suffix, cc in (("", fourcc), ("_infillmask.mkv", "FFV1"), ("_depth.mkv", "FFV1")):
+                parts = [f"{output_tmp_file}{suffix}.rank{r:02d}.mkv" for r in range(world_size)]
+                if all(os.path.isfile(p) for p in parts):
+                    stereo_modes.join_segments(parts, output_tmp_file + suffix, cc, frame_rate, job.out_size)
+        dist.barrier()
+    if rank == 0:
+        depth_frames_helper.verify_and_move(output_tmp_file, total_frames, output_file)
+        if args.infill_mask:
+            depth_frames_helper.verify_and_move(output_tmp_file + "_infillmask.mkv", total_frames, output_file + "_infillmask.mkv")
+        if "depth" in writers:
+            depth_frames_helper.verify_and_move(output_tmp_file + "_depth.mkv", total_frames, output_file + "_depth.mkv")
+        print(f"\nProcessing complete ({total_done} frames, {total_done / max(1e-9, time.time() - t0):.1f} frames/s). Output saved to: {output_file}")
+    if world_size > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -33,11 +33,30 @@ int sm_count() {
     return cached;
 }
 
+int check_decoder(int decoder, int bit16, bool allow_f32) {
+    if (decoder == MDVT_SOURCE_F32 && allow_f32) return MDVT_OK;
+    if (decoder < MDVT_DECODE_D1 || decoder > MDVT_DECODE_D3) {
+        set_error("unknown decoder %d", decoder);
+        return MDVT_ERR_INVALID_ARGUMENT;
+    }
+    if (!bit16 && decoder != MDVT_DECODE_D1) {
+        set_error("the 24-bit wire format exists for decoder D1 only");
+        return MDVT_ERR_UNSUPPORTED;
+    }
+    return MDVT_OK;
+}
+
+int check_source(const mdvt_source *s) {
+    MDVT_REQUIRE(s != nullptr, "mdvt_source is NULL");
+    MDVT_REQUIRE(s->width > 0 && s->height > 0, "bad frame size %dx%d", s->width, s->height);
+    return check_decoder(s->decoder, s->bit16, true);
+}
+
 }  // namespace mdvt
 
 extern "C" int mdvt_abi_version(void) { return MDVT_ABI_VERSION; }
 
-extern "C" const char *mdvt_version(void) { return "mdvt_b200 0.1 (sm_100a)"; }
+extern "C" const char *mdvt_version(void) { return "mdvt_b200 0.2 (sm_100a)"; }
 
 extern "C" const char *mdvt_last_error(void) { return mdvt::g_error; }
 

@@ -104,12 +104,10 @@ struct Pose12d {
 
 template <int DECODER, bool BIT16>
 __global__ void __launch_bounds__(kThreads)
-    unproject_f32_kernel(const uint8_t *__restrict__ rgb, int width, int64_t n, float dec_const, float depth_scale, SourceCam cam,
+    unproject_f32_kernel(const void *__restrict__ rgb, int width, int64_t n, float dec_const, float depth_scale, SourceCam cam,
                          Pose12f pose, float *__restrict__ out_xyz) {
     for (int64_t p = blockIdx.x * (int64_t)kThreads + threadIdx.x; p < n; p += (int64_t)gridDim.x * kThreads) {
-        uint32_t r, g, b;
-        load_px1(rgb, p, r, g, b);
-        const float z = __fmul_rn(depth_of<DECODER>(code_of<DECODER, BIT16>(r, g, b), dec_const), depth_scale);
+        const float z = __fmul_rn(source_depth<DECODER, BIT16>(rgb, p, dec_const), depth_scale);
         const int row = (int)(p / width), col = (int)(p - (int64_t)row * width);
         float X, Y, Z = z;
         unproject_px(cam, col, row, z, X, Y);
@@ -127,13 +125,11 @@ __global__ void __launch_bounds__(kThreads)
 // everything after the subtraction is float64 (NumPy >= 2 promotion).
 template <int DECODER, bool BIT16>
 __global__ void __launch_bounds__(kThreads)
-    unproject_f64_kernel(const uint8_t *__restrict__ rgb, int width, int64_t n, float dec_const, float depth_scale, float sx,
+    unproject_f64_kernel(const void *__restrict__ rgb, int width, int64_t n, float dec_const, float depth_scale, float sx,
                          float sy, int stretched, double fx, double fy, double cx, double cy, Pose12d pose,
                          double *__restrict__ out_xyz) {
     for (int64_t p = blockIdx.x * (int64_t)kThreads + threadIdx.x; p < n; p += (int64_t)gridDim.x * kThreads) {
-        uint32_t r, g, b;
-        load_px1(rgb, p, r, g, b);
-        const float zf = __fmul_rn(depth_of<DECODER>(code_of<DECODER, BIT16>(r, g, b), dec_const), depth_scale);
+        const float zf = __fmul_rn(source_depth<DECODER, BIT16>(rgb, p, dec_const), depth_scale);
         const int row = (int)(p / width), col = (int)(p - (int64_t)row * width);
         double xg = (double)col, yg = (double)row;
         if (stretched) {
@@ -157,37 +153,66 @@ __global__ void __launch_bounds__(kThreads)
     }
 }
 
+// depth_map_tools.transform_points (:977-1004): [x y z 1] @ T.T, w dropped without a divide.  NumPy's matmul
+// accumulates left to right over the 4 terms of each output; reproduced with separately rounded operations.
+__global__ void __launch_bounds__(kThreads) transform_points_f64_kernel(const double *__restrict__ xyz, int64_t n, Pose12d pose,
+                                                                        double *__restrict__ out) {
+    const double *m = pose.m;
+    for (int64_t p = blockIdx.x * (int64_t)kThreads + threadIdx.x; p < n; p += (int64_t)gridDim.x * kThreads) {
+        const double X = xyz[p * 3], Y = xyz[p * 3 + 1], Z = xyz[p * 3 + 2];
+        out[p * 3] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(X, m[0]), __dmul_rn(Y, m[1])), __dmul_rn(Z, m[2])), m[3]);
+        out[p * 3 + 1] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(X, m[4]), __dmul_rn(Y, m[5])), __dmul_rn(Z, m[6])), m[7]);
+        out[p * 3 + 2] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(X, m[8]), __dmul_rn(Y, m[9])), __dmul_rn(Z, m[10])), m[11]);
+    }
+}
+
+// depth_map_tools.project_3d_points_to_2d (:1057-1060) without distortion: u = fx X/Z + cx, v = fy Y/Z + cy in
+// float64 (cv2.projectPoints with zero rvec/tvec/dist; its Z == 0 -> 1/z := 1 rule is kept).
+__global__ void __launch_bounds__(kThreads) project_points_f64_kernel(const double *__restrict__ xyz, int64_t n, double fx, double fy,
+                                                                      double cx, double cy, double *__restrict__ out_uv) {
+    for (int64_t p = blockIdx.x * (int64_t)kThreads + threadIdx.x; p < n; p += (int64_t)gridDim.x * kThreads) {
+        const double X = xyz[p * 3], Y = xyz[p * 3 + 1], Z = xyz[p * 3 + 2];
+        const double iz = Z != 0.0 ? __ddiv_rn(1.0, Z) : 1.0;
+        out_uv[p * 2] = __dadd_rn(__dmul_rn(fx, __dmul_rn(X, iz)), cx);
+        out_uv[p * 2 + 1] = __dadd_rn(__dmul_rn(fy, __dmul_rn(Y, iz)), cy);
+    }
+}
+
 static int grid_for(int64_t work_items) {
     const int64_t blocks = (work_items + kThreads - 1) / kThreads;
     const int64_t cap = (int64_t)sm_count() * 8;  // 8 resident CTAs of 256 threads per SM
     return (int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
 }
 
-// Dispatch a kernel template over (decoder, bit16).
-#define MDVT_DISPATCH_DECODER(decoder, bit16, CALL)                              \
-    do {                                                                         \
-        if ((decoder) == MDVT_DECODE_D1 && (bit16)) { CALL(MDVT_DECODE_D1, true); }   \
-        else if ((decoder) == MDVT_DECODE_D1) { CALL(MDVT_DECODE_D1, false); }        \
-        else if ((decoder) == MDVT_DECODE_D2) { CALL(MDVT_DECODE_D2, true); }         \
-        else { CALL(MDVT_DECODE_D3, true); }                                     \
-    } while (0)
-
-static int check_decoder(int decoder, int bit16) {
-    if (decoder < MDVT_DECODE_D1 || decoder > MDVT_DECODE_D3) {
-        set_error("unknown decoder %d", decoder);
-        return MDVT_ERR_INVALID_ARGUMENT;
-    }
-    if (!bit16 && decoder != MDVT_DECODE_D1) {
-        set_error("the 24-bit wire format exists for decoder D1 only");
-        return MDVT_ERR_UNSUPPORTED;
-    }
-    return MDVT_OK;
+// decode_uint32_as_depth (depth_frames_helper.py:13-24) and the inline divide variants on codes the caller holds.
+template <int DECODER>
+__global__ void __launch_bounds__(kThreads) codes_to_depth_kernel(const uint32_t *__restrict__ codes, int64_t n, float dec_const,
+                                                                  float *__restrict__ out_depth) {
+    for (int64_t p = blockIdx.x * (int64_t)kThreads + threadIdx.x; p < n; p += (int64_t)gridDim.x * kThreads)
+        out_depth[p] = depth_of<DECODER>(__ldg(codes + p), dec_const);
 }
 
-static int check_source(const mdvt_source *s) {
-    MDVT_REQUIRE(s != nullptr, "mdvt_source is NULL");
-    MDVT_REQUIRE(s->width > 0 && s->height > 0, "bad frame size %dx%d", s->width, s->height);
-    return check_decoder(s->decoder, s->bit16);
+// encode_data_as_BGR (depth_frames_helper.py:48-61): bytes of a u32 plane -> u8x3.
+__global__ void __launch_bounds__(kThreads) codes_to_pixels_kernel(const uint32_t *__restrict__ codes, int64_t n, int bit16, int bgr_order,
+                                                                   uint8_t *__restrict__ out_pix) {
+    for (int64_t p = blockIdx.x * (int64_t)kThreads + threadIdx.x; p < n; p += (int64_t)gridDim.x * kThreads) {
+        const uint32_t code = __ldg(codes + p);
+        uint8_t c0, c1, c2;  // R, G, B
+        if (bit16) {
+            c0 = c1 = (uint8_t)(code >> 24);
+            c2 = (uint8_t)(code >> 16);
+        } else {
+            c0 = (uint8_t)(code >> 16);
+            c1 = (uint8_t)(code >> 8);
+            c2 = (uint8_t)code;
+        }
+        uint8_t *o = out_pix + p * 3;
+        if (bgr_order) {
+            o[0] = c2; o[1] = c1; o[2] = c0;
+        } else {
+            o[0] = c0; o[1] = c1; o[2] = c2;
+        }
+    }
 }
 
 }  // namespace mdvt
@@ -197,14 +222,14 @@ using namespace mdvt;
 extern "C" int mdvt_decode_depth(const uint8_t *rgb, int64_t n_pixels, int decoder, int bit16, float dec_const,
                                  uint32_t *out_codes, float *out_depth, void *stream) {
     MDVT_REQUIRE(n_pixels >= 0, "negative pixel count");
-    if (int rc = check_decoder(decoder, bit16)) return rc;
+    if (int rc = check_decoder(decoder, bit16, false)) return rc;
     if (n_pixels == 0 || (!out_codes && !out_depth)) return MDVT_OK;
     MDVT_REQUIRE(rgb != nullptr, "rgb is NULL");
     MDVT_REQUIRE((reinterpret_cast<uintptr_t>(rgb) & 3) == 0, "rgb must be 4-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int grid = grid_for((n_pixels + kPxPerThread - 1) / kPxPerThread);
 #define CALL(D, B) decode_kernel<D, B><<<grid, kThreads, 0, st>>>(rgb, n_pixels, dec_const, out_codes, out_depth)
-    MDVT_DISPATCH_DECODER(decoder, bit16, CALL);
+    MDVT_DISPATCH_SOURCE(decoder, bit16, CALL);
 #undef CALL
     MDVT_CUDA_TRY(cudaGetLastError());
     return MDVT_OK;
@@ -223,7 +248,7 @@ extern "C" int mdvt_encode_depth(const float *depth, int64_t n_pixels, double ma
     return MDVT_OK;
 }
 
-extern "C" int mdvt_unproject_f32(const uint8_t *depth_rgb, const mdvt_source *src, const float *pose_host, float *out_xyz,
+extern "C" int mdvt_unproject_f32(const void *depth_rgb, const mdvt_source *src, const float *pose_host, float *out_xyz,
                                   void *stream) {
     if (int rc = check_source(src)) return rc;
     MDVT_REQUIRE(depth_rgb && out_xyz, "NULL buffer");
@@ -237,13 +262,13 @@ extern "C" int mdvt_unproject_f32(const uint8_t *depth_rgb, const mdvt_source *s
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define CALL(D, B) \
     unproject_f32_kernel<D, B><<<grid_for(n), kThreads, 0, st>>>(depth_rgb, src->width, n, src->dec_const, src->depth_scale, cam, pose, out_xyz)
-    MDVT_DISPATCH_DECODER(src->decoder, src->bit16, CALL);
+    MDVT_DISPATCH_SOURCE(src->decoder, src->bit16, CALL);
 #undef CALL
     MDVT_CUDA_TRY(cudaGetLastError());
     return MDVT_OK;
 }
 
-extern "C" int mdvt_unproject_f64(const uint8_t *depth_rgb, const mdvt_source *src, const double *K_host,
+extern "C" int mdvt_unproject_f64(const void *depth_rgb, const mdvt_source *src, const double *K_host,
                                   const double *pose_host, double *out_xyz, void *stream) {
     if (int rc = check_source(src)) return rc;
     MDVT_REQUIRE(depth_rgb && out_xyz && K_host, "NULL buffer");
@@ -259,8 +284,55 @@ extern "C" int mdvt_unproject_f64(const uint8_t *depth_rgb, const mdvt_source *s
     unproject_f64_kernel<D, B><<<grid_for(n), kThreads, 0, st>>>(depth_rgb, src->width, n, src->dec_const, src->depth_scale, \
                                                                  src->grid_sx, src->grid_sy, stretched, K_host[0], K_host[1], \
                                                                  K_host[2], K_host[3], pose, out_xyz)
-    MDVT_DISPATCH_DECODER(src->decoder, src->bit16, CALL);
+    MDVT_DISPATCH_SOURCE(src->decoder, src->bit16, CALL);
 #undef CALL
+    MDVT_CUDA_TRY(cudaGetLastError());
+    return MDVT_OK;
+}
+
+extern "C" int mdvt_codes_to_depth(const uint32_t *codes, int64_t n_pixels, int decoder, float dec_const, float *out_depth, void *stream) {
+    MDVT_REQUIRE(n_pixels >= 0, "negative pixel count");
+    if (int rc = check_decoder(decoder, 1, false)) return rc;
+    if (n_pixels == 0) return MDVT_OK;
+    MDVT_REQUIRE(codes && out_depth, "NULL buffer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (decoder == MDVT_DECODE_D1)
+        codes_to_depth_kernel<MDVT_DECODE_D1><<<grid_for(n_pixels), kThreads, 0, st>>>(codes, n_pixels, dec_const, out_depth);
+    else
+        codes_to_depth_kernel<MDVT_DECODE_D3><<<grid_for(n_pixels), kThreads, 0, st>>>(codes, n_pixels, dec_const, out_depth);
+    MDVT_CUDA_TRY(cudaGetLastError());
+    return MDVT_OK;
+}
+
+extern "C" int mdvt_codes_to_pixels(const uint32_t *codes, int64_t n_pixels, int bit16, int bgr_order, uint8_t *out_pix, void *stream) {
+    MDVT_REQUIRE(n_pixels >= 0, "negative pixel count");
+    if (n_pixels == 0) return MDVT_OK;
+    MDVT_REQUIRE(codes && out_pix, "NULL buffer");
+    codes_to_pixels_kernel<<<grid_for(n_pixels), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(codes, n_pixels, bit16, bgr_order, out_pix);
+    MDVT_CUDA_TRY(cudaGetLastError());
+    return MDVT_OK;
+}
+
+extern "C" int mdvt_transform_points_f64(const double *xyz, int64_t n_points, const double *pose_host, double *out_xyz, void *stream) {
+    MDVT_REQUIRE(n_points >= 0, "negative point count");
+    MDVT_REQUIRE(pose_host != nullptr, "pose is NULL");
+    if (n_points == 0) return MDVT_OK;
+    MDVT_REQUIRE(xyz && out_xyz, "NULL buffer");
+    Pose12d pose{};
+    for (int k = 0; k < 12; ++k) pose.m[k] = pose_host[k];
+    pose.on = 1;
+    transform_points_f64_kernel<<<grid_for(n_points), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(xyz, n_points, pose, out_xyz);
+    MDVT_CUDA_TRY(cudaGetLastError());
+    return MDVT_OK;
+}
+
+extern "C" int mdvt_project_points_f64(const double *xyz, int64_t n_points, const double *K_host, double *out_uv, void *stream) {
+    MDVT_REQUIRE(n_points >= 0, "negative point count");
+    MDVT_REQUIRE(K_host != nullptr, "K is NULL");
+    if (n_points == 0) return MDVT_OK;
+    MDVT_REQUIRE(xyz && out_uv, "NULL buffer");
+    project_points_f64_kernel<<<grid_for(n_points), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(xyz, n_points, K_host[0], K_host[1],
+                                                                                                      K_host[2], K_host[3], out_uv);
     MDVT_CUDA_TRY(cudaGetLastError());
     return MDVT_OK;
 }

@@ -19,14 +19,13 @@ struct ViewPack {
 
 template <int DECODER, bool BIT16>
 __global__ void __launch_bounds__(kThreads)
-    project_splat_kernel(const uint8_t *__restrict__ rgb, int width, int64_t n, float dec_const, float depth_scale, SourceCam cam,
-                         ViewPack views, float near_plane, int out_w, int out_h, unsigned long long *__restrict__ zbuf,
-                         float *__restrict__ out_uvz) {
+    project_splat_kernel(const void *__restrict__ rgb, int width, int64_t n, float dec_const, float depth_scale, SourceCam cam,
+                         ViewPack views, float near_plane, int out_w, int out_h, uint32_t id_offset,
+                         unsigned long long *__restrict__ zbuf, float *__restrict__ out_uvz) {
     const int64_t out_n = (int64_t)out_w * out_h;
     const float u_max = (float)(out_w - 1), v_max = (float)(out_h - 1);
     for (int64_t p = blockIdx.x * (int64_t)kThreads + threadIdx.x; p < n; p += (int64_t)gridDim.x * kThreads) {
-        const uint32_t r = rgb[p * 3], g = rgb[p * 3 + 1], b = rgb[p * 3 + 2];
-        const float z = __fmul_rn(depth_of<DECODER>(code_of<DECODER, BIT16>(r, g, b), dec_const), depth_scale);
+        const float z = __fmul_rn(source_depth<DECODER, BIT16>(rgb, p, dec_const), depth_scale);
         const int row = (int)(p / width), col = (int)(p - (int64_t)row * width);
         float X, Y;
         unproject_px(cam, col, row, z, X, Y);
@@ -47,7 +46,35 @@ __global__ void __launch_bounds__(kThreads)
                 // comparisons are false for NaN, so non-finite projections are culled too
                 if (Zv > near_plane && ur >= 0.0f && ur <= u_max && vr >= 0.0f && vr <= v_max) {
                     const int64_t t = (int64_t)(int)vr * out_w + (int)ur;
-                    const unsigned long long key = ((unsigned long long)__float_as_uint(Zv) << 32) | (uint32_t)p;
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(Zv) << 32) | (id_offset + (uint32_t)p);
+                    atomicMin(zbuf + (int64_t)k * out_n + t, key);
+                }
+            }
+        }
+    }
+}
+
+// Explicit points (N, 3) float32 in the frame space of the views' M: the reference's point painter
+// (stereo_rerender.py:746-755,814) and render() of point clouds (background cloud, edge points).
+__global__ void __launch_bounds__(kThreads)
+    splat_points_kernel(const float *__restrict__ xyz, int64_t n, ViewPack views, float near_plane, int out_w, int out_h, uint32_t id_offset,
+                        unsigned long long *__restrict__ zbuf) {
+    const int64_t out_n = (int64_t)out_w * out_h;
+    const float u_max = (float)(out_w - 1), v_max = (float)(out_h - 1);
+    for (int64_t p = blockIdx.x * (int64_t)kThreads + threadIdx.x; p < n; p += (int64_t)gridDim.x * kThreads) {
+        const float X = __ldg(xyz + p * 3), Y = __ldg(xyz + p * 3 + 1), Z = __ldg(xyz + p * 3 + 2);
+#pragma unroll
+        for (int k = 0; k < kMaxViews; ++k) {
+            if (k < views.n) {
+                const mdvt_view &vw = views.v[k];
+                const float Xv = affine_row(vw.M, X, Y, Z);
+                const float Yv = affine_row(vw.M + 4, X, Y, Z);
+                const float Zv = affine_row(vw.M + 8, X, Y, Z);
+                const float ur = rintf(__fadd_rn(__fdiv_rn(__fmul_rn(vw.fx, Xv), Zv), vw.cx));
+                const float vr = rintf(__fadd_rn(__fdiv_rn(__fmul_rn(vw.fy, Yv), Zv), vw.cy));
+                if (Zv > near_plane && ur >= 0.0f && ur <= u_max && vr >= 0.0f && vr <= v_max) {
+                    const int64_t t = (int64_t)(int)vr * out_w + (int)ur;
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(Zv) << 32) | (id_offset + (uint32_t)p);
                     atomicMin(zbuf + (int64_t)k * out_n + t, key);
                 }
             }
@@ -168,35 +195,48 @@ extern "C" int mdvt_zbuf_clear(uint64_t *zbuf, int64_t n_slots, void *stream) {
     return MDVT_OK;
 }
 
-extern "C" int mdvt_project_splat(const uint8_t *depth_rgb, const mdvt_source *src, const mdvt_view *views_host, int n_views,
-                                  float near_plane, int out_w, int out_h, uint64_t *zbuf, float *out_uvz, void *stream) {
-    MDVT_REQUIRE(src != nullptr, "mdvt_source is NULL");
-    MDVT_REQUIRE(src->width > 0 && src->height > 0, "bad frame size %dx%d", src->width, src->height);
-    MDVT_REQUIRE(src->decoder >= MDVT_DECODE_D1 && src->decoder <= MDVT_DECODE_D3, "unknown decoder %d", src->decoder);
-    if (!src->bit16 && src->decoder != MDVT_DECODE_D1) {
-        set_error("the 24-bit wire format exists for decoder D1 only");
-        return MDVT_ERR_UNSUPPORTED;
-    }
+static int pack_views(const mdvt_view *views_host, int n_views, ViewPack &pack) {
     MDVT_REQUIRE(n_views >= 1 && n_views <= kMaxViews, "n_views must be 1..%d", kMaxViews);
-    MDVT_REQUIRE(views_host && depth_rgb && zbuf, "NULL buffer");
-    MDVT_REQUIRE(out_w > 0 && out_h > 0, "bad output size %dx%d", out_w, out_h);
-    const int64_t n = (int64_t)src->width * src->height;
-    MDVT_REQUIRE(n <= 0xFFFFFFFFll, "source frame has more than 2^32 pixels");
-    ViewPack pack{};
+    MDVT_REQUIRE(views_host != nullptr, "views is NULL");
     pack.n = n_views;
     for (int k = 0; k < n_views; ++k) pack.v[k] = views_host[k];
+    return MDVT_OK;
+}
+
+extern "C" int mdvt_project_splat(const void *depth_src, const mdvt_source *src, const mdvt_view *views_host, int n_views,
+                                  float near_plane, int out_w, int out_h, uint32_t id_offset, uint64_t *zbuf, float *out_uvz,
+                                  void *stream) {
+    if (int rc = check_source(src)) return rc;
+    ViewPack pack{};
+    if (int rc = pack_views(views_host, n_views, pack)) return rc;
+    MDVT_REQUIRE(depth_src && zbuf, "NULL buffer");
+    MDVT_REQUIRE(out_w > 0 && out_h > 0, "bad output size %dx%d", out_w, out_h);
+    const int64_t n = (int64_t)src->width * src->height;
+    MDVT_REQUIRE(n + id_offset <= 0xFFFFFFFFll, "source index does not fit the 32-bit z-buffer payload");
     SourceCam cam{src->fx, src->fy, src->cx, src->cy, src->grid_sx, src->grid_sy};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     unsigned long long *zb = reinterpret_cast<unsigned long long *>(zbuf);
     const int grid = grid_for(n);
 #define CALL(D, B)                                                                                                          \
-    project_splat_kernel<D, B><<<grid, kThreads, 0, st>>>(depth_rgb, src->width, n, src->dec_const, src->depth_scale, cam, pack, \
-                                                          near_plane, out_w, out_h, zb, out_uvz)
-    if (src->decoder == MDVT_DECODE_D1 && src->bit16) { CALL(MDVT_DECODE_D1, true); }
-    else if (src->decoder == MDVT_DECODE_D1) { CALL(MDVT_DECODE_D1, false); }
-    else if (src->decoder == MDVT_DECODE_D2) { CALL(MDVT_DECODE_D2, true); }
-    else { CALL(MDVT_DECODE_D3, true); }
+    project_splat_kernel<D, B><<<grid, kThreads, 0, st>>>(depth_src, src->width, n, src->dec_const, src->depth_scale, cam, pack, \
+                                                          near_plane, out_w, out_h, id_offset, zb, out_uvz)
+    MDVT_DISPATCH_SOURCE(src->decoder, src->bit16, CALL);
 #undef CALL
+    MDVT_CUDA_TRY(cudaGetLastError());
+    return MDVT_OK;
+}
+
+extern "C" int mdvt_splat_points(const float *xyz, int64_t n_points, const mdvt_view *views_host, int n_views, float near_plane,
+                                 int out_w, int out_h, uint32_t id_offset, uint64_t *zbuf, void *stream) {
+    ViewPack pack{};
+    if (int rc = pack_views(views_host, n_views, pack)) return rc;
+    MDVT_REQUIRE(n_points >= 0, "negative point count");
+    MDVT_REQUIRE(out_w > 0 && out_h > 0, "bad output size %dx%d", out_w, out_h);
+    if (n_points == 0) return MDVT_OK;
+    MDVT_REQUIRE(xyz && zbuf, "NULL buffer");
+    MDVT_REQUIRE(n_points + id_offset <= 0xFFFFFFFFll, "point index does not fit the 32-bit z-buffer payload");
+    splat_points_kernel<<<grid_for(n_points), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        xyz, n_points, pack, near_plane, out_w, out_h, id_offset, reinterpret_cast<unsigned long long *>(zbuf));
     MDVT_CUDA_TRY(cudaGetLastError());
     return MDVT_OK;
 }

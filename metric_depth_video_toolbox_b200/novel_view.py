@@ -1,0 +1,108 @@
+"""Novel-view render of a clip: the body of `3d_view_depthfile.py --render`'s frame loop (:133-255) for
+batches of frames.  Per frame: decode -> unproject -> optional pose -> look-at camera aimed at the vertex
+centroid (Open3D get_center(), :231) -> z-buffered splat -> white-background image.
+
+The centroid is a per-frame reduction that decides the camera of the same frame.  Instead of one host round
+trip per frame, a chunk is processed in two passes: all centroids of the chunk (one reduction kernel per
+frame, results in one device buffer, ONE small D2H copy), then the look-at matrices (host scalars) and the
+splat + resolve per frame."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import geometry as geo
+from . import ops
+
+
+@dataclass
+class NovelViewParams:
+    """Mirrors the 3d_view_depthfile.py CLI values that reach the per-pixel path (:23-47)."""
+    width: int
+    height: int
+    xfov: Optional[float] = None
+    yfov: Optional[float] = None
+    max_depth: float = 100
+    cam_pos: Sequence[float] = (2.0, 2.0, -4.0)              # --x --y --z
+    target: Sequence[Optional[float]] = (None, None, None)   # --tx --ty --tz (None: centroid component)
+    transformations: Optional[Sequence] = None               # per-frame 4x4, already re-based
+    of_by_one: bool = True        # vertex grid used for the centroid (mesh mode; False with --render_as_pointcloud, :178-180)
+    bg_rgb: Sequence[int] = (255, 255, 255)                  # :254
+    near: float = geo.NEAR_PLANE
+
+
+class NovelViewRenderer:
+    def __init__(self, params: NovelViewParams, device: Optional[torch.device] = None):
+        self.p = params
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.K = geo.compute_camera_matrix(params.xfov, params.yfov, params.width, params.height)
+        self._zbuf = None
+        self._sums = None
+
+    def _pose(self, frame: int):
+        return None if self.p.transformations is None else np.asarray(self.p.transformations[frame], dtype=np.float64)
+
+    def centroids(self, depth_rgb: torch.Tensor, start_frame: int = 0) -> np.ndarray:
+        """(n, 3) float64 vertex means of the chunk (host)."""
+        p = self.p
+        n = depth_rgb.shape[0]
+        stride = 4 + _lib.REDUCE_SCRATCH_DOUBLES
+        if self._sums is None or self._sums.shape[0] < n:
+            self._sums = torch.empty((n, stride), dtype=torch.float64, device=depth_rgb.device)
+        src = ops.make_source(p.width, p.height, self.K, p.max_depth, "D1", True, 1.0, p.of_by_one)
+        for k in range(n):
+            ops.centroid_sums(depth_rgb[k], src, self.K, self._pose(start_frame + k), out=self._sums[k])
+        s = self._sums[:n, :4].cpu().numpy()  # the one synchronising copy of the chunk
+        return s[:, :3] / s[:, 3:4]
+
+    def extrinsic(self, centroid: np.ndarray) -> np.ndarray:
+        look = np.array(centroid, dtype=np.float64)
+        for a in range(3):
+            if self.p.target[a] is not None:
+                look[a] = self.p.target[a]
+        return geo.cam_look_at(np.array(self.p.cam_pos).astype(np.float32), look)
+
+    def view_of(self, frame: int, centroid: np.ndarray) -> ops.ViewSpec:
+        """render()'s camera: geometry Y scaled by fy/fx before the extrinsic, fx on both axes
+        (depth_map_tools.py:1528-1552); Open3D uses the upper 3x4 of the look-at matrix."""
+        K = self.K
+        M = self.extrinsic(centroid)[:3, :4] @ np.diag([1.0, K[1, 1] / K[0, 0], 1.0, 1.0])
+        pose = self._pose(frame)
+        if pose is not None:
+            M = M @ pose
+        return ops.ViewSpec(M, K[0, 0], K[0, 0], K[0, 2], K[1, 2])
+
+    def render_device(self, depth_rgb: torch.Tensor, colour: torch.Tensor, start_frame: int = 0, out_rgb: Optional[torch.Tensor] = None,
+                      out_mask: Optional[torch.Tensor] = None):
+        """depth_rgb / colour (n, H, W, 3) u8 CUDA -> (rgb (n, H, W, 3) u8, hole mask (n, H, W) u8)."""
+        p = self.p
+        n, h, w, _ = depth_rgb.shape
+        if (w, h) != (p.width, p.height):
+            raise ValueError(f"frames are {w}x{h}, parameters say {p.width}x{p.height}")
+        dev = depth_rgb.device
+        if out_rgb is None:
+            out_rgb = torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
+        if out_mask is None:
+            out_mask = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
+        if self._zbuf is None or tuple(self._zbuf.shape) != (1, h, w) or self._zbuf.device != dev:
+            self._zbuf = ops.new_zbuf(1, w, h, dev)
+        centres = self.centroids(depth_rgb, start_frame)
+        src = ops.make_source(w, h, self.K, p.max_depth, "D1", True, 1.0, False)
+        for k in range(n):
+            ops.project_splat(depth_rgb[k], src, [self.view_of(start_frame + k, centres[k])], w, h, self._zbuf, p.near)
+            ops.resolve(self._zbuf[0], colour[k], p.bg_rgb, p.bg_rgb, ops.FLAG_RESET_ZBUF, out_rgb=out_rgb[k], out_mask=out_mask[k])
+        return out_rgb, out_mask
+
+    def render_host(self, depth_rgb, colour, out_rgb=None):
+        """Host arrays in, pinned host tensor out (one chunk: H2D, kernels, D2H on the current stream)."""
+        d = torch.as_tensor(depth_rgb).to(self.device, non_blocking=True)
+        c = torch.as_tensor(colour).to(self.device, non_blocking=True)
+        rgb, _ = self.render_device(d, c)
+        if out_rgb is None:
+            out_rgb = torch.empty(rgb.shape, dtype=torch.uint8, pin_memory=True)
+        torch.as_tensor(out_rgb).copy_(rgb, non_blocking=True)
+        return out_rgb

@@ -84,14 +84,78 @@ def encode_depth(depth: torch.Tensor, max_depth, bit16: bool = True, bgr_order: 
     return (pix, codes) if want_codes else pix
 
 
+def codes_to_depth(codes: torch.Tensor, max_depth, decoder: str = "D1") -> torch.Tensor:
+    """decode_uint32_as_depth (depth_frames_helper.py:13-24): uint32 codes -> float32 metres."""
+    _need(codes, torch.uint32, "codes")
+    out = torch.empty(codes.shape, dtype=torch.float32, device=codes.device)
+    _lib.check(_lib.load().mdvt_codes_to_depth(_ptr(codes), codes.numel(), DECODERS[decoder], dec_const(max_depth, decoder), _ptr(out),
+                                               _stream()))
+    return out
+
+
+def codes_to_pixels(codes: torch.Tensor, bit16: bool = False, bgr_order: bool = True) -> torch.Tensor:
+    """encode_data_as_BGR (depth_frames_helper.py:48-61): uint32 plane -> (..., 3) u8."""
+    _need(codes, torch.uint32, "codes")
+    out = torch.empty(codes.shape + (3,), dtype=torch.uint8, device=codes.device)
+    _lib.check(_lib.load().mdvt_codes_to_pixels(_ptr(codes), codes.numel(), int(bool(bit16)), int(bool(bgr_order)), _ptr(out), _stream()))
+    return out
+
+
+def _depth_source(depth_src: torch.Tensor, decoder: str):
+    """(tensor, pixel count, shape without the channel axis) of a wire-format (..., 3) u8 or float32 depth tensor."""
+    if decoder == "F32":
+        _need(depth_src, torch.float32, "depth_src")
+        return depth_src.numel(), tuple(depth_src.shape)
+    _need(depth_src, torch.uint8, "depth_src")
+    if depth_src.shape[-1] != 3:
+        raise ValueError("a wire-format frame must have a trailing dimension of 3")
+    return depth_src.numel() // 3, tuple(depth_src.shape[:-1])
+
+
+def depth_to_grey(depth_src: torch.Tensor, max_depth, bits: int, decoder: str = "D2", bit16: bool = True) -> torch.Tensor:
+    """convert_metric_depth_video_to_other_format.py:752-760: --bit16 -> (...,) uint16, --bit8 -> (..., 3) u8."""
+    n, shape = _depth_source(depth_src, decoder)
+    if bits == 16:
+        factor, out = (255 ** 2) / max_depth, torch.empty(shape, dtype=torch.uint16, device=depth_src.device)
+    elif bits == 8:
+        factor, out = 255 / max_depth, torch.empty(shape + (3,), dtype=torch.uint8, device=depth_src.device)
+    else:
+        raise ValueError("bits must be 8 or 16")
+    dc = 1.0 if decoder == "F32" else dec_const(max_depth, decoder)
+    _lib.check(_lib.load().mdvt_depth_to_grey(_ptr(depth_src), n, DECODERS[decoder], int(bool(bit16)), dc, float(np.float32(factor)), bits,
+                                              3 if bits == 8 else 1, _ptr(out), _stream()))
+    return out
+
+
+def touchly_depth(depth_src: torch.Tensor, touchly_min: float, touchly_max: float, zero_is_far: bool, max_depth=100,
+                  decoder: str = "D1", depth_scale: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One frame (H, W, 3) u8 wire format or (H, W) f32 -> Touchly reverse-depth image (H, W, 3) u8
+    (stereo_rerender.py:548-552,687-690,826-829).  `out` may be a row/column slice of a larger frame."""
+    _, shape = _depth_source(depth_src, decoder)
+    if len(shape) != 2:
+        raise ValueError("touchly_depth takes one frame")
+    h, w = shape
+    if out is None:
+        out = torch.empty((h, w, 3), dtype=torch.uint8, device=depth_src.device)
+    if out.dtype != torch.uint8 or not out.is_cuda or tuple(out.shape) != (h, w, 3) or out.stride(2) != 1 or out.stride(1) != 3:
+        raise ValueError("out must be a (H, W, 3) u8 CUDA view with dense rows")
+    dc = 1.0 if decoder == "F32" else dec_const(max_depth, decoder)
+    _lib.check(_lib.load().mdvt_touchly_depth(_ptr(depth_src), w, h, DECODERS[decoder], 1, dc, float(np.float32(depth_scale)),
+                                              float(np.float32(touchly_min)), float(np.float32(touchly_max)),
+                                              float(np.float32(255 / (touchly_max - touchly_min))), int(bool(zero_is_far)),
+                                              _ptr(out), out.stride(0), _stream()))
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # geometry
 # ---------------------------------------------------------------------------------------------
-def make_source(width: int, height: int, K: np.ndarray, max_depth, decoder: str = "D1", bit16: bool = True,
+def make_source(width: int, height: int, K: np.ndarray, max_depth=100, decoder: str = "D1", bit16: bool = True,
                 depth_scale: float = 1.0, of_by_one: bool = False) -> _lib.Source:
+    """decoder "F32": the source tensor is a (H, W) float32 depth plane instead of a wire-format frame."""
     s = _lib.Source()
     s.width, s.height, s.decoder, s.bit16 = int(width), int(height), DECODERS[decoder], int(bool(bit16))
-    s.dec_const = dec_const(max_depth, decoder)
+    s.dec_const = 1.0 if decoder == "F32" else dec_const(max_depth, decoder)
     s.depth_scale = float(np.float32(depth_scale))
     s.fx, s.fy, s.cx, s.cy = (float(np.float32(v)) for v in (K[0][0], K[1][1], K[0][2], K[1][2]))
     s.grid_sx = float(np.float32((width + 1) / width)) if of_by_one else 1.0
@@ -106,23 +170,58 @@ def _pose12(pose, ctype):
     return (ctype * 12)(*[float(v) for v in m])
 
 
+def _need_source(depth_src: torch.Tensor, source: _lib.Source) -> torch.Tensor:
+    """The frame a mdvt_source describes: (H, W, 3) u8 wire format, or (H, W) float32 for decoder F32."""
+    if source.decoder == _lib.SOURCE_F32:
+        _need(depth_src, torch.float32, "depth_src")
+        want = (source.height, source.width)
+    else:
+        _need(depth_src, torch.uint8, "depth_src")
+        want = (source.height, source.width, 3)
+    if tuple(depth_src.shape) != want:
+        raise ValueError(f"depth_src shape {tuple(depth_src.shape)} != {want}")
+    return depth_src
+
+
+def _k4(K):
+    if K is None:
+        raise ValueError("the float64 path needs the float64 camera matrix K")
+    return (C.c_double * 4)(float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2]))
+
+
 def unproject(depth_rgb: torch.Tensor, source: _lib.Source, pose=None, dtype=torch.float32, K: Optional[np.ndarray] = None):
-    """(H, W, 3) u8 -> (H*W, 3) points.  float64 needs the float64 intrinsics `K` (3x3)."""
-    _need(depth_rgb, torch.uint8, "depth_rgb")
-    if tuple(depth_rgb.shape) != (source.height, source.width, 3):
-        raise ValueError(f"depth_rgb shape {tuple(depth_rgb.shape)} != ({source.height}, {source.width}, 3)")
+    """(H, W, 3) u8 (or (H, W) f32 for an F32 source) -> (H*W, 3) points.  float64 needs the float64 intrinsics `K` (3x3)."""
+    _need_source(depth_rgb, source)
     n = source.width * source.height
     out = torch.empty((n, 3), dtype=dtype, device=depth_rgb.device)
     lib = _lib.load()
     if dtype == torch.float32:
         _lib.check(lib.mdvt_unproject_f32(_ptr(depth_rgb), C.byref(source), _pose12(pose, C.c_float), _ptr(out), _stream()))
     elif dtype == torch.float64:
-        if K is None:
-            raise ValueError("float64 unprojection needs the float64 camera matrix K")
-        k4 = (C.c_double * 4)(float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2]))
+        k4 = _k4(K)
         _lib.check(lib.mdvt_unproject_f64(_ptr(depth_rgb), C.byref(source), k4, _pose12(pose, C.c_double), _ptr(out), _stream()))
     else:
         raise TypeError("dtype must be torch.float32 or torch.float64")
+    return out
+
+
+def transform_points(xyz: torch.Tensor, transform, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """depth_map_tools.transform_points (:977-1004) on (N, 3) float64 device points."""
+    _need(xyz, torch.float64, "xyz")
+    if xyz.dim() != 2 or xyz.shape[1] != 3:
+        raise ValueError("xyz must be (N, 3)")
+    out = torch.empty_like(xyz) if out is None else _need(out, torch.float64, "out")
+    _lib.check(_lib.load().mdvt_transform_points_f64(_ptr(xyz), xyz.shape[0], _pose12(transform, C.c_double), _ptr(out), _stream()))
+    return out
+
+
+def project_points(xyz: torch.Tensor, K) -> torch.Tensor:
+    """depth_map_tools.project_3d_points_to_2d (:1057-1060) on (N, 3) float64 device points -> (N, 2)."""
+    _need(xyz, torch.float64, "xyz")
+    if xyz.dim() != 2 or xyz.shape[1] != 3:
+        raise ValueError("xyz must be (N, 3)")
+    out = torch.empty((xyz.shape[0], 2), dtype=torch.float64, device=xyz.device)
+    _lib.check(_lib.load().mdvt_project_points_f64(_ptr(xyz), xyz.shape[0], _k4(K), _ptr(out), _stream()))
     return out
 
 
@@ -156,20 +255,69 @@ def zbuf_clear(zbuf: torch.Tensor):
 
 
 def project_splat(depth_rgb: torch.Tensor, source: _lib.Source, views: Sequence[ViewSpec], out_w: int, out_h: int,
-                  zbuf: torch.Tensor, near: float = NEAR_PLANE, want_uvz: bool = False):
+                  zbuf: torch.Tensor, near: float = NEAR_PLANE, want_uvz: bool = False, id_offset: int = 0):
     """K1+K2: merge every source pixel into `zbuf` (n_views, out_h, out_w) int64 (u64 bits)."""
-    _need(depth_rgb, torch.uint8, "depth_rgb")
+    _need_source(depth_rgb, source)
     _need(zbuf, torch.int64, "zbuf")
-    if tuple(depth_rgb.shape) != (source.height, source.width, 3):
-        raise ValueError("depth_rgb shape does not match the source description")
     if tuple(zbuf.shape) != (len(views), out_h, out_w):
         raise ValueError(f"zbuf shape {tuple(zbuf.shape)} != ({len(views)}, {out_h}, {out_w})")
     n = source.width * source.height
     uvz = torch.empty((len(views), n, 3), dtype=torch.float32, device=depth_rgb.device) if want_uvz else None
     arr = (_lib.View * len(views))(*[v.to_c() for v in views])
     _lib.check(_lib.load().mdvt_project_splat(_ptr(depth_rgb), C.byref(source), arr, len(views), float(np.float32(near)),
-                                              int(out_w), int(out_h), _ptr(zbuf), _ptr(uvz), _stream()))
+                                              int(out_w), int(out_h), int(id_offset), _ptr(zbuf), _ptr(uvz), _stream()))
     return uvz
+
+
+def splat_points(xyz: torch.Tensor, views: Sequence[ViewSpec], out_w: int, out_h: int, zbuf: torch.Tensor,
+                 near: float = NEAR_PLANE, id_offset: int = 0):
+    """Explicit (N, 3) float32 points through the same visibility rule (the reference's point painter)."""
+    _need(xyz, torch.float32, "xyz")
+    _need(zbuf, torch.int64, "zbuf")
+    if xyz.dim() != 2 or xyz.shape[1] != 3:
+        raise ValueError("xyz must be (N, 3)")
+    if tuple(zbuf.shape) != (len(views), out_h, out_w):
+        raise ValueError(f"zbuf shape {tuple(zbuf.shape)} != ({len(views)}, {out_h}, {out_w})")
+    arr = (_lib.View * len(views))(*[v.to_c() for v in views])
+    _lib.check(_lib.load().mdvt_splat_points(_ptr(xyz), xyz.shape[0], arr, len(views), float(np.float32(near)), int(out_w), int(out_h),
+                                             int(id_offset), _ptr(zbuf), _stream()))
+
+
+# ---------------------------------------------------------------------------------------------
+# per-frame reductions
+# ---------------------------------------------------------------------------------------------
+def _reduce_buffer(device) -> torch.Tensor:
+    return torch.empty(4 + _lib.REDUCE_SCRATCH_DOUBLES, dtype=torch.float64, device=device)
+
+
+def centroid_sums(depth_src: torch.Tensor, source: _lib.Source, K: np.ndarray, pose=None, out: Optional[torch.Tensor] = None):
+    """Device tensor [sum X, sum Y, sum Z, n] (float64) of the unprojected (+posed) vertices: Open3D
+    get_center() without materialising the vertices (3d_view_depthfile.py:231).  Asynchronous."""
+    _need_source(depth_src, source)
+    buf = _reduce_buffer(depth_src.device) if out is None else _need(out, torch.float64, "out")
+    _lib.check(_lib.load().mdvt_centroid(_ptr(depth_src), C.byref(source), _k4(K), _pose12(pose, C.c_double), _ptr(buf), _stream()))
+    return buf[:4]
+
+
+def depth_sums(depth_src: torch.Tensor, max_depth=100, decoder: str = "D3", bit16: bool = True, mask: Optional[torch.Tensor] = None,
+               mask_gt: int = 240, out: Optional[torch.Tensor] = None):
+    """Device tensor [sum, count, sum of squares, 0] (float64) of the decoded depth over pixels whose mask byte
+    is > mask_gt (find_convergence_depth.py:56-80).  Asynchronous."""
+    if decoder == "F32":
+        _need(depth_src, torch.float32, "depth_src")
+        n = depth_src.numel()
+    else:
+        _need(depth_src, torch.uint8, "depth_src")
+        n = depth_src.numel() // 3
+    if mask is not None:
+        _need(mask, torch.uint8, "mask")
+        if mask.numel() != n:
+            raise ValueError("mask must have one byte per pixel")
+    buf = _reduce_buffer(depth_src.device) if out is None else _need(out, torch.float64, "out")
+    dc = 1.0 if decoder == "F32" else dec_const(max_depth, decoder)
+    _lib.check(_lib.load().mdvt_depth_sum(_ptr(depth_src), n, DECODERS[decoder], int(bool(bit16)), dc, _ptr(mask), int(mask_gt), _ptr(buf),
+                                          _stream()))
+    return buf[:4]
 
 
 def resolve(zbuf_view: torch.Tensor, colour: torch.Tensor, bg_rgb=(0, 0, 0), fill_rgb=(0, 0, 0), flags: int = 0,

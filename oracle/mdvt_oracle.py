@@ -335,10 +335,12 @@ def stereo_frame(depth_rgb, colour, xfov, yfov=None, max_depth=100, pupillary_di
 
 
 def novel_view_frame(depth_rgb, colour, xfov, yfov=None, max_depth=100, cam_pos=(2.0, 2.0, -4.0),
-                     target=None, transform=None):
+                     target=None, transform=None, center_of_by_one=False):
     """One iteration of `3d_view_depthfile.py --render` (:133-255) in point-splat form:
-    target defaults to the vertex mean (:231), white background (:254).  render() scales
-    world Y by fy/fx and projects with fx on both axes (depth_map_tools.py:1528-1552)."""
+    target defaults to the vertex mean (:231; the mesh's vertices sit on the stretched grid
+    unless --render_as_pointcloud, :178-182 -> `center_of_by_one`), white background (:254).
+    render() scales world Y by fy/fx and projects with fx on both axes
+    (depth_map_tools.py:1528-1552)."""
     h, w = depth_rgb.shape[:2]
     K = camera_matrix(xfov, yfov, w, h)
     depth = decode_rgb_depth_frame(depth_rgb, max_depth, True)
@@ -346,6 +348,9 @@ def novel_view_frame(depth_rgb, colour, xfov, yfov=None, max_depth=100, cam_pos=
     if transform is not None:
         pts = apply_pose(pts, transform)
     look = pts.mean(axis=0)
+    if center_of_by_one:
+        grid = unproject(depth, K, of_by_one=True)
+        look = (grid if transform is None else apply_pose(grid, transform)).mean(axis=0)
     if target is not None:
         for a in range(3):
             if target[a] is not None:

@@ -72,7 +72,15 @@ def test_argument_validation_without_a_device():
     assert lib.mdvt_stereo_rows(None, None, 0, 64, 4, None, 0, 0, 0, 0, None, None, None) == 0
     assert lib.mdvt_zbuf_clear(None, 0, None) == 0
     src = _lib.Source()
-    assert lib.mdvt_project_splat(None, C.byref(src), None, 1, 1e-4, 4, 4, None, None, None) == -1  # 0x0 frame
+    assert lib.mdvt_project_splat(None, C.byref(src), None, 1, 1e-4, 4, 4, 0, None, None, None) == -1  # 0x0 frame
+    assert lib.mdvt_splat_points(None, -1, None, 1, 1e-4, 4, 4, 0, None, None) == -1
+    assert lib.mdvt_splat_points(None, 0, C.byref(_lib.View()), 1, 1e-4, 4, 4, 0, None, None) == 0
+    assert lib.mdvt_codes_to_depth(None, 0, 0, 1.0, None, None) == 0
+    assert lib.mdvt_codes_to_pixels(None, -3, 1, 1, None, None) == -1
+    assert lib.mdvt_transform_points_f64(None, 0, (C.c_double * 12)(), None, None) == 0
+    assert lib.mdvt_project_points_f64(None, 5, None, None, None) == -1
+    assert lib.mdvt_depth_sum(None, 16, 9, 1, 1.0, None, 240, None, None) == -1  # unknown decoder
+    assert lib.mdvt_centroid(None, C.byref(src), None, None, None, None) == -1
 
 
 def test_ops_refuse_cpu_tensors():

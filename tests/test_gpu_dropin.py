@@ -1,0 +1,329 @@
+"""GPU: the drop-in surface (depth_frames_helper / depth_map_tools modules, the script front ends) against
+the golden vectors generated from the reference and against the CPU oracle.  Everything goes NumPy ->
+drop-in function -> C ABI -> CUDA kernel -> NumPy, as a user of the reference modules would call it."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import depth_frames_helper as dfh   # the root-level launchers: same import names as the reference
+import depth_map_tools as dmt
+from metric_depth_video_toolbox_b200 import ops, video_io
+from metric_depth_video_toolbox_b200.novel_view import NovelViewParams, NovelViewRenderer
+from metric_depth_video_toolbox_b200.synth import SyntheticClip
+from oracle import kernel_model as km
+from oracle import mdvt_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+# ---------------------------------------------------------------------------------------------
+# depth_frames_helper
+# ---------------------------------------------------------------------------------------------
+def test_depth_frames_helper_matches_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "decode_all_codes.npz"))
+    rgb = g["rgb"]
+    h, w = rgb.shape[:2]
+    for md in (100, 20):
+        got = dfh.decode_rgb_depth_frame(rgb, md, True)
+        assert isinstance(got, np.ndarray) and got.dtype == np.float32
+        assert np.array_equal(bits(got), bits(g[f"d1_depth_md{md}"]))
+        assert np.array_equal(bits(dfh.decode_rgb_depth_frame(rgb, md, False)), bits(g[f"d1_depth24_md{md}"]))
+    codes = dfh.decode_rgb_as_data(rgb, w, h, True)
+    assert codes.dtype == np.uint32 and np.array_equal(codes, g["d1_codes"])
+    assert np.array_equal(dfh.decode_rgb_as_data(rgb, w, h, False), g["d1_codes24"])
+    assert np.array_equal(bits(dfh.decode_uint32_as_depth(codes, 100)), bits(g["d1_depth_md100"]))
+    e = np.load(os.path.join(golden_dir, "encode.npz"))
+    for md in (100, 20):
+        enc = dfh.encode_depth_as_uint32(e["depth"], md)
+        assert enc.dtype == np.uint32 and np.array_equal(enc, e[f"codes_md{md}"])
+        assert np.array_equal(dfh.encode_data_as_BGR(enc, 64, 48, bit16=True), e[f"bgr16_md{md}"])
+        assert np.array_equal(dfh.encode_data_as_BGR(enc, 64, 48, bit16=False), e[f"bgr24_md{md}"])
+    # CUDA tensors in -> CUDA tensors out, same bits
+    dev = dfh.decode_rgb_depth_frame(cu(rgb), 100, True)
+    assert dev.is_cuda and np.array_equal(bits(dev.cpu().numpy()), bits(g["d1_depth_md100"]))
+
+
+def test_save_depth_video_round_trip(tmp_path):
+    rng = np.random.default_rng(5)
+    frames = rng.uniform(0.2, 60, (5, 48, 64)).astype(np.float32)
+    path = str(tmp_path / "depth.mkv")
+    dfh.save_depth_video(frames, path, 24.0, 100, 64, 48)
+    back = video_io.read_clip(path)  # RGB order, as the scripts see it
+    assert back.shape == (5, 48, 64, 3)
+    for k in range(5):
+        assert np.array_equal(back[k], orc.encode_depth_frame_rgb(frames[k], 100, True))
+        assert np.abs(dfh.decode_rgb_depth_frame(back[k], 100, True) - frames[k]).max() < 1.56e-3
+    assert dfh.verify_and_move(path, 5, str(tmp_path / "final.mkv")) and os.path.isfile(tmp_path / "final.mkv")
+    assert dfh.verify_and_move(str(tmp_path / "final.mkv"), 6, str(tmp_path / "x.mkv")) is False
+
+
+# ---------------------------------------------------------------------------------------------
+# depth_map_tools
+# ---------------------------------------------------------------------------------------------
+def _frame(w=64, h=48, k=0, zero_fraction=0.005):
+    depth_rgb, colour = SyntheticClip(w, h, 4, zero_fraction=zero_fraction).frame(k)
+    return depth_rgb, colour, orc.decode_rgb_depth_frame(depth_rgb, 100, True)
+
+
+@pytest.mark.parametrize("of_by_one", [False, True])
+def test_create_point_cloud_from_depth_bit_exact(of_by_one):
+    _, _, depth = _frame(640, 480)
+    K = dmt.compute_camera_matrix(60.0, None, 640, 480)
+    pts, h, w = dmt.create_point_cloud_from_depth(depth, K, of_by_one)
+    assert (h, w) == (480, 640) and pts.dtype == np.float64
+    assert np.array_equal(pts.view(np.uint64), orc.unproject(depth, K, of_by_one).view(np.uint64))
+
+
+def test_transform_and_project_points(golden_dir):
+    g = np.load(os.path.join(golden_dir, "geometry_64x48.npz"))
+    rng = np.random.default_rng(2)
+    pts = rng.normal(size=(1000, 3)) * [2, 2, 1] + [0, 0, 6]
+    T = np.eye(4)
+    T[:3, :3] = orc.rot_y(0.3)
+    T[:3, 3] = (0.5, -0.25, 1.5)
+    got = dmt.transform_points(pts, T)
+    np.testing.assert_allclose(got, orc.apply_pose(pts, T), rtol=1e-13, atol=1e-14)
+    K = dmt.compute_camera_matrix(60.0, 45.0, 640, 480)
+    uv = dmt.project_3d_points_to_2d(got, K)
+    K32 = K.astype(np.float32).astype(np.float64)
+    u, v, _ = orc.project(got, K32)
+    np.testing.assert_allclose(uv, np.stack((u, v), -1), rtol=1e-12, atol=1e-9)
+    # the reference's own outputs for these two functions (cv2.projectPoints twin: <= 1e-4 px)
+    np.testing.assert_allclose(dmt.transform_points(g["xyz_obo0"], g["T"]), g["xyz_T"], rtol=1e-12, atol=1e-12)
+    ok = g["xyz_T"][:, 2] > 1e-4  # cv2 mirrors / special-cases z <= 0; those points are culled before projection here
+    assert np.abs(dmt.project_3d_points_to_2d(g["xyz_T"], g["K"])[ok] - g["uv_T"][ok]).max() < 1e-4
+
+
+def test_depth_mesh_pose_algebra_and_center():
+    depth_rgb, colour, depth = _frame(64, 48)
+    K = dmt.compute_camera_matrix(60.0, None, 64, 48)
+    mesh, used = dmt.get_mesh_from_depth_map(depth, K, colour, None, of_by_one=True)
+    assert len(used) == 64 * 48 and np.array_equal(used, np.arange(64 * 48))
+    want = orc.unproject(depth, K, True)
+    assert np.array_equal(mesh.vertices, want)
+    np.testing.assert_allclose(mesh.get_center(), want.mean(axis=0), rtol=1e-12)
+    assert np.array_equal(mesh.vertex_colors, colour.reshape(-1, 3) / 255.0)
+    # the script's eye-pose sequence (stereo_rerender.py:720-725): rotate about the origin, then translate
+    theta = 0.01
+    R = mesh.get_rotation_matrix_from_xyz((0, -theta, 0))
+    np.testing.assert_allclose(R, orc.rot_y(-theta), atol=1e-15)
+    T = np.eye(4)
+    T[:3, 3] = (0.1, 0.0, 0.2)
+    mesh.transform(T)
+    mesh.rotate(R, center=(0, 0, 0))
+    mesh.translate([0.0315, 0.0, 0.0])
+    np.testing.assert_allclose(mesh.pose, orc.eye_pose("left", 0.063, theta) @ T, atol=1e-15)
+    np.testing.assert_allclose(mesh.vertices, orc.apply_pose(want, mesh.pose), rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(mesh.get_center(), orc.apply_pose(want, mesh.pose).mean(axis=0), rtol=1e-11)
+    # mesh reuse keeps the object, resets the pose
+    mesh2, _ = dmt.get_mesh_from_depth_map(depth, K, colour, mesh, of_by_one=False)
+    assert mesh2 is mesh and np.array_equal(mesh.pose, np.eye(4))
+
+
+def test_render_matches_oracle_view():
+    w, h = 160, 120
+    depth_rgb, colour, depth = _frame(w, h, 1)
+    K = dmt.compute_camera_matrix(60.0, None, w, h)
+    mesh, _ = dmt.get_mesh_from_depth_map(depth, K, colour, None, of_by_one=False)
+    mesh.translate([0.2, 0.0, 0.0])
+    bg = np.array([0.0, 1.0, 0.0])
+    img, zplane = dmt.render([mesh], K, depth=-2, bg_color=bg)
+    assert img.dtype == np.float32 and img.shape == (h, w, 3) and zplane.shape == (h, w)
+    M = np.eye(4)
+    M[0, 3] = 0.2
+    want, want_mask, ids = orc.render_view(depth_rgb, colour, 100, K, M, bg_rgb=(0, 255, 0), hole_fill=(0, 255, 0))
+    got = (img * 255).astype(np.uint8)  # what the scripts do with render()'s result (stereo_rerender.py:819)
+    assert (got != want).any(axis=-1).mean() < 2e-3
+    holes = np.all(img == bg, axis=-1)   # stereo_rerender.py:740
+    assert (holes != (want_mask == 255)).mean() < 2e-3 and holes.any()
+    u, v, z = orc.view_uvz(depth_rgb, 100, K, M)
+    assert np.abs(zplane - orc.zbuffer_depth(ids, z)).max() < 1e-4 or (np.abs(zplane - orc.zbuffer_depth(ids, z)) > 1e-4).mean() < 2e-3
+    assert np.array_equal(dmt.render([mesh], K, depth=True), zplane)
+    assert np.array_equal(dmt.render([mesh], K, bg_color=bg), img)
+
+
+def test_render_mesh_plus_point_cloud_shares_one_zbuffer():
+    w, h = 64, 48
+    depth_rgb, colour, depth = _frame(w, h, 0, zero_fraction=0.0)
+    K = dmt.compute_camera_matrix(60.0, None, w, h)
+    mesh, _ = dmt.get_mesh_from_depth_map(depth, K, colour, None, of_by_one=False)
+    # a red point in front of everything at the image centre, a blue one behind everything
+    pts = np.array([[0.0, 0.0, 0.5], [0.0, 0.0, 50.0]])
+    cols = np.array([[1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
+    pcd = dmt.pts_2_pcd(pts, cols)
+    assert np.array_equal(pcd.points, pts) and np.array_equal(pcd.colors, cols)
+    img = (dmt.render([mesh, pcd], K) * 255).astype(np.uint8)
+    base = (dmt.render([mesh], K) * 255).astype(np.uint8)
+    assert tuple(img[h // 2, w // 2]) == (255, 0, 0)
+    diff = (img != base).any(axis=-1)
+    assert diff.sum() == 1  # only the near point changed a pixel; the far one lost the depth test
+    # convert_mesh_to_pcd drops the listed vertices from the render
+    removed = np.arange(0, w * h, 2)
+    pc = dmt.convert_mesh_to_pcd(mesh, removed, None)
+    img2, zp = dmt.render([pc], K, depth=-2)
+    ids = np.arange(w * h).reshape(h, w)
+    assert (zp[ids % 2 == 0] == 0).all() and (zp[ids % 2 == 1] > 0).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# reductions and export formats
+# ---------------------------------------------------------------------------------------------
+def test_depth_sums_and_centroid_vs_numpy():
+    depth_rgb, _, _ = _frame(640, 480, 2)
+    d3 = orc.decode_rgb_depth_frame(depth_rgb, 100, True, "D3").astype(np.float64)
+    s = ops.depth_sums(cu(depth_rgb), 100, "D3").cpu().numpy()
+    assert s[1] == d3.size and abs(s[0] - d3.sum()) <= 1e-12 * d3.sum() and abs(s[2] - (d3 * d3).sum()) <= 1e-12 * (d3 * d3).sum()
+    mask = np.random.default_rng(0).integers(0, 256, (480, 640), dtype=np.uint8)
+    sm = ops.depth_sums(cu(depth_rgb), 100, "D3", mask=cu(mask)).cpu().numpy()
+    sel = d3[mask > 240]
+    assert sm[1] == sel.size and abs(sm[0] - sel.sum()) <= 1e-12 * sel.sum()
+    assert abs(sm[0] / sm[1] - orc.convergence_depth_of_frame(depth_rgb, 100, mask)) < 1e-5  # the reference's float32 mean
+    empty = ops.depth_sums(cu(depth_rgb), 100, "D3", mask=torch.zeros((480, 640), dtype=torch.uint8, device=DEV)).cpu().numpy()
+    assert empty[1] == 0 and empty[0] == 0
+    a = ops.depth_sums(cu(depth_rgb), 100, "D3").cpu().numpy()
+    assert np.array_equal(a, s)  # fixed summation order: bit-reproducible
+
+
+def test_grey_and_touchly_exports():
+    depth_rgb, _, _ = _frame(64, 48, 1)
+    depth_rgb[..., 1] = np.random.default_rng(1).integers(0, 256, (48, 64), dtype=np.uint8)
+    d2 = orc.decode_rgb_depth_frame(depth_rgb, 100, True, "D2")
+    # convert_metric_depth_video_to_other_format.py:752-760
+    want16 = np.rint(d2 * ((255 ** 2) / 100)).astype(np.uint16)
+    want8 = np.repeat(np.rint(d2 * (255 / 100)).astype(np.uint8)[..., None], 3, axis=-1)
+    assert np.array_equal(ops.depth_to_grey(cu(depth_rgb), 100, 16).cpu().numpy(), want16)
+    assert np.array_equal(ops.depth_to_grey(cu(depth_rgb), 100, 8).cpu().numpy(), want8)
+    # stereo_rerender.py:548-551 on the D1-decoded, master-FOV-scaled depth
+    scale = orc.master_fov_depth_scale(45.0, 60.0)
+    depth = orc.apply_depth_scale(orc.decode_rgb_depth_frame(depth_rgb, 100, True), scale)
+    for tmin, tmax in ((0, 5), (0.5, 7.3)):
+        d8 = np.rint(np.maximum(0, np.minimum(depth, tmax) - tmin) * (255 / (tmax - tmin))).astype(np.uint8)
+        want = 255 - np.repeat(d8[..., None], 3, axis=-1)
+        got = ops.touchly_depth(cu(depth_rgb), tmin, tmax, False, 100, "D1", scale).cpu().numpy()
+        assert np.array_equal(got, want), (tmin, tmax)
+        d8z = d8.copy()
+        d8z[d8z == 0] = 255   # :688 / :827
+        got_z = ops.touchly_depth(cu(depth), tmin, tmax, True, decoder="F32").cpu().numpy()
+        assert np.array_equal(got_z, 255 - np.repeat(d8z[..., None], 3, axis=-1))
+    stacked = torch.zeros((96, 64, 3), dtype=torch.uint8, device=DEV)
+    ops.touchly_depth(cu(depth_rgb), 0, 5, False, 100, "D1", scale, out=stacked[48:])
+    assert bool((stacked[:48] == 0).all()) and bool((stacked[48:] != 0).any())
+
+
+# ---------------------------------------------------------------------------------------------
+# novel view (3d_view_depthfile --render)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("of_by_one,yfov", [(True, None), (False, 50.0)])
+def test_novel_view_renderer_vs_oracle(of_by_one, yfov):
+    w, h, n = 160, 120, 2
+    depth, colour = SyntheticClip(w, h, n, zero_fraction=0.005).frames()
+    T = np.tile(np.eye(4), (n, 1, 1))
+    T[1, :3, 3] = (0.1, 0.0, -0.2)
+    nv = NovelViewRenderer(NovelViewParams(w, h, 60, yfov, 100, (2.0, 2.0, -4.0), (None, 0.5, None), T, of_by_one=of_by_one), DEV)
+    rgb, mask = nv.render_device(cu(depth), cu(colour))
+    for k in range(n):
+        want, want_mask, ids, ext = orc.novel_view_frame(depth[k], colour[k], 60, yfov, 100, (2.0, 2.0, -4.0), (None, 0.5, None), T[k],
+                                                         center_of_by_one=of_by_one)
+        centre = nv.centroids(cu(depth[k:k + 1]), k)[0]
+        np.testing.assert_allclose(nv.extrinsic(centre), ext, rtol=1e-9, atol=1e-9)
+        assert (rgb[k].cpu().numpy() != want).any(axis=-1).mean() < 3e-3
+        assert (mask[k].cpu().numpy() != want_mask).mean() < 3e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# script front ends, end to end on small FFV1 clips
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def clip_files(tmp_path_factory):
+    d = tmp_path_factory.mktemp("clip")
+    w, h, n = 128, 72, 7
+    depth, colour = SyntheticClip(w, h, n, zero_fraction=0.005).frames()
+    video_io.write_clip(str(d / "depth.mkv"), depth, 24.0)
+    video_io.write_clip(str(d / "colour.mkv"), colour, 24.0)
+    return dict(dir=d, depth=depth, colour=colour, w=w, h=h, n=n, depth_path=str(d / "depth.mkv"), colour_path=str(d / "colour.mkv"))
+
+
+def test_cli_stereo_rerender_default_and_mask(clip_files):
+    import stereo_rerender
+
+    c = clip_files
+    rc = stereo_rerender.main(["--depth_video", c["depth_path"], "--color_video", c["colour_path"], "--xfov", "60", "--infill_mask",
+                               "--green_and_black_infill_mask", "--chunk_frames", "3"])
+    assert rc == 0
+    out = video_io.read_clip(c["depth_path"] + "_stereo.mkv")
+    msk = video_io.read_clip(c["depth_path"] + "_stereo.mkv_infillmask.mkv")
+    assert out.shape == (c["n"], c["h"], 2 * c["w"], 3) and msk.shape == out.shape
+    assert not os.path.exists(c["depth_path"] + "_tmp_stereo.mkv")
+    consts = ops.stereo_frame_constants(60.0, c["w"], 100, 63, 45.0)
+    for k in range(c["n"]):
+        want_sbs, want_mask, _ = km.stereo_rows_f32(c["depth"][k], c["colour"][k], consts, (0, 255, 0), (0, 0, 0), True)
+        assert np.array_equal(out[k], want_sbs) and np.array_equal(msk[k], orc.mask_to_rgb(want_mask)), k
+        ref_sbs, _, _ = orc.stereo_frame(c["depth"][k], c["colour"][k], 60.0, infill_mask=True)
+        assert (out[k] != ref_sbs).any(axis=-1).mean() < 2e-3
+
+
+def test_cli_stereo_rerender_convergence_pose_and_max_frames(clip_files, tmp_path):
+    import stereo_rerender
+
+    c = clip_files
+    conv = [4.0, float("nan"), 5.0, 6.0, 5.5, 5.0, 4.5]
+    T = np.tile(np.eye(4), (c["n"], 1, 1))
+    T[:, 0, 3] = np.linspace(0, 0.05, c["n"])
+    json.dump(conv, open(tmp_path / "conv.json", "w"))
+    json.dump(T.tolist(), open(tmp_path / "pose.json", "w"))
+    json.dump([60.0 + k for k in range(c["n"])], open(tmp_path / "xfov.json", "w"))
+    rc = stereo_rerender.main(["--depth_video", c["depth_path"], "--color_video", c["colour_path"], "--xfov_file", str(tmp_path / "xfov.json"),
+                               "--convergence_file", str(tmp_path / "conv.json"), "--transformation_file", str(tmp_path / "pose.json"),
+                               "--max_frames", "4"])
+    assert rc == 0
+    out = video_io.read_clip(c["depth_path"] + "_stereo.mkv")
+    assert out.shape[0] == 4
+    smooth = orc.smooth_convergence(orc.fill_nan_with_closest(conv))
+    for k in range(4):
+        ref, _, _ = orc.stereo_frame(c["depth"][k], c["colour"][k], 60.0 + k, convergence_depth=smooth[k], transform=T[k], infill_mask=False)
+        assert (out[k] != ref).any(axis=-1).mean() < 3e-3, k
+
+
+def test_cli_find_convergence_convert_and_view(clip_files, tmp_path):
+    import importlib
+
+    c = clip_files
+    fcd = importlib.import_module("find_convergence_depth")
+    assert fcd.main(["--depth_video", c["depth_path"]]) == 0
+    got = json.load(open(c["depth_path"] + "_convergence_depths.json"))
+    want = [orc.convergence_depth_of_frame(c["depth"][k]) for k in range(c["n"])]
+    np.testing.assert_allclose(got, want, rtol=2e-6)
+
+    conv = importlib.import_module("convert_metric_depth_video_to_other_format")
+    ply_dir = tmp_path / "ply"
+    assert conv.main(["--depth_video", c["depth_path"], "--color_video", c["colour_path"], "--xfov", "60", "--save_ply", str(ply_dir),
+                      "--max_frames", "1", "--bit8"]) == 0
+    files = sorted(os.listdir(ply_dir))
+    assert files == ["0000000.ply", "0000001.ply", "0000002.ply"]  # the reference's loop converts max_frames + 2 frames (:763)
+    for k, f in enumerate(files):
+        xyz, rgb = orc.read_ply(str(ply_dir / f))
+        want_xyz, want_rgb = orc.ply_points_of_frame(c["depth"][k], c["colour"][k], 60.0)
+        assert np.array_equal(xyz.view(np.uint64), want_xyz.view(np.uint64)) and np.array_equal(rgb, want_rgb)
+    grey = video_io.read_clip(c["depth_path"] + "_grey_depth.mkv")
+    d2 = orc.decode_rgb_depth_frame(c["depth"][0], 100, True, "D2")
+    assert np.array_equal(grey[0][..., 0], np.rint(d2 * (255 / 100)).astype(np.uint8))
+
+    view = importlib.import_module("3d_view_depthfile")
+    assert view.main(["--depth_video", c["depth_path"], "--color_video", c["colour_path"], "--xfov", "60", "--render", "--max_frames", "2"]) == 0
+    out = video_io.read_clip(c["depth_path"] + "_render.mkv")
+    assert out.shape == (2, c["h"], c["w"], 3)
+    for k in range(2):
+        want, _, _, _ = orc.novel_view_frame(c["depth"][k], c["colour"][k], 60, center_of_by_one=True)
+        assert (out[k] != want).any(axis=-1).mean() < 3e-3

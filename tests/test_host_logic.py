@@ -1,0 +1,167 @@
+"""CPU: host-side logic of the drop-in surface -- command-line parity with the reference scripts (flag
+metadata extracted from the reference into tests/golden/cli_flags.json), frame sharding and the parameter
+broadcast over a world_size-2 gloo group, and the threaded clip reader / writer."""
+import json
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from metric_depth_video_toolbox_b200 import sharding
+from metric_depth_video_toolbox_b200.stereo import StereoParams, StereoRerenderer
+
+TYPES = {"int": int, "float": float, "str": str, None: None}
+
+
+def _parsers():
+    from metric_depth_video_toolbox_b200.cli import convert_format, find_convergence_depth, stereo_rerender, view_depthfile
+
+    return {"stereo_rerender.py": stereo_rerender.build_parser(), "3d_view_depthfile.py": view_depthfile.build_parser(),
+            "convert_metric_depth_video_to_other_format.py": convert_format.build_parser(),
+            "find_convergence_depth.py": find_convergence_depth.build_parser()}
+
+
+def test_cli_flags_match_reference(golden_dir):
+    golden = json.load(open(os.path.join(golden_dir, "cli_flags.json")))
+    parsers = _parsers()
+    assert set(parsers) == set(golden)
+    for script, flags in golden.items():
+        actions = {a.option_strings[0]: a for a in parsers[script]._actions if a.option_strings}
+        for flag, spec in flags.items():
+            assert flag in actions, f"{script}: {flag} missing"
+            a = actions[flag]
+            if spec["action"] == "store_true":
+                assert a.nargs == 0 and a.const is True and a.default is False, (script, flag)
+            else:
+                assert a.type is TYPES[spec["type"]], (script, flag, a.type)
+                assert a.default == spec["default"] and type(a.default) is type(spec["default"]), (script, flag, a.default)
+            assert bool(a.required) == bool(spec["required"]), (script, flag)
+
+
+def test_root_launchers_exist_with_reference_names():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for name in ("stereo_rerender.py", "3d_view_depthfile.py", "convert_metric_depth_video_to_other_format.py", "find_convergence_depth.py",
+                 "depth_frames_helper.py", "depth_map_tools.py"):
+        assert os.path.isfile(os.path.join(root, name)), name
+
+
+def test_stereo_rerender_validation_errors(tmp_path):
+    from metric_depth_video_toolbox_b200.cli import stereo_rerender as sr
+
+    with pytest.raises(ValueError, match="Either --xfov_file, --xfov or --yfov"):
+        sr.main(["--depth_video", "nope.mkv"])
+    with pytest.raises(ValueError, match="not compatible"):
+        sr.main(["--depth_video", "nope.mkv", "--xfov", "60", "--green_and_black_infill_mask", "--do_basic_infill"])
+    with pytest.raises(FileNotFoundError, match="Depth video not found"):
+        sr.main(["--depth_video", str(tmp_path / "nope.mkv"), "--xfov", "60"])
+    args = sr.build_parser().parse_args(["--depth_video", "a.mkv", "--xfov", "60"])
+    assert sr.output_names(args) == ("a.mkv_stereo.mkv", "a.mkv_tmp_stereo.mkv", "FFV1")
+    args = sr.build_parser().parse_args(["--depth_video", "a.mkv", "--xfov", "60", "--touchly1", "--compressed"])
+    assert sr.output_names(args) == ("a.mkv_Touchly1.mp4", "a.mkv_tmp_Touchly1.mp4", "avc1")
+
+
+# ---------------------------------------------------------------------------------------------
+# sharding
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,world", [(0, 1), (1, 8), (7, 8), (8, 8), (300, 1), (2400, 8), (2401, 4), (1000, 3)])
+def test_frame_ranges_partition_the_clip(n, world):
+    ranges = [sharding.frame_range(n, r, world) for r in range(world)]
+    assert ranges[0][0] == 0 and ranges[-1][1] == n
+    assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+    sizes = [b - a for a, b in ranges]
+    assert max(sizes) - min(sizes) <= 1 and sum(sizes) == n
+    with pytest.raises(ValueError):
+        sharding.frame_range(n, world, world)
+
+
+def _example_params(n):
+    rng = np.random.default_rng(3)
+    T = np.tile(np.eye(4), (n, 1, 1))
+    T[:, :3, 3] = rng.normal(size=(n, 3))
+    return StereoParams(1920, 1080, xfov=None, yfov=None, xfovs=list(rng.uniform(40, 80, n)), max_depth=100, pupillary_distance=63,
+                        master_xfov=45.0, convergence_depths=rng.uniform(1, 9, n), transformations=T, infill_mask=True, mask_rgb=True)
+
+
+def test_param_block_round_trip():
+    p = _example_params(11)
+    q, n = sharding.unpack_params(sharding.pack_params(p, 11))
+    assert n == 11 and q.width == 1920 and q.height == 1080 and q.xfov is None and q.yfov is None and q.mask_rgb and q.infill_mask
+    assert np.array_equal(q.xfovs, p.xfovs) and np.array_equal(q.convergence_depths, p.convergence_depths)
+    assert np.array_equal(q.transformations, p.transformations)
+    plain = StereoParams(640, 480, xfov=60.0, infill_mask=False)
+    q, n = sharding.unpack_params(sharding.pack_params(plain, 5))
+    assert (q.xfov, q.yfov, q.xfovs, q.convergence_depths, q.transformations, q.infill_mask) == (60.0, None, None, None, None, False)
+    with pytest.raises(ValueError, match="entries"):
+        sharding.pack_params(p, 12)
+    sub = sharding.shard_params(p, 3, 7)
+    assert len(sub.xfovs) == 4 and np.array_equal(sub.transformations, p.transformations[3:7])
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _gloo_worker(rank, world, port, n_frames, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        assert sharding.world() == (rank, world)
+        src = _example_params(n_frames) if rank == 0 else None
+        params, n = sharding.broadcast_params(src, n_frames if rank == 0 else 0)
+        start, stop = sharding.frame_range(n)
+        # each rank derives the per-frame constant block of its own shard (host-side part of the render)
+        consts = StereoRerenderer.__new__(StereoRerenderer)
+        consts.p = params
+        block = StereoRerenderer.frame_constants(consts, start, stop - start)
+        views = StereoRerenderer.views_of(consts, start)
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), start=start, stop=stop, block=block, M=views[0].M,
+                 conv=np.asarray(params.convergence_depths), n=n)
+        assert sharding.gather_counts(stop - start) == n
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_broadcast_and_shard(tmp_path):
+    n = 9
+    mp.spawn(_gloo_worker, args=(2, _free_port(), n, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = (np.load(tmp_path / f"rank{r}.npz") for r in range(2))
+    assert (int(r0["start"]), int(r0["stop"]), int(r1["start"]), int(r1["stop"])) == (0, 5, 5, 9)
+    assert int(r1["n"]) == n
+    whole = _example_params(n)
+    rr = StereoRerenderer.__new__(StereoRerenderer)
+    rr.p = whole
+    want = StereoRerenderer.frame_constants(rr, 0, n)
+    assert np.array_equal(np.concatenate([r0["block"], r1["block"]]), want)  # shards concatenate to the single-rank block
+    assert np.array_equal(r1["conv"], whole.convergence_depths)             # rank 1 received the whole smoothed list
+    assert np.array_equal(r1["M"], StereoRerenderer.views_of(rr, 5)[0].M)
+
+
+# ---------------------------------------------------------------------------------------------
+# clip reader / writer threads
+# ---------------------------------------------------------------------------------------------
+def test_chunk_reader_writer_round_trip(tmp_path):
+    from metric_depth_video_toolbox_b200 import video_io
+
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 256, (7, 32, 48, 3), dtype=np.uint8)
+    b = rng.integers(0, 256, (7, 32, 48, 3), dtype=np.uint8)
+    pa, pb = str(tmp_path / "a.mkv"), str(tmp_path / "b.mkv")
+    video_io.write_clip(pa, a, 24.0)
+    video_io.write_clip(pb, b, 24.0)
+    assert video_io.video_info(pa) == (48, 32, 24.0, 7)
+    assert np.array_equal(video_io.read_clip(pa), a)  # FFV1 is lossless
+    got_a, got_b = [], []
+    for n, (ca, cb, none) in video_io.ChunkReader([pa, pb, None], start=2, stop=7, chunk=2, pin=False):
+        assert none is None and ca.shape == (n, 32, 48, 3)
+        got_a.append(ca.numpy().copy())
+        got_b.append(cb.numpy().copy())
+    assert [len(x) for x in got_a] == [2, 2, 1]
+    assert np.array_equal(np.concatenate(got_a), a[2:]) and np.array_equal(np.concatenate(got_b), b[2:])
+    grey = [c[0].numpy().copy() for _, c in video_io.ChunkReader([pa], chunk=4, pin=False, grey=[True])]
+    assert np.concatenate(grey).shape == (7, 32, 48)
