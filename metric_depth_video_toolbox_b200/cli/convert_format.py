@@ -80,7 +80,7 @@ def main(argv: Optional[List[str]] = None) -> int:
 
     device = torch.device("cuda", torch.cuda.current_device())
     first = args.min_frames + 1 if args.min_frames != -1 else 0         # frames <= min_frames are skipped (:637-639)
-    last = total if args.max_frames == -1 else min(total, args.max_frames + 1)  # frame max_frames is still converted (:763)
+    last = total if args.max_frames == -1 else min(total, args.max_frames + 2)  # the loop breaks only after frame max_frames + 1 (:763-766)
     grey = None
     if args.bit16 or args.bit8:
         import cv2

@@ -322,7 +322,7 @@ def depth_sums(depth_src: torch.Tensor, max_depth=100, decoder: str = "D3", bit1
 
 def resolve(zbuf_view: torch.Tensor, colour: torch.Tensor, bg_rgb=(0, 0, 0), fill_rgb=(0, 0, 0), flags: int = 0,
             out_rgb: Optional[torch.Tensor] = None, out_mask: Optional[torch.Tensor] = None, want_depth: bool = False,
-            want_ids: bool = False):
+            want_ids: bool = False, want_mask: bool = True):
     """K3 for one view.  `out_rgb` (H, W, 3) / `out_mask` (H, W[, 3]) may be column slices of wider
     side-by-side tensors (row stride is passed through as the pitch)."""
     _need(zbuf_view, torch.int64, "zbuf_view")
@@ -332,9 +332,11 @@ def resolve(zbuf_view: torch.Tensor, colour: torch.Tensor, bg_rgb=(0, 0, 0), fil
     mask_bpp = 3 if flags & FLAG_MASK_RGB else 1
     if out_rgb is None:
         out_rgb = torch.empty((out_h, out_w, 3), dtype=torch.uint8, device=dev)
-    if out_mask is None:
+    if out_mask is None and want_mask:
         out_mask = torch.empty((out_h, out_w) + ((3,) if mask_bpp == 3 else ()), dtype=torch.uint8, device=dev)
     for t, bpp, name in ((out_rgb, 3, "out_rgb"), (out_mask, mask_bpp, "out_mask")):
+        if t is None:
+            continue
         if t.dtype != torch.uint8 or not t.is_cuda or t.shape[0] != out_h or t.shape[1] != out_w:
             raise ValueError(f"{name} has the wrong dtype / device / shape")
         inner_ok = (t.dim() == 2 and bpp == 1 and t.stride(1) == 1) or (t.dim() == 3 and t.shape[2] == bpp and t.stride(2) == 1 and t.stride(1) == bpp)
@@ -343,7 +345,8 @@ def resolve(zbuf_view: torch.Tensor, colour: torch.Tensor, bg_rgb=(0, 0, 0), fil
     depth = torch.empty((out_h, out_w), dtype=torch.float32, device=dev) if want_depth else None
     ids = torch.empty((out_h, out_w), dtype=torch.int32, device=dev) if want_ids else None
     _lib.check(_lib.load().mdvt_resolve(_ptr(zbuf_view), _ptr(colour), out_w, out_h, pack_rgb(bg_rgb), pack_rgb(fill_rgb), flags,
-                                        _ptr(out_rgb), out_rgb.stride(0), _ptr(out_mask), out_mask.stride(0), _ptr(depth), _ptr(ids),
+                                        _ptr(out_rgb), out_rgb.stride(0), _ptr(out_mask), 0 if out_mask is None else out_mask.stride(0),
+                                        _ptr(depth), _ptr(ids),
                                         _stream()))
     return out_rgb, out_mask, depth, ids
 

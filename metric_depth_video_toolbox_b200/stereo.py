@@ -121,7 +121,6 @@ class StereoRerenderer:
         zbuf = self._zbufs.get(zkey)
         if zbuf is None or tuple(zbuf.shape) != (2, h, w) or zbuf.device != depth_rgb.device:
             zbuf = self._zbufs[zkey] = ops.new_zbuf(2, w, h, depth_rgb.device)
-        scratch_mask = None
         for k in range(n):
             f = start_frame + k
             xf = p.xfov_of(f)
@@ -129,14 +128,9 @@ class StereoRerenderer:
             src = ops.make_source(w, h, K, p.max_depth, "D1", True, geo.master_fov_depth_scale(p.master_xfov, xf), False)
             ops.project_splat(depth_rgb[k], src, self.views_of(f), w, h, zbuf, p.near)
             for e in range(2):
-                if out_mask is not None:
-                    m = out_mask[k, :, e * w:(e + 1) * w]
-                else:
-                    if scratch_mask is None:
-                        scratch_mask = torch.empty((h, w), dtype=torch.uint8, device=depth_rgb.device)
-                    m = scratch_mask
+                m = None if out_mask is None else out_mask[k, :, e * w:(e + 1) * w]
                 ops.resolve(zbuf[e], colour[k], p.bg_rgb, (0, 0, 0), flags | ops.FLAG_RESET_ZBUF,
-                            out_rgb=out_sbs[k, :, e * w:(e + 1) * w], out_mask=m)
+                            out_rgb=out_sbs[k, :, e * w:(e + 1) * w], out_mask=m, want_mask=False)
         return out_sbs, out_mask
 
     # ---- host arrays, pipelined -----------------------------------------------------------------------
