@@ -327,3 +327,37 @@ def test_cli_find_convergence_convert_and_view(clip_files, tmp_path):
     for k in range(2):
         want, _, _, _ = orc.novel_view_frame(c["depth"][k], c["colour"][k], 60, center_of_by_one=True)
         assert (out[k] != want).any(axis=-1).mean() < 3e-3
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_cli_stereo_rerender_torchrun_two_ranks(clip_files, tmp_path):
+    """Frames sharded over two ranks (NCCL broadcast of the parameter block, per-rank segments joined by rank 0)
+    give the same file as the single-process run."""
+    import shutil
+    import subprocess
+    import sys
+
+    c = clip_files
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    work = tmp_path / "mg"
+    work.mkdir()
+    for name in ("depth.mkv", "colour.mkv"):
+        shutil.copy(c["dir"] / name, work / name)
+    conv = [4.0, 4.5, 5.0, 6.0, 5.5, 5.0, 4.5]
+    json.dump(conv, open(work / "conv.json", "w"))
+    base = ["--depth_video", str(work / "depth.mkv"), "--color_video", str(work / "colour.mkv"), "--xfov", "60", "--infill_mask",
+            "--green_and_black_infill_mask", "--convergence_file", str(work / "conv.json")]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port",
+           "29517", os.path.join(root, "stereo_rerender.py")] + base
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    sharded = video_io.read_clip(str(work / "depth.mkv") + "_stereo.mkv")
+    sharded_mask = video_io.read_clip(str(work / "depth.mkv") + "_stereo.mkv_infillmask.mkv")
+    assert not [f for f in os.listdir(work) if ".rank" in f]
+    import stereo_rerender
+
+    assert stereo_rerender.main(base) == 0
+    single = video_io.read_clip(str(work / "depth.mkv") + "_stereo.mkv")
+    assert sharded.shape == single.shape == (c["n"], c["h"], 2 * c["w"], 3)
+    assert np.array_equal(sharded, single)
+    assert np.array_equal(sharded_mask, video_io.read_clip(str(work / "depth.mkv") + "_stereo.mkv_infillmask.mkv"))
