@@ -82,13 +82,14 @@ def stereo_rows_f32(depth_rgb, colour, consts, bg_rgb=(0, 0, 0), fill_rgb=(0, 0,
     z = ((c16 << 16).astype(f32) * dec) * scale
     with np.errstate(divide="ignore"):
         d = fxs / z
-    col = np.broadcast_to(np.arange(w, dtype=f32), (h, w))
+    # target column = round-half-even of the EXACT sum j +- d, rounded once (the kernels add d to the exactly
+    # representable 1.5*2^23 + j, whose float32 ulp is 1); float64 holds j + d exactly whenever it can tie
+    col = np.broadcast_to(np.arange(w, dtype=np.float64), (h, w))
     row = np.broadcast_to(np.arange(h, dtype=np.float64)[:, None], (h, w)).reshape(-1)
     outs = []
     for sign in (+1, -1):
-        u = (col + d) if sign > 0 else (col - d)
-        assert u.dtype == f32
-        ids = orc.splat_ids(u.reshape(-1).astype(np.float64), row, z.reshape(-1).astype(np.float64), w, h, float(near))
+        u = col + sign * d.astype(np.float64)
+        ids = orc.splat_ids(u.reshape(-1), row, z.reshape(-1).astype(np.float64), w, h, float(near))
         img, mask = orc.resolve(ids, colour, bg_rgb, fill_rgb, bg_collide)
         outs.append((img, mask, ids))
     sbs = np.concatenate([outs[0][0], outs[1][0]], axis=1)
