@@ -313,7 +313,7 @@ def run_ours(args):
     traffic = ncu_traffic_per_frame()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (traffic["dram_bytes_per_frame"] * n_frames) if traffic else None,
-                "kernel": "mdvt::stereo_rows_w32_kernel<1,true>", "algorithmic_bytes_per_launch": algorithmic,
+                "kernel": "mdvt::stereo_rows_w32_kernel<1,true,160,4>", "algorithmic_bytes_per_launch": algorithmic,
                 "launch_ms": mean_launch_ms, "peak_source": peak_kind,
                 "traffic_source": traffic.get("source") if traffic else None}
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),

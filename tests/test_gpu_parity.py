@@ -294,3 +294,31 @@ def test_full_size_properties_1080p():
         assert all(tuple(px) in row_cols for px in out[r][drawn][::37])
     hole_frac = (mask == 255).float().mean().item()
     assert 0.001 < hole_frac < 0.2
+
+
+@pytest.mark.parametrize("threads", ["128", "160", "256"])
+def test_stereo_rows_every_cta_size_gives_identical_bytes(threads):
+    """The fast kernel is instantiated for several CTA sizes (MDVT_ROW_THREADS); each must reproduce the model
+    bit for bit.  The choice is read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+
+    code = (
+        "import numpy as np, torch, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "from metric_depth_video_toolbox_b200 import ops\n"
+        "from metric_depth_video_toolbox_b200.synth import SyntheticClip\n"
+        "from oracle import kernel_model as km\n"
+        "for w, h in ((1920, 6), (640, 9), (96, 5), (3840, 3)):\n"
+        "    d, c = SyntheticClip(w, h, 2, zero_fraction=0.01).frames()\n"
+        "    c[:, 1, 2] = (0, 255, 0)\n"
+        "    k = ops.stereo_frame_constants(60.0, w, 100, 63, 45.0)\n"
+        "    sbs, m = ops.stereo_rows(torch.from_numpy(d).cuda(), torch.from_numpy(c).cuda(), torch.from_numpy(k[None]).cuda(), (0, 255, 0), (0, 0, 0), ops.FLAG_BG_COLLIDE)\n"
+        "    for f in range(2):\n"
+        "        ws, wm, _ = km.stereo_rows_f32(d[f], c[f], k, (0, 255, 0), (0, 0, 0), True)\n"
+        "        assert np.array_equal(sbs[f].cpu().numpy(), ws) and np.array_equal(m[f].cpu().numpy(), wm), (w, h, f)\n"
+        "print('ok')\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MDVT_ROW_THREADS=threads)
+    proc = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert proc.returncode == 0 and "ok" in proc.stdout, proc.stderr[-2000:]
