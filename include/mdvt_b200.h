@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MDVT_ABI_VERSION 2
+#define MDVT_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define MDVT_API __attribute__((visibility("default")))
@@ -184,11 +184,31 @@ MDVT_API int mdvt_splat_points(const float *xyz, int64_t n_points, const mdvt_vi
 /* K3.  zbuf (one view, out_w*out_h) + source colours -> image / hole mask / depth plane.
  * out_rgb: row r starts at out_rgb + r*rgb_pitch (bytes), so a view can be written straight into its
  * half of a side-by-side frame (cv2.hconcat, stereo_rerender.py:918); same for out_mask / mask_pitch.
- * out_depth (f32, dense out_w*out_h; 0 where nothing was drawn), out_ids (int32, -1 = hole) optional.
+ * out_depth (f32, row r at out_depth + r*depth_pitch floats, depth_pitch 0 = out_w; 0 where nothing was drawn --
+ * the `left_depth` / `right_depth` planes of stereo_rerender.py:738,852), out_ids (int32, dense, -1 = hole) optional.
  * bg_rgb / fill_rgb: 0x00BBGGRR packed (R in the low byte). */
 MDVT_API int mdvt_resolve(uint64_t *zbuf, const uint8_t *colour_rgb, int out_w, int out_h, uint32_t bg_rgb,
                  uint32_t fill_rgb, uint32_t flags, uint8_t *out_rgb, int64_t rgb_pitch, uint8_t *out_mask,
-                 int64_t mask_pitch, float *out_depth, int32_t *out_ids, void *stream);
+                 int64_t mask_pitch, float *out_depth, int64_t depth_pitch, int32_t *out_ids, void *stream);
+
+/* Where the per-frame, per-view planes of mdvt_render_views go: plane (frame f, view v) starts at
+ * base + f*frame_stride + v*view_stride, its row r at + r*row_pitch (all in BYTES).  A side-by-side stereo
+ * frame (cv2.hconcat, stereo_rerender.py:918) is {frame_stride = H*2W*3, view_stride = W*3, row_pitch = 2W*3}. */
+typedef struct mdvt_plane_layout {
+    void *base;
+    int64_t frame_stride, view_stride, row_pitch;
+} mdvt_plane_layout;
+
+/* The generic frame loop in one call (stereo_rerender.py:471-941 with a pose file / convergence rotation;
+ * 3d_view_depthfile.py:133-255): for each of n_frames frames, K1+K2 of all n_views cameras
+ * (views_host[f*n_views + v]) into `zbuf` (n_views planes, left empty again), then K3 per view into the planes
+ * described by rgb_out / mask_out (optional) / depth_out (optional, f32).  sources_host: one mdvt_source per
+ * frame (per_frame_source = 1) or one for all.  depth_src / colour_rgb: frame f at + f*frame_stride bytes. */
+MDVT_API int mdvt_render_views(const void *depth_src, int64_t depth_frame_stride, const uint8_t *colour_rgb,
+                      int64_t colour_frame_stride, int n_frames, const mdvt_source *sources_host, int per_frame_source,
+                      const mdvt_view *views_host, int n_views, float near_plane, int out_w, int out_h, uint64_t *zbuf,
+                      uint32_t bg_rgb, uint32_t fill_rgb, uint32_t flags, const mdvt_plane_layout *rgb_out,
+                      const mdvt_plane_layout *mask_out, const mdvt_plane_layout *depth_out, void *stream);
 
 /* ---- per-frame reductions (fixed summation order: reproducible) -------------------------------- */
 /* Result buffers hold 4 doubles of result followed by MDVT_REDUCE_SCRATCH_DOUBLES doubles of scratch. */

@@ -18,7 +18,7 @@ DECODERS = {"D1": DECODE_D1, "D2": DECODE_D2, "D3": DECODE_D3, "F32": SOURCE_F32
 REDUCE_SCRATCH_DOUBLES = 4096
 FLAG_BG_COLLIDE, FLAG_RESET_ZBUF, FLAG_MASK_RGB, FLAG_ANYWIDTH = 0x1, 0x2, 0x4, 0x8
 ZBUF_EMPTY = 0xFFFFFFFFFFFFFFFF
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class MdvtError(RuntimeError):
@@ -38,6 +38,11 @@ class Source(C.Structure):
 class View(C.Structure):
     """mdvt_view"""
     _fields_ = [("M", C.c_float * 12), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float)]
+
+
+class PlaneLayout(C.Structure):
+    """mdvt_plane_layout (strides in bytes)"""
+    _fields_ = [("base", C.c_void_p), ("frame_stride", C.c_int64), ("view_stride", C.c_int64), ("row_pitch", C.c_int64)]
 
 
 class StereoFrame(C.Structure):
@@ -73,7 +78,10 @@ _PROTOTYPES = {
     "mdvt_centroid": (C.c_int, [_u8p, C.POINTER(Source), C.POINTER(C.c_double), C.POINTER(C.c_double), _f64p, _stream]),
     "mdvt_depth_sum": (C.c_int, [_u8p, C.c_int64, C.c_int, C.c_int, C.c_float, _u8p, C.c_int, _f64p, _stream]),
     "mdvt_resolve": (C.c_int, [_u64p, _u8p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, _u8p, C.c_int64,
-                               _u8p, C.c_int64, _f32p, _i32p, _stream]),
+                               _u8p, C.c_int64, _f32p, C.c_int64, _i32p, _stream]),
+    "mdvt_render_views": (C.c_int, [_u8p, C.c_int64, _u8p, C.c_int64, C.c_int, C.POINTER(Source), C.c_int, C.POINTER(View), C.c_int,
+                                    C.c_float, C.c_int, C.c_int, _u64p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PlaneLayout),
+                                    C.POINTER(PlaneLayout), C.POINTER(PlaneLayout), _stream]),
     "mdvt_stereo_rows": (C.c_int, [_u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32,
                                    C.c_uint32, _u8p, _u8p, _stream]),
 }

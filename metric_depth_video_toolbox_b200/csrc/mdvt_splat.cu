@@ -98,7 +98,7 @@ template <int VEC>
 __global__ void __launch_bounds__(kThreads)
     resolve_kernel(unsigned long long *__restrict__ zbuf, const uint8_t *__restrict__ colour, int out_w, int out_h, uint32_t bg_rgb,
                    uint32_t fill_rgb, uint32_t flags, uint8_t *__restrict__ out_rgb, int64_t rgb_pitch, uint8_t *__restrict__ out_mask,
-                   int64_t mask_pitch, float *__restrict__ out_depth, int32_t *__restrict__ out_ids) {
+                   int64_t mask_pitch, float *__restrict__ out_depth, int64_t depth_pitch, int32_t *__restrict__ out_ids) {
     const int groups_per_row = out_w / VEC;
     const int64_t n_groups = (int64_t)groups_per_row * out_h;
     const bool collide = flags & MDVT_FLAG_BG_COLLIDE, reset = flags & MDVT_FLAG_RESET_ZBUF, mask_rgb = flags & MDVT_FLAG_MASK_RGB;
@@ -125,7 +125,8 @@ __global__ void __launch_bounds__(kThreads)
             }
             px[k] = c;
             mk[k] = hole ? 1u : 0u;
-            if (out_depth) out_depth[t0 + k] = (key[k] == MDVT_ZBUF_EMPTY) ? 0.0f : __uint_as_float((uint32_t)(key[k] >> 32));
+            if (out_depth)
+                out_depth[row * depth_pitch + col0 + k] = (key[k] == MDVT_ZBUF_EMPTY) ? 0.0f : __uint_as_float((uint32_t)(key[k] >> 32));
             if (out_ids) out_ids[t0 + k] = (key[k] == MDVT_ZBUF_EMPTY) ? -1 : (int32_t)(uint32_t)key[k];
         }
         if (reset) {
@@ -195,6 +196,9 @@ extern "C" int mdvt_zbuf_clear(uint64_t *zbuf, int64_t n_slots, void *stream) {
     return MDVT_OK;
 }
 
+static int launch_project_splat(const void *depth_src, const mdvt_source *src, const ViewPack &pack, float near_plane, int out_w, int out_h,
+                                uint32_t id_offset, unsigned long long *zb, float *out_uvz, cudaStream_t st);
+
 static int pack_views(const mdvt_view *views_host, int n_views, ViewPack &pack) {
     MDVT_REQUIRE(n_views >= 1 && n_views <= kMaxViews, "n_views must be 1..%d", kMaxViews);
     MDVT_REQUIRE(views_host != nullptr, "views is NULL");
@@ -211,19 +215,9 @@ extern "C" int mdvt_project_splat(const void *depth_src, const mdvt_source *src,
     if (int rc = pack_views(views_host, n_views, pack)) return rc;
     MDVT_REQUIRE(depth_src && zbuf, "NULL buffer");
     MDVT_REQUIRE(out_w > 0 && out_h > 0, "bad output size %dx%d", out_w, out_h);
-    const int64_t n = (int64_t)src->width * src->height;
-    MDVT_REQUIRE(n + id_offset <= 0xFFFFFFFFll, "source index does not fit the 32-bit z-buffer payload");
-    SourceCam cam{src->fx, src->fy, src->cx, src->cy, src->grid_sx, src->grid_sy};
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    unsigned long long *zb = reinterpret_cast<unsigned long long *>(zbuf);
-    const int grid = grid_for(n);
-#define CALL(D, B)                                                                                                          \
-    project_splat_kernel<D, B><<<grid, kThreads, 0, st>>>(depth_src, src->width, n, src->dec_const, src->depth_scale, cam, pack, \
-                                                          near_plane, out_w, out_h, id_offset, zb, out_uvz)
-    MDVT_DISPATCH_SOURCE(src->decoder, src->bit16, CALL);
-#undef CALL
-    MDVT_CUDA_TRY(cudaGetLastError());
-    return MDVT_OK;
+    MDVT_REQUIRE((int64_t)src->width * src->height + id_offset <= 0xFFFFFFFFll, "source index does not fit the 32-bit z-buffer payload");
+    return launch_project_splat(depth_src, src, pack, near_plane, out_w, out_h, id_offset, reinterpret_cast<unsigned long long *>(zbuf), out_uvz,
+                                static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mdvt_splat_points(const float *xyz, int64_t n_points, const mdvt_view *views_host, int n_views, float near_plane,
@@ -241,28 +235,85 @@ extern "C" int mdvt_splat_points(const float *xyz, int64_t n_points, const mdvt_
     return MDVT_OK;
 }
 
-extern "C" int mdvt_resolve(uint64_t *zbuf, const uint8_t *colour_rgb, int out_w, int out_h, uint32_t bg_rgb, uint32_t fill_rgb,
-                            uint32_t flags, uint8_t *out_rgb, int64_t rgb_pitch, uint8_t *out_mask, int64_t mask_pitch,
-                            float *out_depth, int32_t *out_ids, void *stream) {
-    MDVT_REQUIRE(zbuf && colour_rgb, "NULL buffer");
-    MDVT_REQUIRE(out_w > 0 && out_h > 0, "bad output size %dx%d", out_w, out_h);
+static int launch_resolve(unsigned long long *zb, const uint8_t *colour_rgb, int out_w, int out_h, uint32_t bg_rgb, uint32_t fill_rgb,
+                          uint32_t flags, uint8_t *out_rgb, int64_t rgb_pitch, uint8_t *out_mask, int64_t mask_pitch, float *out_depth,
+                          int64_t depth_pitch, int32_t *out_ids, cudaStream_t st) {
     const int mask_bpp = (flags & MDVT_FLAG_MASK_RGB) ? 3 : 1;
     MDVT_REQUIRE(!out_rgb || rgb_pitch >= (int64_t)out_w * 3, "rgb_pitch %lld too small", (long long)rgb_pitch);
     MDVT_REQUIRE(!out_mask || mask_pitch >= (int64_t)out_w * mask_bpp, "mask_pitch %lld too small", (long long)mask_pitch);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    unsigned long long *zb = reinterpret_cast<unsigned long long *>(zbuf);
-    const bool vec4 = (out_w % 4 == 0) && (reinterpret_cast<uintptr_t>(zbuf) % 16 == 0) &&
+    if (depth_pitch == 0) depth_pitch = out_w;
+    MDVT_REQUIRE(!out_depth || depth_pitch >= out_w, "depth_pitch %lld too small", (long long)depth_pitch);
+    const bool vec4 = (out_w % 4 == 0) && (reinterpret_cast<uintptr_t>(zb) % 16 == 0) &&
                       (!out_rgb || (reinterpret_cast<uintptr_t>(out_rgb) % 4 == 0 && rgb_pitch % 4 == 0)) &&
                       (!out_mask || (reinterpret_cast<uintptr_t>(out_mask) % 4 == 0 && mask_pitch % 4 == 0));
     bg_rgb &= 0xFFFFFF;
     fill_rgb &= 0xFFFFFF;
     if (vec4) {
         resolve_kernel<4><<<grid_for((int64_t)out_w / 4 * out_h), kThreads, 0, st>>>(
-            zb, colour_rgb, out_w, out_h, bg_rgb, fill_rgb, flags, out_rgb, rgb_pitch, out_mask, mask_pitch, out_depth, out_ids);
+            zb, colour_rgb, out_w, out_h, bg_rgb, fill_rgb, flags, out_rgb, rgb_pitch, out_mask, mask_pitch, out_depth, depth_pitch, out_ids);
     } else {
         resolve_kernel<1><<<grid_for((int64_t)out_w * out_h), kThreads, 0, st>>>(
-            zb, colour_rgb, out_w, out_h, bg_rgb, fill_rgb, flags, out_rgb, rgb_pitch, out_mask, mask_pitch, out_depth, out_ids);
+            zb, colour_rgb, out_w, out_h, bg_rgb, fill_rgb, flags, out_rgb, rgb_pitch, out_mask, mask_pitch, out_depth, depth_pitch, out_ids);
     }
     MDVT_CUDA_TRY(cudaGetLastError());
+    return MDVT_OK;
+}
+
+static int launch_project_splat(const void *depth_src, const mdvt_source *src, const ViewPack &pack, float near_plane, int out_w, int out_h,
+                                uint32_t id_offset, unsigned long long *zb, float *out_uvz, cudaStream_t st) {
+    const int64_t n = (int64_t)src->width * src->height;
+    SourceCam cam{src->fx, src->fy, src->cx, src->cy, src->grid_sx, src->grid_sy};
+    const int grid = grid_for(n);
+#define CALL(D, B)                                                                                                          \
+    project_splat_kernel<D, B><<<grid, kThreads, 0, st>>>(depth_src, src->width, n, src->dec_const, src->depth_scale, cam, pack, \
+                                                          near_plane, out_w, out_h, id_offset, zb, out_uvz)
+    MDVT_DISPATCH_SOURCE(src->decoder, src->bit16, CALL);
+#undef CALL
+    MDVT_CUDA_TRY(cudaGetLastError());
+    return MDVT_OK;
+}
+
+extern "C" int mdvt_resolve(uint64_t *zbuf, const uint8_t *colour_rgb, int out_w, int out_h, uint32_t bg_rgb, uint32_t fill_rgb,
+                            uint32_t flags, uint8_t *out_rgb, int64_t rgb_pitch, uint8_t *out_mask, int64_t mask_pitch,
+                            float *out_depth, int64_t depth_pitch, int32_t *out_ids, void *stream) {
+    MDVT_REQUIRE(zbuf && colour_rgb, "NULL buffer");
+    MDVT_REQUIRE(out_w > 0 && out_h > 0, "bad output size %dx%d", out_w, out_h);
+    return launch_resolve(reinterpret_cast<unsigned long long *>(zbuf), colour_rgb, out_w, out_h, bg_rgb, fill_rgb, flags, out_rgb, rgb_pitch,
+                          out_mask, mask_pitch, out_depth, depth_pitch, out_ids, static_cast<cudaStream_t>(stream));
+}
+
+// Frame loop of the generic path in one call: per frame K1+K2 for all views, then K3 per view.
+extern "C" int mdvt_render_views(const void *depth_src, int64_t depth_frame_stride, const uint8_t *colour_rgb, int64_t colour_frame_stride,
+                                 int n_frames, const mdvt_source *sources_host, int per_frame_source, const mdvt_view *views_host,
+                                 int n_views, float near_plane, int out_w, int out_h, uint64_t *zbuf, uint32_t bg_rgb, uint32_t fill_rgb,
+                                 uint32_t flags, const mdvt_plane_layout *rgb_out, const mdvt_plane_layout *mask_out,
+                                 const mdvt_plane_layout *depth_out, void *stream) {
+    MDVT_REQUIRE(n_frames >= 0, "negative frame count");
+    MDVT_REQUIRE(n_views >= 1 && n_views <= kMaxViews, "n_views must be 1..%d", kMaxViews);
+    MDVT_REQUIRE(out_w > 0 && out_h > 0, "bad output size %dx%d", out_w, out_h);
+    if (n_frames == 0) return MDVT_OK;
+    MDVT_REQUIRE(depth_src && colour_rgb && sources_host && views_host && zbuf && rgb_out && rgb_out->base, "NULL buffer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned long long *zb = reinterpret_cast<unsigned long long *>(zbuf);
+    const int64_t out_n = (int64_t)out_w * out_h;
+    for (int f = 0; f < n_frames; ++f) {
+        const mdvt_source *src = sources_host + (per_frame_source ? f : 0);
+        if (int rc = check_source(src)) return rc;
+        MDVT_REQUIRE((int64_t)src->width * src->height <= 0xFFFFFFFFll, "source frame has more than 2^32 pixels");
+        ViewPack pack{};
+        if (int rc = pack_views(views_host + (int64_t)f * n_views, n_views, pack)) return rc;
+        const uint8_t *dsrc = static_cast<const uint8_t *>(depth_src) + f * depth_frame_stride;
+        if (int rc = launch_project_splat(dsrc, src, pack, near_plane, out_w, out_h, 0, zb, nullptr, st)) return rc;
+        for (int v = 0; v < n_views; ++v) {
+            auto at = [&](const mdvt_plane_layout *L) -> uint8_t * {
+                return (L && L->base) ? static_cast<uint8_t *>(L->base) + f * L->frame_stride + v * L->view_stride : nullptr;
+            };
+            if (int rc = launch_resolve(zb + v * out_n, colour_rgb + f * colour_frame_stride, out_w, out_h, bg_rgb, fill_rgb,
+                                        flags | MDVT_FLAG_RESET_ZBUF, at(rgb_out), rgb_out->row_pitch, at(mask_out),
+                                        mask_out ? mask_out->row_pitch : 0, reinterpret_cast<float *>(at(depth_out)),
+                                        depth_out ? depth_out->row_pitch / 4 : 0, nullptr, st))
+                return rc;
+        }
+    }
     return MDVT_OK;
 }

@@ -92,9 +92,8 @@ class NovelViewRenderer:
             self._zbuf = ops.new_zbuf(1, w, h, dev)
         centres = self.centroids(depth_rgb, start_frame)
         src = ops.make_source(w, h, self.K, p.max_depth, "D1", True, 1.0, False)
-        for k in range(n):
-            ops.project_splat(depth_rgb[k], src, [self.view_of(start_frame + k, centres[k])], w, h, self._zbuf, p.near)
-            ops.resolve(self._zbuf[0], colour[k], p.bg_rgb, p.bg_rgb, ops.FLAG_RESET_ZBUF, out_rgb=out_rgb[k], out_mask=out_mask[k])
+        views = [[self.view_of(start_frame + k, centres[k])] for k in range(n)]
+        ops.render_views(depth_rgb, colour, [src], views, w, h, self._zbuf, out_rgb, out_mask, None, p.bg_rgb, p.bg_rgb, 0, p.near)
         return out_rgb, out_mask
 
     def render_host(self, depth_rgb, colour, out_rgb=None):

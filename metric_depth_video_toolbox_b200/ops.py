@@ -269,6 +269,53 @@ def project_splat(depth_rgb: torch.Tensor, source: _lib.Source, views: Sequence[
     return uvz
 
 
+def _plane_layout(t: Optional[torch.Tensor], n_frames: int, n_views: int, out_h: int, out_w: int, channels: int, name: str):
+    """mdvt_plane_layout of a (n, H, n_views*W[, C]) side-by-side tensor (or (n, H, W[, C]) for one view)."""
+    if t is None:
+        return None
+    want = (n_frames, out_h, n_views * out_w) + ((channels,) if channels > 1 else ())
+    if tuple(t.shape) != want or not t.is_cuda or not t.is_contiguous():
+        raise ValueError(f"{name} must be a contiguous CUDA tensor of shape {want}, got {tuple(t.shape)}")
+    es = t.element_size()
+    row = n_views * out_w * channels * es
+    return _lib.PlaneLayout(t.data_ptr(), out_h * row, out_w * channels * es, row)
+
+
+def render_views(depth_src: torch.Tensor, colour: torch.Tensor, sources: Sequence[_lib.Source], views: Sequence[Sequence[ViewSpec]],
+                 out_w: int, out_h: int, zbuf: torch.Tensor, out_rgb: torch.Tensor, out_mask: Optional[torch.Tensor] = None,
+                 out_depth: Optional[torch.Tensor] = None, bg_rgb=(0, 0, 0), fill_rgb=(0, 0, 0), flags: int = 0, near: float = NEAR_PLANE):
+    """The generic frame loop in ONE library call: frames (n, H, W, 3) u8 (or (n, H, W) f32 for F32 sources),
+    `sources` one per frame or a single one, `views[f]` the cameras of frame f (same count for every frame).
+    Views are laid side by side: out_rgb (n, out_h, n_views*out_w, 3) u8, out_mask (n, out_h, n_views*out_w[, 3]) u8,
+    out_depth (n, out_h, n_views*out_w) f32.  The z-buffer (n_views, out_h, out_w) must be empty and is left empty."""
+    n = depth_src.shape[0]
+    n_views = len(views[0])
+    if len(views) != n or any(len(v) != n_views for v in views):
+        raise ValueError("views must hold the same number of cameras for each of the n frames")
+    if len(sources) not in (1, n):
+        raise ValueError("sources must hold one entry or one per frame")
+    _need(colour, torch.uint8, "colour")
+    _need(zbuf, torch.int64, "zbuf")
+    if tuple(zbuf.shape) != (n_views, out_h, out_w):
+        raise ValueError(f"zbuf shape {tuple(zbuf.shape)} != ({n_views}, {out_h}, {out_w})")
+    for k, src in enumerate(sources):
+        _need_source(depth_src[k], src)
+    if colour.shape[0] != n or colour.shape[1] * colour.shape[2] != sources[0].width * sources[0].height:
+        raise ValueError("colour must hold one (H, W, 3) frame per depth frame")
+    mask_ch = 3 if flags & FLAG_MASK_RGB else 1
+    rgb_l = _plane_layout(_need(out_rgb, torch.uint8, "out_rgb"), n, n_views, out_h, out_w, 3, "out_rgb")
+    mask_l = _plane_layout(None if out_mask is None else _need(out_mask, torch.uint8, "out_mask"), n, n_views, out_h, out_w, mask_ch, "out_mask")
+    depth_l = _plane_layout(None if out_depth is None else _need(out_depth, torch.float32, "out_depth"), n, n_views, out_h, out_w, 1, "out_depth")
+    src_arr = (_lib.Source * len(sources))(*sources)
+    view_arr = (_lib.View * (n * n_views))(*[v.to_c() for fv in views for v in fv])
+    opt = lambda l: None if l is None else C.byref(l)  # noqa: E731
+    _lib.check(_lib.load().mdvt_render_views(_ptr(depth_src), depth_src.stride(0) * depth_src.element_size(), _ptr(colour),
+                                             colour.stride(0), n, src_arr, int(len(sources) == n and n > 1), view_arr, n_views,
+                                             float(np.float32(near)), int(out_w), int(out_h), _ptr(zbuf), pack_rgb(bg_rgb), pack_rgb(fill_rgb),
+                                             flags, C.byref(rgb_l), opt(mask_l), opt(depth_l), _stream()))
+    return out_rgb, out_mask, out_depth
+
+
 def splat_points(xyz: torch.Tensor, views: Sequence[ViewSpec], out_w: int, out_h: int, zbuf: torch.Tensor,
                  near: float = NEAR_PLANE, id_offset: int = 0):
     """Explicit (N, 3) float32 points through the same visibility rule (the reference's point painter)."""
@@ -322,7 +369,7 @@ def depth_sums(depth_src: torch.Tensor, max_depth=100, decoder: str = "D3", bit1
 
 def resolve(zbuf_view: torch.Tensor, colour: torch.Tensor, bg_rgb=(0, 0, 0), fill_rgb=(0, 0, 0), flags: int = 0,
             out_rgb: Optional[torch.Tensor] = None, out_mask: Optional[torch.Tensor] = None, want_depth: bool = False,
-            want_ids: bool = False, want_mask: bool = True):
+            want_ids: bool = False, want_mask: bool = True, out_depth: Optional[torch.Tensor] = None):
     """K3 for one view.  `out_rgb` (H, W, 3) / `out_mask` (H, W[, 3]) may be column slices of wider
     side-by-side tensors (row stride is passed through as the pitch)."""
     _need(zbuf_view, torch.int64, "zbuf_view")
@@ -342,11 +389,15 @@ def resolve(zbuf_view: torch.Tensor, colour: torch.Tensor, bg_rgb=(0, 0, 0), fil
         inner_ok = (t.dim() == 2 and bpp == 1 and t.stride(1) == 1) or (t.dim() == 3 and t.shape[2] == bpp and t.stride(2) == 1 and t.stride(1) == bpp)
         if not inner_ok:
             raise ValueError(f"{name} rows must be dense")
-    depth = torch.empty((out_h, out_w), dtype=torch.float32, device=dev) if want_depth else None
+    depth = out_depth
+    if depth is None and want_depth:
+        depth = torch.empty((out_h, out_w), dtype=torch.float32, device=dev)
+    if depth is not None and (depth.dtype != torch.float32 or not depth.is_cuda or tuple(depth.shape) != (out_h, out_w) or depth.stride(1) != 1):
+        raise ValueError("out_depth must be a (H, W) float32 CUDA view with dense rows")
     ids = torch.empty((out_h, out_w), dtype=torch.int32, device=dev) if want_ids else None
     _lib.check(_lib.load().mdvt_resolve(_ptr(zbuf_view), _ptr(colour), out_w, out_h, pack_rgb(bg_rgb), pack_rgb(fill_rgb), flags,
                                         _ptr(out_rgb), out_rgb.stride(0), _ptr(out_mask), 0 if out_mask is None else out_mask.stride(0),
-                                        _ptr(depth), _ptr(ids),
+                                        _ptr(depth), 0 if depth is None else depth.stride(0), _ptr(ids),
                                         _stream()))
     return out_rgb, out_mask, depth, ids
 

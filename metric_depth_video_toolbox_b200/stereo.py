@@ -102,8 +102,10 @@ class StereoRerenderer:
 
     # ---- device-resident ------------------------------------------------------------------------------
     def render_device(self, depth_rgb: torch.Tensor, colour: torch.Tensor, start_frame: int = 0,
-                      out_sbs: Optional[torch.Tensor] = None, out_mask: Optional[torch.Tensor] = None):
-        """depth_rgb / colour: (n, H, W, 3) u8 CUDA.  Returns (sbs (n, H, 2W, 3), mask (n, H, 2W[, 3]) or None)."""
+                      out_sbs: Optional[torch.Tensor] = None, out_mask: Optional[torch.Tensor] = None,
+                      out_depth: Optional[torch.Tensor] = None):
+        """depth_rgb / colour: (n, H, W, 3) u8 CUDA.  Returns (sbs (n, H, 2W, 3), mask (n, H, 2W[, 3]) or None).
+        `out_depth` (n, H, 2W) float32 receives the rendered depth of both eyes (generic path only for now)."""
         p = self.p
         n, h, w, _ = depth_rgb.shape
         if (w, h) != (p.width, p.height):
@@ -121,16 +123,13 @@ class StereoRerenderer:
         zbuf = self._zbufs.get(zkey)
         if zbuf is None or tuple(zbuf.shape) != (2, h, w) or zbuf.device != depth_rgb.device:
             zbuf = self._zbufs[zkey] = ops.new_zbuf(2, w, h, depth_rgb.device)
-        for k in range(n):
-            f = start_frame + k
+        sources = []
+        for f in (range(start_frame, start_frame + n) if p.xfovs is not None else [start_frame]):
             xf = p.xfov_of(f)
             K = geo.compute_camera_matrix(xf, None if p.xfovs is not None else p.yfov, w, h)
-            src = ops.make_source(w, h, K, p.max_depth, "D1", True, geo.master_fov_depth_scale(p.master_xfov, xf), False)
-            ops.project_splat(depth_rgb[k], src, self.views_of(f), w, h, zbuf, p.near)
-            for e in range(2):
-                m = None if out_mask is None else out_mask[k, :, e * w:(e + 1) * w]
-                ops.resolve(zbuf[e], colour[k], p.bg_rgb, (0, 0, 0), flags | ops.FLAG_RESET_ZBUF,
-                            out_rgb=out_sbs[k, :, e * w:(e + 1) * w], out_mask=m, want_mask=False)
+            sources.append(ops.make_source(w, h, K, p.max_depth, "D1", True, geo.master_fov_depth_scale(p.master_xfov, xf), False))
+        views = [self.views_of(f) for f in range(start_frame, start_frame + n)]
+        ops.render_views(depth_rgb, colour, sources, views, w, h, zbuf, out_sbs, out_mask, out_depth, p.bg_rgb, (0, 0, 0), flags, p.near)
         return out_sbs, out_mask
 
     # ---- host arrays, pipelined -----------------------------------------------------------------------

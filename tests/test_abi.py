@@ -43,6 +43,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.Source) == 4 * 4 + 8 * 4
     assert C.sizeof(_lib.View) == 16 * 4
     assert C.sizeof(_lib.StereoFrame) == 16
+    assert C.sizeof(_lib.PlaneLayout) == 32
 
 
 def test_sass_contains_tma_and_atomics():
@@ -81,6 +82,9 @@ def test_argument_validation_without_a_device():
     assert lib.mdvt_project_points_f64(None, 5, None, None, None) == -1
     assert lib.mdvt_depth_sum(None, 16, 9, 1, 1.0, None, 240, None, None) == -1  # unknown decoder
     assert lib.mdvt_centroid(None, C.byref(src), None, None, None, None) == -1
+    assert lib.mdvt_render_views(None, 0, None, 0, 0, None, 0, None, 2, 1e-4, 4, 4, None, 0, 0, 0, None, None, None, None) == 0
+    assert lib.mdvt_render_views(None, 0, None, 0, 1, None, 0, None, 9, 1e-4, 4, 4, None, 0, 0, 0, None, None, None, None) == -1
+    assert lib.mdvt_resolve(None, None, 4, 4, 0, 0, 0, None, 0, None, 0, None, 0, None, None) == -1
 
 
 def test_ops_refuse_cpu_tensors():
