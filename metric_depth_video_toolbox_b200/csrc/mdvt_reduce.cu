@@ -41,34 +41,71 @@ __device__ __forceinline__ void block_sum4(double (&a)[4]) {
     }
 }
 
-template <int DECODER, bool BIT16>
+// Vertex sums of one frame.  The per-vertex formula is X = (xg - cx) * z / fx (depth_map_tools.py:1127-1128); its
+// SUM over the frame is rearranged so that the per-pixel work is three float64 multiply-adds and no division:
+//     sum X = (sum(xg * z) - cx * sum(z)) / fx,   sum Y likewise,   sum Z = sum(z)
+// (the pose, being affine, is applied to the mean on the host side of the ABI: mean(T p) = T mean(p)).  The result
+// differs from a sum of individually rounded vertices by O(1e-16) relative -- the reference's own mean is a pairwise
+// float64 sum, i.e. no bit-exact target exists; tests hold it to 1e-12 relative.
+// partial[block] = {sum(xg*z), sum(yg*z), sum(z), count}.  VEC4: 4 pixels per thread from three aligned words.
+template <int DECODER, bool BIT16, bool VEC4>
 __global__ void __launch_bounds__(kThreads)
     centroid_partial_kernel(const void *__restrict__ src, int width, int64_t n, float dec_const, float depth_scale, float sx, float sy,
-                            int stretched, double fx, double fy, double cx, double cy, Pose12d pose, double *__restrict__ partial) {
+                            int stretched, double *__restrict__ partial) {
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int64_t p = blockIdx.x * (int64_t)kThreads + threadIdx.x; p < n; p += (int64_t)gridDim.x * kThreads) {
-        const float zf = __fmul_rn(source_depth<DECODER, BIT16>(src, p, dec_const), depth_scale);
+    auto add = [&](int64_t p, float zf) {
         const int row = (int)(p / width), col = (int)(p - (int64_t)row * width);
-        double xg = (double)col, yg = (double)row;
-        if (stretched) {
-            xg = (double)__fmul_rn(__int2float_rn(col), sx);
-            yg = (double)__fmul_rn(__int2float_rn(row), sy);
-        }
+        const double xg = stretched ? (double)__fmul_rn(__int2float_rn(col), sx) : (double)col;
+        const double yg = stretched ? (double)__fmul_rn(__int2float_rn(row), sy) : (double)row;
         const double z = (double)zf;
-        double X = (xg - cx) * z / fx, Y = (yg - cy) * z / fy, Z = z;
-        if (pose.on) {
-            const double *m = pose.m;
-            const double x2 = m[0] * X + m[1] * Y + m[2] * Z + m[3];
-            const double y2 = m[4] * X + m[5] * Y + m[6] * Z + m[7];
-            const double z2 = m[8] * X + m[9] * Y + m[10] * Z + m[11];
-            X = x2; Y = y2; Z = z2;
+        acc[0] = fma(xg, z, acc[0]);
+        acc[1] = fma(yg, z, acc[1]);
+        acc[2] += z;
+        acc[3] += 1.0;
+    };
+    if (VEC4 && DECODER != MDVT_SOURCE_F32) {
+        const uint32_t *words = reinterpret_cast<const uint32_t *>(src);
+        const int64_t n4 = n / 4;
+        for (int64_t g = blockIdx.x * (int64_t)kThreads + threadIdx.x; g < n4; g += (int64_t)gridDim.x * kThreads) {
+            const uint32_t w0 = __ldg(words + 3 * g), w1 = __ldg(words + 3 * g + 1), w2 = __ldg(words + 3 * g + 2);
+            const uint32_t r[4] = {w0 & 0xFF, w0 >> 24, (w1 >> 16) & 0xFF, (w2 >> 8) & 0xFF};
+            const uint32_t gr[4] = {(w0 >> 8) & 0xFF, w1 & 0xFF, w1 >> 24, (w2 >> 16) & 0xFF};
+            const uint32_t b[4] = {(w0 >> 16) & 0xFF, (w1 >> 8) & 0xFF, w2 & 0xFF, w2 >> 24};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                add(4 * g + k, __fmul_rn(depth_of<DECODER>(code_of<DECODER, BIT16>(r[k], gr[k], b[k]), dec_const), depth_scale));
         }
-        acc[0] += X; acc[1] += Y; acc[2] += Z; acc[3] += 1.0;
+    } else {
+        for (int64_t p = blockIdx.x * (int64_t)kThreads + threadIdx.x; p < n; p += (int64_t)gridDim.x * kThreads)
+            add(p, __fmul_rn(source_depth<DECODER, BIT16>(src, p, dec_const), depth_scale));
     }
     block_sum4(acc);
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) partial[blockIdx.x * 4 + k] = acc[k];
+    }
+}
+
+// Single CTA: fixed-order sum of the partials, then the closed form above and the optional pose.
+__global__ void __launch_bounds__(kThreads) finish_centroid_kernel(const double *__restrict__ partial, int n_blocks, double fx, double fy,
+                                                                   double cx, double cy, Pose12d pose, double *__restrict__ out) {
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int b = threadIdx.x; b < n_blocks; b += kThreads) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] += partial[b * 4 + k];
+    }
+    block_sum4(acc);
+    if (threadIdx.x == 0) {
+        const double sz = acc[2], cnt = acc[3];
+        double X = (acc[0] - cx * sz) / fx, Y = (acc[1] - cy * sz) / fy, Z = sz;
+        if (pose.on) {  // sum(T p) = T[:, :3] sum(p) + count * T[:, 3]
+            const double *m = pose.m;
+            const double x2 = m[0] * X + m[1] * Y + m[2] * Z + m[3] * cnt;
+            const double y2 = m[4] * X + m[5] * Y + m[6] * Z + m[7] * cnt;
+            const double z2 = m[8] * X + m[9] * Y + m[10] * Z + m[11] * cnt;
+            X = x2; Y = y2; Z = z2;
+        }
+        out[0] = X; out[1] = Y; out[2] = Z; out[3] = cnt;
     }
 }
 
@@ -124,15 +161,22 @@ extern "C" int mdvt_centroid(const void *depth_src, const mdvt_source *src, cons
     }
     const int stretched = !(src->grid_sx == 1.0f && src->grid_sy == 1.0f);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int grid = reduce_grid(n);
+    const bool vec4 = (n % 4 == 0) && (reinterpret_cast<uintptr_t>(depth_src) % 4 == 0);
+    const int grid = reduce_grid(vec4 ? n / 4 : n);
     double *partial = out_sums + 4;
 #define CALL(D, B)                                                                                                            \
-    centroid_partial_kernel<D, B><<<grid, kThreads, 0, st>>>(depth_src, src->width, n, src->dec_const, src->depth_scale, src->grid_sx, \
-                                                             src->grid_sy, stretched, K_host[0], K_host[1], K_host[2], K_host[3], pose, partial)
+    do {                                                                                                                      \
+        if (vec4)                                                                                                             \
+            centroid_partial_kernel<D, B, true><<<grid, kThreads, 0, st>>>(depth_src, src->width, n, src->dec_const, src->depth_scale, \
+                                                                           src->grid_sx, src->grid_sy, stretched, partial);   \
+        else                                                                                                                  \
+            centroid_partial_kernel<D, B, false><<<grid, kThreads, 0, st>>>(depth_src, src->width, n, src->dec_const, src->depth_scale, \
+                                                                            src->grid_sx, src->grid_sy, stretched, partial);  \
+    } while (0)
     MDVT_DISPATCH_SOURCE(src->decoder, src->bit16, CALL);
 #undef CALL
     MDVT_CUDA_TRY(cudaGetLastError());
-    finish_sum4_kernel<<<1, kThreads, 0, st>>>(partial, grid, out_sums);
+    finish_centroid_kernel<<<1, kThreads, 0, st>>>(partial, grid, K_host[0], K_host[1], K_host[2], K_host[3], pose, out_sums);
     MDVT_CUDA_TRY(cudaGetLastError());
     return MDVT_OK;
 }

@@ -171,6 +171,26 @@ def test_project_splat_resolve(size, theta, posed):
     assert (sbs.cpu().numpy() != want_sbs).any(axis=-1).mean() < 2e-3
 
 
+def test_project_splat_fast_division_equals_ieee_path():
+    """The production splat shares one refined reciprocal per divisor; the parity-output variant (want_uvz) uses
+    IEEE divisions.  Both must build the same z-buffer, bit for bit, also for a float32 depth source."""
+    w, h = 640, 480
+    depth_rgb, colour = SyntheticClip(w, h, 4, zero_fraction=0.01).frame(1)
+    K = orc.camera_matrix(60.0, 41.0, w, h)
+    T = np.eye(4)
+    T[:3, :3] = orc.rot_y(0.05)
+    T[:3, 3] = (0.3, -0.1, 0.2)
+    views = _stereo_views(K, 0.063, 0.01, T)
+    src = ops.make_source(w, h, K, 100, "D1", True, 1.37, False)
+    za, zb, zc = (ops.new_zbuf(2, w, h, DEV) for _ in range(3))
+    ops.project_splat(cu(depth_rgb), src, views, w, h, za, want_uvz=True)
+    ops.project_splat(cu(depth_rgb), src, views, w, h, zb, want_uvz=False)
+    assert torch.equal(za, zb) and bool((za != -1).any())
+    depth = ops.decode_depth(cu(depth_rgb), 100)
+    ops.project_splat(depth, ops.make_source(w, h, K, decoder="F32", depth_scale=1.37), views, w, h, zc)
+    assert torch.equal(za, zc)
+
+
 def test_resolve_mask_rgb_and_white_background():
     w, h = 64, 48
     depth_rgb, colour = SyntheticClip(w, h, 2).frame(0)
