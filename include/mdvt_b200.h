@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MDVT_ABI_VERSION 3
+#define MDVT_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define MDVT_API __attribute__((visibility("default")))
@@ -231,11 +231,12 @@ MDVT_API int mdvt_depth_sum(const void *depth_src, int64_t n_pixels, int decoder
  * pose file and no convergence rotation.  depth_rgb / colour_rgb: n_frames*H*W*3 u8;
  * frames_dev: DEVICE array of mdvt_stereo_frame, n_frames entries (or 1 entry if per_frame == 0);
  * out_sbs: n_frames * H * 2W * 3 u8 (left | right); out_mask: n_frames * H * 2W u8 {0,255}
- * (or u8x3 with MDVT_FLAG_MASK_RGB), may be NULL.  z-buffers live in shared memory; nothing else
- * touches HBM.  Requires W <= 65535. */
+ * (or u8x3 with MDVT_FLAG_MASK_RGB), may be NULL; out_depth: n_frames * H * 2W float32 rendered depth
+ * (left | right, 0 where nothing was drawn -- render(depth=-2), :738,:852), may be NULL.  z-buffers live in
+ * shared memory; nothing else touches HBM.  Requires W <= 65535. */
 MDVT_API int mdvt_stereo_rows(const uint8_t *depth_rgb, const uint8_t *colour_rgb, int n_frames, int width, int height,
                      const mdvt_stereo_frame *frames_dev, int per_frame, uint32_t bg_rgb, uint32_t fill_rgb,
-                     uint32_t flags, uint8_t *out_sbs, uint8_t *out_mask, void *stream);
+                     uint32_t flags, uint8_t *out_sbs, uint8_t *out_mask, float *out_depth, void *stream);
 
 #ifdef __cplusplus
 }

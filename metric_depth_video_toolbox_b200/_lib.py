@@ -18,7 +18,7 @@ DECODERS = {"D1": DECODE_D1, "D2": DECODE_D2, "D3": DECODE_D3, "F32": SOURCE_F32
 REDUCE_SCRATCH_DOUBLES = 4096
 FLAG_BG_COLLIDE, FLAG_RESET_ZBUF, FLAG_MASK_RGB, FLAG_ANYWIDTH = 0x1, 0x2, 0x4, 0x8
 ZBUF_EMPTY = 0xFFFFFFFFFFFFFFFF
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class MdvtError(RuntimeError):
@@ -83,7 +83,7 @@ _PROTOTYPES = {
                                     C.c_float, C.c_int, C.c_int, _u64p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PlaneLayout),
                                     C.POINTER(PlaneLayout), C.POINTER(PlaneLayout), _stream]),
     "mdvt_stereo_rows": (C.c_int, [_u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32,
-                                   C.c_uint32, _u8p, _u8p, _stream]),
+                                   C.c_uint32, _u8p, _u8p, _f32p, _stream]),
 }
 
 _lock = threading.Lock()

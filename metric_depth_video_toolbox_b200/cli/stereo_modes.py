@@ -15,21 +15,36 @@ class StereoJob:
     """One clip shard -> chunks of output frames on the host.
 
     render_chunk(depth_rgb, colour, first_frame) takes pinned host tensors (n, H, W, 3) u8 RGB and returns
-    {"main": (n, oh, ow, 3) u8 RGB, "mask": ... (with --infill_mask), "depth": ... BGR (with
-    --create_sbs_depth_video)} host tensors that stay valid until the next call."""
+    {"main": (n, oh, ow, 3) u8 RGB, "mask": ... RGB (with --infill_mask), "depth": ... BGR wire format (with
+    --create_sbs_depth_video)} host tensors that stay valid until the next call.
+
+    Modes (stereo_rerender.py:406-422):
+      stereo    left | right side by side (:910-918), green/black hole mask (:787-793,921-928), optional SBS depth
+                video (:930-939)
+      touchly1  colour over reverse depth (:548-552 without a pose file -- no render at all; :677-692 with one)
+    """
 
     def __init__(self, args, params: StereoParams, device: torch.device, frame_width: int, frame_height: int):
         self.args, self.params, self.device = args, params, device
         self.w, self.h = frame_width, frame_height
-        for flag in ("touchly0", "touchly1", "vr180", "create_sbs_depth_video", "do_basic_infill"):
+        for flag in ("touchly0", "vr180"):
             if getattr(args, flag, False):
-                raise NotImplementedError(f"--{flag} is not built yet in this front end")
+                raise NotImplementedError(f"--{flag} needs the VR180 equirectangular remap, which is not built yet")
+        if getattr(args, "do_basic_infill", False):
+            raise NotImplementedError("--do_basic_infill (normal-march infill) is not built yet")
         if args.infill_mask and not args.green_and_black_infill_mask:
             raise NotImplementedError("the normals-coded infill mask is not built yet: add --green_and_black_infill_mask")
-        self.out_size = (2 * self.w, self.h)
-        self.has_depth_output = False
+        self.touchly1 = bool(getattr(args, "touchly1", False))
+        if self.touchly1 and params.transformations is not None and args.infill_mask:
+            raise NotImplementedError("--touchly1 with a pose file and --infill_mask: the reference itself fails here "
+                                      "(cv2.cvtColor(RGB2BGR) on its single-channel mask, stereo_rerender.py:701-702)")
+        self.out_size = (self.w, 2 * self.h) if self.touchly1 else (2 * self.w, self.h)
+        self.has_depth_output = bool(getattr(args, "create_sbs_depth_video", False)) and not self.touchly1
+        self.writes_mask = bool(args.infill_mask) and not self.touchly1  # the touchly1 fast path never writes mask frames
         self.renderer = StereoRerenderer(params, device)
         self._host: Dict[str, torch.Tensor] = {}
+        self._dev: Dict[str, torch.Tensor] = {}
+        self._zbuf = None
 
     def _host_buf(self, key: str, shape) -> torch.Tensor:
         buf = self._host.get(key)
@@ -37,15 +52,81 @@ class StereoJob:
             buf = self._host[key] = torch.empty(tuple(shape), dtype=torch.uint8, pin_memory=True)
         return buf[:shape[0]]
 
-    def render_chunk(self, depth_rgb: torch.Tensor, colour: torch.Tensor, first_frame: int) -> Dict[str, torch.Tensor]:
+    def _dev_buf(self, key: str, shape, dtype=torch.uint8) -> torch.Tensor:
+        buf = self._dev.get(key)
+        if buf is None or buf.shape[1:] != tuple(shape[1:]) or buf.shape[0] < shape[0] or buf.dtype != dtype:
+            buf = self._dev[key] = torch.empty(tuple(shape), dtype=dtype, device=self.device)
+        return buf[:shape[0]]
+
+    # ---- stereo ---------------------------------------------------------------------------------------
+    def _stereo_chunk(self, depth_rgb, colour, first_frame):
         n = depth_rgb.shape[0]
         sbs = self._host_buf("main", (n, self.h, 2 * self.w, 3))
         mask = self._host_buf("mask", (n, self.h, 2 * self.w, 3)) if self.params.infill_mask else None
-        self.renderer.render_host(depth_rgb, colour, sbs, mask, start_frame=first_frame, chunk_frames=max(1, min(n, 8)))
-        out = {"main": sbs}
+        if not self.has_depth_output:  # the pipelined two-stream path
+            self.renderer.render_host(depth_rgb, colour, sbs, mask, start_frame=first_frame, chunk_frames=max(1, min(n, 8)))
+            out = {"main": sbs}
+        else:
+            from .. import ops
+
+            d = self._dev_buf("d", depth_rgb.shape)
+            c = self._dev_buf("c", colour.shape)
+            d.copy_(depth_rgb, non_blocking=True)
+            c.copy_(colour, non_blocking=True)
+            dsbs = self._dev_buf("sbs", (n, self.h, 2 * self.w, 3))
+            dmask = self._dev_buf("mask", (n, self.h, 2 * self.w, 3)) if mask is not None else None
+            ddepth = self._dev_buf("depth", (n, self.h, 2 * self.w), torch.float32)
+            self.renderer.render_device(d, c, first_frame, dsbs, dmask, ddepth)
+            coded = ops.encode_depth(ddepth, self.params.max_depth, True, True)  # B, G, R like encode_data_as_BGR (:932-936)
+            sbs.copy_(dsbs, non_blocking=True)
+            if mask is not None:
+                mask.copy_(dmask, non_blocking=True)
+            hdepth = self._host_buf("depthcode", coded.shape)
+            hdepth.copy_(coded, non_blocking=True)
+            out = {"main": sbs, "depth": hdepth}
         if mask is not None:
             out["mask"] = mask
         return out
+
+    # ---- touchly1 -------------------------------------------------------------------------------------
+    def _touchly1_chunk(self, depth_rgb, colour, first_frame):
+        from .. import geometry as geo
+        from .. import ops
+
+        p, a = self.params, self.args
+        n = depth_rgb.shape[0]
+        d = self._dev_buf("d", depth_rgb.shape)
+        c = self._dev_buf("c", colour.shape)
+        d.copy_(depth_rgb, non_blocking=True)
+        c.copy_(colour, non_blocking=True)
+        out = self._dev_buf("t1", (n, 2 * self.h, self.w, 3))
+        if p.transformations is None:  # fast path: no render pass (:548-552)
+            out[:, :self.h].copy_(c)
+            for k in range(n):
+                scale = geo.master_fov_depth_scale(p.master_xfov, p.xfov_of(first_frame + k))
+                ops.touchly_depth(d[k], a.touchly_min_depth, a.touchly_max_depth, False, p.max_depth, "D1", scale, out=out[k, self.h:])
+        else:  # mono render at the frame's pose, then the rendered depth plane (:677-692)
+            if self._zbuf is None:
+                self._zbuf = ops.new_zbuf(1, self.w, self.h, self.device)
+            rgb = self._dev_buf("mono", (n, self.h, self.w, 3))
+            depth = self._dev_buf("monodepth", (n, self.h, self.w), torch.float32)
+            sources, views = [], []
+            for k in range(n):
+                f = first_frame + k
+                xf = p.xfov_of(f)
+                K = geo.compute_camera_matrix(xf, None if p.xfovs is not None else p.yfov, self.w, self.h)
+                sources.append(ops.make_source(self.w, self.h, K, p.max_depth, "D1", True, geo.master_fov_depth_scale(p.master_xfov, xf), False))
+                views.append([ops.ViewSpec(np.asarray(p.transformations[f], dtype=np.float64), K[0, 0], K[1, 1], K[0, 2], K[1, 2])])
+            ops.render_views(d, c, sources, views, self.w, self.h, self._zbuf, rgb, None, depth, p.bg_rgb, p.bg_rgb, 0, p.near)
+            out[:, :self.h].copy_(rgb)
+            for k in range(n):
+                ops.touchly_depth(depth[k], a.touchly_min_depth, a.touchly_max_depth, True, decoder="F32", out=out[k, self.h:])
+        host = self._host_buf("main", out.shape)
+        host.copy_(out, non_blocking=True)
+        return {"main": host}
+
+    def render_chunk(self, depth_rgb: torch.Tensor, colour: torch.Tensor, first_frame: int) -> Dict[str, torch.Tensor]:
+        return self._touchly1_chunk(depth_rgb, colour, first_frame) if self.touchly1 else self._stereo_chunk(depth_rgb, colour, first_frame)
 
 
 def join_segments(parts: List[str], out_path: str, fourcc: str, fps: float, size):

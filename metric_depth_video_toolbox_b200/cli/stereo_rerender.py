@@ -153,9 +153,9 @@ def main(argv: Optional[List[str]] = None) -> int:
     seg = (lambda p: p) if world_size == 1 else (lambda p: f"{p}.rank{rank:02d}.mkv")
     seg_fourcc = fourcc if world_size == 1 else "FFV1"
     writers = {"main": video_io.ChunkWriter(seg(output_tmp_file), seg_fourcc, frame_rate, job.out_size)}
-    if args.infill_mask:
+    if job.writes_mask:
         writers["mask"] = video_io.ChunkWriter(seg(output_tmp_file + "_infillmask.mkv"), "FFV1", frame_rate, job.out_size)
-    if args.create_sbs_depth_video and job.has_depth_output:
+    if job.has_depth_output:
         writers["depth"] = video_io.ChunkWriter(seg(output_tmp_file + "_depth.mkv"), "FFV1", frame_rate, job.out_size)
 
     reader = video_io.ChunkReader([args.depth_video, args.color_video], start, stop, chunk=args.chunk_frames)
@@ -186,7 +186,7 @@ def main(argv: Optional[List[str]] = None) -> int:
         dist.barrier()
     if rank == 0:
         depth_frames_helper.verify_and_move(output_tmp_file, total_frames, output_file)
-        if args.infill_mask:
+        if "mask" in writers:
             depth_frames_helper.verify_and_move(output_tmp_file + "_infillmask.mkv", total_frames, output_file + "_infillmask.mkv")
         if "depth" in writers:
             depth_frames_helper.verify_and_move(output_tmp_file + "_depth.mkv", total_frames, output_file + "_depth.mkv")

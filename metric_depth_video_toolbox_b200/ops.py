@@ -417,7 +417,7 @@ def stereo_frame_constants(xfov_deg: float, width: int, max_depth, pupillary_dis
 
 def stereo_rows(depth_rgb: torch.Tensor, colour: torch.Tensor, frames: torch.Tensor, bg_rgb=(0, 0, 0), fill_rgb=(0, 0, 0),
                 flags: int = 0, out_sbs: Optional[torch.Tensor] = None, out_mask: Optional[torch.Tensor] = None,
-                want_mask: bool = True):
+                want_mask: bool = True, out_depth: Optional[torch.Tensor] = None):
     """Fused stereo kernel over a batch: depth_rgb / colour (n, H, W, 3) u8; frames (n, 4) or (1, 4) float32
     CUDA tensor of mdvt_stereo_frame rows.  Returns (sbs (n, H, 2W, 3), mask (n, H, 2W[, 3]) or None)."""
     _need(depth_rgb, torch.uint8, "depth_rgb")
@@ -441,6 +441,11 @@ def stereo_rows(depth_rgb: torch.Tensor, colour: torch.Tensor, frames: torch.Ten
         _need(out_mask, torch.uint8, "out_mask")
         if out_mask.numel() != n * h * 2 * w * mask_bpp:
             raise ValueError("out_mask has the wrong size")
+    if out_depth is not None:
+        _need(out_depth, torch.float32, "out_depth")
+        if out_depth.numel() != n * h * 2 * w:
+            raise ValueError("out_depth must be (n, H, 2W) float32")
     _lib.check(_lib.load().mdvt_stereo_rows(_ptr(depth_rgb), _ptr(colour), n, w, h, _ptr(frames), int(frames.shape[0] == n and n > 1),
-                                            pack_rgb(bg_rgb), pack_rgb(fill_rgb), flags, _ptr(out_sbs), _ptr(out_mask), _stream()))
+                                            pack_rgb(bg_rgb), pack_rgb(fill_rgb), flags, _ptr(out_sbs), _ptr(out_mask), _ptr(out_depth),
+                                            _stream()))
     return out_sbs, out_mask

@@ -105,7 +105,7 @@ class StereoRerenderer:
                       out_sbs: Optional[torch.Tensor] = None, out_mask: Optional[torch.Tensor] = None,
                       out_depth: Optional[torch.Tensor] = None):
         """depth_rgb / colour: (n, H, W, 3) u8 CUDA.  Returns (sbs (n, H, 2W, 3), mask (n, H, 2W[, 3]) or None).
-        `out_depth` (n, H, 2W) float32 receives the rendered depth of both eyes (generic path only for now)."""
+        `out_depth` (n, H, 2W) float32 receives the rendered depth of both eyes (0 where nothing was drawn)."""
         p = self.p
         n, h, w, _ = depth_rgb.shape
         if (w, h) != (p.width, p.height):
@@ -113,7 +113,7 @@ class StereoRerenderer:
         flags = (ops.FLAG_BG_COLLIDE if p.infill_mask else 0) | (ops.FLAG_MASK_RGB if p.mask_rgb else 0)
         if p.row_local():
             return ops.stereo_rows(depth_rgb, colour, self._device_constants(start_frame, n), p.bg_rgb, (0, 0, 0), flags,
-                                   out_sbs, out_mask, want_mask=p.infill_mask)
+                                   out_sbs, out_mask, want_mask=p.infill_mask, out_depth=out_depth)
         # generic path: per frame K1+K2 into a persistent 2-view z-buffer, K3 per eye straight into the SBS halves
         if out_sbs is None:
             out_sbs = torch.empty((n, h, 2 * w, 3), dtype=torch.uint8, device=depth_rgb.device)

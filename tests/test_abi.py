@@ -68,9 +68,9 @@ def test_argument_validation_without_a_device():
     assert lib.mdvt_decode_depth(None, 16, _lib.DECODE_D2, 0, 1.0, None, None, None) == -2  # 24-bit is D1-only
     assert lib.mdvt_decode_depth(None, 0, 0, 1, 1.0, None, None, None) == 0  # empty input is a no-op
     assert lib.mdvt_encode_depth(None, 4, 0.0, 1, 1, None, None, None) == -1
-    assert lib.mdvt_stereo_rows(None, None, 1, 70000, 4, None, 0, 0, 0, 0, None, None, None) == -2
+    assert lib.mdvt_stereo_rows(None, None, 1, 70000, 4, None, 0, 0, 0, 0, None, None, None, None) == -2
     assert b"65535" in lib.mdvt_last_error()
-    assert lib.mdvt_stereo_rows(None, None, 0, 64, 4, None, 0, 0, 0, 0, None, None, None) == 0
+    assert lib.mdvt_stereo_rows(None, None, 0, 64, 4, None, 0, 0, 0, 0, None, None, None, None) == 0
     assert lib.mdvt_zbuf_clear(None, 0, None) == 0
     src = _lib.Source()
     assert lib.mdvt_project_splat(None, C.byref(src), None, 1, 1e-4, 4, 4, 0, None, None, None) == -1  # 0x0 frame

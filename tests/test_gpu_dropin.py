@@ -361,3 +361,86 @@ def test_cli_stereo_rerender_torchrun_two_ranks(clip_files, tmp_path):
     assert sharded.shape == single.shape == (c["n"], c["h"], 2 * c["w"], 3)
     assert np.array_equal(sharded, single)
     assert np.array_equal(sharded_mask, video_io.read_clip(str(work / "depth.mkv") + "_stereo.mkv_infillmask.mkv"))
+
+
+# ---------------------------------------------------------------------------------------------
+# rendered depth planes, SBS depth video, Touchly1
+# ---------------------------------------------------------------------------------------------
+def _model_depth_planes(depth_rgb, consts, ids_pair):
+    dec, scale = np.float32(consts[0]), np.float32(consts[1])
+    c16 = (depth_rgb[..., 0].astype(np.uint32) << 8) | depth_rgb[..., 2].astype(np.uint32)
+    z = (((c16 << 16).astype(np.float32) * dec) * scale).reshape(-1)
+    return np.concatenate([np.where(ids >= 0, z[np.maximum(ids, 0)], np.float32(0)) for ids in ids_pair], axis=1).astype(np.float32)
+
+
+@pytest.mark.parametrize("size,flags", [((640, 48), 0), ((70, 33), 0), ((1920, 8), 0x8)])  # fast kernel, any-width kernel, forced any-width
+def test_stereo_rows_depth_plane_bit_exact(size, flags):
+    w, h = size
+    depth, colour = SyntheticClip(w, h, 2, zero_fraction=0.01).frames()
+    consts = ops.stereo_frame_constants(60.0, w, 100, 63, 45.0)
+    out_depth = torch.full((2, h, 2 * w), -1.0, dtype=torch.float32, device=DEV)
+    ops.stereo_rows(cu(depth), cu(colour), cu(consts[None]), flags=flags, out_depth=out_depth)
+    for f in range(2):
+        _, _, ids = km.stereo_rows_f32(depth[f], colour[f], consts)
+        assert np.array_equal(bits(out_depth[f].cpu().numpy()), bits(_model_depth_planes(depth[f], consts, ids))), f
+
+
+def test_cli_sbs_depth_video_and_touchly1(clip_files, tmp_path):
+    import shutil
+
+    import stereo_rerender
+
+    c = clip_files
+    work = tmp_path / "modes"
+    work.mkdir()
+    for name in ("depth.mkv", "colour.mkv"):
+        shutil.copy(c["dir"] / name, work / name)
+    dv, cv = str(work / "depth.mkv"), str(work / "colour.mkv")
+    consts = ops.stereo_frame_constants(60.0, c["w"], 100, 63, 45.0)
+    # row-local path
+    assert stereo_rerender.main(["--depth_video", dv, "--color_video", cv, "--xfov", "60", "--create_sbs_depth_video", "--max_frames", "3"]) == 0
+    coded = video_io.read_clip(dv + "_stereo.mkv_depth.mkv")  # RGB order, 16-bit wire format
+    sbs = video_io.read_clip(dv + "_stereo.mkv")
+    assert coded.shape == sbs.shape == (3, c["h"], 2 * c["w"], 3)
+    for k in range(3):
+        want_sbs, _, ids = km.stereo_rows_f32(c["depth"][k], c["colour"][k], consts)
+        assert np.array_equal(sbs[k], want_sbs)
+        plane = _model_depth_planes(c["depth"][k], consts, ids)
+        assert np.array_equal(coded[k], orc.encode_depth_frame_rgb(plane, 100, True)), k  # stereo_rerender.py:932-939
+    # generic path (convergence): depth planes come from the 64-bit z-buffer
+    json.dump([5.0] * c["n"], open(work / "conv.json", "w"))
+    assert stereo_rerender.main(["--depth_video", dv, "--color_video", cv, "--xfov", "60", "--create_sbs_depth_video", "--max_frames", "2",
+                                 "--convergence_file", str(work / "conv.json")]) == 0
+    coded = video_io.read_clip(dv + "_stereo.mkv_depth.mkv")
+    back = dfh.decode_rgb_depth_frame(coded[0], 100, True)
+    K = orc.camera_matrix(60.0, None, c["w"], c["h"])
+    scale = orc.master_fov_depth_scale(45.0, 60.0)
+    theta = orc.convergence_angle(5.0 * scale, 0.063)
+    for e, eye in enumerate(("left", "right")):
+        u, v, z = orc.view_uvz(c["depth"][0], 100, K, orc.eye_pose(eye, 0.063, theta), depth_scale=scale)
+        want = orc.zbuffer_depth(orc.splat_ids(u, v, z, c["w"], c["h"]), z)
+        got = back[:, e * c["w"]:(e + 1) * c["w"]]
+        assert (np.abs(got - want) > 2e-3).mean() < 3e-3  # 1.55 mm wire-format quantisation + rounding-boundary pixels
+    # touchly1 without a pose file: colour over reverse depth, no render (stereo_rerender.py:548-552)
+    assert stereo_rerender.main(["--depth_video", dv, "--color_video", cv, "--xfov", "60", "--touchly1", "--touchly_max_depth", "7.5",
+                                 "--max_frames", "2"]) == 0
+    t1 = video_io.read_clip(dv + "_Touchly1.mkv")
+    assert t1.shape == (2, 2 * c["h"], c["w"], 3)
+    for k in range(2):
+        depth = orc.apply_depth_scale(orc.decode_rgb_depth_frame(c["depth"][k], 100, True), scale)
+        d8 = np.rint(np.maximum(0, np.minimum(depth, 7.5) - 0) * (255 / (7.5 - 0))).astype(np.uint8)
+        assert np.array_equal(t1[k, :c["h"]], c["colour"][k]) and np.array_equal(t1[k, c["h"]:], 255 - np.repeat(d8[..., None], 3, axis=-1))
+    # touchly1 with a pose file: mono render + rendered-depth plane (:677-692)
+    T = np.tile(np.eye(4), (c["n"], 1, 1))
+    T[:, 0, 3] = 0.04
+    json.dump(T.tolist(), open(work / "pose.json", "w"))
+    assert stereo_rerender.main(["--depth_video", dv, "--color_video", cv, "--xfov", "60", "--touchly1", "--max_frames", "1",
+                                 "--transformation_file", str(work / "pose.json")]) == 0
+    t1 = video_io.read_clip(dv + "_Touchly1.mkv")
+    want_img, _, ids = orc.render_view(c["depth"][0], c["colour"][0], 100, K, T[0], depth_scale=scale)
+    assert (t1[0, :c["h"]] != want_img).any(axis=-1).mean() < 3e-3
+    u, v, z = orc.view_uvz(c["depth"][0], 100, K, T[0], depth_scale=scale)
+    zplane = orc.zbuffer_depth(ids, z)
+    d8 = np.rint(np.maximum(0, np.minimum(zplane, 5) - 0) * (255 / 5)).astype(np.uint8)
+    d8[d8 == 0] = 255
+    assert (t1[0, c["h"]:, :, 0] != 255 - d8).mean() < 5e-3
