@@ -225,6 +225,32 @@ MDVT_API int mdvt_centroid(const void *depth_src, const mdvt_source *src_host, c
 MDVT_API int mdvt_depth_sum(const void *depth_src, int64_t n_pixels, int decoder, int bit16, float dec_const,
                    const uint8_t *mask, int mask_gt, double *out_sums, void *stream);
 
+/* ---- normals-coded infill mask: the per-pixel parts (stereo_rerender.py --infill_mask) ------------ */
+/* E1.  The edge test of the reference's mesh builder on the depth grid (depth_map_tools.py:1243-1376, called with
+ * remove_edges=True, return_normals_of_removed=True at stereo_rerender.py:583), float64 like the reference:
+ * out_flags[p] = 1 where vertex p belongs to a triangle seen at more than angle_threshold_deg (89) degrees,
+ * out_normals[3p..] = the unit normal the reference attaches to it (written for flagged vertices only; may be NULL).
+ * cell_flags_scratch: (W-1)*(H-1) bytes.  The grid is the source's (grid_sx/sy: of_by_one stretch). */
+MDVT_API int mdvt_edge_vertices(const void *depth_src, const mdvt_source *src_host, const double *K_host,
+                       double angle_threshold_deg, uint8_t *cell_flags_scratch, uint8_t *out_flags, double *out_normals,
+                       void *stream);
+/* E2.  Flagged vertices -> "edge points" (stereo_rerender.py:589-606) -> pose (12 doubles, frame -> eye camera,
+ * :615-619,723-732) -> projection with the render camera (K_render_host: fx, fy, cx, cy as the float32-rounded values
+ * the reference hands to cv2.projectPoints, :735) -> np.round -> z-buffered into zbuf (out_w*out_h u64, pre-cleared;
+ * nearest wins, :745-755). */
+MDVT_API int mdvt_edge_splat(const void *depth_src, const mdvt_source *src_host, const double *K_host, const uint8_t *flags,
+                    const double *pose_host, const double *K_render_host, int out_w, int out_h, uint64_t *zbuf,
+                    void *stream);
+/* E3.  Per target pixel of one eye: mask image (u8x3) = bg_rgb at holes, black elsewhere; with code_normals the
+ * border holes get the fixed inward normals of :796-799 and a hole pixel hit by an edge point gets that point's
+ * normal, rotated into the eye camera, as (n+1)/2*255 (:733,778-780,802); `image` (optional, in/out) receives the edge
+ * point's colour there (:813-814).  hole_mask: u8, non-zero = hole (what mdvt_resolve / mdvt_stereo_rows wrote).
+ * Leaves zbuf empty.  The TELEA inpainting + masked blur that follow (:805-808) are OpenCV calls on the host. */
+MDVT_API int mdvt_edge_resolve(uint64_t *zbuf, const void *depth_src, const mdvt_source *src_host, const double *K_host,
+                      const double *normals, const double *pose_host, const uint8_t *colour_rgb, const uint8_t *hole_mask,
+                      int64_t hole_pitch, int out_w, int out_h, uint32_t bg_rgb, int code_normals, uint8_t *image,
+                      int64_t image_pitch, uint8_t *mask_img, int64_t mask_pitch, void *stream);
+
 /* ---- row-local stereo fast path: ONE fused kernel, frames batched ---------------------------- */
 /* Whole stereo_rerender.py frame loop body (:512-541 decode+scale, :583 unproject, :723-738,:831-852 eye
  * poses + render, :740,:787-793,:854 hole mask, :918 hconcat) for a batch of frames when there is no

@@ -32,8 +32,11 @@ class StereoJob:
                 raise NotImplementedError(f"--{flag} needs the VR180 equirectangular remap, which is not built yet")
         if getattr(args, "do_basic_infill", False):
             raise NotImplementedError("--do_basic_infill (normal-march infill) is not built yet")
-        if args.infill_mask and not args.green_and_black_infill_mask:
-            raise NotImplementedError("the normals-coded infill mask is not built yet: add --green_and_black_infill_mask")
+        # stereo_rerender.py:568-573,589: the mesh edge test runs for --infill_mask / --remove_edges / --do_basic_infill unless
+        # --dont_remove_edges; its vertices are painted into the holes unless --dont_place_points_in_edges
+        remove_edges = (args.infill_mask or args.remove_edges) and not args.dont_remove_edges
+        self.paint_edges = bool(remove_edges and not args.dont_place_points_in_edges)
+        self.code_normals = bool(args.infill_mask and not args.green_and_black_infill_mask)
         self.touchly1 = bool(getattr(args, "touchly1", False))
         if self.touchly1 and params.transformations is not None and args.infill_mask:
             raise NotImplementedError("--touchly1 with a pose file and --infill_mask: the reference itself fails here "
@@ -42,6 +45,11 @@ class StereoJob:
         self.has_depth_output = bool(getattr(args, "create_sbs_depth_video", False)) and not self.touchly1
         self.writes_mask = bool(args.infill_mask) and not self.touchly1  # the touchly1 fast path never writes mask frames
         self.renderer = StereoRerenderer(params, device)
+        self.infill = None
+        if (self.paint_edges or self.code_normals) and not self.touchly1:
+            from ..infill import InfillMaskRenderer
+
+            self.infill = InfillMaskRenderer(self.renderer)
         self._host: Dict[str, torch.Tensor] = {}
         self._dev: Dict[str, torch.Tensor] = {}
         self._zbuf = None
@@ -63,9 +71,32 @@ class StereoJob:
         n = depth_rgb.shape[0]
         sbs = self._host_buf("main", (n, self.h, 2 * self.w, 3))
         mask = self._host_buf("mask", (n, self.h, 2 * self.w, 3)) if self.params.infill_mask else None
-        if not self.has_depth_output:  # the pipelined two-stream path
+        if not self.has_depth_output and self.infill is None:  # the pipelined two-stream path
             self.renderer.render_host(depth_rgb, colour, sbs, mask, start_frame=first_frame, chunk_frames=max(1, min(n, 8)))
             out = {"main": sbs}
+        elif self.infill is not None:  # edge points painted into the holes, normals-coded (or green/black) mask image
+            from .. import ops
+
+            d = self._dev_buf("d", depth_rgb.shape)
+            c = self._dev_buf("c", colour.shape)
+            d.copy_(depth_rgb, non_blocking=True)
+            c.copy_(colour, non_blocking=True)
+            dsbs = self._dev_buf("sbs", (n, self.h, 2 * self.w, 3))
+            dmask = self._dev_buf("mask", (n, self.h, 2 * self.w, 3))
+            ddepth = self._dev_buf("depth", (n, self.h, 2 * self.w), torch.float32) if self.has_depth_output else None
+            self.infill.render_device(d, c, first_frame, dsbs, dmask, self.code_normals, self.paint_edges, ddepth)
+            sbs.copy_(dsbs, non_blocking=True)
+            out = {"main": sbs}
+            if ddepth is not None:
+                coded = ops.encode_depth(ddepth, self.params.max_depth, True, True)
+                hdepth = self._host_buf("depthcode", coded.shape)
+                hdepth.copy_(coded, non_blocking=True)
+                out["depth"] = hdepth
+            if mask is not None:
+                mask.copy_(dmask, non_blocking=True)
+                if self.code_normals:  # host part: TELEA + masked blur per eye (OpenCV, as the reference)
+                    torch.cuda.synchronize(self.device)
+                    mask.copy_(torch.from_numpy(self.infill.finish(mask.numpy())))
         else:
             from .. import ops
 

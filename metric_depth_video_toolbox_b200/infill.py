@@ -1,0 +1,106 @@
+"""Normals-coded infill mask of `stereo_rerender.py --infill_mask` (:583-606,727-819,838-907): the mask video the
+infill engines consume (movie_2_3D passes --infill_mask by default, movie_2_3D.py:440).
+
+Per frame, on the GPU: the stereo render itself (row kernel or generic path, unchanged), the edge test of the mesh
+builder (E1), and per eye the edge-point splat (E2) and the mask / image painting (E3).  On the host, exactly as the
+reference does it with OpenCV: TELEA inpainting of everything that is not a coded normal, copied into the hole pixels,
+then the black-ignoring Gaussian -- fanned over a thread pool (cv2 releases the GIL), one eye of one frame per task.
+"""
+from __future__ import annotations
+
+from concurrent.futures import ThreadPoolExecutor
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import geometry as geo
+from . import ops
+from .stereo import StereoRerenderer
+
+GREEN = (0, 255, 0)
+
+
+def masked_blur(img: np.ndarray, ksize=(6, 6), sigma=0) -> np.ndarray:
+    """stereo_rerender.masked_blur (:114-153): Gaussian blur in which pure-black pixels carry no weight."""
+    import cv2
+
+    g = cv2.getGaussianKernel(ksize[0], sigma)
+    kernel = g @ g.T
+    black = np.all(img == 0, axis=2)
+    weights = cv2.filter2D((~black).astype(np.float32), -1, kernel, borderType=cv2.BORDER_ISOLATED)
+    total = cv2.filter2D(img.astype(np.float32), -1, kernel, borderType=cv2.BORDER_ISOLATED)
+    out = total / np.where(weights == 0, 1.0, weights)[..., None]
+    out[weights == 0] = 0
+    out[black] = 0
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def finish_mask(mask_u8: np.ndarray) -> np.ndarray:
+    """stereo_rerender.py:803-808,817 on the u8 image the GPU produced: inpaint (TELEA, radius 3) all background-green
+    and black pixels from the coded normals, keep the result in the green (hole) pixels only, masked blur."""
+    import cv2
+
+    green = np.all(mask_u8 == np.asarray(GREEN, dtype=np.uint8), axis=-1)
+    area = green | np.all(mask_u8 == 0, axis=-1)
+    filled = cv2.inpaint(mask_u8, area.astype(np.uint8) * 255, inpaintRadius=3, flags=cv2.INPAINT_TELEA)
+    mask = mask_u8.astype(np.float64) / 255.0
+    mask[green] = filled[green].astype(np.float32) / 255.0
+    blurred = masked_blur((mask * 255).astype(np.uint8)).astype(np.float32) / 255.0
+    return (blurred * 255).astype(np.uint8)
+
+
+class InfillMaskRenderer:
+    """StereoRerenderer plus the normals-coded mask.  render_device returns (sbs u8 (n, H, 2W, 3) with edge colours
+    painted into the holes, mask image u8 (n, H, 2W, 3) BEFORE inpainting); finish() runs the host part."""
+
+    def __init__(self, renderer: StereoRerenderer, workers: int = 8):
+        self.r = renderer
+        self.pool = ThreadPoolExecutor(max_workers=max(1, workers))
+        self._zbuf = None
+        self._flags = self._normals = self._holes = None
+
+    def render_device(self, depth_rgb: torch.Tensor, colour: torch.Tensor, start_frame: int = 0, out_sbs: Optional[torch.Tensor] = None,
+                      out_mask_img: Optional[torch.Tensor] = None, code_normals: bool = True, paint_edge_colours: bool = True,
+                      out_depth: Optional[torch.Tensor] = None):
+        r, p = self.r, self.r.p
+        n, h, w, _ = depth_rgb.shape
+        dev = depth_rgb.device
+        if out_sbs is None:
+            out_sbs = torch.empty((n, h, 2 * w, 3), dtype=torch.uint8, device=dev)
+        if out_mask_img is None:
+            out_mask_img = torch.empty((n, h, 2 * w, 3), dtype=torch.uint8, device=dev)
+        if self._holes is None or self._holes.shape != (n, h, 2 * w):
+            self._holes = torch.empty((n, h, 2 * w), dtype=torch.uint8, device=dev)
+        if self._zbuf is None or tuple(self._zbuf.shape) != (h, w):
+            self._zbuf = ops.new_zbuf(1, w, h, dev)[0]
+            self._flags = torch.empty((h, w), dtype=torch.uint8, device=dev)
+            self._normals = torch.empty((h, w, 3), dtype=torch.float64, device=dev)
+        # 1. the stereo render with a plain u8 hole mask (what bg_mask is in the reference, :740,854)
+        r.render_device(depth_rgb, colour, start_frame, out_sbs, self._holes, out_depth, mask_rgb=False)
+        # 2. edge vertices once per frame, edge points once per eye
+        for k in range(n):
+            f = start_frame + k
+            xf = p.xfov_of(f)
+            K = geo.compute_camera_matrix(xf, None if p.xfovs is not None else p.yfov, w, h)
+            src = ops.make_source(w, h, K, p.max_depth, "D1", True, geo.master_fov_depth_scale(p.master_xfov, xf), True)  # mesh grid: of_by_one (:575)
+            ops.edge_vertices(depth_rgb[k], src, K, True, flags=self._flags, normals=self._normals)
+            for e, view in enumerate(r.views_of(f)):
+                half = slice(e * w, (e + 1) * w)
+                ops.edge_splat(depth_rgb[k], src, K, self._flags, view.M, K, w, h, self._zbuf)
+                ops.edge_resolve(self._zbuf, depth_rgb[k], src, K, self._normals if code_normals else None, view.M, colour[k],
+                                 self._holes[k, :, half], out_mask_img[k, :, half], out_sbs[k, :, half] if paint_edge_colours else None,
+                                 p.bg_rgb, code_normals)
+        return out_sbs, out_mask_img
+
+    def finish(self, mask_img_host: np.ndarray) -> np.ndarray:
+        """(n, H, 2W, 3) u8 pre-inpaint mask images (host) -> final mask frames; each eye is finished on its own, as the
+        reference does (left_img_mask / right_img_mask, :805-808,893-896)."""
+        n, h, w2, _ = mask_img_host.shape
+        w = w2 // 2
+        out = np.empty_like(mask_img_host)
+        jobs = [(k, e, self.pool.submit(finish_mask, np.ascontiguousarray(mask_img_host[k, :, e * w:(e + 1) * w])))
+                for k in range(n) for e in range(2)]
+        for k, e, fut in jobs:
+            out[k, :, e * w:(e + 1) * w] = fut.result()
+        return out

@@ -449,3 +449,61 @@ def stereo_rows(depth_rgb: torch.Tensor, colour: torch.Tensor, frames: torch.Ten
                                             pack_rgb(bg_rgb), pack_rgb(fill_rgb), flags, _ptr(out_sbs), _ptr(out_mask), _ptr(out_depth),
                                             _stream()))
     return out_sbs, out_mask
+
+
+# ---------------------------------------------------------------------------------------------
+# normals-coded infill mask: edge vertices, edge-point splat, mask / image painting
+# ---------------------------------------------------------------------------------------------
+EDGE_ANGLE_DEG = 89.0  # depth_map_tools.py:1192
+
+
+def edge_vertices(depth_src: torch.Tensor, source: _lib.Source, K: np.ndarray, want_normals: bool = True,
+                  angle_threshold_deg: float = EDGE_ANGLE_DEG, flags: Optional[torch.Tensor] = None,
+                  normals: Optional[torch.Tensor] = None):
+    """Edge test of the reference's mesh builder (depth_map_tools.py:1243-1376).  Returns (flags (H, W) u8 with 1 at
+    vertices of too-oblique triangles, normals (H, W, 3) float64 -- defined at flagged vertices only -- or None)."""
+    _need_source(depth_src, source)
+    h, w = source.height, source.width
+    dev = depth_src.device
+    if flags is None:
+        flags = torch.empty((h, w), dtype=torch.uint8, device=dev)
+    if normals is None and want_normals:
+        normals = torch.empty((h, w, 3), dtype=torch.float64, device=dev)
+    scratch = torch.empty(((h - 1) * (w - 1),), dtype=torch.uint8, device=dev)
+    _lib.check(_lib.load().mdvt_edge_vertices(_ptr(depth_src), C.byref(source), _k4(K), float(angle_threshold_deg), _ptr(scratch),
+                                              _ptr(_need(flags, torch.uint8, "flags")), _ptr(normals), _stream()))
+    return flags, normals
+
+
+def edge_splat(depth_src: torch.Tensor, source: _lib.Source, K: np.ndarray, flags: torch.Tensor, pose, K_render: np.ndarray,
+               out_w: int, out_h: int, zbuf: torch.Tensor):
+    """Flagged vertices -> edge points -> eye camera (`pose`, 4x4 float64) -> z-buffer (out_h, out_w) int64."""
+    _need_source(depth_src, source)
+    _need(flags, torch.uint8, "flags")
+    _need(zbuf, torch.int64, "zbuf")
+    if tuple(zbuf.shape) != (out_h, out_w):
+        raise ValueError(f"zbuf shape {tuple(zbuf.shape)} != ({out_h}, {out_w})")
+    k32 = np.asarray(K_render).astype(np.float32).astype(np.float64)  # the reference hands cv2 a float32 camera matrix
+    _lib.check(_lib.load().mdvt_edge_splat(_ptr(depth_src), C.byref(source), _k4(K), _ptr(flags), _pose12(pose, C.c_double), _k4(k32),
+                                           int(out_w), int(out_h), _ptr(zbuf), _stream()))
+
+
+def edge_resolve(zbuf: torch.Tensor, depth_src: torch.Tensor, source: _lib.Source, K: np.ndarray, normals: Optional[torch.Tensor], pose,
+                 colour: torch.Tensor, hole_mask: torch.Tensor, mask_img: torch.Tensor, image: Optional[torch.Tensor] = None,
+                 bg_rgb=(0, 255, 0), code_normals: bool = True):
+    """Per target pixel: the (pre-inpainting) mask image and the edge colours painted into `image`.  hole_mask (H, W)
+    u8, mask_img / image (H, W, 3) u8 may be column slices of side-by-side tensors.  Leaves `zbuf` empty."""
+    _need(zbuf, torch.int64, "zbuf")
+    _need(colour, torch.uint8, "colour")
+    out_h, out_w = zbuf.shape
+    for t, ch, name in ((hole_mask, 1, "hole_mask"), (mask_img, 3, "mask_img"), (image, 3, "image")):
+        if t is None:
+            continue
+        ok = t.dtype == torch.uint8 and t.is_cuda and t.shape[0] == out_h and t.shape[1] == out_w and t.stride(-1) == 1
+        ok = ok and ((ch == 1 and t.dim() == 2) or (ch == 3 and t.dim() == 3 and t.shape[2] == 3 and t.stride(1) == 3))
+        if not ok:
+            raise ValueError(f"{name} must be a ({out_h}, {out_w}{', 3' if ch == 3 else ''}) u8 CUDA view with dense rows")
+    _lib.check(_lib.load().mdvt_edge_resolve(_ptr(zbuf), _ptr(depth_src), C.byref(source), _k4(K), _ptr(normals), _pose12(pose, C.c_double),
+                                             _ptr(colour), _ptr(hole_mask), hole_mask.stride(0), out_w, out_h, pack_rgb(bg_rgb),
+                                             int(bool(code_normals)), _ptr(image), 0 if image is None else image.stride(0), _ptr(mask_img),
+                                             mask_img.stride(0), _stream()))

@@ -103,22 +103,23 @@ class StereoRerenderer:
     # ---- device-resident ------------------------------------------------------------------------------
     def render_device(self, depth_rgb: torch.Tensor, colour: torch.Tensor, start_frame: int = 0,
                       out_sbs: Optional[torch.Tensor] = None, out_mask: Optional[torch.Tensor] = None,
-                      out_depth: Optional[torch.Tensor] = None):
+                      out_depth: Optional[torch.Tensor] = None, mask_rgb: Optional[bool] = None):
         """depth_rgb / colour: (n, H, W, 3) u8 CUDA.  Returns (sbs (n, H, 2W, 3), mask (n, H, 2W[, 3]) or None).
         `out_depth` (n, H, 2W) float32 receives the rendered depth of both eyes (0 where nothing was drawn)."""
         p = self.p
         n, h, w, _ = depth_rgb.shape
         if (w, h) != (p.width, p.height):
             raise ValueError(f"frames are {w}x{h}, parameters say {p.width}x{p.height}")
-        flags = (ops.FLAG_BG_COLLIDE if p.infill_mask else 0) | (ops.FLAG_MASK_RGB if p.mask_rgb else 0)
+        mask_rgb = p.mask_rgb if mask_rgb is None else mask_rgb  # u8x3 background-colour mask image, or plain u8 {0,255}
+        flags = (ops.FLAG_BG_COLLIDE if p.infill_mask else 0) | (ops.FLAG_MASK_RGB if mask_rgb else 0)
         if p.row_local():
             return ops.stereo_rows(depth_rgb, colour, self._device_constants(start_frame, n), p.bg_rgb, (0, 0, 0), flags,
-                                   out_sbs, out_mask, want_mask=p.infill_mask, out_depth=out_depth)
+                                   out_sbs, out_mask, want_mask=p.infill_mask or out_mask is not None, out_depth=out_depth)
         # generic path: per frame K1+K2 into a persistent 2-view z-buffer, K3 per eye straight into the SBS halves
         if out_sbs is None:
             out_sbs = torch.empty((n, h, 2 * w, 3), dtype=torch.uint8, device=depth_rgb.device)
         if out_mask is None and p.infill_mask:
-            out_mask = torch.empty((n, h, 2 * w) + ((3,) if p.mask_rgb else ()), dtype=torch.uint8, device=depth_rgb.device)
+            out_mask = torch.empty((n, h, 2 * w) + ((3,) if mask_rgb else ()), dtype=torch.uint8, device=depth_rgb.device)
         zkey = torch.cuda.current_stream(depth_rgb.device).cuda_stream
         zbuf = self._zbufs.get(zkey)
         if zbuf is None or tuple(zbuf.shape) != (2, h, w) or zbuf.device != depth_rgb.device:

@@ -35,7 +35,12 @@ def load(name: str):
         return sys.modules[alias]
     for stub in _STUBS:
         if stub not in sys.modules:
-            sys.modules[stub] = types.ModuleType(stub)
+            if stub == "open3d":
+                from . import fake_o3d
+
+                sys.modules[stub] = fake_o3d.module()  # enough of Open3D to RUN the mesh-building NumPy code
+            else:
+                sys.modules[stub] = types.ModuleType(stub)
     shaders = sys.modules["OpenGL.GL.shaders"]
     for attr in ("compileProgram", "compileShader"):
         if not hasattr(shaders, attr):

@@ -260,7 +260,7 @@ def test_cli_stereo_rerender_default_and_mask(clip_files):
 
     c = clip_files
     rc = stereo_rerender.main(["--depth_video", c["depth_path"], "--color_video", c["colour_path"], "--xfov", "60", "--infill_mask",
-                               "--green_and_black_infill_mask", "--chunk_frames", "3"])
+                               "--green_and_black_infill_mask", "--dont_place_points_in_edges", "--chunk_frames", "3"])
     assert rc == 0
     out = video_io.read_clip(c["depth_path"] + "_stereo.mkv")
     msk = video_io.read_clip(c["depth_path"] + "_stereo.mkv_infillmask.mkv")
@@ -444,3 +444,137 @@ def test_cli_sbs_depth_video_and_touchly1(clip_files, tmp_path):
     d8 = np.rint(np.maximum(0, np.minimum(zplane, 5) - 0) * (255 / 5)).astype(np.uint8)
     d8[d8 == 0] = 255
     assert (t1[0, c["h"]:, :, 0] != 255 - d8).mean() < 5e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# normals-coded infill mask (golden vectors made by running the reference, oracle/make_infill_golden.py)
+# ---------------------------------------------------------------------------------------------
+def _infill_case(golden_dir, tag):
+    from oracle import infill_oracle as io
+
+    g = np.load(os.path.join(golden_dir, "infill_mask.npz"))
+    w, h, xfov, conv = g[tag + "_params"]
+    w, h = int(w), int(h)
+    K = orc.camera_matrix(xfov, None, w, h)
+    scale = orc.master_fov_depth_scale(45.0, xfov)
+    theta = None if conv == 0 else orc.convergence_angle(conv * scale, 0.063)
+    M = orc.eye_pose("left", 0.063, theta) @ g[tag + "_transform"]
+    return g, io, w, h, float(xfov), float(conv), K, scale, M
+
+
+@pytest.mark.parametrize("tag", ["plain", "posed"])
+def test_edge_vertices_match_reference_mesh_builder(golden_dir, tag):
+    g, io, w, h, xfov, conv, K, scale, M = _infill_case(golden_dir, tag)
+    src = ops.make_source(w, h, K, 100, "D1", True, scale, True)
+    flags, normals = ops.edge_vertices(cu(g[tag + "_depth_rgb"]), src, K)
+    idx = np.flatnonzero(flags.cpu().numpy().reshape(-1))
+    assert np.array_equal(idx, g[tag + "_unused"])                       # the reference's unused_indices, exactly
+    got = normals.cpu().numpy().reshape(-1, 3)[idx]
+    np.testing.assert_allclose(got, g[tag + "_removed_normals"], rtol=0, atol=1e-14)
+    # the drop-in module surface: get_mesh_from_depth_map(remove_edges=True, return_normals_of_removed=True)
+    depth = orc.apply_depth_scale(orc.decode_rgb_depth_frame(g[tag + "_depth_rgb"], 100, True), scale)
+    mesh, unused, removed = dmt.get_mesh_from_depth_map(depth, K, g[tag + "_colour"], None, remove_edges=True, of_by_one=True,
+                                                        return_normals_of_removed=True)
+    assert np.array_equal(unused, g[tag + "_unused"]) and np.abs(removed - g[tag + "_removed_normals"]).max() < 1e-14
+    mesh2, used = dmt.get_mesh_from_depth_map(depth, K, g[tag + "_colour"], None, remove_edges=True, of_by_one=True)
+    assert np.array_equal(np.setdiff1d(np.arange(w * h), used), g[tag + "_unused"])
+
+
+@pytest.mark.parametrize("tag", ["plain", "posed"])
+def test_infill_mask_painting_matches_reference_lines(golden_dir, tag):
+    """E2 + E3 on the reference's own inputs: same left-eye image (holes = green) in, the reference's mask image before
+    inpainting and its painted eye image out -- byte for byte; then the host finish against the reference's final mask."""
+    from metric_depth_video_toolbox_b200 import infill
+
+    g, io, w, h, xfov, conv, K, scale, M = _infill_case(golden_dir, tag)
+    d, c = cu(g[tag + "_depth_rgb"]), cu(g[tag + "_colour"])
+    src = ops.make_source(w, h, K, 100, "D1", True, scale, True)
+    flags, normals = ops.edge_vertices(d, src, K)
+    left = g[tag + "_left_image_u8"]
+    hole = np.all(left == (0, 255, 0), axis=-1)
+    image = left.copy()
+    image[hole] = 0
+    image_dev, hole_dev = cu(image), cu(hole.astype(np.uint8) * 255)
+    mask_img = torch.zeros((h, w, 3), dtype=torch.uint8, device=DEV)
+    zbuf = ops.new_zbuf(1, w, h, DEV)[0]
+    ops.edge_splat(d, src, K, flags, M, K, w, h, zbuf)
+    ops.edge_resolve(zbuf, d, src, K, normals, M, c, hole_dev, mask_img, image_dev)
+    assert bool((zbuf == -1).all())
+    assert np.array_equal(mask_img.cpu().numpy(), g[tag + "_mask_pre_inpaint"])
+    assert np.array_equal(image_dev.cpu().numpy(), g[tag + "_image_final"])
+    assert np.array_equal(infill.finish_mask(mask_img.cpu().numpy()), g[tag + "_mask_final"])
+    # --green_and_black_infill_mask: no normals, no borders, but the edge colours are still painted (:777,794,813)
+    image_dev2 = cu(image)
+    ops.edge_splat(d, src, K, flags, M, K, w, h, zbuf)
+    ops.edge_resolve(zbuf, d, src, K, None, M, c, hole_dev, mask_img, image_dev2, code_normals=False)
+    assert np.array_equal(mask_img.cpu().numpy(), orc.mask_to_rgb(hole.astype(np.uint8) * 255))
+    assert np.array_equal(image_dev2.cpu().numpy(), g[tag + "_image_final"])
+
+
+def test_infill_mask_renderer_end_to_end(golden_dir):
+    """InfillMaskRenderer (GPU render + E1-E3) against the oracle chain on a synthetic frame, both eyes."""
+    from metric_depth_video_toolbox_b200 import infill
+    from metric_depth_video_toolbox_b200.stereo import StereoParams, StereoRerenderer
+    from oracle import infill_oracle as io
+
+    w, h = 160, 96
+    depth, colour = SyntheticClip(w, h, 2, zero_fraction=0.003).frames()
+    rr = StereoRerenderer(StereoParams(w, h, xfov=60.0, infill_mask=True), DEV)
+    im = infill.InfillMaskRenderer(rr, workers=2)
+    sbs, mask_img = im.render_device(cu(depth), cu(colour))
+    K = orc.camera_matrix(60.0, None, w, h)
+    scale = orc.master_fov_depth_scale(45.0, 60.0)
+    f = 1
+    d_scaled = orc.apply_depth_scale(orc.decode_rgb_depth_frame(depth[f], 100, True), scale)
+    unused, normals = io.edge_vertices(d_scaled, K, True)
+    pts, ends = io.edge_points(d_scaled, K, unused, normals)
+    for e, eye in enumerate(("left", "right")):
+        M = orc.eye_pose(eye, 0.063, None)
+        img, _, _ = orc.render_view(depth[f], colour[f], 100, K, M, depth_scale=scale, bg_rgb=(0, 255, 0), hole_fill=(0, 255, 0))
+        want_mask, want_img, _, _ = io.mask_before_inpaint(img, colour[f], pts, ends, unused, M, K)
+        got_mask = mask_img[f, :, e * w:(e + 1) * w].cpu().numpy()
+        got_img = sbs[f, :, e * w:(e + 1) * w].cpu().numpy()
+        assert (got_mask != want_mask).any(axis=-1).mean() < 3e-3 and (got_img != want_img).any(axis=-1).mean() < 3e-3
+        assert (want_mask != 0).any()
+    final = im.finish(mask_img.cpu().numpy())
+    assert final.shape == (2, h, 2 * w, 3) and final.dtype == np.uint8
+    assert np.array_equal(final[f, :, :w], infill.finish_mask(mask_img[f, :, :w].cpu().numpy()))
+
+
+def test_cli_infill_mask_normals_coded(clip_files, tmp_path):
+    """`--infill_mask` as movie_2_3D passes it (movie_2_3D.py:440): edge colours in the holes of the SBS video and the
+    normals-coded, inpainted, blurred mask video -- against the oracle chain that is pinned to the reference's lines."""
+    import shutil
+
+    import stereo_rerender
+    from metric_depth_video_toolbox_b200 import infill
+    from oracle import infill_oracle as io
+
+    c = clip_files
+    work = tmp_path / "infill"
+    work.mkdir()
+    for name in ("depth.mkv", "colour.mkv"):
+        shutil.copy(c["dir"] / name, work / name)
+    dv = str(work / "depth.mkv")
+    assert stereo_rerender.main(["--depth_video", dv, "--color_video", str(work / "colour.mkv"), "--xfov", "60", "--infill_mask",
+                                 "--max_frames", "2"]) == 0
+    sbs = video_io.read_clip(dv + "_stereo.mkv")
+    msk = video_io.read_clip(dv + "_stereo.mkv_infillmask.mkv")
+    w, h = c["w"], c["h"]
+    assert sbs.shape == msk.shape == (2, h, 2 * w, 3)
+    K = orc.camera_matrix(60.0, None, w, h)
+    scale = orc.master_fov_depth_scale(45.0, 60.0)
+    for k in range(2):
+        d_scaled = orc.apply_depth_scale(orc.decode_rgb_depth_frame(c["depth"][k], 100, True), scale)
+        unused, normals = io.edge_vertices(d_scaled, K, True)
+        pts, ends = io.edge_points(d_scaled, K, unused, normals)
+        for e, eye in enumerate(("left", "right")):
+            M = orc.eye_pose(eye, 0.063, None)
+            img, _, _ = orc.render_view(c["depth"][k], c["colour"][k], 100, K, M, depth_scale=scale, bg_rgb=(0, 255, 0), hole_fill=(0, 255, 0))
+            pre, want_img, green, area = io.mask_before_inpaint(img, c["colour"][k], pts, ends, unused, M, K)
+            assert (sbs[k, :, e * w:(e + 1) * w] != want_img).any(axis=-1).mean() < 3e-3
+            # TELEA spreads a differing seed pixel over its neighbourhood: compare where the inputs agree
+            want_final = io.finish_mask(pre, green, area)
+            got_final = msk[k, :, e * w:(e + 1) * w]
+            assert (np.abs(got_final.astype(int) - want_final.astype(int)) > 2).any(axis=-1).mean() < 0.02
+            assert (want_final != 0).any()
