@@ -118,7 +118,12 @@ def output_names(args):
 
 
 def main(argv: Optional[List[str]] = None) -> int:
-    args = build_parser().parse_args(argv)
+    return run(build_parser().parse_args(argv))
+
+
+def run(args, keep_process_group: bool = False) -> int:
+    """The script body for already-parsed arguments.  keep_process_group: leave torch.distributed initialised (a caller
+    that renders several clips in one torchrun job, e.g. movie_steps.step5_render_sbs)."""
     if args.xfov is None and args.yfov is None and args.xfov_file is None:
         raise ValueError("Error: Either --xfov_file, --xfov or --yfov must be provided.")
     if args.green_and_black_infill_mask and args.do_basic_infill:
@@ -191,7 +196,7 @@ def main(argv: Optional[List[str]] = None) -> int:
         if "depth" in writers:
             depth_frames_helper.verify_and_move(output_tmp_file + "_depth.mkv", total_frames, output_file + "_depth.mkv")
         print(f"\nProcessing complete ({total_done} frames, {total_done / max(1e-9, time.time() - t0):.1f} frames/s). Output saved to: {output_file}")
-    if world_size > 1:
+    if world_size > 1 and not keep_process_group:
         import torch.distributed as dist
 
         dist.destroy_process_group()

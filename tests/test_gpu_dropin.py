@@ -578,3 +578,47 @@ def test_cli_infill_mask_normals_coded(clip_files, tmp_path):
             got_final = msk[k, :, e * w:(e + 1) * w]
             assert (np.abs(got_final.astype(int) - want_final.astype(int)) > 2).any(axis=-1).mean() < 0.02
             assert (want_final != 0).any()
+
+
+def test_movie_2_3d_steps_4_and_5(clip_files, tmp_path):
+    """BASELINE config 5 in miniature: precomputed depth + colour + focus-mask videos of one scene -> convergence list
+    (step 4) -> stereo SBS + normals-coded infill mask videos (step 5), through the reference's step signatures."""
+    import argparse
+    import shutil
+
+    import movie_2_3D
+    from oracle import infill_oracle as io
+
+    c = clip_files
+    work = tmp_path / "movie"
+    work.mkdir()
+    for name in ("depth.mkv", "colour.mkv"):
+        shutil.copy(c["dir"] / name, work / name)
+    w, h, n = c["w"], c["h"], c["n"]
+    focus = np.zeros((n, h, w, 3), dtype=np.uint8)
+    focus[:, h // 4: h // 2, w // 4: w // 2] = 255
+    video_io.write_clip(str(work / "mask.mkv"), focus, 24.0)
+    scene = {"finished": False, "scene_video_file": str(work / "colour.mkv"), "depth_video_file": str(work / "depth.mkv"),
+             "mask_video_file": str(work / "mask.mkv"), "xfov": 60.0, "sbs": str(work / "depth.mkv") + "_stereo.mkv"}
+    movie_2_3D.step4_find_convergence([scene])
+    conv = json.load(open(scene["convergence_file"]))
+    want_conv = [orc.convergence_depth_of_frame(c["depth"][k], 100, focus[k, ..., 0]) for k in range(n)]
+    np.testing.assert_allclose(conv, want_conv, rtol=2e-6)
+    movie_2_3D.step5_render_sbs(argparse.Namespace(parallel=4), [scene])
+    sbs = video_io.read_clip(scene["sbs"])
+    msk = video_io.read_clip(scene["sbs"] + "_infillmask.mkv")
+    assert sbs.shape == msk.shape == (n, h, 2 * w, 3)
+    smooth = orc.smooth_convergence(orc.fill_nan_with_closest(conv))
+    k = 3
+    K = orc.camera_matrix(60.0, None, w, h)
+    scale = orc.master_fov_depth_scale(45.0, 60.0)
+    theta = orc.convergence_angle(smooth[k] * scale, 0.063)
+    d_scaled = orc.apply_depth_scale(orc.decode_rgb_depth_frame(c["depth"][k], 100, True), scale)
+    unused, normals = io.edge_vertices(d_scaled, K, True)
+    pts, ends = io.edge_points(d_scaled, K, unused, normals)
+    M = orc.eye_pose("left", 0.063, theta)
+    img, _, _ = orc.render_view(c["depth"][k], c["colour"][k], 100, K, M, depth_scale=scale, bg_rgb=(0, 255, 0), hole_fill=(0, 255, 0))
+    _, want_img, _, _ = io.mask_before_inpaint(img, c["colour"][k], pts, ends, unused, M, K)
+    assert (sbs[k, :, :w] != want_img).any(axis=-1).mean() < 4e-3
+    # a second call finds the outputs and skips the scene (movie_2_3D.py:431)
+    movie_2_3D.step5_render_sbs(argparse.Namespace(parallel=4), [scene])

@@ -165,3 +165,18 @@ def test_chunk_reader_writer_round_trip(tmp_path):
     assert np.array_equal(np.concatenate(got_a), a[2:]) and np.array_equal(np.concatenate(got_b), b[2:])
     grey = [c[0].numpy().copy() for _, c in video_io.ChunkReader([pa], chunk=4, pin=False, grey=[True])]
     assert np.concatenate(grey).shape == (7, 32, 48)
+
+
+def test_movie_step5_command_line_matches_reference_string():
+    """movie_2_3D.py:431-445 builds `stereo_rerender.py --color_video S {conv} {xfov} --depth_video D {edge} {infm}`."""
+    from metric_depth_video_toolbox_b200.cli import stereo_rerender
+    from metric_depth_video_toolbox_b200.movie_steps import stereo_rerender_argv
+
+    scene = {"scene_video_file": "s.mkv", "depth_video_file": "d.mkv", "convergence_file": "c.json", "xfov": 52.5}
+    assert stereo_rerender_argv(scene) == ["--color_video", "s.mkv", "--convergence_file", "c.json", "--xfov", "52.5", "--depth_video", "d.mkv",
+                                           "--infill_mask"]
+    scene = {"scene_video_file": "s.mkv", "depth_video_file": "d.mkv", "xfovs_file": "x.json", "xfov": None, "infill": False, "convergence": False}
+    argv = stereo_rerender_argv(scene)
+    assert argv == ["--color_video", "s.mkv", "--xfov_file", "x.json", "--depth_video", "d.mkv"]
+    args = stereo_rerender.build_parser().parse_args(argv)
+    assert args.xfov_file == "x.json" and not args.infill_mask and args.convergence_file is None
