@@ -316,7 +316,7 @@ def test_full_size_properties_1080p():
     assert 0.001 < hole_frac < 0.2
 
 
-@pytest.mark.parametrize("threads", ["128", "160", "256"])
+@pytest.mark.parametrize("threads", ["128", "160", "256", "320"])
 def test_stereo_rows_every_cta_size_gives_identical_bytes(threads):
     """The fast kernel is instantiated for several CTA sizes (MDVT_ROW_THREADS); each must reproduce the model
     bit for bit.  The choice is read once per process, hence the subprocess."""
@@ -342,3 +342,39 @@ def test_stereo_rows_every_cta_size_gives_identical_bytes(threads):
     env = dict(os.environ, MDVT_ROW_THREADS=threads)
     proc = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert proc.returncode == 0 and "ok" in proc.stdout, proc.stderr[-2000:]
+
+
+def test_full_size_properties_4k_novel_view_and_rows():
+    """BASELINE configs[2] size (3840x2160).  (a) a camera at the origin looking down +z is the identity warp: the
+    render equals the colour frame wherever the depth code is non-zero, holes exactly where it is zero;
+    (b) moving the camera keeps every drawn pixel a colour of the source frame and leaves holes;
+    (c) the row kernel at 4K is bit-exact against the model on a band of rows and an ipd of 0 is the identity."""
+    from metric_depth_video_toolbox_b200.novel_view import NovelViewParams, NovelViewRenderer
+
+    w, h = 3840, 2160
+    depth, colour = SyntheticClip(w, h, 1, zero_fraction=0.002).frames()
+    d, c = cu(depth), cu(colour)
+    nv = NovelViewRenderer(NovelViewParams(w, h, 60, None, 100, (0.0, 0.0, 0.0), (0.0, 0.0, 1.0)), DEV)
+    assert np.allclose(nv.extrinsic(np.zeros(3))[:3, :4], np.eye(4)[:3, :4])
+    rgb, mask = nv.render_device(d, c)
+    code_zero = torch.from_numpy((depth[0, ..., 0] == 0) & (depth[0, ..., 2] == 0)).to(DEV)
+    assert torch.equal(mask[0] == 255, code_zero)
+    assert torch.equal(rgb[0][~code_zero], c[0][~code_zero])
+    white = torch.tensor([255, 255, 255], dtype=torch.uint8, device=DEV)
+    assert bool((rgb[0][code_zero] == white).all())
+    nv2 = NovelViewRenderer(NovelViewParams(w, h, 60, None, 100), DEV)  # the script's default camera (2, 2, -4) -> centroid
+    rgb2, mask2 = nv2.render_device(d, c)
+    hole_frac = (mask2 == 255).float().mean().item()
+    assert 0.05 < hole_frac < 0.95
+    drawn = (mask2[0] == 0)
+    assert bool(((rgb2[0][~drawn] == white).all(dim=-1)).all())
+    # (c) row kernel at W = 3840
+    consts0 = cu(ops.stereo_frame_constants(60.0, w, 100, 0, 45.0)[None])
+    sbs, m = ops.stereo_rows(d, c, consts0)
+    for half in (slice(0, w), slice(w, 2 * w)):
+        assert torch.equal(m[0, :, half] == 255, code_zero) and torch.equal(sbs[0, :, half][~code_zero], c[0][~code_zero])
+    k = ops.stereo_frame_constants(60.0, w, 100, 63, 45.0)
+    sbs, m = ops.stereo_rows(d, c, cu(k[None]))
+    rows = slice(1000, 1016)
+    want_sbs, want_mask, _ = km.stereo_rows_f32(depth[0, rows], colour[0, rows], k)
+    assert np.array_equal(sbs[0, rows].cpu().numpy(), want_sbs) and np.array_equal(m[0, rows].cpu().numpy(), want_mask)
