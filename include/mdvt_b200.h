@@ -138,6 +138,14 @@ MDVT_API int mdvt_touchly_depth(const void *depth_src, int width, int height, in
                        float depth_scale, float touchly_min, float touchly_max, float gain, int zero_is_far,
                        uint8_t *out_rgb, int64_t out_pitch, void *stream);
 
+/* cv2.remap(src, map_x, map_y, INTER_LINEAR, BORDER_CONSTANT, border_rgb) for u8x3 images and float32 maps
+ * (dst_w*dst_h each), bit-exact with OpenCV's fixed-point bilinear (1/32-pixel coordinates, 15-bit weights): the
+ * per-pixel part of stereo_rerender.convert_to_equirectangular (stereo_rerender.py:25-86), used for --vr180 /
+ * --touchly0 (:914-916).  Row r of src / dst at + r*pitch bytes. */
+MDVT_API int mdvt_remap_bilinear_u8x3(const uint8_t *src, int src_w, int src_h, int64_t src_pitch, const float *map_x,
+                             const float *map_y, int dst_w, int dst_h, uint32_t border_rgb, uint8_t *dst,
+                             int64_t dst_pitch, void *stream);
+
 /* ---- decode + unproject (+ pose) -> point cloud --------------------------------------------- */
 /* `depth_src` below is the u8x3 wire-format frame (n*3 bytes), or n float32 depths when
  * src->decoder == MDVT_SOURCE_F32.

@@ -66,6 +66,8 @@ _PROTOTYPES = {
     "mdvt_depth_to_grey": (C.c_int, [_u8p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, _stream]),
     "mdvt_touchly_depth": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                      C.c_int, _u8p, C.c_int64, _stream]),
+    "mdvt_remap_bilinear_u8x3": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int64, _f32p, _f32p, C.c_int, C.c_int, C.c_uint32, _u8p, C.c_int64,
+                                           _stream]),
     "mdvt_transform_points_f64": (C.c_int, [_f64p, C.c_int64, C.POINTER(C.c_double), _f64p, _stream]),
     "mdvt_project_points_f64": (C.c_int, [_f64p, C.c_int64, C.POINTER(C.c_double), _f64p, _stream]),
     "mdvt_zbuf_clear": (C.c_int, [_u64p, C.c_int64, _stream]),

@@ -27,9 +27,11 @@ class StereoJob:
     def __init__(self, args, params: StereoParams, device: torch.device, frame_width: int, frame_height: int):
         self.args, self.params, self.device = args, params, device
         self.w, self.h = frame_width, frame_height
-        for flag in ("touchly0", "vr180"):
-            if getattr(args, flag, False):
-                raise NotImplementedError(f"--{flag} needs the VR180 equirectangular remap, which is not built yet")
+        self.touchly0 = bool(getattr(args, "touchly0", False))
+        self.vr180 = bool(getattr(args, "vr180", False)) or self.touchly0       # :406-407
+        if self.vr180 and args.infill_mask:
+            raise NotImplementedError("--vr180 / --touchly0 with --infill_mask: the reference itself fails here (a 1920x1920 hole "
+                                      "mask indexed into a frame-sized mask image, stereo_rerender.py:527-528,740,787-792)")
         if getattr(args, "do_basic_infill", False):
             raise NotImplementedError("--do_basic_infill (normal-march infill) is not built yet")
         # stereo_rerender.py:568-573,589: the mesh edge test runs for --infill_mask / --remove_edges / --do_basic_infill unless
@@ -42,11 +44,14 @@ class StereoJob:
             raise NotImplementedError("--touchly1 with a pose file and --infill_mask: the reference itself fails here "
                                       "(cv2.cvtColor(RGB2BGR) on its single-channel mask, stereo_rerender.py:701-702)")
         self.out_size = (self.w, 2 * self.h) if self.touchly1 else (2 * self.w, self.h)
+        if self.vr180 and not self.touchly1:
+            self.vr_side = 1920                                                 # out_width, out_height = 1920, 1920 (:528)
+            self.out_size = ((3 if self.touchly0 else 2) * self.vr_side, self.vr_side)
         self.has_depth_output = bool(getattr(args, "create_sbs_depth_video", False)) and not self.touchly1
         self.writes_mask = bool(args.infill_mask) and not self.touchly1  # the touchly1 fast path never writes mask frames
         self.renderer = StereoRerenderer(params, device)
         self.infill = None
-        if (self.paint_edges or self.code_normals) and not self.touchly1:
+        if (self.paint_edges or self.code_normals) and not self.touchly1 and not self.vr180:
             from ..infill import InfillMaskRenderer
 
             self.infill = InfillMaskRenderer(self.renderer)
@@ -156,8 +161,66 @@ class StereoJob:
         host.copy_(out, non_blocking=True)
         return {"main": host}
 
+    # ---- vr180 / touchly0 ---------------------------------------------------------------------------
+    def _vr180_chunk(self, depth_rgb, colour, first_frame):
+        """stereo_rerender.py:527-541,704-738,823-852,910-918: both eyes rendered by a square 1920x1920 camera of
+        render_fov = max(75, widest source FOV), that FOV also taken as the master FOV of the depth scale; every
+        panel (left, right, and for touchly0 the left eye's reverse-depth image) goes through the equirect remap."""
+        import math
+
+        from .. import geometry as geo
+        from .. import ops, vr180
+
+        p, a, side = self.params, self.args, self.vr_side
+        n = depth_rgb.shape[0]
+        d = self._dev_buf("d", depth_rgb.shape)
+        c = self._dev_buf("c", colour.shape)
+        d.copy_(depth_rgb, non_blocking=True)
+        c.copy_(colour, non_blocking=True)
+        if self._zbuf is None:
+            self._zbuf = ops.new_zbuf(2, side, side, self.device)
+        rect = self._dev_buf("rect", (n, side, 2 * side, 3))
+        depth = self._dev_buf("rectdepth", (n, side, 2 * side), torch.float32) if self.touchly0 else None
+        sources, views, fovs = [], [], []
+        ipd = p.pupillary_distance / 1000
+        for k in range(n):
+            f = first_frame + k
+            xf = p.xfov_of(f)
+            K = geo.compute_camera_matrix(xf, None if p.xfovs is not None else p.yfov, self.w, self.h)
+            fovx, fovy = geo.fov_from_camera_matrix(K)
+            if max(fovx, fovy) >= 180:
+                raise ValueError("fov cant be 180 or over, the tool is not built to handle fisheye distorted input video")
+            render_fov = max(75, max(fovx, fovy))
+            Kr = geo.compute_camera_matrix(render_fov, render_fov, side, side)
+            scale = 1.0 / (math.tan(math.radians(render_fov / 2)) / math.tan(math.radians(xf / 2)))
+            theta = None
+            if p.convergence_depths is not None and float(p.convergence_depths[f]) != 0:
+                theta = geo.convergence_angle(float(p.convergence_depths[f]) * scale, ipd)
+            T = np.eye(4) if p.transformations is None else np.asarray(p.transformations[f], dtype=np.float64)
+            sources.append(ops.make_source(self.w, self.h, K, p.max_depth, "D1", True, scale, False))
+            views.append([ops.ViewSpec(geo.stereo_eye_pose(eye, ipd, theta) @ T, Kr[0, 0], Kr[1, 1], Kr[0, 2], Kr[1, 2]) for eye in ("left", "right")])
+            fovs.append(render_fov)
+        ops.render_views(d, c, sources, views, side, side, self._zbuf, rect, None, depth, p.bg_rgb, (0, 0, 0), 0, p.near)
+        panels = 3 if self.touchly0 else 2
+        out = self._dev_buf("vr", (n, side, panels * side, 3))
+        tdepth = self._dev_buf("tdepth", (side, side, 3)) if self.touchly0 else None
+        for k in range(n):
+            mx, my = vr180.device_maps(side, side, fovs[k], self.device)
+            for e in range(2):
+                ops.remap_bilinear(rect[k, :, e * side:(e + 1) * side], mx, my, out=out[k, :, e * side:(e + 1) * side])
+            if self.touchly0:
+                ops.touchly_depth(depth[k, :, :side].contiguous(), a.touchly_min_depth, a.touchly_max_depth, True, decoder="F32", out=tdepth)
+                ops.remap_bilinear(tdepth, mx, my, out=out[k, :, 2 * side:])
+        host = self._host_buf("main", out.shape)
+        host.copy_(out, non_blocking=True)
+        return {"main": host}
+
     def render_chunk(self, depth_rgb: torch.Tensor, colour: torch.Tensor, first_frame: int) -> Dict[str, torch.Tensor]:
-        return self._touchly1_chunk(depth_rgb, colour, first_frame) if self.touchly1 else self._stereo_chunk(depth_rgb, colour, first_frame)
+        if self.touchly1:
+            return self._touchly1_chunk(depth_rgb, colour, first_frame)
+        if self.vr180:
+            return self._vr180_chunk(depth_rgb, colour, first_frame)
+        return self._stereo_chunk(depth_rgb, colour, first_frame)
 
 
 def join_segments(parts: List[str], out_path: str, fourcc: str, fps: float, size):

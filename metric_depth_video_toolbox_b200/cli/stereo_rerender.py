@@ -26,7 +26,9 @@ import torch
 
 from .. import depth_frames_helper, sharding, video_io
 from ..geometry import convergence_angle, curve_fit, fill_nan_with_closest, rebase_transformations  # noqa: F401
+from ..infill import masked_blur  # noqa: F401  (module-level helpers other reference scripts import from stereo_rerender)
 from ..stereo import StereoParams, StereoRerenderer
+from ..vr180 import convert_to_equirectangular  # noqa: F401
 
 UNSUPPORTED = {
     "mask_video": "--mask_video (background accumulation) is sequential host state outside the per-frame GPU path",

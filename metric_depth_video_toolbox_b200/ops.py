@@ -147,6 +147,29 @@ def touchly_depth(depth_src: torch.Tensor, touchly_min: float, touchly_max: floa
     return out
 
 
+def remap_bilinear(src: torch.Tensor, map_x: torch.Tensor, map_y: torch.Tensor, out: Optional[torch.Tensor] = None,
+                   border_rgb=(0, 0, 0)) -> torch.Tensor:
+    """cv2.remap(src, map_x, map_y, INTER_LINEAR, BORDER_CONSTANT) for (H, W, 3) u8 images, bit-exact with OpenCV.
+    `src` / `out` may be column slices of wider frames (dense rows)."""
+    for t, name in ((src, "src"), (out, "out")):
+        if t is None:
+            continue
+        if t.dtype != torch.uint8 or not t.is_cuda or t.dim() != 3 or t.shape[2] != 3 or t.stride(2) != 1 or t.stride(1) != 3:
+            raise ValueError(f"{name} must be a (H, W, 3) u8 CUDA view with dense rows")
+    _need(map_x, torch.float32, "map_x")
+    _need(map_y, torch.float32, "map_y")
+    if map_x.shape != map_y.shape or map_x.dim() != 2:
+        raise ValueError("map_x / map_y must be (H_out, W_out) float32")
+    dh, dw = map_x.shape
+    if out is None:
+        out = torch.empty((dh, dw, 3), dtype=torch.uint8, device=src.device)
+    if tuple(out.shape) != (dh, dw, 3):
+        raise ValueError("out does not match the maps")
+    _lib.check(_lib.load().mdvt_remap_bilinear_u8x3(_ptr(src), src.shape[1], src.shape[0], src.stride(0), _ptr(map_x), _ptr(map_y), dw, dh,
+                                                    pack_rgb(border_rgb), _ptr(out), out.stride(0), _stream()))
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # geometry
 # ---------------------------------------------------------------------------------------------

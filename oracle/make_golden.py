@@ -153,6 +153,12 @@ def golden_misc(dmt, sr):
         filled = sr.fill_nan_with_closest(list(vals))
         out[f"conv_filled{k}"] = np.array(filled)
         out[f"conv_smooth{k}"] = np.asarray(sr.curve_fit(filled))
+    # VR180 remap (stereo_rerender.py:25-86) on small frames: the reference's own maps + cv2.remap
+    eq = np.random.default_rng(33)
+    for k, (hw, fov) in enumerate((((48, 64), 75.0), ((60, 60), 100.0), ((33, 70), 120.0))):
+        img = eq.integers(0, 256, hw + (3,), dtype=np.uint8)
+        out[f"equirect_in{k}"], out[f"equirect_fov{k}"] = img, np.array(fov)
+        out[f"equirect_out{k}"] = sr.convert_to_equirectangular(img, input_fov=fov)
     np.savez_compressed(os.path.join(OUT, "misc.npz"), **out)
 
 

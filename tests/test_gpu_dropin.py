@@ -622,3 +622,79 @@ def test_movie_2_3d_steps_4_and_5(clip_files, tmp_path):
     assert (sbs[k, :, :w] != want_img).any(axis=-1).mean() < 4e-3
     # a second call finds the outputs and skips the scene (movie_2_3D.py:431)
     movie_2_3D.step5_render_sbs(argparse.Namespace(parallel=4), [scene])
+
+
+# ---------------------------------------------------------------------------------------------
+# VR180: bit-exact cv2.remap on the GPU, --vr180 / --touchly0
+# ---------------------------------------------------------------------------------------------
+def test_remap_bilinear_bit_exact_vs_opencv(golden_dir):
+    import cv2
+
+    import stereo_rerender
+
+    rng = np.random.default_rng(9)
+    img = rng.integers(0, 256, (61, 83, 3), dtype=np.uint8)
+    mx = rng.uniform(-4, 87, (70, 90)).astype(np.float32)
+    my = rng.uniform(-4, 65, (70, 90)).astype(np.float32)
+    mx[0, :5] = [0.0, 82.0, 82.5, -0.5, 1e9]          # exact pixel, last column, half out, half out, far out
+    my[0, :5] = [0.0, 60.0, 60.5, -0.5, -1e9]
+    mx[1, :4] = [10.015625, 10.484375, 10.5, 10.515625]  # ties of the 1/32-pixel quantisation (round half to even)
+    my[1, :4] = 20.0
+    want = cv2.remap(img, mx, my, interpolation=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=(0, 0, 0))
+    got = ops.remap_bilinear(cu(img), cu(mx), cu(my)).cpu().numpy()
+    assert np.array_equal(got, want)
+    g = np.load(os.path.join(golden_dir, "misc.npz"))
+    for k in range(3):  # the drop-in function against the reference's own outputs
+        out = stereo_rerender.convert_to_equirectangular(g[f"equirect_in{k}"], input_fov=float(g[f"equirect_fov{k}"]))
+        assert isinstance(out, np.ndarray) and np.array_equal(out, g[f"equirect_out{k}"]), k
+    big = rng.integers(0, 256, (1920, 1920, 3), dtype=np.uint8)
+    from metric_depth_video_toolbox_b200 import vr180
+
+    bx, by = vr180.equirect_maps(1920, 1920, 75.0)
+    want = cv2.remap(big, bx, by, interpolation=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=(0, 0, 0))
+    assert np.array_equal(stereo_rerender.convert_to_equirectangular(big, input_fov=75.0), want)
+
+
+def test_cli_vr180_and_touchly0(clip_files, tmp_path):
+    import shutil
+
+    import cv2
+
+    import stereo_rerender
+    from metric_depth_video_toolbox_b200 import vr180
+
+    c = clip_files
+    work = tmp_path / "vr"
+    work.mkdir()
+    for name in ("depth.mkv", "colour.mkv"):
+        shutil.copy(c["dir"] / name, work / name)
+    dv, cv = str(work / "depth.mkv"), str(work / "colour.mkv")
+    assert stereo_rerender.main(["--depth_video", dv, "--color_video", cv, "--xfov", "60", "--touchly0", "--max_frames", "1"]) == 0
+    out = video_io.read_clip(dv + "_Touchly0.mkv")
+    side = 1920
+    assert out.shape == (1, side, 3 * side, 3)
+    w, h = c["w"], c["h"]
+    K = orc.camera_matrix(60.0, None, w, h)
+    fovx, fovy = orc.fov_of_camera_matrix(K)
+    render_fov = max(75, max(fovx, fovy))
+    Kr = orc.camera_matrix(render_fov, render_fov, side, side)
+    scale = orc.master_fov_depth_scale(render_fov, 60.0)   # the render FOV is the master FOV in this mode (:534-538)
+    mx, my = vr180.equirect_maps(side, side, render_fov)
+    for e, eye in enumerate(("left", "right")):
+        M = orc.eye_pose(eye, 0.063, None)
+        img, _, ids = orc.render_view(c["depth"][0], c["colour"][0], 100, K, M, depth_scale=scale, K_out=Kr, out_size=(side, side))
+        want = cv2.remap(img, mx, my, interpolation=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=(0, 0, 0))
+        got = out[0, :, e * side:(e + 1) * side]
+        assert (got != want).any(axis=-1).mean() < 5e-3 and want.any()
+        if e == 0:  # third panel: the left eye's reverse depth through the same remap (:825-829,911-916)
+            u, v, z = orc.view_uvz(c["depth"][0], 100, K, M, depth_scale=scale, K_out=Kr)
+            zplane = orc.zbuffer_depth(ids, z)
+            d8 = np.rint(np.maximum(0, np.minimum(zplane, 5) - 0) * (255 / 5)).astype(np.uint8)
+            d8[d8 == 0] = 255
+            panel = cv2.remap(np.repeat((255 - d8)[..., None], 3, axis=-1), mx, my, interpolation=cv2.INTER_LINEAR,
+                              borderMode=cv2.BORDER_CONSTANT, borderValue=(0, 0, 0))
+            assert (np.abs(out[0, :, 2 * side:].astype(int) - panel.astype(int)) > 1).any(axis=-1).mean() < 5e-3
+    assert stereo_rerender.main(["--depth_video", dv, "--color_video", cv, "--xfov", "60", "--vr180", "--max_frames", "1"]) == 0
+    assert video_io.read_clip(dv + "_stereo.mkv").shape == (1, side, 2 * side, 3)
+    with pytest.raises(NotImplementedError, match="reference itself fails"):
+        stereo_rerender.main(["--depth_video", dv, "--color_video", cv, "--xfov", "60", "--vr180", "--infill_mask"])

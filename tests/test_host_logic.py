@@ -180,3 +180,19 @@ def test_movie_step5_command_line_matches_reference_string():
     assert argv == ["--color_video", "s.mkv", "--xfov_file", "x.json", "--depth_video", "d.mkv"]
     args = stereo_rerender.build_parser().parse_args(argv)
     assert args.xfov_file == "x.json" and not args.infill_mask and args.convergence_file is None
+
+
+def test_equirect_maps_match_reference(golden_dir):
+    """The VR180 coordinate maps are host-side NumPy (they depend on the frame size and FOV only); with OpenCV's remap
+    they must reproduce the reference's convert_to_equirectangular outputs bit for bit."""
+    import cv2
+
+    from metric_depth_video_toolbox_b200 import vr180
+
+    g = np.load(os.path.join(golden_dir, "misc.npz"))
+    for k in range(3):
+        img, fov = g[f"equirect_in{k}"], float(g[f"equirect_fov{k}"])
+        mx, my = vr180.equirect_maps(img.shape[0], img.shape[1], fov)
+        assert mx.dtype == np.float32 and (mx == -1).any()
+        out = cv2.remap(img, mx, my, interpolation=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=(0, 0, 0))
+        assert np.array_equal(out, g[f"equirect_out{k}"]), k
