@@ -259,6 +259,13 @@ MDVT_API int mdvt_edge_resolve(uint64_t *zbuf, const void *depth_src, const mdvt
                       int64_t hole_pitch, int out_w, int out_h, uint32_t bg_rgb, int code_normals, uint8_t *image,
                       int64_t image_pitch, uint8_t *mask_img, int64_t mask_pitch, void *stream);
 
+/* --do_basic_infill: stereo_rerender.infill_using_normals (stereo_rerender.py:155-240,810-812) for one eye, in place.
+ * image: u8x3 eye image with black holes; hole_mask: u8, non-zero = hole; mask_img: the FINAL mask image (u8x3, after
+ * inpainting and blur) whose R, G channels code the march direction as (m/255)*2-1.  max_steps: 400 in the reference. */
+MDVT_API int mdvt_normal_march_infill(uint8_t *image, int64_t image_pitch, const uint8_t *hole_mask, int64_t hole_pitch,
+                             const uint8_t *mask_img, int64_t mask_pitch, int width, int height, int max_steps,
+                             void *stream);
+
 /* ---- row-local stereo fast path: ONE fused kernel, frames batched ---------------------------- */
 /* Whole stereo_rerender.py frame loop body (:512-541 decode+scale, :583 unproject, :723-738,:831-852 eye
  * poses + render, :740,:787-793,:854 hole mask, :918 hconcat) for a batch of frames when there is no

@@ -89,6 +89,7 @@ _PROTOTYPES = {
                                   C.c_int, C.c_int, _u64p, _stream]),
     "mdvt_edge_resolve": (C.c_int, [_u64p, _u8p, C.POINTER(Source), C.POINTER(C.c_double), _f64p, C.POINTER(C.c_double), _u8p, _u8p,
                                     C.c_int64, C.c_int, C.c_int, C.c_uint32, C.c_int, _u8p, C.c_int64, _u8p, C.c_int64, _stream]),
+    "mdvt_normal_march_infill": (C.c_int, [_u8p, C.c_int64, _u8p, C.c_int64, _u8p, C.c_int64, C.c_int, C.c_int, C.c_int, _stream]),
     "mdvt_stereo_rows": (C.c_int, [_u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32,
                                    C.c_uint32, _u8p, _u8p, _f32p, _stream]),
 }

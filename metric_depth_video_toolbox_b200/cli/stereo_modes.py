@@ -32,11 +32,13 @@ class StereoJob:
         if self.vr180 and args.infill_mask:
             raise NotImplementedError("--vr180 / --touchly0 with --infill_mask: the reference itself fails here (a 1920x1920 hole "
                                       "mask indexed into a frame-sized mask image, stereo_rerender.py:527-528,740,787-792)")
-        if getattr(args, "do_basic_infill", False):
-            raise NotImplementedError("--do_basic_infill (normal-march infill) is not built yet")
+        self.basic_infill = bool(getattr(args, "do_basic_infill", False))
+        if self.basic_infill and not args.infill_mask:
+            raise NotImplementedError("--do_basic_infill without --infill_mask marks holes with a black background, which a black pixel "
+                                      "of the film is indistinguishable from; pass --infill_mask as movie_2_3D does")
         # stereo_rerender.py:568-573,589: the mesh edge test runs for --infill_mask / --remove_edges / --do_basic_infill unless
         # --dont_remove_edges; its vertices are painted into the holes unless --dont_place_points_in_edges
-        remove_edges = (args.infill_mask or args.remove_edges) and not args.dont_remove_edges
+        remove_edges = (args.infill_mask or args.remove_edges or self.basic_infill) and not args.dont_remove_edges
         self.paint_edges = bool(remove_edges and not args.dont_place_points_in_edges)
         self.code_normals = bool(args.infill_mask and not args.green_and_black_infill_mask)
         self.touchly1 = bool(getattr(args, "touchly1", False))
@@ -89,8 +91,11 @@ class StereoJob:
             dsbs = self._dev_buf("sbs", (n, self.h, 2 * self.w, 3))
             dmask = self._dev_buf("mask", (n, self.h, 2 * self.w, 3))
             ddepth = self._dev_buf("depth", (n, self.h, 2 * self.w), torch.float32) if self.has_depth_output else None
-            self.infill.render_device(d, c, first_frame, dsbs, dmask, self.code_normals, self.paint_edges, ddepth)
-            sbs.copy_(dsbs, non_blocking=True)
+            # with --do_basic_infill the holes are filled by the normal march instead of the edge colours (:810-814); the
+            # edge points still contribute their normals to the mask
+            self.infill.render_device(d, c, first_frame, dsbs, dmask, self.code_normals, self.paint_edges and not self.basic_infill, ddepth)
+            if not self.basic_infill:
+                sbs.copy_(dsbs, non_blocking=True)
             out = {"main": sbs}
             if ddepth is not None:
                 coded = ops.encode_depth(ddepth, self.params.max_depth, True, True)
@@ -102,6 +107,10 @@ class StereoJob:
                 if self.code_normals:  # host part: TELEA + masked blur per eye (OpenCV, as the reference)
                     torch.cuda.synchronize(self.device)
                     mask.copy_(torch.from_numpy(self.infill.finish(mask.numpy())))
+                    if self.basic_infill:  # final mask back to the device, march, filled image to the host
+                        dmask.copy_(mask, non_blocking=True)
+                        self.infill.basic_infill(dsbs, dmask)
+                        sbs.copy_(dsbs, non_blocking=True)
         else:
             from .. import ops
 

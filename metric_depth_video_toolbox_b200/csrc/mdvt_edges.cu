@@ -197,6 +197,48 @@ __global__ void __launch_bounds__(kThreads)
     }
 }
 
+// --do_basic_infill (stereo_rerender.infill_using_normals, :155-240): one thread per hole pixel marches along the XY
+// direction coded in the final mask image until it leaves the hole, then copies the colour found two / one / zero
+// steps further on (the first that is inside the frame and not a hole).  Float32, one rounding per operation, like
+// the NumPy code.  Only hole pixels are written and only non-hole pixels are read, so the image is updated in place.
+__global__ void __launch_bounds__(kThreads)
+    normal_march_kernel(uint8_t *__restrict__ image, int64_t image_pitch, const uint8_t *__restrict__ hole, int64_t hole_pitch,
+                        const uint8_t *__restrict__ mask_img, int64_t mask_pitch, int width, int height, int max_steps) {
+    const int64_t n = (int64_t)width * height;
+    for (int64_t p = blockIdx.x * (int64_t)kThreads + threadIdx.x; p < n; p += (int64_t)gridDim.x * kThreads) {
+        const int y = (int)(p / width), x = (int)(p - (int64_t)y * width);
+        if (!hole[y * hole_pitch + x]) continue;
+        const uint8_t *m = mask_img + y * mask_pitch + (int64_t)x * 3;
+        float dx = __fsub_rn(__fmul_rn(__fdiv_rn((float)m[0], 255.0f), 2.0f), 1.0f);  // ((m / 255) * 2) - 1 (:808,811)
+        float dy = __fsub_rn(__fmul_rn(__fdiv_rn((float)m[1], 255.0f), 2.0f), 1.0f);
+        const float norm = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+        if (!(norm > 1e-6f)) continue;
+        dx = __fdiv_rn(dx, norm);
+        dy = __fdiv_rn(dy, norm);
+        const float fx = (float)x, fy = (float)y;
+        auto at = [&](int t, int &xi, int &yi) {
+            xi = __float2int_rn(__fadd_rn(fx, __fmul_rn(dx, (float)t)));  // rint: half to even
+            yi = __float2int_rn(__fadd_rn(fy, __fmul_rn(dy, (float)t)));
+            return xi >= 0 && xi < width && yi >= 0 && yi < height;
+        };
+        for (int t = 1; t <= max_steps; ++t) {
+            int xi, yi;
+            if (!at(t, xi, yi)) break;                       // left the frame: the ray dies, the pixel stays as it is
+            if (hole[yi * hole_pitch + xi]) continue;
+            for (int dt = 2; dt >= 0; --dt) {
+                int x2, y2;
+                if (at(t + dt, x2, y2) && !hole[y2 * hole_pitch + x2]) {
+                    const uint8_t *s = image + y2 * image_pitch + (int64_t)x2 * 3;
+                    uint8_t *o = image + y * image_pitch + (int64_t)x * 3;
+                    o[0] = s[0]; o[1] = s[1]; o[2] = s[2];
+                    break;
+                }
+            }
+            break;
+        }
+    }
+}
+
 static int grid_for(int64_t work_items) {
     const int64_t blocks = (work_items + kThreads - 1) / kThreads;
     const int64_t cap = (int64_t)sm_count() * 8;
@@ -278,6 +320,18 @@ extern "C" int mdvt_edge_resolve(uint64_t *zbuf, const void *depth_src, const md
         mask_pitch)
     MDVT_DISPATCH_SOURCE(src->decoder, src->bit16, CALL);
 #undef CALL
+    MDVT_CUDA_TRY(cudaGetLastError());
+    return MDVT_OK;
+}
+
+extern "C" int mdvt_normal_march_infill(uint8_t *image, int64_t image_pitch, const uint8_t *hole_mask, int64_t hole_pitch,
+                                        const uint8_t *mask_img, int64_t mask_pitch, int width, int height, int max_steps, void *stream) {
+    MDVT_REQUIRE(width > 0 && height > 0, "bad frame size %dx%d", width, height);
+    MDVT_REQUIRE(image && hole_mask && mask_img, "NULL buffer");
+    MDVT_REQUIRE(image_pitch >= (int64_t)width * 3 && mask_pitch >= (int64_t)width * 3 && hole_pitch >= width, "pitch too small");
+    MDVT_REQUIRE(max_steps >= 0, "negative step count");
+    normal_march_kernel<<<grid_for((int64_t)width * height), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        image, image_pitch, hole_mask, hole_pitch, mask_img, mask_pitch, width, height, max_steps);
     MDVT_CUDA_TRY(cudaGetLastError());
     return MDVT_OK;
 }

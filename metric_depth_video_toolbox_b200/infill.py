@@ -93,6 +93,17 @@ class InfillMaskRenderer:
                                  p.bg_rgb, code_normals)
         return out_sbs, out_mask_img
 
+    def basic_infill(self, sbs: torch.Tensor, final_mask_img: torch.Tensor, max_steps: int = 400) -> torch.Tensor:
+        """--do_basic_infill (stereo_rerender.py:810-812,898-900): fill the holes of both eyes of the frames rendered by the
+        last render_device call by marching along the normals coded in the FINAL mask images (n, H, 2W, 3) u8 (device)."""
+        n, h, w2, _ = sbs.shape
+        w = w2 // 2
+        for k in range(n):
+            for e in range(2):
+                half = slice(e * w, (e + 1) * w)
+                ops.normal_march_infill(sbs[k, :, half], self._holes[k, :, half], final_mask_img[k, :, half], max_steps)
+        return sbs
+
     def finish(self, mask_img_host: np.ndarray) -> np.ndarray:
         """(n, H, 2W, 3) u8 pre-inpaint mask images (host) -> final mask frames; each eye is finished on its own, as the
         reference does (left_img_mask / right_img_mask, :805-808,893-896)."""

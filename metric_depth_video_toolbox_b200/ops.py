@@ -530,3 +530,17 @@ def edge_resolve(zbuf: torch.Tensor, depth_src: torch.Tensor, source: _lib.Sourc
                                              _ptr(colour), _ptr(hole_mask), hole_mask.stride(0), out_w, out_h, pack_rgb(bg_rgb),
                                              int(bool(code_normals)), _ptr(image), 0 if image is None else image.stride(0), _ptr(mask_img),
                                              mask_img.stride(0), _stream()))
+
+
+def normal_march_infill(image: torch.Tensor, hole_mask: torch.Tensor, mask_img: torch.Tensor, max_steps: int = 400) -> torch.Tensor:
+    """stereo_rerender.infill_using_normals (:155-240) for one eye, in place on `image` (H, W, 3) u8; hole_mask (H, W) u8,
+    mask_img (H, W, 3) u8 = the final (inpainted, blurred) mask image.  All three may be column slices."""
+    h, w = hole_mask.shape
+    for t, ch, name in ((image, 3, "image"), (hole_mask, 1, "hole_mask"), (mask_img, 3, "mask_img")):
+        ok = t.dtype == torch.uint8 and t.is_cuda and t.shape[0] == h and t.shape[1] == w and t.stride(-1) == 1
+        ok = ok and ((ch == 1 and t.dim() == 2) or (ch == 3 and t.dim() == 3 and t.shape[2] == 3 and t.stride(1) == 3))
+        if not ok:
+            raise ValueError(f"{name} must be a ({h}, {w}{', 3' if ch == 3 else ''}) u8 CUDA view with dense rows")
+    _lib.check(_lib.load().mdvt_normal_march_infill(_ptr(image), image.stride(0), _ptr(hole_mask), hole_mask.stride(0), _ptr(mask_img),
+                                                    mask_img.stride(0), w, h, int(max_steps), _stream()))
+    return image

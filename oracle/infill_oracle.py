@@ -143,3 +143,33 @@ def masked_blur(img: np.ndarray, ksize=(6, 6), sigma=0) -> np.ndarray:
     out[weight == 0] = 0
     out[black] = 0
     return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def normal_march_infill(image_u8: np.ndarray, hole: np.ndarray, mask_final_u8: np.ndarray, max_steps: int = 400) -> np.ndarray:
+    """`--do_basic_infill` (stereo_rerender.py:155-240,810-812) per pixel, scalar float32: every hole pixel marches
+    along the XY direction coded in the final mask image ((m/255)*2-1, normalised) until it leaves the hole, then takes
+    the colour two steps / one step / zero steps further on, whichever is first inside the frame and not a hole.
+    Pure-Python loop: small frames only."""
+    f32 = np.float32
+    h, w = hole.shape
+    out = image_u8.copy()
+    for y, x in zip(*np.nonzero(hole)):
+        m = mask_final_u8[y, x].astype(f32) / f32(255.0)
+        dx, dy = m[0] * f32(2) - f32(1), m[1] * f32(2) - f32(1)
+        norm = np.sqrt(dx * dx + dy * dy)
+        if not norm > f32(1e-6):
+            continue
+        dx, dy = dx / norm, dy / norm
+        for t in range(1, max_steps + 1):
+            xi, yi = int(np.rint(f32(x) + dx * f32(t))), int(np.rint(f32(y) + dy * f32(t)))
+            if not (0 <= xi < w and 0 <= yi < h):
+                break
+            if hole[yi, xi]:
+                continue
+            for dt in (2, 1, 0):
+                x2, y2 = int(np.rint(f32(x) + dx * f32(t + dt))), int(np.rint(f32(y) + dy * f32(t + dt)))
+                if 0 <= x2 < w and 0 <= y2 < h and not hole[y2, x2]:
+                    out[y, x] = image_u8[y2, x2]
+                    break
+            break
+    return out

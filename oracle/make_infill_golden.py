@@ -68,6 +68,12 @@ def run_case(dfh, dmt, sr, tag, w, h, xfov, conv_depth, transform, out):
     out[f"{tag}_mask_pre_inpaint"] = (ns["left_img_mask"] * 255).astype("uint8")
     out[f"{tag}_infill_area"] = ns["infill_area_mask"]
     ref_bridge.exec_lines("stereo_rerender.py", 806, 808, ns)            # TELEA + masked blur
+    basic = dict(ns)                                                     # --do_basic_infill variant of :810-819 (normal-march infill)
+    basic["args"] = argparse.Namespace(**{**vars(args), "do_basic_infill": True})
+    basic["left_image"], basic["left_img_mask"] = ns["left_image"].copy(), ns["left_img_mask"].copy()
+    ref_bridge.exec_lines("stereo_rerender.py", 810, 819, basic)
+    out[f"{tag}_image_basic_infill"] = basic["left_image"]
+    out[f"{tag}_hole_mask"] = ns["bg_mask"]
     ref_bridge.exec_lines("stereo_rerender.py", 810, 819, ns)            # edge colours into the image, u8 conversions
     out[f"{tag}_mask_final"], out[f"{tag}_image_final"] = ns["left_img_mask"], ns["left_image"]
     print(tag, "edge vertices", len(unused), "painted", int(ns["mask"].sum()), "holes", int(ns["bg_mask"].sum()))

@@ -698,3 +698,46 @@ def test_cli_vr180_and_touchly0(clip_files, tmp_path):
     assert video_io.read_clip(dv + "_stereo.mkv").shape == (1, side, 2 * side, 3)
     with pytest.raises(NotImplementedError, match="reference itself fails"):
         stereo_rerender.main(["--depth_video", dv, "--color_video", cv, "--xfov", "60", "--vr180", "--infill_mask"])
+
+
+@pytest.mark.parametrize("tag", ["plain", "posed"])
+def test_normal_march_infill_matches_reference(golden_dir, tag):
+    """--do_basic_infill: the reference's infill_using_normals was run on its own mask / image; same bytes here."""
+    g = np.load(os.path.join(golden_dir, "infill_mask.npz"))
+    hole = g[tag + "_hole_mask"]
+    image = g[tag + "_left_image_u8"].copy()
+    image[hole] = 0
+    dev = cu(image)
+    ops.normal_march_infill(dev, cu(hole.astype(np.uint8) * 255), cu(g[tag + "_mask_final"]))
+    assert np.array_equal(dev.cpu().numpy(), g[tag + "_image_basic_infill"])
+    assert (g[tag + "_image_basic_infill"][hole] != 0).any()
+
+
+def test_cli_do_basic_infill(clip_files, tmp_path):
+    import shutil
+
+    import stereo_rerender
+    from oracle import infill_oracle as io
+
+    c = clip_files
+    work = tmp_path / "basic"
+    work.mkdir()
+    for name in ("depth.mkv", "colour.mkv"):
+        shutil.copy(c["dir"] / name, work / name)
+    dv = str(work / "depth.mkv")
+    assert stereo_rerender.main(["--depth_video", dv, "--color_video", str(work / "colour.mkv"), "--xfov", "60", "--infill_mask",
+                                 "--do_basic_infill", "--max_frames", "1"]) == 0
+    sbs = video_io.read_clip(dv + "_stereo.mkv")
+    msk = video_io.read_clip(dv + "_stereo.mkv_infillmask.mkv")
+    w = c["w"]
+    K = orc.camera_matrix(60.0, None, w, c["h"])
+    scale = orc.master_fov_depth_scale(45.0, 60.0)
+    M = orc.eye_pose("left", 0.063, None)
+    img, hole_mask, _ = orc.render_view(c["depth"][0], c["colour"][0], 100, K, M, depth_scale=scale, bg_rgb=(0, 255, 0), hole_fill=(0, 0, 0))
+    hole = hole_mask == 255
+    # march with the mask the front end itself wrote: the image must then agree except at rounding-boundary pixels of the render
+    want = io.normal_march_infill(img, hole, msk[0, :, :w])
+    assert (sbs[0, :, :w] != want).any(axis=-1).mean() < 4e-3
+    assert (want[hole] != 0).any(axis=-1).mean() > 0.5  # most holes got a colour
+    with pytest.raises(NotImplementedError, match="--infill_mask"):
+        stereo_rerender.main(["--depth_video", dv, "--xfov", "60", "--do_basic_infill"])

@@ -28,3 +28,13 @@ def test_infill_oracle_equals_reference_outputs(golden_dir, tag):
     assert np.array_equal(img, g[tag + "_image_final"])
     assert np.array_equal(io.finish_mask(pre, green, area), g[tag + "_mask_final"])
     assert len(unused) > 100 and (pre != 0).any()
+
+
+@pytest.mark.parametrize("tag", ["plain", "posed"])
+def test_normal_march_oracle_equals_reference(golden_dir, tag):
+    """--do_basic_infill: the scalar float32 restatement against the reference's infill_using_normals output."""
+    g = np.load(os.path.join(golden_dir, "infill_mask.npz"))
+    hole = g[tag + "_hole_mask"]
+    image = g[tag + "_left_image_u8"].copy()
+    image[hole] = 0
+    assert np.array_equal(io.normal_march_infill(image, hole, g[tag + "_mask_final"]), g[tag + "_image_basic_infill"])
