@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MDVT_ABI_VERSION 4
+#define MDVT_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define MDVT_API __attribute__((visibility("default")))
@@ -278,6 +278,23 @@ MDVT_API int mdvt_normal_march_infill(uint8_t *image, int64_t image_pitch, const
 MDVT_API int mdvt_stereo_rows(const uint8_t *depth_rgb, const uint8_t *colour_rgb, int n_frames, int width, int height,
                      const mdvt_stereo_frame *frames_dev, int per_frame, uint32_t bg_rgb, uint32_t fill_rgb,
                      uint32_t flags, uint8_t *out_sbs, uint8_t *out_mask, float *out_depth, void *stream);
+
+/* ---- stereo with a convergence rotation: ONE fused kernel, frames batched ------------------------ */
+/* Per-frame constants (DEVICE array, one entry per frame).  view[0] = left eye, view[1] = right eye; each M must be a
+ * rotation about the y axis plus a translation along x (M[1] = M[4] = M[6] = M[7] = M[9] = M[11] = 0, M[5] = 1), which
+ * is what stereo_rerender.py builds without a pose file (:704-725,831-836): then a pixel's target row does not depend
+ * on its depth and one CTA can own a target row.  The output has the size of the source frames. */
+typedef struct mdvt_conv_frame {
+    float dec_const, depth_scale, near_plane, reserved;
+    float fx, fy, cx, cy;   /* source camera, exact pixel grid */
+    mdvt_view view[2];
+} mdvt_conv_frame;
+
+/* Same inputs / outputs / flags as mdvt_stereo_rows; results are bit-identical to mdvt_project_splat + mdvt_resolve with
+ * the same cameras (nearest Zv wins, ties -> lowest source index), without the global z-buffer.  Requires W <= 4096. */
+MDVT_API int mdvt_stereo_conv_rows(const uint8_t *depth_rgb, const uint8_t *colour_rgb, int n_frames, int width, int height,
+                          const mdvt_conv_frame *frames_dev, uint32_t bg_rgb, uint32_t fill_rgb, uint32_t flags,
+                          uint8_t *out_sbs, uint8_t *out_mask, float *out_depth, void *stream);
 
 #ifdef __cplusplus
 }

@@ -18,7 +18,7 @@ DECODERS = {"D1": DECODE_D1, "D2": DECODE_D2, "D3": DECODE_D3, "F32": SOURCE_F32
 REDUCE_SCRATCH_DOUBLES = 4096
 FLAG_BG_COLLIDE, FLAG_RESET_ZBUF, FLAG_MASK_RGB, FLAG_ANYWIDTH = 0x1, 0x2, 0x4, 0x8
 ZBUF_EMPTY = 0xFFFFFFFFFFFFFFFF
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class MdvtError(RuntimeError):
@@ -38,6 +38,12 @@ class Source(C.Structure):
 class View(C.Structure):
     """mdvt_view"""
     _fields_ = [("M", C.c_float * 12), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float)]
+
+
+class ConvFrame(C.Structure):
+    """mdvt_conv_frame (40 x float32; built on the host, copied to the device as bytes)"""
+    _fields_ = [("dec_const", C.c_float), ("depth_scale", C.c_float), ("near_plane", C.c_float), ("reserved", C.c_float),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("view", View * 2)]
 
 
 class PlaneLayout(C.Structure):
@@ -90,6 +96,8 @@ _PROTOTYPES = {
     "mdvt_edge_resolve": (C.c_int, [_u64p, _u8p, C.POINTER(Source), C.POINTER(C.c_double), _f64p, C.POINTER(C.c_double), _u8p, _u8p,
                                     C.c_int64, C.c_int, C.c_int, C.c_uint32, C.c_int, _u8p, C.c_int64, _u8p, C.c_int64, _stream]),
     "mdvt_normal_march_infill": (C.c_int, [_u8p, C.c_int64, _u8p, C.c_int64, _u8p, C.c_int64, C.c_int, C.c_int, C.c_int, _stream]),
+    "mdvt_stereo_conv_rows": (C.c_int, [_u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _u8p, _u8p,
+                                        _f32p, _stream]),
     "mdvt_stereo_rows": (C.c_int, [_u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32,
                                    C.c_uint32, _u8p, _u8p, _f32p, _stream]),
 }

@@ -544,3 +544,66 @@ def normal_march_infill(image: torch.Tensor, hole_mask: torch.Tensor, mask_img: 
     _lib.check(_lib.load().mdvt_normal_march_infill(_ptr(image), image.stride(0), _ptr(hole_mask), hole_mask.stride(0), _ptr(mask_img),
                                                     mask_img.stride(0), w, h, int(max_steps), _stream()))
     return image
+
+
+# ---------------------------------------------------------------------------------------------
+# stereo with a convergence rotation: fused target-row kernel
+# ---------------------------------------------------------------------------------------------
+def conv_frames(sources: Sequence[_lib.Source], views: Sequence[Sequence[ViewSpec]], near: float = NEAR_PLANE) -> np.ndarray:
+    """Host array of mdvt_conv_frame (as (n, 40) float32) from per-frame sources and [left, right] cameras; raises if a
+    camera is not `rotation about y + shift along x` (the only poses the fused kernel handles)."""
+    n = len(views)
+    if len(sources) not in (1, n):
+        raise ValueError("sources must hold one entry or one per frame")
+    arr = (_lib.ConvFrame * n)()
+    for k in range(n):
+        s = sources[k if len(sources) == n else 0]
+        if s.decoder != _lib.DECODE_D1 or not s.bit16 or s.grid_sx != 1.0 or s.grid_sy != 1.0:
+            raise ValueError("the fused convergence kernel takes 16-bit D1 wire-format frames on the exact pixel grid")
+        f = arr[k]
+        f.dec_const, f.depth_scale, f.near_plane = s.dec_const, s.depth_scale, float(np.float32(near))
+        f.fx, f.fy, f.cx, f.cy = s.fx, s.fy, s.cx, s.cy
+        if len(views[k]) != 2:
+            raise ValueError("two cameras (left, right) per frame")
+        for e, v in enumerate(views[k]):
+            c = v.to_c()
+            m = [c.M[i] for i in range(12)]
+            if any(m[i] != 0.0 for i in (1, 4, 6, 7, 9, 11)) or m[5] != 1.0:
+                raise ValueError("camera pose is not a y-rotation plus an x-shift")
+            f.view[e] = c
+    return np.frombuffer(bytes(arr), dtype=np.float32).reshape(n, C.sizeof(_lib.ConvFrame) // 4).copy()
+
+
+def stereo_conv_rows(depth_rgb: torch.Tensor, colour: torch.Tensor, frames: torch.Tensor, bg_rgb=(0, 0, 0), fill_rgb=(0, 0, 0),
+                     flags: int = 0, out_sbs: Optional[torch.Tensor] = None, out_mask: Optional[torch.Tensor] = None,
+                     want_mask: bool = True, out_depth: Optional[torch.Tensor] = None):
+    """Fused convergence-stereo kernel over a batch: depth_rgb / colour (n, H, W, 3) u8, frames (n, 40) float32 CUDA
+    tensor from conv_frames().  Same outputs as stereo_rows; bit-identical to project_splat + resolve."""
+    _need(depth_rgb, torch.uint8, "depth_rgb")
+    _need(colour, torch.uint8, "colour")
+    _need(frames, torch.float32, "frames")
+    if depth_rgb.dim() != 4 or depth_rgb.shape[-1] != 3 or depth_rgb.shape != colour.shape:
+        raise ValueError("depth_rgb and colour must both be (n, H, W, 3)")
+    n, h, w, _ = depth_rgb.shape
+    if tuple(frames.shape) != (n, C.sizeof(_lib.ConvFrame) // 4):
+        raise ValueError("frames must be (n, 40) float32 rows of mdvt_conv_frame")
+    dev = depth_rgb.device
+    mask_bpp = 3 if flags & FLAG_MASK_RGB else 1
+    if out_sbs is None:
+        out_sbs = torch.empty((n, h, 2 * w, 3), dtype=torch.uint8, device=dev)
+    _need(out_sbs, torch.uint8, "out_sbs")
+    if want_mask and out_mask is None:
+        out_mask = torch.empty((n, h, 2 * w) + ((3,) if mask_bpp == 3 else ()), dtype=torch.uint8, device=dev)
+    if out_mask is not None:
+        _need(out_mask, torch.uint8, "out_mask")
+        if out_mask.numel() != n * h * 2 * w * mask_bpp:
+            raise ValueError("out_mask has the wrong size")
+    if out_sbs.numel() != n * h * 2 * w * 3:
+        raise ValueError("out_sbs has the wrong size")
+    if out_depth is not None:
+        _need(out_depth, torch.float32, "out_depth")
+        if out_depth.numel() != n * h * 2 * w:
+            raise ValueError("out_depth must be (n, H, 2W) float32")
+    _lib.check(_lib.load().mdvt_stereo_conv_rows(_ptr(depth_rgb), _ptr(colour), n, w, h, _ptr(frames), pack_rgb(bg_rgb), pack_rgb(fill_rgb),
+                                                 flags, _ptr(out_sbs), _ptr(out_mask), _ptr(out_depth), _stream()))
+    return out_sbs, out_mask

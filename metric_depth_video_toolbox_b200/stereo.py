@@ -39,6 +39,7 @@ class StereoParams:
     infill_mask: bool = True              # --infill_mask: green background, hole mask written
     mask_rgb: bool = False                # mask as the reference's green/black u8x3 image instead of u8
     near: float = geo.NEAR_PLANE
+    force_generic: bool = False           # test / comparison aid: always take the K1+K2+K3 path
 
     def __post_init__(self):
         if self.xfov is None and self.yfov is None and self.xfovs is None:
@@ -57,7 +58,12 @@ class StereoParams:
 
     def row_local(self) -> bool:
         """True when every frame is a pure +-ipd/2 shift: v' == v, one fused kernel does it all."""
-        return self.transformations is None and self.convergence_depths is None
+        return self.transformations is None and self.convergence_depths is None and not self.force_generic
+
+    def conv_local(self) -> bool:
+        """True when the eye poses are `rotation about y + shift along x` (convergence without a pose file): the row
+        displacement is then depth independent and the fused target-row kernel applies."""
+        return self.transformations is None and self.convergence_depths is not None and not self.force_generic and self.width <= 4096
 
 
 class StereoRerenderer:
@@ -115,21 +121,29 @@ class StereoRerenderer:
         if p.row_local():
             return ops.stereo_rows(depth_rgb, colour, self._device_constants(start_frame, n), p.bg_rgb, (0, 0, 0), flags,
                                    out_sbs, out_mask, want_mask=p.infill_mask or out_mask is not None, out_depth=out_depth)
-        # generic path: per frame K1+K2 into a persistent 2-view z-buffer, K3 per eye straight into the SBS halves
         if out_sbs is None:
             out_sbs = torch.empty((n, h, 2 * w, 3), dtype=torch.uint8, device=depth_rgb.device)
         if out_mask is None and p.infill_mask:
             out_mask = torch.empty((n, h, 2 * w) + ((3,) if mask_rgb else ()), dtype=torch.uint8, device=depth_rgb.device)
-        zkey = torch.cuda.current_stream(depth_rgb.device).cuda_stream
-        zbuf = self._zbufs.get(zkey)
-        if zbuf is None or tuple(zbuf.shape) != (2, h, w) or zbuf.device != depth_rgb.device:
-            zbuf = self._zbufs[zkey] = ops.new_zbuf(2, w, h, depth_rgb.device)
         sources = []
         for f in (range(start_frame, start_frame + n) if p.xfovs is not None else [start_frame]):
             xf = p.xfov_of(f)
             K = geo.compute_camera_matrix(xf, None if p.xfovs is not None else p.yfov, w, h)
             sources.append(ops.make_source(w, h, K, p.max_depth, "D1", True, geo.master_fov_depth_scale(p.master_xfov, xf), False))
         views = [self.views_of(f) for f in range(start_frame, start_frame + n)]
+        if p.conv_local():  # convergence only: fused target-row kernel, no global z-buffer
+            key = ("conv", start_frame, n)
+            if key not in self._consts_cache:
+                if len(self._consts_cache) > 64:
+                    self._consts_cache.clear()
+                self._consts_cache[key] = torch.from_numpy(ops.conv_frames(sources, views, p.near)).to(self.device)
+            return ops.stereo_conv_rows(depth_rgb, colour, self._consts_cache[key], p.bg_rgb, (0, 0, 0), flags, out_sbs, out_mask,
+                                        want_mask=False, out_depth=out_depth)
+        # generic path: per frame K1+K2 into a persistent 2-view z-buffer, K3 per eye straight into the SBS halves
+        zkey = torch.cuda.current_stream(depth_rgb.device).cuda_stream
+        zbuf = self._zbufs.get(zkey)
+        if zbuf is None or tuple(zbuf.shape) != (2, h, w) or zbuf.device != depth_rgb.device:
+            zbuf = self._zbufs[zkey] = ops.new_zbuf(2, w, h, depth_rgb.device)
         ops.render_views(depth_rgb, colour, sources, views, w, h, zbuf, out_sbs, out_mask, out_depth, p.bg_rgb, (0, 0, 0), flags, p.near)
         return out_sbs, out_mask
 

@@ -378,3 +378,32 @@ def test_full_size_properties_4k_novel_view_and_rows():
     rows = slice(1000, 1016)
     want_sbs, want_mask, _ = km.stereo_rows_f32(depth[0, rows], colour[0, rows], k)
     assert np.array_equal(sbs[0, rows].cpu().numpy(), want_sbs) and np.array_equal(m[0, rows].cpu().numpy(), want_mask)
+
+
+@pytest.mark.parametrize("size,conv,yfov,mask_rgb", [((64, 48), 5.0, None, False), ((640, 480), 2.0, None, True), ((640, 480), 0.4, 50.0, False),
+                                                     ((70, 33), 3.0, None, False), ((1920, 24), 1.0, None, False)])
+def test_stereo_conv_rows_bit_identical_to_generic_path(size, conv, yfov, mask_rgb):
+    """The fused target-row kernel for convergence stereo against K1+K2+K3 with the same cameras: every output byte,
+    the hole masks and the float32 depth planes must be identical (same float32 arithmetic, same winner order)."""
+    from metric_depth_video_toolbox_b200.stereo import StereoParams, StereoRerenderer
+
+    w, h = size
+    n = 3
+    depth, colour = SyntheticClip(w, h, n, zero_fraction=0.01).frames()
+    colour[:, 1, 2] = (0, 255, 0)
+    convs = [conv, 0.0, conv * 1.7]  # 0 -> "skipping convergence" for that frame (stereo_rerender.py:710-712)
+    outs = []
+    for force in (False, True):
+        p = StereoParams(w, h, xfov=60.0, yfov=yfov, convergence_depths=convs, infill_mask=True, mask_rgb=mask_rgb, force_generic=force)
+        assert p.conv_local() != force
+        rr = StereoRerenderer(p, DEV)
+        out_depth = torch.full((n, h, 2 * w), -1.0, dtype=torch.float32, device=DEV)
+        sbs, mask = rr.render_device(cu(depth), cu(colour), out_depth=out_depth)
+        outs.append((sbs, mask, out_depth))
+    (sa, ma, da), (sb, mb, db) = outs
+    assert torch.equal(sa, sb) and torch.equal(ma, mb)
+    assert torch.equal(da.view(torch.int32), db.view(torch.int32))
+    assert bool((ma != 0).any()) and bool((da > 0).any())
+    # and, through the generic path's own oracle check, against the float64 reference restatement
+    want, _, _ = orc.stereo_frame(depth[2], colour[2], 60.0, yfov, convergence_depth=convs[2], infill_mask=True)
+    assert (sa[2].cpu().numpy() != want).any(axis=-1).mean() < 3e-3
