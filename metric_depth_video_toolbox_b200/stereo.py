@@ -125,20 +125,23 @@ class StereoRerenderer:
             out_sbs = torch.empty((n, h, 2 * w, 3), dtype=torch.uint8, device=depth_rgb.device)
         if out_mask is None and p.infill_mask:
             out_mask = torch.empty((n, h, 2 * w) + ((3,) if mask_rgb else ()), dtype=torch.uint8, device=depth_rgb.device)
-        sources = []
-        for f in (range(start_frame, start_frame + n) if p.xfovs is not None else [start_frame]):
-            xf = p.xfov_of(f)
-            K = geo.compute_camera_matrix(xf, None if p.xfovs is not None else p.yfov, w, h)
-            sources.append(ops.make_source(w, h, K, p.max_depth, "D1", True, geo.master_fov_depth_scale(p.master_xfov, xf), False))
-        views = [self.views_of(f) for f in range(start_frame, start_frame + n)]
+        def cameras():
+            sources = []
+            for f in (range(start_frame, start_frame + n) if p.xfovs is not None else [start_frame]):
+                xf = p.xfov_of(f)
+                K = geo.compute_camera_matrix(xf, None if p.xfovs is not None else p.yfov, w, h)
+                sources.append(ops.make_source(w, h, K, p.max_depth, "D1", True, geo.master_fov_depth_scale(p.master_xfov, xf), False))
+            return sources, [self.views_of(f) for f in range(start_frame, start_frame + n)]
+
         if p.conv_local():  # convergence only: fused target-row kernel, no global z-buffer
             key = ("conv", start_frame, n)
             if key not in self._consts_cache:
                 if len(self._consts_cache) > 64:
                     self._consts_cache.clear()
-                self._consts_cache[key] = torch.from_numpy(ops.conv_frames(sources, views, p.near)).to(self.device)
+                self._consts_cache[key] = torch.from_numpy(ops.conv_frames(*cameras(), p.near)).to(self.device)
             return ops.stereo_conv_rows(depth_rgb, colour, self._consts_cache[key], p.bg_rgb, (0, 0, 0), flags, out_sbs, out_mask,
                                         want_mask=False, out_depth=out_depth)
+        sources, views = cameras()
         # generic path: per frame K1+K2 into a persistent 2-view z-buffer, K3 per eye straight into the SBS halves
         zkey = torch.cuda.current_stream(depth_rgb.device).cuda_stream
         zbuf = self._zbufs.get(zkey)

@@ -44,6 +44,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.View) == 16 * 4
     assert C.sizeof(_lib.StereoFrame) == 16
     assert C.sizeof(_lib.PlaneLayout) == 32
+    assert C.sizeof(_lib.ConvFrame) == 160
 
 
 def test_sass_contains_tma_and_atomics():
@@ -85,6 +86,13 @@ def test_argument_validation_without_a_device():
     assert lib.mdvt_render_views(None, 0, None, 0, 0, None, 0, None, 2, 1e-4, 4, 4, None, 0, 0, 0, None, None, None, None) == 0
     assert lib.mdvt_render_views(None, 0, None, 0, 1, None, 0, None, 9, 1e-4, 4, 4, None, 0, 0, 0, None, None, None, None) == -1
     assert lib.mdvt_resolve(None, None, 4, 4, 0, 0, 0, None, 0, None, 0, None, 0, None, None) == -1
+    assert lib.mdvt_stereo_conv_rows(None, None, 1, 5000, 4, None, 0, 0, 0, None, None, None, None) == -2  # column does not fit 12 bits
+    assert lib.mdvt_stereo_conv_rows(None, None, 0, 64, 4, None, 0, 0, 0, None, None, None, None) == 0
+    assert lib.mdvt_remap_bilinear_u8x3(None, 4, 4, 12, None, None, 4, 4, 0, None, 12, None) == -1
+    assert lib.mdvt_normal_march_infill(None, 12, None, 4, None, 12, 4, 4, 400, None) == -1
+    assert lib.mdvt_edge_vertices(None, C.byref(src), None, 89.0, None, None, None, None) == -1
+    assert lib.mdvt_depth_to_grey(None, 4, 0, 1, 1.0, 1.0, 12, 1, None, None) == -1  # 12-bit output does not exist
+    assert lib.mdvt_touchly_depth(None, 4, 4, 0, 1, 1.0, 1.0, 5.0, 5.0, 1.0, 0, None, 12, None) == -1  # max must exceed min
 
 
 def test_ops_refuse_cpu_tensors():
