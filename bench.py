@@ -298,8 +298,8 @@ def run_ours(args):
         checksum = int(host_mask[::17].sum().item())  # the step's result is read on the host
         per_frame_in = 2 * HEIGHT * WIDTH * 3
         per_frame_out = HEIGHT * 2 * WIDTH * 4
-        e2e = {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(per_frame_in * n_frames),
-               "d2h_bytes_per_step": int(per_frame_out * n_frames), "steps": args.e2e_steps,
+        e2e = {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(per_frame_in * n_frames * world),
+               "d2h_bytes_per_step": int(per_frame_out * n_frames * world), "steps": args.e2e_steps,
                "api": "StereoRerenderer.render_host (pinned host ring, 2-stream chunked H2D/kernel/D2H)", "mask_checksum": checksum}
 
     if rank != 0:
