@@ -61,7 +61,11 @@ def whole():
     nv.render_device(d, c, 0, rgb, mask)
 
 
-for name, fn in (("centroid", centroid), ("splat (accumulating zbuf)", splat), ("resolve (no reset)", resolve), ("whole render_device", whole)):
+def whole_hostcam():
+    nv.render_device_hostcam(d, c, 0, rgb, mask)
+
+
+for name, fn in (("centroid", centroid), ("splat (accumulating zbuf)", splat), ("resolve (no reset)", resolve), ("whole render_device (one call, device camera)", whole), ("whole render_device_hostcam (v1)", whole_hostcam)):
     ms = timed(fn)
     print(f"{w}x{h} {name}: {ms / n * 1e3:.1f} us/frame")
 print("holes", float((mask == 255).float().mean()))

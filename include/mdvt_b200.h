@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MDVT_ABI_VERSION 5
+#define MDVT_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define MDVT_API __attribute__((visibility("default")))
@@ -217,6 +217,32 @@ MDVT_API int mdvt_render_views(const void *depth_src, int64_t depth_frame_stride
                       const mdvt_view *views_host, int n_views, float near_plane, int out_w, int out_h, uint64_t *zbuf,
                       uint32_t bg_rgb, uint32_t fill_rgb, uint32_t flags, const mdvt_plane_layout *rgb_out,
                       const mdvt_plane_layout *mask_out, const mdvt_plane_layout *depth_out, void *stream);
+
+/* The camera of `3d_view_depthfile.py --render` (3d_view_depthfile.py:231-241, depth_map_tools.py:1618-1638,1528-1552):
+ * look-at point = vertex centroid of the frame (Open3D get_center()) with per-axis --tx/--ty/--tz overrides. */
+typedef struct mdvt_lookat {
+    double cam_pos[3];     /* --x --y --z after .astype(np.float32) (:240), widened */
+    double target[3];      /* --tx --ty --tz */
+    int32_t target_set[3]; /* 0: that component is the centroid's */
+    int32_t reserved;
+    double y_scale;        /* fy / fx: render() scales geometry Y and passes fx in both focal slots (:1528-1552) */
+    float fx, fy, cx, cy;  /* intrinsics of the rendering camera (fy == fx for the reference's path) */
+} mdvt_lookat;
+
+/* The frame loop of `3d_view_depthfile.py --render` (:133-255) for n_frames frames in ONE call with no host round
+ * trip: per frame the vertex centroid (as mdvt_centroid, vertex grid `centroid_src_host`, usually the of_by_one
+ * stretched grid of mesh mode), the look-at camera of that frame computed ON THE DEVICE into views_dev[f], K1+K2 of
+ * the frame (pixel grid `src_host`) through that camera, K3 into the planes of rgb_out / mask_out (optional).
+ * poses_host: n_frames x 16 doubles (row-major 4x4, the frame's transformation) or NULL.  sums_dev: n_frames x
+ * (4 + MDVT_REDUCE_SCRATCH_DOUBLES) doubles (results {sum X, sum Y, sum Z, n} first); views_dev: n_frames
+ * mdvt_view, 16-byte aligned; both stay valid for the caller to read back.  zbuf: one out_w x out_h plane, empty on
+ * entry, left empty. */
+MDVT_API int mdvt_novel_view_frames(const void *depth_src, int64_t depth_frame_stride, const uint8_t *colour_rgb,
+                           int64_t colour_frame_stride, int n_frames, const mdvt_source *centroid_src_host,
+                           const mdvt_source *src_host, const double *K_host, const double *poses_host,
+                           const mdvt_lookat *look_host, float near_plane, int out_w, int out_h, uint64_t *zbuf,
+                           double *sums_dev, mdvt_view *views_dev, uint32_t bg_rgb, uint32_t fill_rgb, uint32_t flags,
+                           const mdvt_plane_layout *rgb_out, const mdvt_plane_layout *mask_out, void *stream);
 
 /* ---- per-frame reductions (fixed summation order: reproducible) -------------------------------- */
 /* Result buffers hold 4 doubles of result followed by MDVT_REDUCE_SCRATCH_DOUBLES doubles of scratch. */

@@ -18,7 +18,7 @@ DECODERS = {"D1": DECODE_D1, "D2": DECODE_D2, "D3": DECODE_D3, "F32": SOURCE_F32
 REDUCE_SCRATCH_DOUBLES = 4096
 FLAG_BG_COLLIDE, FLAG_RESET_ZBUF, FLAG_MASK_RGB, FLAG_ANYWIDTH = 0x1, 0x2, 0x4, 0x8
 ZBUF_EMPTY = 0xFFFFFFFFFFFFFFFF
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class MdvtError(RuntimeError):
@@ -49,6 +49,12 @@ class ConvFrame(C.Structure):
 class PlaneLayout(C.Structure):
     """mdvt_plane_layout (strides in bytes)"""
     _fields_ = [("base", C.c_void_p), ("frame_stride", C.c_int64), ("view_stride", C.c_int64), ("row_pitch", C.c_int64)]
+
+
+class LookAt(C.Structure):
+    """mdvt_lookat"""
+    _fields_ = [("cam_pos", C.c_double * 3), ("target", C.c_double * 3), ("target_set", C.c_int32 * 3), ("reserved", C.c_int32),
+                ("y_scale", C.c_double), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float)]
 
 
 class StereoFrame(C.Structure):
@@ -90,6 +96,9 @@ _PROTOTYPES = {
     "mdvt_render_views": (C.c_int, [_u8p, C.c_int64, _u8p, C.c_int64, C.c_int, C.POINTER(Source), C.c_int, C.POINTER(View), C.c_int,
                                     C.c_float, C.c_int, C.c_int, _u64p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PlaneLayout),
                                     C.POINTER(PlaneLayout), C.POINTER(PlaneLayout), _stream]),
+    "mdvt_novel_view_frames": (C.c_int, [_u8p, C.c_int64, _u8p, C.c_int64, C.c_int, C.POINTER(Source), C.POINTER(Source), C.POINTER(C.c_double),
+                                         C.POINTER(C.c_double), C.POINTER(LookAt), C.c_float, C.c_int, C.c_int, _u64p, _f64p, C.c_void_p,
+                                         C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PlaneLayout), C.POINTER(PlaneLayout), _stream]),
     "mdvt_edge_vertices": (C.c_int, [_u8p, C.POINTER(Source), C.POINTER(C.c_double), C.c_double, _u8p, _u8p, _f64p, _stream]),
     "mdvt_edge_splat": (C.c_int, [_u8p, C.POINTER(Source), C.POINTER(C.c_double), _u8p, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                   C.c_int, C.c_int, _u64p, _stream]),

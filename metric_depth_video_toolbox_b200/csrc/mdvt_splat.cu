@@ -61,20 +61,50 @@ __device__ __forceinline__ void splat_pixel(uint32_t p, int col, int row, float 
 // the lanes of a warp cover 32 consecutive source pixels (-> mostly consecutive z-buffer slots: few L2 sectors per
 // 64-bit RED).  A 4-pixels-per-thread variant with word loads was measured SLOWER (29 vs 17 us at 1080p x 2 views):
 // its lanes hit every fourth slot and each RED touches 4x the sectors -- the atomics, not the loads, matter here.
-template <int DECODER, bool BIT16>
+// Rows are taken in batches of kSplatRows with all source loads issued before the first pixel is pushed through the
+// cameras (ncu v1: the kernel sat on the scoreboard of its own byte loads at 53 % issue-active), and the grid is sized
+// from the occupancy API so that every CTA is resident (v1 launched 2370 CTAs onto 1924 slots: a second, mostly
+// empty wave).  DEVVIEW: the single camera is read from device memory (written by the look-at kernel of the same
+// stream, mdvt_novel_view_frames) instead of the kernel parameters.
+constexpr int kSplatRows = 4;
+
+template <int DECODER, bool BIT16, bool DEVVIEW>
 __global__ void __launch_bounds__(kSplatThreads)
     project_splat_kernel(const void *__restrict__ rgb, int width, int height, float dec_const, float depth_scale, SourceCam cam,
-                         ViewPack views, float near_plane, int out_w, int out_h, uint32_t id_offset,
-                         unsigned long long *__restrict__ zbuf, float *__restrict__ out_uvz) {
+                         ViewPack views_param, const mdvt_view *__restrict__ view_dev, float near_plane, int out_w, int out_h,
+                         uint32_t id_offset, unsigned long long *__restrict__ zbuf, float *__restrict__ out_uvz) {
     const uint32_t out_n = (uint32_t)out_w * (uint32_t)out_h, n = (uint32_t)width * (uint32_t)height;
     const float u_max = (float)(out_w - 1), v_max = (float)(out_h - 1);
     const float rfx = rcp_refined(cam.fx), rfy = rcp_refined(cam.fy);
     const int col = blockIdx.x * kSplatThreads + threadIdx.x;
     if (col >= width) return;
-    for (int row = blockIdx.y; row < height; row += gridDim.y) {
-        const uint32_t p = (uint32_t)row * (uint32_t)width + (uint32_t)col;
-        const float z = __fmul_rn(source_depth<DECODER, BIT16>(rgb, p, dec_const), depth_scale);
-        splat_pixel(p, col, row, z, cam, rfx, rfy, views, near_plane, out_w, out_n, u_max, v_max, id_offset, n, zbuf, out_uvz);
+    ViewPack local;
+    if (DEVVIEW) {
+        local.n = 1;
+        const float4 *v4 = reinterpret_cast<const float4 *>(view_dev);
+        float4 *l4 = reinterpret_cast<float4 *>(&local.v[0]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) l4[k] = __ldg(v4 + k);
+    }
+    const ViewPack &views = DEVVIEW ? local : views_param;
+    const int stride = gridDim.y;
+    for (int row0 = blockIdx.y; row0 < height; row0 += stride * kSplatRows) {
+        float z[kSplatRows];
+#pragma unroll
+        for (int k = 0; k < kSplatRows; ++k) {
+            const int row = row0 + k * stride;
+            z[k] = 0.0f;
+            if (row < height) z[k] = source_depth<DECODER, BIT16>(rgb, (uint32_t)row * (uint32_t)width + (uint32_t)col, dec_const);
+        }
+#pragma unroll
+        for (int k = 0; k < kSplatRows; ++k) {
+            const int row = row0 + k * stride;
+            if (row < height) {
+                const uint32_t p = (uint32_t)row * (uint32_t)width + (uint32_t)col;
+                splat_pixel(p, col, row, __fmul_rn(z[k], depth_scale), cam, rfx, rfy, views, near_plane, out_w, out_n, u_max, v_max, id_offset, n,
+                            zbuf, out_uvz);
+            }
+        }
     }
 }
 
@@ -117,87 +147,122 @@ __device__ __forceinline__ uint32_t gather_rgb(const uint8_t *__restrict__ colou
 }
 
 // One thread per target pixel (scalar stores): used when widths / pitches are not multiples of 4.
-// VEC = 4: one thread per 4 consecutive target pixels of a row, word stores.
+// VEC = 4: one thread per 4 consecutive target pixels of a row, word stores; two such groups per iteration with both
+// groups' z-buffer loads issued first and both groups' colour gathers second (ncu v1: 44 % issue-active, 48 % of DRAM
+// peak, stalled on the key -> gather dependency), 32-bit index arithmetic, every CTA resident.
 template <int VEC>
 __global__ void __launch_bounds__(kThreads)
     resolve_kernel(unsigned long long *__restrict__ zbuf, const uint8_t *__restrict__ colour, int out_w, int out_h, uint32_t bg_rgb,
                    uint32_t fill_rgb, uint32_t flags, uint8_t *__restrict__ out_rgb, int64_t rgb_pitch, uint8_t *__restrict__ out_mask,
                    int64_t mask_pitch, float *__restrict__ out_depth, int64_t depth_pitch, int32_t *__restrict__ out_ids) {
-    const int groups_per_row = out_w / VEC;
-    const int64_t n_groups = (int64_t)groups_per_row * out_h;
+    constexpr int G = VEC == 4 ? 2 : 1;  // groups in flight per thread
+    const uint32_t groups_per_row = (uint32_t)out_w / VEC;
+    const uint32_t n_groups = groups_per_row * (uint32_t)out_h, stride = gridDim.x * kThreads;
     const bool collide = flags & MDVT_FLAG_BG_COLLIDE, reset = flags & MDVT_FLAG_RESET_ZBUF, mask_rgb = flags & MDVT_FLAG_MASK_RGB;
-    for (int64_t gidx = blockIdx.x * (int64_t)kThreads + threadIdx.x; gidx < n_groups; gidx += (int64_t)gridDim.x * kThreads) {
-        const int row = (int)(gidx / groups_per_row), col0 = (int)(gidx - (int64_t)row * groups_per_row) * VEC;
-        const int64_t t0 = (int64_t)row * out_w + col0;
-        unsigned long long key[4];
-        if (VEC == 4) {
-            const ulonglong2 a = reinterpret_cast<const ulonglong2 *>(zbuf + t0)[0];
-            const ulonglong2 b = reinterpret_cast<const ulonglong2 *>(zbuf + t0)[1];
-            key[0] = a.x; key[1] = a.y; key[2] = b.x; key[3] = b.y;
-        } else {
-            key[0] = zbuf[t0];
-        }
-        uint32_t px[4], mk[4];
+    for (uint32_t g0 = blockIdx.x * kThreads + threadIdx.x; g0 < n_groups; g0 += stride * G) {
+        unsigned long long key[G][4];
+        uint32_t px[G][4], mk[G][4];
+        int rows[G], cols[G];
+        bool on[G];
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-            bool hole = key[k] == MDVT_ZBUF_EMPTY;
-            uint32_t c = fill_rgb;
-            if (!hole) {
-                c = gather_rgb(colour, (uint32_t)key[k]);
-                if (collide && c == bg_rgb) hole = true;
-                if (hole) c = fill_rgb;
-            }
-            px[k] = c;
-            mk[k] = hole ? 1u : 0u;
-            if (out_depth)
-                out_depth[row * depth_pitch + col0 + k] = (key[k] == MDVT_ZBUF_EMPTY) ? 0.0f : __uint_as_float((uint32_t)(key[k] >> 32));
-            if (out_ids) out_ids[t0 + k] = (key[k] == MDVT_ZBUF_EMPTY) ? -1 : (int32_t)(uint32_t)key[k];
-        }
-        if (reset) {
-            if (VEC == 4) {
-                const ulonglong2 e = make_ulonglong2(MDVT_ZBUF_EMPTY, MDVT_ZBUF_EMPTY);
-                reinterpret_cast<ulonglong2 *>(zbuf + t0)[0] = e;
-                reinterpret_cast<ulonglong2 *>(zbuf + t0)[1] = e;
-            } else {
-                zbuf[t0] = MDVT_ZBUF_EMPTY;
+        for (int j = 0; j < G; ++j) {
+            const uint32_t gidx = g0 + j * stride;
+            on[j] = gidx < n_groups;
+            rows[j] = (int)(gidx / groups_per_row);
+            cols[j] = (int)(gidx - (uint32_t)rows[j] * groups_per_row) * VEC;
+            if (on[j]) {
+                const uint32_t t0 = (uint32_t)rows[j] * (uint32_t)out_w + (uint32_t)cols[j];
+                if (VEC == 4) {
+                    const ulonglong2 a = reinterpret_cast<const ulonglong2 *>(zbuf + t0)[0];
+                    const ulonglong2 b = reinterpret_cast<const ulonglong2 *>(zbuf + t0)[1];
+                    key[j][0] = a.x; key[j][1] = a.y; key[j][2] = b.x; key[j][3] = b.y;
+                } else {
+                    key[j][0] = zbuf[t0];
+                }
             }
         }
-        if (out_rgb) {
-            uint8_t *o = out_rgb + row * rgb_pitch + (int64_t)col0 * 3;
-            if (VEC == 4) {
-                uint32_t *ow = reinterpret_cast<uint32_t *>(o);
-                ow[0] = px[0] | (px[1] << 24);
-                ow[1] = (px[1] >> 8) | (px[2] << 16);
-                ow[2] = (px[2] >> 16) | (px[3] << 8);
-            } else {
-                o[0] = (uint8_t)px[0]; o[1] = (uint8_t)(px[0] >> 8); o[2] = (uint8_t)(px[0] >> 16);
-            }
-        }
-        if (out_mask) {
-            if (mask_rgb) {
-                uint8_t *o = out_mask + row * mask_pitch + (int64_t)col0 * 3;
-                uint32_t m[4];
 #pragma unroll
-                for (int k = 0; k < VEC; ++k) m[k] = mk[k] ? bg_rgb : 0u;
+        for (int j = 0; j < G; ++j) {
+            if (!on[j]) continue;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                bool hole = key[j][k] == MDVT_ZBUF_EMPTY;
+                uint32_t c = fill_rgb;
+                if (!hole) {
+                    c = gather_rgb(colour, (uint32_t)key[j][k]);
+                    if (collide && c == bg_rgb) hole = true;
+                    if (hole) c = fill_rgb;
+                }
+                px[j][k] = c;
+                mk[j][k] = hole ? 1u : 0u;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            if (!on[j]) continue;
+            const int row = rows[j], col0 = cols[j];
+            const uint32_t t0 = (uint32_t)row * (uint32_t)out_w + (uint32_t)col0;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                if (out_depth)
+                    out_depth[row * depth_pitch + col0 + k] =
+                        (key[j][k] == MDVT_ZBUF_EMPTY) ? 0.0f : __uint_as_float((uint32_t)(key[j][k] >> 32));
+                if (out_ids) out_ids[t0 + k] = (key[j][k] == MDVT_ZBUF_EMPTY) ? -1 : (int32_t)(uint32_t)key[j][k];
+            }
+            if (reset) {
+                if (VEC == 4) {
+                    const ulonglong2 e = make_ulonglong2(MDVT_ZBUF_EMPTY, MDVT_ZBUF_EMPTY);
+                    reinterpret_cast<ulonglong2 *>(zbuf + t0)[0] = e;
+                    reinterpret_cast<ulonglong2 *>(zbuf + t0)[1] = e;
+                } else {
+                    zbuf[t0] = MDVT_ZBUF_EMPTY;
+                }
+            }
+            if (out_rgb) {
+                uint8_t *o = out_rgb + row * rgb_pitch + (int64_t)col0 * 3;
                 if (VEC == 4) {
                     uint32_t *ow = reinterpret_cast<uint32_t *>(o);
-                    ow[0] = m[0] | (m[1] << 24);
-                    ow[1] = (m[1] >> 8) | (m[2] << 16);
-                    ow[2] = (m[2] >> 16) | (m[3] << 8);
+                    ow[0] = px[j][0] | (px[j][1] << 24);
+                    ow[1] = (px[j][1] >> 8) | (px[j][2] << 16);
+                    ow[2] = (px[j][2] >> 16) | (px[j][3] << 8);
                 } else {
-                    o[0] = (uint8_t)m[0]; o[1] = (uint8_t)(m[0] >> 8); o[2] = (uint8_t)(m[0] >> 16);
+                    o[0] = (uint8_t)px[j][0]; o[1] = (uint8_t)(px[j][0] >> 8); o[2] = (uint8_t)(px[j][0] >> 16);
                 }
-            } else {
-                uint8_t *o = out_mask + row * mask_pitch + col0;
-                if (VEC == 4) {
-                    *reinterpret_cast<uint32_t *>(o) =
-                        (mk[0] * 0xFFu) | ((mk[1] * 0xFFu) << 8) | ((mk[2] * 0xFFu) << 16) | ((mk[3] * 0xFFu) << 24);
+            }
+            if (out_mask) {
+                if (mask_rgb) {
+                    uint8_t *o = out_mask + row * mask_pitch + (int64_t)col0 * 3;
+                    uint32_t m[4];
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) m[k] = mk[j][k] ? bg_rgb : 0u;
+                    if (VEC == 4) {
+                        uint32_t *ow = reinterpret_cast<uint32_t *>(o);
+                        ow[0] = m[0] | (m[1] << 24);
+                        ow[1] = (m[1] >> 8) | (m[2] << 16);
+                        ow[2] = (m[2] >> 16) | (m[3] << 8);
+                    } else {
+                        o[0] = (uint8_t)m[0]; o[1] = (uint8_t)(m[0] >> 8); o[2] = (uint8_t)(m[0] >> 16);
+                    }
                 } else {
-                    o[0] = mk[0] ? 255 : 0;
+                    uint8_t *o = out_mask + row * mask_pitch + col0;
+                    if (VEC == 4) {
+                        *reinterpret_cast<uint32_t *>(o) =
+                            (mk[j][0] * 0xFFu) | ((mk[j][1] * 0xFFu) << 8) | ((mk[j][2] * 0xFFu) << 16) | ((mk[j][3] * 0xFFu) << 24);
+                    } else {
+                        o[0] = mk[j][0] ? 255 : 0;
+                    }
                 }
             }
         }
     }
+}
+
+// Resident CTAs per SM of a kernel (occupancy API), looked up once per kernel.
+template <typename K>
+static int resident_ctas(K kernel, int threads) {
+    int ctas = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kernel, threads, 0) != cudaSuccess || ctas < 1) ctas = 1;
+    return ctas;
 }
 
 static int grid_for(int64_t work_items) {
@@ -220,8 +285,8 @@ extern "C" int mdvt_zbuf_clear(uint64_t *zbuf, int64_t n_slots, void *stream) {
     return MDVT_OK;
 }
 
-static int launch_project_splat(const void *depth_src, const mdvt_source *src, const ViewPack &pack, float near_plane, int out_w, int out_h,
-                                uint32_t id_offset, unsigned long long *zb, float *out_uvz, cudaStream_t st);
+static int launch_project_splat(const void *depth_src, const mdvt_source *src, const ViewPack &pack, const mdvt_view *view_dev, float near_plane,
+                                int out_w, int out_h, uint32_t id_offset, unsigned long long *zb, float *out_uvz, cudaStream_t st);
 
 static int pack_views(const mdvt_view *views_host, int n_views, ViewPack &pack) {
     MDVT_REQUIRE(n_views >= 1 && n_views <= kMaxViews, "n_views must be 1..%d", kMaxViews);
@@ -240,8 +305,8 @@ extern "C" int mdvt_project_splat(const void *depth_src, const mdvt_source *src,
     MDVT_REQUIRE(depth_src && zbuf, "NULL buffer");
     MDVT_REQUIRE(out_w > 0 && out_h > 0, "bad output size %dx%d", out_w, out_h);
     MDVT_REQUIRE((int64_t)src->width * src->height + id_offset <= 0xFFFFFFFFll, "source index does not fit the 32-bit z-buffer payload");
-    return launch_project_splat(depth_src, src, pack, near_plane, out_w, out_h, id_offset, reinterpret_cast<unsigned long long *>(zbuf), out_uvz,
-                                static_cast<cudaStream_t>(stream));
+    return launch_project_splat(depth_src, src, pack, nullptr, near_plane, out_w, out_h, id_offset, reinterpret_cast<unsigned long long *>(zbuf),
+                                out_uvz, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mdvt_splat_points(const float *xyz, int64_t n_points, const mdvt_view *views_host, int n_views, float near_plane,
@@ -272,29 +337,43 @@ static int launch_resolve(unsigned long long *zb, const uint8_t *colour_rgb, int
                       (!out_mask || (reinterpret_cast<uintptr_t>(out_mask) % 4 == 0 && mask_pitch % 4 == 0));
     bg_rgb &= 0xFFFFFF;
     fill_rgb &= 0xFFFFFF;
+    MDVT_REQUIRE((int64_t)out_w * out_h < 0x7FFFFFFFll, "target plane must hold fewer than 2^31 pixels");
+    static int per_sm4 = 0, per_sm1 = 0;
+    if (!per_sm4) per_sm4 = resident_ctas(resolve_kernel<4>, kThreads);
+    if (!per_sm1) per_sm1 = resident_ctas(resolve_kernel<1>, kThreads);
+    auto grid_of = [&](int64_t items, int per_sm) {
+        const int64_t blocks = (items + kThreads - 1) / kThreads, cap = (int64_t)sm_count() * per_sm;
+        return (int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
+    };
     if (vec4) {
-        resolve_kernel<4><<<grid_for((int64_t)out_w / 4 * out_h), kThreads, 0, st>>>(
+        resolve_kernel<4><<<grid_of(((int64_t)out_w / 4 * out_h + 1) / 2, per_sm4), kThreads, 0, st>>>(
             zb, colour_rgb, out_w, out_h, bg_rgb, fill_rgb, flags, out_rgb, rgb_pitch, out_mask, mask_pitch, out_depth, depth_pitch, out_ids);
     } else {
-        resolve_kernel<1><<<grid_for((int64_t)out_w * out_h), kThreads, 0, st>>>(
+        resolve_kernel<1><<<grid_of((int64_t)out_w * out_h, per_sm1), kThreads, 0, st>>>(
             zb, colour_rgb, out_w, out_h, bg_rgb, fill_rgb, flags, out_rgb, rgb_pitch, out_mask, mask_pitch, out_depth, depth_pitch, out_ids);
     }
     MDVT_CUDA_TRY(cudaGetLastError());
     return MDVT_OK;
 }
 
-static int launch_project_splat(const void *depth_src, const mdvt_source *src, const ViewPack &pack, float near_plane, int out_w, int out_h,
-                                uint32_t id_offset, unsigned long long *zb, float *out_uvz, cudaStream_t st) {
+static int launch_project_splat(const void *depth_src, const mdvt_source *src, const ViewPack &pack, const mdvt_view *view_dev, float near_plane,
+                                int out_w, int out_h, uint32_t id_offset, unsigned long long *zb, float *out_uvz, cudaStream_t st) {
     MDVT_REQUIRE((int64_t)src->width * src->height < 0x7FFFFFFFll && (int64_t)out_w * out_h * pack.n < 0x7FFFFFFFll,
                  "source / target planes must hold fewer than 2^31 pixels");
     SourceCam cam{src->fx, src->fy, src->cx, src->cy, src->grid_sx, src->grid_sy};
     const int col_blocks = (src->width + kSplatThreads - 1) / kSplatThreads;
-    int row_blocks = (sm_count() * 16 + col_blocks - 1) / col_blocks;  // ~8 resident CTAs per SM, rows strided
-    if (row_blocks > src->height) row_blocks = src->height;
-    const dim3 grid(col_blocks, row_blocks);
-#define CALL(D, B)                                                                                                                 \
-    project_splat_kernel<D, B><<<grid, kSplatThreads, 0, st>>>(depth_src, src->width, src->height, src->dec_const, src->depth_scale, cam, pack, \
-                                                          near_plane, out_w, out_h, id_offset, zb, out_uvz)
+#define CALL(D, B)                                                                                                                   \
+    do {                                                                                                                             \
+        auto kernel = view_dev ? project_splat_kernel<D, B, true> : project_splat_kernel<D, B, false>;                               \
+        static int per_sm_of[2] = {0, 0};                                                                                            \
+        int &per_sm = per_sm_of[view_dev ? 1 : 0];                                                                                   \
+        if (!per_sm) per_sm = resident_ctas(kernel, kSplatThreads);                                                                   \
+        int row_blocks = sm_count() * per_sm / col_blocks; /* every CTA resident: no second wave */                                  \
+        if (row_blocks < 1) row_blocks = 1;                                                                                          \
+        if (row_blocks > src->height) row_blocks = src->height;                                                                      \
+        kernel<<<dim3(col_blocks, row_blocks), kSplatThreads, 0, st>>>(depth_src, src->width, src->height, src->dec_const, src->depth_scale, cam, \
+                                                                     pack, view_dev, near_plane, out_w, out_h, id_offset, zb, out_uvz); \
+    } while (0)
     MDVT_DISPATCH_SOURCE(src->decoder, src->bit16, CALL);
 #undef CALL
     MDVT_CUDA_TRY(cudaGetLastError());
@@ -331,7 +410,7 @@ extern "C" int mdvt_render_views(const void *depth_src, int64_t depth_frame_stri
         ViewPack pack{};
         if (int rc = pack_views(views_host + (int64_t)f * n_views, n_views, pack)) return rc;
         const uint8_t *dsrc = static_cast<const uint8_t *>(depth_src) + f * depth_frame_stride;
-        if (int rc = launch_project_splat(dsrc, src, pack, near_plane, out_w, out_h, 0, zb, nullptr, st)) return rc;
+        if (int rc = launch_project_splat(dsrc, src, pack, nullptr, near_plane, out_w, out_h, 0, zb, nullptr, st)) return rc;
         for (int v = 0; v < n_views; ++v) {
             auto at = [&](const mdvt_plane_layout *L) -> uint8_t * {
                 return (L && L->base) ? static_cast<uint8_t *>(L->base) + f * L->frame_stride + v * L->view_stride : nullptr;
@@ -342,6 +421,41 @@ extern "C" int mdvt_render_views(const void *depth_src, int64_t depth_frame_stri
                                         depth_out ? depth_out->row_pitch / 4 : 0, nullptr, st))
                 return rc;
         }
+    }
+    return MDVT_OK;
+}
+
+// 3d_view_depthfile.py --render, whole chunk, no host synchronisation: centroid -> device look-at -> splat -> resolve.
+extern "C" int mdvt_novel_view_frames(const void *depth_src, int64_t depth_frame_stride, const uint8_t *colour_rgb, int64_t colour_frame_stride,
+                                      int n_frames, const mdvt_source *centroid_src, const mdvt_source *src, const double *K_host,
+                                      const double *poses_host, const mdvt_lookat *look, float near_plane, int out_w, int out_h,
+                                      uint64_t *zbuf, double *sums_dev, mdvt_view *views_dev, uint32_t bg_rgb, uint32_t fill_rgb,
+                                      uint32_t flags, const mdvt_plane_layout *rgb_out, const mdvt_plane_layout *mask_out, void *stream) {
+    MDVT_REQUIRE(n_frames >= 0, "negative frame count");
+    MDVT_REQUIRE(out_w > 0 && out_h > 0, "bad output size %dx%d", out_w, out_h);
+    if (int rc = check_source(centroid_src)) return rc;
+    if (int rc = check_source(src)) return rc;
+    if (n_frames == 0) return MDVT_OK;
+    MDVT_REQUIRE(depth_src && colour_rgb && K_host && look && zbuf && sums_dev && views_dev && rgb_out && rgb_out->base, "NULL buffer");
+    MDVT_REQUIRE(reinterpret_cast<uintptr_t>(views_dev) % 16 == 0, "views_dev must be 16-byte aligned");
+    MDVT_REQUIRE(centroid_src->width == src->width && centroid_src->height == src->height, "the two source descriptions differ in size");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned long long *zb = reinterpret_cast<unsigned long long *>(zbuf);
+    ViewPack pack{};
+    pack.n = 1;
+    const int64_t sums_stride = 4 + MDVT_REDUCE_SCRATCH_DOUBLES;
+    for (int f = 0; f < n_frames; ++f) {
+        const uint8_t *dsrc = static_cast<const uint8_t *>(depth_src) + f * depth_frame_stride;
+        if (int rc = launch_centroid_lookat(dsrc, centroid_src, K_host, poses_host ? poses_host + 16 * (int64_t)f : nullptr, look,
+                                            sums_dev + f * sums_stride, views_dev + f, st))
+            return rc;
+        if (int rc = launch_project_splat(dsrc, src, pack, views_dev + f, near_plane, out_w, out_h, 0, zb, nullptr, st)) return rc;
+        auto at = [&](const mdvt_plane_layout *L) -> uint8_t * {
+            return (L && L->base) ? static_cast<uint8_t *>(L->base) + f * L->frame_stride : nullptr;
+        };
+        if (int rc = launch_resolve(zb, colour_rgb + f * colour_frame_stride, out_w, out_h, bg_rgb, fill_rgb, flags | MDVT_FLAG_RESET_ZBUF,
+                                    at(rgb_out), rgb_out->row_pitch, at(mask_out), mask_out ? mask_out->row_pitch : 0, nullptr, 0, nullptr, st))
+            return rc;
     }
     return MDVT_OK;
 }

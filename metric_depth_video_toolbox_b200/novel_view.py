@@ -2,10 +2,12 @@
 batches of frames.  Per frame: decode -> unproject -> optional pose -> look-at camera aimed at the vertex
 centroid (Open3D get_center(), :231) -> z-buffered splat -> white-background image.
 
-The centroid is a per-frame reduction that decides the camera of the same frame.  Instead of one host round
-trip per frame, a chunk is processed in two passes: all centroids of the chunk (one reduction kernel per
-frame, results in one device buffer, ONE small D2H copy), then the look-at matrices (host scalars) and the
-splat + resolve per frame."""
+The centroid is a per-frame reduction that decides the camera of the same frame.  `render_device` runs the whole
+chunk in ONE library call with no host round trip (`mdvt_novel_view_frames`): per frame the reduction, a
+finishing kernel that also evaluates the look-at camera in float64 on the device, the splat reading that camera
+from device memory, and the resolve.  `render_device_hostcam` is the two-pass form (all centroids of the chunk,
+one small D2H copy, NumPy look-at matrices, splat + resolve per frame) kept as the cross-check of the device
+camera."""
 from __future__ import annotations
 
 from dataclasses import dataclass
@@ -42,6 +44,8 @@ class NovelViewRenderer:
         self.K = geo.compute_camera_matrix(params.xfov, params.yfov, params.width, params.height)
         self._zbuf = None
         self._sums = None
+        self._views = None
+        self._csums = None
 
     def _pose(self, frame: int):
         return None if self.p.transformations is None else np.asarray(self.p.transformations[frame], dtype=np.float64)
@@ -51,12 +55,12 @@ class NovelViewRenderer:
         p = self.p
         n = depth_rgb.shape[0]
         stride = 4 + _lib.REDUCE_SCRATCH_DOUBLES
-        if self._sums is None or self._sums.shape[0] < n:
-            self._sums = torch.empty((n, stride), dtype=torch.float64, device=depth_rgb.device)
+        if self._csums is None or self._csums.shape[0] < n or self._csums.device != depth_rgb.device:
+            self._csums = torch.empty((n, stride), dtype=torch.float64, device=depth_rgb.device)
         src = ops.make_source(p.width, p.height, self.K, p.max_depth, "D1", True, 1.0, p.of_by_one)
         for k in range(n):
-            ops.centroid_sums(depth_rgb[k], src, self.K, self._pose(start_frame + k), out=self._sums[k])
-        s = self._sums[:n, :4].cpu().numpy()  # the one synchronising copy of the chunk
+            ops.centroid_sums(depth_rgb[k], src, self.K, self._pose(start_frame + k), out=self._csums[k])
+        s = self._csums[:n, :4].cpu().numpy()  # the one synchronising copy of the chunk
         return s[:, :3] / s[:, 3:4]
 
     def extrinsic(self, centroid: np.ndarray) -> np.ndarray:
@@ -76,9 +80,7 @@ class NovelViewRenderer:
             M = M @ pose
         return ops.ViewSpec(M, K[0, 0], K[0, 0], K[0, 2], K[1, 2])
 
-    def render_device(self, depth_rgb: torch.Tensor, colour: torch.Tensor, start_frame: int = 0, out_rgb: Optional[torch.Tensor] = None,
-                      out_mask: Optional[torch.Tensor] = None):
-        """depth_rgb / colour (n, H, W, 3) u8 CUDA -> (rgb (n, H, W, 3) u8, hole mask (n, H, W) u8)."""
+    def _outputs(self, depth_rgb, out_rgb, out_mask):
         p = self.p
         n, h, w, _ = depth_rgb.shape
         if (w, h) != (p.width, p.height):
@@ -90,6 +92,31 @@ class NovelViewRenderer:
             out_mask = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
         if self._zbuf is None or tuple(self._zbuf.shape) != (1, h, w) or self._zbuf.device != dev:
             self._zbuf = ops.new_zbuf(1, w, h, dev)
+        return n, h, w, out_rgb, out_mask
+
+    def render_device(self, depth_rgb: torch.Tensor, colour: torch.Tensor, start_frame: int = 0, out_rgb: Optional[torch.Tensor] = None,
+                      out_mask: Optional[torch.Tensor] = None):
+        """depth_rgb / colour (n, H, W, 3) u8 CUDA -> (rgb (n, H, W, 3) u8, hole mask (n, H, W) u8).  Asynchronous: one
+        library call, cameras computed on the device (`self.last_views`: (n, 16) float32, `self.last_sums`)."""
+        p = self.p
+        n, h, w, out_rgb, out_mask = self._outputs(depth_rgb, out_rgb, out_mask)
+        stride = 4 + _lib.REDUCE_SCRATCH_DOUBLES
+        if self._sums is None or self._sums.shape[0] < n or self._sums.device != depth_rgb.device:
+            self._sums = torch.empty((n, stride), dtype=torch.float64, device=depth_rgb.device)
+            self._views = torch.empty((n, 16), dtype=torch.float32, device=depth_rgb.device)
+        src_c = ops.make_source(w, h, self.K, p.max_depth, "D1", True, 1.0, p.of_by_one)
+        src = ops.make_source(w, h, self.K, p.max_depth, "D1", True, 1.0, False)
+        poses = None if p.transformations is None else np.stack([self._pose(start_frame + k) for k in range(n)])
+        ops.novel_view_frames(depth_rgb, colour, src_c, src, self.K, p.cam_pos, p.target, poses, self._zbuf, out_rgb, out_mask, p.bg_rgb,
+                              p.bg_rgb, 0, p.near, self._sums[:n], self._views[:n])
+        self.last_sums, self.last_views = self._sums[:n], self._views[:n]
+        return out_rgb, out_mask
+
+    def render_device_hostcam(self, depth_rgb: torch.Tensor, colour: torch.Tensor, start_frame: int = 0,
+                              out_rgb: Optional[torch.Tensor] = None, out_mask: Optional[torch.Tensor] = None):
+        """Same result with the cameras evaluated on the host (synchronises once per chunk)."""
+        p = self.p
+        n, h, w, out_rgb, out_mask = self._outputs(depth_rgb, out_rgb, out_mask)
         centres = self.centroids(depth_rgb, start_frame)
         src = ops.make_source(w, h, self.K, p.max_depth, "D1", True, 1.0, False)
         views = [[self.view_of(start_frame + k, centres[k])] for k in range(n)]

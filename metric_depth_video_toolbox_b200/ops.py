@@ -339,6 +339,59 @@ def render_views(depth_src: torch.Tensor, colour: torch.Tensor, sources: Sequenc
     return out_rgb, out_mask, out_depth
 
 
+def novel_view_frames(depth_src: torch.Tensor, colour: torch.Tensor, centroid_source: _lib.Source, source: _lib.Source, K: np.ndarray,
+                      cam_pos, target, poses, zbuf: torch.Tensor, out_rgb: torch.Tensor, out_mask: Optional[torch.Tensor] = None,
+                      bg_rgb=(255, 255, 255), fill_rgb=(255, 255, 255), flags: int = 0, near: float = NEAR_PLANE,
+                      sums: Optional[torch.Tensor] = None, views_dev: Optional[torch.Tensor] = None):
+    """`3d_view_depthfile.py --render`'s frame loop (:133-255) for a chunk in ONE library call and no host round trip:
+    per frame vertex centroid -> look-at camera (on the device) -> splat -> resolve.  `cam_pos`: --x --y --z;
+    `target`: three values or None per axis (None: centroid); `poses`: (n, 4, 4) float64 or None.
+    Returns (out_rgb, out_mask, sums (n, 4+scratch) f64 device, views (n, 16) f32 device: M 3x4 then fx fy cx cy)."""
+    n, h, w = depth_src.shape[0], source.height, source.width
+    if n == 0:
+        return out_rgb, out_mask, sums, views_dev
+    _need_source(depth_src[0], source)
+    if not depth_src.is_contiguous():
+        raise ValueError("depth_src must be contiguous")
+    _need(colour, torch.uint8, "colour")
+    _need(zbuf, torch.int64, "zbuf")
+    if tuple(zbuf.shape) != (1, h, w):
+        raise ValueError(f"zbuf shape {tuple(zbuf.shape)} != (1, {h}, {w})")
+    if colour.shape[0] != n or colour.shape[1] * colour.shape[2] != w * h:
+        raise ValueError("colour must hold one (H, W, 3) frame per depth frame")
+    dev = depth_src.device
+    stride = 4 + _lib.REDUCE_SCRATCH_DOUBLES
+    if sums is None:
+        sums = torch.empty((n, stride), dtype=torch.float64, device=dev)
+    if views_dev is None:
+        views_dev = torch.empty((n, 16), dtype=torch.float32, device=dev)
+    if tuple(_need(sums, torch.float64, "sums").shape) != (n, stride) or tuple(_need(views_dev, torch.float32, "views_dev").shape) != (n, 16):
+        raise ValueError("sums must be (n, 4 + scratch) float64 and views_dev (n, 16) float32")
+    K = np.asarray(K, dtype=np.float64)
+    look = _lib.LookAt()
+    cam32 = np.array(cam_pos).astype(np.float32)          # 3d_view_depthfile.py:240
+    for a in range(3):
+        look.cam_pos[a] = float(cam32[a])
+        look.target_set[a] = int(target[a] is not None)
+        look.target[a] = 0.0 if target[a] is None else float(target[a])
+    look.y_scale = float(K[1, 1] / K[0, 0])
+    look.fx = look.fy = float(np.float32(K[0, 0]))
+    look.cx, look.cy = float(np.float32(K[0, 2])), float(np.float32(K[1, 2]))
+    pose_arr = None
+    if poses is not None:
+        pm = np.ascontiguousarray(np.asarray(poses, dtype=np.float64).reshape(n, 16))
+        pose_arr = pm.ctypes.data_as(C.POINTER(C.c_double))
+    rgb_l = _plane_layout(_need(out_rgb, torch.uint8, "out_rgb"), n, 1, h, w, 3, "out_rgb")
+    mask_ch = 3 if flags & FLAG_MASK_RGB else 1
+    mask_l = _plane_layout(None if out_mask is None else _need(out_mask, torch.uint8, "out_mask"), n, 1, h, w, mask_ch, "out_mask")
+    _lib.check(_lib.load().mdvt_novel_view_frames(_ptr(depth_src), depth_src.stride(0) * depth_src.element_size(), _ptr(colour), colour.stride(0),
+                                                  n, C.byref(centroid_source), C.byref(source), _k4(K), pose_arr, C.byref(look),
+                                                  float(np.float32(near)), w, h, _ptr(zbuf), _ptr(sums), _ptr(views_dev), pack_rgb(bg_rgb),
+                                                  pack_rgb(fill_rgb), flags, C.byref(rgb_l), None if mask_l is None else C.byref(mask_l),
+                                                  _stream()))
+    return out_rgb, out_mask, sums, views_dev
+
+
 def splat_points(xyz: torch.Tensor, views: Sequence[ViewSpec], out_w: int, out_h: int, zbuf: torch.Tensor,
                  near: float = NEAR_PLANE, id_offset: int = 0):
     """Explicit (N, 3) float32 points through the same visibility rule (the reference's point painter)."""

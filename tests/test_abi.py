@@ -45,6 +45,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.StereoFrame) == 16
     assert C.sizeof(_lib.PlaneLayout) == 32
     assert C.sizeof(_lib.ConvFrame) == 160
+    assert C.sizeof(_lib.LookAt) == 88
 
 
 def test_sass_contains_tma_and_atomics():

@@ -242,6 +242,48 @@ def test_novel_view_renderer_vs_oracle(of_by_one, yfov):
         assert (mask[k].cpu().numpy() != want_mask).mean() < 3e-3
 
 
+@pytest.mark.parametrize("of_by_one,yfov,posed", [(True, None, True), (False, 50.0, False), (True, 40.0, True)])
+def test_novel_view_device_camera_equals_host_camera(of_by_one, yfov, posed):
+    """mdvt_novel_view_frames evaluates centroid -> look-at -> view on the device: its cameras must equal the NumPy
+    helpers' (<= 1 float32 ulp per entry), and its images must be what the generic path renders from those cameras."""
+    w, h, n = 160, 120, 3
+    depth, colour = SyntheticClip(w, h, n, zero_fraction=0.005).frames()
+    T = None
+    if posed:
+        T = np.tile(np.eye(4), (n, 1, 1))
+        T[1, :3, 3] = (0.1, 0.0, -0.2)
+        c, s_ = np.cos(0.05), np.sin(0.05)
+        T[2, :3, :3] = [[c, 0, s_], [0, 1, 0], [-s_, 0, c]]
+    nv = NovelViewRenderer(NovelViewParams(w, h, 60, yfov, 100, (2.0, 2.0, -4.0), (None, 0.5, None), T, of_by_one=of_by_one), DEV)
+    d, c_ = cu(depth), cu(colour)
+    rgb, mask = nv.render_device(d, c_)
+    views_dev = nv.last_views.cpu().numpy()
+    sums_dev = nv.last_sums[:, :4].cpu().numpy()
+    centres = nv.centroids(d)
+    np.testing.assert_allclose(sums_dev[:, :3] / sums_dev[:, 3:4], centres, rtol=1e-13)
+    host_views = []
+    for k in range(n):
+        v = nv.view_of(k, centres[k]).to_c()
+        hv = np.array(list(v.M) + [v.fx, v.fy, v.cx, v.cy], dtype=np.float32)
+        host_views.append(hv)
+        ulps = np.abs(views_dev[k].view(np.int32).astype(np.int64) - hv.view(np.int32).astype(np.int64))
+        tiny = np.abs(hv) < 1e-12   # +-0 entries
+        assert (ulps[~tiny] <= 1).all(), (k, views_dev[k], hv)
+        assert (np.abs(views_dev[k][tiny]) < 1e-12).all()
+    # images: the generic path fed with the device's cameras, bit for bit
+    specs = [[ops.ViewSpec(views_dev[k][:12].reshape(3, 4).astype(np.float64), *[float(x) for x in views_dev[k][12:]])] for k in range(n)]
+    src = ops.make_source(w, h, nv.K, 100, "D1", True, 1.0, False)
+    zb = ops.new_zbuf(1, w, h, DEV)
+    rgb2 = torch.empty_like(rgb)
+    mask2 = torch.empty_like(mask)
+    ops.render_views(d, c_, [src], specs, w, h, zb, rgb2, mask2, None, (255, 255, 255), (255, 255, 255), 0)
+    assert torch.equal(rgb, rgb2) and torch.equal(mask, mask2)
+    assert bool((zb == -1).all())
+    rgb3, mask3 = nv.render_device_hostcam(d, c_)
+    assert (rgb3 != rgb).any(dim=-1).float().mean().item() < 1e-4
+    assert bool((mask != 0).any()) and bool((mask == 0).any())
+
+
 # ---------------------------------------------------------------------------------------------
 # script front ends, end to end on small FFV1 clips
 # ---------------------------------------------------------------------------------------------
