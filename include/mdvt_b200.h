@@ -236,13 +236,17 @@ typedef struct mdvt_lookat {
  * poses_host: n_frames x 16 doubles (row-major 4x4, the frame's transformation) or NULL.  sums_dev: n_frames x
  * (4 + MDVT_REDUCE_SCRATCH_DOUBLES) doubles (results {sum X, sum Y, sum Z, n} first); views_dev: n_frames
  * mdvt_view, 16-byte aligned; both stay valid for the caller to read back.  zbuf: one out_w x out_h plane, empty on
- * entry, left empty. */
+ * entry, left empty.  touched: mdvt_touched_bytes(out_w, out_h) bytes of scratch (per-segment "something was drawn
+ * here" flags that let K3 skip the z-buffer traffic of empty regions).  The centroid kernels run on an internal second
+ * stream forked from / joined to `stream` with events (legal under stream capture). */
+MDVT_API int64_t mdvt_touched_bytes(int out_w, int out_h);
 MDVT_API int mdvt_novel_view_frames(const void *depth_src, int64_t depth_frame_stride, const uint8_t *colour_rgb,
                            int64_t colour_frame_stride, int n_frames, const mdvt_source *centroid_src_host,
                            const mdvt_source *src_host, const double *K_host, const double *poses_host,
                            const mdvt_lookat *look_host, float near_plane, int out_w, int out_h, uint64_t *zbuf,
-                           double *sums_dev, mdvt_view *views_dev, uint32_t bg_rgb, uint32_t fill_rgb, uint32_t flags,
-                           const mdvt_plane_layout *rgb_out, const mdvt_plane_layout *mask_out, void *stream);
+                           double *sums_dev, mdvt_view *views_dev, uint8_t *touched, uint32_t bg_rgb, uint32_t fill_rgb,
+                           uint32_t flags, const mdvt_plane_layout *rgb_out, const mdvt_plane_layout *mask_out,
+                           void *stream);
 
 /* ---- per-frame reductions (fixed summation order: reproducible) -------------------------------- */
 /* Result buffers hold 4 doubles of result followed by MDVT_REDUCE_SCRATCH_DOUBLES doubles of scratch. */

@@ -96,8 +96,9 @@ _PROTOTYPES = {
     "mdvt_render_views": (C.c_int, [_u8p, C.c_int64, _u8p, C.c_int64, C.c_int, C.POINTER(Source), C.c_int, C.POINTER(View), C.c_int,
                                     C.c_float, C.c_int, C.c_int, _u64p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PlaneLayout),
                                     C.POINTER(PlaneLayout), C.POINTER(PlaneLayout), _stream]),
+    "mdvt_touched_bytes": (C.c_int64, [C.c_int, C.c_int]),
     "mdvt_novel_view_frames": (C.c_int, [_u8p, C.c_int64, _u8p, C.c_int64, C.c_int, C.POINTER(Source), C.POINTER(Source), C.POINTER(C.c_double),
-                                         C.POINTER(C.c_double), C.POINTER(LookAt), C.c_float, C.c_int, C.c_int, _u64p, _f64p, C.c_void_p,
+                                         C.POINTER(C.c_double), C.POINTER(LookAt), C.c_float, C.c_int, C.c_int, _u64p, _f64p, C.c_void_p, _u8p,
                                          C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PlaneLayout), C.POINTER(PlaneLayout), _stream]),
     "mdvt_edge_vertices": (C.c_int, [_u8p, C.POINTER(Source), C.POINTER(C.c_double), C.c_double, _u8p, _u8p, _f64p, _stream]),
     "mdvt_edge_splat": (C.c_int, [_u8p, C.POINTER(Source), C.POINTER(C.c_double), _u8p, C.POINTER(C.c_double), C.POINTER(C.c_double),

@@ -41,6 +41,76 @@ __device__ __forceinline__ void block_sum4(double (&a)[4]) {
     }
 }
 
+// finish_centroid_kernel + the camera of 3d_view_depthfile.py:231-241 on the device: look-at point = centroid with the
+// --tx/--ty/--tz overrides, cam_look_at (depth_map_tools.py:1618-1638: r, u, f as columns, translation (px, py, -pz)),
+// render()'s Y scale (:1528-1552) and the frame's pose folded into one 3x4, rounded to float32 into `view` -- the
+// per-frame host round trip (reduce -> D2H -> NumPy look-at -> launch) of v1 is gone; float64, one rounding per written
+// operation, evaluation order of the NumPy helpers (a 1-ulp float64 difference against BLAS-evaluated dot products can
+// survive the float32 rounding of an entry only with probability ~1e-8).
+struct Pose16d {
+    double m[16];
+    int on;
+};
+
+// Runs in the LAST CTA of centroid_partial_kernel to finish (threadfence + counter): no second launch, and the partials
+// are still in L2.  The sum over partials keeps its fixed order (by CTA index), so the result is reproducible.
+struct LookAtFinish {
+    double fx, fy, cx, cy;
+    Pose16d pose;
+    mdvt_lookat look;
+    double *out;
+    mdvt_view *view;
+    unsigned int *counter;  // zero on entry, left zero
+};
+
+__device__ __forceinline__ void finish_lookat(const double *partial, int n_blocks, const LookAtFinish &A) {
+    const double fx = A.fx, fy = A.fy, cx = A.cx, cy = A.cy;
+    const Pose16d &pose = A.pose;
+    const mdvt_lookat &look = A.look;
+    double *out = A.out;
+    mdvt_view *view = A.view;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int b = threadIdx.x; b < n_blocks; b += kThreads) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] += __ldcg(partial + b * 4 + k);
+    }
+    block_sum4(acc);
+    if (threadIdx.x != 0) return;
+    const double sz = acc[2], cnt = acc[3];
+    double X = (acc[0] - cx * sz) / fx, Y = (acc[1] - cy * sz) / fy, Z = sz;
+    if (pose.on) {
+        const double *m = pose.m;
+        const double x2 = m[0] * X + m[1] * Y + m[2] * Z + m[3] * cnt;
+        const double y2 = m[4] * X + m[5] * Y + m[6] * Z + m[7] * cnt;
+        const double z2 = m[8] * X + m[9] * Y + m[10] * Z + m[11] * cnt;
+        X = x2; Y = y2; Z = z2;
+    }
+    out[0] = X; out[1] = Y; out[2] = Z; out[3] = cnt;
+    double t[3] = {X / cnt, Y / cnt, Z / cnt};
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        if (look.target_set[a]) t[a] = look.target[a];
+    double f[3] = {t[0] - look.cam_pos[0], t[1] - look.cam_pos[1], t[2] - look.cam_pos[2]};
+    const double nf = sqrt((f[0] * f[0] + f[1] * f[1]) + f[2] * f[2]);
+    f[0] /= nf; f[1] /= nf; f[2] /= nf;
+    double r[3] = {1.0 * f[2] - 0.0 * f[1], 0.0 * f[0] - 0.0 * f[2], 0.0 * f[1] - 1.0 * f[0]};  // cross(up = (0, 1, 0), f)
+    const double nr = sqrt((r[0] * r[0] + r[1] * r[1]) + r[2] * r[2]);
+    r[0] /= nr; r[1] /= nr; r[2] /= nr;
+    const double u[3] = {f[1] * r[2] - f[2] * r[1], f[2] * r[0] - f[0] * r[2], f[0] * r[1] - f[1] * r[0]};
+    double M[12] = {r[0], u[0] * look.y_scale, f[0], look.cam_pos[0],
+                    r[1], u[1] * look.y_scale, f[1], look.cam_pos[1],
+                    r[2], u[2] * look.y_scale, f[2], -look.cam_pos[2]};
+    if (pose.on) {  // M (3x4) @ pose (4x4)
+        double P[12];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 4; ++j)
+                P[i * 4 + j] = ((M[i * 4] * pose.m[j] + M[i * 4 + 1] * pose.m[4 + j]) + M[i * 4 + 2] * pose.m[8 + j]) + M[i * 4 + 3] * pose.m[12 + j];
+        for (int k = 0; k < 12; ++k) M[k] = P[k];
+    }
+    for (int k = 0; k < 12; ++k) view->M[k] = (float)M[k];
+    view->fx = look.fx; view->fy = look.fy; view->cx = look.cx; view->cy = look.cy;
+}
+
 // Vertex sums of one frame.  The per-vertex formula is X = (xg - cx) * z / fx (depth_map_tools.py:1127-1128); its
 // SUM over the frame is rearranged so that the per-pixel work is float64 multiply-adds and no division:
 //     sum X = (sum(xg * z) - cx * sum(z)) / fx,   sum Y likewise,   sum Z = sum(z)
@@ -63,10 +133,10 @@ __device__ __forceinline__ void group_depths(const uint32_t w0, const uint32_t w
         z[k] = (double)__fmul_rn(depth_of<DECODER>(code_of<DECODER, BIT16>(r[k], gr[k], b[k]), dec_const), depth_scale);
 }
 
-template <int DECODER, bool BIT16, bool VEC4>
+template <int DECODER, bool BIT16, bool VEC4, bool LOOKAT>
 __global__ void __launch_bounds__(kThreads)
     centroid_partial_kernel(const void *__restrict__ src, int width, int64_t n, float dec_const, float depth_scale, float sx, float sy,
-                            int stretched, double *__restrict__ partial) {
+                            int stretched, double *partial, LookAtFinish fin) {
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     if (VEC4) {
         const int gpr = width / 4;                                   // groups per row
@@ -151,6 +221,19 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
         for (int k = 0; k < 4; ++k) partial[blockIdx.x * 4 + k] = acc[k];
     }
+    if (LOOKAT) {
+        __shared__ int is_last;
+        if (threadIdx.x == 0) {
+            __threadfence();
+            is_last = atomicAdd(fin.counter, 1u) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (is_last) {
+            __threadfence();
+            finish_lookat(partial, (int)gridDim.x, fin);
+            if (threadIdx.x == 0) *fin.counter = 0u;
+        }
+    }
 }
 
 // Single CTA: fixed-order sum of the partials, then the closed form above and the optional pose.
@@ -174,62 +257,6 @@ __global__ void __launch_bounds__(kThreads) finish_centroid_kernel(const double 
         }
         out[0] = X; out[1] = Y; out[2] = Z; out[3] = cnt;
     }
-}
-
-// finish_centroid_kernel + the camera of 3d_view_depthfile.py:231-241 on the device: look-at point = centroid with the
-// --tx/--ty/--tz overrides, cam_look_at (depth_map_tools.py:1618-1638: r, u, f as columns, translation (px, py, -pz)),
-// render()'s Y scale (:1528-1552) and the frame's pose folded into one 3x4, rounded to float32 into `view` -- the
-// per-frame host round trip (reduce -> D2H -> NumPy look-at -> launch) of v1 is gone; float64, one rounding per written
-// operation, evaluation order of the NumPy helpers (a 1-ulp float64 difference against BLAS-evaluated dot products can
-// survive the float32 rounding of an entry only with probability ~1e-8).
-struct Pose16d {
-    double m[16];
-    int on;
-};
-
-__global__ void __launch_bounds__(kThreads) finish_centroid_lookat_kernel(const double *__restrict__ partial, int n_blocks, double fx, double fy,
-                                                                          double cx, double cy, Pose16d pose, mdvt_lookat look,
-                                                                          double *__restrict__ out, mdvt_view *__restrict__ view) {
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int b = threadIdx.x; b < n_blocks; b += kThreads) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) acc[k] += partial[b * 4 + k];
-    }
-    block_sum4(acc);
-    if (threadIdx.x != 0) return;
-    const double sz = acc[2], cnt = acc[3];
-    double X = (acc[0] - cx * sz) / fx, Y = (acc[1] - cy * sz) / fy, Z = sz;
-    if (pose.on) {
-        const double *m = pose.m;
-        const double x2 = m[0] * X + m[1] * Y + m[2] * Z + m[3] * cnt;
-        const double y2 = m[4] * X + m[5] * Y + m[6] * Z + m[7] * cnt;
-        const double z2 = m[8] * X + m[9] * Y + m[10] * Z + m[11] * cnt;
-        X = x2; Y = y2; Z = z2;
-    }
-    out[0] = X; out[1] = Y; out[2] = Z; out[3] = cnt;
-    double t[3] = {X / cnt, Y / cnt, Z / cnt};
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-        if (look.target_set[a]) t[a] = look.target[a];
-    double f[3] = {t[0] - look.cam_pos[0], t[1] - look.cam_pos[1], t[2] - look.cam_pos[2]};
-    const double nf = sqrt((f[0] * f[0] + f[1] * f[1]) + f[2] * f[2]);
-    f[0] /= nf; f[1] /= nf; f[2] /= nf;
-    double r[3] = {1.0 * f[2] - 0.0 * f[1], 0.0 * f[0] - 0.0 * f[2], 0.0 * f[1] - 1.0 * f[0]};  // cross(up = (0, 1, 0), f)
-    const double nr = sqrt((r[0] * r[0] + r[1] * r[1]) + r[2] * r[2]);
-    r[0] /= nr; r[1] /= nr; r[2] /= nr;
-    const double u[3] = {f[1] * r[2] - f[2] * r[1], f[2] * r[0] - f[0] * r[2], f[0] * r[1] - f[1] * r[0]};
-    double M[12] = {r[0], u[0] * look.y_scale, f[0], look.cam_pos[0],
-                    r[1], u[1] * look.y_scale, f[1], look.cam_pos[1],
-                    r[2], u[2] * look.y_scale, f[2], -look.cam_pos[2]};
-    if (pose.on) {  // M (3x4) @ pose (4x4)
-        double P[12];
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 4; ++j)
-                P[i * 4 + j] = ((M[i * 4] * pose.m[j] + M[i * 4 + 1] * pose.m[4 + j]) + M[i * 4 + 2] * pose.m[8 + j]) + M[i * 4 + 3] * pose.m[12 + j];
-        for (int k = 0; k < 12; ++k) M[k] = P[k];
-    }
-    for (int k = 0; k < 12; ++k) view->M[k] = (float)M[k];
-    view->fx = look.fx; view->fy = look.fy; view->cx = look.cx; view->cy = look.cy;
 }
 
 template <int DECODER, bool BIT16>
@@ -264,7 +291,7 @@ __global__ void __launch_bounds__(kThreads) finish_sum4_kernel(const double *__r
 
 static int reduce_grid(int64_t n) {
     const int64_t blocks = (n + kThreads * 8 - 1) / (kThreads * 8);  // >= 8 elements per thread
-    const int64_t cap = sm_count() * 4 < kMaxBlocks ? sm_count() * 4 : kMaxBlocks;
+    const int64_t cap = sm_count() * 6 < kMaxBlocks - 1 ? sm_count() * 6 : kMaxBlocks - 1;  // the last scratch double is left free
     return (int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
 }
 
@@ -272,23 +299,25 @@ static int reduce_grid(int64_t n) {
 
 using namespace mdvt;
 
-static int launch_centroid_partials(const void *depth_src, const mdvt_source *src, double *partial, int *grid_out, cudaStream_t st) {
+static int launch_centroid_partials(const void *depth_src, const mdvt_source *src, double *partial, int *grid_out, const LookAtFinish *fin,
+                                    cudaStream_t st) {
     const int64_t n = (int64_t)src->width * src->height;
     const int stretched = !(src->grid_sx == 1.0f && src->grid_sy == 1.0f);
     const bool vec4 = (src->width % 4 == 0) && (n / 4 < 0x7FFFFFFFll) &&
                       (reinterpret_cast<uintptr_t>(depth_src) % (src->decoder == MDVT_SOURCE_F32 ? 16 : 4) == 0);
     const int grid = reduce_grid(vec4 ? n / 4 : n);
+    const LookAtFinish none{};
+#define ARGS depth_src, src->width, n, src->dec_const, src->depth_scale, src->grid_sx, src->grid_sy, stretched, partial
 #define CALL(D, B)                                                                                                            \
     do {                                                                                                                      \
-        if (vec4)                                                                                                             \
-            centroid_partial_kernel<D, B, true><<<grid, kThreads, 0, st>>>(depth_src, src->width, n, src->dec_const, src->depth_scale, \
-                                                                           src->grid_sx, src->grid_sy, stretched, partial);   \
-        else                                                                                                                  \
-            centroid_partial_kernel<D, B, false><<<grid, kThreads, 0, st>>>(depth_src, src->width, n, src->dec_const, src->depth_scale, \
-                                                                            src->grid_sx, src->grid_sy, stretched, partial);  \
+        if (vec4 && fin) centroid_partial_kernel<D, B, true, true><<<grid, kThreads, 0, st>>>(ARGS, *fin);                    \
+        else if (vec4) centroid_partial_kernel<D, B, true, false><<<grid, kThreads, 0, st>>>(ARGS, none);                     \
+        else if (fin) centroid_partial_kernel<D, B, false, true><<<grid, kThreads, 0, st>>>(ARGS, *fin);                      \
+        else centroid_partial_kernel<D, B, false, false><<<grid, kThreads, 0, st>>>(ARGS, none);                              \
     } while (0)
     MDVT_DISPATCH_SOURCE(src->decoder, src->bit16, CALL);
 #undef CALL
+#undef ARGS
     MDVT_CUDA_TRY(cudaGetLastError());
     *grid_out = grid;
     return MDVT_OK;
@@ -306,7 +335,7 @@ extern "C" int mdvt_centroid(const void *depth_src, const mdvt_source *src, cons
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     double *partial = out_sums + 4;
     int grid = 0;
-    if (int rc = launch_centroid_partials(depth_src, src, partial, &grid, st)) return rc;
+    if (int rc = launch_centroid_partials(depth_src, src, partial, &grid, nullptr, st)) return rc;
     finish_centroid_kernel<<<1, kThreads, 0, st>>>(partial, grid, K_host[0], K_host[1], K_host[2], K_host[3], pose, out_sums);
     MDVT_CUDA_TRY(cudaGetLastError());
     return MDVT_OK;
@@ -316,18 +345,18 @@ namespace mdvt {
 // Centroid of one frame -> look-at camera of the same frame, all on the device (used by mdvt_novel_view_frames).
 int launch_centroid_lookat(const void *depth_src, const mdvt_source *src, const double *K_host, const double *pose16_host,
                            const mdvt_lookat *look, double *out_sums, mdvt_view *view_dev, cudaStream_t st) {
-    Pose16d pose{};
+    LookAtFinish fin{};
+    fin.fx = K_host[0]; fin.fy = K_host[1]; fin.cx = K_host[2]; fin.cy = K_host[3];
     if (pose16_host) {
-        for (int k = 0; k < 16; ++k) pose.m[k] = pose16_host[k];
-        pose.on = 1;
+        for (int k = 0; k < 16; ++k) fin.pose.m[k] = pose16_host[k];
+        fin.pose.on = 1;
     }
-    double *partial = out_sums + 4;
+    fin.look = *look;
+    fin.out = out_sums;
+    fin.view = view_dev;
+    fin.counter = reinterpret_cast<unsigned int *>(out_sums + 4 + MDVT_REDUCE_SCRATCH_DOUBLES - 1);  // last scratch double (never a partial)
     int grid = 0;
-    if (int rc = launch_centroid_partials(depth_src, src, partial, &grid, st)) return rc;
-    finish_centroid_lookat_kernel<<<1, kThreads, 0, st>>>(partial, grid, K_host[0], K_host[1], K_host[2], K_host[3], pose, *look, out_sums,
-                                                         view_dev);
-    MDVT_CUDA_TRY(cudaGetLastError());
-    return MDVT_OK;
+    return launch_centroid_partials(depth_src, src, out_sums + 4, &grid, &fin, st);
 }
 }  // namespace mdvt
 

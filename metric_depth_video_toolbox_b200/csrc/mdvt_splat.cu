@@ -12,6 +12,12 @@ namespace mdvt {
 constexpr int kThreads = 256;
 constexpr int kMaxViews = 4;
 constexpr int kSplatThreads = 128;  // divides 640 / 1280 / 1920 / 3840: no idle tail block per row
+constexpr float kRoundMagic = 12582912.0f;     // 1.5 * 2^23
+constexpr int kRoundMagicBits = 0x4B400000;
+// "Touched" flags: one byte per 64-pixel segment of a target row, set by the splat next to its RED (single view only).
+// The resolve skips the z-buffer load AND the re-arm store of untouched segments: with the 62 % holes of the config-3
+// camera, z-buffer traffic drops from 2 x 66 MB to 2 x 25 MB per 4K frame and the touched part stays L2-resident.
+constexpr int kSegShift = 6;
 
 struct ViewPack {
     mdvt_view v[kMaxViews];
@@ -23,7 +29,8 @@ struct ViewPack {
 // All index arithmetic is 32-bit (the entry point checks that source and target planes have < 2^31 pixels).
 __device__ __forceinline__ void splat_pixel(uint32_t p, int col, int row, float z, const SourceCam &cam, float rfx, float rfy,
                                             const ViewPack &views, float near_plane, int out_w, uint32_t out_n, float u_max, float v_max,
-                                            uint32_t id_offset, uint32_t n, unsigned long long *__restrict__ zbuf, float *__restrict__ out_uvz) {
+                                            uint32_t id_offset, uint32_t n, unsigned long long *__restrict__ zbuf, float *__restrict__ out_uvz,
+                                            uint64_t keep, uint8_t *__restrict__ touched, int segs_per_row) {
     const float xg = __fmul_rn(__int2float_rn(col), cam.sx);
     const float yg = __fmul_rn(__int2float_rn(row), cam.sy);
     const float X = div_rn_by(__fmul_rn(__fsub_rn(xg, cam.cx), z), cam.fx, rfx);
@@ -46,12 +53,18 @@ __device__ __forceinline__ void splat_pixel(uint32_t p, int col, int row, float 
                 u = __fadd_rn(div_rn_by(__fmul_rn(vw.fx, Xv), Zv, rz), vw.cx);
                 v = __fadd_rn(div_rn_by(__fmul_rn(vw.fy, Yv), Zv, rz), vw.cy);
             }
-            const float ur = rintf(u), vr = rintf(v);  // round half to even, like np.round
+            // round half to even, like np.round, without FRND / F2I (quarter-rate conversion pipe): adding 1.5 * 2^23 rounds
+            // to an integer (the sum's ulp is 1) for |u| < 2^22 and leaves the integer in the mantissa; larger |u| stay far
+            // outside [0, u_max] and NaN stays NaN, so the bounds test still rejects them.
+            const float um = __fadd_rn(u, kRoundMagic), vm = __fadd_rn(v, kRoundMagic);
+            const float ur = __fsub_rn(um, kRoundMagic), vr = __fsub_rn(vm, kRoundMagic);
             // comparisons are false for NaN, so non-finite projections are culled too
             if (Zv > near_plane && ur >= 0.0f && ur <= u_max && vr >= 0.0f && vr <= v_max) {
-                const uint32_t t = (uint32_t)k * out_n + (uint32_t)(int)vr * (uint32_t)out_w + (uint32_t)(int)ur;
+                const uint32_t ui = (uint32_t)(__float_as_int(um) - kRoundMagicBits), vi = (uint32_t)(__float_as_int(vm) - kRoundMagicBits);
+                const uint32_t t = (uint32_t)k * out_n + vi * (uint32_t)out_w + ui;
                 const unsigned long long key = ((unsigned long long)__float_as_uint(Zv) << 32) | (id_offset + p);
-                atomicMin(zbuf + t, key);
+                red_min_u64_keep(zbuf + t, key, keep);
+                if (touched) touched[vi * (uint32_t)segs_per_row + (ui >> kSegShift)] = 1;
             }
         }
     }
@@ -72,7 +85,8 @@ template <int DECODER, bool BIT16, bool DEVVIEW>
 __global__ void __launch_bounds__(kSplatThreads)
     project_splat_kernel(const void *__restrict__ rgb, int width, int height, float dec_const, float depth_scale, SourceCam cam,
                          ViewPack views_param, const mdvt_view *__restrict__ view_dev, float near_plane, int out_w, int out_h,
-                         uint32_t id_offset, unsigned long long *__restrict__ zbuf, float *__restrict__ out_uvz) {
+                         uint32_t id_offset, unsigned long long *__restrict__ zbuf, float *__restrict__ out_uvz,
+                         uint8_t *__restrict__ touched, int segs_per_row) {
     const uint32_t out_n = (uint32_t)out_w * (uint32_t)out_h, n = (uint32_t)width * (uint32_t)height;
     const float u_max = (float)(out_w - 1), v_max = (float)(out_h - 1);
     const float rfx = rcp_refined(cam.fx), rfy = rcp_refined(cam.fy);
@@ -87,6 +101,7 @@ __global__ void __launch_bounds__(kSplatThreads)
         for (int k = 0; k < 4; ++k) l4[k] = __ldg(v4 + k);
     }
     const ViewPack &views = DEVVIEW ? local : views_param;
+    const uint64_t keep = l2_keep_policy();
     const int stride = gridDim.y;
     for (int row0 = blockIdx.y; row0 < height; row0 += stride * kSplatRows) {
         float z[kSplatRows];
@@ -102,7 +117,7 @@ __global__ void __launch_bounds__(kSplatThreads)
             if (row < height) {
                 const uint32_t p = (uint32_t)row * (uint32_t)width + (uint32_t)col;
                 splat_pixel(p, col, row, __fmul_rn(z[k], depth_scale), cam, rfx, rfy, views, near_plane, out_w, out_n, u_max, v_max, id_offset, n,
-                            zbuf, out_uvz);
+                            zbuf, out_uvz, keep, touched, segs_per_row);
             }
         }
     }
@@ -115,6 +130,7 @@ __global__ void __launch_bounds__(kThreads)
                         unsigned long long *__restrict__ zbuf) {
     const int64_t out_n = (int64_t)out_w * out_h;
     const float u_max = (float)(out_w - 1), v_max = (float)(out_h - 1);
+    const uint64_t keep = l2_keep_policy();
     for (int64_t p = blockIdx.x * (int64_t)kThreads + threadIdx.x; p < n; p += (int64_t)gridDim.x * kThreads) {
         const float X = __ldg(xyz + p * 3), Y = __ldg(xyz + p * 3 + 1), Z = __ldg(xyz + p * 3 + 2);
 #pragma unroll
@@ -129,7 +145,7 @@ __global__ void __launch_bounds__(kThreads)
                 if (Zv > near_plane && ur >= 0.0f && ur <= u_max && vr >= 0.0f && vr <= v_max) {
                     const int64_t t = (int64_t)(int)vr * out_w + (int)ur;
                     const unsigned long long key = ((unsigned long long)__float_as_uint(Zv) << 32) | (id_offset + (uint32_t)p);
-                    atomicMin(zbuf + (int64_t)k * out_n + t, key);
+                    red_min_u64_keep(zbuf + (int64_t)k * out_n + t, key, keep);
                 }
             }
         }
@@ -137,8 +153,9 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 __global__ void __launch_bounds__(kThreads) zbuf_clear_kernel(unsigned long long *__restrict__ zbuf, int64_t n) {
+    const uint64_t keep = l2_keep_policy();
     for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
-        zbuf[i] = MDVT_ZBUF_EMPTY;
+        st_u64_keep(zbuf + i, MDVT_ZBUF_EMPTY, keep);
 }
 
 __device__ __forceinline__ uint32_t gather_rgb(const uint8_t *__restrict__ colour, uint32_t id) {
@@ -154,30 +171,40 @@ template <int VEC>
 __global__ void __launch_bounds__(kThreads)
     resolve_kernel(unsigned long long *__restrict__ zbuf, const uint8_t *__restrict__ colour, int out_w, int out_h, uint32_t bg_rgb,
                    uint32_t fill_rgb, uint32_t flags, uint8_t *__restrict__ out_rgb, int64_t rgb_pitch, uint8_t *__restrict__ out_mask,
-                   int64_t mask_pitch, float *__restrict__ out_depth, int64_t depth_pitch, int32_t *__restrict__ out_ids) {
+                   int64_t mask_pitch, float *__restrict__ out_depth, int64_t depth_pitch, int32_t *__restrict__ out_ids,
+                   const uint8_t *__restrict__ touched, uint8_t *__restrict__ touched_clear, int segs_per_row) {
     constexpr int G = VEC == 4 ? 2 : 1;  // groups in flight per thread
     const uint32_t groups_per_row = (uint32_t)out_w / VEC;
     const uint32_t n_groups = groups_per_row * (uint32_t)out_h, stride = gridDim.x * kThreads;
     const bool collide = flags & MDVT_FLAG_BG_COLLIDE, reset = flags & MDVT_FLAG_RESET_ZBUF, mask_rgb = flags & MDVT_FLAG_MASK_RGB;
+    const uint64_t keep = l2_keep_policy();
     for (uint32_t g0 = blockIdx.x * kThreads + threadIdx.x; g0 < n_groups; g0 += stride * G) {
         unsigned long long key[G][4];
         uint32_t px[G][4], mk[G][4];
         int rows[G], cols[G];
-        bool on[G];
+        bool on[G], live[G];
 #pragma unroll
         for (int j = 0; j < G; ++j) {
             const uint32_t gidx = g0 + j * stride;
             on[j] = gidx < n_groups;
             rows[j] = (int)(gidx / groups_per_row);
             cols[j] = (int)(gidx - (uint32_t)rows[j] * groups_per_row) * VEC;
-            if (on[j]) {
+            live[j] = on[j];
+            if (on[j] && touched) {
+                const uint32_t seg = (uint32_t)rows[j] * (uint32_t)segs_per_row + ((uint32_t)cols[j] >> kSegShift);
+                live[j] = touched[seg] != 0;
+                if (((uint32_t)cols[j] & ((1u << kSegShift) - 1)) == 0) touched_clear[seg] = 0;  // the OTHER plane: next frame's
+#pragma unroll
+                for (int k = 0; k < 4; ++k) key[j][k] = MDVT_ZBUF_EMPTY;
+            }
+            if (live[j]) {
                 const uint32_t t0 = (uint32_t)rows[j] * (uint32_t)out_w + (uint32_t)cols[j];
                 if (VEC == 4) {
-                    const ulonglong2 a = reinterpret_cast<const ulonglong2 *>(zbuf + t0)[0];
-                    const ulonglong2 b = reinterpret_cast<const ulonglong2 *>(zbuf + t0)[1];
+                    const ulonglong2 a = ld_u64x2_keep(zbuf + t0, keep);
+                    const ulonglong2 b = ld_u64x2_keep(zbuf + t0 + 2, keep);
                     key[j][0] = a.x; key[j][1] = a.y; key[j][2] = b.x; key[j][3] = b.y;
                 } else {
-                    key[j][0] = zbuf[t0];
+                    key[j][0] = ld_u64_keep(zbuf + t0, keep);
                 }
             }
         }
@@ -209,22 +236,22 @@ __global__ void __launch_bounds__(kThreads)
                         (key[j][k] == MDVT_ZBUF_EMPTY) ? 0.0f : __uint_as_float((uint32_t)(key[j][k] >> 32));
                 if (out_ids) out_ids[t0 + k] = (key[j][k] == MDVT_ZBUF_EMPTY) ? -1 : (int32_t)(uint32_t)key[j][k];
             }
-            if (reset) {
+            if (reset && live[j]) {
                 if (VEC == 4) {
                     const ulonglong2 e = make_ulonglong2(MDVT_ZBUF_EMPTY, MDVT_ZBUF_EMPTY);
-                    reinterpret_cast<ulonglong2 *>(zbuf + t0)[0] = e;
-                    reinterpret_cast<ulonglong2 *>(zbuf + t0)[1] = e;
+                    st_u64x2_keep(zbuf + t0, e, keep);
+                    st_u64x2_keep(zbuf + t0 + 2, e, keep);
                 } else {
-                    zbuf[t0] = MDVT_ZBUF_EMPTY;
+                    st_u64_keep(zbuf + t0, MDVT_ZBUF_EMPTY, keep);
                 }
             }
             if (out_rgb) {
                 uint8_t *o = out_rgb + row * rgb_pitch + (int64_t)col0 * 3;
                 if (VEC == 4) {
                     uint32_t *ow = reinterpret_cast<uint32_t *>(o);
-                    ow[0] = px[j][0] | (px[j][1] << 24);
-                    ow[1] = (px[j][1] >> 8) | (px[j][2] << 16);
-                    ow[2] = (px[j][2] >> 16) | (px[j][3] << 8);
+                    __stcs(ow, px[j][0] | (px[j][1] << 24));
+                    __stcs(ow + 1, (px[j][1] >> 8) | (px[j][2] << 16));
+                    __stcs(ow + 2, (px[j][2] >> 16) | (px[j][3] << 8));
                 } else {
                     o[0] = (uint8_t)px[j][0]; o[1] = (uint8_t)(px[j][0] >> 8); o[2] = (uint8_t)(px[j][0] >> 16);
                 }
@@ -237,17 +264,17 @@ __global__ void __launch_bounds__(kThreads)
                     for (int k = 0; k < VEC; ++k) m[k] = mk[j][k] ? bg_rgb : 0u;
                     if (VEC == 4) {
                         uint32_t *ow = reinterpret_cast<uint32_t *>(o);
-                        ow[0] = m[0] | (m[1] << 24);
-                        ow[1] = (m[1] >> 8) | (m[2] << 16);
-                        ow[2] = (m[2] >> 16) | (m[3] << 8);
+                        __stcs(ow, m[0] | (m[1] << 24));
+                        __stcs(ow + 1, (m[1] >> 8) | (m[2] << 16));
+                        __stcs(ow + 2, (m[2] >> 16) | (m[3] << 8));
                     } else {
                         o[0] = (uint8_t)m[0]; o[1] = (uint8_t)(m[0] >> 8); o[2] = (uint8_t)(m[0] >> 16);
                     }
                 } else {
                     uint8_t *o = out_mask + row * mask_pitch + col0;
                     if (VEC == 4) {
-                        *reinterpret_cast<uint32_t *>(o) =
-                            (mk[j][0] * 0xFFu) | ((mk[j][1] * 0xFFu) << 8) | ((mk[j][2] * 0xFFu) << 16) | ((mk[j][3] * 0xFFu) << 24);
+                        __stcs(reinterpret_cast<uint32_t *>(o),
+                               (mk[j][0] * 0xFFu) | ((mk[j][1] * 0xFFu) << 8) | ((mk[j][2] * 0xFFu) << 16) | ((mk[j][3] * 0xFFu) << 24));
                     } else {
                         o[0] = mk[j][0] ? 255 : 0;
                     }
@@ -286,7 +313,8 @@ extern "C" int mdvt_zbuf_clear(uint64_t *zbuf, int64_t n_slots, void *stream) {
 }
 
 static int launch_project_splat(const void *depth_src, const mdvt_source *src, const ViewPack &pack, const mdvt_view *view_dev, float near_plane,
-                                int out_w, int out_h, uint32_t id_offset, unsigned long long *zb, float *out_uvz, cudaStream_t st);
+                                int out_w, int out_h, uint32_t id_offset, unsigned long long *zb, float *out_uvz, cudaStream_t st,
+                                uint8_t *touched = nullptr);
 
 static int pack_views(const mdvt_view *views_host, int n_views, ViewPack &pack) {
     MDVT_REQUIRE(n_views >= 1 && n_views <= kMaxViews, "n_views must be 1..%d", kMaxViews);
@@ -326,7 +354,9 @@ extern "C" int mdvt_splat_points(const float *xyz, int64_t n_points, const mdvt_
 
 static int launch_resolve(unsigned long long *zb, const uint8_t *colour_rgb, int out_w, int out_h, uint32_t bg_rgb, uint32_t fill_rgb,
                           uint32_t flags, uint8_t *out_rgb, int64_t rgb_pitch, uint8_t *out_mask, int64_t mask_pitch, float *out_depth,
-                          int64_t depth_pitch, int32_t *out_ids, cudaStream_t st) {
+                          int64_t depth_pitch, int32_t *out_ids, cudaStream_t st, const uint8_t *touched = nullptr,
+                          uint8_t *touched_clear = nullptr) {
+    const int segs_per_row = (out_w + (1 << kSegShift) - 1) >> kSegShift;
     const int mask_bpp = (flags & MDVT_FLAG_MASK_RGB) ? 3 : 1;
     MDVT_REQUIRE(!out_rgb || rgb_pitch >= (int64_t)out_w * 3, "rgb_pitch %lld too small", (long long)rgb_pitch);
     MDVT_REQUIRE(!out_mask || mask_pitch >= (int64_t)out_w * mask_bpp, "mask_pitch %lld too small", (long long)mask_pitch);
@@ -347,17 +377,22 @@ static int launch_resolve(unsigned long long *zb, const uint8_t *colour_rgb, int
     };
     if (vec4) {
         resolve_kernel<4><<<grid_of(((int64_t)out_w / 4 * out_h + 1) / 2, per_sm4), kThreads, 0, st>>>(
-            zb, colour_rgb, out_w, out_h, bg_rgb, fill_rgb, flags, out_rgb, rgb_pitch, out_mask, mask_pitch, out_depth, depth_pitch, out_ids);
+            zb, colour_rgb, out_w, out_h, bg_rgb, fill_rgb, flags, out_rgb, rgb_pitch, out_mask, mask_pitch, out_depth, depth_pitch, out_ids,
+            touched, touched_clear, segs_per_row);
     } else {
         resolve_kernel<1><<<grid_of((int64_t)out_w * out_h, per_sm1), kThreads, 0, st>>>(
-            zb, colour_rgb, out_w, out_h, bg_rgb, fill_rgb, flags, out_rgb, rgb_pitch, out_mask, mask_pitch, out_depth, depth_pitch, out_ids);
+            zb, colour_rgb, out_w, out_h, bg_rgb, fill_rgb, flags, out_rgb, rgb_pitch, out_mask, mask_pitch, out_depth, depth_pitch, out_ids,
+            touched, touched_clear, segs_per_row);
     }
     MDVT_CUDA_TRY(cudaGetLastError());
     return MDVT_OK;
 }
 
 static int launch_project_splat(const void *depth_src, const mdvt_source *src, const ViewPack &pack, const mdvt_view *view_dev, float near_plane,
-                                int out_w, int out_h, uint32_t id_offset, unsigned long long *zb, float *out_uvz, cudaStream_t st) {
+                                int out_w, int out_h, uint32_t id_offset, unsigned long long *zb, float *out_uvz, cudaStream_t st,
+                                uint8_t *touched) {
+    MDVT_REQUIRE(!touched || pack.n == 1, "touched flags need a single view");
+    const int segs_per_row = (out_w + (1 << kSegShift) - 1) >> kSegShift;
     MDVT_REQUIRE((int64_t)src->width * src->height < 0x7FFFFFFFll && (int64_t)out_w * out_h * pack.n < 0x7FFFFFFFll,
                  "source / target planes must hold fewer than 2^31 pixels");
     SourceCam cam{src->fx, src->fy, src->cx, src->cy, src->grid_sx, src->grid_sy};
@@ -372,7 +407,7 @@ static int launch_project_splat(const void *depth_src, const mdvt_source *src, c
         if (row_blocks < 1) row_blocks = 1;                                                                                          \
         if (row_blocks > src->height) row_blocks = src->height;                                                                      \
         kernel<<<dim3(col_blocks, row_blocks), kSplatThreads, 0, st>>>(depth_src, src->width, src->height, src->dec_const, src->depth_scale, cam, \
-                                                                     pack, view_dev, near_plane, out_w, out_h, id_offset, zb, out_uvz); \
+                                                                     pack, view_dev, near_plane, out_w, out_h, id_offset, zb, out_uvz, touched, segs_per_row); \
     } while (0)
     MDVT_DISPATCH_SOURCE(src->decoder, src->bit16, CALL);
 #undef CALL
@@ -426,36 +461,92 @@ extern "C" int mdvt_render_views(const void *depth_src, int64_t depth_frame_stri
 }
 
 // 3d_view_depthfile.py --render, whole chunk, no host synchronisation: centroid -> device look-at -> splat -> resolve.
+// The centroid (+ look-at) of frame f+1 does not depend on frame f, is latency-bound and small, so it runs on an
+// internal second stream underneath the splat / resolve of the frames before it (fork / join with events; at most
+// kAhead frames ahead so that its input is still in L2 when the splat reads it again).
+namespace {
+constexpr int kAhead = 2, kRing = 4;
+struct AuxStream {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, centroid_done[kRing] = {}, frame_done[kRing] = {};
+};
+int aux_for_current_device(AuxStream **out) {
+    static AuxStream aux;
+    int dev = 0;
+    MDVT_CUDA_TRY(cudaGetDevice(&dev));
+    if (aux.device != dev) {
+        MDVT_REQUIRE(aux.device == -1, "one process drives one GPU: the library was first used on device %d, now on %d", aux.device, dev);
+        MDVT_CUDA_TRY(cudaStreamCreateWithFlags(&aux.stream, cudaStreamNonBlocking));
+        MDVT_CUDA_TRY(cudaEventCreateWithFlags(&aux.fork, cudaEventDisableTiming));
+        for (int k = 0; k < kRing; ++k) {
+            MDVT_CUDA_TRY(cudaEventCreateWithFlags(&aux.centroid_done[k], cudaEventDisableTiming));
+            MDVT_CUDA_TRY(cudaEventCreateWithFlags(&aux.frame_done[k], cudaEventDisableTiming));
+        }
+        aux.device = dev;
+    }
+    *out = &aux;
+    return MDVT_OK;
+}
+}  // namespace
+
+extern "C" int64_t mdvt_touched_bytes(int out_w, int out_h) {
+    if (out_w <= 0 || out_h <= 0) return 0;
+    return 2 * (int64_t)out_h * ((out_w + (1 << kSegShift) - 1) >> kSegShift);
+}
+
 extern "C" int mdvt_novel_view_frames(const void *depth_src, int64_t depth_frame_stride, const uint8_t *colour_rgb, int64_t colour_frame_stride,
                                       int n_frames, const mdvt_source *centroid_src, const mdvt_source *src, const double *K_host,
                                       const double *poses_host, const mdvt_lookat *look, float near_plane, int out_w, int out_h,
-                                      uint64_t *zbuf, double *sums_dev, mdvt_view *views_dev, uint32_t bg_rgb, uint32_t fill_rgb,
-                                      uint32_t flags, const mdvt_plane_layout *rgb_out, const mdvt_plane_layout *mask_out, void *stream) {
+                                      uint64_t *zbuf, double *sums_dev, mdvt_view *views_dev, uint8_t *touched, uint32_t bg_rgb,
+                                      uint32_t fill_rgb, uint32_t flags, const mdvt_plane_layout *rgb_out, const mdvt_plane_layout *mask_out,
+                                      void *stream) {
     MDVT_REQUIRE(n_frames >= 0, "negative frame count");
     MDVT_REQUIRE(out_w > 0 && out_h > 0, "bad output size %dx%d", out_w, out_h);
     if (int rc = check_source(centroid_src)) return rc;
     if (int rc = check_source(src)) return rc;
     if (n_frames == 0) return MDVT_OK;
-    MDVT_REQUIRE(depth_src && colour_rgb && K_host && look && zbuf && sums_dev && views_dev && rgb_out && rgb_out->base, "NULL buffer");
+    MDVT_REQUIRE(depth_src && colour_rgb && K_host && look && zbuf && sums_dev && views_dev && touched && rgb_out && rgb_out->base,
+                 "NULL buffer");
     MDVT_REQUIRE(reinterpret_cast<uintptr_t>(views_dev) % 16 == 0, "views_dev must be 16-byte aligned");
     MDVT_REQUIRE(centroid_src->width == src->width && centroid_src->height == src->height, "the two source descriptions differ in size");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    AuxStream *aux = nullptr;
+    if (int rc = aux_for_current_device(&aux)) return rc;
     unsigned long long *zb = reinterpret_cast<unsigned long long *>(zbuf);
     ViewPack pack{};
     pack.n = 1;
     const int64_t sums_stride = 4 + MDVT_REDUCE_SCRATCH_DOUBLES;
+    const int64_t plane = mdvt_touched_bytes(out_w, out_h) / 2;
+    // the "last CTA finishes" counters of the centroid kernels (last scratch double of every frame) and both planes of
+    // touched flags: zeroed on the caller's stream before the fork
+    MDVT_CUDA_TRY(cudaMemset2DAsync(sums_dev + sums_stride - 1, sums_stride * sizeof(double), 0, sizeof(double), n_frames, st));
+    MDVT_CUDA_TRY(cudaMemsetAsync(touched, 0, 2 * plane, st));
+    MDVT_CUDA_TRY(cudaEventRecord(aux->fork, st));
+    MDVT_CUDA_TRY(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
+    auto centroid_of = [&](int f) -> int {
+        const uint8_t *dsrc = static_cast<const uint8_t *>(depth_src) + f * depth_frame_stride;
+        if (f >= kAhead) MDVT_CUDA_TRY(cudaStreamWaitEvent(aux->stream, aux->frame_done[(f - kAhead) % kRing], 0));
+        if (int rc = launch_centroid_lookat(dsrc, centroid_src, K_host, poses_host ? poses_host + 16 * (int64_t)f : nullptr, look,
+                                            sums_dev + f * sums_stride, views_dev + f, aux->stream))
+            return rc;
+        MDVT_CUDA_TRY(cudaEventRecord(aux->centroid_done[f % kRing], aux->stream));
+        return MDVT_OK;
+    };
     for (int f = 0; f < n_frames; ++f) {
         const uint8_t *dsrc = static_cast<const uint8_t *>(depth_src) + f * depth_frame_stride;
-        if (int rc = launch_centroid_lookat(dsrc, centroid_src, K_host, poses_host ? poses_host + 16 * (int64_t)f : nullptr, look,
-                                            sums_dev + f * sums_stride, views_dev + f, st))
-            return rc;
-        if (int rc = launch_project_splat(dsrc, src, pack, views_dev + f, near_plane, out_w, out_h, 0, zb, nullptr, st)) return rc;
+        if (int rc = centroid_of(f)) return rc;
+        MDVT_CUDA_TRY(cudaStreamWaitEvent(st, aux->centroid_done[f % kRing], 0));
+        uint8_t *cur = touched + (f & 1) * plane, *other = touched + ((f + 1) & 1) * plane;
+        if (int rc = launch_project_splat(dsrc, src, pack, views_dev + f, near_plane, out_w, out_h, 0, zb, nullptr, st, cur)) return rc;
         auto at = [&](const mdvt_plane_layout *L) -> uint8_t * {
             return (L && L->base) ? static_cast<uint8_t *>(L->base) + f * L->frame_stride : nullptr;
         };
         if (int rc = launch_resolve(zb, colour_rgb + f * colour_frame_stride, out_w, out_h, bg_rgb, fill_rgb, flags | MDVT_FLAG_RESET_ZBUF,
-                                    at(rgb_out), rgb_out->row_pitch, at(mask_out), mask_out ? mask_out->row_pitch : 0, nullptr, 0, nullptr, st))
+                                    at(rgb_out), rgb_out->row_pitch, at(mask_out), mask_out ? mask_out->row_pitch : 0, nullptr, 0, nullptr, st,
+                                    cur, other))
             return rc;
+        MDVT_CUDA_TRY(cudaEventRecord(aux->frame_done[f % kRing], st));
     }
     return MDVT_OK;
 }

@@ -104,11 +104,12 @@ class NovelViewRenderer:
         if self._sums is None or self._sums.shape[0] < n or self._sums.device != depth_rgb.device:
             self._sums = torch.empty((n, stride), dtype=torch.float64, device=depth_rgb.device)
             self._views = torch.empty((n, 16), dtype=torch.float32, device=depth_rgb.device)
+            self._touched = torch.empty(int(_lib.load().mdvt_touched_bytes(w, h)), dtype=torch.uint8, device=depth_rgb.device)
         src_c = ops.make_source(w, h, self.K, p.max_depth, "D1", True, 1.0, p.of_by_one)
         src = ops.make_source(w, h, self.K, p.max_depth, "D1", True, 1.0, False)
         poses = None if p.transformations is None else np.stack([self._pose(start_frame + k) for k in range(n)])
         ops.novel_view_frames(depth_rgb, colour, src_c, src, self.K, p.cam_pos, p.target, poses, self._zbuf, out_rgb, out_mask, p.bg_rgb,
-                              p.bg_rgb, 0, p.near, self._sums[:n], self._views[:n])
+                              p.bg_rgb, 0, p.near, self._sums[:n], self._views[:n], self._touched)
         self.last_sums, self.last_views = self._sums[:n], self._views[:n]
         return out_rgb, out_mask
 

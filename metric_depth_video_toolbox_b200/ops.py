@@ -342,7 +342,7 @@ def render_views(depth_src: torch.Tensor, colour: torch.Tensor, sources: Sequenc
 def novel_view_frames(depth_src: torch.Tensor, colour: torch.Tensor, centroid_source: _lib.Source, source: _lib.Source, K: np.ndarray,
                       cam_pos, target, poses, zbuf: torch.Tensor, out_rgb: torch.Tensor, out_mask: Optional[torch.Tensor] = None,
                       bg_rgb=(255, 255, 255), fill_rgb=(255, 255, 255), flags: int = 0, near: float = NEAR_PLANE,
-                      sums: Optional[torch.Tensor] = None, views_dev: Optional[torch.Tensor] = None):
+                      sums: Optional[torch.Tensor] = None, views_dev: Optional[torch.Tensor] = None, touched: Optional[torch.Tensor] = None):
     """`3d_view_depthfile.py --render`'s frame loop (:133-255) for a chunk in ONE library call and no host round trip:
     per frame vertex centroid -> look-at camera (on the device) -> splat -> resolve.  `cam_pos`: --x --y --z;
     `target`: three values or None per axis (None: centroid); `poses`: (n, 4, 4) float64 or None.
@@ -367,6 +367,11 @@ def novel_view_frames(depth_src: torch.Tensor, colour: torch.Tensor, centroid_so
         views_dev = torch.empty((n, 16), dtype=torch.float32, device=dev)
     if tuple(_need(sums, torch.float64, "sums").shape) != (n, stride) or tuple(_need(views_dev, torch.float32, "views_dev").shape) != (n, 16):
         raise ValueError("sums must be (n, 4 + scratch) float64 and views_dev (n, 16) float32")
+    need = int(_lib.load().mdvt_touched_bytes(w, h))
+    if touched is None:
+        touched = torch.empty(need, dtype=torch.uint8, device=dev)
+    if _need(touched, torch.uint8, "touched").numel() < need:
+        raise ValueError(f"touched must hold {need} bytes")
     K = np.asarray(K, dtype=np.float64)
     look = _lib.LookAt()
     cam32 = np.array(cam_pos).astype(np.float32)          # 3d_view_depthfile.py:240
@@ -386,7 +391,7 @@ def novel_view_frames(depth_src: torch.Tensor, colour: torch.Tensor, centroid_so
     mask_l = _plane_layout(None if out_mask is None else _need(out_mask, torch.uint8, "out_mask"), n, 1, h, w, mask_ch, "out_mask")
     _lib.check(_lib.load().mdvt_novel_view_frames(_ptr(depth_src), depth_src.stride(0) * depth_src.element_size(), _ptr(colour), colour.stride(0),
                                                   n, C.byref(centroid_source), C.byref(source), _k4(K), pose_arr, C.byref(look),
-                                                  float(np.float32(near)), w, h, _ptr(zbuf), _ptr(sums), _ptr(views_dev), pack_rgb(bg_rgb),
+                                                  float(np.float32(near)), w, h, _ptr(zbuf), _ptr(sums), _ptr(views_dev), _ptr(touched), pack_rgb(bg_rgb),
                                                   pack_rgb(fill_rgb), flags, C.byref(rgb_l), None if mask_l is None else C.byref(mask_l),
                                                   _stream()))
     return out_rgb, out_mask, sums, views_dev
