@@ -14,7 +14,7 @@ constexpr int kMaxViews = 4;
 constexpr int kSplatThreads = 128;  // divides 640 / 1280 / 1920 / 3840: no idle tail block per row
 constexpr float kRoundMagic = 12582912.0f;     // 1.5 * 2^23
 constexpr int kRoundMagicBits = 0x4B400000;
-// "Touched" flags: one byte per 64-pixel segment of a target row, set by the splat next to its RED (single view only).
+// "Touched" flags: one byte per 64 consecutive slots of the z-buffer plane, set by the splat next to its RED (single view only).
 // The resolve skips the z-buffer load AND the re-arm store of untouched segments: with the 62 % holes of the config-3
 // camera, z-buffer traffic drops from 2 x 66 MB to 2 x 25 MB per 4K frame and the touched part stays L2-resident.
 constexpr int kSegShift = 6;
@@ -64,7 +64,7 @@ __device__ __forceinline__ void splat_pixel(uint32_t p, int col, int row, float 
                 const uint32_t t = (uint32_t)k * out_n + vi * (uint32_t)out_w + ui;
                 const unsigned long long key = ((unsigned long long)__float_as_uint(Zv) << 32) | (id_offset + p);
                 red_min_u64_keep(zbuf + t, key, keep);
-                if (touched) touched[vi * (uint32_t)segs_per_row + (ui >> kSegShift)] = 1;
+                if (touched) touched[t >> kSegShift] = 1;  // flat 64-slot segments of the plane (single view: t < out_n)
             }
         }
     }
@@ -191,9 +191,9 @@ __global__ void __launch_bounds__(kThreads)
             cols[j] = (int)(gidx - (uint32_t)rows[j] * groups_per_row) * VEC;
             live[j] = on[j];
             if (on[j] && touched) {
-                const uint32_t seg = (uint32_t)rows[j] * (uint32_t)segs_per_row + ((uint32_t)cols[j] >> kSegShift);
+                const uint32_t tt = (uint32_t)rows[j] * (uint32_t)out_w + (uint32_t)cols[j], seg = tt >> kSegShift;
                 live[j] = touched[seg] != 0;
-                if (((uint32_t)cols[j] & ((1u << kSegShift) - 1)) == 0) touched_clear[seg] = 0;  // the OTHER plane: next frame's
+                if ((tt & ((1u << kSegShift) - 1)) == 0) touched_clear[seg] = 0;  // the OTHER plane: next frame's
 #pragma unroll
                 for (int k = 0; k < 4; ++k) key[j][k] = MDVT_ZBUF_EMPTY;
             }
@@ -292,6 +292,108 @@ static int resident_ctas(K kernel, int threads) {
     return ctas;
 }
 
+// K3, row form (out_w % 4 == 0, aligned planes, no id plane): blockIdx.x tiles the 4-pixel groups of a row, blockIdx.y
+// strides over the rows two at a time (both rows' z-buffer loads first, then both rows' gathers), so there is no
+// division, and a warp whose 128 target pixels lie in untouched segments takes a ~25-instruction path that only
+// writes fill colour and mask (ncu v4: the one-kernel-fits-all resolve spent 56 instructions per pixel).
+constexpr int kRowResolveThreads = 160;  // 640 px per CTA row chunk: divides 640 / 1280 / 1920 / 3840
+
+template <bool DEPTH>
+__global__ void __launch_bounds__(kRowResolveThreads)
+    resolve_rows_kernel(unsigned long long *__restrict__ zbuf, const uint8_t *__restrict__ colour, int out_w, int out_h, uint32_t bg_rgb,
+                        uint32_t fill_rgb, uint32_t flags, uint8_t *__restrict__ out_rgb, int64_t rgb_pitch, uint8_t *__restrict__ out_mask,
+                        int64_t mask_pitch, float *__restrict__ out_depth, int64_t depth_pitch, const uint8_t *__restrict__ touched,
+                        uint8_t *__restrict__ touched_clear) {
+    const int g = blockIdx.x * kRowResolveThreads + threadIdx.x;
+    if (g >= out_w / 4) return;
+    const int col0 = g * 4;
+    const bool collide = flags & MDVT_FLAG_BG_COLLIDE, reset = flags & MDVT_FLAG_RESET_ZBUF, mask_rgb = flags & MDVT_FLAG_MASK_RGB;
+    const uint64_t keep = l2_keep_policy();
+    const int stride = gridDim.y;
+    for (int row0 = blockIdx.y; row0 < out_h; row0 += 2 * stride) {
+        uint32_t hi[2][4], id[2][4];
+        bool on[2], live[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int row = row0 + j * stride;
+            on[j] = row < out_h;
+            live[j] = on[j];
+            if (on[j]) {
+                const uint32_t t0 = (uint32_t)row * (uint32_t)out_w + (uint32_t)col0;
+                if (touched) {
+                    live[j] = touched[t0 >> kSegShift] != 0;
+                    if ((t0 & ((1u << kSegShift) - 1)) == 0) touched_clear[t0 >> kSegShift] = 0;  // the OTHER plane: next frame's
+                }
+                if (live[j]) {
+                    const ulonglong2 a = ld_u64x2_keep(zbuf + t0, keep);
+                    const ulonglong2 b = ld_u64x2_keep(zbuf + t0 + 2, keep);
+                    hi[j][0] = (uint32_t)(a.x >> 32); id[j][0] = (uint32_t)a.x;
+                    hi[j][1] = (uint32_t)(a.y >> 32); id[j][1] = (uint32_t)a.y;
+                    hi[j][2] = (uint32_t)(b.x >> 32); id[j][2] = (uint32_t)b.x;
+                    hi[j][3] = (uint32_t)(b.y >> 32); id[j][3] = (uint32_t)b.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (!on[j]) continue;
+            const int row = row0 + j * stride;
+            uint32_t px[4] = {fill_rgb, fill_rgb, fill_rgb, fill_rgb};
+            uint32_t holes = 0xF;  // bit k: pixel k is a hole
+            if (live[j]) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (hi[j][k] != 0xFFFFFFFFu) {  // a filled slot holds the bits of a positive finite float there
+                        const uint32_t c = gather_rgb(colour, id[j][k]);
+                        if (!(collide && c == bg_rgb)) {
+                            px[k] = c;
+                            holes &= ~(1u << k);
+                        }
+                    }
+                }
+                if (reset) {
+                    const ulonglong2 e = make_ulonglong2(MDVT_ZBUF_EMPTY, MDVT_ZBUF_EMPTY);
+                    unsigned long long *z = zbuf + (uint32_t)row * (uint32_t)out_w + (uint32_t)col0;
+                    st_u64x2_keep(z, e, keep);
+                    st_u64x2_keep(z + 2, e, keep);
+                }
+            }
+            if (DEPTH) {
+                float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live[j]) {
+                    d.x = hi[j][0] == 0xFFFFFFFFu ? 0.0f : __uint_as_float(hi[j][0]);
+                    d.y = hi[j][1] == 0xFFFFFFFFu ? 0.0f : __uint_as_float(hi[j][1]);
+                    d.z = hi[j][2] == 0xFFFFFFFFu ? 0.0f : __uint_as_float(hi[j][2]);
+                    d.w = hi[j][3] == 0xFFFFFFFFu ? 0.0f : __uint_as_float(hi[j][3]);
+                }
+                float *o = out_depth + row * depth_pitch + col0;
+                o[0] = d.x; o[1] = d.y; o[2] = d.z; o[3] = d.w;
+            }
+            if (out_rgb) {
+                uint32_t *ow = reinterpret_cast<uint32_t *>(out_rgb + row * rgb_pitch + (int64_t)col0 * 3);
+                __stcs(ow, px[0] | (px[1] << 24));
+                __stcs(ow + 1, (px[1] >> 8) | (px[2] << 16));
+                __stcs(ow + 2, (px[2] >> 16) | (px[3] << 8));
+            }
+            if (out_mask) {
+                if (mask_rgb) {
+                    uint32_t m[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) m[k] = (holes >> k) & 1 ? bg_rgb : 0u;
+                    uint32_t *ow = reinterpret_cast<uint32_t *>(out_mask + row * mask_pitch + (int64_t)col0 * 3);
+                    __stcs(ow, m[0] | (m[1] << 24));
+                    __stcs(ow + 1, (m[1] >> 8) | (m[2] << 16));
+                    __stcs(ow + 2, (m[2] >> 16) | (m[3] << 8));
+                } else {
+                    // bits 0..3 -> bytes 0x00 / 0xFF
+                    const uint32_t spread = ((holes & 1) | ((holes & 2) << 7) | ((holes & 4) << 14) | ((holes & 8) << 21)) * 0xFFu;
+                    __stcs(reinterpret_cast<uint32_t *>(out_mask + row * mask_pitch + col0), spread);
+                }
+            }
+        }
+    }
+}
+
 static int grid_for(int64_t work_items) {
     const int64_t blocks = (work_items + kThreads - 1) / kThreads;
     const int64_t cap = (int64_t)sm_count() * 8;
@@ -375,7 +477,23 @@ static int launch_resolve(unsigned long long *zb, const uint8_t *colour_rgb, int
         const int64_t blocks = (items + kThreads - 1) / kThreads, cap = (int64_t)sm_count() * per_sm;
         return (int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
     };
-    if (vec4) {
+    if (vec4 && !out_ids && (!out_depth || (reinterpret_cast<uintptr_t>(out_depth) % 4 == 0))) {
+        static int per_sm_rows[2] = {0, 0};
+        int &per_sm = per_sm_rows[out_depth ? 1 : 0];
+        if (!per_sm)
+            per_sm = out_depth ? resident_ctas(resolve_rows_kernel<true>, kRowResolveThreads) : resident_ctas(resolve_rows_kernel<false>, kRowResolveThreads);
+        const int col_blocks = (out_w / 4 + kRowResolveThreads - 1) / kRowResolveThreads;
+        int row_blocks = sm_count() * per_sm / col_blocks;
+        if (row_blocks < 1) row_blocks = 1;
+        if (row_blocks > (out_h + 1) / 2) row_blocks = (out_h + 1) / 2;
+        const dim3 grid(col_blocks, row_blocks);
+        if (out_depth)
+            resolve_rows_kernel<true><<<grid, kRowResolveThreads, 0, st>>>(zb, colour_rgb, out_w, out_h, bg_rgb, fill_rgb, flags, out_rgb, rgb_pitch,
+                                                                          out_mask, mask_pitch, out_depth, depth_pitch, touched, touched_clear);
+        else
+            resolve_rows_kernel<false><<<grid, kRowResolveThreads, 0, st>>>(zb, colour_rgb, out_w, out_h, bg_rgb, fill_rgb, flags, out_rgb, rgb_pitch,
+                                                                           out_mask, mask_pitch, out_depth, depth_pitch, touched, touched_clear);
+    } else if (vec4) {
         resolve_kernel<4><<<grid_of(((int64_t)out_w / 4 * out_h + 1) / 2, per_sm4), kThreads, 0, st>>>(
             zb, colour_rgb, out_w, out_h, bg_rgb, fill_rgb, flags, out_rgb, rgb_pitch, out_mask, mask_pitch, out_depth, depth_pitch, out_ids,
             touched, touched_clear, segs_per_row);
@@ -492,7 +610,7 @@ int aux_for_current_device(AuxStream **out) {
 
 extern "C" int64_t mdvt_touched_bytes(int out_w, int out_h) {
     if (out_w <= 0 || out_h <= 0) return 0;
-    return 2 * (int64_t)out_h * ((out_w + (1 << kSegShift) - 1) >> kSegShift);
+    return 2 * (((int64_t)out_h * out_w + (1 << kSegShift) - 1) >> kSegShift);
 }
 
 extern "C" int mdvt_novel_view_frames(const void *depth_src, int64_t depth_frame_stride, const uint8_t *colour_rgb, int64_t colour_frame_stride,
