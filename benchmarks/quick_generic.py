@@ -41,9 +41,19 @@ if which in ("stereo", "both"):
     px = w * h * n
     print(f"generic stereo (convergence) 1080p: {ms / n * 1e3:.1f} us/frame  {n / ms * 1e3:.0f} frames/s  {px * 14 / ms / 1e6:.0f} GB/s algorithmic "
           f"({px * 14 / ms / 1e6 / 6454:.3f} of HBM peak)  holes {float((mask == 255).float().mean()):.4f}")
+if which in ("stereo", "both"):
+    w, h, n = 1920, 1080, 32
+    d, c = clip(w, h, n)
+    rr = StereoRerenderer(StereoParams(w, h, xfov=60.0, convergence_depths=[5.0] * n, infill_mask=True, force_generic=True), "cuda")
+    sbs = torch.empty((n, h, 2 * w, 3), dtype=torch.uint8, device="cuda")
+    mask = torch.empty((n, h, 2 * w), dtype=torch.uint8, device="cuda")
+    ms = timed(lambda: rr.render_device(d, c, 0, sbs, mask), 3)
+    px = w * h * n
+    print(f"generic stereo (K1+K2 two views, 2 x K3; what a pose file selects) 1080p: {ms / n * 1e3:.1f} us/frame  {n / ms * 1e3:.0f} frames/s  "
+          f"{px * 14 / ms / 1e6:.0f} GB/s algorithmic ({px * 14 / ms / 1e6 / 6454:.3f} of HBM peak)")
 if which in ("novel", "both"):
-    w, h, n = 3840, 2160, 8
-    d, c = clip(w, h, n, 2)
+    w, h, n = 3840, 2160, 24
+    d, c = clip(w, h, n, 4)
     nv = NovelViewRenderer(NovelViewParams(w, h, 60, None, 100), "cuda")
     rgb = torch.empty((n, h, w, 3), dtype=torch.uint8, device="cuda")
     mask = torch.empty((n, h, w), dtype=torch.uint8, device="cuda")

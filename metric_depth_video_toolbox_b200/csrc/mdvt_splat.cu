@@ -27,13 +27,13 @@ struct ViewPack {
 // One source pixel through every view.  Divisions are correctly rounded (== the float32 model's `/`): the
 // reciprocals of fx, fy are refined once per thread, the one of Zv once per view and shared by u and v.
 // All index arithmetic is 32-bit (the entry point checks that source and target planes have < 2^31 pixels).
-__device__ __forceinline__ void splat_pixel(uint32_t p, int col, int row, float z, const SourceCam &cam, float rfx, float rfy,
-                                            const ViewPack &views, float near_plane, int out_w, uint32_t out_n, float u_max, float v_max,
+template <bool UVZ, bool TOUCHED>
+__device__ __forceinline__ void splat_pixel(uint32_t p, float xc, int row, float z, const SourceCam &cam, float rfx, float rfy,
+                                            const ViewPack &views, float near_plane, int out_w, uint32_t out_n, uint32_t out_h,
                                             uint32_t id_offset, uint32_t n, unsigned long long *__restrict__ zbuf, float *__restrict__ out_uvz,
-                                            uint64_t keep, uint8_t *__restrict__ touched, int segs_per_row) {
-    const float xg = __fmul_rn(__int2float_rn(col), cam.sx);
+                                            uint64_t keep, uint8_t *__restrict__ touched) {
     const float yg = __fmul_rn(__int2float_rn(row), cam.sy);
-    const float X = div_rn_by(__fmul_rn(__fsub_rn(xg, cam.cx), z), cam.fx, rfx);
+    const float X = div_rn_by(__fmul_rn(xc, z), cam.fx, rfx);  // xc = fl(fl(col * sx) - cx), hoisted by the caller
     const float Y = div_rn_by(__fmul_rn(__fsub_rn(yg, cam.cy), z), cam.fy, rfy);
 #pragma unroll
     for (int k = 0; k < kMaxViews; ++k) {
@@ -43,7 +43,7 @@ __device__ __forceinline__ void splat_pixel(uint32_t p, int col, int row, float 
             const float Yv = affine_row(vw.M + 4, X, Y, z);
             const float Zv = affine_row(vw.M + 8, X, Y, z);
             float u, v;
-            if (out_uvz) {  // parity output: IEEE division also where Zv is zero / negative / tiny
+            if (UVZ) {  // parity output: IEEE division also where Zv is zero / negative / tiny
                 u = __fadd_rn(__fdiv_rn(__fmul_rn(vw.fx, Xv), Zv), vw.cx);
                 v = __fadd_rn(__fdiv_rn(__fmul_rn(vw.fy, Yv), Zv), vw.cy);
                 float *o = out_uvz + ((int64_t)k * n + p) * 3;
@@ -53,18 +53,18 @@ __device__ __forceinline__ void splat_pixel(uint32_t p, int col, int row, float 
                 u = __fadd_rn(div_rn_by(__fmul_rn(vw.fx, Xv), Zv, rz), vw.cx);
                 v = __fadd_rn(div_rn_by(__fmul_rn(vw.fy, Yv), Zv, rz), vw.cy);
             }
-            // round half to even, like np.round, without FRND / F2I (quarter-rate conversion pipe): adding 1.5 * 2^23 rounds
-            // to an integer (the sum's ulp is 1) for |u| < 2^22 and leaves the integer in the mantissa; larger |u| stay far
-            // outside [0, u_max] and NaN stays NaN, so the bounds test still rejects them.
-            const float um = __fadd_rn(u, kRoundMagic), vm = __fadd_rn(v, kRoundMagic);
-            const float ur = __fsub_rn(um, kRoundMagic), vr = __fsub_rn(vm, kRoundMagic);
-            // comparisons are false for NaN, so non-finite projections are culled too
-            if (Zv > near_plane && ur >= 0.0f && ur <= u_max && vr >= 0.0f && vr <= v_max) {
-                const uint32_t ui = (uint32_t)(__float_as_int(um) - kRoundMagicBits), vi = (uint32_t)(__float_as_int(vm) - kRoundMagicBits);
+            // Round half to even, like np.round, and test the bounds without FRND / F2I and with two compares: adding
+            // 1.5 * 2^23 rounds to an integer (the sum's ulp is 1) for |u| < 2^22 and leaves rint(u) in the mantissa, so
+            // bits(sum) - bits(1.5 * 2^23) is rint(u) as a signed integer and ONE unsigned compare tests 0 <= rint(u) < W.
+            // |u| >= 2^22, +-inf and NaN give differences >= 2^22 or "negative" ones, i.e. huge unsigned values: rejected
+            // (out_w, out_h < 2^22 is checked at the entry points).  Zv > near is false for NaN.
+            const uint32_t ui = (uint32_t)(__float_as_int(__fadd_rn(u, kRoundMagic)) - kRoundMagicBits);
+            const uint32_t vi = (uint32_t)(__float_as_int(__fadd_rn(v, kRoundMagic)) - kRoundMagicBits);
+            if (Zv > near_plane && ui < (uint32_t)out_w && vi < out_h) {
                 const uint32_t t = (uint32_t)k * out_n + vi * (uint32_t)out_w + ui;
                 const unsigned long long key = ((unsigned long long)__float_as_uint(Zv) << 32) | (id_offset + p);
                 red_min_u64_keep(zbuf + t, key, keep);
-                if (touched) touched[t >> kSegShift] = 1;  // flat 64-slot segments of the plane (single view: t < out_n)
+                if (TOUCHED) touched[t >> kSegShift] = 1;  // flat 64-slot segments of the plane (single view: t < out_n)
             }
         }
     }
@@ -86,9 +86,8 @@ __global__ void __launch_bounds__(kSplatThreads)
     project_splat_kernel(const void *__restrict__ rgb, int width, int height, float dec_const, float depth_scale, SourceCam cam,
                          ViewPack views_param, const mdvt_view *__restrict__ view_dev, float near_plane, int out_w, int out_h,
                          uint32_t id_offset, unsigned long long *__restrict__ zbuf, float *__restrict__ out_uvz,
-                         uint8_t *__restrict__ touched, int segs_per_row) {
+                         uint8_t *__restrict__ touched) {
     const uint32_t out_n = (uint32_t)out_w * (uint32_t)out_h, n = (uint32_t)width * (uint32_t)height;
-    const float u_max = (float)(out_w - 1), v_max = (float)(out_h - 1);
     const float rfx = rcp_refined(cam.fx), rfy = rcp_refined(cam.fy);
     const int col = blockIdx.x * kSplatThreads + threadIdx.x;
     if (col >= width) return;
@@ -101,6 +100,7 @@ __global__ void __launch_bounds__(kSplatThreads)
         for (int k = 0; k < 4; ++k) l4[k] = __ldg(v4 + k);
     }
     const ViewPack &views = DEVVIEW ? local : views_param;
+    const float xc = __fsub_rn(__fmul_rn(__int2float_rn(col), cam.sx), cam.cx);
     const uint64_t keep = l2_keep_policy();
     const int stride = gridDim.y;
     for (int row0 = blockIdx.y; row0 < height; row0 += stride * kSplatRows) {
@@ -116,8 +116,17 @@ __global__ void __launch_bounds__(kSplatThreads)
             const int row = row0 + k * stride;
             if (row < height) {
                 const uint32_t p = (uint32_t)row * (uint32_t)width + (uint32_t)col;
-                splat_pixel(p, col, row, __fmul_rn(z[k], depth_scale), cam, rfx, rfy, views, near_plane, out_w, out_n, u_max, v_max, id_offset, n,
-                            zbuf, out_uvz, keep, touched, segs_per_row);
+                const float zs = __fmul_rn(z[k], depth_scale);
+                // DEVVIEW: the novel-view frame loop -- touched flags always on, never a (u, v, z) dump
+                if (DEVVIEW)
+                    splat_pixel<false, true>(p, xc, row, zs, cam, rfx, rfy, views, near_plane, out_w, out_n, (uint32_t)out_h, id_offset, n, zbuf,
+                                             nullptr, keep, touched);
+                else if (out_uvz)
+                    splat_pixel<true, false>(p, xc, row, zs, cam, rfx, rfy, views, near_plane, out_w, out_n, (uint32_t)out_h, id_offset, n, zbuf,
+                                             out_uvz, keep, nullptr);
+                else
+                    splat_pixel<false, false>(p, xc, row, zs, cam, rfx, rfy, views, near_plane, out_w, out_n, (uint32_t)out_h, id_offset, n, zbuf,
+                                              nullptr, keep, nullptr);
             }
         }
     }
@@ -172,7 +181,7 @@ __global__ void __launch_bounds__(kThreads)
     resolve_kernel(unsigned long long *__restrict__ zbuf, const uint8_t *__restrict__ colour, int out_w, int out_h, uint32_t bg_rgb,
                    uint32_t fill_rgb, uint32_t flags, uint8_t *__restrict__ out_rgb, int64_t rgb_pitch, uint8_t *__restrict__ out_mask,
                    int64_t mask_pitch, float *__restrict__ out_depth, int64_t depth_pitch, int32_t *__restrict__ out_ids,
-                   const uint8_t *__restrict__ touched, uint8_t *__restrict__ touched_clear, int segs_per_row) {
+                   const uint8_t *__restrict__ touched, uint8_t *__restrict__ touched_clear) {
     constexpr int G = VEC == 4 ? 2 : 1;  // groups in flight per thread
     const uint32_t groups_per_row = (uint32_t)out_w / VEC;
     const uint32_t n_groups = groups_per_row * (uint32_t)out_h, stride = gridDim.x * kThreads;
@@ -313,26 +322,35 @@ __global__ void __launch_bounds__(kRowResolveThreads)
     for (int row0 = blockIdx.y; row0 < out_h; row0 += 2 * stride) {
         uint32_t hi[2][4], id[2][4];
         bool on[2], live[2];
+        uint32_t t0[2];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < 2; ++j) {  // both rows' flags first, then both rows' keys
             const int row = row0 + j * stride;
             on[j] = row < out_h;
+            t0[j] = (uint32_t)row * (uint32_t)out_w + (uint32_t)col0;
             live[j] = on[j];
-            if (on[j]) {
-                const uint32_t t0 = (uint32_t)row * (uint32_t)out_w + (uint32_t)col0;
-                if (touched) {
-                    live[j] = touched[t0 >> kSegShift] != 0;
-                    if ((t0 & ((1u << kSegShift) - 1)) == 0) touched_clear[t0 >> kSegShift] = 0;  // the OTHER plane: next frame's
-                }
-                if (live[j]) {
-                    const ulonglong2 a = ld_u64x2_keep(zbuf + t0, keep);
-                    const ulonglong2 b = ld_u64x2_keep(zbuf + t0 + 2, keep);
-                    hi[j][0] = (uint32_t)(a.x >> 32); id[j][0] = (uint32_t)a.x;
-                    hi[j][1] = (uint32_t)(a.y >> 32); id[j][1] = (uint32_t)a.y;
-                    hi[j][2] = (uint32_t)(b.x >> 32); id[j][2] = (uint32_t)b.x;
-                    hi[j][3] = (uint32_t)(b.y >> 32); id[j][3] = (uint32_t)b.y;
-                }
+            if (on[j] && touched) live[j] = touched[t0[j] >> kSegShift] != 0;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (on[j] && touched && (t0[j] & ((1u << kSegShift) - 1)) == 0) touched_clear[t0[j] >> kSegShift] = 0;  // the OTHER plane: next frame's
+            if (live[j]) {
+                const ulonglong2 a = ld_u64x2_keep(zbuf + t0[j], keep);
+                const ulonglong2 b = ld_u64x2_keep(zbuf + t0[j] + 2, keep);
+                hi[j][0] = (uint32_t)(a.x >> 32); id[j][0] = (uint32_t)a.x;
+                hi[j][1] = (uint32_t)(a.y >> 32); id[j][1] = (uint32_t)a.y;
+                hi[j][2] = (uint32_t)(b.x >> 32); id[j][2] = (uint32_t)b.x;
+                hi[j][3] = (uint32_t)(b.y >> 32); id[j][3] = (uint32_t)b.y;
             }
+        }
+        // all colour gathers of both rows issued back to back, branch-free (an empty slot reads source pixel 0 and is
+        // discarded): one memory latency per iteration instead of up to eight dependent ones
+        uint32_t cg[2][4];
+        if (live[0] || live[1]) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) cg[j][k] = gather_rgb(colour, (live[j] && hi[j][k] != 0xFFFFFFFFu) ? id[j][k] : 0u);
         }
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -343,12 +361,9 @@ __global__ void __launch_bounds__(kRowResolveThreads)
             if (live[j]) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if (hi[j][k] != 0xFFFFFFFFu) {  // a filled slot holds the bits of a positive finite float there
-                        const uint32_t c = gather_rgb(colour, id[j][k]);
-                        if (!(collide && c == bg_rgb)) {
-                            px[k] = c;
-                            holes &= ~(1u << k);
-                        }
+                    if (hi[j][k] != 0xFFFFFFFFu && !(collide && cg[j][k] == bg_rgb)) {  // a filled slot holds positive finite float bits there
+                        px[k] = cg[j][k];
+                        holes &= ~(1u << k);
                     }
                 }
                 if (reset) {
@@ -458,7 +473,6 @@ static int launch_resolve(unsigned long long *zb, const uint8_t *colour_rgb, int
                           uint32_t flags, uint8_t *out_rgb, int64_t rgb_pitch, uint8_t *out_mask, int64_t mask_pitch, float *out_depth,
                           int64_t depth_pitch, int32_t *out_ids, cudaStream_t st, const uint8_t *touched = nullptr,
                           uint8_t *touched_clear = nullptr) {
-    const int segs_per_row = (out_w + (1 << kSegShift) - 1) >> kSegShift;
     const int mask_bpp = (flags & MDVT_FLAG_MASK_RGB) ? 3 : 1;
     MDVT_REQUIRE(!out_rgb || rgb_pitch >= (int64_t)out_w * 3, "rgb_pitch %lld too small", (long long)rgb_pitch);
     MDVT_REQUIRE(!out_mask || mask_pitch >= (int64_t)out_w * mask_bpp, "mask_pitch %lld too small", (long long)mask_pitch);
@@ -496,11 +510,11 @@ static int launch_resolve(unsigned long long *zb, const uint8_t *colour_rgb, int
     } else if (vec4) {
         resolve_kernel<4><<<grid_of(((int64_t)out_w / 4 * out_h + 1) / 2, per_sm4), kThreads, 0, st>>>(
             zb, colour_rgb, out_w, out_h, bg_rgb, fill_rgb, flags, out_rgb, rgb_pitch, out_mask, mask_pitch, out_depth, depth_pitch, out_ids,
-            touched, touched_clear, segs_per_row);
+            touched, touched_clear);
     } else {
         resolve_kernel<1><<<grid_of((int64_t)out_w * out_h, per_sm1), kThreads, 0, st>>>(
             zb, colour_rgb, out_w, out_h, bg_rgb, fill_rgb, flags, out_rgb, rgb_pitch, out_mask, mask_pitch, out_depth, depth_pitch, out_ids,
-            touched, touched_clear, segs_per_row);
+            touched, touched_clear);
     }
     MDVT_CUDA_TRY(cudaGetLastError());
     return MDVT_OK;
@@ -509,8 +523,8 @@ static int launch_resolve(unsigned long long *zb, const uint8_t *colour_rgb, int
 static int launch_project_splat(const void *depth_src, const mdvt_source *src, const ViewPack &pack, const mdvt_view *view_dev, float near_plane,
                                 int out_w, int out_h, uint32_t id_offset, unsigned long long *zb, float *out_uvz, cudaStream_t st,
                                 uint8_t *touched) {
-    MDVT_REQUIRE(!touched || pack.n == 1, "touched flags need a single view");
-    const int segs_per_row = (out_w + (1 << kSegShift) - 1) >> kSegShift;
+    MDVT_REQUIRE((touched != nullptr) == (view_dev != nullptr), "touched flags go with the device-resident single view");
+    MDVT_REQUIRE(out_w < (1 << 22) && out_h < (1 << 22), "target sides must be below 2^22 pixels");
     MDVT_REQUIRE((int64_t)src->width * src->height < 0x7FFFFFFFll && (int64_t)out_w * out_h * pack.n < 0x7FFFFFFFll,
                  "source / target planes must hold fewer than 2^31 pixels");
     SourceCam cam{src->fx, src->fy, src->cx, src->cy, src->grid_sx, src->grid_sy};
@@ -525,7 +539,7 @@ static int launch_project_splat(const void *depth_src, const mdvt_source *src, c
         if (row_blocks < 1) row_blocks = 1;                                                                                          \
         if (row_blocks > src->height) row_blocks = src->height;                                                                      \
         kernel<<<dim3(col_blocks, row_blocks), kSplatThreads, 0, st>>>(depth_src, src->width, src->height, src->dec_const, src->depth_scale, cam, \
-                                                                     pack, view_dev, near_plane, out_w, out_h, id_offset, zb, out_uvz, touched, segs_per_row); \
+                                                                     pack, view_dev, near_plane, out_w, out_h, id_offset, zb, out_uvz, touched); \
     } while (0)
     MDVT_DISPATCH_SOURCE(src->decoder, src->bit16, CALL);
 #undef CALL
