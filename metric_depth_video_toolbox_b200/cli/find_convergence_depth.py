@@ -22,12 +22,12 @@ def build_parser() -> argparse.ArgumentParser:
     return p
 
 
-def convergence_depths(depth_video: str, mask_video: Optional[str], max_depth, device, chunk: int = 8) -> List[float]:
+def convergence_depths(depth_video: str, mask_video: Optional[str], max_depth, device, chunk: int = 12) -> List[float]:
     """find_convergence_depth.py:46-80.  A mask video shorter than the depth video ends the analysis there
     (ChunkReader reads in lock step), frames without any selected pixel give NaN."""
     out: List[float] = []
     sums = torch.empty((chunk, 4 + _lib.REDUCE_SCRATCH_DOUBLES), dtype=torch.float64, device=device)
-    for n, (depth_rgb, mask) in video_io.ChunkReader([depth_video, mask_video], chunk=chunk, grey=[False, True]):
+    for n, (depth_rgb, mask) in video_io.ChunkReader([depth_video, mask_video], chunk=chunk, grey=[False, True], decoders=video_io.default_decoders()):
         d = depth_rgb.to(device, non_blocking=True)
         m = None if mask is None else mask.to(device, non_blocking=True)
         for k in range(n):

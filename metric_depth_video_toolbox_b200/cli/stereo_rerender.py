@@ -71,7 +71,8 @@ def build_parser() -> argparse.ArgumentParser:
     add("--load_background", help="Load the compound background from a file.")
     add("--create_sbs_depth_video", action="store_true", help="Save a depth version of the final sbs video")
     # additions (not in the reference)
-    add("--chunk_frames", default=8, type=int, help="frames per GPU batch")
+    add("--chunk_frames", default=12, type=int, help="frames per GPU batch (a multiple of 12, OpenCV's FFV1 key-frame interval, lets several decoders work on one input)")
+    add("--writer_lanes", default=0, type=int, help="parallel FFV1 encoder lanes per output file (0: from the host core count, 1: the reference's single writer)")
     return p
 
 
@@ -151,21 +152,33 @@ def run(args, keep_process_group: bool = False) -> int:
     # whole-clip parameters: built once on rank 0, broadcast (the only inter-GPU traffic of the job)
     params = load_clip_parameters(args, frame_width, frame_height, total) if rank == 0 else None
     params, _ = sharding.broadcast_params(params, total)
-    start, stop = sharding.frame_range(total_frames, rank, world_size)
+    # GOP-aligned ranges when every rank still gets work: range starts are key frames of the input files
+    align = video_io.GOP if total_frames >= world_size * video_io.GOP else 1
+    start, stop = sharding.frame_range(total_frames, rank, world_size, align)
 
     from . import stereo_modes
 
     job = stereo_modes.StereoJob(args, params, device, frame_width, frame_height)
     output_file, output_tmp_file, fourcc = output_names(args)
     seg = (lambda p: p) if world_size == 1 else (lambda p: f"{p}.rank{rank:02d}.mkv")
-    seg_fourcc = fourcc if world_size == 1 else "FFV1"
-    writers = {"main": video_io.ChunkWriter(seg(output_tmp_file), seg_fourcc, frame_rate, job.out_size)}
-    if job.writes_mask:
-        writers["mask"] = video_io.ChunkWriter(seg(output_tmp_file + "_infillmask.mkv"), "FFV1", frame_rate, job.out_size)
-    if job.has_depth_output:
-        writers["depth"] = video_io.ChunkWriter(seg(output_tmp_file + "_depth.mkv"), "FFV1", frame_rate, job.out_size)
+    # FFV1 results go through parallel encoder lanes joined at packet level (video_io.ParallelWriter); the compressed
+    # (avc1) variant keeps the single writer and, under torchrun, the frame-copy join
+    lanes = args.writer_lanes if args.writer_lanes > 0 else video_io.default_lanes(world_size)
+    parallel = fourcc == "FFV1" and lanes > 1
 
-    reader = video_io.ChunkReader([args.depth_video, args.color_video], start, stop, chunk=args.chunk_frames)
+    def open_writer(path: str, cc: str):
+        if parallel and cc == "FFV1":
+            return video_io.ParallelWriter(seg(path), frame_rate, job.out_size, lanes=lanes, join_on_close=(world_size == 1))
+        return video_io.ChunkWriter(seg(path), cc if world_size == 1 else "FFV1", frame_rate, job.out_size)
+
+    writers = {"main": open_writer(output_tmp_file, fourcc)}
+    if job.writes_mask:
+        writers["mask"] = open_writer(output_tmp_file + "_infillmask.mkv", "FFV1")
+    if job.has_depth_output:
+        writers["depth"] = open_writer(output_tmp_file + "_depth.mkv", "FFV1")
+
+    reader = video_io.ChunkReader([args.depth_video, args.color_video], start, stop, chunk=args.chunk_frames,
+                                  decoders=video_io.default_decoders(world_size))
     t0 = time.time()
     done = 0
     for n, (depth_rgb, colour) in reader:
@@ -188,7 +201,9 @@ def run(args, keep_process_group: bool = False) -> int:
         if rank == 0:
             for suffix, cc in (("", fourcc), ("_infillmask.mkv", "FFV1"), ("_depth.mkv", "FFV1")):
                 parts = [f"{output_tmp_file}{suffix}.rank{r:02d}.mkv" for r in range(world_size)]
-                if all(os.path.isfile(p) for p in parts):
+                if all(os.path.isfile(p + ".plan.json") for p in parts):   # parallel lanes: packet-level join, no re-encode
+                    video_io.join_plans([video_io.load_plan(p) for p in parts], output_tmp_file + suffix, frame_rate)
+                elif all(os.path.isfile(p) for p in parts):
                     stereo_modes.join_segments(parts, output_tmp_file + suffix, cc, frame_rate, job.out_size)
         dist.barrier()
     if rank == 0:

@@ -45,7 +45,7 @@ def build_parser() -> argparse.ArgumentParser:
     add("--tx", default=-99.0, type=float, help="camera target x coordinate in meters")
     add("--ty", default=-99.0, type=float, help="camera target y coordinate in meters")
     add("--tz", default=-99.0, type=float, help="camera target z coordinate in meters")
-    add("--chunk_frames", default=4, type=int, help="frames per GPU batch (addition)")
+    add("--chunk_frames", default=12, type=int, help="frames per GPU batch (addition; a multiple of 12 lets several decoders read one input)")
     return p
 
 
@@ -79,10 +79,13 @@ def main(argv: Optional[List[str]] = None) -> int:
     renderer = NovelViewRenderer(NovelViewParams(w, h, args.xfov, args.yfov, args.max_depth, (args.x, args.y, args.z), target, transformations,
                                                  of_by_one=not args.render_as_pointcloud), device)
     output_file, fourcc = (args.depth_video + "_render.mp4", "avc1") if args.compressed else (args.depth_video + "_render.mkv", "FFV1")
-    writer = video_io.ChunkWriter(output_file, fourcc, fps, (w, h))
+    lanes = video_io.default_lanes()
+    writer = video_io.ParallelWriter(output_file, fps, (w, h), lanes=lanes) if (fourcc == "FFV1" and lanes > 1) else \
+        video_io.ChunkWriter(output_file, fourcc, fps, (w, h))
     done = 0
     host_out = None
-    for n, (depth_rgb, colour) in video_io.ChunkReader([args.depth_video, args.color_video], 0, total_frames, chunk=args.chunk_frames):
+    for n, (depth_rgb, colour) in video_io.ChunkReader([args.depth_video, args.color_video], 0, total_frames, chunk=args.chunk_frames,
+                                                          decoders=video_io.default_decoders()):
         d = depth_rgb.to(device, non_blocking=True)
         c = d if colour is None else colour.to(device, non_blocking=True)
         rgb, _ = renderer.render_device(d, c, done)

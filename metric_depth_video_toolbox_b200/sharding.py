@@ -49,16 +49,20 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
     return rank, world_size, local_rank
 
 
-def frame_range(n_frames: int, rank: Optional[int] = None, world_size: Optional[int] = None) -> Tuple[int, int]:
-    """Contiguous [start, stop) of `rank`: ranges differ by at most one frame, concatenate in rank order to
-    [0, n_frames), and are empty only when there are fewer frames than ranks."""
+def frame_range(n_frames: int, rank: Optional[int] = None, world_size: Optional[int] = None, align: int = 1) -> Tuple[int, int]:
+    """Contiguous [start, stop) of `rank`: ranges differ by at most one frame (one block of `align` frames), concatenate
+    in rank order to [0, n_frames), and are empty only when there are fewer frames (blocks) than ranks.  align > 1 puts
+    every range start on a multiple of `align` (the key-frame interval of the clip files: seeks to a range start are
+    exact and cheap, and every rank can decode with several threads)."""
     if rank is None or world_size is None:
         rank, world_size = world()
-    if n_frames < 0 or world_size < 1 or not 0 <= rank < world_size:
-        raise ValueError(f"bad sharding request: {n_frames} frames, rank {rank} of {world_size}")
-    base, extra = divmod(n_frames, world_size)
+    if n_frames < 0 or world_size < 1 or not 0 <= rank < world_size or align < 1:
+        raise ValueError(f"bad sharding request: {n_frames} frames, rank {rank} of {world_size}, align {align}")
+    blocks = (n_frames + align - 1) // align
+    base, extra = divmod(blocks, world_size)
     start = rank * base + min(rank, extra)
-    return start, start + base + (1 if rank < extra else 0)
+    stop = start + base + (1 if rank < extra else 0)
+    return min(start * align, n_frames), min(stop * align, n_frames)
 
 
 # ---------------------------------------------------------------------------------------------

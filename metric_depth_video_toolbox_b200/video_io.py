@@ -5,6 +5,8 @@ cv2.VideoWriter, FFV1 or avc1); nothing per-pixel besides the BGR<->RGB byte swa
 """
 from __future__ import annotations
 
+import json
+import os
 import queue
 import threading
 from typing import List, Optional, Sequence, Tuple
@@ -30,72 +32,146 @@ def video_info(path: str) -> Tuple[int, int, float, int]:
         cap.release()
 
 
+def _is_ffv1(cap) -> bool:
+    cv2 = _cv2()
+    cc = int(cap.get(cv2.CAP_PROP_FOURCC))
+    return bytes((cc >> (8 * k)) & 0xFF for k in range(4)).upper() == b"FFV1"
+
+
+def default_decoders(world_size: int = 1) -> int:
+    env = os.environ.get("MDVT_READER_THREADS")
+    if env:
+        return max(1, int(env))
+    return max(1, min(4, (os.cpu_count() or 2) // (4 * max(1, world_size))))
+
+
+class _DecodeWorker(threading.Thread):
+    """One cv2.VideoCapture on its own thread: fills (buffer, first frame, count) requests, seeking when the request
+    does not continue where the previous one ended."""
+
+    def __init__(self, path: str, grey: bool):
+        super().__init__(daemon=True)
+        self.path, self.grey = path, grey
+        self.tasks: "queue.Queue" = queue.Queue()
+        self.start()
+
+    def submit(self, buf, first: int, count: int) -> dict:
+        ticket = {"done": threading.Event(), "n": 0, "err": None}
+        self.tasks.put((buf, first, count, ticket))
+        return ticket
+
+    def run(self):
+        cv2 = _cv2()
+        cap = cv2.VideoCapture(self.path)
+        pos = 0
+        code = cv2.COLOR_BGR2GRAY if self.grey else cv2.COLOR_BGR2RGB
+        while True:
+            item = self.tasks.get()
+            if item is None:
+                cap.release()
+                return
+            buf, first, count, ticket = item
+            try:
+                if first != pos:
+                    cap.set(cv2.CAP_PROP_POS_FRAMES, first)  # block starts are key frames of FFV1 / intra-only sources: exact
+                    pos = first
+                out = buf.numpy()
+                n = 0
+                while n < count:
+                    ok, frame = cap.read()
+                    if not ok:
+                        break
+                    cv2.cvtColor(frame, code, dst=out[n])
+                    n += 1
+                    pos += 1
+                ticket["n"] = n
+            except BaseException as exc:
+                ticket["err"] = exc
+            ticket["done"].set()
+
+
 class ChunkReader:
     """Reads frames [start, stop) of one or more same-length videos in lock step, converts BGR -> RGB and
     yields chunks of up to `chunk` frames as pinned uint8 tensors (n, H, W, 3) -- one tensor per video.
-    A background thread stays `depth` chunks ahead.  A short video ends the iteration for all of them
-    (the scripts stop at the first failed read, stereo_rerender.py:489-503)."""
+    Every video has its own decode thread(s); background threads stay `depth` chunks ahead.  `decoders` > 1 decodes
+    several chunks of the same video at once (FFV1 sources with GOP-aligned chunks only: each decoder seeks to the
+    chunk's first frame, a key frame).  A short video ends the iteration for all of them (the scripts stop at the first
+    failed read, stereo_rerender.py:489-503)."""
 
     def __init__(self, paths: Sequence[Optional[str]], start: int = 0, stop: Optional[int] = None, chunk: int = 8, depth: int = 3,
-                 pin: bool = True, grey: Sequence[bool] = ()):
+                 pin: bool = True, grey: Sequence[bool] = (), decoders: int = 1):
         cv2 = _cv2()
         self.paths = list(paths)
-        self.caps = [None if p is None else cv2.VideoCapture(p) for p in self.paths]
         self.grey = list(grey) + [False] * (len(self.paths) - len(grey))
-        first = next(c for c in self.caps if c is not None)
+        probes = [None if p is None else cv2.VideoCapture(p) for p in self.paths]
+        first = next(c for c in probes if c is not None)
         self.width, self.height = int(first.get(cv2.CAP_PROP_FRAME_WIDTH)), int(first.get(cv2.CAP_PROP_FRAME_HEIGHT))
-        total = min(int(c.get(cv2.CAP_PROP_FRAME_COUNT)) for c in self.caps if c is not None)
+        total = min(int(c.get(cv2.CAP_PROP_FRAME_COUNT)) for c in probes if c is not None)
+        all_ffv1 = all(_is_ffv1(c) for c in probes if c is not None)
+        for c in probes:
+            if c is not None:
+                c.release()
         self.start, self.stop = start, total if stop is None else min(stop, total)
-        if start > 0:
-            for c in self.caps:
-                if c is not None:
-                    c.set(cv2.CAP_PROP_POS_FRAMES, start)  # FFV1 / intra-only: exact
         self.chunk, self.pin = max(1, chunk), pin and torch.cuda.is_available()
+        # parallel decode needs exact, cheap seeks: FFV1 written with OpenCV's GOP, chunks that start on key frames
+        self.decoders = max(1, decoders) if (all_ffv1 and self.chunk % GOP == 0 and start % GOP == 0) else 1
+        self._workers = [None if p is None else [_DecodeWorker(p, g) for _ in range(self.decoders)] for p, g in zip(self.paths, self.grey)]
         self._q: "queue.Queue" = queue.Queue(maxsize=max(1, depth))
         self._free: "queue.Queue" = queue.Queue()
-        for _ in range(depth + 2):
+        for _ in range(depth + 2 + self.decoders):
             self._free.put(self._alloc())
-        self._thread = threading.Thread(target=self._run, daemon=True)
-        self._thread.start()
+        self._tickets: "queue.Queue" = queue.Queue(maxsize=max(1, depth) + self.decoders)
+        self._threads = [threading.Thread(target=self._dispatch, daemon=True), threading.Thread(target=self._collect, daemon=True)]
+        for t in self._threads:
+            t.start()
 
     def _alloc(self) -> List[Optional[torch.Tensor]]:
         bufs = []
-        for c, g in zip(self.caps, self.grey):
+        for p, g in zip(self.paths, self.grey):
             shape = (self.chunk, self.height, self.width) + (() if g else (3,))
-            bufs.append(None if c is None else torch.empty(shape, dtype=torch.uint8, pin_memory=self.pin))
+            bufs.append(None if p is None else torch.empty(shape, dtype=torch.uint8, pin_memory=self.pin))
         return bufs
 
-    def _run(self):
-        cv2 = _cv2()
+    def _dispatch(self):
+        c = 0
         pos = self.start
         try:
             while pos < self.stop:
                 bufs = self._free.get()
-                n = 0
-                while n < self.chunk and pos < self.stop:
-                    ok_all = True
-                    for cap, buf, g in zip(self.caps, bufs, self.grey):
-                        if cap is None:
-                            continue
-                        ok, frame = cap.read()
-                        if not ok:
-                            ok_all = False
-                            break
-                        cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY if g else cv2.COLOR_BGR2RGB, dst=buf[n].numpy())
-                    if not ok_all:
-                        pos = self.stop
-                        break
-                    n += 1
-                    pos += 1
+                count = min(self.chunk, self.stop - pos)
+                tickets = [None if w is None else w[c % self.decoders].submit(b, pos, count) for w, b in zip(self._workers, bufs)]
+                self._tickets.put((count, bufs, tickets))
+                pos += count
+                c += 1
+        finally:
+            self._tickets.put(None)
+
+    def _collect(self):
+        try:
+            while True:
+                item = self._tickets.get()
+                if item is None:
+                    break
+                count, bufs, tickets = item
+                n = count
+                for t in tickets:
+                    if t is None:
+                        continue
+                    t["done"].wait()
+                    if t["err"] is not None:
+                        raise t["err"]
+                    n = min(n, t["n"])
                 if n:
                     self._q.put((n, bufs))
+                if n < count:   # a video ended early: stop here for all of them
+                    break
         except BaseException as exc:  # surfaced on the consumer side
             self._q.put(exc)
         finally:
             self._q.put(None)
-            for c in self.caps:
-                if c is not None:
-                    c.release()
+            for ws in self._workers:
+                for w in ws or ():
+                    w.tasks.put(None)
 
     def __iter__(self):
         while True:
@@ -154,6 +230,117 @@ class ChunkWriter:
         self.writer.release()
         if self._err is not None:
             raise self._err
+
+
+GOP = 12  # key-frame interval of OpenCV's FFmpeg writer (AVCodecContext.gop_size): lanes are filled in whole GOPs
+
+
+def default_lanes(world_size: int = 1) -> int:
+    env = os.environ.get("MDVT_WRITER_LANES")
+    if env:
+        return max(1, int(env))
+    return max(1, min(12, (os.cpu_count() or 2) // (2 * max(1, world_size))))
+
+
+class ParallelWriter:
+    """An FFV1 .mkv written by `lanes` cv2.VideoWriters at once.  The single-threaded FFV1 entropy coder behind
+    cv2.VideoWriter is the end-to-end limiter of every script (about 0.45 s per 3840x1080 frame); here the clip is cut
+    into blocks of GOP frames, block b goes to lane b % lanes (its own writer thread and lane file, so each lane file
+    is a sequence of closed GOPs), and `close()` stitches the encoded packets back into display order with
+    `mkv_join.join` -- no re-encode, same container / codec parameters, frames decode bit-identically.
+    join_on_close=False leaves the lane files and a `<path>.plan.json` for a later join of several writers' lanes
+    (the torchrun ranks of one job)."""
+
+    def __init__(self, path: str, fps: float, size: Tuple[int, int], lanes: Optional[int] = None, join_on_close: bool = True):
+        self.path, self.fps, self.size, self.join_on_close = path, fps, size, join_on_close
+        n = default_lanes() if lanes is None else max(1, lanes)
+        self.lane_paths = [f"{path}.lane{k:02d}.mkv" for k in range(n)]
+        self.lane_writers = [ChunkWriter(p, "FFV1", fps, size, depth=1) for p in self.lane_paths]
+        self.plan: List[Tuple[str, int]] = []
+        self.frames = 0
+        self._pending: List[np.ndarray] = []
+        self._pending_n = 0
+        self._rgb: Optional[bool] = None
+        self._block = 0
+
+    def _emit(self, n: int):
+        """Send the first n pending frames to the next lane as one block."""
+        take, got = [], 0
+        while got < n:
+            a = self._pending[0]
+            need = n - got
+            if a.shape[0] <= need:
+                take.append(a)
+                got += a.shape[0]
+                self._pending.pop(0)
+            else:
+                take.append(a[:need])
+                self._pending[0] = a[need:]
+                got += need
+        self._pending_n -= n
+        lane = self._block % len(self.lane_writers)
+        self.lane_writers[lane].write(take[0] if len(take) == 1 else np.concatenate(take), rgb=bool(self._rgb))
+        self.plan.append((self.lane_paths[lane], n))
+        self._block += 1
+
+    def write(self, frames, rgb: bool = True):
+        arr = frames.numpy() if isinstance(frames, torch.Tensor) else np.asarray(frames)
+        if arr.shape[1:3] != (self.size[1], self.size[0]):
+            raise ValueError(f"frames are {arr.shape[2]}x{arr.shape[1]}, writer expects {self.size[0]}x{self.size[1]}")
+        if self._rgb is None:
+            self._rgb = rgb
+        elif self._rgb != rgb:
+            raise ValueError("one writer takes either RGB or BGR frames, not both")
+        if arr.shape[0] == 0:
+            return
+        # the caller may recycle its buffer after write() returns: blocks that are not sent right away are copied
+        self._pending.append(arr)
+        self._pending_n += arr.shape[0]
+        self.frames += arr.shape[0]
+        while self._pending_n >= GOP:
+            self._emit(GOP)
+        self._pending = [a.copy() for a in self._pending]
+
+    def close(self):
+        if self._pending_n:
+            self._emit(self._pending_n)
+        for w in self.lane_writers:
+            w.close()
+        if self.join_on_close:
+            join_plans([self.plan], self.path, self.fps)
+            for p in self.lane_paths:  # lanes that never received a block
+                if os.path.exists(p):
+                    os.remove(p)
+        else:
+            with open(self.path + ".plan.json", "w") as fh:
+                json.dump({"fps": self.fps, "plan": self.plan, "lanes": self.lane_paths}, fh)
+
+
+def join_plans(plans: Sequence[Sequence[Tuple[str, int]]], out_path: str, fps: float, remove: bool = True) -> int:
+    """Packet-level join of the lanes of one or more ParallelWriters (in the given order) into `out_path`."""
+    from . import mkv_join
+
+    plan = [(p, int(n)) for pl in plans for p, n in pl]
+    lanes = sorted({p for p, _ in plan})
+    total = mkv_join.join(plan, out_path, fps) if plan else 0
+    if remove:
+        for p in lanes:
+            if os.path.exists(p):
+                os.remove(p)
+    return total
+
+
+def load_plan(path: str, remove: bool = True):
+    """The plan a ParallelWriter(join_on_close=False) left next to its lane files (+ lane files that hold no block)."""
+    with open(path + ".plan.json") as fh:
+        d = json.load(fh)
+    if remove:
+        os.remove(path + ".plan.json")
+        used = {p for p, _ in d["plan"]}
+        for p in d["lanes"]:
+            if p not in used and os.path.exists(p):
+                os.remove(p)
+    return [(p, int(n)) for p, n in d["plan"]]
 
 
 def write_clip(path: str, frames_rgb, fps: float = 24.0, fourcc: str = "FFV1", rgb: bool = True):

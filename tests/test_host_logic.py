@@ -196,3 +196,86 @@ def test_equirect_maps_match_reference(golden_dir):
         assert mx.dtype == np.float32 and (mx == -1).any()
         out = cv2.remap(img, mx, my, interpolation=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=(0, 0, 0))
         assert np.array_equal(out, g[f"equirect_out{k}"]), k
+
+
+@pytest.mark.parametrize("n,world,align", [(100, 3, 12), (7, 2, 12), (2400, 8, 12), (25, 4, 12), (12, 2, 12)])
+def test_aligned_frame_ranges_partition_the_clip(n, world, align):
+    ranges = [sharding.frame_range(n, r, world, align) for r in range(world)]
+    assert ranges[0][0] == 0 and ranges[-1][1] == n
+    for (a0, a1), (b0, b1) in zip(ranges, ranges[1:]):
+        assert a1 == b0 and a0 <= a1
+    assert all(a % align == 0 or a == n for a, _ in ranges)
+
+
+def _noise_clip(n, h=48, w=64, seed=0):
+    return np.random.default_rng(seed).integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+
+
+@pytest.mark.parametrize("lanes,n,step", [(1, 30, 8), (3, 77, 8), (8, 25, 12), (4, 12, 5), (5, 3, 3)])
+def test_parallel_writer_joins_lanes_into_the_same_frames(tmp_path, lanes, n, step):
+    """K FFV1 encoder lanes + the packet-level Matroska join == the frames a single cv2.VideoWriter file holds:
+    same frame count, fps and size as OpenCV reports them, every frame bit-identical, exact random access."""
+    import cv2
+
+    from metric_depth_video_toolbox_b200 import video_io
+
+    frames = _noise_clip(n)
+    path = str(tmp_path / "out.mkv")
+    w = video_io.ParallelWriter(path, 24.0, (64, 48), lanes=lanes)
+    for s in range(0, n, step):
+        w.write(frames[s:s + step])
+    w.close()
+    assert sorted(os.listdir(tmp_path)) == ["out.mkv"]          # lane files are gone
+    assert video_io.video_info(path) == (64, 48, 24.0, n)
+    assert np.array_equal(video_io.read_clip(path), frames)
+    cap = cv2.VideoCapture(path)
+    for pos in (n - 1, n // 2, 0):
+        cap.set(cv2.CAP_PROP_POS_FRAMES, pos)
+        ok, f = cap.read()
+        assert ok and np.array_equal(f[..., ::-1], frames[pos])
+
+
+def test_parallel_writers_of_two_ranks_join_in_rank_order(tmp_path):
+    from metric_depth_video_toolbox_b200 import video_io
+
+    frames = _noise_clip(50, seed=1)
+    parts = []
+    for r, (a, b) in enumerate(((0, 24), (24, 50))):
+        p = str(tmp_path / f"seg.rank{r:02d}.mkv")
+        w = video_io.ParallelWriter(p, 30.0, (64, 48), lanes=3, join_on_close=False)
+        w.write(frames[a:b])
+        w.close()
+        parts.append(p)
+    out = str(tmp_path / "joined.mkv")
+    assert video_io.join_plans([video_io.load_plan(p) for p in parts], out, 30.0) == 50
+    assert sorted(os.listdir(tmp_path)) == ["joined.mkv"]
+    assert video_io.video_info(out) == (64, 48, 30.0, 50)
+    assert np.array_equal(video_io.read_clip(out), frames)
+
+
+@pytest.mark.parametrize("decoders,chunk,start", [(1, 8, 0), (3, 12, 0), (3, 12, 24), (2, 24, 12), (3, 8, 5)])
+def test_chunk_reader_parallel_decoders_read_the_same_frames(tmp_path, decoders, chunk, start):
+    from metric_depth_video_toolbox_b200 import video_io
+
+    a, b = _noise_clip(77, seed=2), _noise_clip(70, seed=3)
+    pa, pb = str(tmp_path / "a.mkv"), str(tmp_path / "b.mkv")
+    video_io.write_clip(pa, a, 24.0)
+    w = video_io.ParallelWriter(pb, 24.0, (64, 48), lanes=3)   # a joined file as input
+    w.write(b)
+    w.close()
+    r = video_io.ChunkReader([pa, pb], start, None, chunk=chunk, decoders=decoders, pin=False)
+    got_a, got_b = [], []
+    for n, (xa, xb) in r:
+        got_a.append(xa.numpy().copy())
+        got_b.append(xb.numpy().copy())
+    assert np.array_equal(np.concatenate(got_a), a[start:70]) and np.array_equal(np.concatenate(got_b), b[start:])
+
+
+def test_mkv_join_refuses_a_run_that_does_not_start_on_a_key_frame(tmp_path):
+    from metric_depth_video_toolbox_b200 import mkv_join, video_io
+
+    p = str(tmp_path / "a.mkv")
+    video_io.write_clip(p, _noise_clip(20), 24.0)
+    with pytest.raises(mkv_join.MkvError):
+        mkv_join.join([(p, 5), (p, 5)], str(tmp_path / "bad.mkv"), 24.0)   # packet 5 is inside a GOP
+    assert mkv_join.join([(p, 12), (p, 8)], str(tmp_path / "ok.mkv"), 24.0) == 20
