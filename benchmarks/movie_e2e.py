@@ -24,7 +24,12 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 48
 green = "--green" in sys.argv
 w, h = 1920, 1080
 rank, world, local = sharding.init_from_env()
-tmp = os.environ.get("MDVT_E2E_DIR") or tempfile.mkdtemp(prefix="mdvt_e2e_")
+tmp = os.environ.get("MDVT_E2E_DIR") or os.path.join(tempfile.gettempdir(), f"mdvt_e2e_{os.environ.get('MASTER_PORT', 'single')}_{n}")
+if rank == 0:
+    import shutil
+
+    shutil.rmtree(tmp, ignore_errors=True)
+    os.makedirs(tmp)
 paths = {k: os.path.join(tmp, k + ".mkv") for k in ("depth", "colour", "mask")}
 t_gen = time.time()
 if rank == 0:
