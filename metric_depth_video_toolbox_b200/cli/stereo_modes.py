@@ -76,6 +76,7 @@ class StereoJob:
     # ---- stereo ---------------------------------------------------------------------------------------
     def _stereo_chunk(self, depth_rgb, colour, first_frame):
         n = depth_rgb.shape[0]
+        deferred_mask = None
         sbs = self._host_buf("main", (n, self.h, 2 * self.w, 3))
         mask = self._host_buf("mask", (n, self.h, 2 * self.w, 3)) if self.params.infill_mask else None
         if not self.has_depth_output and self.infill is None:  # the pipelined two-stream path
@@ -106,11 +107,13 @@ class StereoJob:
                 mask.copy_(dmask, non_blocking=True)
                 if self.code_normals:  # host part: TELEA + masked blur per eye (OpenCV, as the reference)
                     torch.cuda.synchronize(self.device)
-                    mask.copy_(torch.from_numpy(self.infill.finish(mask.numpy())))
                     if self.basic_infill:  # final mask back to the device, march, filled image to the host
+                        mask.copy_(torch.from_numpy(self.infill.finish(mask.numpy())))
                         dmask.copy_(mask, non_blocking=True)
                         self.infill.basic_infill(dsbs, dmask)
                         sbs.copy_(dsbs, non_blocking=True)
+                    else:  # finished on the worker pool while the loop goes on; the front end writes it one chunk later
+                        deferred_mask = self.infill.finish_async(mask.numpy())
         else:
             from .. import ops
 
@@ -130,7 +133,7 @@ class StereoJob:
             hdepth.copy_(coded, non_blocking=True)
             out = {"main": sbs, "depth": hdepth}
         if mask is not None:
-            out["mask"] = mask
+            out["mask"] = deferred_mask if deferred_mask is not None else mask
         return out
 
     # ---- touchly1 -------------------------------------------------------------------------------------

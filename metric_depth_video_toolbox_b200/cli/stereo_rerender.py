@@ -181,15 +181,24 @@ def run(args, keep_process_group: bool = False) -> int:
                                   decoders=video_io.default_decoders(world_size))
     t0 = time.time()
     done = 0
+    deferred = {}
     for n, (depth_rgb, colour) in reader:
         outputs = job.render_chunk(depth_rgb, depth_rgb if colour is None else colour, start + done)
         torch.cuda.synchronize(device)  # results are on the host, the reader may recycle its buffers
+        for key, pending in list(deferred.items()):   # last chunk's host-finished frames (TELEA tail of the mask)
+            writers[key].write(pending.result(), rgb=(key != "depth"))
+            del deferred[key]
         for key, w in writers.items():
-            w.write(outputs[key], rgb=(key != "depth"))
+            if hasattr(outputs[key], "result"):
+                deferred[key] = outputs[key]
+            else:
+                w.write(outputs[key], rgb=(key != "depth"))
         done += n
         if rank == 0:
             pct = 100.0 * done / max(1, stop - start)
             print(f"[{pct:5.1f}%] Frame #{done:4d}/{stop - start}  {done / max(1e-9, time.time() - t0):7.1f} frames/s", end="\r", file=sys.stderr)
+    for key, pending in deferred.items():
+        writers[key].write(pending.result(), rgb=(key != "depth"))
     for w in writers.values():
         w.close()
     total_done = sharding.gather_counts(done)

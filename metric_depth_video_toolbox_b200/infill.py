@@ -54,9 +54,11 @@ class InfillMaskRenderer:
     """StereoRerenderer plus the normals-coded mask.  render_device returns (sbs u8 (n, H, 2W, 3) with edge colours
     painted into the holes, mask image u8 (n, H, 2W, 3) BEFORE inpainting); finish() runs the host part."""
 
-    def __init__(self, renderer: StereoRerenderer, workers: int = 8):
+    def __init__(self, renderer: StereoRerenderer, workers: Optional[int] = None):
+        import os
+
         self.r = renderer
-        self.pool = ThreadPoolExecutor(max_workers=max(1, workers))
+        self.pool = ThreadPoolExecutor(max_workers=max(1, workers or (os.cpu_count() or 8)))
         self._zbuf = None
         self._flags = self._normals = self._holes = None
 
@@ -104,14 +106,33 @@ class InfillMaskRenderer:
                 ops.normal_march_infill(sbs[k, :, half], self._holes[k, :, half], final_mask_img[k, :, half], max_steps)
         return sbs
 
-    def finish(self, mask_img_host: np.ndarray) -> np.ndarray:
-        """(n, H, 2W, 3) u8 pre-inpaint mask images (host) -> final mask frames; each eye is finished on its own, as the
-        reference does (left_img_mask / right_img_mask, :805-808,893-896)."""
+    def finish_async(self, mask_img_host: np.ndarray) -> "DeferredFrames":
+        """(n, H, 2W, 3) u8 pre-inpaint mask images (host) -> final mask frames, finished on the worker pool; each eye is
+        finished on its own, as the reference does (left_img_mask / right_img_mask, :805-808,893-896).  The inputs are
+        copied before this returns (the caller may reuse its buffer); `.result()` waits for the frames."""
         n, h, w2, _ = mask_img_host.shape
         w = w2 // 2
         out = np.empty_like(mask_img_host)
-        jobs = [(k, e, self.pool.submit(finish_mask, np.ascontiguousarray(mask_img_host[k, :, e * w:(e + 1) * w])))
-                for k in range(n) for e in range(2)]
-        for k, e, fut in jobs:
-            out[k, :, e * w:(e + 1) * w] = fut.result()
-        return out
+
+        def task(src, k, e):
+            out[k, :, e * w:(e + 1) * w] = finish_mask(src)
+
+        futures = [self.pool.submit(task, np.ascontiguousarray(mask_img_host[k, :, e * w:(e + 1) * w]), k, e)
+                   for k in range(n) for e in range(2)]
+        return DeferredFrames(out, futures)
+
+    def finish(self, mask_img_host: np.ndarray) -> np.ndarray:
+        return self.finish_async(mask_img_host).result()
+
+
+class DeferredFrames:
+    """Frames that host workers are still producing (the TELEA + blur tail of the infill mask): the frame loop keeps
+    reading, rendering and encoding the other outputs meanwhile and asks for `.result()` one chunk later."""
+
+    def __init__(self, frames: np.ndarray, futures):
+        self._frames, self._futures = frames, futures
+
+    def result(self) -> np.ndarray:
+        for f in self._futures:
+            f.result()
+        return self._frames
