@@ -11,6 +11,7 @@ video track) and Clusters of SimpleBlocks / BlockGroups.
 """
 from __future__ import annotations
 
+import mmap
 import os
 import struct
 from typing import BinaryIO, Iterator, List, Sequence, Tuple
@@ -98,13 +99,13 @@ class MkvPackets:
 
     def __init__(self, path: str):
         self.path = path
-        with open(path, "rb") as fh:
-            buf = fh.read()
+        with open(path, "rb") as fh:   # mapped, not read: the lanes of a long clip add up to the size of the result
+            buf = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) if os.path.getsize(path) else b""
         self._buf = buf
         top = list(_children(buf, 0, len(buf)))
         if not top or top[0][0] != ID_EBML:
             raise MkvError(f"{path}: not an EBML file")
-        self.ebml_header = buf[0:top[0][2]]
+        self.ebml_header = bytes(buf[0:top[0][2]])
         seg = next((t for t in top if t[0] == ID_SEGMENT), None)
         if seg is None:
             raise MkvError(f"{path}: no Segment")
@@ -113,7 +114,7 @@ class MkvPackets:
         self.packets: List[Tuple[int, int, bool]] = []
         for eid, s, e in _children(buf, seg[1], seg[2]):
             if eid == ID_TRACKS:
-                self.tracks = buf[s:e]
+                self.tracks = bytes(buf[s:e])
             elif eid == ID_INFO:
                 for cid, cs, ce in _children(buf, s, e):
                     if cid == ID_TIMECODE_SCALE:
@@ -149,6 +150,11 @@ class MkvPackets:
     def payload(self, index: int) -> bytes:
         off, size, _ = self.packets[index]
         return self._buf[off:off + size]
+
+    def close(self):
+        if isinstance(self._buf, mmap.mmap):
+            self._buf.close()
+        self._buf = b""
 
     def codec_private(self) -> bytes:
         for eid, s, e in _children(self.tracks, 0, len(self.tracks)):
@@ -236,5 +242,7 @@ def join(plan: Sequence[Tuple[str, int]], out_path: str, fps: float, frames_per_
         seg_size = out.tell() - seg_start
         out.seek(seg_start - 8)
         out.write(_enc_size(seg_size, 8))
+    for lane in lanes.values():
+        lane.close()
     os.replace(tmp, out_path)
     return total
