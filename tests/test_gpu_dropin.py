@@ -242,11 +242,16 @@ def test_novel_view_renderer_vs_oracle(of_by_one, yfov):
         assert (mask[k].cpu().numpy() != want_mask).mean() < 3e-3
 
 
-@pytest.mark.parametrize("of_by_one,yfov,posed", [(True, None, True), (False, 50.0, False), (True, 40.0, True)])
-def test_novel_view_device_camera_equals_host_camera(of_by_one, yfov, posed):
+@pytest.mark.parametrize("of_by_one,yfov,posed,size", [(True, None, True, (160, 120)), (False, 50.0, False, (160, 120)),
+                                                       (True, 40.0, True, (160, 120)), (True, None, False, (70, 33)),
+                                                       (False, None, True, (132, 50))])
+def test_novel_view_device_camera_equals_host_camera(of_by_one, yfov, posed, size):
     """mdvt_novel_view_frames evaluates centroid -> look-at -> view on the device: its cameras must equal the NumPy
-    helpers' (<= 1 float32 ulp per entry), and its images must be what the generic path renders from those cameras."""
-    w, h, n = 160, 120, 3
+    helpers' (<= 1 float32 ulp per entry), and its images must be what the generic path renders from those cameras.
+    (70, 33): widths that are not multiples of 4 take the scalar centroid / resolve kernels with the touched flags;
+    (132, 50): rows that are not multiples of the 64-slot touched segments."""
+    w, h = size
+    n = 3
     depth, colour = SyntheticClip(w, h, n, zero_fraction=0.005).frames()
     T = None
     if posed:
