@@ -151,7 +151,12 @@ def save_depth_video(frames, output_video_path, fps, max_depth_arg, rescale_widt
         print("max metric depth: ", deepest)
         if max_depth_arg < deepest:
             print("warning: output depth is deeper than max_depth. The depth will be clipped")
-    out = cv2.VideoWriter(output_video_path, cv2.VideoWriter_fourcc(*"FFV1"), fps, (rescale_width, rescale_height))
+    from . import video_io
+
+    # parallel FFV1 encoder lanes joined at packet level: the same frames as one cv2.VideoWriter would hold
+    lanes = video_io.default_lanes()
+    out = video_io.ParallelWriter(output_video_path, fps, (rescale_width, rescale_height), lanes=lanes) if lanes > 1 else \
+        video_io.ChunkWriter(output_video_path, "FFV1", fps, (rescale_width, rescale_height))
     batch = max(1, min(nr_frames, (256 << 20) // max(1, rescale_width * rescale_height * 4)))
     for start in range(0, nr_frames, batch):
         chunk = []
@@ -161,10 +166,8 @@ def save_depth_video(frames, output_video_path, fps, max_depth_arg, rescale_widt
                 depth = cv2.resize(depth, (rescale_width, rescale_height), interpolation=cv2.INTER_LINEAR)
             chunk.append(np.ascontiguousarray(depth, dtype=np.float32))
         dev = torch.from_numpy(np.stack(chunk)).to(_device())
-        bgr = ops.encode_depth(dev, max_depth_arg, True, True).cpu().numpy()
-        for frame in bgr:
-            out.write(frame)
-    out.release()
+        out.write(ops.encode_depth(dev, max_depth_arg, True, True).cpu().numpy(), rgb=False)  # B, G, R like encode_data_as_BGR
+    out.close()
 
 
 def verify_and_move(tmp_file, expected_frames, output_file):
