@@ -15,6 +15,8 @@
 // Phase B gathers the winners' colours straight from global memory (the few source rows involved are L1/L2 hot),
 // packs RGB / mask bytes into a staging row and hands it to a TMA bulk store, like the row-local kernel.
 // HBM traffic is the algorithmic 14 B/px; the 33 MB z-buffer planes and their read / re-arm passes are gone.
+#include <cstdlib>
+
 #include "mdvt_common.cuh"
 
 namespace mdvt {
@@ -52,7 +54,7 @@ __device__ __forceinline__ float approx_div(float a, float b) {
 constexpr float kRowWindow = 0.505f;
 
 // MASK_MODE: 0 none, 1 u8 {0,255}, 2 u8x3 (bg colour / black)
-template <int MASK_MODE, int kConvThreads>
+template <int MASK_MODE, int kConvThreads, int U>
 __global__ void __launch_bounds__(kConvThreads)
     stereo_conv_rows_kernel(const uint8_t *__restrict__ depth_rgb, const uint8_t *__restrict__ colour_rgb, int n_units, int width, int height,
                             const mdvt_conv_frame *__restrict__ frames, uint32_t bg_rgb, uint32_t fill_rgb, int collide,
@@ -67,7 +69,6 @@ __global__ void __launch_bounds__(kConvThreads)
     uint32_t *s_qcount = reinterpret_cast<uint32_t *>(smem);  // bytes [0, 4)
     const int tid = threadIdx.x;
     const uint32_t row_bytes = 3u * width;
-    const float u_max = (float)(width - 1);
     const bool vec4 = (width % 4 == 0) && (!out_depth || (reinterpret_cast<uintptr_t>(out_depth) & 15) == 0);
 
     for (int k = tid; k < 2 * width; k += kConvThreads) s_z[k] = kEmpty64;
@@ -124,16 +125,19 @@ __global__ void __launch_bounds__(kConvThreads)
                 const float rz = rcp_refined(Zv);
                 const float u = __fadd_rn(div_rn_by(__fmul_rn(vfx, Xv), Zv, rz), vcx);
                 const float v = __fadd_rn(div_rn_by(__fmul_rn(vfy, Y), Zv, rz), vcy);
-                const float ur = rintf(u), vr = rintf(v);
-                if (Zv > near_plane && vr == fr && ur >= 0.0f && ur <= u_max) {
+                // rint + bounds as in splat_pixel(): the integer sits in the mantissa of u + 1.5 * 2^23; anything out of
+                // range, infinite or NaN becomes a huge unsigned value
+                const uint32_t ui = (uint32_t)(__float_as_int(__fadd_rn(u, 12582912.0f)) - 0x4B400000);
+                const int vi = __float_as_int(__fadd_rn(v, 12582912.0f)) - 0x4B400000;
+                if (Zv > near_plane && vi == r && ui < (uint32_t)width) {
                     const unsigned long long key =
                         ((unsigned long long)__float_as_uint(Zv) << 32) | ((uint32_t)(i - i_base) << 12) | (uint32_t)j;
-                    atomicMin(&zb[(int)ur], key);
+                    atomicMin(&zb[ui], key);
                 }
             };
             if (tid == 0) *s_qcount = 0;
             __syncthreads();
-            constexpr int U = 4;  // columns per thread and pass: all 2U byte loads are issued before the first is used
+            // U columns per thread and pass: all 2U byte loads are issued before the first is used
             for (int jb = tid; jb < width; jb += U * kConvThreads) {
                 int i0[U];
                 uint32_t red[U], blue[U];
@@ -311,10 +315,19 @@ extern "C" int mdvt_stereo_conv_rows(const uint8_t *depth_rgb, const uint8_t *co
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // 256 threads per CTA (4 CTAs/SM at 1080p): measured 30.5 us/frame; 128 -> 44.9, 160 -> 39.0, 320 -> 31.9.  Unlike the
     // row-local kernel this one is bound by instruction issue and global-load latency, so it wants the warps.
-#define LAUNCH(M) LAUNCH_T(M, 256)
-#define LAUNCH_T(M, kConvThreads)                                                                                                   \
+    static int conv_u = 0;  // columns in flight per thread: MDVT_CONV_U = 4 | 8 (development switch)
+    if (!conv_u) {
+        const char *e = getenv("MDVT_CONV_U");
+        conv_u = (e && atoi(e) == 8) ? 8 : 4;  // measured equal (30.6 vs 30.7 us per 1080p frame): loads in flight are not the limiter
+    }
+#define LAUNCH(M)                     \
+    do {                              \
+        if (conv_u == 4) LAUNCH_T(M, 256, 4); \
+        else LAUNCH_T(M, 256, 8);     \
+    } while (0)
+#define LAUNCH_T(M, kConvThreads, UU)                                                                                                   \
     do {                                                                                                                            \
-        auto kernel = stereo_conv_rows_kernel<M, kConvThreads>;                                                                                   \
+        auto kernel = stereo_conv_rows_kernel<M, kConvThreads, UU>;                                                                                   \
         MDVT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));                          \
         int ctas = 0;                                                                                                               \
         MDVT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kernel, kConvThreads, L.total));                         \
