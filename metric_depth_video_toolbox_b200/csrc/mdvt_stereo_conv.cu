@@ -139,13 +139,15 @@ __global__ void __launch_bounds__(kConvThreads)
             __syncthreads();
             // U columns per thread and pass: all 2U byte loads are issued before the first is used
             for (int jb = tid; jb < width; jb += U * kConvThreads) {
-                int i0[U];
+                int i0[U], i1[U];   // nearest source row; neighbour row that may also round into r (-1: none)
                 uint32_t red[U], blue[U];
                 bool in0[U];
+                // (1) predictions of all U columns: pure arithmetic, nothing long-latency in between
 #pragma unroll
                 for (int k = 0; k < U; ++k) {
                     const int j = jb + k * kConvThreads;
                     in0[k] = false;
+                    i1[k] = -1;
                     if (j >= width) continue;
                     // prediction (approximate on purpose; the window below absorbs its error): g = Zv / z of this column
                     const float g = __fmaf_rn(m8, __fmul_rn(__fsub_rn((float)j, scx), inv_sfx), m10);
@@ -155,18 +157,26 @@ __global__ void __launch_bounds__(kConvThreads)
                     const float step = __fmul_rn(ratio, inv_g);                                            // d v' / d i
                     const float v0 = __fsub_rn(__fmaf_rn(__fsub_rn((float)i0[k], scy), step, vcy), fr);    // predicted v' - r of row i0
                     in0[k] = (uint32_t)i0[k] < (uint32_t)height;
+                    if (fabsf(v0) >= __fsub_rn(step, kRowWindow)) {  // the neighbour's predicted v' is within the window of r too
+                        const int cand = v0 < 0.0f ? i0[k] + 1 : i0[k] - 1;
+                        if ((uint32_t)cand < (uint32_t)height) i1[k] = cand;
+                    }
+                }
+                // (2) all 2U byte loads back to back (v3 interleaved them with the queue's warp-aggregated atomics and ncu
+                //     showed every column's prediction waiting on the previous column's loads: 27 % of the stall samples)
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
                     if (in0[k]) {
-                        const uint8_t *px = dframe + ((uint32_t)i0[k] * (uint32_t)width + (uint32_t)j) * 3u;
+                        const uint8_t *px = dframe + ((uint32_t)i0[k] * (uint32_t)width + (uint32_t)(jb + k * kConvThreads)) * 3u;
                         red[k] = __ldg(px);
                         blue[k] = __ldg(px + 2);
                     }
-                    if (fabsf(v0) >= __fsub_rn(step, kRowWindow)) {  // the neighbour's predicted v' is within the window of r too
-                        const int i1 = v0 < 0.0f ? i0[k] + 1 : i0[k] - 1;
-                        if ((uint32_t)i1 < (uint32_t)height) {
-                            s_queue[atomicAdd(s_qcount, 1u)] = ((uint32_t)(i1 - i_base) << 12) | (uint32_t)j;  // <= one per column
-                        }
-                    }
                 }
+                // (3) second candidates -> queue (<= one per column)
+#pragma unroll
+                for (int k = 0; k < U; ++k)
+                    if (i1[k] >= 0) s_queue[atomicAdd(s_qcount, 1u)] = ((uint32_t)(i1[k] - i_base) << 12) | (uint32_t)(jb + k * kConvThreads);
+                // (4) exact arithmetic
 #pragma unroll
                 for (int k = 0; k < U; ++k)
                     if (in0[k]) evaluate(i0[k], jb + k * kConvThreads, red[k], blue[k]);
