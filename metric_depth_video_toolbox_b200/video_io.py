@@ -39,10 +39,12 @@ def _is_ffv1(cap) -> bool:
 
 
 def default_decoders(world_size: int = 1) -> int:
+    """Decode threads per input video.  1: every input has its own sequential decoder.  More (MDVT_READER_THREADS) makes
+    each decoder seek to its chunks -- measured counter-productive with OpenCV, whose frame-exact seek lands on the key
+    frame at or before (target - 16) and decodes forward from there (~22 frames per seek with a GOP of 12): 3.5 -> 1.2
+    frames/s on two 4K inputs.  Kept for containers / builds with cheap exact seeks."""
     env = os.environ.get("MDVT_READER_THREADS")
-    if env:
-        return max(1, int(env))
-    return max(1, min(4, (os.cpu_count() or 2) // (4 * max(1, world_size))))
+    return max(1, int(env)) if env else 1
 
 
 class _DecodeWorker(threading.Thread):
@@ -118,7 +120,7 @@ class ChunkReader:
         self._workers = [None if p is None else [_DecodeWorker(p, g) for _ in range(self.decoders)] for p, g in zip(self.paths, self.grey)]
         self._q: "queue.Queue" = queue.Queue(maxsize=max(1, depth))
         self._free: "queue.Queue" = queue.Queue()
-        for _ in range(depth + 2 + self.decoders):
+        for _ in range(depth + 1 + self.decoders):   # pinned: 300 MB per 12-frame 4K chunk, keep the ring short
             self._free.put(self._alloc())
         self._tickets: "queue.Queue" = queue.Queue(maxsize=max(1, depth) + self.decoders)
         self._threads = [threading.Thread(target=self._dispatch, daemon=True), threading.Thread(target=self._collect, daemon=True)]
