@@ -279,3 +279,18 @@ def test_mkv_join_refuses_a_run_that_does_not_start_on_a_key_frame(tmp_path):
     with pytest.raises(mkv_join.MkvError):
         mkv_join.join([(p, 5), (p, 5)], str(tmp_path / "bad.mkv"), 24.0)   # packet 5 is inside a GOP
     assert mkv_join.join([(p, 12), (p, 8)], str(tmp_path / "ok.mkv"), 24.0) == 20
+
+
+@pytest.mark.parametrize("fps", [23.976, 29.97, 59.94, 12.5])
+def test_parallel_writer_keeps_fractional_frame_rates(tmp_path, fps):
+    """The joined file reports the frame rate and frame count of a single-writer file (verify_and_move checks the count)."""
+    from metric_depth_video_toolbox_b200 import video_io
+
+    frames = _noise_clip(40, seed=4)
+    single, joined = str(tmp_path / "s.mkv"), str(tmp_path / "p.mkv")
+    video_io.write_clip(single, frames, fps)
+    w = video_io.ParallelWriter(joined, fps, (64, 48), lanes=3)
+    w.write(frames)
+    w.close()
+    assert video_io.video_info(joined) == video_io.video_info(single) == (64, 48, fps, 40)
+    assert np.array_equal(video_io.read_clip(joined), frames)
