@@ -234,7 +234,7 @@ class ChunkWriter:
             raise self._err
 
 
-GOP = 12  # key-frame interval of OpenCV's FFmpeg writer (AVCodecContext.gop_size): lanes are filled in whole GOPs
+GOP = 12  # key-frame interval of OpenCV's FFmpeg writer (AVCodecContext.gop_size): rank ranges start on key frames of the inputs
 
 
 def default_lanes(world_size: int = 1) -> int:
@@ -245,28 +245,46 @@ def default_lanes(world_size: int = 1) -> int:
 
 
 class ParallelWriter:
-    """An FFV1 .mkv written by `lanes` cv2.VideoWriters at once.  The single-threaded FFV1 entropy coder behind
+    """An FFV1 .mkv written by up to `lanes` cv2.VideoWriters at once.  The single-threaded FFV1 entropy coder behind
     cv2.VideoWriter is the end-to-end limiter of every script (about 0.45 s per 3840x1080 frame); here the clip is cut
-    into blocks of GOP frames, block b goes to lane b % lanes (its own writer thread and lane file, so each lane file
-    is a sequence of closed GOPs), and `close()` stitches the encoded packets back into display order with
-    `mkv_join.join` -- no re-encode, same container / codec parameters, frames decode bit-identically.
-    join_on_close=False leaves the lane files and a `<path>.plan.json` for a later join of several writers' lanes
+    into blocks of `block` frames, every block is encoded into its own small file by a worker thread (a fresh writer:
+    the block starts with a key frame whatever its length), and `close()` stitches the encoded packets back into display
+    order with `mkv_join.join` -- no re-encode, same container / codec parameters, frames decode bit-identically.
+    Small blocks keep the drain short (a 96-frame clip is 16 blocks for 16 cores, not 8 GOPs); FFV1 is intra-only, a key
+    frame merely resets the adaptive coder state, so the extra key frames cost about a per cent of file size.
+    join_on_close=False leaves the block files and a `<path>.plan.json` for a later join of several writers' blocks
     (the torchrun ranks of one job)."""
 
-    def __init__(self, path: str, fps: float, size: Tuple[int, int], lanes: Optional[int] = None, join_on_close: bool = True):
+    def __init__(self, path: str, fps: float, size: Tuple[int, int], lanes: Optional[int] = None, join_on_close: bool = True,
+                 block: int = 4):
+        from concurrent.futures import ThreadPoolExecutor
+
         self.path, self.fps, self.size, self.join_on_close = path, fps, size, join_on_close
-        n = default_lanes() if lanes is None else max(1, lanes)
-        self.lane_paths = [f"{path}.lane{k:02d}.mkv" for k in range(n)]
-        self.lane_writers = [ChunkWriter(p, "FFV1", fps, size, depth=1) for p in self.lane_paths]
+        self.lanes = default_lanes() if lanes is None else max(1, lanes)
+        self.block = max(1, block)
         self.plan: List[Tuple[str, int]] = []
         self.frames = 0
+        self._pool = ThreadPoolExecutor(max_workers=self.lanes)
+        self._slots = threading.Semaphore(2 * self.lanes)   # blocks encoded or waiting: bounds the host memory held
+        self._futures = []
         self._pending: List[np.ndarray] = []
         self._pending_n = 0
         self._rgb: Optional[bool] = None
-        self._block = 0
+
+    def _encode(self, block_path: str, frames: np.ndarray, rgb: bool):
+        cv2 = _cv2()
+        try:
+            w = cv2.VideoWriter(block_path, cv2.VideoWriter_fourcc(*"FFV1"), self.fps, self.size)
+            if not w.isOpened():
+                raise RuntimeError(f"cannot open an FFV1 writer for {block_path}")
+            for f in frames:
+                w.write(cv2.cvtColor(f, cv2.COLOR_RGB2BGR) if rgb else f)
+            w.release()
+        finally:
+            self._slots.release()
 
     def _emit(self, n: int):
-        """Send the first n pending frames to the next lane as one block."""
+        """Hand the first n pending frames to a worker as one block."""
         take, got = [], 0
         while got < n:
             a = self._pending[0]
@@ -280,10 +298,14 @@ class ParallelWriter:
                 self._pending[0] = a[need:]
                 got += need
         self._pending_n -= n
-        lane = self._block % len(self.lane_writers)
-        self.lane_writers[lane].write(take[0] if len(take) == 1 else np.concatenate(take), rgb=bool(self._rgb))
-        self.plan.append((self.lane_paths[lane], n))
-        self._block += 1
+        frames = np.concatenate(take) if len(take) > 1 else take[0].copy()   # own copy: the caller recycles its buffer
+        block_path = f"{self.path}.blk{len(self.plan):06d}.mkv"
+        self.plan.append((block_path, n))
+        self._slots.acquire()
+        for f in self._futures:   # surface a worker's failure early
+            if f.done() and f.exception() is not None:
+                raise f.exception()
+        self._futures.append(self._pool.submit(self._encode, block_path, frames, bool(self._rgb)))
 
     def write(self, frames, rgb: bool = True):
         arr = frames.numpy() if isinstance(frames, torch.Tensor) else np.asarray(frames)
@@ -295,27 +317,24 @@ class ParallelWriter:
             raise ValueError("one writer takes either RGB or BGR frames, not both")
         if arr.shape[0] == 0:
             return
-        # the caller may recycle its buffer after write() returns: blocks that are not sent right away are copied
         self._pending.append(arr)
         self._pending_n += arr.shape[0]
         self.frames += arr.shape[0]
-        while self._pending_n >= GOP:
-            self._emit(GOP)
-        self._pending = [a.copy() for a in self._pending]
+        while self._pending_n >= self.block:
+            self._emit(self.block)
+        self._pending = [a.copy() for a in self._pending]   # the remainder outlives the caller's buffer
 
     def close(self):
         if self._pending_n:
             self._emit(self._pending_n)
-        for w in self.lane_writers:
-            w.close()
+        for f in self._futures:
+            f.result()
+        self._pool.shutdown()
         if self.join_on_close:
             join_plans([self.plan], self.path, self.fps)
-            for p in self.lane_paths:  # lanes that never received a block
-                if os.path.exists(p):
-                    os.remove(p)
         else:
             with open(self.path + ".plan.json", "w") as fh:
-                json.dump({"fps": self.fps, "plan": self.plan, "lanes": self.lane_paths}, fh)
+                json.dump({"fps": self.fps, "plan": self.plan}, fh)
 
 
 def join_plans(plans: Sequence[Sequence[Tuple[str, int]]], out_path: str, fps: float, remove: bool = True) -> int:
@@ -333,15 +352,11 @@ def join_plans(plans: Sequence[Sequence[Tuple[str, int]]], out_path: str, fps: f
 
 
 def load_plan(path: str, remove: bool = True):
-    """The plan a ParallelWriter(join_on_close=False) left next to its lane files (+ lane files that hold no block)."""
+    """The plan a ParallelWriter(join_on_close=False) left next to its block files."""
     with open(path + ".plan.json") as fh:
         d = json.load(fh)
     if remove:
         os.remove(path + ".plan.json")
-        used = {p for p, _ in d["plan"]}
-        for p in d["lanes"]:
-            if p not in used and os.path.exists(p):
-                os.remove(p)
     return [(p, int(n)) for p, n in d["plan"]]
 
 
