@@ -60,7 +60,13 @@ def main(argv: Optional[List[str]] = None) -> int:
         raise Exception("input color_video does not exist")
     if not args.render or args.draw_frame != -1:
         raise NotImplementedError("the interactive Open3D viewer is a GUI feature; use --render")
-    for flag in ("mask_video", "background_ply", "show_camera"):
+    if args.mask_video:
+        # In the reference the flag only works together with --remove_edges: without it create_mesh_from_point_cloud reads
+        # `normals` before assignment (depth_map_tools.py:1346, UnboundLocalError); with it the result depends on the
+        # per-triangle 89-degree test of the mesh, which the point splat does not build.
+        raise NotImplementedError("--mask_video filters mesh triangles (and crashes the reference without --remove_edges); "
+                                  "the point-splat render path has no triangles to filter")
+    for flag in ("background_ply", "show_camera"):
         if getattr(args, flag):
             raise NotImplementedError(f"--{flag} adds scene objects the point-splat render path does not draw")
     transformations = None
