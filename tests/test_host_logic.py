@@ -294,3 +294,43 @@ def test_parallel_writer_keeps_fractional_frame_rates(tmp_path, fps):
     w.close()
     assert video_io.video_info(joined) == video_io.video_info(single) == (64, 48, fps, 40)
     assert np.array_equal(video_io.read_clip(joined), frames)
+
+
+def _random_mask_image(h, w, seed, holes, max_width):
+    """A pre-inpaint mask image like the GPU produces: black, green hole stripes, coded normals scattered in them."""
+    rng = np.random.default_rng(seed)
+    m = np.zeros((h, w, 3), np.uint8)
+    for _ in range(holes):
+        x, y = int(rng.integers(5, w - max_width - 5)), int(rng.integers(5, h - 40))
+        hh, ww = int(rng.integers(8, min(120, h - y - 2))), int(rng.integers(2, max_width))
+        m[y:y + hh, x:x + ww] = (0, 255, 0)
+        pts = int(rng.integers(hh // 2, hh * 2))
+        m[rng.integers(y, y + hh, pts), rng.integers(max(0, x - 1), min(w, x + ww + 1), pts)] = rng.integers(1, 255, (pts, 3)).astype(np.uint8)
+    return m
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_restricted_telea_area_gives_the_reference_hole_pixels(seed, monkeypatch):
+    """finish_mask inpaints only as far around the holes as can influence a hole pixel; the result must be the image the
+    reference's full inpaint area (everything that is not a coded normal) gives, byte for byte."""
+    from metric_depth_video_toolbox_b200 import infill
+
+    m = _random_mask_image(150, 260, 50 + seed, holes=4 + 3 * seed, max_width=6 + 4 * seed)
+    monkeypatch.delenv("MDVT_TELEA_FULL", raising=False)
+    fast = infill.finish_mask(m)
+    monkeypatch.setenv("MDVT_TELEA_FULL", "1")
+    full = infill.finish_mask(m)
+    assert np.array_equal(fast, full)
+    assert (fast != m).any()
+
+
+def test_restricted_telea_matches_the_reference_golden_masks():
+    """The golden pre-inpaint / final mask pairs were produced by the reference's own lines (stereo_rerender.py:740-819)."""
+    from metric_depth_video_toolbox_b200 import infill
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "infill_mask.npz"))
+    for tag in ("plain", "posed"):
+        assert np.array_equal(infill.finish_mask(g[f"{tag}_mask_pre_inpaint"]), g[f"{tag}_mask_final"]), tag
+    blank = np.zeros((40, 60, 3), np.uint8)
+    blank[5, 7] = (200, 100, 50)
+    assert np.array_equal(infill.finish_mask(blank), infill.masked_blur(blank))   # no hole: nothing to inpaint
