@@ -208,7 +208,13 @@ def run_ours(args):
         raise SystemExit("bench.py --impl ours needs a CUDA device: there is no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    saved_stdout = None
     if world > 1:
+        # stdout carries exactly ONE JSON line (the contract): NCCL prints its version banner to fd 1 when the box sets
+        # NCCL_DEBUG, so fd 1 points at stderr until the line is ready
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     n_frames = args.frames
 
@@ -326,8 +332,14 @@ def run_ours(args):
             "roofline": roofline, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks.summary()}
     if not args.no_cpu and world == 1:
         line["cpu_baseline"] = cpu_baseline(args.cpu_frames)
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     print(json.dumps(line), flush=True)
     if world > 1:
+        sys.stdout.flush()
+        os.dup2(2, 1)   # teardown messages, if any, do not follow the JSON line on stdout
         dist.destroy_process_group()
 
 
