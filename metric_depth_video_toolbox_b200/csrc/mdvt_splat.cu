@@ -308,14 +308,25 @@ static int resident_ctas(K kernel, int threads) {
 // writes fill colour and mask (ncu v4: the one-kernel-fits-all resolve spent 56 instructions per pixel).
 constexpr int kRowResolveThreads = 160;  // 640 px per CTA row chunk: divides 640 / 1280 / 1920 / 3840
 
+struct ViewStrides {  // plane of view v relative to view 0: z-buffer slots, RGB / mask bytes, depth floats
+    int64_t zbuf, rgb, mask, depth;
+};
+
 template <bool DEPTH>
 __global__ void __launch_bounds__(kRowResolveThreads)
     resolve_rows_kernel(unsigned long long *__restrict__ zbuf, const uint8_t *__restrict__ colour, int out_w, int out_h, uint32_t bg_rgb,
                         uint32_t fill_rgb, uint32_t flags, uint8_t *__restrict__ out_rgb, int64_t rgb_pitch, uint8_t *__restrict__ out_mask,
                         int64_t mask_pitch, float *__restrict__ out_depth, int64_t depth_pitch, const uint8_t *__restrict__ touched,
-                        uint8_t *__restrict__ touched_clear) {
+                        uint8_t *__restrict__ touched_clear, ViewStrides vs) {
     const int g = blockIdx.x * kRowResolveThreads + threadIdx.x;
     if (g >= out_w / 4) return;
+    if (blockIdx.z) {  // several views in one launch: view v = blockIdx.z works on planes v strides further on
+        const int64_t v = blockIdx.z;
+        zbuf += v * vs.zbuf;
+        if (out_rgb) out_rgb += v * vs.rgb;
+        if (out_mask) out_mask += v * vs.mask;
+        if (DEPTH) out_depth += v * vs.depth;
+    }
     const int col0 = g * 4;
     const bool collide = flags & MDVT_FLAG_BG_COLLIDE, reset = flags & MDVT_FLAG_RESET_ZBUF, mask_rgb = flags & MDVT_FLAG_MASK_RGB;
     const uint64_t keep = l2_keep_policy();
@@ -473,7 +484,7 @@ extern "C" int mdvt_splat_points(const float *xyz, int64_t n_points, const mdvt_
 static int launch_resolve(unsigned long long *zb, const uint8_t *colour_rgb, int out_w, int out_h, uint32_t bg_rgb, uint32_t fill_rgb,
                           uint32_t flags, uint8_t *out_rgb, int64_t rgb_pitch, uint8_t *out_mask, int64_t mask_pitch, float *out_depth,
                           int64_t depth_pitch, int32_t *out_ids, cudaStream_t st, const uint8_t *touched = nullptr,
-                          uint8_t *touched_clear = nullptr) {
+                          uint8_t *touched_clear = nullptr, int n_views = 1, ViewStrides vs = ViewStrides{0, 0, 0, 0}) {
     const int mask_bpp = (flags & MDVT_FLAG_MASK_RGB) ? 3 : 1;
     MDVT_REQUIRE(!out_rgb || rgb_pitch >= (int64_t)out_w * 3, "rgb_pitch %lld too small", (long long)rgb_pitch);
     MDVT_REQUIRE(!out_mask || mask_pitch >= (int64_t)out_w * mask_bpp, "mask_pitch %lld too small", (long long)mask_pitch);
@@ -498,21 +509,23 @@ static int launch_resolve(unsigned long long *zb, const uint8_t *colour_rgb, int
         if (!per_sm)
             per_sm = out_depth ? resident_ctas(resolve_rows_kernel<true>, kRowResolveThreads) : resident_ctas(resolve_rows_kernel<false>, kRowResolveThreads);
         const int col_blocks = (out_w / 4 + kRowResolveThreads - 1) / kRowResolveThreads;
-        int row_blocks = sm_count() * per_sm / col_blocks;
+        int row_blocks = sm_count() * per_sm / (col_blocks * n_views);
         if (row_blocks < 1) row_blocks = 1;
         if (row_blocks > (out_h + 1) / 2) row_blocks = (out_h + 1) / 2;
-        const dim3 grid(col_blocks, row_blocks);
+        const dim3 grid(col_blocks, row_blocks, n_views);
         if (out_depth)
             resolve_rows_kernel<true><<<grid, kRowResolveThreads, 0, st>>>(zb, colour_rgb, out_w, out_h, bg_rgb, fill_rgb, flags, out_rgb, rgb_pitch,
-                                                                          out_mask, mask_pitch, out_depth, depth_pitch, touched, touched_clear);
+                                                                          out_mask, mask_pitch, out_depth, depth_pitch, touched, touched_clear, vs);
         else
             resolve_rows_kernel<false><<<grid, kRowResolveThreads, 0, st>>>(zb, colour_rgb, out_w, out_h, bg_rgb, fill_rgb, flags, out_rgb, rgb_pitch,
-                                                                           out_mask, mask_pitch, out_depth, depth_pitch, touched, touched_clear);
+                                                                           out_mask, mask_pitch, out_depth, depth_pitch, touched, touched_clear, vs);
     } else if (vec4) {
+        MDVT_REQUIRE(n_views == 1, "several views per launch need the row form of the resolve");
         resolve_kernel<4><<<grid_of(((int64_t)out_w / 4 * out_h + 1) / 2, per_sm4), kThreads, 0, st>>>(
             zb, colour_rgb, out_w, out_h, bg_rgb, fill_rgb, flags, out_rgb, rgb_pitch, out_mask, mask_pitch, out_depth, depth_pitch, out_ids,
             touched, touched_clear);
     } else {
+        MDVT_REQUIRE(n_views == 1, "several views per launch need the row form of the resolve");
         resolve_kernel<1><<<grid_of((int64_t)out_w * out_h, per_sm1), kThreads, 0, st>>>(
             zb, colour_rgb, out_w, out_h, bg_rgb, fill_rgb, flags, out_rgb, rgb_pitch, out_mask, mask_pitch, out_depth, depth_pitch, out_ids,
             touched, touched_clear);
@@ -579,15 +592,30 @@ extern "C" int mdvt_render_views(const void *depth_src, int64_t depth_frame_stri
         if (int rc = pack_views(views_host + (int64_t)f * n_views, n_views, pack)) return rc;
         const uint8_t *dsrc = static_cast<const uint8_t *>(depth_src) + f * depth_frame_stride;
         if (int rc = launch_project_splat(dsrc, src, pack, nullptr, near_plane, out_w, out_h, 0, zb, nullptr, st)) return rc;
-        for (int v = 0; v < n_views; ++v) {
-            auto at = [&](const mdvt_plane_layout *L) -> uint8_t * {
-                return (L && L->base) ? static_cast<uint8_t *>(L->base) + f * L->frame_stride + v * L->view_stride : nullptr;
-            };
-            if (int rc = launch_resolve(zb + v * out_n, colour_rgb + f * colour_frame_stride, out_w, out_h, bg_rgb, fill_rgb,
-                                        flags | MDVT_FLAG_RESET_ZBUF, at(rgb_out), rgb_out->row_pitch, at(mask_out),
-                                        mask_out ? mask_out->row_pitch : 0, reinterpret_cast<float *>(at(depth_out)),
-                                        depth_out ? depth_out->row_pitch / 4 : 0, nullptr, st))
+        auto at = [&](const mdvt_plane_layout *L, int v) -> uint8_t * {
+            return (L && L->base) ? static_cast<uint8_t *>(L->base) + f * L->frame_stride + v * L->view_stride : nullptr;
+        };
+        const uint8_t *colour_f = colour_rgb + f * colour_frame_stride;
+        const int64_t mask_pitch = mask_out ? mask_out->row_pitch : 0, depth_pitch = depth_out ? depth_out->row_pitch / 4 : 0;
+        // all views in ONE launch (blockIdx.z) when every plane qualifies for the row form of the resolve
+        auto word_ok = [](const void *p, int64_t a, int64_t b) { return (reinterpret_cast<uintptr_t>(p) % 4 == 0) && a % 4 == 0 && b % 4 == 0; };
+        const bool one_launch = n_views > 1 && out_w % 4 == 0 && reinterpret_cast<uintptr_t>(zb) % 16 == 0 && out_n % 2 == 0 &&
+                                word_ok(at(rgb_out, 0), rgb_out->row_pitch, rgb_out->view_stride) &&
+                                (!at(mask_out, 0) || word_ok(at(mask_out, 0), mask_pitch, mask_out->view_stride)) &&
+                                (!at(depth_out, 0) || word_ok(at(depth_out, 0), 0, depth_out->view_stride));
+        if (one_launch) {
+            const ViewStrides vs{out_n, rgb_out->view_stride, mask_out ? mask_out->view_stride : 0, depth_out ? depth_out->view_stride / 4 : 0};
+            if (int rc = launch_resolve(zb, colour_f, out_w, out_h, bg_rgb, fill_rgb, flags | MDVT_FLAG_RESET_ZBUF, at(rgb_out, 0),
+                                        rgb_out->row_pitch, at(mask_out, 0), mask_pitch, reinterpret_cast<float *>(at(depth_out, 0)), depth_pitch,
+                                        nullptr, st, nullptr, nullptr, n_views, vs))
                 return rc;
+        } else {
+            for (int v = 0; v < n_views; ++v) {
+                if (int rc = launch_resolve(zb + v * out_n, colour_f, out_w, out_h, bg_rgb, fill_rgb, flags | MDVT_FLAG_RESET_ZBUF, at(rgb_out, v),
+                                            rgb_out->row_pitch, at(mask_out, v), mask_pitch, reinterpret_cast<float *>(at(depth_out, v)),
+                                            depth_pitch, nullptr, st))
+                    return rc;
+            }
         }
     }
     return MDVT_OK;
