@@ -334,3 +334,19 @@ def test_restricted_telea_matches_the_reference_golden_masks():
     blank = np.zeros((40, 60, 3), np.uint8)
     blank[5, 7] = (200, 100, 50)
     assert np.array_equal(infill.finish_mask(blank), infill.masked_blur(blank))   # no hole: nothing to inpaint
+
+
+def test_infill_finish_async_equals_finish_per_eye():
+    """The deferred (worker-pool) TELEA + blur tail produces, per eye, exactly what finish_mask gives."""
+    from metric_depth_video_toolbox_b200 import infill
+
+    frames = np.stack([np.concatenate([_random_mask_image(90, 128, 10 + k, 5, 12), _random_mask_image(90, 128, 20 + k, 7, 9)], axis=1)
+                       for k in range(3)])
+    im = infill.InfillMaskRenderer(None, workers=4)
+    deferred = im.finish_async(frames)
+    frames_before = frames.copy()
+    frames[:] = 0                      # the caller recycles its buffer right away
+    out = deferred.result()
+    for k in range(3):
+        for e in range(2):
+            assert np.array_equal(out[k, :, e * 128:(e + 1) * 128], infill.finish_mask(frames_before[k, :, e * 128:(e + 1) * 128]))
