@@ -238,7 +238,7 @@ typedef struct mdvt_lookat {
  * mdvt_view, 16-byte aligned; both stay valid for the caller to read back.  zbuf: one out_w x out_h plane, empty on
  * entry, left empty.  touched: mdvt_touched_bytes(out_w, out_h) bytes of scratch (per-segment "something was drawn
  * here" flags that let K3 skip the z-buffer traffic of empty regions).  The centroid kernels run on an internal second
- * stream forked from / joined to `stream` with events (legal under stream capture). */
+ * stream forked from / joined to `stream` with events. */
 MDVT_API int64_t mdvt_touched_bytes(int out_w, int out_h);
 MDVT_API int mdvt_novel_view_frames(const void *depth_src, int64_t depth_frame_stride, const uint8_t *colour_rgb,
                            int64_t colour_frame_stride, int n_frames, const mdvt_source *centroid_src_host,
