@@ -6,6 +6,8 @@
 // lowest source index" deterministically.  1080p stereo = 33 MB: resident in the 126 MB L2 (ncu: 0.5 MB of DRAM reads
 // per splat).  One 4K view = 66 MB does NOT stay resident next to the streams (ncu: 43 % L2 hit rate; the two-die L2
 // holds about half of its nominal size for one working set), which is what the touched-segment flags below are for.
+#include <mutex>
+
 #include "mdvt_common.cuh"
 
 namespace mdvt {
@@ -672,6 +674,9 @@ extern "C" int mdvt_novel_view_frames(const void *depth_src, int64_t depth_frame
     MDVT_REQUIRE(reinterpret_cast<uintptr_t>(views_dev) % 16 == 0, "views_dev must be 16-byte aligned");
     MDVT_REQUIRE(centroid_src->width == src->width && centroid_src->height == src->height, "the two source descriptions differ in size");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // the internal stream and its event ring are process-wide: calls from several host threads enqueue one after the other
+    static std::mutex aux_mutex;
+    std::lock_guard<std::mutex> aux_lock(aux_mutex);
     AuxStream *aux = nullptr;
     if (int rc = aux_for_current_device(&aux)) return rc;
     unsigned long long *zb = reinterpret_cast<unsigned long long *>(zbuf);
