@@ -178,6 +178,71 @@ def _write_cluster(out: BinaryIO, t_ms: int, blocks: Sequence[Tuple[int, bool, b
         out.write(b)
 
 
+def replace_codec_private(tracks: bytes, codec_private: bytes) -> bytes:
+    """The Tracks payload with the (single) TrackEntry's CodecPrivate replaced; element sizes rebuilt."""
+    out = b""
+    for eid, s, e in _children(tracks, 0, len(tracks)):
+        if eid != ID_TRACK_ENTRY:
+            out += _enc_id(eid) + _enc_size(e - s) + tracks[s:e]
+            continue
+        entry = b""
+        seen = False
+        for cid, cs, ce in _children(tracks, s, e):
+            if cid == ID_CODEC_PRIVATE:
+                entry += _element(ID_CODEC_PRIVATE, codec_private)
+                seen = True
+            else:
+                entry += _enc_id(cid) + _enc_size(ce - cs) + tracks[cs:ce]
+        if not seen:
+            entry += _element(ID_CODEC_PRIVATE, codec_private)
+        out += _element(ID_TRACK_ENTRY, entry)
+    return out
+
+
+def write_stream(out_path: str, ebml_header: bytes, tracks: bytes, packets, total: int, fps: float, frames_per_cluster: int = 24) -> int:
+    """Write one .mkv from an iterable of (payload bytes, is_key) in display order: Info with the right Duration, the
+    given Tracks payload, Clusters of SimpleBlocks that start on key frames, Cues per cluster."""
+    frame_ms = 1000.0 / fps
+    info = _uint(ID_TIMECODE_SCALE, 1000000) + _element(ID_MUXING_APP, b"mdvt-b200 mkv_join") + \
+        _element(ID_WRITING_APP, b"mdvt-b200") + _element(ID_DURATION, struct.pack(">d", total * frame_ms))
+    tmp = out_path + ".joining"
+    cues: List[Tuple[int, int]] = []  # (time ms, cluster position relative to the Segment payload)
+    with open(tmp, "wb") as out:
+        out.write(ebml_header)
+        out.write(_enc_id(ID_SEGMENT) + _enc_size(0, 8))  # patched below
+        seg_start = out.tell()
+        out.write(_element(ID_INFO, info))
+        out.write(_element(ID_TRACKS, tracks))
+        frame = 0
+        pending: List[Tuple[int, bool, bytes]] = []
+        cluster_t = 0
+
+        def flush():
+            nonlocal pending
+            if pending:
+                cues.append((cluster_t, out.tell() - seg_start))
+                _write_cluster(out, cluster_t, pending)
+                pending = []
+
+        for data, key in packets:
+            t = int(round(frame * frame_ms))
+            if key and len(pending) >= frames_per_cluster or (pending and t - cluster_t > 30000):
+                flush()
+            if not pending:
+                cluster_t = t
+            pending.append((t - cluster_t, key, data))
+            frame += 1
+        flush()
+        cue_body = b"".join(_element(ID_CUE_POINT, _uint(ID_CUE_TIME, t) + _element(
+            ID_CUE_TRACK_POSITIONS, _uint(ID_CUE_TRACK, 1) + _uint(ID_CUE_CLUSTER_POSITION, pos))) for t, pos in cues)
+        out.write(_element(ID_CUES, cue_body))
+        seg_size = out.tell() - seg_start
+        out.seek(seg_start - 8)
+        out.write(_enc_size(seg_size, 8))
+    os.replace(tmp, out_path)
+    return frame
+
+
 def join(plan: Sequence[Tuple[str, int]], out_path: str, fps: float, frames_per_cluster: int = 24) -> int:
     """Write `out_path` from the packets of the lane files: `plan` = [(lane file, n packets), ...] in display order,
     each lane file consumed front to back across its entries.  Every run taken from a lane must start with a key
@@ -194,30 +259,8 @@ def join(plan: Sequence[Tuple[str, int]], out_path: str, fps: float, frames_per_
             if lane.codec_private() != first.codec_private():
                 raise MkvError(f"{path}: codec parameters differ from {first.path}; the lanes cannot be joined at packet level")
     total = sum(n for _, n in plan)
-    frame_ms = 1000.0 / fps
-    info = _uint(ID_TIMECODE_SCALE, 1000000) + _element(ID_MUXING_APP, b"mdvt-b200 mkv_join") + \
-        _element(ID_WRITING_APP, b"mdvt-b200") + _element(ID_DURATION, struct.pack(">d", total * frame_ms))
-    info_el = _element(ID_INFO, info)
-    tracks_el = _element(ID_TRACKS, first.tracks)
-    tmp = out_path + ".joining"
-    cues: List[Tuple[int, int]] = []  # (time ms, cluster position relative to the Segment payload)
-    with open(tmp, "wb") as out:
-        out.write(first.ebml_header)
-        out.write(_enc_id(ID_SEGMENT) + _enc_size(0, 8))  # patched below
-        seg_start = out.tell()
-        out.write(info_el)
-        out.write(tracks_el)
-        frame = 0
-        pending: List[Tuple[int, bool, bytes]] = []
-        cluster_t = 0
 
-        def flush():
-            nonlocal pending
-            if pending:
-                cues.append((cluster_t, out.tell() - seg_start))
-                _write_cluster(out, cluster_t, pending)
-                pending = []
-
+    def packets():
         for path, n in plan:
             lane = lanes[path]
             at = cursor[path]
@@ -226,23 +269,14 @@ def join(plan: Sequence[Tuple[str, int]], out_path: str, fps: float, frames_per_
             if n and not lane.packets[at][2]:
                 raise MkvError(f"{path}: packet {at} starts a run but is not a key frame")
             for k in range(n):
-                key = lane.packets[at + k][2]
-                t = int(round(frame * frame_ms))
-                if key and len(pending) >= frames_per_cluster or (pending and t - cluster_t > 30000):
-                    flush()
-                if not pending:
-                    cluster_t = t
-                pending.append((t - cluster_t, key, lane.payload(at + k)))
-                frame += 1
+                yield lane.payload(at + k), lane.packets[at + k][2]
             cursor[path] = at + n
-        flush()
-        cue_body = b"".join(_element(ID_CUE_POINT, _uint(ID_CUE_TIME, t) + _element(
-            ID_CUE_TRACK_POSITIONS, _uint(ID_CUE_TRACK, 1) + _uint(ID_CUE_CLUSTER_POSITION, pos))) for t, pos in cues)
-        out.write(_element(ID_CUES, cue_body))
-        seg_size = out.tell() - seg_start
-        out.seek(seg_start - 8)
-        out.write(_enc_size(seg_size, 8))
-    for lane in lanes.values():
-        lane.close()
-    os.replace(tmp, out_path)
-    return total
+
+    try:
+        written = write_stream(out_path, first.ebml_header, first.tracks, packets(), total, fps, frames_per_cluster)
+    finally:
+        for lane in lanes.values():
+            lane.close()
+        if os.path.exists(out_path + ".joining"):
+            os.remove(out_path + ".joining")
+    return written
