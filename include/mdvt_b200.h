@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MDVT_ABI_VERSION 6
+#define MDVT_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define MDVT_API __attribute__((visibility("default")))
@@ -325,6 +325,34 @@ typedef struct mdvt_conv_frame {
 MDVT_API int mdvt_stereo_conv_rows(const uint8_t *depth_rgb, const uint8_t *colour_rgb, int n_frames, int width, int height,
                           const mdvt_conv_frame *frames_dev, uint32_t bg_rgb, uint32_t fill_rgb, uint32_t flags,
                           uint8_t *out_sbs, uint8_t *out_mask, float *out_depth, void *stream);
+
+/* ---- FFV1 result-video encoder -----------------------------------------------------------------------------------------
+ * Replaces the entropy coder behind the reference's cv2.VideoWriter(fourcc "FFV1") result writers
+ * (stereo_rerender.py:420-442,941; depth_frames_helper.py:125-161; 3d_view_depthfile.py:118-127), i.e. libavcodec's FFV1
+ * version 3 encoder with the parameters OpenCV selects (Golomb-Rice coder, RGB colourspace with the JPEG2000 RCT, 8 bit,
+ * per-slice CRC), with two differences that keep the stream standard and its decoded frames bit-identical: every frame
+ * is a key frame, and a frame is cut into nh x nv (<= 1024) slices instead of 2 x 2 -- one device thread codes one slice.
+ * alpha = 1 adds the constant-255 alpha plane OpenCV's BGRA input produces; alpha = 0 writes the 3-plane stream. */
+
+/* HOST function, no device needed.  Writes the codec configuration record (Matroska CodecPrivate; <= 64 bytes) and the
+ * range-coded header of each of the nh * nv slices (16 bytes reserved per slice; header_len_host[s] bytes used). */
+MDVT_API int mdvt_ffv1_stream_setup(int width, int height, int nh, int nv, int alpha, uint8_t *config_host, int config_capacity,
+                           int *config_len, uint8_t *headers_host, int32_t *header_len_host);
+
+/* Bytes to reserve per slice (worst case of the coder, a multiple of 16), and bytes of coder state for a batch; -1 on
+ * bad arguments. */
+MDVT_API int64_t mdvt_ffv1_slice_capacity(int width, int height, int nh, int nv, int alpha);
+MDVT_API int64_t mdvt_ffv1_state_bytes(int n_frames, int nh, int nv, int alpha);
+
+/* Encodes n_frames u8x3 frames (RGB order, or BGR with bgr_order = 1).  headers / header_len: DEVICE copies of what
+ * mdvt_ffv1_stream_setup wrote.  states: mdvt_ffv1_state_bytes scratch.  slices: n_frames * nh * nv * capacity bytes of
+ * scratch.  Results: sizes[f * S + s] = bytes of slice s of frame f (S = nh * nv), offsets[f * S + s] = its position in
+ * `packed`, offsets[n_frames * S] = total bytes; packed[offsets[f * S] .. offsets[(f + 1) * S]) is the packet of frame f,
+ * ready for a Matroska SimpleBlock with the key flag.  `packed` must hold n_frames * S * capacity bytes. */
+MDVT_API int mdvt_ffv1_encode_frames(const uint8_t *frames, int64_t frame_stride, int64_t row_pitch, int n_frames, int width,
+                            int height, int nh, int nv, int alpha, int bgr_order, const uint8_t *headers,
+                            const int32_t *header_len, void *states, uint8_t *slices, int64_t capacity, int32_t *sizes,
+                            int64_t *offsets, uint8_t *packed, void *stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,164 @@
+"""FFV1 result videos coded on the device (`mdvt_ffv1_encode_frames`, csrc/mdvt_ffv1.cu) and muxed here.
+
+The reference writes every result through `cv2.VideoWriter(..., fourcc "FFV1", ...)` (stereo_rerender.py:420-442,941;
+depth_frames_helper.py:125-161; 3d_view_depthfile.py:118-127): ~0.45 core-seconds of entropy coding per 3840x1080 frame,
+which caps the scripts at a few frames/s whatever renders the frames.  Here the rendered frames never
+leave the device uncompressed: one thread codes one FFV1 slice (up to 1024 per frame, a batch of frames per launch), the
+slices are compacted into packets on the device, and only the packets cross PCIe; `mkv_join.StreamWriter` puts them in a
+Matroska file whose header and track description are the ones OpenCV/FFmpeg write for that size and rate, with the codec
+configuration record replaced by the one of this stream.  The stream is standard FFV1 version 3 (same coder, colour
+transform, quant tables and CRC as OpenCV's files; every frame a key frame, more slices) and decodes bit-identically.
+
+There is no CPU implementation: without the library / a device the encoder raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import tempfile
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib, mkv_join
+
+HEADER_STRIDE = 16
+
+
+def slice_grid(width: int, height: int, target_pixels: int = 4096) -> Tuple[int, int]:
+    """Slices per row / column: as many as FFV1 allows (1024) while a slice keeps about target_pixels pixels -- the
+    per-slice coder state needs something to adapt on -- and is roughly square (fewest border samples)."""
+    total = max(1, min(1024, (width * height) // max(1, target_pixels)))
+    nv = max(1, min(height, total, int(round((total * height / width) ** 0.5))))
+    nh = max(1, min(width, total // nv))
+    return nh, nv
+
+
+def stream_setup(width: int, height: int, nh: int, nv: int, alpha: bool = False):
+    """(configuration record bytes, slice headers (S, 16) uint8, header lengths (S,) int32) -- host arrays."""
+    lib = _lib.load()
+    config = (C.c_uint8 * 64)()
+    n = C.c_int(0)
+    headers = np.zeros((nh * nv, HEADER_STRIDE), np.uint8)
+    lens = np.zeros(nh * nv, np.int32)
+    _lib.check(lib.mdvt_ffv1_stream_setup(width, height, nh, nv, int(alpha), C.addressof(config), 64, C.byref(n),
+                                          headers.ctypes.data, lens.ctypes.data))
+    return bytes(config[:n.value]), headers, lens
+
+
+class Ffv1Encoder:
+    """Device buffers + stream constants for frames of one size; `encode` turns a batch of device frames into packets."""
+
+    def __init__(self, width: int, height: int, device, max_frames: int = 8, slices: Optional[Tuple[int, int]] = None,
+                 alpha: bool = False):
+        self.lib = _lib.load()
+        self.width, self.height, self.alpha = int(width), int(height), bool(alpha)
+        self.nh, self.nv = slices if slices is not None else slice_grid(width, height)
+        self.per_frame = self.nh * self.nv
+        self.max_frames = int(max_frames)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.MdvtError(-4, "the FFV1 encoder runs on a CUDA device only")
+        self.config, headers, lens = stream_setup(width, height, self.nh, self.nv, alpha)
+        self.capacity = int(self.lib.mdvt_ffv1_slice_capacity(width, height, self.nh, self.nv, int(alpha)))
+        state_bytes = int(self.lib.mdvt_ffv1_state_bytes(self.max_frames, self.nh, self.nv, int(alpha)))
+        if self.capacity <= 0 or state_bytes < 0:
+            raise ValueError(f"bad FFV1 stream parameters {width}x{height}, {self.nh}x{self.nv} slices")
+        n_slices = self.max_frames * self.per_frame
+        dev = self.device
+        self.headers = torch.from_numpy(headers).to(dev)
+        self.header_len = torch.from_numpy(lens).to(dev)
+        self.states = torch.empty(state_bytes, dtype=torch.uint8, device=dev)
+        self.slices = torch.empty(n_slices * self.capacity, dtype=torch.uint8, device=dev)
+        self.packed = torch.empty(n_slices * self.capacity, dtype=torch.uint8, device=dev)
+        self.sizes = torch.empty(n_slices, dtype=torch.int32, device=dev)
+        self.offsets = torch.empty(n_slices + 1, dtype=torch.int64, device=dev)
+        self._host = torch.empty(0, dtype=torch.uint8).pin_memory()
+
+    def encode_device(self, frames: torch.Tensor, rgb: bool = True):
+        """frames: (n <= max_frames, H, W, 3) uint8 on the device.  Enqueues the encode on the current stream and
+        returns (packed device bytes, offsets device int64 (n * S + 1,)) -- views of this encoder's buffers."""
+        if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[3] != 3 or not frames.is_cuda:
+            raise TypeError("expected a CUDA uint8 tensor (n, H, W, 3)")
+        n, h, w = int(frames.shape[0]), int(frames.shape[1]), int(frames.shape[2])
+        if (h, w) != (self.height, self.width) or n > self.max_frames:
+            raise ValueError(f"encoder built for <= {self.max_frames} frames of {self.width}x{self.height}, got {n} of {w}x{h}")
+        if frames.stride(3) != 1 or frames.stride(2) != 3:
+            frames = frames.contiguous()
+        stream = torch.cuda.current_stream(frames.device).cuda_stream
+        _lib.check(self.lib.mdvt_ffv1_encode_frames(
+            frames.data_ptr(), frames.stride(0), frames.stride(1), n, w, h, self.nh, self.nv, int(self.alpha), 0 if rgb else 1,
+            self.headers.data_ptr(), self.header_len.data_ptr(), self.states.data_ptr(), self.slices.data_ptr(), self.capacity,
+            self.sizes.data_ptr(), self.offsets.data_ptr(), self.packed.data_ptr(), stream))
+        return self.packed, self.offsets[: n * self.per_frame + 1]
+
+    def encode(self, frames: torch.Tensor, rgb: bool = True):
+        """-> list of n packets (bytes), one per frame.  Two device-to-host copies: the offsets, then the used bytes."""
+        n = int(frames.shape[0])
+        if n == 0:
+            return []
+        packed, offsets = self.encode_device(frames, rgb)
+        bounds = offsets[:: self.per_frame].cpu().numpy()   # synchronises with the encode
+        total = int(bounds[-1])
+        if self._host.numel() < total:
+            self._host = torch.empty(max(total, 2 * self._host.numel()), dtype=torch.uint8).pin_memory()
+        self._host[:total].copy_(packed[:total])
+        buf = self._host.numpy()
+        return [buf[int(bounds[k]):int(bounds[k + 1])].tobytes() for k in range(n)]
+
+
+def container_template(width: int, height: int, fps: float):
+    """(EBML header, Tracks payload) of the file OpenCV/FFmpeg write for an FFV1 video of this size and rate."""
+    import cv2
+
+    fd, path = tempfile.mkstemp(suffix=".mkv", prefix="mdvt_ffv1_template_")
+    os.close(fd)
+    try:
+        w = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"FFV1"), fps, (width, height))
+        if not w.isOpened():
+            raise RuntimeError("cannot open an FFV1 writer for the container template")
+        w.write(np.zeros((height, width, 3), np.uint8))
+        w.release()
+        pk = mkv_join.MkvPackets(path)
+        out = pk.ebml_header, pk.tracks
+        pk.close()
+        return out
+    finally:
+        if os.path.exists(path):
+            os.remove(path)
+
+
+class GpuFfv1Writer:
+    """`cv2.VideoWriter(path, FFV1, fps, size)` for frames that live on the device.  write() takes (n, H, W, 3) uint8
+    tensors (device; host tensors / arrays are uploaded), RGB by default; close() finishes the file."""
+
+    def __init__(self, path: str, fps: float, size: Tuple[int, int], device=None, batch: int = 8,
+                 slices: Optional[Tuple[int, int]] = None, alpha: bool = False):
+        self.path, self.fps, self.size = path, fps, (int(size[0]), int(size[1]))
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.enc = Ffv1Encoder(self.size[0], self.size[1], self.device, max_frames=batch, slices=slices, alpha=alpha)
+        header, tracks = container_template(self.size[0], self.size[1], fps)
+        self._mux = mkv_join.StreamWriter(path, header, mkv_join.replace_codec_private(tracks, self.enc.config), fps)
+        self.frames = 0
+        self.bytes = 0
+
+    def write(self, frames, rgb: bool = True):
+        t = frames if isinstance(frames, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(frames))
+        if t.dim() == 3:
+            t = t[None]
+        if tuple(t.shape[1:3]) != (self.size[1], self.size[0]):
+            raise ValueError(f"frames are {t.shape[2]}x{t.shape[1]}, writer expects {self.size[0]}x{self.size[1]}")
+        if not t.is_cuda:
+            t = t.to(self.device, non_blocking=True)
+        for a in range(0, int(t.shape[0]), self.enc.max_frames):
+            for pkt in self.enc.encode(t[a:a + self.enc.max_frames], rgb):
+                self._mux.add(pkt, True)
+                self.bytes += len(pkt)
+                self.frames += 1
+
+    def close(self) -> int:
+        return self._mux.close()
+
+    def abort(self):
+        self._mux.abort()

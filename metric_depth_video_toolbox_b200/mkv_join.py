@@ -199,48 +199,82 @@ def replace_codec_private(tracks: bytes, codec_private: bytes) -> bytes:
     return out
 
 
-def write_stream(out_path: str, ebml_header: bytes, tracks: bytes, packets, total: int, fps: float, frames_per_cluster: int = 24) -> int:
-    """Write one .mkv from an iterable of (payload bytes, is_key) in display order: Info with the right Duration, the
-    given Tracks payload, Clusters of SimpleBlocks that start on key frames, Cues per cluster."""
-    frame_ms = 1000.0 / fps
-    info = _uint(ID_TIMECODE_SCALE, 1000000) + _element(ID_MUXING_APP, b"mdvt-b200 mkv_join") + \
-        _element(ID_WRITING_APP, b"mdvt-b200") + _element(ID_DURATION, struct.pack(">d", total * frame_ms))
-    tmp = out_path + ".joining"
-    cues: List[Tuple[int, int]] = []  # (time ms, cluster position relative to the Segment payload)
-    with open(tmp, "wb") as out:
+class StreamWriter:
+    """One .mkv written packet by packet in display order: Info (Duration patched on close), the given Tracks payload,
+    Clusters of SimpleBlocks that start on key frames, Cues per cluster.  The file appears under its name on close()."""
+
+    def __init__(self, out_path: str, ebml_header: bytes, tracks: bytes, fps: float, frames_per_cluster: int = 24):
+        self.out_path, self.tmp = out_path, out_path + ".joining"
+        self.frame_ms = 1000.0 / fps
+        self.frames_per_cluster = frames_per_cluster
+        self.frames = 0
+        self._cues: List[Tuple[int, int]] = []  # (time ms, cluster position relative to the Segment payload)
+        self._pending: List[Tuple[int, bool, bytes]] = []
+        self._cluster_t = 0
+        self._out = open(self.tmp, "wb")
+        out = self._out
         out.write(ebml_header)
-        out.write(_enc_id(ID_SEGMENT) + _enc_size(0, 8))  # patched below
-        seg_start = out.tell()
-        out.write(_element(ID_INFO, info))
+        out.write(_enc_id(ID_SEGMENT) + _enc_size(0, 8))  # patched on close
+        self._seg_start = out.tell()
+        info = _uint(ID_TIMECODE_SCALE, 1000000) + _element(ID_MUXING_APP, b"mdvt-b200 mkv_join") + \
+            _element(ID_WRITING_APP, b"mdvt-b200")
+        duration = _element(ID_DURATION, struct.pack(">d", 0.0))
+        out.write(_enc_id(ID_INFO) + _enc_size(len(info) + len(duration)) + info)
+        self._duration_at = out.tell() + len(duration) - 8
+        out.write(duration)
         out.write(_element(ID_TRACKS, tracks))
-        frame = 0
-        pending: List[Tuple[int, bool, bytes]] = []
-        cluster_t = 0
 
-        def flush():
-            nonlocal pending
-            if pending:
-                cues.append((cluster_t, out.tell() - seg_start))
-                _write_cluster(out, cluster_t, pending)
-                pending = []
+    def _flush(self):
+        if self._pending:
+            self._cues.append((self._cluster_t, self._out.tell() - self._seg_start))
+            _write_cluster(self._out, self._cluster_t, self._pending)
+            self._pending = []
 
-        for data, key in packets:
-            t = int(round(frame * frame_ms))
-            if key and len(pending) >= frames_per_cluster or (pending and t - cluster_t > 30000):
-                flush()
-            if not pending:
-                cluster_t = t
-            pending.append((t - cluster_t, key, data))
-            frame += 1
-        flush()
+    def add(self, data: bytes, key: bool = True):
+        t = int(round(self.frames * self.frame_ms))
+        if key and len(self._pending) >= self.frames_per_cluster or (self._pending and t - self._cluster_t > 30000):
+            self._flush()
+        if not self._pending:
+            self._cluster_t = t
+        self._pending.append((t - self._cluster_t, key, data))
+        self.frames += 1
+
+    def abort(self):
+        if self._out is not None:
+            self._out.close()
+            self._out = None
+            if os.path.exists(self.tmp):
+                os.remove(self.tmp)
+
+    def close(self) -> int:
+        out = self._out
+        self._flush()
         cue_body = b"".join(_element(ID_CUE_POINT, _uint(ID_CUE_TIME, t) + _element(
-            ID_CUE_TRACK_POSITIONS, _uint(ID_CUE_TRACK, 1) + _uint(ID_CUE_CLUSTER_POSITION, pos))) for t, pos in cues)
+            ID_CUE_TRACK_POSITIONS, _uint(ID_CUE_TRACK, 1) + _uint(ID_CUE_CLUSTER_POSITION, pos))) for t, pos in self._cues)
         out.write(_element(ID_CUES, cue_body))
-        seg_size = out.tell() - seg_start
-        out.seek(seg_start - 8)
+        seg_size = out.tell() - self._seg_start
+        out.seek(self._seg_start - 8)
         out.write(_enc_size(seg_size, 8))
-    os.replace(tmp, out_path)
-    return frame
+        out.seek(self._duration_at)
+        out.write(struct.pack(">d", self.frames * self.frame_ms))
+        out.close()
+        self._out = None
+        os.replace(self.tmp, self.out_path)
+        return self.frames
+
+
+def write_stream(out_path: str, ebml_header: bytes, tracks: bytes, packets, total: int, fps: float, frames_per_cluster: int = 24) -> int:
+    """Write one .mkv from an iterable of (payload bytes, is_key) in display order (see StreamWriter)."""
+    w = StreamWriter(out_path, ebml_header, tracks, fps, frames_per_cluster)
+    try:
+        for data, key in packets:
+            w.add(data, key)
+        if w.frames != total:
+            raise MkvError(f"{out_path}: {w.frames} packets written, {total} expected")
+        return w.close()
+    except BaseException:
+        w.abort()
+        raise
 
 
 def join(plan: Sequence[Tuple[str, int]], out_path: str, fps: float, frames_per_cluster: int = 24) -> int:

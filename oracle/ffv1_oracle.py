@@ -237,7 +237,7 @@ class SliceState:
     def __init__(self, cfg):
         self.states = None  # per plane-context list of VlcState lists
     def reset(self, cfg, qidx):
-        self.states = [[VlcState() for _ in range(cfg["context_count"][qidx[pc]])] for pc in range(3)]
+        self.states = [[VlcState() for _ in range(cfg["context_count"][qidx[pc]])] for pc in range(len(qidx))]
 
 def decode_frame(packet, cfg, W, H, slice_states):
     nh, nv = cfg["num_h_slices"], cfg["num_v_slices"]

@@ -1,0 +1,53 @@
+// Test support only: csrc/mdvt_ffv1_slice.h (the per-slice FFV1 coder the device runs, one thread per slice) compiled
+// as plain C++, so that tests can step the very same text against oracle/ffv1_oracle.py and libavcodec without a GPU.
+// Nothing in the package builds or loads this.
+#include <cstdlib>
+#include <cstring>
+
+#include "mdvt_ffv1_slice.h"
+
+static uint32_t g_crc[256];
+static void init_crc() {
+    for (uint32_t i = 0; i < 256; ++i) {
+        uint32_t c = i << 24;
+        for (int k = 0; k < 8; ++k) c = (c & 0x80000000u) ? (c << 1) ^ 0x04C11DB7u : c << 1;
+        g_crc[i] = c;
+    }
+}
+
+extern "C" long long ffv1_host_slice_capacity(int w, int h, int n_planes) { return mdvt_ffv1::slice_capacity(w, h, n_planes); }
+
+// Encodes all nh x nv slices of one frame into `packet` (slices concatenated in raster order); returns its size.
+extern "C" long long ffv1_host_encode_frame(const uint8_t *frame, long long row_pitch, int width, int height, int nh, int nv,
+                                            int n_planes, int bgr_order, const uint8_t *headers, const int32_t *header_len,
+                                            uint8_t *packet, long long packet_capacity) {
+    init_crc();
+    mdvt_ffv1::VlcState *states = (mdvt_ffv1::VlcState *)malloc(sizeof(mdvt_ffv1::VlcState) * 3 * mdvt_ffv1::kContexts);
+    long long pos = 0;
+    for (int sy = 0; sy < nv; ++sy)
+        for (int sx = 0; sx < nh; ++sx) {
+            const int si = sy * nh + sx;
+            const int x0 = (int)((long long)sx * width / nh), x1 = (int)((long long)(sx + 1) * width / nh);
+            const int y0 = (int)((long long)sy * height / nv), y1 = (int)((long long)(sy + 1) * height / nv);
+            mdvt_ffv1::SliceJob job;
+            job.frame = frame + y0 * row_pitch + 3LL * x0;
+            job.row_pitch = row_pitch;
+            job.w = x1 - x0;
+            job.h = y1 - y0;
+            job.n_planes = n_planes;
+            job.ib = bgr_order ? 0 : 2;
+            job.ir = bgr_order ? 2 : 0;
+            job.header = headers + si * mdvt_ffv1::kHeaderStride;
+            job.header_len = header_len[si];
+            job.states = states;
+            if (pos + mdvt_ffv1::slice_capacity(job.w, job.h, n_planes) > packet_capacity) {
+                free(states);
+                return -1;
+            }
+            job.out = packet + pos;
+            job.crc_table = g_crc;
+            pos += mdvt_ffv1::encode_slice(job);
+        }
+    free(states);
+    return pos;
+}

@@ -1,0 +1,132 @@
+"""CPU: the FFV1 stream constants the C-ABI library writes on the host (mdvt_ffv1_stream_setup: configuration record,
+slice headers) and the per-slice coder the device runs (csrc/mdvt_ffv1_slice.h, compiled here as plain C++ by
+tests/support/ffv1_slice_host.cpp) against libavcodec (through OpenCV) and oracle/ffv1_oracle.py.  No device call."""
+import ctypes as C
+import os
+import subprocess
+
+import cv2
+import numpy as np
+import pytest
+
+from metric_depth_video_toolbox_b200 import ffv1_gpu, mkv_join
+from oracle import ffv1_oracle as fo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def host_coder(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("ffv1_host") / "ffv1_slice_host.so")
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-I", os.path.join(ROOT, "metric_depth_video_toolbox_b200", "csrc"),
+                    os.path.join(ROOT, "tests", "support", "ffv1_slice_host.cpp"), "-o", so], check=True)
+    lib = C.CDLL(so)
+    lib.ffv1_host_encode_frame.restype = C.c_longlong
+    lib.ffv1_host_encode_frame.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_longlong]
+
+    def encode(frame, nh, nv, alpha, bgr):
+        h, w = frame.shape[:2]
+        frame = np.ascontiguousarray(frame)
+        _, headers, lens = ffv1_gpu.stream_setup(w, h, nh, nv, alpha)
+        cap = w * h * 12 + 4096 * nh * nv
+        out = np.zeros(cap, np.uint8)
+        n = lib.ffv1_host_encode_frame(frame.ctypes.data, frame.strides[0], w, h, nh, nv, 3 + int(alpha), int(bgr), headers.ctypes.data,
+                                       lens.ctypes.data, out.ctypes.data, cap)
+        assert n > 0
+        return out[:n].tobytes()
+
+    return encode
+
+
+def _cv_file(path, frames, fps=24.0):
+    h, w = frames[0].shape[:2]
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"FFV1"), fps, (w, h))
+    if not wr.isOpened():
+        pytest.skip("this OpenCV build has no FFV1 encoder")
+    for f in frames:
+        wr.write(f)
+    wr.release()
+    return mkv_join.MkvPackets(path)
+
+
+def _content(w, h, seed=0):
+    rng = np.random.default_rng(seed)
+    noise = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    flat = np.empty_like(noise)
+    flat[:] = noise[:1, :1]
+    smooth = cv2.GaussianBlur(rng.integers(0, 256, (h, w, 3), dtype=np.uint8), (0, 0), 4)
+    yy, xx = np.mgrid[0:h, 0:w]
+    ramp = np.dstack([(xx * 3 + yy) & 255, (xx + yy * 2) & 255, (xx ^ yy) & 255]).astype(np.uint8)
+    ramp[h // 3: h // 2, w // 4: w // 2] = (0, 255, 0)      # the green / black mask look: long runs with hard edges
+    extremes = np.where(rng.random((h, w, 1)) < 0.5, 0, 255).astype(np.uint8).repeat(3, 2)
+    extremes[..., 1] = 255 - extremes[..., 0]               # worst-case residuals: escape codes
+    return [noise, flat, smooth, ramp, extremes]
+
+
+def test_config_record_and_headers_match_libavcodec(tmp_path):
+    """2 x 2 slices with alpha is what OpenCV writes: the record must be its CodecPrivate byte for byte, and the slice
+    headers must be the leading bytes of its key-frame slices."""
+    w, h = 64, 48
+    frames = _content(w, h)[:1]
+    pk = _cv_file(str(tmp_path / "cv.mkv"), frames)
+    config, headers, lens = ffv1_gpu.stream_setup(w, h, 2, 2, alpha=True)
+    assert config == pk.codec_private()
+    cfg = fo.parse_config(config)
+    packet = pk.payload(0)
+    for (a, b), head, n in zip(fo.slice_ranges(packet, 4, cfg["ec"]), headers, lens):
+        assert packet[a:a + n] == head[:n].tobytes()
+    for nh, nv, alpha in ((32, 32, False), (59, 17, False), (5, 7, True)):
+        config, headers, lens = ffv1_gpu.stream_setup(3840, 1080, nh, nv, alpha)
+        c = fo.parse_config(config)
+        assert (c["num_h_slices"], c["num_v_slices"], c["transparency"], c["ec"], c["version"], c["ac"]) == (nh, nv, int(alpha), 1, 3, 0)
+        assert c["quant_tables"] == cfg["quant_tables"] and fo.crc32_mpeg(config) == 0
+        assert lens.min() >= 2 and lens.max() <= 16 and headers.shape == (nh * nv, 16)
+
+
+def test_packet_equals_libavcodec_key_frame(host_coder, tmp_path):
+    """Same parameters as OpenCV (2 x 2 slices, alpha plane): whole key-frame packets are byte-identical."""
+    w, h = 96, 40
+    for k, f in enumerate(_content(w, h, seed=3)):
+        pk = _cv_file(str(tmp_path / f"cv{k}.mkv"), [f])
+        assert host_coder(f, 2, 2, True, True) == pk.payload(0), f"content {k}"
+        rgb = cv2.cvtColor(f, cv2.COLOR_BGR2RGB)
+        assert host_coder(rgb, 2, 2, True, False) == pk.payload(0), f"content {k} (RGB order)"
+
+
+@pytest.mark.parametrize("w,h,nh,nv,alpha", [(64, 48, 8, 8, False), (64, 48, 16, 12, True), (70, 33, 5, 7, False), (33, 17, 33, 17, False),
+                                             (48, 32, 1, 1, False)])
+def test_packet_equals_oracle(host_coder, w, h, nh, nv, alpha):
+    base = fo.parse_config(ffv1_gpu.stream_setup(w, h, nh, nv, alpha)[0])
+    for k, f in enumerate(_content(w, h, seed=5)):
+        ss = [fo.SliceState(base) for _ in range(nh * nv)]
+        want = fo.encode_frame(np.dstack([f, np.full((h, w), 255, np.uint8)]), base, True, ss)
+        assert host_coder(f, nh, nv, alpha, True) == want, f"content {k}"
+
+
+@pytest.mark.parametrize("w,h,nh,nv,alpha", [(256, 144, 16, 9, False), (256, 144, 32, 32, False), (200, 120, 7, 5, True)])
+def test_stream_decodes_in_opencv(host_coder, tmp_path, w, h, nh, nv, alpha):
+    """Packets of the slice coder + this library's configuration record + mkv_join's muxer -> OpenCV returns the frames."""
+    frames = _content(w, h, seed=9)
+    header, tracks = ffv1_gpu.container_template(w, h, 24.0)
+    config = ffv1_gpu.stream_setup(w, h, nh, nv, alpha)[0]
+    path = str(tmp_path / "gpu_style.mkv")
+    mux = mkv_join.StreamWriter(path, header, mkv_join.replace_codec_private(tracks, config), 24.0)
+    for f in frames:
+        mux.add(host_coder(f, nh, nv, alpha, True), True)
+    assert mux.close() == len(frames)
+    cap = cv2.VideoCapture(path)
+    assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == len(frames)
+    assert (int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)), int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT))) == (w, h)
+    for k, f in enumerate(frames):
+        ok, got = cap.read()
+        assert ok and np.array_equal(got, f), f"frame {k}"
+    assert not cap.read()[0]
+
+
+def test_slice_grid():
+    for w, h in ((3840, 1080), (1920, 1080), (3840, 2160), (640, 480), (64, 48), (7, 3)):
+        nh, nv = ffv1_gpu.slice_grid(w, h)
+        assert 1 <= nh <= w and 1 <= nv <= h and nh * nv <= 1024
+    assert ffv1_gpu.slice_grid(3840, 1080)[0] * ffv1_gpu.slice_grid(3840, 1080)[1] > 900
+    assert ffv1_gpu.slice_grid(64, 48) == (1, 1)

@@ -1,0 +1,112 @@
+"""GPU: the FFV1 encoder (mdvt_ffv1_encode_frames, one device thread per slice) through the C ABI.
+
+* packets are byte-identical to the same slice coder stepped on the host (tests/support/ffv1_slice_host.cpp), which
+  tests/test_ffv1_slice_coder.py pins against libavcodec and oracle/ffv1_oracle.py;
+* files written by GpuFfv1Writer are read back bit-exactly by OpenCV (libavcodec's decoder), at the 3840x1080 size of a
+  1080p side-by-side result too;
+* the offsets / sizes the device reports add up.
+(Named zz: it runs after every other GPU test.)"""
+import ctypes as C
+import os
+import subprocess
+
+import cv2
+import numpy as np
+import pytest
+import torch
+
+from metric_depth_video_toolbox_b200 import ffv1_gpu
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def content(w, h, n, seed=0):
+    rng = np.random.default_rng(seed)
+    out = []
+    for k in range(n):
+        kind = k % 4
+        if kind == 0:
+            f = cv2.GaussianBlur(rng.integers(0, 256, (h, w, 3), dtype=np.uint8), (0, 0), 3)
+            f[h // 4: h // 2, w // 8: w // 3] = rng.integers(0, 256, 3)
+        elif kind == 1:
+            f = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        elif kind == 2:
+            f = np.zeros((h, w, 3), np.uint8)
+            f[h // 3: 2 * h // 3, w // 5: w // 2] = (0, 255, 0)   # green / black hole mask
+        else:
+            f = np.where(rng.random((h, w, 1)) < 0.5, 0, 255).astype(np.uint8).repeat(3, 2)
+            f[..., 1] = 255 - f[..., 0]
+        out.append(f)
+    return np.stack(out)
+
+
+@pytest.fixture(scope="module")
+def host_coder(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("ffv1_host") / "ffv1_slice_host.so")
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-I", os.path.join(ROOT, "metric_depth_video_toolbox_b200", "csrc"),
+                    os.path.join(ROOT, "tests", "support", "ffv1_slice_host.cpp"), "-o", so], check=True)
+    lib = C.CDLL(so)
+    lib.ffv1_host_encode_frame.restype = C.c_longlong
+    lib.ffv1_host_encode_frame.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_longlong]
+
+    def encode(frame, nh, nv, alpha, bgr):
+        h, w = frame.shape[:2]
+        frame = np.ascontiguousarray(frame)
+        _, headers, lens = ffv1_gpu.stream_setup(w, h, nh, nv, alpha)
+        cap = w * h * 12 + 4096 * nh * nv
+        out = np.zeros(cap, np.uint8)
+        n = lib.ffv1_host_encode_frame(frame.ctypes.data, frame.strides[0], w, h, nh, nv, 3 + int(alpha), int(bgr), headers.ctypes.data,
+                                       lens.ctypes.data, out.ctypes.data, cap)
+        assert n > 0
+        return out[:n].tobytes()
+
+    return encode
+
+
+@pytest.mark.parametrize("w,h,slices,alpha,rgb", [(256, 144, (16, 9), False, True), (200, 120, (7, 5), True, False),
+                                                  (320, 200, (32, 32), False, False), (64, 48, (1, 1), False, True)])
+def test_packets_equal_host_stepped_coder(host_coder, w, h, slices, alpha, rgb):
+    frames = content(w, h, 6, seed=w)
+    enc = ffv1_gpu.Ffv1Encoder(w, h, DEV, max_frames=8, slices=slices, alpha=alpha)
+    dev = torch.from_numpy(frames).to(DEV)
+    packets = enc.encode(dev, rgb=rgb)
+    assert len(packets) == len(frames)
+    for k, f in enumerate(frames):
+        assert packets[k] == host_coder(f, slices[0], slices[1], alpha, not rgb), f"frame {k}"
+    s = enc.per_frame
+    sizes = enc.sizes[: len(frames) * s].cpu().numpy().astype(np.int64)
+    offsets = enc.offsets[: len(frames) * s + 1].cpu().numpy()
+    assert offsets[0] == 0 and np.array_equal(np.diff(offsets), sizes)
+    assert sizes.max() <= enc.capacity
+
+
+@pytest.mark.parametrize("w,h,n", [(640, 360, 9), (3840, 1080, 3)])
+def test_writer_files_decode_bit_exactly_in_opencv(tmp_path, w, h, n):
+    frames = content(w, h, n, seed=7)      # RGB order, as the renderers hold them
+    path = str(tmp_path / "gpu.mkv")
+    wr = ffv1_gpu.GpuFfv1Writer(path, 24.0, (w, h), device=DEV, batch=4)
+    dev = torch.from_numpy(frames).to(DEV)
+    wr.write(dev[:5], rgb=True)
+    wr.write(dev[5:], rgb=True)
+    assert wr.close() == n and os.path.isfile(path) and not os.path.exists(path + ".joining")
+    cap = cv2.VideoCapture(path)
+    assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == n
+    assert abs(cap.get(cv2.CAP_PROP_FPS) - 24.0) < 1e-6
+    for k in range(n):
+        ok, got = cap.read()
+        assert ok and np.array_equal(cv2.cvtColor(got, cv2.COLOR_BGR2RGB), frames[k]), f"frame {k}"
+    assert not cap.read()[0]
+
+
+def test_rejects_host_tensors_and_bad_sizes():
+    enc = ffv1_gpu.Ffv1Encoder(64, 48, DEV, max_frames=2)
+    with pytest.raises(TypeError):
+        enc.encode(torch.zeros((1, 48, 64, 3), dtype=torch.uint8))
+    with pytest.raises(ValueError):
+        enc.encode(torch.zeros((3, 48, 64, 3), dtype=torch.uint8, device=DEV))
+    with pytest.raises(ValueError):
+        enc.encode(torch.zeros((1, 40, 64, 3), dtype=torch.uint8, device=DEV))
+    assert enc.encode(torch.zeros((0, 48, 64, 3), dtype=torch.uint8, device=DEV)) == []
