@@ -40,11 +40,13 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--cv_frames", type=int, default=2)
+    ap.add_argument("--grids", default="auto,32x32,16x16", help="slice grids to time: auto or NHxNV, comma separated")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     frames = frames_like(a.width, a.height, a.frames)
     d = torch.from_numpy(frames).to(dev)
-    for slices in (None, (32, 32), (16, 16)):
+    for grid in a.grids.split(","):
+        slices = None if grid == "auto" else tuple(int(v) for v in grid.split("x"))
         enc = ffv1_gpu.Ffv1Encoder(a.width, a.height, dev, max_frames=a.batch, slices=slices)
         enc.encode_device(d[: a.batch])
         torch.cuda.synchronize()

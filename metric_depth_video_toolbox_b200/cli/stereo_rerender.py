@@ -72,6 +72,8 @@ def build_parser() -> argparse.ArgumentParser:
     add("--create_sbs_depth_video", action="store_true", help="Save a depth version of the final sbs video")
     # additions (not in the reference)
     add("--chunk_frames", default=12, type=int, help="frames per GPU batch (a multiple of 12, OpenCV's FFV1 key-frame interval, lets several decoders work on one input)")
+    add("--gpu_ffv1", action="store_true", help="code the FFV1 result videos on the GPU (addition; also MDVT_FFV1_WRITER=gpu): same "
+        "container and codec, every frame a key frame and ~1000 slices per frame, frames decode bit-identically")
     add("--writer_lanes", default=0, type=int, help="parallel FFV1 encoder lanes per output file (0: from the host core count, 1: the reference's single writer)")
     return p
 
@@ -166,7 +168,14 @@ def run(args, keep_process_group: bool = False) -> int:
     lanes = args.writer_lanes if args.writer_lanes > 0 else video_io.default_lanes(world_size)
     parallel = fourcc == "FFV1" and lanes > 1
 
+    gpu_ffv1 = bool(getattr(args, "gpu_ffv1", False)) or os.environ.get("MDVT_FFV1_WRITER", "") == "gpu"
+
     def open_writer(path: str, cc: str):
+        if gpu_ffv1 and cc == "FFV1":   # entropy coding on the device; ranks leave segments + plans for the packet-level join
+            from .. import ffv1_gpu
+
+            return ffv1_gpu.GpuFfv1Writer(seg(path), frame_rate, job.out_size, device=device, batch=min(8, max(1, args.chunk_frames)),
+                                          join_on_close=(world_size == 1))
         if parallel and cc == "FFV1":
             return video_io.ParallelWriter(seg(path), frame_rate, job.out_size, lanes=lanes, join_on_close=(world_size == 1))
         return video_io.ChunkWriter(seg(path), cc if world_size == 1 else "FFV1", frame_rate, job.out_size)

@@ -131,34 +131,90 @@ def container_template(width: int, height: int, fps: float):
 
 class GpuFfv1Writer:
     """`cv2.VideoWriter(path, FFV1, fps, size)` for frames that live on the device.  write() takes (n, H, W, 3) uint8
-    tensors (device; host tensors / arrays are uploaded), RGB by default; close() finishes the file."""
+    tensors (device; host tensors / arrays are uploaded before it returns, so the caller may recycle its buffer), RGB by
+    default; close() finishes the file.  Encoding, the packet download and the muxing run on a worker thread, at most
+    `depth` write() calls behind the caller."""
 
     def __init__(self, path: str, fps: float, size: Tuple[int, int], device=None, batch: int = 8,
-                 slices: Optional[Tuple[int, int]] = None, alpha: bool = False):
+                 slices: Optional[Tuple[int, int]] = None, alpha: bool = False, join_on_close: bool = True, depth: int = 2):
+        """join_on_close=False: `path` is one rank's segment of a torchrun job; close() leaves `<path>.plan.json` next to
+        it in video_io.ParallelWriter's format, and rank 0 stitches the segments at packet level (video_io.join_plans)."""
+        import queue
+        import threading
+
         self.path, self.fps, self.size = path, fps, (int(size[0]), int(size[1]))
+        self.join_on_close = join_on_close
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.enc = Ffv1Encoder(self.size[0], self.size[1], self.device, max_frames=batch, slices=slices, alpha=alpha)
         header, tracks = container_template(self.size[0], self.size[1], fps)
         self._mux = mkv_join.StreamWriter(path, header, mkv_join.replace_codec_private(tracks, self.enc.config), fps)
         self.frames = 0
         self.bytes = 0
+        self._error: Optional[BaseException] = None
+        self._queue: "queue.Queue" = queue.Queue(maxsize=max(1, depth))
+        self._worker = threading.Thread(target=self._run, name="mdvt-ffv1-writer", daemon=True)
+        self._worker.start()
+
+    def _run(self):
+        torch.cuda.set_device(self.device)
+        while True:
+            item = self._queue.get()
+            if item is None:
+                return
+            if self._error is not None:
+                continue   # keep draining so the producer never blocks
+            t, rgb = item
+            try:
+                for a in range(0, int(t.shape[0]), self.enc.max_frames):
+                    for pkt in self.enc.encode(t[a:a + self.enc.max_frames], rgb):
+                        self._mux.add(pkt, True)
+                        self.bytes += len(pkt)
+            except BaseException as e:   # surfaced by the next write() / close()
+                self._error = e
+
+    def _raise_pending(self):
+        if self._error is not None:
+            e, self._error = self._error, None
+            raise e
 
     def write(self, frames, rgb: bool = True):
+        self._raise_pending()
         t = frames if isinstance(frames, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(frames))
         if t.dim() == 3:
             t = t[None]
+        if t.dtype != torch.uint8 or t.dim() != 4 or t.shape[3] != 3:
+            raise TypeError("expected uint8 frames (n, H, W, 3)")
         if tuple(t.shape[1:3]) != (self.size[1], self.size[0]):
             raise ValueError(f"frames are {t.shape[2]}x{t.shape[1]}, writer expects {self.size[0]}x{self.size[1]}")
-        if not t.is_cuda:
-            t = t.to(self.device, non_blocking=True)
-        for a in range(0, int(t.shape[0]), self.enc.max_frames):
-            for pkt in self.enc.encode(t[a:a + self.enc.max_frames], rgb):
-                self._mux.add(pkt, True)
-                self.bytes += len(pkt)
-                self.frames += 1
+        if t.shape[0] == 0:
+            return
+        # an own device copy, complete before returning (blocking upload / stream-ordered clone + synchronise)
+        if t.is_cuda:
+            t = t.clone()
+            torch.cuda.current_stream(t.device).synchronize()
+        else:
+            t = t.to(self.device)
+        self.frames += int(t.shape[0])
+        self._queue.put((t, rgb))
+
+    def _stop(self):
+        if self._worker.is_alive():
+            self._queue.put(None)
+            self._worker.join()
 
     def close(self) -> int:
-        return self._mux.close()
+        self._stop()
+        if self._error is not None:
+            self._mux.abort()
+            self._raise_pending()
+        n = self._mux.close()
+        if not self.join_on_close:
+            import json
+
+            with open(self.path + ".plan.json", "w") as fh:
+                json.dump({"fps": self.fps, "plan": [(self.path, n)] if n else []}, fh)
+        return n
 
     def abort(self):
+        self._stop()
         self._mux.abort()

@@ -110,3 +110,30 @@ def test_rejects_host_tensors_and_bad_sizes():
     with pytest.raises(ValueError):
         enc.encode(torch.zeros((1, 40, 64, 3), dtype=torch.uint8, device=DEV))
     assert enc.encode(torch.zeros((0, 48, 64, 3), dtype=torch.uint8, device=DEV)) == []
+
+
+def test_cli_stereo_rerender_with_gpu_writer_equals_default_writer(tmp_path):
+    """stereo_rerender --gpu_ffv1 writes the same frames (main, mask and SBS depth video) as the default host writers."""
+    import stereo_rerender   # the root-level launcher
+    from metric_depth_video_toolbox_b200 import video_io
+    from metric_depth_video_toolbox_b200.synth import SyntheticClip
+
+    w, h, n = 192, 108, 7
+    depth, colour = SyntheticClip(w, h, n).frames()
+    dpath, cpath = str(tmp_path / "depth.mkv"), str(tmp_path / "colour.mkv")
+    video_io.write_clip(dpath, depth, 24.0)
+    video_io.write_clip(cpath, colour, 24.0)
+    argv = ["--depth_video", dpath, "--color_video", cpath, "--xfov", "60", "--infill_mask", "--green_and_black_infill_mask",
+            "--dont_place_points_in_edges", "--create_sbs_depth_video", "--chunk_frames", "3"]
+    names = [dpath + "_stereo.mkv", dpath + "_stereo.mkv_infillmask.mkv", dpath + "_stereo.mkv_depth.mkv"]
+    assert stereo_rerender.main(argv) == 0
+    want = [video_io.read_clip(p) for p in names]
+    for p in names:
+        os.remove(p)
+    assert stereo_rerender.main(argv + ["--gpu_ffv1"]) == 0
+    for p, ref in zip(names, want):
+        got = video_io.read_clip(p)
+        assert ref.shape[0] == n and got.shape == ref.shape and np.array_equal(got, ref), p
+        cap = cv2.VideoCapture(p)
+        assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == n
+    assert not [f for f in os.listdir(tmp_path) if "_tmp_" in f or f.endswith(".joining")]
