@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--cv_frames", type=int, default=2)
+    ap.add_argument("--encode_only", action="store_true", help="skip the cv2.VideoWriter and file legs")
     ap.add_argument("--grids", default="auto,32x32,16x16", help="slice grids to time: auto or NHxNV, comma separated")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -68,6 +69,8 @@ def main():
                           "with_d2h_frames_per_s": a.frames / host_s, "bytes_per_frame": nbytes / a.frames,
                           "bits_per_pixel": 8.0 * nbytes / a.frames / (a.width * a.height)}), flush=True)
         del enc
+    if a.encode_only:
+        return
     with tempfile.TemporaryDirectory() as tmp:
         path = os.path.join(tmp, "cv.mkv")
         t0 = time.perf_counter()

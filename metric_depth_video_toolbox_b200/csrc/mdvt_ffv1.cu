@@ -146,12 +146,22 @@ int check_stream(int width, int height, int nh, int nv, int alpha) {
     return MDVT_OK;
 }
 
-__device__ uint32_t g_crc_table[256];
+// Four CRC tables for word-at-a-time updates: g_crc_table[k * 256 + i] = CRC of byte i followed by k zero bytes.
+__device__ uint32_t g_crc_table[1024];
+
+__device__ __forceinline__ uint32_t crc_of_byte(uint32_t b) {
+    uint32_t c = b << 24;
+    for (int k = 0; k < 8; ++k) c = (c & 0x80000000u) ? (c << 1) ^ 0x04C11DB7u : c << 1;
+    return c;
+}
 
 __global__ void ffv1_crc_table_kernel() {
-    uint32_t c = threadIdx.x << 24;
-    for (int k = 0; k < 8; ++k) c = (c & 0x80000000u) ? (c << 1) ^ 0x04C11DB7u : c << 1;
+    uint32_t c = crc_of_byte(threadIdx.x);
     g_crc_table[threadIdx.x] = c;
+    for (int k = 1; k < 4; ++k) {
+        c = (c << 8) ^ crc_of_byte(c >> 24);
+        g_crc_table[k * 256 + threadIdx.x] = c;
+    }
 }
 
 // One thread per slice.  Consecutive threads take horizontally adjacent slices of one frame, so a warp walks neighbouring
@@ -161,8 +171,8 @@ __global__ void __launch_bounds__(64) ffv1_encode_kernel(const uint8_t *__restri
                                                          int ir, const uint8_t *__restrict__ headers,
                                                          const int32_t *__restrict__ header_len, mdvt_ffv1::VlcState *states,
                                                          uint8_t *out, int64_t capacity, int32_t *sizes) {
-    __shared__ uint32_t crc_s[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) crc_s[i] = g_crc_table[i];
+    __shared__ uint32_t crc_s[1024];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) crc_s[i] = g_crc_table[i];
     __syncthreads();
     const int per_frame = nh * nv;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

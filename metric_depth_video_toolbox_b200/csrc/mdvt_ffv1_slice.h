@@ -23,37 +23,61 @@ constexpr int kContexts = 666;        // (11*11*11 + 1) / 2: quant-table set 0 o
 constexpr int kHeaderStride = 16;     // bytes reserved per precomputed range-coded slice header
 constexpr int kFooterBytes = 8;       // 3-byte size, error-status byte, CRC-32
 
-// VLC state of one context (ffv1.h VlcState): 8 bytes, one load + one store per coded sample.
-struct VlcState {
-    uint32_t error_sum;
-    int16_t drift;
-    int8_t bias;
-    uint8_t count;
-};
+// VLC state of one context (ffv1.h VlcState), 8 bytes, handled as one 64-bit word: one load + one store per coded sample.
+// bits 0-31 error_sum, 32-47 drift (int16), 48-55 bias (int8), 56-63 count.
+typedef uint64_t VlcState;
+constexpr uint64_t kVlcInit = 4ull | (1ull << 56);   // error_sum 4, drift 0, bias 0, count 1
 
-// Big-endian bit writer into the slice's own byte range, carrying the running CRC-32 (polynomial 0x04C11DB7, MSB first,
-// initial value 0, no final xor -- libavutil's AV_CRC_32_IEEE as ffv1enc.c uses it) of every byte it has emitted.
+MDVT_FFV1_HD inline int clz32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __clz((int)x);
+#else
+    return x ? __builtin_clz(x) : 32;
+#endif
+}
+
+// Big-endian bit writer into the slice's own (4-byte aligned) byte range, carrying the running CRC-32 (polynomial
+// 0x04C11DB7, MSB first, initial value 0, no final xor -- libavutil's AV_CRC_32_IEEE as ffv1enc.c uses it) of everything
+// emitted.  Whole 32-bit words leave the accumulator; the CRC takes a word per step through four tables
+// (crc_table[k * 256 + i] = CRC of byte i followed by k zero bytes).
 struct BitSink {
     uint8_t *out;
     uint32_t pos;       // bytes written
     uint32_t crc;
     uint64_t acc;       // pending bits, right-aligned
-    int nbits;
+    int nbits;          // < 32 between calls
     const uint32_t *crc_table;
 
     MDVT_FFV1_HD inline void byte(uint32_t b) {
         out[pos++] = (uint8_t)b;
         crc = (crc << 8) ^ crc_table[(crc >> 24) ^ b];
     }
-    MDVT_FFV1_HD inline void put(int n, uint32_t v) {   // n <= 32
+    MDVT_FFV1_HD inline void word(uint32_t v) {
+#ifdef __CUDA_ARCH__
+        *reinterpret_cast<uint32_t *>(out + pos) = __byte_perm(v, 0, 0x0123);
+#else
+        out[pos] = (uint8_t)(v >> 24);
+        out[pos + 1] = (uint8_t)(v >> 16);
+        out[pos + 2] = (uint8_t)(v >> 8);
+        out[pos + 3] = (uint8_t)v;
+#endif
+        pos += 4;
+        const uint32_t x = crc ^ v;
+        crc = crc_table[768 + (x >> 24)] ^ crc_table[512 + ((x >> 16) & 0xFFu)] ^ crc_table[256 + ((x >> 8) & 0xFFu)] ^ crc_table[x & 0xFFu];
+    }
+    MDVT_FFV1_HD inline void put(int n, uint32_t v) {   // n <= 32, v < 2^n
         acc = (acc << n) | v;
         nbits += n;
+        if (nbits >= 32) {
+            nbits -= 32;
+            word((uint32_t)(acc >> nbits));
+        }
+    }
+    MDVT_FFV1_HD inline void flush() {   // pads the last byte with zero bits
         while (nbits >= 8) {
             nbits -= 8;
             byte((uint32_t)(acc >> nbits) & 0xFFu);
         }
-    }
-    MDVT_FFV1_HD inline void flush() {
         if (nbits) {
             byte((uint32_t)(acc << (8 - nbits)) & 0xFFu);
             nbits = 0;
@@ -83,31 +107,32 @@ MDVT_FFV1_HD inline int log2_run(int i) {   // ffv1.h ff_log2_run[41]
     return i < 16 ? i >> 2 : (i < 24 ? 4 + ((i - 16) >> 1) : i - 16);
 }
 
-// One sample through the adaptive Golomb-Rice coder (ffv1enc.c put_vlc_symbol + golomb.h set_ur_golomb, limit 12, escape 9).
-MDVT_FFV1_HD inline void put_vlc(BitSink &bs, VlcState *sp, int v) {
-    VlcState s = *sp;
-    v = fold9(v - s.bias);
-    int i = s.count, k = 0;
-    while (i < (int)s.error_sum) {
-        ++k;
-        i += i;
-    }
-    const int code = (2 * s.drift + s.count) < 0 ? ~v : v;
+// One sample through the adaptive Golomb-Rice coder (ffv1enc.c put_vlc_symbol + golomb.h set_ur_golomb, limit 12, escape
+// 9); returns the updated state.
+MDVT_FFV1_HD inline VlcState put_vlc(BitSink &bs, VlcState st, int v) {
+    const uint32_t error_sum = (uint32_t)st;
+    const uint32_t hi = (uint32_t)(st >> 32);
+    int drift = (int16_t)(hi & 0xFFFFu), bias = (int8_t)((hi >> 16) & 0xFFu), count = (int)(hi >> 24);
+    v = fold9(v - bias);
+    // k = smallest k with (count << k) >= error_sum  (the `while (i < error_sum) { k++; i += i; }` of put_vlc_symbol)
+    int k = clz32((uint32_t)count) - clz32(error_sum);
+    if (k < 0) k = 0;
+    else if (((uint32_t)count << k) < error_sum) ++k;
+    const int code = (2 * drift + count) < 0 ? ~v : v;
     const uint32_t u = code >= 0 ? 2u * (uint32_t)code : (uint32_t)(-2 * code - 1);
     const uint32_t e = u >> k;
     if (e < 12)
         bs.put((int)e + k + 1, (1u << k) + (u & ((1u << k) - 1u)));
     else
         bs.put(21, u - 11u);
-    int drift = s.drift + v, count = s.count;
-    uint32_t es = s.error_sum + (uint32_t)(v < 0 ? -v : v);
+    drift += v;
+    uint32_t es = error_sum + (uint32_t)(v < 0 ? -v : v);
     if (count == 128) {
         count >>= 1;
         drift >>= 1;
         es >>= 1;
     }
     ++count;
-    int bias = s.bias;
     if (drift <= -count) {
         bias = bias > -128 ? bias - 1 : -128;
         drift += count;
@@ -117,22 +142,45 @@ MDVT_FFV1_HD inline void put_vlc(BitSink &bs, VlcState *sp, int v) {
         drift -= count;
         if (drift > 0) drift = 0;
     }
-    s.error_sum = es;
-    s.drift = (int16_t)drift;
-    s.bias = (int8_t)bias;
-    s.count = (uint8_t)count;
-    *sp = s;
+    return (uint64_t)es | ((uint64_t)((uint32_t)(drift & 0xFFFF) | ((uint32_t)(bias & 0xFF) << 16) | ((uint32_t)count << 24)) << 32);
 }
 
-// Sample of plane `pl` (0: G', 1: B - G + 256, 2: R - G + 256, 3: alpha = 255) of one source pixel (three bytes; ib / ir
-// are the byte positions of blue and red: 2 / 0 for RGB-order frames, 0 / 2 for BGR).
-MDVT_FFV1_HD inline int plane_sample(const uint8_t *px, int pl, int ib, int ir) {
-    if (pl == 3) return 255;
-    const int g = MDVT_FFV1_LD(px + 1);
-    if (pl == 1) return (int)MDVT_FFV1_LD(px + ib) - g + 256;
-    if (pl == 2) return (int)MDVT_FFV1_LD(px + ir) - g + 256;
-    const int b = (int)MDVT_FFV1_LD(px + ib) - g, r = (int)MDVT_FFV1_LD(px + ir) - g;
-    return g + ((b + r) >> 2);
+// The bytes of one source pixel a plane needs, and the plane's sample from them.  Planes: 0: G' = G + ((B-G + R-G) >> 2),
+// 1: B - G + 256, 2: R - G + 256, 3: alpha = 255.  ib / ir: byte positions of blue and red (2 / 0 for RGB-order frames,
+// 0 / 2 for BGR).  Loading and evaluating are separate so that the loads can be issued an iteration ahead of their use.
+struct Raw {
+    int g, b, r;
+};
+
+template <int PL>
+MDVT_FFV1_HD inline Raw load_raw(const uint8_t *px, int ib, int ir) {
+    Raw v;
+    v.g = v.b = v.r = 0;
+    if (PL < 3) v.g = MDVT_FFV1_LD(px + 1);
+    if (PL == 0 || PL == 1) v.b = MDVT_FFV1_LD(px + ib);
+    if (PL == 0 || PL == 2) v.r = MDVT_FFV1_LD(px + ir);
+    return v;
+}
+
+template <int PL>
+MDVT_FFV1_HD inline int eval_raw(const Raw &v) {
+    if (PL == 3) return 255;
+    if (PL == 1) return v.b - v.g + 256;
+    if (PL == 2) return v.r - v.g + 256;
+    return v.g + ((v.b + v.r - 2 * v.g) >> 2);
+}
+
+// Context and prediction residual of one sample from its neighbours (ffv1.h get_context / predict, sign folded as in
+// encode_line).  q_lt_t = quant11(LT - T) comes from the previous sample (it was its quant11(T - RT)).
+MDVT_FFV1_HD inline void context_and_residual(int L, int LT, int T, int RT, int C, int q_lt_t, int &q_t_rt, int &ctx, int &diff) {
+    q_t_rt = quant11(T - RT);
+    ctx = quant11(L - LT) + 11 * q_lt_t + 121 * q_t_rt;
+    diff = C - median3(L, L + T - LT, T);
+    if (ctx < 0) {
+        ctx = -ctx;
+        diff = -diff;
+    }
+    diff = fold9(diff);
 }
 
 struct SliceJob {
@@ -144,9 +192,94 @@ struct SliceJob {
     const uint8_t *header;    // range-coded slice header (mdvt_ffv1_stream_setup), header_len bytes
     int header_len;
     VlcState *states;         // n_plane_contexts * kContexts, reset here (every frame is a key frame)
-    uint8_t *out;             // capacity >= mdvt_ffv1_slice_capacity(w, h, n_planes)
-    const uint32_t *crc_table;
+    uint8_t *out;             // 4-byte aligned, capacity >= slice_capacity(w, h, n_planes)
+    const uint32_t *crc_table;   // 4 x 256 entries (BitSink)
 };
+
+// One line of one plane (ffv1enc.c encode_line).  The loop is software-pipelined by hand: while sample x is coded, the
+// context / residual of sample x+1 are already known and its VLC state is in flight, and the pixel bytes of sample x+2
+// are in flight -- the serial coder never waits for memory except when two consecutive samples share a context, and
+// then the state is forwarded in registers.  first1 / first2: sample 0 of rows y-1 / y-2 (the format's left border:
+// ffv1enc.c encode_rgb_frame sets sample[p][0][-1] = sample[p][1][0] and sample[p][1][w] = sample[p][1][w-1]; rows above
+// the slice read as 0).
+template <int PL>
+MDVT_FFV1_HD inline void encode_line(BitSink &bs, VlcState *states, const uint8_t *row, const uint8_t *up, bool has_up, int w, int ib,
+                                     int ir, int &run_index, int &first1, int &first2) {
+    const uint8_t *upper = has_up ? up : row;   // a readable address either way; the value is dropped without a row above
+    const int last = w - 1;
+    int C = eval_raw<PL>(load_raw<PL>(row, ib, ir));
+    int T = first1;
+    int RT = has_up ? eval_raw<PL>(load_raw<PL>(upper + 3 * (last < 1 ? last : 1), ib, ir)) : 0;
+    int q, ctx, diff;
+    context_and_residual(first1, first2, T, RT, C, quant11(first2 - T), q, ctx, diff);
+    first2 = first1;
+    first1 = C;
+    VlcState *sp = states + ctx;
+    VlcState st = *sp;
+    // bytes of sample 1 (current row x = 1, upper row x = 2)
+    Raw rc_n = load_raw<PL>(row + 3 * (last < 1 ? last : 1), ib, ir);
+    Raw rrt_n = load_raw<PL>(upper + 3 * (last < 2 ? last : 2), ib, ir);
+    int run_count = 0, run_mode = 0;
+    for (int x = 0; x < w; ++x) {
+        // bytes of sample x + 2: issued now, used in the next iteration
+        const int xc = x + 2 < last ? x + 2 : last, xu = x + 3 < last ? x + 3 : last;
+        const Raw rc_nn = load_raw<PL>(row + 3 * xc, ib, ir);
+        const Raw rrt_nn = load_raw<PL>(upper + 3 * xu, ib, ir);
+        // sample x + 1: context, residual, state load
+        int ctx_n = ctx, diff_n = 0;
+        VlcState *sp_n = sp;
+        VlcState st_n = st;
+        if (x < last) {
+            const int Cn = eval_raw<PL>(rc_n);
+            const int RTn = has_up ? eval_raw<PL>(rrt_n) : 0;
+            int qn;
+            context_and_residual(C, T, RT, RTn, Cn, q, qn, ctx_n, diff_n);
+            q = qn;
+            T = RT;
+            RT = RTn;
+            C = Cn;
+            sp_n = states + ctx_n;
+            st_n = *sp_n;
+        }
+        // sample x
+        if (ctx == 0) run_mode = 1;
+        if (run_mode) {
+            if (diff) {
+                while (run_count >= (1 << log2_run(run_index))) {
+                    run_count -= 1 << log2_run(run_index);
+                    ++run_index;
+                    bs.put(1, 1);
+                }
+                bs.put(1 + log2_run(run_index), (uint32_t)run_count);
+                if (run_index) --run_index;
+                run_count = 0;
+                run_mode = 0;
+                if (diff > 0) --diff;
+            } else {
+                ++run_count;
+            }
+        }
+        if (!run_mode) {
+            st = put_vlc(bs, st, diff);
+            *sp = st;
+            if (sp_n == sp) st_n = st;   // the load above was issued before this store
+        }
+        sp = sp_n;
+        st = st_n;
+        ctx = ctx_n;
+        diff = diff_n;
+        rc_n = rc_nn;
+        rrt_n = rrt_nn;
+    }
+    if (run_mode) {
+        while (run_count >= (1 << log2_run(run_index))) {
+            run_count -= 1 << log2_run(run_index);
+            ++run_index;
+            bs.put(1, 1);
+        }
+        if (run_count) bs.put(1, 1);
+    }
+}
 
 // Codes one slice; returns its size in the packet (body + footer).
 MDVT_FFV1_HD inline uint32_t encode_slice(const SliceJob &job) {
@@ -157,78 +290,21 @@ MDVT_FFV1_HD inline uint32_t encode_slice(const SliceJob &job) {
     bs.acc = 0;
     bs.nbits = 0;
     bs.crc_table = job.crc_table;
-    for (int i = 0; i < job.header_len; ++i) bs.byte(job.header[i]);
+    for (int i = 0; i < job.header_len; ++i) bs.put(8, job.header[i]);
 
     const int n_pc = job.n_planes > 3 ? 3 : 2;   // plane contexts: G | B,R | alpha
-    for (int i = 0; i < n_pc * kContexts; ++i) {
-        VlcState z;
-        z.error_sum = 4;
-        z.drift = 0;
-        z.bias = 0;
-        z.count = 1;
-        job.states[i] = z;
-    }
+    for (int i = 0; i < n_pc * kContexts; ++i) job.states[i] = kVlcInit;
 
     int run_index = 0;
-    int first1[4] = {0, 0, 0, 0}, first2[4] = {0, 0, 0, 0};   // sample 0 of rows y-1 and y-2 per plane
-    const int w = job.w;
+    int f1_0 = 0, f1_1 = 0, f1_2 = 0, f1_3 = 0, f2_0 = 0, f2_1 = 0, f2_2 = 0, f2_3 = 0;   // sample 0 of rows y-1, y-2 per plane
     for (int y = 0; y < job.h; ++y) {
         const uint8_t *row = job.frame + (int64_t)y * job.row_pitch;
         const uint8_t *up = row - job.row_pitch;
-        for (int pl = 0; pl < job.n_planes; ++pl) {
-            VlcState *states = job.states + ((pl + 1) >> 1) * kContexts;
-            // neighbours of x = 0 (ffv1enc.c encode_rgb_frame: sample[p][0][-1] = sample[p][1][0];
-            // sample[p][1][w] = sample[p][1][w-1]; rows above the slice read as 0)
-            int L = first1[pl], LT = first2[pl], T = first1[pl];
-            int RT = y ? plane_sample(up + 3 * (w > 1 ? 1 : 0), pl, job.ib, job.ir) : 0;
-            int run_count = 0, run_mode = 0;
-            int row_first = 0;
-            for (int x = 0; x < w; ++x) {
-                const int cur = plane_sample(row + 3 * x, pl, job.ib, job.ir);
-                if (x == 0) row_first = cur;
-                int ctx = quant11(L - LT) + 11 * quant11(LT - T) + 121 * quant11(T - RT);
-                int diff = cur - median3(L, L + T - LT, T);
-                if (ctx < 0) {
-                    ctx = -ctx;
-                    diff = -diff;
-                }
-                diff = fold9(diff);
-                if (ctx == 0) run_mode = 1;
-                if (run_mode) {
-                    if (diff) {
-                        while (run_count >= (1 << log2_run(run_index))) {
-                            run_count -= 1 << log2_run(run_index);
-                            ++run_index;
-                            bs.put(1, 1);
-                        }
-                        bs.put(1 + log2_run(run_index), (uint32_t)run_count);
-                        if (run_index) --run_index;
-                        run_count = 0;
-                        run_mode = 0;
-                        if (diff > 0) --diff;
-                    } else {
-                        ++run_count;
-                    }
-                }
-                if (!run_mode) put_vlc(bs, states + ctx, diff);
-                // slide the window
-                LT = T;
-                T = RT;
-                L = cur;
-                const int xr = x + 2 < w ? x + 2 : w - 1;
-                RT = y ? plane_sample(up + 3 * xr, pl, job.ib, job.ir) : 0;
-            }
-            if (run_mode) {
-                while (run_count >= (1 << log2_run(run_index))) {
-                    run_count -= 1 << log2_run(run_index);
-                    ++run_index;
-                    bs.put(1, 1);
-                }
-                if (run_count) bs.put(1, 1);
-            }
-            first2[pl] = first1[pl];
-            first1[pl] = row_first;
-        }
+        const bool has_up = y > 0;
+        encode_line<0>(bs, job.states, row, up, has_up, job.w, job.ib, job.ir, run_index, f1_0, f2_0);
+        encode_line<1>(bs, job.states + kContexts, row, up, has_up, job.w, job.ib, job.ir, run_index, f1_1, f2_1);
+        encode_line<2>(bs, job.states + kContexts, row, up, has_up, job.w, job.ib, job.ir, run_index, f1_2, f2_2);
+        if (job.n_planes > 3) encode_line<3>(bs, job.states + 2 * kContexts, row, up, has_up, job.w, job.ib, job.ir, run_index, f1_3, f2_3);
     }
     bs.flush();
     const uint32_t body = bs.pos;

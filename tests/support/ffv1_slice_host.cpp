@@ -6,13 +6,15 @@
 
 #include "mdvt_ffv1_slice.h"
 
-static uint32_t g_crc[256];
+static uint32_t g_crc[1024];   // [k * 256 + i]: CRC of byte i followed by k zero bytes
 static void init_crc() {
     for (uint32_t i = 0; i < 256; ++i) {
         uint32_t c = i << 24;
         for (int k = 0; k < 8; ++k) c = (c & 0x80000000u) ? (c << 1) ^ 0x04C11DB7u : c << 1;
         g_crc[i] = c;
     }
+    for (int k = 1; k < 4; ++k)
+        for (uint32_t i = 0; i < 256; ++i) g_crc[k * 256 + i] = (g_crc[(k - 1) * 256 + i] << 8) ^ g_crc[g_crc[(k - 1) * 256 + i] >> 24];
 }
 
 extern "C" long long ffv1_host_slice_capacity(int w, int h, int n_planes) { return mdvt_ffv1::slice_capacity(w, h, n_planes); }
