@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MDVT_ABI_VERSION 7
+#define MDVT_ABI_VERSION 8
 
 #if defined(__GNUC__)
 #define MDVT_API __attribute__((visibility("default")))
@@ -353,6 +353,26 @@ MDVT_API int mdvt_ffv1_encode_frames(const uint8_t *frames, int64_t frame_stride
                             int height, int nh, int nv, int alpha, int bgr_order, const uint8_t *headers,
                             const int32_t *header_len, void *states, uint8_t *slices, int64_t capacity, int32_t *sizes,
                             int64_t *offsets, uint8_t *packed, void *stream);
+
+/* ---- FFV1 reader for the streams written above ------------------------------------------------------------------------
+ * The mirror image of mdvt_ffv1_encode_frames: one device thread decodes one slice.  Only streams with this library's
+ * parameters are accepted (FFV1 v3 written by cv2.VideoWriter has 2 x 2 slices and carries coder state across the 12
+ * frames of a GOP -- 4 serial threads per GOP -- and stays with cv2.VideoCapture on the host, as in the reference:
+ * stereo_rerender.py:471-503, depth_frames_helper.py load_video_frames_from_path). */
+
+/* HOST function.  Reads nh / nv / alpha from a configuration record (Matroska CodecPrivate) and returns MDVT_OK only if
+ * the record is byte for byte what mdvt_ffv1_stream_setup writes for them; MDVT_ERR_UNSUPPORTED otherwise. */
+MDVT_API int mdvt_ffv1_parse_config(const uint8_t *config_host, int config_len, int width, int height, int *nh, int *nv, int *alpha);
+
+/* packets: the n_frames packets back to back (DEVICE), packet_offsets[n_frames + 1] their bounds.  states:
+ * mdvt_ffv1_state_bytes scratch; slice_offsets: n_frames * nh * nv int64 of scratch.  frames: u8x3 output, RGB order (BGR
+ * with bgr_order = 1).  status[f] (DEVICE, one per frame): 0 = decoded; -2 the slice sizes of the packet do not add up,
+ * -3 a slice header is not the expected one (e.g. a non-key frame), -4 a slice size is inconsistent, -5 the bit stream
+ * of a slice overran.  Slice CRCs are not verified. */
+MDVT_API int mdvt_ffv1_decode_frames(const uint8_t *packets, const int64_t *packet_offsets, int n_frames, int width, int height, int nh,
+                            int nv, int alpha, int bgr_order, const uint8_t *headers, const int32_t *header_len, void *states,
+                            int64_t *slice_offsets, uint8_t *frames, int64_t frame_stride, int64_t row_pitch, int32_t *status,
+                            void *stream);
 
 #ifdef __cplusplus
 }

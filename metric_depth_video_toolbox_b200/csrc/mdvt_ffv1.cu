@@ -110,6 +110,59 @@ struct RangeCoder {
     }
 };
 
+// The reading side of the same coder (rangecoder.h get_rac / ffv1.h get_symbol): only the leading fields of a
+// configuration record are read here.
+struct RangeReader {
+    RangeCoder tables;   // state transition tables
+    const uint8_t *buf;
+    int pos = 2, end;
+    uint32_t low, range = 0xFF00;
+    bool bad = false;
+
+    RangeReader(const uint8_t *b, int n) : buf(b), end(n) {
+        low = n >= 2 ? ((uint32_t)b[0] << 8) | b[1] : 0;
+        if (n < 2) bad = true;
+        if (low >= 0xFF00) {
+            low = 0xFF00;
+            end = pos;
+        }
+    }
+    void refill() {
+        if (range < 0x100) {
+            range <<= 8;
+            low <<= 8;
+            if (pos < end) low += buf[pos++];
+        }
+    }
+    int get_rac(uint8_t *state) {
+        const uint32_t range1 = (range * *state) >> 8;
+        range -= range1;
+        if (low < range) {
+            *state = tables.zero_state[*state];
+            refill();
+            return 0;
+        }
+        low -= range;
+        *state = tables.one_state[*state];
+        range = range1;
+        refill();
+        return 1;
+    }
+    int get_symbol(uint8_t *state) {   // unsigned symbols only
+        if (get_rac(state + 0)) return 0;
+        int e = 0;
+        while (get_rac(state + 1 + (e < 9 ? e : 9))) {
+            if (++e > 31) {
+                bad = true;
+                return 0;
+            }
+        }
+        int a = 1;
+        for (int i = e - 1; i >= 0; --i) a += a + get_rac(state + 22 + (i < 9 ? i : 9));
+        return a;
+    }
+};
+
 struct CrcTable {
     uint32_t t[256];
     CrcTable() {
@@ -195,6 +248,66 @@ __global__ void __launch_bounds__(64) ffv1_encode_kernel(const uint8_t *__restri
     job.out = out + t * capacity;
     job.crc_table = crc_s;
     sizes[t] = (int32_t)mdvt_ffv1::encode_slice(job);
+}
+
+// ---- decoder ----------------------------------------------------------------------------------------------------------
+// Slice boundaries of every packet: the footers are walked backwards from the end of the packet (ffv1dec.c decode_frame:
+// each footer holds the size of its slice).  One thread per frame.  status[f] = 0, or -2 when the sizes do not add up.
+__global__ void ffv1_index_kernel(const uint8_t *__restrict__ packets, const int64_t *__restrict__ packet_offsets, int n_frames,
+                                  int per_frame, int64_t *__restrict__ slice_offsets, int32_t *__restrict__ status) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) return;
+    const int64_t begin = packet_offsets[f];
+    int64_t p = packet_offsets[f + 1];
+    int code = 0;
+    for (int s = per_frame - 1; s >= 0; --s) {
+        int64_t size = -1;
+        if (p - begin >= mdvt_ffv1::kFooterBytes) {
+            const uint8_t *foot = packets + p - mdvt_ffv1::kFooterBytes;
+            size = (((int64_t)foot[0] << 16) | ((int64_t)foot[1] << 8) | (int64_t)foot[2]) + mdvt_ffv1::kFooterBytes;
+        }
+        if (size < 0 || p - size < begin) {   // malformed: give the remaining slices empty ranges
+            code = -2;
+            size = 0;
+        }
+        p -= size;
+        slice_offsets[(int64_t)f * per_frame + s] = p;
+    }
+    if (p != begin) code = -2;
+    status[f] = code;
+}
+
+__global__ void __launch_bounds__(64, 12) ffv1_decode_kernel(const uint8_t *__restrict__ packets, const int64_t *__restrict__ packet_offsets,
+                                                         const int64_t *__restrict__ slice_offsets, int n_frames, int width, int height,
+                                                         int nh, int nv, int n_planes, int ib, int ir,
+                                                         const uint8_t *__restrict__ headers, const int32_t *__restrict__ header_len,
+                                                         mdvt_ffv1::VlcState *states, uint8_t *frames, int64_t frame_stride,
+                                                         int64_t row_pitch, int32_t *status) {
+    const int per_frame = nh * nv;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)n_frames * per_frame) return;
+    const int f = (int)(t / per_frame), si = (int)(t - (int64_t)f * per_frame);
+    if (status[f] == -2) return;   // the index kernel could not split this packet
+    const int sy = si / nh, sx = si - sy * nh;
+    const int x0 = (int)((int64_t)sx * width / nh), x1 = (int)((int64_t)(sx + 1) * width / nh);
+    const int y0 = (int)((int64_t)sy * height / nv), y1 = (int)((int64_t)(sy + 1) * height / nv);
+    const int64_t begin = slice_offsets[t];
+    const int64_t end = si + 1 < per_frame ? slice_offsets[t + 1] : packet_offsets[f + 1];
+    mdvt_ffv1::SliceInput in;
+    in.data = packets + begin;
+    in.size = (uint32_t)(end - begin);
+    in.header = headers + si * mdvt_ffv1::kHeaderStride;
+    in.header_len = header_len[si];
+    in.frame = frames + f * frame_stride + y0 * row_pitch + 3 * (int64_t)x0;
+    in.row_pitch = row_pitch;
+    in.w = x1 - x0;
+    in.h = y1 - y0;
+    in.n_planes = n_planes;
+    in.ib = ib;
+    in.ir = ir;
+    in.states = states + t * (int64_t)((n_planes > 3 ? 3 : 2) * mdvt_ffv1::kContexts);
+    const int code = mdvt_ffv1::decode_slice(in);
+    if (code < 0) atomicMin(&status[f], code - 2);   // -3: foreign slice header, -4: slice size, -5: bit stream overrun
 }
 
 // Packet layout: offsets[f * S + s] = first byte of slice s of frame f in the packed stream, offsets[n * S] = total.
@@ -365,6 +478,60 @@ extern "C" int mdvt_ffv1_encode_frames(const uint8_t *frames, int64_t frame_stri
         header_len, static_cast<mdvt_ffv1::VlcState *>(states), slices, capacity, sizes);
     mdvt::ffv1_offsets_kernel<<<1, 1024, 0, s>>>(sizes, n_frames, per_frame, offsets);
     mdvt::ffv1_pack_kernel<<<(unsigned)total, 128, 0, s>>>(slices, capacity, sizes, offsets, packed);
+    MDVT_CUDA_TRY(cudaGetLastError());
+    return MDVT_OK;
+}
+
+extern "C" int mdvt_ffv1_parse_config(const uint8_t *config_host, int config_len, int width, int height, int *nh, int *nv, int *alpha) {
+    MDVT_REQUIRE(config_host && nh && nv && alpha && config_len > 0, "NULL / empty configuration record");
+    mdvt::RangeReader rr(config_host, config_len);
+    uint8_t st[32];
+    memset(st, 128, sizeof st);
+    const int version = rr.get_symbol(st), micro = rr.get_symbol(st), coder = rr.get_symbol(st), colourspace = rr.get_symbol(st);
+    const int bits = rr.get_symbol(st), chroma = rr.get_rac(st), hshift = rr.get_symbol(st), vshift = rr.get_symbol(st);
+    const int transparency = rr.get_rac(st);
+    const int h_slices = 1 + rr.get_symbol(st), v_slices = 1 + rr.get_symbol(st);
+    (void)micro, (void)bits, (void)chroma, (void)hshift, (void)vshift;
+    if (rr.bad || version != 3 || coder != 0 || colourspace != 1) {
+        mdvt::set_error("not an FFV1 version 3 Golomb-Rice RGB stream (version %d, coder %d, colourspace %d)", version, coder, colourspace);
+        return MDVT_ERR_UNSUPPORTED;
+    }
+    if (mdvt::check_stream(width, height, h_slices, v_slices, transparency) != MDVT_OK) return MDVT_ERR_UNSUPPORTED;
+    // everything else (8 bit, quant tables, CRC, ...) must be exactly what this library writes for these parameters
+    uint8_t own[64];
+    int own_len = 0;
+    std::vector<uint8_t> headers((size_t)h_slices * v_slices * mdvt_ffv1::kHeaderStride);
+    std::vector<int32_t> lens((size_t)h_slices * v_slices);
+    if (int rc = mdvt_ffv1_stream_setup(width, height, h_slices, v_slices, transparency, own, 64, &own_len, headers.data(), lens.data()))
+        return rc;
+    if (own_len != config_len || memcmp(own, config_host, (size_t)own_len) != 0) {
+        mdvt::set_error("FFV1 stream parameters differ from the ones this library writes (8 bit, quant-table set 0, CRC)");
+        return MDVT_ERR_UNSUPPORTED;
+    }
+    *nh = h_slices;
+    *nv = v_slices;
+    *alpha = transparency;
+    return MDVT_OK;
+}
+
+extern "C" int mdvt_ffv1_decode_frames(const uint8_t *packets, const int64_t *packet_offsets, int n_frames, int width, int height, int nh,
+                                       int nv, int alpha, int bgr_order, const uint8_t *headers, const int32_t *header_len, void *states,
+                                       int64_t *slice_offsets, uint8_t *frames, int64_t frame_stride, int64_t row_pitch, int32_t *status,
+                                       void *stream) {
+    if (int rc = mdvt::check_stream(width, height, nh, nv, alpha)) return rc;
+    MDVT_REQUIRE(n_frames >= 0, "negative frame count");
+    if (n_frames == 0) return MDVT_OK;
+    MDVT_REQUIRE(row_pitch >= 3 * (int64_t)width && frame_stride >= row_pitch * height, "bad pitches");
+    MDVT_REQUIRE(packets && packet_offsets && headers && header_len && states && slice_offsets && frames && status, "NULL buffer");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int per_frame = nh * nv;
+    const int64_t total = (int64_t)n_frames * per_frame;
+    MDVT_REQUIRE(total < (1LL << 30), "too many slices in one call");
+    mdvt::ffv1_index_kernel<<<(n_frames + 31) / 32, 32, 0, s>>>(packets, packet_offsets, n_frames, per_frame, slice_offsets, status);
+    const int threads = 64;
+    mdvt::ffv1_decode_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(
+        packets, packet_offsets, slice_offsets, n_frames, width, height, nh, nv, 3 + alpha, bgr_order ? 0 : 2, bgr_order ? 2 : 0, headers,
+        header_len, static_cast<mdvt_ffv1::VlcState *>(states), frames, frame_stride, row_pitch, status);
     MDVT_CUDA_TRY(cudaGetLastError());
     return MDVT_OK;
 }

@@ -320,6 +320,211 @@ MDVT_FFV1_HD inline uint32_t encode_slice(const SliceJob &job) {
     return bs.pos;
 }
 
+// ---- decoder: the mirror image (ffv1dec.c decode_slice -> decode_rgb_frame -> decode_line / get_vlc_symbol) -------------------
+// Reads the slices this encoder writes (every frame a key frame, slice header known in advance, quant-table set 0).
+
+// Big-endian bit reader over [p, end): a 64-bit window refilled 32 bits at a time; reads past the end see zero bits.
+struct BitSource {
+    const uint8_t *p, *end;
+    uint64_t acc;   // valid bits left-aligned
+    int nbits;
+
+    MDVT_FFV1_HD inline void refill() {   // at least 33 valid bits afterwards
+        if (nbits <= 32) {
+            uint32_t w = 0;
+            if (p + 4 <= end) {
+                w = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
+            } else {
+                for (int i = 0; i < 4; ++i)
+                    if (p + i < end) w |= (uint32_t)p[i] << (24 - 8 * i);
+            }
+            p += 4;
+            acc |= (uint64_t)w << (32 - nbits);
+            nbits += 32;
+        }
+    }
+    MDVT_FFV1_HD inline uint32_t peek32() {
+        refill();
+        return (uint32_t)(acc >> 32);
+    }
+    MDVT_FFV1_HD inline void skip(int n) {   // n <= 32 after a peek32 / refill
+        acc <<= n;
+        nbits -= n;
+    }
+    MDVT_FFV1_HD inline uint32_t get(int n) {   // 0 <= n <= 25
+        if (n == 0) return 0;
+        const uint32_t v = peek32() >> (32 - n);
+        skip(n);
+        return v;
+    }
+};
+
+// get_vlc_symbol (ffv1dec.c) + get_ur_golomb (golomb.h, limit 12, escape 9): returns the residual, updates the state.
+MDVT_FFV1_HD inline int get_vlc(BitSource &bs, VlcState &st) {
+    const uint32_t error_sum = (uint32_t)st;
+    const uint32_t hi = (uint32_t)(st >> 32);
+    int drift = (int16_t)(hi & 0xFFFFu), bias = (int8_t)((hi >> 16) & 0xFFu), count = (int)(hi >> 24);
+    int k = clz32((uint32_t)count) - clz32(error_sum);
+    if (k < 0) k = 0;
+    else if (((uint32_t)count << k) < error_sum) ++k;
+    const uint32_t window = bs.peek32();
+    const int z = clz32(window);          // leading zero bits (32 if the window is empty)
+    uint32_t u;
+    if (z < 12) {
+        bs.skip(z + 1);
+        u = ((uint32_t)z << k) + bs.get(k);
+    } else {
+        bs.skip(12);
+        u = bs.get(9) + 11u;
+    }
+    int v = (int)(u >> 1) ^ -(int)(u & 1u);
+    if ((2 * drift + count) < 0) v = ~v;
+    const int ret = fold9(v + bias);
+    drift += v;
+    uint32_t es = error_sum + (uint32_t)(v < 0 ? -v : v);
+    if (count == 128) {
+        count >>= 1;
+        drift >>= 1;
+        es >>= 1;
+    }
+    ++count;
+    if (drift <= -count) {
+        bias = bias > -128 ? bias - 1 : -128;
+        drift += count;
+        if (drift < -count + 1) drift = -count + 1;
+    } else if (drift > 0) {
+        bias = bias < 127 ? bias + 1 : 127;
+        drift -= count;
+        if (drift > 0) drift = 0;
+    }
+    st = (uint64_t)es | ((uint64_t)((uint32_t)(drift & 0xFFFF) | ((uint32_t)(bias & 0xFF) << 16) | ((uint32_t)count << 24)) << 32);
+    return ret;
+}
+
+// Plain (coherent) loads: the frame being decoded is written by the same thread.
+template <int PL>
+MDVT_FFV1_HD inline int plane_of_pixel(const uint8_t *px, int ib, int ir) {
+    Raw v;
+    v.g = v.b = v.r = 0;
+    if (PL < 3) v.g = px[1];
+    if (PL == 0 || PL == 1) v.b = px[ib];
+    if (PL == 0 || PL == 2) v.r = px[ir];
+    return eval_raw<PL>(v);
+}
+
+struct SliceInput {
+    const uint8_t *data;      // the slice's bytes in the packet: header, Golomb-Rice bits, footer
+    uint32_t size;            // including the 8 footer bytes
+    const uint8_t *header;    // what the header must be (mdvt_ffv1_stream_setup)
+    int header_len;
+    uint8_t *frame;           // first byte of the slice's top-left pixel in the output frame (u8x3)
+    int64_t row_pitch;
+    int w, h, n_planes, ib, ir;
+    VlcState *states;
+};
+
+// One line of one plane.  Plane 0 / 1 leave their samples in the output row as scratch (G' in the green byte; the low 8
+// bits of B' in the blue byte and its ninth bit in the red byte); plane 2 turns the three into the final pixel (inverse
+// RCT); plane 3 (alpha) is decoded and dropped.  Neighbours of the row above are recomputed from its final pixels.
+template <int PL>
+MDVT_FFV1_HD inline void decode_line(BitSource &bs, VlcState *states, uint8_t *row, const uint8_t *up, bool has_up, int w, int ib, int ir,
+                                     int &run_index, int &first1, int &first2) {
+    const int last = w - 1;
+    int L = first1, LT = first2, T = first1;
+    int RT = has_up ? plane_of_pixel<PL>(up + 3 * (last < 1 ? last : 1), ib, ir) : 0;
+    int q_lt_t = quant11(LT - T);
+    int run_count = 0, run_mode = 0;
+    int row_first = 0;
+    for (int x = 0; x < w; ++x) {
+        const int q_t_rt = quant11(T - RT);
+        int ctx = quant11(L - LT) + 11 * q_lt_t + 121 * q_t_rt;
+        const bool sign = ctx < 0;
+        if (sign) ctx = -ctx;
+        int diff;
+        if (ctx == 0 && run_mode == 0) run_mode = 1;
+        if (run_mode) {
+            if (run_count == 0 && run_mode == 1) {
+                if (bs.get(1)) {
+                    run_count = 1 << log2_run(run_index);
+                    if (x + run_count <= w) ++run_index;
+                } else {
+                    run_count = (int)bs.get(log2_run(run_index));
+                    if (run_index) --run_index;
+                    run_mode = 2;
+                }
+            }
+            --run_count;
+            if (run_count < 0) {
+                run_mode = 0;
+                run_count = 0;
+                diff = get_vlc(bs, states[ctx]);
+                if (diff >= 0) ++diff;
+            } else {
+                diff = 0;
+            }
+        } else {
+            diff = get_vlc(bs, states[ctx]);
+        }
+        if (sign) diff = -diff;
+        const int cur = (median3(L, L + T - LT, T) + diff) & 511;
+        if (x == 0) row_first = cur;
+        uint8_t *px = row + 3 * x;
+        if (PL == 0) {
+            px[1] = (uint8_t)cur;
+        } else if (PL == 1) {
+            px[ib] = (uint8_t)cur;
+            px[ir] = (uint8_t)(cur >> 8);
+        } else if (PL == 2) {
+            const int b = ((int)px[ib] | ((int)px[ir] << 8)) - 256, r = cur - 256;
+            const int g = (int)px[1] - ((b + r) >> 2);
+            px[1] = (uint8_t)g;
+            px[ib] = (uint8_t)(b + g);
+            px[ir] = (uint8_t)(r + g);
+        }
+        LT = T;
+        T = RT;
+        L = cur;
+        q_lt_t = q_t_rt;
+        const int xr = x + 2 < last ? x + 2 : last;
+        RT = has_up ? plane_of_pixel<PL>(up + 3 * xr, ib, ir) : 0;
+    }
+    first2 = first1;
+    first1 = row_first;
+}
+
+// Decodes one slice into the frame; returns 0, or a negative code: -1 the header is not the expected one, -2 the size in
+// the footer does not match, -3 the bit stream ran past the slice.
+MDVT_FFV1_HD inline int decode_slice(const SliceInput &in) {
+    if (in.size < (uint32_t)(in.header_len + kFooterBytes)) return -2;
+    for (int i = 0; i < in.header_len; ++i)
+        if (in.data[i] != in.header[i]) return -1;
+    const uint8_t *foot = in.data + in.size - kFooterBytes;
+    const uint32_t body = ((uint32_t)foot[0] << 16) | ((uint32_t)foot[1] << 8) | (uint32_t)foot[2];
+    if (body + kFooterBytes != in.size) return -2;
+    BitSource bs;
+    bs.p = in.data + in.header_len;
+    bs.end = foot;
+    bs.acc = 0;
+    bs.nbits = 0;
+    const int n_pc = in.n_planes > 3 ? 3 : 2;
+    for (int i = 0; i < n_pc * kContexts; ++i) in.states[i] = kVlcInit;
+    int run_index = 0;
+    int f1_0 = 0, f1_1 = 0, f1_2 = 0, f1_3 = 0, f2_0 = 0, f2_1 = 0, f2_2 = 0, f2_3 = 0;
+    for (int y = 0; y < in.h; ++y) {
+        uint8_t *row = in.frame + (int64_t)y * in.row_pitch;
+        const uint8_t *up = row - in.row_pitch;
+        const bool has_up = y > 0;
+        decode_line<0>(bs, in.states, row, up, has_up, in.w, in.ib, in.ir, run_index, f1_0, f2_0);
+        decode_line<1>(bs, in.states + kContexts, row, up, has_up, in.w, in.ib, in.ir, run_index, f1_1, f2_1);
+        decode_line<2>(bs, in.states + kContexts, row, up, has_up, in.w, in.ib, in.ir, run_index, f1_2, f2_2);
+        if (in.n_planes > 3) decode_line<3>(bs, in.states + 2 * kContexts, row, up, has_up, in.w, in.ib, in.ir, run_index, f1_3, f2_3);
+    }
+    // bits consumed must lie inside the body (the window holds bytes read ahead)
+    const int64_t consumed_bits = (int64_t)(bs.p - (in.data + in.header_len)) * 8 - bs.nbits;
+    if (consumed_bits > (int64_t)(foot - (in.data + in.header_len)) * 8) return -3;
+    return 0;
+}
+
 // Worst case of one slice: 21 bits per sample (escape code) + 1 run bit, 512 bits for the run-length prefixes of a
 // descending run index, header, footer, padding to 16 bytes.
 MDVT_FFV1_HD inline int64_t slice_capacity(int w, int h, int n_planes) {

@@ -108,6 +108,114 @@ class Ffv1Encoder:
         return [buf[int(bounds[k]):int(bounds[k + 1])].tobytes() for k in range(n)]
 
 
+class Ffv1Decoder:
+    """The mirror image of Ffv1Encoder: packets of a stream written with this library's parameters -> frames on the device,
+    one device thread per slice (`mdvt_ffv1_decode_frames`)."""
+
+    def __init__(self, width: int, height: int, device, max_frames: int = 8, slices: Optional[Tuple[int, int]] = None,
+                 alpha: bool = False):
+        self.lib = _lib.load()
+        self.width, self.height, self.alpha = int(width), int(height), bool(alpha)
+        self.nh, self.nv = slices if slices is not None else slice_grid(width, height)
+        self.per_frame = self.nh * self.nv
+        self.max_frames = int(max_frames)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.MdvtError(-4, "the FFV1 decoder runs on a CUDA device only")
+        self.config, headers, lens = stream_setup(width, height, self.nh, self.nv, alpha)
+        state_bytes = int(self.lib.mdvt_ffv1_state_bytes(self.max_frames, self.nh, self.nv, int(alpha)))
+        if state_bytes < 0:
+            raise ValueError(f"bad FFV1 stream parameters {width}x{height}, {self.nh}x{self.nv} slices")
+        dev = self.device
+        self.headers = torch.from_numpy(headers).to(dev)
+        self.header_len = torch.from_numpy(lens).to(dev)
+        self.states = torch.empty(state_bytes, dtype=torch.uint8, device=dev)
+        self.slice_offsets = torch.empty(self.max_frames * self.per_frame, dtype=torch.int64, device=dev)
+        self.status = torch.empty(self.max_frames, dtype=torch.int32, device=dev)
+        self._host = torch.empty(0, dtype=torch.uint8).pin_memory()
+        self._dev = torch.empty(0, dtype=torch.uint8, device=dev)
+
+    @classmethod
+    def for_config(cls, config: bytes, width: int, height: int, device, max_frames: int = 8):
+        """A decoder for the stream whose configuration record (Matroska CodecPrivate) is `config`; raises MdvtError when
+        the stream was not written with this library's parameters."""
+        lib = _lib.load()
+        nh, nv, alpha = C.c_int(), C.c_int(), C.c_int()
+        _lib.check(lib.mdvt_ffv1_parse_config(config, len(config), width, height, C.byref(nh), C.byref(nv), C.byref(alpha)))
+        return cls(width, height, device, max_frames, (nh.value, nv.value), bool(alpha.value))
+
+    def decode(self, packets, rgb: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """packets: a sequence of n <= max_frames packets (bytes-like).  Returns (n, H, W, 3) uint8 on the device (RGB
+        order by default); raises MdvtError naming the first frame that could not be decoded."""
+        n = len(packets)
+        if n > self.max_frames:
+            raise ValueError(f"decoder built for <= {self.max_frames} frames per call, got {n}")
+        if out is None:
+            out = torch.empty((n, self.height, self.width, 3), dtype=torch.uint8, device=self.device)
+        elif tuple(out.shape) != (n, self.height, self.width, 3) or out.dtype != torch.uint8 or not out.is_cuda or not out.is_contiguous():
+            raise TypeError("`out` must be a contiguous CUDA uint8 tensor (n, H, W, 3)")
+        if n == 0:
+            return out
+        bounds = np.zeros(n + 1, np.int64)
+        np.cumsum([len(p) for p in packets], out=bounds[1:])
+        total = int(bounds[-1])
+        if self._host.numel() < total:
+            self._host = torch.empty(max(total, 2 * self._host.numel()), dtype=torch.uint8).pin_memory()
+            self._dev = torch.empty(self._host.numel(), dtype=torch.uint8, device=self.device)
+        host = self._host.numpy()
+        for k, p in enumerate(packets):
+            host[int(bounds[k]):int(bounds[k + 1])] = np.frombuffer(p, np.uint8)
+        self._dev[:total].copy_(self._host[:total], non_blocking=True)
+        offsets = torch.from_numpy(bounds).to(self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.mdvt_ffv1_decode_frames(
+            self._dev.data_ptr(), offsets.data_ptr(), n, self.width, self.height, self.nh, self.nv, int(self.alpha), 0 if rgb else 1,
+            self.headers.data_ptr(), self.header_len.data_ptr(), self.states.data_ptr(), self.slice_offsets.data_ptr(), out.data_ptr(),
+            out.stride(0), out.stride(1), self.status.data_ptr(), stream))
+        status = self.status[:n].cpu().numpy()   # synchronises: the pinned staging buffer is free again
+        if (status != 0).any():
+            k = int(np.nonzero(status)[0][0])
+            reason = {-2: "slice sizes do not add up", -3: "foreign slice header (not a key frame of this library's stream)",
+                      -4: "inconsistent slice size", -5: "bit stream overrun"}.get(int(status[k]), "unknown")
+            raise _lib.MdvtError(int(status[k]), f"FFV1 packet {k} of {n}: {reason}")
+        return out
+
+
+class GpuFfv1Reader:
+    """Frames of an .mkv written by GpuFfv1Writer, decoded on the device: iterating yields (n, H, W, 3) uint8 CUDA tensors
+    (RGB order by default) of up to `batch` frames.  Files with other FFV1 parameters (e.g. cv2.VideoWriter's) raise
+    MdvtError on open: they stay with cv2.VideoCapture on the host, as in the reference."""
+
+    def __init__(self, path: str, device=None, batch: int = 8, rgb: bool = True, start: int = 0, stop: Optional[int] = None):
+        from . import video_io
+
+        self.path, self.rgb, self.batch = path, rgb, max(1, batch)
+        self.width, self.height, self.fps, _ = video_io.video_info(path)
+        self._pk = mkv_join.MkvPackets(path)
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.dec = Ffv1Decoder.for_config(self._pk.codec_private(), self.width, self.height, self.device, max_frames=self.batch)
+        self.frames = len(self._pk.packets)
+        if not all(key for _, _, key in self._pk.packets):   # cv2.VideoWriter's 2 x 2 + alpha record equals this library's
+            raise _lib.MdvtError(-2, f"{path}: the stream carries coder state across frames (non-key frames); only all-key-frame "
+                                     "streams are decoded on the device")
+        self.start, self.stop = max(0, start), self.frames if stop is None else min(stop, self.frames)
+
+    def __len__(self):
+        return max(0, self.stop - self.start)
+
+    def __iter__(self):
+        for a in range(self.start, self.stop, self.batch):
+            b = min(a + self.batch, self.stop)
+            yield self.dec.decode([self._pk.payload(k) for k in range(a, b)], rgb=self.rgb)
+
+    def read_all(self) -> torch.Tensor:
+        chunks = list(self)
+        return torch.cat(chunks) if chunks else torch.empty((0, self.height, self.width, 3), dtype=torch.uint8, device=self.device)
+
+    def close(self):
+        self._pk.close()
+
+
 def container_template(width: int, height: int, fps: float):
     """(EBML header, Tracks payload) of the file OpenCV/FFmpeg write for an FFV1 video of this size and rate."""
     import cv2

@@ -53,3 +53,57 @@ extern "C" long long ffv1_host_encode_frame(const uint8_t *frame, long long row_
     free(states);
     return pos;
 }
+
+// Decodes one packet (all nh x nv slices of a key frame written with this coder's parameters) into `frame` (u8x3).
+// Returns 0, or the first negative slice code (see decode_slice) / -10 when the footers do not add up.
+extern "C" int ffv1_host_decode_frame(const uint8_t *packet, long long packet_len, uint8_t *frame, long long row_pitch, int width,
+                                      int height, int nh, int nv, int n_planes, int bgr_order, const uint8_t *headers,
+                                      const int32_t *header_len) {
+    const int S = nh * nv;
+    long long *starts = (long long *)malloc(sizeof(long long) * (S + 1));
+    long long p = packet_len;
+    starts[S] = packet_len;
+    for (int s = S - 1; s >= 0; --s) {
+        if (p < mdvt_ffv1::kFooterBytes) {
+            free(starts);
+            return -10;
+        }
+        const uint8_t *foot = packet + p - mdvt_ffv1::kFooterBytes;
+        const long long size = (((long long)foot[0] << 16) | ((long long)foot[1] << 8) | foot[2]) + mdvt_ffv1::kFooterBytes;
+        p -= size;
+        if (p < 0) {
+            free(starts);
+            return -10;
+        }
+        starts[s] = p;
+    }
+    if (p != 0) {
+        free(starts);
+        return -10;
+    }
+    mdvt_ffv1::VlcState *states = (mdvt_ffv1::VlcState *)malloc(sizeof(mdvt_ffv1::VlcState) * 3 * mdvt_ffv1::kContexts);
+    int rc = 0;
+    for (int sy = 0; sy < nv && rc == 0; ++sy)
+        for (int sx = 0; sx < nh && rc == 0; ++sx) {
+            const int si = sy * nh + sx;
+            const int x0 = (int)((long long)sx * width / nh), x1 = (int)((long long)(sx + 1) * width / nh);
+            const int y0 = (int)((long long)sy * height / nv), y1 = (int)((long long)(sy + 1) * height / nv);
+            mdvt_ffv1::SliceInput in;
+            in.data = packet + starts[si];
+            in.size = (uint32_t)(starts[si + 1] - starts[si]);
+            in.header = headers + si * mdvt_ffv1::kHeaderStride;
+            in.header_len = header_len[si];
+            in.frame = frame + y0 * row_pitch + 3LL * x0;
+            in.row_pitch = row_pitch;
+            in.w = x1 - x0;
+            in.h = y1 - y0;
+            in.n_planes = n_planes;
+            in.ib = bgr_order ? 0 : 2;
+            in.ir = bgr_order ? 2 : 0;
+            in.states = states;
+            rc = mdvt_ffv1::decode_slice(in);
+        }
+    free(states);
+    free(starts);
+    return rc;
+}

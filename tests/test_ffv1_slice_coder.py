@@ -25,6 +25,18 @@ def host_coder(tmp_path_factory):
     lib.ffv1_host_encode_frame.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_longlong]
 
+    lib.ffv1_host_decode_frame.restype = C.c_int
+    lib.ffv1_host_decode_frame.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, C.c_void_p, C.c_void_p]
+
+    def decode(packet, w, h, nh, nv, alpha, bgr):
+        _, headers, lens = ffv1_gpu.stream_setup(w, h, nh, nv, alpha)
+        buf = np.frombuffer(packet, np.uint8)
+        out = np.full((h, w, 3), 0xA5, np.uint8)
+        rc = lib.ffv1_host_decode_frame(buf.ctypes.data, len(packet), out.ctypes.data, out.strides[0], w, h, nh, nv, 3 + int(alpha), int(bgr),
+                                        headers.ctypes.data, lens.ctypes.data)
+        return rc, out
+
     def encode(frame, nh, nv, alpha, bgr):
         h, w = frame.shape[:2]
         frame = np.ascontiguousarray(frame)
@@ -36,6 +48,7 @@ def host_coder(tmp_path_factory):
         assert n > 0
         return out[:n].tobytes()
 
+    encode.decode = decode
     return encode
 
 
@@ -122,6 +135,59 @@ def test_stream_decodes_in_opencv(host_coder, tmp_path, w, h, nh, nv, alpha):
         ok, got = cap.read()
         assert ok and np.array_equal(got, f), f"frame {k}"
     assert not cap.read()[0]
+
+
+@pytest.mark.parametrize("w,h,nh,nv,alpha", [(64, 48, 8, 8, False), (70, 33, 5, 7, True), (33, 17, 33, 17, False), (48, 32, 1, 1, False),
+                                             (256, 144, 16, 9, False)])
+def test_decoder_mirrors_encoder_and_oracle(host_coder, w, h, nh, nv, alpha):
+    """The slice decoder the device runs (host-stepped): packets of the slice coder and of the oracle's encoder decode
+    to the source frames in either channel order; damaged packets are reported, not decoded."""
+    base = fo.parse_config(ffv1_gpu.stream_setup(w, h, nh, nv, alpha)[0])
+    for k, f in enumerate(_content(w, h, seed=11)):
+        packet = host_coder(f, nh, nv, alpha, True)
+        rc, out = host_coder.decode(packet, w, h, nh, nv, alpha, True)
+        assert rc == 0 and np.array_equal(out, f), f"content {k}"
+        rc, out = host_coder.decode(packet, w, h, nh, nv, alpha, False)     # RGB-order output of a BGR-order source
+        assert rc == 0 and np.array_equal(out, f[..., ::-1]), f"content {k} (channel order)"
+        if w * h <= 64 * 48:
+            ss = [fo.SliceState(base) for _ in range(nh * nv)]
+            want = fo.encode_frame(np.dstack([f, np.full((h, w), 255, np.uint8)]), base, True, ss)
+            rc, out = host_coder.decode(want, w, h, nh, nv, alpha, True)
+            assert rc == 0 and np.array_equal(out, f), f"content {k} (oracle packet)"
+    bad = bytearray(packet)
+    bad[0] ^= 0x40                                         # slice 0's header (key-frame bit / slice position)
+    assert host_coder.decode(bytes(bad), w, h, nh, nv, alpha, True)[0] == -1
+    assert host_coder.decode(packet[:-1], w, h, nh, nv, alpha, True)[0] != 0       # truncated: sizes do not add up
+    assert host_coder.decode(packet + b"\0", w, h, nh, nv, alpha, True)[0] != 0
+
+
+def test_decoder_rejects_opencv_non_key_frames(host_coder, tmp_path):
+    """OpenCV's own packets: the key frame has this coder's parameters (2 x 2, alpha) and decodes; the frames after it
+    carry coder state over and start with a different slice header -> refused (they stay with cv2.VideoCapture)."""
+    w, h = 96, 40
+    frames = _content(w, h, seed=2)[:3]
+    pk = _cv_file(str(tmp_path / "cv.mkv"), frames)
+    rc, out = host_coder.decode(pk.payload(0), w, h, 2, 2, True, True)
+    assert rc == 0 and np.array_equal(out, frames[0])
+    assert host_coder.decode(pk.payload(1), w, h, 2, 2, True, True)[0] == -1
+
+
+def test_parse_config_accepts_only_this_librarys_streams(tmp_path):
+    from metric_depth_video_toolbox_b200 import _lib
+
+    lib = _lib.load()
+    nh, nv, alpha = C.c_int(), C.c_int(), C.c_int()
+    for grid in ((59, 17, 0), (2, 2, 1), (1, 1, 0)):
+        cfg = ffv1_gpu.stream_setup(3840, 1080, grid[0], grid[1], bool(grid[2]))[0]
+        assert lib.mdvt_ffv1_parse_config(cfg, len(cfg), 3840, 1080, C.byref(nh), C.byref(nv), C.byref(alpha)) == 0
+        assert (nh.value, nv.value, alpha.value) == grid
+    pk = _cv_file(str(tmp_path / "cv.mkv"), _content(64, 48)[:1])
+    cfg = pk.codec_private()                # OpenCV's record is byte-identical to this library's 2 x 2 + alpha record
+    assert lib.mdvt_ffv1_parse_config(cfg, len(cfg), 64, 48, C.byref(nh), C.byref(nv), C.byref(alpha)) == 0
+    broken = bytearray(cfg)
+    broken[20] ^= 1                         # inside the quant tables
+    assert lib.mdvt_ffv1_parse_config(bytes(broken), len(broken), 64, 48, C.byref(nh), C.byref(nv), C.byref(alpha)) == -2
+    assert lib.mdvt_ffv1_parse_config(b"\x00\x01\x02\x03", 4, 64, 48, C.byref(nh), C.byref(nv), C.byref(alpha)) == -2
 
 
 def test_slice_grid():

@@ -137,3 +137,48 @@ def test_cli_stereo_rerender_with_gpu_writer_equals_default_writer(tmp_path):
         cap = cv2.VideoCapture(p)
         assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == n
     assert not [f for f in os.listdir(tmp_path) if "_tmp_" in f or f.endswith(".joining")]
+
+
+@pytest.mark.parametrize("w,h,slices,alpha,rgb", [(256, 144, (16, 9), False, True), (200, 120, (7, 5), True, False),
+                                                  (320, 200, (32, 32), False, True)])
+def test_device_decoder_mirrors_encoder(w, h, slices, alpha, rgb):
+    frames = content(w, h, 6, seed=w + 1)
+    enc = ffv1_gpu.Ffv1Encoder(w, h, DEV, max_frames=8, slices=slices, alpha=alpha)
+    packets = enc.encode(torch.from_numpy(frames).to(DEV), rgb=rgb)
+    dec = ffv1_gpu.Ffv1Decoder.for_config(enc.config, w, h, DEV, max_frames=8)
+    assert (dec.nh, dec.nv, dec.alpha) == (slices[0], slices[1], alpha)
+    got = dec.decode(packets, rgb=rgb)
+    assert got.is_cuda and np.array_equal(got.cpu().numpy(), frames)
+    swapped = dec.decode(packets[:2], rgb=not rgb)
+    assert np.array_equal(swapped.cpu().numpy(), frames[:2, ..., ::-1])
+    bad = bytearray(packets[1])
+    bad[len(bad) // 2] ^= 0xFF      # damaged bits: the frame still decodes to *something* or overruns, the others are intact
+    try:
+        out = dec.decode([packets[0], bytes(bad), packets[2]], rgb=rgb).cpu().numpy()
+        assert np.array_equal(out[0], frames[0]) and np.array_equal(out[2], frames[2])
+    except Exception as e:
+        assert "packet 1" in str(e)
+    with pytest.raises(Exception, match="packet 0"):
+        dec.decode([packets[0][:-3]], rgb=rgb)
+
+
+def test_reader_reads_writer_files_and_refuses_opencv_files(tmp_path):
+    from metric_depth_video_toolbox_b200 import _lib, video_io
+
+    w, h, n = 640, 360, 11
+    frames = content(w, h, n, seed=21)
+    path = str(tmp_path / "gpu.mkv")
+    wr = ffv1_gpu.GpuFfv1Writer(path, 30.0, (w, h), device=DEV, batch=4)
+    wr.write(torch.from_numpy(frames).to(DEV))
+    assert wr.close() == n
+    rd = ffv1_gpu.GpuFfv1Reader(path, device=DEV, batch=4)
+    assert len(rd) == n and (rd.width, rd.height) == (w, h) and abs(rd.fps - 30.0) < 1e-6
+    chunks = list(rd)
+    assert [int(c.shape[0]) for c in chunks] == [4, 4, 3]
+    assert np.array_equal(torch.cat(chunks).cpu().numpy(), frames)
+    part = ffv1_gpu.GpuFfv1Reader(path, device=DEV, batch=8, start=3, stop=9).read_all()
+    assert np.array_equal(part.cpu().numpy(), frames[3:9])
+    cvpath = str(tmp_path / "cv.mkv")
+    video_io.write_clip(cvpath, frames[:3], 30.0)
+    with pytest.raises(_lib.MdvtError):
+        ffv1_gpu.GpuFfv1Reader(cvpath, device=DEV)
