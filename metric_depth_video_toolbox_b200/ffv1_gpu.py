@@ -321,6 +321,8 @@ class GpuFfv1Writer:
 
             with open(self.path + ".plan.json", "w") as fh:
                 json.dump({"fps": self.fps, "plan": [(self.path, n)] if n else []}, fh)
+            if n == 0 and os.path.exists(self.path):   # a rank without frames leaves no segment behind
+                os.remove(self.path)
         return n
 
     def abort(self):

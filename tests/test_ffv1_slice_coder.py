@@ -190,6 +190,40 @@ def test_parse_config_accepts_only_this_librarys_streams(tmp_path):
     assert lib.mdvt_ffv1_parse_config(b"\x00\x01\x02\x03", 4, 64, 48, C.byref(nh), C.byref(nv), C.byref(alpha)) == -2
 
 
+def test_rank_segments_join_at_packet_level(host_coder, tmp_path):
+    """What `stereo_rerender --gpu_ffv1` does under torchrun: every rank leaves a segment .mkv + `<segment>.plan.json`
+    (GpuFfv1Writer(join_on_close=False)); rank 0 stitches them with video_io.join_plans.  Segments are made here with the
+    host-stepped coder; an empty rank (fewer GOP-aligned ranges than ranks) leaves an empty plan."""
+    import json
+
+    from metric_depth_video_toolbox_b200 import video_io
+
+    w, h, nh, nv = 128, 72, 4, 3
+    frames = _content(w, h, seed=13) + _content(w, h, seed=14)[:2]
+    header, tracks = ffv1_gpu.container_template(w, h, 25.0)
+    tracks = mkv_join.replace_codec_private(tracks, ffv1_gpu.stream_setup(w, h, nh, nv, False)[0])
+    parts = []
+    for rank, (a, b) in enumerate(((0, 4), (4, 7), (7, 7))):
+        seg = str(tmp_path / f"out.mkv.rank{rank:02d}.mkv")
+        mux = mkv_join.StreamWriter(seg, header, tracks, 25.0)
+        for f in frames[a:b]:
+            mux.add(host_coder(f, nh, nv, False, True), True)
+        n = mux.close()
+        json.dump({"fps": 25.0, "plan": [(seg, n)] if n else []}, open(seg + ".plan.json", "w"))
+        parts.append(seg)
+    out = str(tmp_path / "out.mkv")
+    assert video_io.join_plans([video_io.load_plan(p) for p in parts], out, 25.0) == len(frames)
+    got = video_io.read_clip(out, rgb=False)
+    assert got.shape[0] == len(frames) and all(np.array_equal(g, f) for g, f in zip(got, frames))
+    cap = cv2.VideoCapture(out)
+    assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == len(frames) and abs(cap.get(cv2.CAP_PROP_FPS) - 25.0) < 1e-6
+    cap.set(cv2.CAP_PROP_POS_FRAMES, 5)                      # every frame is a key frame: random access is exact
+    ok, f5 = cap.read()
+    assert ok and np.array_equal(f5, frames[5])
+    assert not any(os.path.exists(p + ".plan.json") for p in parts)
+    assert not os.path.exists(parts[0]) and not os.path.exists(parts[1])   # joined lanes are removed
+
+
 def test_slice_grid():
     for w, h in ((3840, 1080), (1920, 1080), (3840, 2160), (640, 480), (64, 48), (7, 3)):
         nh, nv = ffv1_gpu.slice_grid(w, h)
