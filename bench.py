@@ -15,6 +15,8 @@ collective (weak scaling: 300 frames per GPU; rank 0 broadcasts the per-frame co
             H2D + kernel + D2H inside the timed region
   roofline  algorithmic bytes (14 B/px: 6 in, 8 out) / mean launch time vs MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the NumPy oracle port of the reference path on a bounded sample (rank 0, N=1)
+  result_codec  informational, N=1: the SBS frames of the step through the device FFV1 encoder (frames/s, bytes/frame);
+            measured after the timed regions, never part of `value` / `e2e`
 
 --impl reference times the reference's CPU path (NumPy oracle port; the reference itself needs
 open3d + a Windows-only render()) on all host cores, a bounded sample per step.
@@ -308,6 +310,33 @@ def run_ours(args):
                "d2h_bytes_per_step": int(per_frame_out * n_frames * world), "steps": args.e2e_steps,
                "api": "StereoRerenderer.render_host (pinned host ring, 2-stream chunked H2D/kernel/D2H)", "mask_checksum": checksum}
 
+    # ---- informational: the result codec on the device (N=1 only; outside every timed region above) ----------
+    # The side-by-side frames the timed kernel just wrote, through mdvt_ffv1_encode_frames (FFV1 as the reference's result
+    # writers produce it, stereo_rerender.py:420-442,941).  Never fails the bench line: errors are reported in the key.
+    result_codec = None
+    if world == 1 and not args.no_e2e:
+        try:
+            from metric_depth_video_toolbox_b200 import ffv1_gpu
+
+            batch = min(32, n_frames)
+            enc = ffv1_gpu.Ffv1Encoder(2 * WIDTH, HEIGHT, dev, max_frames=batch)
+            enc.encode_device(out_sbs[:batch])
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(3):
+                _, offsets = enc.encode_device(out_sbs[:batch])
+            c1.record()
+            torch.cuda.synchronize()
+            ms = c0.elapsed_time(c1) / 3
+            nbytes = int(offsets[-1].item())
+            result_codec = {"what": "FFV1 v3 entropy coding of the SBS result on the device (mdvt_ffv1_encode_frames), not part of `value`",
+                            "frames_per_s": 1e3 * batch / ms, "ms_per_frame": ms / batch, "batch": batch, "slices_per_frame": enc.per_frame,
+                            "bytes_per_frame": nbytes / batch, "frame": f"{2 * WIDTH}x{HEIGHT}"}
+            del enc
+        except Exception as exc:  # noqa: BLE001 - informational leg only
+            result_codec = {"error": f"{type(exc).__name__}: {exc}"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -330,6 +359,8 @@ def run_ours(args):
                        "master_xfov": MASTER_XFOV, "sharding": f"frames, {world} rank(s), no data-path collective",
                        "l2": f"inputs {(dev_d.numel() + dev_c.numel()) / 1e9:.2f} GB + outputs {(out_sbs.numel() + out_mask.numel()) / 1e9:.2f} GB per step >> 126 MB L2 (no flush needed)"},
             "roofline": roofline, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks.summary()}
+    if result_codec is not None:
+        line["result_codec"] = result_codec
     if not args.no_cpu and world == 1:
         line["cpu_baseline"] = cpu_baseline(args.cpu_frames)
     if saved_stdout is not None:
