@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--cv_frames", type=int, default=2)
+    ap.add_argument("--context_model", type=int, default=0, help="0: libavcodec's 666 contexts, 1: 63 contexts")
     ap.add_argument("--encode_only", action="store_true", help="skip the cv2.VideoWriter and file legs")
     ap.add_argument("--grids", default="auto,32x32,16x16", help="slice grids to time: auto or NHxNV, comma separated")
     a = ap.parse_args()
@@ -48,7 +49,7 @@ def main():
     d = torch.from_numpy(frames).to(dev)
     for grid in a.grids.split(","):
         slices = None if grid == "auto" else tuple(int(v) for v in grid.split("x"))
-        enc = ffv1_gpu.Ffv1Encoder(a.width, a.height, dev, max_frames=a.batch, slices=slices)
+        enc = ffv1_gpu.Ffv1Encoder(a.width, a.height, dev, max_frames=a.batch, slices=slices, context_model=a.context_model)
         enc.encode_device(d[: a.batch])
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -64,7 +65,7 @@ def main():
         for s in range(0, a.frames, a.batch):
             nbytes += sum(len(p) for p in enc.encode(d[s: s + a.batch]))
         host_s = time.perf_counter() - t0
-        print(json.dumps({"what": "device FFV1 encode", "size": [a.width, a.height], "slices": [enc.nh, enc.nv], "frames": a.frames,
+        print(json.dumps({"what": "device FFV1 encode", "size": [a.width, a.height], "slices": [enc.nh, enc.nv], "context_model": a.context_model, "frames": a.frames,
                           "batch": a.batch, "device_ms_per_frame": ms / a.frames, "device_frames_per_s": 1000.0 * a.frames / ms,
                           "with_d2h_frames_per_s": a.frames / host_s, "bytes_per_frame": nbytes / a.frames,
                           "bits_per_pixel": 8.0 * nbytes / a.frames / (a.width * a.height)}), flush=True)
@@ -83,7 +84,7 @@ def main():
                           "bytes_per_frame": os.path.getsize(path) / a.cv_frames}), flush=True)
         gpath = os.path.join(tmp, "gpu.mkv")
         t0 = time.perf_counter()
-        gw = ffv1_gpu.GpuFfv1Writer(gpath, 24.0, (a.width, a.height), device=dev, batch=a.batch)
+        gw = ffv1_gpu.GpuFfv1Writer(gpath, 24.0, (a.width, a.height), device=dev, batch=a.batch, context_model=a.context_model)
         t1 = time.perf_counter()
         gw.write(d)
         gw.close()

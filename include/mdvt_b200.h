@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MDVT_ABI_VERSION 8
+#define MDVT_ABI_VERSION 9
 
 #if defined(__GNUC__)
 #define MDVT_API __attribute__((visibility("default")))
@@ -332,17 +332,21 @@ MDVT_API int mdvt_stereo_conv_rows(const uint8_t *depth_rgb, const uint8_t *colo
  * version 3 encoder with the parameters OpenCV selects (Golomb-Rice coder, RGB colourspace with the JPEG2000 RCT, 8 bit,
  * per-slice CRC), with two differences that keep the stream standard and its decoded frames bit-identical: every frame
  * is a key frame, and a frame is cut into nh x nv (<= 1024) slices instead of 2 x 2 -- one device thread codes one slice.
- * alpha = 1 adds the constant-255 alpha plane OpenCV's BGRA input produces; alpha = 0 writes the 3-plane stream. */
+ * alpha = 1 adds the constant-255 alpha plane OpenCV's BGRA input produces; alpha = 0 writes the 3-plane stream.
+ * context_model = 0 uses libavcodec's quant tables for 8-bit content (666 contexts per plane context, what OpenCV's files
+ * carry: at OpenCV's 2 x 2 slices + alpha the key-frame packets are byte-identical to libavcodec's); context_model = 1
+ * writes a 5-level table instead (63 contexts: a tenth of the coder state per slice; the tables travel in the
+ * configuration record, so any FFV1 decoder follows). */
 
 /* HOST function, no device needed.  Writes the codec configuration record (Matroska CodecPrivate; <= 64 bytes) and the
  * range-coded header of each of the nh * nv slices (16 bytes reserved per slice; header_len_host[s] bytes used). */
-MDVT_API int mdvt_ffv1_stream_setup(int width, int height, int nh, int nv, int alpha, uint8_t *config_host, int config_capacity,
-                           int *config_len, uint8_t *headers_host, int32_t *header_len_host);
+MDVT_API int mdvt_ffv1_stream_setup(int width, int height, int nh, int nv, int alpha, int context_model, uint8_t *config_host,
+                           int config_capacity, int *config_len, uint8_t *headers_host, int32_t *header_len_host);
 
 /* Bytes to reserve per slice (worst case of the coder, a multiple of 16), and bytes of coder state for a batch; -1 on
  * bad arguments. */
 MDVT_API int64_t mdvt_ffv1_slice_capacity(int width, int height, int nh, int nv, int alpha);
-MDVT_API int64_t mdvt_ffv1_state_bytes(int n_frames, int nh, int nv, int alpha);
+MDVT_API int64_t mdvt_ffv1_state_bytes(int n_frames, int nh, int nv, int alpha, int context_model);
 
 /* Encodes n_frames u8x3 frames (RGB order, or BGR with bgr_order = 1).  headers / header_len: DEVICE copies of what
  * mdvt_ffv1_stream_setup wrote.  states: mdvt_ffv1_state_bytes scratch.  slices: n_frames * nh * nv * capacity bytes of
@@ -350,7 +354,7 @@ MDVT_API int64_t mdvt_ffv1_state_bytes(int n_frames, int nh, int nv, int alpha);
  * `packed`, offsets[n_frames * S] = total bytes; packed[offsets[f * S] .. offsets[(f + 1) * S]) is the packet of frame f,
  * ready for a Matroska SimpleBlock with the key flag.  `packed` must hold n_frames * S * capacity bytes. */
 MDVT_API int mdvt_ffv1_encode_frames(const uint8_t *frames, int64_t frame_stride, int64_t row_pitch, int n_frames, int width,
-                            int height, int nh, int nv, int alpha, int bgr_order, const uint8_t *headers,
+                            int height, int nh, int nv, int alpha, int context_model, int bgr_order, const uint8_t *headers,
                             const int32_t *header_len, void *states, uint8_t *slices, int64_t capacity, int32_t *sizes,
                             int64_t *offsets, uint8_t *packed, void *stream);
 
@@ -360,9 +364,10 @@ MDVT_API int mdvt_ffv1_encode_frames(const uint8_t *frames, int64_t frame_stride
  * frames of a GOP -- 4 serial threads per GOP -- and stays with cv2.VideoCapture on the host, as in the reference:
  * stereo_rerender.py:471-503, depth_frames_helper.py load_video_frames_from_path). */
 
-/* HOST function.  Reads nh / nv / alpha from a configuration record (Matroska CodecPrivate) and returns MDVT_OK only if
- * the record is byte for byte what mdvt_ffv1_stream_setup writes for them; MDVT_ERR_UNSUPPORTED otherwise. */
-MDVT_API int mdvt_ffv1_parse_config(const uint8_t *config_host, int config_len, int width, int height, int *nh, int *nv, int *alpha);
+/* HOST function.  Reads nh / nv / alpha / context_model from a configuration record (Matroska CodecPrivate) and returns
+ * MDVT_OK only if the record is byte for byte what mdvt_ffv1_stream_setup writes for them; MDVT_ERR_UNSUPPORTED otherwise. */
+MDVT_API int mdvt_ffv1_parse_config(const uint8_t *config_host, int config_len, int width, int height, int *nh, int *nv, int *alpha,
+                           int *context_model);
 
 /* packets: the n_frames packets back to back (DEVICE), packet_offsets[n_frames + 1] their bounds.  states:
  * mdvt_ffv1_state_bytes scratch; slice_offsets: n_frames * nh * nv int64 of scratch.  frames: u8x3 output, RGB order (BGR
@@ -370,7 +375,7 @@ MDVT_API int mdvt_ffv1_parse_config(const uint8_t *config_host, int config_len, 
  * -3 a slice header is not the expected one (e.g. a non-key frame), -4 a slice size is inconsistent, -5 the bit stream
  * of a slice overran.  Slice CRCs are not verified. */
 MDVT_API int mdvt_ffv1_decode_frames(const uint8_t *packets, const int64_t *packet_offsets, int n_frames, int width, int height, int nh,
-                            int nv, int alpha, int bgr_order, const uint8_t *headers, const int32_t *header_len, void *states,
+                            int nv, int alpha, int context_model, int bgr_order, const uint8_t *headers, const int32_t *header_len, void *states,
                             int64_t *slice_offsets, uint8_t *frames, int64_t frame_stride, int64_t row_pitch, int32_t *status,
                             void *stream);
 

@@ -18,7 +18,7 @@ DECODERS = {"D1": DECODE_D1, "D2": DECODE_D2, "D3": DECODE_D3, "F32": SOURCE_F32
 REDUCE_SCRATCH_DOUBLES = 4096
 FLAG_BG_COLLIDE, FLAG_RESET_ZBUF, FLAG_MASK_RGB, FLAG_ANYWIDTH = 0x1, 0x2, 0x4, 0x8
 ZBUF_EMPTY = 0xFFFFFFFFFFFFFFFF
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 class MdvtError(RuntimeError):
@@ -110,15 +110,16 @@ _PROTOTYPES = {
                                         _f32p, _stream]),
     "mdvt_stereo_rows": (C.c_int, [_u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32,
                                    C.c_uint32, _u8p, _u8p, _f32p, _stream]),
-    "mdvt_ffv1_stream_setup": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int),
+    "mdvt_ffv1_stream_setup": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int),
                                          C.c_void_p, C.c_void_p]),
     "mdvt_ffv1_slice_capacity": (C.c_int64, [C.c_int] * 5),
-    "mdvt_ffv1_state_bytes": (C.c_int64, [C.c_int] * 4),
-    "mdvt_ffv1_encode_frames": (C.c_int, [_u8p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+    "mdvt_ffv1_state_bytes": (C.c_int64, [C.c_int] * 5),
+    "mdvt_ffv1_encode_frames": (C.c_int, [_u8p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                           _u8p, _i32p, C.c_void_p, _u8p, C.c_int64, _i32p, C.c_void_p, _u8p, _stream]),
-    "mdvt_ffv1_parse_config": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
-    "mdvt_ffv1_decode_frames": (C.c_int, [_u8p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, _i32p,
-                                          C.c_void_p, C.c_void_p, _u8p, C.c_int64, C.c_int64, _i32p, _stream]),
+    "mdvt_ffv1_parse_config": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                         C.POINTER(C.c_int)]),
+    "mdvt_ffv1_decode_frames": (C.c_int, [_u8p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p,
+                                          _i32p, C.c_void_p, C.c_void_p, _u8p, C.c_int64, C.c_int64, _i32p, _stream]),
 }
 
 _lock = threading.Lock()

@@ -199,6 +199,11 @@ int check_stream(int width, int height, int nh, int nv, int alpha) {
     return MDVT_OK;
 }
 
+int check_model(int context_model) {
+    MDVT_REQUIRE(context_model == 0 || context_model == 1, "context_model must be 0 (libavcodec's 666 contexts) or 1 (63 contexts)");
+    return MDVT_OK;
+}
+
 // Four CRC tables for word-at-a-time updates: g_crc_table[k * 256 + i] = CRC of byte i followed by k zero bytes.
 __device__ uint32_t g_crc_table[1024];
 
@@ -221,7 +226,7 @@ __global__ void ffv1_crc_table_kernel() {
 // row segments (shared 128-byte lines); each thread owns a contiguous state block and a contiguous output range.
 __global__ void __launch_bounds__(64) ffv1_encode_kernel(const uint8_t *__restrict__ frames, int64_t frame_stride, int64_t row_pitch,
                                                          int n_frames, int width, int height, int nh, int nv, int n_planes, int ib,
-                                                         int ir, const uint8_t *__restrict__ headers,
+                                                         int ir, int model, const uint8_t *__restrict__ headers,
                                                          const int32_t *__restrict__ header_len, mdvt_ffv1::VlcState *states,
                                                          uint8_t *out, int64_t capacity, int32_t *sizes) {
     __shared__ uint32_t crc_s[1024];
@@ -244,10 +249,10 @@ __global__ void __launch_bounds__(64) ffv1_encode_kernel(const uint8_t *__restri
     job.ir = ir;
     job.header = headers + si * mdvt_ffv1::kHeaderStride;
     job.header_len = header_len[si];
-    job.states = states + t * (int64_t)((n_planes > 3 ? 3 : 2) * mdvt_ffv1::kContexts);
+    job.states = states + t * (int64_t)((n_planes > 3 ? 3 : 2) * mdvt_ffv1::contexts_of(model));
     job.out = out + t * capacity;
     job.crc_table = crc_s;
-    sizes[t] = (int32_t)mdvt_ffv1::encode_slice(job);
+    sizes[t] = (int32_t)(model ? mdvt_ffv1::encode_slice<true>(job) : mdvt_ffv1::encode_slice<false>(job));
 }
 
 // ---- decoder ----------------------------------------------------------------------------------------------------------
@@ -279,7 +284,7 @@ __global__ void ffv1_index_kernel(const uint8_t *__restrict__ packets, const int
 
 __global__ void __launch_bounds__(64, 12) ffv1_decode_kernel(const uint8_t *__restrict__ packets, const int64_t *__restrict__ packet_offsets,
                                                          const int64_t *__restrict__ slice_offsets, int n_frames, int width, int height,
-                                                         int nh, int nv, int n_planes, int ib, int ir,
+                                                         int nh, int nv, int n_planes, int ib, int ir, int model,
                                                          const uint8_t *__restrict__ headers, const int32_t *__restrict__ header_len,
                                                          mdvt_ffv1::VlcState *states, uint8_t *frames, int64_t frame_stride,
                                                          int64_t row_pitch, int32_t *status) {
@@ -305,8 +310,8 @@ __global__ void __launch_bounds__(64, 12) ffv1_decode_kernel(const uint8_t *__re
     in.n_planes = n_planes;
     in.ib = ib;
     in.ir = ir;
-    in.states = states + t * (int64_t)((n_planes > 3 ? 3 : 2) * mdvt_ffv1::kContexts);
-    const int code = mdvt_ffv1::decode_slice(in);
+    in.states = states + t * (int64_t)((n_planes > 3 ? 3 : 2) * mdvt_ffv1::contexts_of(model));
+    const int code = model ? mdvt_ffv1::decode_slice<true>(in) : mdvt_ffv1::decode_slice<false>(in);
     if (code < 0) atomicMin(&status[f], code - 2);   // -3: foreign slice header, -4: slice size, -5: bit stream overrun
 }
 
@@ -382,18 +387,20 @@ extern "C" int64_t mdvt_ffv1_slice_capacity(int width, int height, int nh, int n
     return mdvt_ffv1::slice_capacity(w, h, 3 + alpha);
 }
 
-extern "C" int64_t mdvt_ffv1_state_bytes(int n_frames, int nh, int nv, int alpha) {
-    if (n_frames < 0 || nh < 1 || nv < 1 || nh * nv > 1024) return -1;
-    return (int64_t)n_frames * nh * nv * (alpha ? 3 : 2) * mdvt_ffv1::kContexts * (int64_t)sizeof(mdvt_ffv1::VlcState);
+extern "C" int64_t mdvt_ffv1_state_bytes(int n_frames, int nh, int nv, int alpha, int context_model) {
+    if (n_frames < 0 || nh < 1 || nv < 1 || nh * nv > 1024 || (context_model != 0 && context_model != 1)) return -1;
+    return (int64_t)n_frames * nh * nv * (alpha ? 3 : 2) * mdvt_ffv1::contexts_of(context_model) * (int64_t)sizeof(mdvt_ffv1::VlcState);
 }
 
-extern "C" int mdvt_ffv1_stream_setup(int width, int height, int nh, int nv, int alpha, uint8_t *config_host, int config_capacity,
-                                      int *config_len, uint8_t *headers_host, int32_t *header_len_host) {
+extern "C" int mdvt_ffv1_stream_setup(int width, int height, int nh, int nv, int alpha, int context_model, uint8_t *config_host,
+                                      int config_capacity, int *config_len, uint8_t *headers_host, int32_t *header_len_host) {
     using mdvt::RangeCoder;
     if (int rc = mdvt::check_stream(width, height, nh, nv, alpha)) return rc;
+    if (int rc = mdvt::check_model(context_model)) return rc;
     MDVT_REQUIRE(config_host && config_len && headers_host && header_len_host, "NULL output");
     static const int q11[] = {1, 1, 3, 7, 23, 93}, q5[] = {1, 3, 124}, q0[] = {128};
-    {   // ffv1enc.c write_extradata: version 3.4, Golomb-Rice, RGB, 8 bit, both of libavcodec's quant-table sets
+    {   // ffv1enc.c write_extradata: version 3.4, Golomb-Rice, RGB, 8 bit; model 0: both of libavcodec's quant-table sets
+        // (as its encoder writes them), model 1: one set, the 5-level table on three inputs
         RangeCoder rc;
         uint8_t st[32];
         memset(st, 128, sizeof st);
@@ -408,18 +415,25 @@ extern "C" int mdvt_ffv1_stream_setup(int width, int height, int nh, int nv, int
         rc.put_rac(st, alpha);                // transparency
         rc.put_symbol(st, nh - 1, false);
         rc.put_symbol(st, nv - 1, false);
-        rc.put_symbol(st, 2, false);          // quant table sets
-        for (int set = 0; set < 2; ++set) {
-            mdvt::write_run_table(rc, q11, 6);
-            mdvt::write_run_table(rc, q11, 6);
-            for (int k = 2; k < 5; ++k) {
-                if (set == 0 && k == 2) mdvt::write_run_table(rc, q11, 6);
-                else if (set == 0) mdvt::write_run_table(rc, q0, 1);
-                else mdvt::write_run_table(rc, q5, 3);
+        if (context_model == 0) {
+            rc.put_symbol(st, 2, false);      // quant table sets
+            for (int set = 0; set < 2; ++set) {
+                mdvt::write_run_table(rc, q11, 6);
+                mdvt::write_run_table(rc, q11, 6);
+                for (int k = 2; k < 5; ++k) {
+                    if (set == 0 && k == 2) mdvt::write_run_table(rc, q11, 6);
+                    else if (set == 0) mdvt::write_run_table(rc, q0, 1);
+                    else mdvt::write_run_table(rc, q5, 3);
+                }
             }
+            rc.put_rac(st, 0);                // no coded initial states, per set
+            rc.put_rac(st, 0);
+        } else {
+            rc.put_symbol(st, 1, false);
+            for (int k = 0; k < 3; ++k) mdvt::write_run_table(rc, q5, 3);
+            for (int k = 3; k < 5; ++k) mdvt::write_run_table(rc, q0, 1);
+            rc.put_rac(st, 0);
         }
-        rc.put_rac(st, 0);                    // no coded initial states, per set
-        rc.put_rac(st, 0);
         rc.put_symbol(st, 1, false);          // ec: per-slice CRC
         rc.put_symbol(st, 0, false);          // intra flag as libavcodec writes it for gop_size > 1
         rc.terminate(false);
@@ -457,10 +471,11 @@ extern "C" int mdvt_ffv1_stream_setup(int width, int height, int nh, int nv, int
 }
 
 extern "C" int mdvt_ffv1_encode_frames(const uint8_t *frames, int64_t frame_stride, int64_t row_pitch, int n_frames, int width,
-                                       int height, int nh, int nv, int alpha, int bgr_order, const uint8_t *headers,
+                                       int height, int nh, int nv, int alpha, int context_model, int bgr_order, const uint8_t *headers,
                                        const int32_t *header_len, void *states, uint8_t *slices, int64_t capacity, int32_t *sizes,
                                        int64_t *offsets, uint8_t *packed, void *stream) {
     if (int rc = mdvt::check_stream(width, height, nh, nv, alpha)) return rc;
+    if (int rc = mdvt::check_model(context_model)) return rc;
     MDVT_REQUIRE(n_frames >= 0, "negative frame count");
     if (n_frames == 0) return MDVT_OK;
     MDVT_REQUIRE(capacity >= mdvt_ffv1_slice_capacity(width, height, nh, nv, alpha) && capacity % 16 == 0,
@@ -474,16 +489,17 @@ extern "C" int mdvt_ffv1_encode_frames(const uint8_t *frames, int64_t frame_stri
     mdvt::ffv1_crc_table_kernel<<<1, 256, 0, s>>>();
     const int threads = 64;
     mdvt::ffv1_encode_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(
-        frames, frame_stride, row_pitch, n_frames, width, height, nh, nv, 3 + alpha, bgr_order ? 0 : 2, bgr_order ? 2 : 0, headers,
-        header_len, static_cast<mdvt_ffv1::VlcState *>(states), slices, capacity, sizes);
+        frames, frame_stride, row_pitch, n_frames, width, height, nh, nv, 3 + alpha, bgr_order ? 0 : 2, bgr_order ? 2 : 0, context_model,
+        headers, header_len, static_cast<mdvt_ffv1::VlcState *>(states), slices, capacity, sizes);
     mdvt::ffv1_offsets_kernel<<<1, 1024, 0, s>>>(sizes, n_frames, per_frame, offsets);
     mdvt::ffv1_pack_kernel<<<(unsigned)total, 128, 0, s>>>(slices, capacity, sizes, offsets, packed);
     MDVT_CUDA_TRY(cudaGetLastError());
     return MDVT_OK;
 }
 
-extern "C" int mdvt_ffv1_parse_config(const uint8_t *config_host, int config_len, int width, int height, int *nh, int *nv, int *alpha) {
-    MDVT_REQUIRE(config_host && nh && nv && alpha && config_len > 0, "NULL / empty configuration record");
+extern "C" int mdvt_ffv1_parse_config(const uint8_t *config_host, int config_len, int width, int height, int *nh, int *nv, int *alpha,
+                                      int *context_model) {
+    MDVT_REQUIRE(config_host && nh && nv && alpha && context_model && config_len > 0, "NULL / empty configuration record");
     mdvt::RangeReader rr(config_host, config_len);
     uint8_t st[32];
     memset(st, 128, sizeof st);
@@ -491,6 +507,7 @@ extern "C" int mdvt_ffv1_parse_config(const uint8_t *config_host, int config_len
     const int bits = rr.get_symbol(st), chroma = rr.get_rac(st), hshift = rr.get_symbol(st), vshift = rr.get_symbol(st);
     const int transparency = rr.get_rac(st);
     const int h_slices = 1 + rr.get_symbol(st), v_slices = 1 + rr.get_symbol(st);
+    const int model = rr.get_symbol(st) == 1 ? 1 : 0;   // quant table sets: 1 = this library's small model, 2 = libavcodec's
     (void)micro, (void)bits, (void)chroma, (void)hshift, (void)vshift;
     if (rr.bad || version != 3 || coder != 0 || colourspace != 1) {
         mdvt::set_error("not an FFV1 version 3 Golomb-Rice RGB stream (version %d, coder %d, colourspace %d)", version, coder, colourspace);
@@ -502,23 +519,26 @@ extern "C" int mdvt_ffv1_parse_config(const uint8_t *config_host, int config_len
     int own_len = 0;
     std::vector<uint8_t> headers((size_t)h_slices * v_slices * mdvt_ffv1::kHeaderStride);
     std::vector<int32_t> lens((size_t)h_slices * v_slices);
-    if (int rc = mdvt_ffv1_stream_setup(width, height, h_slices, v_slices, transparency, own, 64, &own_len, headers.data(), lens.data()))
+    if (int rc = mdvt_ffv1_stream_setup(width, height, h_slices, v_slices, transparency, model, own, 64, &own_len, headers.data(),
+                                        lens.data()))
         return rc;
     if (own_len != config_len || memcmp(own, config_host, (size_t)own_len) != 0) {
-        mdvt::set_error("FFV1 stream parameters differ from the ones this library writes (8 bit, quant-table set 0, CRC)");
+        mdvt::set_error("FFV1 stream parameters differ from the ones this library writes (8 bit, its quant tables, CRC)");
         return MDVT_ERR_UNSUPPORTED;
     }
     *nh = h_slices;
     *nv = v_slices;
     *alpha = transparency;
+    *context_model = model;
     return MDVT_OK;
 }
 
 extern "C" int mdvt_ffv1_decode_frames(const uint8_t *packets, const int64_t *packet_offsets, int n_frames, int width, int height, int nh,
-                                       int nv, int alpha, int bgr_order, const uint8_t *headers, const int32_t *header_len, void *states,
+                                       int nv, int alpha, int context_model, int bgr_order, const uint8_t *headers, const int32_t *header_len, void *states,
                                        int64_t *slice_offsets, uint8_t *frames, int64_t frame_stride, int64_t row_pitch, int32_t *status,
                                        void *stream) {
     if (int rc = mdvt::check_stream(width, height, nh, nv, alpha)) return rc;
+    if (int rc = mdvt::check_model(context_model)) return rc;
     MDVT_REQUIRE(n_frames >= 0, "negative frame count");
     if (n_frames == 0) return MDVT_OK;
     MDVT_REQUIRE(row_pitch >= 3 * (int64_t)width && frame_stride >= row_pitch * height, "bad pitches");
@@ -530,8 +550,8 @@ extern "C" int mdvt_ffv1_decode_frames(const uint8_t *packets, const int64_t *pa
     mdvt::ffv1_index_kernel<<<(n_frames + 31) / 32, 32, 0, s>>>(packets, packet_offsets, n_frames, per_frame, slice_offsets, status);
     const int threads = 64;
     mdvt::ffv1_decode_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(
-        packets, packet_offsets, slice_offsets, n_frames, width, height, nh, nv, 3 + alpha, bgr_order ? 0 : 2, bgr_order ? 2 : 0, headers,
-        header_len, static_cast<mdvt_ffv1::VlcState *>(states), frames, frame_stride, row_pitch, status);
+        packets, packet_offsets, slice_offsets, n_frames, width, height, nh, nv, 3 + alpha, bgr_order ? 0 : 2, bgr_order ? 2 : 0, context_model,
+        headers, header_len, static_cast<mdvt_ffv1::VlcState *>(states), frames, frame_stride, row_pitch, status);
     MDVT_CUDA_TRY(cudaGetLastError());
     return MDVT_OK;
 }

@@ -35,14 +35,15 @@ def slice_grid(width: int, height: int, target_pixels: int = 4096) -> Tuple[int,
     return nh, nv
 
 
-def stream_setup(width: int, height: int, nh: int, nv: int, alpha: bool = False):
-    """(configuration record bytes, slice headers (S, 16) uint8, header lengths (S,) int32) -- host arrays."""
+def stream_setup(width: int, height: int, nh: int, nv: int, alpha: bool = False, context_model: int = 0):
+    """(configuration record bytes, slice headers (S, 16) uint8, header lengths (S,) int32) -- host arrays.
+    context_model 0: libavcodec's quant tables (666 contexts), 1: the 5-level table (63 contexts)."""
     lib = _lib.load()
     config = (C.c_uint8 * 64)()
     n = C.c_int(0)
     headers = np.zeros((nh * nv, HEADER_STRIDE), np.uint8)
     lens = np.zeros(nh * nv, np.int32)
-    _lib.check(lib.mdvt_ffv1_stream_setup(width, height, nh, nv, int(alpha), C.addressof(config), 64, C.byref(n),
+    _lib.check(lib.mdvt_ffv1_stream_setup(width, height, nh, nv, int(alpha), int(context_model), C.addressof(config), 64, C.byref(n),
                                           headers.ctypes.data, lens.ctypes.data))
     return bytes(config[:n.value]), headers, lens
 
@@ -51,18 +52,18 @@ class Ffv1Encoder:
     """Device buffers + stream constants for frames of one size; `encode` turns a batch of device frames into packets."""
 
     def __init__(self, width: int, height: int, device, max_frames: int = 8, slices: Optional[Tuple[int, int]] = None,
-                 alpha: bool = False):
+                 alpha: bool = False, context_model: int = 0):
         self.lib = _lib.load()
-        self.width, self.height, self.alpha = int(width), int(height), bool(alpha)
+        self.width, self.height, self.alpha, self.context_model = int(width), int(height), bool(alpha), int(context_model)
         self.nh, self.nv = slices if slices is not None else slice_grid(width, height)
         self.per_frame = self.nh * self.nv
         self.max_frames = int(max_frames)
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.MdvtError(-4, "the FFV1 encoder runs on a CUDA device only")
-        self.config, headers, lens = stream_setup(width, height, self.nh, self.nv, alpha)
+        self.config, headers, lens = stream_setup(width, height, self.nh, self.nv, alpha, self.context_model)
         self.capacity = int(self.lib.mdvt_ffv1_slice_capacity(width, height, self.nh, self.nv, int(alpha)))
-        state_bytes = int(self.lib.mdvt_ffv1_state_bytes(self.max_frames, self.nh, self.nv, int(alpha)))
+        state_bytes = int(self.lib.mdvt_ffv1_state_bytes(self.max_frames, self.nh, self.nv, int(alpha), self.context_model))
         if self.capacity <= 0 or state_bytes < 0:
             raise ValueError(f"bad FFV1 stream parameters {width}x{height}, {self.nh}x{self.nv} slices")
         n_slices = self.max_frames * self.per_frame
@@ -88,7 +89,8 @@ class Ffv1Encoder:
             frames = frames.contiguous()
         stream = torch.cuda.current_stream(frames.device).cuda_stream
         _lib.check(self.lib.mdvt_ffv1_encode_frames(
-            frames.data_ptr(), frames.stride(0), frames.stride(1), n, w, h, self.nh, self.nv, int(self.alpha), 0 if rgb else 1,
+            frames.data_ptr(), frames.stride(0), frames.stride(1), n, w, h, self.nh, self.nv, int(self.alpha), self.context_model,
+            0 if rgb else 1,
             self.headers.data_ptr(), self.header_len.data_ptr(), self.states.data_ptr(), self.slices.data_ptr(), self.capacity,
             self.sizes.data_ptr(), self.offsets.data_ptr(), self.packed.data_ptr(), stream))
         return self.packed, self.offsets[: n * self.per_frame + 1]
@@ -113,17 +115,17 @@ class Ffv1Decoder:
     one device thread per slice (`mdvt_ffv1_decode_frames`)."""
 
     def __init__(self, width: int, height: int, device, max_frames: int = 8, slices: Optional[Tuple[int, int]] = None,
-                 alpha: bool = False):
+                 alpha: bool = False, context_model: int = 0):
         self.lib = _lib.load()
-        self.width, self.height, self.alpha = int(width), int(height), bool(alpha)
+        self.width, self.height, self.alpha, self.context_model = int(width), int(height), bool(alpha), int(context_model)
         self.nh, self.nv = slices if slices is not None else slice_grid(width, height)
         self.per_frame = self.nh * self.nv
         self.max_frames = int(max_frames)
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.MdvtError(-4, "the FFV1 decoder runs on a CUDA device only")
-        self.config, headers, lens = stream_setup(width, height, self.nh, self.nv, alpha)
-        state_bytes = int(self.lib.mdvt_ffv1_state_bytes(self.max_frames, self.nh, self.nv, int(alpha)))
+        self.config, headers, lens = stream_setup(width, height, self.nh, self.nv, alpha, self.context_model)
+        state_bytes = int(self.lib.mdvt_ffv1_state_bytes(self.max_frames, self.nh, self.nv, int(alpha), self.context_model))
         if state_bytes < 0:
             raise ValueError(f"bad FFV1 stream parameters {width}x{height}, {self.nh}x{self.nv} slices")
         dev = self.device
@@ -140,9 +142,9 @@ class Ffv1Decoder:
         """A decoder for the stream whose configuration record (Matroska CodecPrivate) is `config`; raises MdvtError when
         the stream was not written with this library's parameters."""
         lib = _lib.load()
-        nh, nv, alpha = C.c_int(), C.c_int(), C.c_int()
-        _lib.check(lib.mdvt_ffv1_parse_config(config, len(config), width, height, C.byref(nh), C.byref(nv), C.byref(alpha)))
-        return cls(width, height, device, max_frames, (nh.value, nv.value), bool(alpha.value))
+        nh, nv, alpha, model = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _lib.check(lib.mdvt_ffv1_parse_config(config, len(config), width, height, C.byref(nh), C.byref(nv), C.byref(alpha), C.byref(model)))
+        return cls(width, height, device, max_frames, (nh.value, nv.value), bool(alpha.value), model.value)
 
     def decode(self, packets, rgb: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """packets: a sequence of n <= max_frames packets (bytes-like).  Returns (n, H, W, 3) uint8 on the device (RGB
@@ -169,7 +171,8 @@ class Ffv1Decoder:
         offsets = torch.from_numpy(bounds).to(self.device)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self.lib.mdvt_ffv1_decode_frames(
-            self._dev.data_ptr(), offsets.data_ptr(), n, self.width, self.height, self.nh, self.nv, int(self.alpha), 0 if rgb else 1,
+            self._dev.data_ptr(), offsets.data_ptr(), n, self.width, self.height, self.nh, self.nv, int(self.alpha), self.context_model,
+            0 if rgb else 1,
             self.headers.data_ptr(), self.header_len.data_ptr(), self.states.data_ptr(), self.slice_offsets.data_ptr(), out.data_ptr(),
             out.stride(0), out.stride(1), self.status.data_ptr(), stream))
         status = self.status[:n].cpu().numpy()   # synchronises: the pinned staging buffer is free again
@@ -244,7 +247,8 @@ class GpuFfv1Writer:
     `depth` write() calls behind the caller."""
 
     def __init__(self, path: str, fps: float, size: Tuple[int, int], device=None, batch: int = 8,
-                 slices: Optional[Tuple[int, int]] = None, alpha: bool = False, join_on_close: bool = True, depth: int = 2):
+                 slices: Optional[Tuple[int, int]] = None, alpha: bool = False, join_on_close: bool = True, depth: int = 2,
+                 context_model: int = 0):
         """join_on_close=False: `path` is one rank's segment of a torchrun job; close() leaves `<path>.plan.json` next to
         it in video_io.ParallelWriter's format, and rank 0 stitches the segments at packet level (video_io.join_plans)."""
         import queue
@@ -253,7 +257,8 @@ class GpuFfv1Writer:
         self.path, self.fps, self.size = path, fps, (int(size[0]), int(size[1]))
         self.join_on_close = join_on_close
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
-        self.enc = Ffv1Encoder(self.size[0], self.size[1], self.device, max_frames=batch, slices=slices, alpha=alpha)
+        self.enc = Ffv1Encoder(self.size[0], self.size[1], self.device, max_frames=batch, slices=slices, alpha=alpha,
+                               context_model=context_model)
         header, tracks = container_template(self.size[0], self.size[1], fps)
         self._mux = mkv_join.StreamWriter(path, header, mkv_join.replace_codec_private(tracks, self.enc.config), fps)
         self.frames = 0

@@ -7,6 +7,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+SUPPORT = os.path.join(ROOT, "tests", "support")   # test-only helpers (ffv1_host.py)
+if SUPPORT not in sys.path:
+    sys.path.insert(0, SUPPORT)
+
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 

@@ -21,8 +21,8 @@ extern "C" long long ffv1_host_slice_capacity(int w, int h, int n_planes) { retu
 
 // Encodes all nh x nv slices of one frame into `packet` (slices concatenated in raster order); returns its size.
 extern "C" long long ffv1_host_encode_frame(const uint8_t *frame, long long row_pitch, int width, int height, int nh, int nv,
-                                            int n_planes, int bgr_order, const uint8_t *headers, const int32_t *header_len,
-                                            uint8_t *packet, long long packet_capacity) {
+                                            int n_planes, int bgr_order, int context_model, const uint8_t *headers,
+                                            const int32_t *header_len, uint8_t *packet, long long packet_capacity) {
     init_crc();
     mdvt_ffv1::VlcState *states = (mdvt_ffv1::VlcState *)malloc(sizeof(mdvt_ffv1::VlcState) * 3 * mdvt_ffv1::kContexts);
     long long pos = 0;
@@ -48,7 +48,7 @@ extern "C" long long ffv1_host_encode_frame(const uint8_t *frame, long long row_
             }
             job.out = packet + pos;
             job.crc_table = g_crc;
-            pos += mdvt_ffv1::encode_slice(job);
+            pos += context_model ? mdvt_ffv1::encode_slice<true>(job) : mdvt_ffv1::encode_slice<false>(job);
         }
     free(states);
     return pos;
@@ -57,7 +57,7 @@ extern "C" long long ffv1_host_encode_frame(const uint8_t *frame, long long row_
 // Decodes one packet (all nh x nv slices of a key frame written with this coder's parameters) into `frame` (u8x3).
 // Returns 0, or the first negative slice code (see decode_slice) / -10 when the footers do not add up.
 extern "C" int ffv1_host_decode_frame(const uint8_t *packet, long long packet_len, uint8_t *frame, long long row_pitch, int width,
-                                      int height, int nh, int nv, int n_planes, int bgr_order, const uint8_t *headers,
+                                      int height, int nh, int nv, int n_planes, int bgr_order, int context_model, const uint8_t *headers,
                                       const int32_t *header_len) {
     const int S = nh * nv;
     long long *starts = (long long *)malloc(sizeof(long long) * (S + 1));
@@ -101,7 +101,7 @@ extern "C" int ffv1_host_decode_frame(const uint8_t *packet, long long packet_le
             in.ib = bgr_order ? 0 : 2;
             in.ir = bgr_order ? 2 : 0;
             in.states = states;
-            rc = mdvt_ffv1::decode_slice(in);
+            rc = context_model ? mdvt_ffv1::decode_slice<true>(in) : mdvt_ffv1::decode_slice<false>(in);
         }
     free(states);
     free(starts);

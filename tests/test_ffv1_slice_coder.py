@@ -3,7 +3,6 @@ slice headers) and the per-slice coder the device runs (csrc/mdvt_ffv1_slice.h, 
 tests/support/ffv1_slice_host.cpp) against libavcodec (through OpenCV) and oracle/ffv1_oracle.py.  No device call."""
 import ctypes as C
 import os
-import subprocess
 
 import cv2
 import numpy as np
@@ -17,39 +16,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.fixture(scope="module")
 def host_coder(tmp_path_factory):
-    so = str(tmp_path_factory.mktemp("ffv1_host") / "ffv1_slice_host.so")
-    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-I", os.path.join(ROOT, "metric_depth_video_toolbox_b200", "csrc"),
-                    os.path.join(ROOT, "tests", "support", "ffv1_slice_host.cpp"), "-o", so], check=True)
-    lib = C.CDLL(so)
-    lib.ffv1_host_encode_frame.restype = C.c_longlong
-    lib.ffv1_host_encode_frame.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
-                                           C.c_void_p, C.c_void_p, C.c_longlong]
+    from ffv1_host import HostCoder
 
-    lib.ffv1_host_decode_frame.restype = C.c_int
-    lib.ffv1_host_decode_frame.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                           C.c_int, C.c_void_p, C.c_void_p]
-
-    def decode(packet, w, h, nh, nv, alpha, bgr):
-        _, headers, lens = ffv1_gpu.stream_setup(w, h, nh, nv, alpha)
-        buf = np.frombuffer(packet, np.uint8)
-        out = np.full((h, w, 3), 0xA5, np.uint8)
-        rc = lib.ffv1_host_decode_frame(buf.ctypes.data, len(packet), out.ctypes.data, out.strides[0], w, h, nh, nv, 3 + int(alpha), int(bgr),
-                                        headers.ctypes.data, lens.ctypes.data)
-        return rc, out
-
-    def encode(frame, nh, nv, alpha, bgr):
-        h, w = frame.shape[:2]
-        frame = np.ascontiguousarray(frame)
-        _, headers, lens = ffv1_gpu.stream_setup(w, h, nh, nv, alpha)
-        cap = w * h * 12 + 4096 * nh * nv
-        out = np.zeros(cap, np.uint8)
-        n = lib.ffv1_host_encode_frame(frame.ctypes.data, frame.strides[0], w, h, nh, nv, 3 + int(alpha), int(bgr), headers.ctypes.data,
-                                       lens.ctypes.data, out.ctypes.data, cap)
-        assert n > 0
-        return out[:n].tobytes()
-
-    encode.decode = decode
-    return encode
+    return HostCoder(str(tmp_path_factory.mktemp("ffv1_host")))
 
 
 def _cv_file(path, frames, fps=24.0):
@@ -107,26 +76,31 @@ def test_packet_equals_libavcodec_key_frame(host_coder, tmp_path):
         assert host_coder(rgb, 2, 2, True, False) == pk.payload(0), f"content {k} (RGB order)"
 
 
-@pytest.mark.parametrize("w,h,nh,nv,alpha", [(64, 48, 8, 8, False), (64, 48, 16, 12, True), (70, 33, 5, 7, False), (33, 17, 33, 17, False),
-                                             (48, 32, 1, 1, False)])
-def test_packet_equals_oracle(host_coder, w, h, nh, nv, alpha):
-    base = fo.parse_config(ffv1_gpu.stream_setup(w, h, nh, nv, alpha)[0])
+@pytest.mark.parametrize("w,h,nh,nv,alpha,model", [(64, 48, 8, 8, False, 0), (64, 48, 16, 12, True, 0), (70, 33, 5, 7, False, 0),
+                                                   (33, 17, 33, 17, False, 0), (48, 32, 1, 1, False, 0), (64, 48, 8, 8, False, 1),
+                                                   (70, 33, 5, 7, True, 1), (48, 32, 1, 1, False, 1)])
+def test_packet_equals_oracle(host_coder, w, h, nh, nv, alpha, model):
+    """The oracle codes with whatever quant tables the configuration record carries: model 0 = libavcodec's (666
+    contexts), model 1 = the 5-level table (63 contexts)."""
+    base = fo.parse_config(ffv1_gpu.stream_setup(w, h, nh, nv, alpha, model)[0])
+    assert base["context_count"][0] == (63 if model else 666) and base["quant_table_count"] == (1 if model else 2)
     for k, f in enumerate(_content(w, h, seed=5)):
         ss = [fo.SliceState(base) for _ in range(nh * nv)]
         want = fo.encode_frame(np.dstack([f, np.full((h, w), 255, np.uint8)]), base, True, ss)
-        assert host_coder(f, nh, nv, alpha, True) == want, f"content {k}"
+        assert host_coder(f, nh, nv, alpha, True, model) == want, f"content {k}"
 
 
-@pytest.mark.parametrize("w,h,nh,nv,alpha", [(256, 144, 16, 9, False), (256, 144, 32, 32, False), (200, 120, 7, 5, True)])
-def test_stream_decodes_in_opencv(host_coder, tmp_path, w, h, nh, nv, alpha):
+@pytest.mark.parametrize("w,h,nh,nv,alpha,model", [(256, 144, 16, 9, False, 0), (256, 144, 32, 32, False, 0), (200, 120, 7, 5, True, 0),
+                                                   (256, 144, 16, 9, False, 1), (200, 120, 7, 5, True, 1)])
+def test_stream_decodes_in_opencv(host_coder, tmp_path, w, h, nh, nv, alpha, model):
     """Packets of the slice coder + this library's configuration record + mkv_join's muxer -> OpenCV returns the frames."""
     frames = _content(w, h, seed=9)
     header, tracks = ffv1_gpu.container_template(w, h, 24.0)
-    config = ffv1_gpu.stream_setup(w, h, nh, nv, alpha)[0]
+    config = ffv1_gpu.stream_setup(w, h, nh, nv, alpha, model)[0]
     path = str(tmp_path / "gpu_style.mkv")
     mux = mkv_join.StreamWriter(path, header, mkv_join.replace_codec_private(tracks, config), 24.0)
     for f in frames:
-        mux.add(host_coder(f, nh, nv, alpha, True), True)
+        mux.add(host_coder(f, nh, nv, alpha, True, model), True)
     assert mux.close() == len(frames)
     cap = cv2.VideoCapture(path)
     assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == len(frames)
@@ -137,28 +111,31 @@ def test_stream_decodes_in_opencv(host_coder, tmp_path, w, h, nh, nv, alpha):
     assert not cap.read()[0]
 
 
-@pytest.mark.parametrize("w,h,nh,nv,alpha", [(64, 48, 8, 8, False), (70, 33, 5, 7, True), (33, 17, 33, 17, False), (48, 32, 1, 1, False),
-                                             (256, 144, 16, 9, False)])
-def test_decoder_mirrors_encoder_and_oracle(host_coder, w, h, nh, nv, alpha):
+@pytest.mark.parametrize("w,h,nh,nv,alpha,model", [(64, 48, 8, 8, False, 0), (70, 33, 5, 7, True, 0), (33, 17, 33, 17, False, 0),
+                                                   (48, 32, 1, 1, False, 0), (256, 144, 16, 9, False, 0), (64, 48, 8, 8, False, 1),
+                                                   (70, 33, 5, 7, True, 1), (256, 144, 16, 9, False, 1)])
+def test_decoder_mirrors_encoder_and_oracle(host_coder, w, h, nh, nv, alpha, model):
     """The slice decoder the device runs (host-stepped): packets of the slice coder and of the oracle's encoder decode
     to the source frames in either channel order; damaged packets are reported, not decoded."""
-    base = fo.parse_config(ffv1_gpu.stream_setup(w, h, nh, nv, alpha)[0])
+    base = fo.parse_config(ffv1_gpu.stream_setup(w, h, nh, nv, alpha, model)[0])
     for k, f in enumerate(_content(w, h, seed=11)):
-        packet = host_coder(f, nh, nv, alpha, True)
-        rc, out = host_coder.decode(packet, w, h, nh, nv, alpha, True)
+        packet = host_coder(f, nh, nv, alpha, True, model)
+        rc, out = host_coder.decode(packet, w, h, nh, nv, alpha, True, model)
         assert rc == 0 and np.array_equal(out, f), f"content {k}"
-        rc, out = host_coder.decode(packet, w, h, nh, nv, alpha, False)     # RGB-order output of a BGR-order source
+        if k == 0 and 16 * nh * nv <= w * h <= 64 * 48 * 2:      # the other model's decoder must not reproduce the frame
+            assert not np.array_equal(host_coder.decode(packet, w, h, nh, nv, alpha, True, 1 - model)[1], f)
+        rc, out = host_coder.decode(packet, w, h, nh, nv, alpha, False, model)     # RGB-order output of a BGR-order source
         assert rc == 0 and np.array_equal(out, f[..., ::-1]), f"content {k} (channel order)"
         if w * h <= 64 * 48:
             ss = [fo.SliceState(base) for _ in range(nh * nv)]
             want = fo.encode_frame(np.dstack([f, np.full((h, w), 255, np.uint8)]), base, True, ss)
-            rc, out = host_coder.decode(want, w, h, nh, nv, alpha, True)
+            rc, out = host_coder.decode(want, w, h, nh, nv, alpha, True, model)
             assert rc == 0 and np.array_equal(out, f), f"content {k} (oracle packet)"
     bad = bytearray(packet)
     bad[0] ^= 0x40                                         # slice 0's header (key-frame bit / slice position)
-    assert host_coder.decode(bytes(bad), w, h, nh, nv, alpha, True)[0] == -1
-    assert host_coder.decode(packet[:-1], w, h, nh, nv, alpha, True)[0] != 0       # truncated: sizes do not add up
-    assert host_coder.decode(packet + b"\0", w, h, nh, nv, alpha, True)[0] != 0
+    assert host_coder.decode(bytes(bad), w, h, nh, nv, alpha, True, model)[0] == -1
+    assert host_coder.decode(packet[:-1], w, h, nh, nv, alpha, True, model)[0] != 0       # truncated: sizes do not add up
+    assert host_coder.decode(packet + b"\0", w, h, nh, nv, alpha, True, model)[0] != 0
 
 
 def test_decoder_rejects_opencv_non_key_frames(host_coder, tmp_path):
@@ -176,18 +153,19 @@ def test_parse_config_accepts_only_this_librarys_streams(tmp_path):
     from metric_depth_video_toolbox_b200 import _lib
 
     lib = _lib.load()
-    nh, nv, alpha = C.c_int(), C.c_int(), C.c_int()
-    for grid in ((59, 17, 0), (2, 2, 1), (1, 1, 0)):
-        cfg = ffv1_gpu.stream_setup(3840, 1080, grid[0], grid[1], bool(grid[2]))[0]
-        assert lib.mdvt_ffv1_parse_config(cfg, len(cfg), 3840, 1080, C.byref(nh), C.byref(nv), C.byref(alpha)) == 0
-        assert (nh.value, nv.value, alpha.value) == grid
+    nh, nv, alpha, model = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    for grid in ((59, 17, 0, 0), (2, 2, 1, 0), (1, 1, 0, 0), (59, 17, 0, 1), (4, 3, 1, 1)):
+        cfg = ffv1_gpu.stream_setup(3840, 1080, grid[0], grid[1], bool(grid[2]), grid[3])[0]
+        assert lib.mdvt_ffv1_parse_config(cfg, len(cfg), 3840, 1080, C.byref(nh), C.byref(nv), C.byref(alpha), C.byref(model)) == 0
+        assert (nh.value, nv.value, alpha.value, model.value) == grid
     pk = _cv_file(str(tmp_path / "cv.mkv"), _content(64, 48)[:1])
     cfg = pk.codec_private()                # OpenCV's record is byte-identical to this library's 2 x 2 + alpha record
-    assert lib.mdvt_ffv1_parse_config(cfg, len(cfg), 64, 48, C.byref(nh), C.byref(nv), C.byref(alpha)) == 0
+    assert lib.mdvt_ffv1_parse_config(cfg, len(cfg), 64, 48, C.byref(nh), C.byref(nv), C.byref(alpha), C.byref(model)) == 0
+    assert (nh.value, nv.value, alpha.value, model.value) == (2, 2, 1, 0)
     broken = bytearray(cfg)
     broken[20] ^= 1                         # inside the quant tables
-    assert lib.mdvt_ffv1_parse_config(bytes(broken), len(broken), 64, 48, C.byref(nh), C.byref(nv), C.byref(alpha)) == -2
-    assert lib.mdvt_ffv1_parse_config(b"\x00\x01\x02\x03", 4, 64, 48, C.byref(nh), C.byref(nv), C.byref(alpha)) == -2
+    assert lib.mdvt_ffv1_parse_config(bytes(broken), len(broken), 64, 48, C.byref(nh), C.byref(nv), C.byref(alpha), C.byref(model)) == -2
+    assert lib.mdvt_ffv1_parse_config(b"\x00\x01\x02\x03", 4, 64, 48, C.byref(nh), C.byref(nv), C.byref(alpha), C.byref(model)) == -2
 
 
 def test_rank_segments_join_at_packet_level(host_coder, tmp_path):

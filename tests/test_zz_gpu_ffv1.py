@@ -6,9 +6,7 @@
   1080p side-by-side result too;
 * the offsets / sizes the device reports add up.
 (Named zz: it runs after every other GPU test.)"""
-import ctypes as C
 import os
-import subprocess
 
 import cv2
 import numpy as np
@@ -44,38 +42,22 @@ def content(w, h, n, seed=0):
 
 @pytest.fixture(scope="module")
 def host_coder(tmp_path_factory):
-    so = str(tmp_path_factory.mktemp("ffv1_host") / "ffv1_slice_host.so")
-    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-I", os.path.join(ROOT, "metric_depth_video_toolbox_b200", "csrc"),
-                    os.path.join(ROOT, "tests", "support", "ffv1_slice_host.cpp"), "-o", so], check=True)
-    lib = C.CDLL(so)
-    lib.ffv1_host_encode_frame.restype = C.c_longlong
-    lib.ffv1_host_encode_frame.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
-                                           C.c_void_p, C.c_void_p, C.c_longlong]
+    from ffv1_host import HostCoder
 
-    def encode(frame, nh, nv, alpha, bgr):
-        h, w = frame.shape[:2]
-        frame = np.ascontiguousarray(frame)
-        _, headers, lens = ffv1_gpu.stream_setup(w, h, nh, nv, alpha)
-        cap = w * h * 12 + 4096 * nh * nv
-        out = np.zeros(cap, np.uint8)
-        n = lib.ffv1_host_encode_frame(frame.ctypes.data, frame.strides[0], w, h, nh, nv, 3 + int(alpha), int(bgr), headers.ctypes.data,
-                                       lens.ctypes.data, out.ctypes.data, cap)
-        assert n > 0
-        return out[:n].tobytes()
-
-    return encode
+    return HostCoder(str(tmp_path_factory.mktemp("ffv1_host")))
 
 
-@pytest.mark.parametrize("w,h,slices,alpha,rgb", [(256, 144, (16, 9), False, True), (200, 120, (7, 5), True, False),
-                                                  (320, 200, (32, 32), False, False), (64, 48, (1, 1), False, True)])
-def test_packets_equal_host_stepped_coder(host_coder, w, h, slices, alpha, rgb):
+@pytest.mark.parametrize("w,h,slices,alpha,rgb,model", [(256, 144, (16, 9), False, True, 0), (200, 120, (7, 5), True, False, 0),
+                                                        (320, 200, (32, 32), False, False, 0), (64, 48, (1, 1), False, True, 0),
+                                                        (256, 144, (16, 9), False, True, 1), (200, 120, (7, 5), True, False, 1)])
+def test_packets_equal_host_stepped_coder(host_coder, w, h, slices, alpha, rgb, model):
     frames = content(w, h, 6, seed=w)
-    enc = ffv1_gpu.Ffv1Encoder(w, h, DEV, max_frames=8, slices=slices, alpha=alpha)
+    enc = ffv1_gpu.Ffv1Encoder(w, h, DEV, max_frames=8, slices=slices, alpha=alpha, context_model=model)
     dev = torch.from_numpy(frames).to(DEV)
     packets = enc.encode(dev, rgb=rgb)
     assert len(packets) == len(frames)
     for k, f in enumerate(frames):
-        assert packets[k] == host_coder(f, slices[0], slices[1], alpha, not rgb), f"frame {k}"
+        assert packets[k] == host_coder(f, slices[0], slices[1], alpha, not rgb, model), f"frame {k}"
     s = enc.per_frame
     sizes = enc.sizes[: len(frames) * s].cpu().numpy().astype(np.int64)
     offsets = enc.offsets[: len(frames) * s + 1].cpu().numpy()
@@ -83,11 +65,11 @@ def test_packets_equal_host_stepped_coder(host_coder, w, h, slices, alpha, rgb):
     assert sizes.max() <= enc.capacity
 
 
-@pytest.mark.parametrize("w,h,n", [(640, 360, 9), (3840, 1080, 3)])
-def test_writer_files_decode_bit_exactly_in_opencv(tmp_path, w, h, n):
+@pytest.mark.parametrize("w,h,n,model", [(640, 360, 9, 0), (3840, 1080, 3, 0), (640, 360, 9, 1)])
+def test_writer_files_decode_bit_exactly_in_opencv(tmp_path, w, h, n, model):
     frames = content(w, h, n, seed=7)      # RGB order, as the renderers hold them
     path = str(tmp_path / "gpu.mkv")
-    wr = ffv1_gpu.GpuFfv1Writer(path, 24.0, (w, h), device=DEV, batch=4)
+    wr = ffv1_gpu.GpuFfv1Writer(path, 24.0, (w, h), device=DEV, batch=4, context_model=model)
     dev = torch.from_numpy(frames).to(DEV)
     wr.write(dev[:5], rgb=True)
     wr.write(dev[5:], rgb=True)
@@ -139,14 +121,15 @@ def test_cli_stereo_rerender_with_gpu_writer_equals_default_writer(tmp_path):
     assert not [f for f in os.listdir(tmp_path) if "_tmp_" in f or f.endswith(".joining")]
 
 
-@pytest.mark.parametrize("w,h,slices,alpha,rgb", [(256, 144, (16, 9), False, True), (200, 120, (7, 5), True, False),
-                                                  (320, 200, (32, 32), False, True)])
-def test_device_decoder_mirrors_encoder(w, h, slices, alpha, rgb):
+@pytest.mark.parametrize("w,h,slices,alpha,rgb,model", [(256, 144, (16, 9), False, True, 0), (200, 120, (7, 5), True, False, 0),
+                                                        (320, 200, (32, 32), False, True, 0), (256, 144, (16, 9), False, True, 1),
+                                                        (200, 120, (7, 5), True, False, 1)])
+def test_device_decoder_mirrors_encoder(w, h, slices, alpha, rgb, model):
     frames = content(w, h, 6, seed=w + 1)
-    enc = ffv1_gpu.Ffv1Encoder(w, h, DEV, max_frames=8, slices=slices, alpha=alpha)
+    enc = ffv1_gpu.Ffv1Encoder(w, h, DEV, max_frames=8, slices=slices, alpha=alpha, context_model=model)
     packets = enc.encode(torch.from_numpy(frames).to(DEV), rgb=rgb)
     dec = ffv1_gpu.Ffv1Decoder.for_config(enc.config, w, h, DEV, max_frames=8)
-    assert (dec.nh, dec.nv, dec.alpha) == (slices[0], slices[1], alpha)
+    assert (dec.nh, dec.nv, dec.alpha, dec.context_model) == (slices[0], slices[1], alpha, model)
     got = dec.decode(packets, rgb=rgb)
     assert got.is_cuda and np.array_equal(got.cpu().numpy(), frames)
     swapped = dec.decode(packets[:2], rgb=not rgb)
