@@ -202,6 +202,24 @@ def test_rank_segments_join_at_packet_level(host_coder, tmp_path):
     assert not os.path.exists(parts[0]) and not os.path.exists(parts[1])   # joined lanes are removed
 
 
+def test_slice_coder_under_address_sanitizer(tmp_path):
+    """The coder text the device runs, built for the host with ASan + UBSan: round trips over 1-pixel / ragged slices and
+    decoding of bit-flipped packets never leave the packet, the state block or the frame."""
+    import subprocess
+
+    from metric_depth_video_toolbox_b200 import build
+
+    exe = str(tmp_path / "ffv1_sanitize")
+    sup = os.path.join(ROOT, "tests", "support")
+    proc = subprocess.run(["g++", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-I",
+                           os.path.join(ROOT, "metric_depth_video_toolbox_b200", "csrc"), os.path.join(sup, "ffv1_sanitize_main.cpp"),
+                           os.path.join(sup, "ffv1_slice_host.cpp"), "-ldl", "-o", exe], capture_output=True, text=True)
+    if proc.returncode != 0:
+        pytest.skip("no sanitizer runtime for g++ here: " + proc.stderr[-200:])
+    run = subprocess.run([exe, build.build()], capture_output=True, text=True, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
+    assert run.returncode == 0 and "done, 0 bad" in run.stdout, run.stdout[-2000:] + run.stderr[-4000:]
+
+
 def test_slice_grid():
     for w, h in ((3840, 1080), (1920, 1080), (3840, 2160), (640, 480), (64, 48), (7, 3)):
         nh, nv = ffv1_gpu.slice_grid(w, h)
