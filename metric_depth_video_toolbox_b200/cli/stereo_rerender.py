@@ -168,7 +168,7 @@ def run(args, keep_process_group: bool = False) -> int:
     lanes = args.writer_lanes if args.writer_lanes > 0 else video_io.default_lanes(world_size)
     parallel = fourcc == "FFV1" and lanes > 1
 
-    gpu_ffv1 = bool(getattr(args, "gpu_ffv1", False)) or os.environ.get("MDVT_FFV1_WRITER", "") == "gpu"
+    gpu_ffv1 = video_io.gpu_ffv1_requested(getattr(args, "gpu_ffv1", False))
 
     def open_writer(path: str, cc: str):
         if gpu_ffv1 and cc == "FFV1":   # entropy coding on the device; ranks leave segments + plans for the packet-level join

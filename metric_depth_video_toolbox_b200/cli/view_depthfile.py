@@ -46,6 +46,8 @@ def build_parser() -> argparse.ArgumentParser:
     add("--ty", default=-99.0, type=float, help="camera target y coordinate in meters")
     add("--tz", default=-99.0, type=float, help="camera target z coordinate in meters")
     add("--chunk_frames", default=12, type=int, help="frames per GPU batch (addition; a multiple of 12 lets several decoders read one input)")
+    add("--gpu_ffv1", action="store_true", help="code the FFV1 result video on the GPU (addition; also MDVT_FFV1_WRITER=gpu): the rendered "
+        "frames never leave the device uncompressed; same container and codec, frames decode bit-identically")
     return p
 
 
@@ -86,8 +88,14 @@ def main(argv: Optional[List[str]] = None) -> int:
                                                  of_by_one=not args.render_as_pointcloud), device)
     output_file, fourcc = (args.depth_video + "_render.mp4", "avc1") if args.compressed else (args.depth_video + "_render.mkv", "FFV1")
     lanes = video_io.default_lanes()
-    writer = video_io.ParallelWriter(output_file, fps, (w, h), lanes=lanes) if (fourcc == "FFV1" and lanes > 1) else \
-        video_io.ChunkWriter(output_file, fourcc, fps, (w, h))
+    on_device = fourcc == "FFV1" and video_io.gpu_ffv1_requested(getattr(args, "gpu_ffv1", False))
+    if on_device:
+        from .. import ffv1_gpu
+
+        writer = ffv1_gpu.GpuFfv1Writer(output_file, fps, (w, h), device=device, batch=min(8, max(1, args.chunk_frames)))
+    else:
+        writer = video_io.ParallelWriter(output_file, fps, (w, h), lanes=lanes) if (fourcc == "FFV1" and lanes > 1) else \
+            video_io.ChunkWriter(output_file, fourcc, fps, (w, h))
     done = 0
     host_out = None
     for n, (depth_rgb, colour) in video_io.ChunkReader([args.depth_video, args.color_video], 0, total_frames, chunk=args.chunk_frames,
@@ -95,6 +103,11 @@ def main(argv: Optional[List[str]] = None) -> int:
         d = depth_rgb.to(device, non_blocking=True)
         c = d if colour is None else colour.to(device, non_blocking=True)
         rgb, _ = renderer.render_device(d, c, done)
+        if on_device:   # the writer takes its own device copy: no raw frame crosses PCIe
+            writer.write(rgb[:n])
+            done += n
+            print(f"Frame: {done} {done / fps}s", end="\r", file=sys.stderr)
+            continue
         if host_out is None:
             host_out = torch.empty((args.chunk_frames, h, w, 3), dtype=torch.uint8, pin_memory=True)
         host_out[:n].copy_(rgb, non_blocking=True)

@@ -155,8 +155,14 @@ def save_depth_video(frames, output_video_path, fps, max_depth_arg, rescale_widt
 
     # parallel FFV1 encoder lanes joined at packet level: the same frames as one cv2.VideoWriter would hold
     lanes = video_io.default_lanes()
-    out = video_io.ParallelWriter(output_video_path, fps, (rescale_width, rescale_height), lanes=lanes) if lanes > 1 else \
-        video_io.ChunkWriter(output_video_path, "FFV1", fps, (rescale_width, rescale_height))
+    on_device = video_io.gpu_ffv1_requested()   # MDVT_FFV1_WRITER=gpu: wire-format pixels go from the encode kernel to the FFV1 coder
+    if on_device:
+        from . import ffv1_gpu
+
+        out = ffv1_gpu.GpuFfv1Writer(output_video_path, fps, (rescale_width, rescale_height), device=_device())
+    else:
+        out = video_io.ParallelWriter(output_video_path, fps, (rescale_width, rescale_height), lanes=lanes) if lanes > 1 else \
+            video_io.ChunkWriter(output_video_path, "FFV1", fps, (rescale_width, rescale_height))
     batch = max(1, min(nr_frames, (256 << 20) // max(1, rescale_width * rescale_height * 4)))
     for start in range(0, nr_frames, batch):
         chunk = []
@@ -166,7 +172,8 @@ def save_depth_video(frames, output_video_path, fps, max_depth_arg, rescale_widt
                 depth = cv2.resize(depth, (rescale_width, rescale_height), interpolation=cv2.INTER_LINEAR)
             chunk.append(np.ascontiguousarray(depth, dtype=np.float32))
         dev = torch.from_numpy(np.stack(chunk)).to(_device())
-        out.write(ops.encode_depth(dev, max_depth_arg, True, True).cpu().numpy(), rgb=False)  # B, G, R like encode_data_as_BGR
+        coded = ops.encode_depth(dev, max_depth_arg, True, True)  # B, G, R like encode_data_as_BGR
+        out.write(coded if on_device else coded.cpu().numpy(), rgb=False)
     out.close()
 
 

@@ -237,6 +237,12 @@ class ChunkWriter:
 GOP = 12  # key-frame interval of OpenCV's FFmpeg writer (AVCodecContext.gop_size): rank ranges start on key frames of the inputs
 
 
+def gpu_ffv1_requested(flag: bool = False) -> bool:
+    """FFV1 result videos coded on the device (ffv1_gpu.GpuFfv1Writer) instead of by cv2.VideoWriter lanes: asked for by a
+    front end's --gpu_ffv1 or by MDVT_FFV1_WRITER=gpu in the environment."""
+    return bool(flag) or os.environ.get("MDVT_FFV1_WRITER", "") == "gpu"
+
+
 def default_lanes(world_size: int = 1) -> int:
     env = os.environ.get("MDVT_WRITER_LANES")
     if env:

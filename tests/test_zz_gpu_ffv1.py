@@ -165,3 +165,49 @@ def test_reader_reads_writer_files_and_refuses_opencv_files(tmp_path):
     video_io.write_clip(cvpath, frames[:3], 30.0)
     with pytest.raises(_lib.MdvtError):
         ffv1_gpu.GpuFfv1Reader(cvpath, device=DEV)
+
+
+def test_view_depthfile_and_save_depth_video_with_gpu_writer_equal_default_writers(tmp_path, monkeypatch):
+    """3d_view_depthfile --render --gpu_ffv1 and depth_frames_helper.save_depth_video under MDVT_FFV1_WRITER=gpu write the
+    same frames as their default (cv2.VideoWriter lanes) writers."""
+    import importlib
+
+    import depth_frames_helper as dfh
+    from metric_depth_video_toolbox_b200 import video_io
+    from metric_depth_video_toolbox_b200.synth import SyntheticClip
+
+    w, h, n = 192, 108, 5
+    depth, colour = SyntheticClip(w, h, n).frames()
+    dpath, cpath = str(tmp_path / "depth.mkv"), str(tmp_path / "colour.mkv")
+    video_io.write_clip(dpath, depth, 24.0)
+    video_io.write_clip(cpath, colour, 24.0)
+    view = importlib.import_module("3d_view_depthfile")
+    argv = ["--depth_video", dpath, "--color_video", cpath, "--xfov", "60", "--render", "--chunk_frames", "3"]
+    assert view.main(argv) == 0
+    want = video_io.read_clip(dpath + "_render.mkv")
+    os.remove(dpath + "_render.mkv")
+    assert view.main(argv + ["--gpu_ffv1"]) == 0
+    got = video_io.read_clip(dpath + "_render.mkv")
+    assert want.shape == (n, h, w, 3) and np.array_equal(got, want)
+
+    rng = np.random.default_rng(5)
+    metres = rng.uniform(0.2, 60, (n, 48, 64)).astype(np.float32)
+    a, b = str(tmp_path / "host.mkv"), str(tmp_path / "gpu.mkv")
+    dfh.save_depth_video(metres, a, 24.0, 100, 64, 48)
+    monkeypatch.setenv("MDVT_FFV1_WRITER", "gpu")
+    dfh.save_depth_video(metres, b, 24.0, 100, 64, 48)
+    monkeypatch.delenv("MDVT_FFV1_WRITER")
+    fa, fb = video_io.read_clip(a), video_io.read_clip(b)
+    assert fa.shape == (n, 48, 64, 3) and np.array_equal(fa, fb)
+    assert mkv_packets_all_key(b) and not mkv_packets_all_key(a)
+    assert dfh.verify_and_move(b, n, str(tmp_path / "final.mkv"))
+
+
+def mkv_packets_all_key(path):
+    from metric_depth_video_toolbox_b200 import mkv_join
+
+    pk = mkv_join.MkvPackets(path)
+    try:
+        return all(key for _, _, key in pk.packets)
+    finally:
+        pk.close()
