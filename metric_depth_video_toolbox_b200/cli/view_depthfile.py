@@ -105,6 +105,7 @@ def main(argv: Optional[List[str]] = None) -> int:
         rgb, _ = renderer.render_device(d, c, done)
         if on_device:   # the writer takes its own device copy: no raw frame crosses PCIe
             writer.write(rgb[:n])
+            torch.cuda.synchronize(device)   # as below: the reader may recycle its buffers, the renderer's second stream is idle
             done += n
             print(f"Frame: {done} {done / fps}s", end="\r", file=sys.stderr)
             continue
