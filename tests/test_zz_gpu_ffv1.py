@@ -211,3 +211,36 @@ def mkv_packets_all_key(path):
         return all(key for _, _, key in pk.packets)
     finally:
         pk.close()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_cli_stereo_rerender_gpu_writer_torchrun_two_ranks(tmp_path):
+    """--gpu_ffv1 under torchrun: every rank codes its GOP-aligned frame range into a segment, rank 0 joins the segments at
+    packet level; the joined files hold the frames of the single-process run."""
+    import subprocess
+    import sys
+
+    import stereo_rerender
+    from metric_depth_video_toolbox_b200 import video_io
+    from metric_depth_video_toolbox_b200.synth import SyntheticClip
+
+    w, h, n = 192, 108, 29            # 29 frames: ranges [0, 12) and [12, 29) with GOP-aligned starts
+    depth, colour = SyntheticClip(w, h, n).frames()
+    dpath, cpath = str(tmp_path / "depth.mkv"), str(tmp_path / "colour.mkv")
+    video_io.write_clip(dpath, depth, 24.0)
+    video_io.write_clip(cpath, colour, 24.0)
+    base = ["--depth_video", dpath, "--color_video", cpath, "--xfov", "60", "--infill_mask", "--green_and_black_infill_mask",
+            "--dont_place_points_in_edges", "--gpu_ffv1"]
+    names = [dpath + "_stereo.mkv", dpath + "_stereo.mkv_infillmask.mkv"]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port",
+           "29531", os.path.join(ROOT, "stereo_rerender.py")] + base
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    sharded = [video_io.read_clip(p) for p in names]
+    assert not [f for f in os.listdir(tmp_path) if ".rank" in f or f.endswith(".plan.json")]
+    for p in names:
+        os.remove(p)
+    assert stereo_rerender.main(base) == 0
+    for p, got in zip(names, sharded):
+        want = video_io.read_clip(p)
+        assert got.shape == want.shape and got.shape[0] == n and np.array_equal(got, want), p
