@@ -373,7 +373,7 @@ MDVT_API int mdvt_ffv1_parse_config(const uint8_t *config_host, int config_len, 
  * mdvt_ffv1_state_bytes scratch; slice_offsets: n_frames * nh * nv int64 of scratch.  frames: u8x3 output, RGB order (BGR
  * with bgr_order = 1).  status[f] (DEVICE, one per frame): 0 = decoded; -2 the slice sizes of the packet do not add up,
  * -3 a slice header is not the expected one (e.g. a non-key frame), -4 a slice size is inconsistent, -5 the bit stream
- * of a slice overran.  Slice CRCs are not verified. */
+ * of a slice overran, -6 a slice's CRC-32 is wrong (every slice is checked before it is decoded, as ffv1dec.c does). */
 MDVT_API int mdvt_ffv1_decode_frames(const uint8_t *packets, const int64_t *packet_offsets, int n_frames, int width, int height, int nh,
                             int nv, int alpha, int context_model, int bgr_order, const uint8_t *headers, const int32_t *header_len, void *states,
                             int64_t *slice_offsets, uint8_t *frames, int64_t frame_stride, int64_t row_pitch, int32_t *status,

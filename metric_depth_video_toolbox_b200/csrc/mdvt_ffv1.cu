@@ -288,6 +288,9 @@ __global__ void __launch_bounds__(64, 12) ffv1_decode_kernel(const uint8_t *__re
                                                          const uint8_t *__restrict__ headers, const int32_t *__restrict__ header_len,
                                                          mdvt_ffv1::VlcState *states, uint8_t *frames, int64_t frame_stride,
                                                          int64_t row_pitch, int32_t *status) {
+    __shared__ uint32_t crc_s[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) crc_s[i] = g_crc_table[i];
+    __syncthreads();
     const int per_frame = nh * nv;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)n_frames * per_frame) return;
@@ -311,8 +314,9 @@ __global__ void __launch_bounds__(64, 12) ffv1_decode_kernel(const uint8_t *__re
     in.ib = ib;
     in.ir = ir;
     in.states = states + t * (int64_t)((n_planes > 3 ? 3 : 2) * mdvt_ffv1::contexts_of(model));
+    in.crc_table = crc_s;
     const int code = model ? mdvt_ffv1::decode_slice<true>(in) : mdvt_ffv1::decode_slice<false>(in);
-    if (code < 0) atomicMin(&status[f], code - 2);   // -3: foreign slice header, -4: slice size, -5: bit stream overrun
+    if (code < 0) atomicMin(&status[f], code - 2);   // -3: foreign slice header, -4: slice size, -5: bit stream overrun, -6: CRC
 }
 
 // Packet layout: offsets[f * S + s] = first byte of slice s of frame f in the packed stream, offsets[n * S] = total.
@@ -547,6 +551,7 @@ extern "C" int mdvt_ffv1_decode_frames(const uint8_t *packets, const int64_t *pa
     const int per_frame = nh * nv;
     const int64_t total = (int64_t)n_frames * per_frame;
     MDVT_REQUIRE(total < (1LL << 30), "too many slices in one call");
+    mdvt::ffv1_crc_table_kernel<<<1, 256, 0, s>>>();
     mdvt::ffv1_index_kernel<<<(n_frames + 31) / 32, 32, 0, s>>>(packets, packet_offsets, n_frames, per_frame, slice_offsets, status);
     const int threads = 64;
     mdvt::ffv1_decode_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(

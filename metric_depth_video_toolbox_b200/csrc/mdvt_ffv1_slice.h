@@ -434,6 +434,7 @@ struct SliceInput {
     int64_t row_pitch;
     int w, h, n_planes, ib, ir;
     VlcState *states;
+    const uint32_t *crc_table;   // 256 entries (the first of BitSink's four tables)
 };
 
 // One line of one plane.  Plane 0 / 1 leave their samples in the output row as scratch (G' in the green byte; the low 8
@@ -506,7 +507,8 @@ MDVT_FFV1_HD inline void decode_line(BitSource &bs, VlcState *states, uint8_t *r
 }
 
 // Decodes one slice into the frame; returns 0, or a negative code: -1 the header is not the expected one, -2 the size in
-// the footer does not match, -3 the bit stream ran past the slice.
+// the footer does not match, -3 the bit stream ran past the slice, -4 the slice's CRC-32 is wrong (checked first: a damaged
+// slice is reported, not decoded -- ffv1dec.c decode_frame does the same check on every slice when ec is set).
 template <bool SMALL>
 MDVT_FFV1_HD inline int decode_slice(const SliceInput &in) {
     constexpr int NC = SMALL ? kContextsSmall : kContexts;
@@ -516,6 +518,9 @@ MDVT_FFV1_HD inline int decode_slice(const SliceInput &in) {
     const uint8_t *foot = in.data + in.size - kFooterBytes;
     const uint32_t body = ((uint32_t)foot[0] << 16) | ((uint32_t)foot[1] << 8) | (uint32_t)foot[2];
     if (body + kFooterBytes != in.size) return -2;
+    uint32_t crc = 0;   // over body, size, error status and the stored CRC: zero for an intact slice
+    for (uint32_t i = 0; i < in.size; ++i) crc = (crc << 8) ^ in.crc_table[(crc >> 24) ^ in.data[i]];
+    if (crc != 0) return -4;
     BitSource bs;
     bs.p = in.data + in.header_len;
     bs.end = foot;

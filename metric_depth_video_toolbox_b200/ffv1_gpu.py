@@ -179,7 +179,7 @@ class Ffv1Decoder:
         if (status != 0).any():
             k = int(np.nonzero(status)[0][0])
             reason = {-2: "slice sizes do not add up", -3: "foreign slice header (not a key frame of this library's stream)",
-                      -4: "inconsistent slice size", -5: "bit stream overrun"}.get(int(status[k]), "unknown")
+                      -4: "inconsistent slice size", -5: "bit stream overrun", -6: "slice CRC mismatch (damaged data)"}.get(int(status[k]), "unknown")
             raise _lib.MdvtError(int(status[k]), f"FFV1 packet {k} of {n}: {reason}")
         return out
 

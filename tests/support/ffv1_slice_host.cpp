@@ -101,6 +101,8 @@ extern "C" int ffv1_host_decode_frame(const uint8_t *packet, long long packet_le
             in.ib = bgr_order ? 0 : 2;
             in.ir = bgr_order ? 2 : 0;
             in.states = states;
+            init_crc();
+            in.crc_table = g_crc;
             rc = context_model ? mdvt_ffv1::decode_slice<true>(in) : mdvt_ffv1::decode_slice<false>(in);
         }
     free(states);

@@ -134,6 +134,9 @@ def test_decoder_mirrors_encoder_and_oracle(host_coder, w, h, nh, nv, alpha, mod
     bad = bytearray(packet)
     bad[0] ^= 0x40                                         # slice 0's header (key-frame bit / slice position)
     assert host_coder.decode(bytes(bad), w, h, nh, nv, alpha, True, model)[0] == -1
+    bad = bytearray(packet)
+    bad[len(bad) // 2] ^= 0x10                             # anywhere else: the slice's CRC catches it before decoding
+    assert host_coder.decode(bytes(bad), w, h, nh, nv, alpha, True, model)[0] in (-4, -10)
     assert host_coder.decode(packet[:-1], w, h, nh, nv, alpha, True, model)[0] != 0       # truncated: sizes do not add up
     assert host_coder.decode(packet + b"\0", w, h, nh, nv, alpha, True, model)[0] != 0
 
