@@ -60,6 +60,9 @@ class StereoJob:
         self._host: Dict[str, torch.Tensor] = {}
         self._dev: Dict[str, torch.Tensor] = {}
         self._zbuf = None
+        # True (set by the front end when the result videos are coded on the device): the plain stereo mode hands out its
+        # device tensors instead of downloading them -- valid until the next render_chunk, the writer takes its own copy
+        self.device_outputs = False
 
     def _host_buf(self, key: str, shape) -> torch.Tensor:
         buf = self._host.get(key)
@@ -79,6 +82,18 @@ class StereoJob:
         deferred_mask = None
         sbs = self._host_buf("main", (n, self.h, 2 * self.w, 3))
         mask = self._host_buf("mask", (n, self.h, 2 * self.w, 3)) if self.params.infill_mask else None
+        if self.device_outputs and not self.has_depth_output and self.infill is None:
+            d = self._dev_buf("d", depth_rgb.shape)
+            c = self._dev_buf("c", colour.shape)
+            d.copy_(depth_rgb, non_blocking=True)
+            c.copy_(colour, non_blocking=True)
+            dsbs = self._dev_buf("sbs", (n, self.h, 2 * self.w, 3))
+            dmask = self._dev_buf("mask", (n, self.h, 2 * self.w, 3)) if self.params.infill_mask else None
+            self.renderer.render_device(d, c, first_frame, dsbs, dmask, None)
+            out = {"main": dsbs}
+            if dmask is not None:
+                out["mask"] = dmask
+            return out
         if not self.has_depth_output and self.infill is None:  # the pipelined two-stream path
             self.renderer.render_host(depth_rgb, colour, sbs, mask, start_frame=first_frame, chunk_frames=max(1, min(n, 8)))
             out = {"main": sbs}

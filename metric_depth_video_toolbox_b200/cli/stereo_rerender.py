@@ -169,6 +169,7 @@ def run(args, keep_process_group: bool = False) -> int:
     parallel = fourcc == "FFV1" and lanes > 1
 
     gpu_ffv1 = video_io.gpu_ffv1_requested(getattr(args, "gpu_ffv1", False))
+    job.device_outputs = gpu_ffv1 and fourcc == "FFV1"   # plain stereo mode: SBS + mask go to the coder without a host round trip
 
     def open_writer(path: str, cc: str):
         if gpu_ffv1 and cc == "FFV1":   # entropy coding on the device; ranks leave segments + plans for the packet-level join

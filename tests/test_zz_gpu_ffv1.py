@@ -94,8 +94,10 @@ def test_rejects_host_tensors_and_bad_sizes():
     assert enc.encode(torch.zeros((0, 48, 64, 3), dtype=torch.uint8, device=DEV)) == []
 
 
-def test_cli_stereo_rerender_with_gpu_writer_equals_default_writer(tmp_path):
-    """stereo_rerender --gpu_ffv1 writes the same frames (main, mask and SBS depth video) as the default host writers."""
+@pytest.mark.parametrize("depth_video", [True, False])
+def test_cli_stereo_rerender_with_gpu_writer_equals_default_writer(tmp_path, depth_video):
+    """stereo_rerender --gpu_ffv1 writes the same frames (main, mask and SBS depth video) as the default host writers.
+    Without --create_sbs_depth_video the front end hands the device tensors of the row kernel straight to the coder."""
     import stereo_rerender   # the root-level launcher
     from metric_depth_video_toolbox_b200 import video_io
     from metric_depth_video_toolbox_b200.synth import SyntheticClip
@@ -106,8 +108,8 @@ def test_cli_stereo_rerender_with_gpu_writer_equals_default_writer(tmp_path):
     video_io.write_clip(dpath, depth, 24.0)
     video_io.write_clip(cpath, colour, 24.0)
     argv = ["--depth_video", dpath, "--color_video", cpath, "--xfov", "60", "--infill_mask", "--green_and_black_infill_mask",
-            "--dont_place_points_in_edges", "--create_sbs_depth_video", "--chunk_frames", "3"]
-    names = [dpath + "_stereo.mkv", dpath + "_stereo.mkv_infillmask.mkv", dpath + "_stereo.mkv_depth.mkv"]
+            "--dont_place_points_in_edges", "--chunk_frames", "3"] + (["--create_sbs_depth_video"] if depth_video else [])
+    names = [dpath + "_stereo.mkv", dpath + "_stereo.mkv_infillmask.mkv"] + ([dpath + "_stereo.mkv_depth.mkv"] if depth_video else [])
     assert stereo_rerender.main(argv) == 0
     want = [video_io.read_clip(p) for p in names]
     for p in names:
