@@ -205,6 +205,42 @@ def test_rank_segments_join_at_packet_level(host_coder, tmp_path):
     assert not os.path.exists(parts[0]) and not os.path.exists(parts[1])   # joined lanes are removed
 
 
+def test_round_trip_property(host_coder):
+    """Random sizes, slice grids, context models, channel orders and content classes: decode(encode(x)) == x, and the
+    packet is the oracle's for the small ones."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(w=st.integers(1, 96), h=st.integers(1, 40), fx=st.integers(1, 12), fy=st.integers(1, 12), alpha=st.booleans(), model=st.integers(0, 1),
+           bgr=st.booleans(), kind=st.integers(0, 4), seed=st.integers(0, 2**31 - 1))
+    def check(w, h, fx, fy, alpha, model, bgr, kind, seed):
+        nh, nv = min(fx, w), min(fy, h)
+        rng = np.random.default_rng(seed)
+        if kind == 0:
+            f = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        elif kind == 1:
+            f = np.full((h, w, 3), rng.integers(0, 256, 3), np.uint8)
+        elif kind == 2:
+            f = (rng.integers(0, 2, (h, w, 1), dtype=np.uint8) * 255).repeat(3, 2)
+            f[..., 1] = 255 - f[..., 1]
+        elif kind == 3:
+            f = (128 + rng.integers(-3, 4, (h, w, 3))).astype(np.uint8)
+        else:
+            yy, xx = np.mgrid[0:h, 0:w]
+            f = np.dstack([(3 * xx + yy) & 255, (xx + 2 * yy) & 255, (xx * yy) & 255]).astype(np.uint8)
+        packet = host_coder(f, nh, nv, alpha, bgr, model)
+        rc, out = host_coder.decode(packet, w, h, nh, nv, alpha, bgr, model)
+        assert rc == 0 and np.array_equal(out, f)
+        if w * h <= 600:
+            cfg = fo.parse_config(ffv1_gpu.stream_setup(w, h, nh, nv, alpha, model)[0])
+            ss = [fo.SliceState(cfg) for _ in range(nh * nv)]
+            src = f if bgr else f[..., ::-1]
+            assert fo.encode_frame(np.dstack([src, np.full((h, w), 255, np.uint8)]), cfg, True, ss) == packet
+
+    check()
+
+
 def test_slice_coder_under_address_sanitizer(tmp_path):
     """The coder text the device runs, built for the host with ASan + UBSan: round trips over 1-pixel / ragged slices and
     decoding of bit-flipped packets never leave the packet, the state block or the frame."""
