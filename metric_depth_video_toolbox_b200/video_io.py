@@ -39,21 +39,27 @@ def _is_ffv1(cap) -> bool:
 
 
 def default_decoders(world_size: int = 1) -> int:
-    """Decode threads per input video.  1: every input has its own sequential decoder.  More (MDVT_READER_THREADS) makes
-    each decoder seek to its chunks -- measured counter-productive with OpenCV, whose frame-exact seek lands on the key
-    frame at or before (target - 16) and decodes forward from there (~22 frames per seek with a GOP of 12): 3.5 -> 1.2
-    frames/s on two 4K inputs.  Kept for containers / builds with cheap exact seeks."""
+    """Decode threads per input video.  1: every input has its own sequential decoder.  More (MDVT_READER_THREADS) gives
+    every decoder its own chunks.  With seeking decoders that was measured counter-productive (OpenCV's frame-exact seek
+    lands on the key frame at or before (target - 16) and decodes forward from there, ~22 frames per seek with a GOP of
+    12: 3.5 -> 1.2 frames/s on two 4K inputs); Matroska inputs are now served without seeking (the chunk's packets are
+    copied into a small temporary file, _DecodeWorker).  One FFV1 decoder already runs up to four slice threads, so more
+    decoders only pay on hosts with more cores than 4 x inputs: on 8 cores one noisy 1080p input alone went 16 -> 22
+    frames/s with four such decoders, two inputs in lock step 16.9 -> 14.7 (cores already saturated); not yet measured
+    on the 16-core GPU box, hence still opt-in."""
     env = os.environ.get("MDVT_READER_THREADS")
     return max(1, int(env)) if env else 1
 
 
 class _DecodeWorker(threading.Thread):
-    """One cv2.VideoCapture on its own thread: fills (buffer, first frame, count) requests, seeking when the request
-    does not continue where the previous one ended."""
+    """One cv2.VideoCapture on its own thread: fills (buffer, first frame, count) requests.  A request that does not
+    continue where the previous one ended is served, when the input is a Matroska file `mkv_join` can read, from a small
+    temporary file holding just the packets from the key frame at or before `first` to the end of the request (a packet
+    copy: no seek, no decoding of frames nobody asked for beyond that GOP); otherwise by seeking."""
 
-    def __init__(self, path: str, grey: bool):
+    def __init__(self, path: str, grey: bool, cut: bool = False):
         super().__init__(daemon=True)
-        self.path, self.grey = path, grey
+        self.path, self.grey, self.cut = path, grey, cut
         self.tasks: "queue.Queue" = queue.Queue()
         self.start()
 
@@ -62,34 +68,97 @@ class _DecodeWorker(threading.Thread):
         self.tasks.put((buf, first, count, ticket))
         return ticket
 
+    def _read(self, cap, out, count: int, code) -> int:
+        cv2 = _cv2()
+        n = 0
+        while n < count:
+            ok, frame = cap.read()
+            if not ok:
+                break
+            cv2.cvtColor(frame, code, dst=out[n])
+            n += 1
+        return n
+
+    def _read_cut(self, packets, fps: float, out, first: int, count: int, code) -> int:
+        """Frames [first, first + count) through a temporary file of their packets."""
+        import tempfile
+
+        from . import mkv_join
+
+        cv2 = _cv2()
+        total = len(packets.packets)
+        if first >= total:
+            return 0
+        key = first
+        while key > 0 and not packets.packets[key][2]:
+            key -= 1
+        stop = min(total, first + count)
+        fd, tmp = tempfile.mkstemp(suffix=".mkv", prefix="mdvt_cut_")
+        os.close(fd)
+        try:
+            mkv_join.write_stream(tmp, packets.ebml_header, packets.tracks,
+                                  ((packets.payload(k), packets.packets[k][2]) for k in range(key, stop)), stop - key, fps)
+            cap = cv2.VideoCapture(tmp)
+            for _ in range(first - key):
+                if not cap.grab():
+                    break
+            n = self._read(cap, out, stop - first, code)
+            cap.release()
+            return n
+        finally:
+            if os.path.exists(tmp):
+                os.remove(tmp)
+
     def run(self):
         cv2 = _cv2()
         cap = cv2.VideoCapture(self.path)
+        fps = cap.get(cv2.CAP_PROP_FPS) or 24.0
+        packets = None
+        if self.cut:
+            try:
+                from . import mkv_join
+
+                packets = mkv_join.MkvPackets(self.path)
+            except Exception:   # not a file mkv_join reads: seek instead
+                packets = None
         pos = 0
         code = cv2.COLOR_BGR2GRAY if self.grey else cv2.COLOR_BGR2RGB
         while True:
             item = self.tasks.get()
             if item is None:
                 cap.release()
+                if packets is not None:
+                    packets.close()
                 return
             buf, first, count, ticket = item
             try:
-                if first != pos:
-                    cap.set(cv2.CAP_PROP_POS_FRAMES, first)  # block starts are key frames of FFV1 / intra-only sources: exact
-                    pos = first
                 out = buf.numpy()
-                n = 0
-                while n < count:
-                    ok, frame = cap.read()
-                    if not ok:
-                        break
-                    cv2.cvtColor(frame, code, dst=out[n])
-                    n += 1
-                    pos += 1
-                ticket["n"] = n
+                if first != pos and packets is not None:
+                    ticket["n"] = self._read_cut(packets, fps, out, first, count, code)
+                else:
+                    if first != pos:
+                        cap.set(cv2.CAP_PROP_POS_FRAMES, first)  # block starts are key frames of FFV1 / intra-only sources: exact
+                        pos = first
+                    n = self._read(cap, out, count, code)
+                    pos += n
+                    ticket["n"] = n
             except BaseException as exc:
                 ticket["err"] = exc
             ticket["done"].set()
+
+
+def _can_cut(path: str) -> bool:
+    """True when `mkv_join` can take the file apart packet by packet (what _DecodeWorker needs to serve a frame range
+    without seeking)."""
+    from . import mkv_join
+
+    try:
+        pk = mkv_join.MkvPackets(path)
+        ok = len(pk.packets) > 0 and pk.packets[0][2]
+        pk.close()
+        return bool(ok)
+    except Exception:
+        return False
 
 
 class ChunkReader:
@@ -115,9 +184,12 @@ class ChunkReader:
                 c.release()
         self.start, self.stop = start, total if stop is None else min(stop, total)
         self.chunk, self.pin = max(1, chunk), pin and torch.cuda.is_available()
-        # parallel decode needs exact, cheap seeks: FFV1 written with OpenCV's GOP, chunks that start on key frames
-        self.decoders = max(1, decoders) if (all_ffv1 and self.chunk % GOP == 0 and start % GOP == 0) else 1
-        self._workers = [None if p is None else [_DecodeWorker(p, g) for _ in range(self.decoders)] for p, g in zip(self.paths, self.grey)]
+        # parallel decode: every decoder is handed the packets of its chunk (any chunk size / start) when the containers can be
+        # taken apart; else it needs exact seeks: FFV1 written with OpenCV's GOP, chunks that start on key frames
+        cut = decoders > 1 and all_ffv1 and all(_can_cut(p) for p in self.paths if p is not None)
+        self.decoders = max(1, decoders) if (cut or (all_ffv1 and self.chunk % GOP == 0 and start % GOP == 0)) else 1
+        self._workers = [None if p is None else [_DecodeWorker(p, g, cut) for _ in range(self.decoders)]
+                         for p, g in zip(self.paths, self.grey)]
         self._q: "queue.Queue" = queue.Queue(maxsize=max(1, depth))
         self._free: "queue.Queue" = queue.Queue()
         for _ in range(depth + 1 + self.decoders):   # pinned: 300 MB per 12-frame 4K chunk, keep the ring short

@@ -264,6 +264,7 @@ def test_chunk_reader_parallel_decoders_read_the_same_frames(tmp_path, decoders,
     w.write(b)
     w.close()
     r = video_io.ChunkReader([pa, pb], start, None, chunk=chunk, decoders=decoders, pin=False)
+    assert r.decoders == decoders      # Matroska inputs: every decoder is handed the packets of its chunks, any chunk size / start
     got_a, got_b = [], []
     for n, (xa, xb) in r:
         got_a.append(xa.numpy().copy())
