@@ -219,8 +219,19 @@ class GpuFfv1Reader:
         self._pk.close()
 
 
+_TEMPLATES: dict = {}
+
+
 def container_template(width: int, height: int, fps: float):
-    """(EBML header, Tracks payload) of the file OpenCV/FFmpeg write for an FFV1 video of this size and rate."""
+    """(EBML header, Tracks payload) of the file OpenCV/FFmpeg write for an FFV1 video of this size and rate (made once
+    per size and rate: cv2.VideoWriter codes a whole frame for it)."""
+    key = (int(width), int(height), float(fps))
+    if key not in _TEMPLATES:
+        _TEMPLATES[key] = _make_container_template(*key)
+    return _TEMPLATES[key]
+
+
+def _make_container_template(width: int, height: int, fps: float):
     import cv2
 
     fd, path = tempfile.mkstemp(suffix=".mkv", prefix="mdvt_ffv1_template_")
