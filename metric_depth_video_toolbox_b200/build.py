@@ -48,17 +48,36 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every source to an object file (in parallel: the sources are independent) and link the shared library."""
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", INCLUDE, "-I", CSRC]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or proc.returncode != 0:
-        sys.stderr.write(proc.stdout + proc.stderr)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed building libmdvt_b200.so")
+    import tempfile
+    from concurrent.futures import ThreadPoolExecutor
+
+    nvcc = _nvcc()
+    compile_flags = [f for f in NVCC_FLAGS if f != "--shared"]
+    with tempfile.TemporaryDirectory(prefix="mdvt_b200_build_") as tmp:
+        def compile_one(src: str):
+            obj = os.path.join(tmp, os.path.splitext(src)[0] + ".o")
+            cmd = [nvcc, *compile_flags, "-I", INCLUDE, "-I", CSRC] + (["-Xptxas", "-v"] if verbose else []) + \
+                ["-c", os.path.join(CSRC, src), "-o", obj]
+            return obj, subprocess.run(cmd, capture_output=True, text=True)
+
+        with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as pool:
+            results = list(pool.map(compile_one, SOURCES))
+        failed = [r for _, r in results if r.returncode != 0]
+        if verbose or failed:
+            for _, r in results:
+                sys.stderr.write(r.stdout + r.stderr)
+        if failed:
+            raise RuntimeError("nvcc failed building libmdvt_b200.so")
+        tmp_lib = LIB_PATH + ".linking"
+        link = subprocess.run([nvcc, *NVCC_FLAGS, *[obj for obj, _ in results], "-o", tmp_lib], capture_output=True, text=True)
+        if verbose or link.returncode != 0:
+            sys.stderr.write(link.stdout + link.stderr)
+        if link.returncode != 0:
+            raise RuntimeError("nvcc failed linking libmdvt_b200.so")
+        os.replace(tmp_lib, LIB_PATH)
     return LIB_PATH
 
 
