@@ -106,3 +106,29 @@ def test_ops_refuse_cpu_tensors():
     with pytest.raises(TypeError, match="no CPU path"):
         ops.stereo_rows(torch.zeros((1, 2, 16, 3), dtype=torch.uint8), torch.zeros((1, 2, 16, 3), dtype=torch.uint8),
                         torch.zeros((1, 4)))
+
+
+def test_ffv1_argument_validation_without_a_device():
+    lib = _lib.load()
+    cfg = (C.c_uint8 * 64)()
+    n = C.c_int()
+    hdr = (C.c_uint8 * (16 * 1024))()
+    lens = (C.c_int32 * 1024)()
+    assert lib.mdvt_ffv1_stream_setup(64, 48, 2, 2, 1, 0, cfg, 64, C.byref(n), hdr, lens) == 0 and n.value == 42
+    assert lib.mdvt_ffv1_stream_setup(64, 48, 2, 2, 0, 1, cfg, 64, C.byref(n), hdr, lens) == 0 and 0 < n.value < 42   # one quant-table set
+    assert lib.mdvt_ffv1_stream_setup(64, 48, 2, 2, 1, 0, cfg, 8, C.byref(n), hdr, lens) == -1                         # record does not fit
+    assert lib.mdvt_ffv1_stream_setup(64, 48, 33, 32, 0, 0, cfg, 64, C.byref(n), hdr, lens) == -1
+    assert b"1024" in lib.mdvt_last_error()
+    assert lib.mdvt_ffv1_stream_setup(64, 48, 65, 1, 0, 0, cfg, 64, C.byref(n), hdr, lens) == -1                       # more slices than columns
+    assert lib.mdvt_ffv1_stream_setup(64, 48, 2, 2, 0, 2, cfg, 64, C.byref(n), hdr, lens) == -1                        # unknown context model
+    assert lib.mdvt_ffv1_slice_capacity(3840, 1080, 59, 17, 0) % 16 == 0 and lib.mdvt_ffv1_slice_capacity(3840, 1080, 59, 17, 0) > 66 * 64 * 3
+    assert lib.mdvt_ffv1_slice_capacity(0, 1080, 1, 1, 0) == -1
+    assert lib.mdvt_ffv1_state_bytes(2, 59, 17, 0, 0) == 2 * 1003 * 2 * 666 * 8
+    assert lib.mdvt_ffv1_state_bytes(2, 59, 17, 1, 1) == 2 * 1003 * 3 * 63 * 8
+    assert lib.mdvt_ffv1_state_bytes(2, 59, 17, 0, 3) == -1
+    assert lib.mdvt_ffv1_encode_frames(None, 0, 0, 0, 64, 48, 2, 2, 0, 0, 0, None, None, None, None, 0, None, None, None, None) == 0  # no frames
+    assert lib.mdvt_ffv1_encode_frames(None, 0, 0, 1, 64, 48, 2, 2, 0, 0, 0, None, None, None, None, 16, None, None, None, None) == -1
+    assert b"capacity" in lib.mdvt_last_error()
+    assert lib.mdvt_ffv1_decode_frames(None, None, 0, 64, 48, 2, 2, 0, 0, 0, None, None, None, None, None, 0, 0, None, None) == 0
+    assert lib.mdvt_ffv1_decode_frames(None, None, 1, 64, 48, 2, 2, 0, 0, 0, None, None, None, None, None, 1, 1, None, None) == -1
+    assert b"pitch" in lib.mdvt_last_error()
