@@ -450,6 +450,9 @@ MDVT_FFV1_HD inline void decode_line(BitSource &bs, VlcState *states, uint8_t *r
     int run_count = 0, run_mode = 0;
     int row_first = 0;
     for (int x = 0; x < w; ++x) {
+        // the next sample's upper-right neighbour: a load that does not depend on the serial chain, issued a whole sample early
+        const int xr = x + 2 < last ? x + 2 : last;
+        const int RT_next = has_up ? plane_of_pixel<PL>(up + 3 * xr, ib, ir) : 0;
         const int q_t_rt = quant<SMALL>(T - RT);
         int ctx = quant<SMALL>(L - LT) + (SMALL ? 5 : 11) * q_lt_t + (SMALL ? 25 : 121) * q_t_rt;
         const bool sign = ctx < 0;
@@ -499,8 +502,7 @@ MDVT_FFV1_HD inline void decode_line(BitSource &bs, VlcState *states, uint8_t *r
         T = RT;
         L = cur;
         q_lt_t = q_t_rt;
-        const int xr = x + 2 < last ? x + 2 : last;
-        RT = has_up ? plane_of_pixel<PL>(up + 3 * xr, ib, ir) : 0;
+        RT = RT_next;
     }
     first2 = first1;
     first1 = row_first;
