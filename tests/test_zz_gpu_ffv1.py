@@ -48,8 +48,7 @@ def host_coder(tmp_path_factory):
 
 
 @pytest.mark.parametrize("w,h,slices,alpha,rgb,model", [(256, 144, (16, 9), False, True, 0), (200, 120, (7, 5), True, False, 0),
-                                                        (320, 200, (32, 32), False, False, 0), (64, 48, (1, 1), False, True, 0),
-                                                        (256, 144, (16, 9), False, True, 1), (200, 120, (7, 5), True, False, 1)])
+                                                        (320, 200, (32, 32), False, False, 0), (64, 48, (1, 1), False, True, 0)])
 def test_packets_equal_host_stepped_coder(host_coder, w, h, slices, alpha, rgb, model):
     frames = content(w, h, 6, seed=w)
     enc = ffv1_gpu.Ffv1Encoder(w, h, DEV, max_frames=8, slices=slices, alpha=alpha, context_model=model)
@@ -65,7 +64,7 @@ def test_packets_equal_host_stepped_coder(host_coder, w, h, slices, alpha, rgb, 
     assert sizes.max() <= enc.capacity
 
 
-@pytest.mark.parametrize("w,h,n,model", [(640, 360, 9, 0), (3840, 1080, 3, 0), (640, 360, 9, 1)])
+@pytest.mark.parametrize("w,h,n,model", [(640, 360, 9, 0), (3840, 1080, 3, 0)])
 def test_writer_files_decode_bit_exactly_in_opencv(tmp_path, w, h, n, model):
     frames = content(w, h, n, seed=7)      # RGB order, as the renderers hold them
     path = str(tmp_path / "gpu.mkv")
@@ -94,8 +93,7 @@ def test_rejects_host_tensors_and_bad_sizes():
     assert enc.encode(torch.zeros((0, 48, 64, 3), dtype=torch.uint8, device=DEV)) == []
 
 
-@pytest.mark.parametrize("depth_video", [True, False])
-def test_cli_stereo_rerender_with_gpu_writer_equals_default_writer(tmp_path, depth_video):
+def test_cli_stereo_rerender_with_gpu_writer_equals_default_writer(tmp_path, depth_video=True):
     """stereo_rerender --gpu_ffv1 writes the same frames (main, mask and SBS depth video) as the default host writers.
     Without --create_sbs_depth_video the front end hands the device tensors of the row kernel straight to the coder."""
     import stereo_rerender   # the root-level launcher
@@ -124,8 +122,7 @@ def test_cli_stereo_rerender_with_gpu_writer_equals_default_writer(tmp_path, dep
 
 
 @pytest.mark.parametrize("w,h,slices,alpha,rgb,model", [(256, 144, (16, 9), False, True, 0), (200, 120, (7, 5), True, False, 0),
-                                                        (320, 200, (32, 32), False, True, 0), (256, 144, (16, 9), False, True, 1),
-                                                        (200, 120, (7, 5), True, False, 1)])
+                                                        (320, 200, (32, 32), False, True, 0)])
 def test_device_decoder_mirrors_encoder(w, h, slices, alpha, rgb, model):
     frames = content(w, h, 6, seed=w + 1)
     enc = ffv1_gpu.Ffv1Encoder(w, h, DEV, max_frames=8, slices=slices, alpha=alpha, context_model=model)
@@ -167,6 +164,59 @@ def test_reader_reads_writer_files_and_refuses_opencv_files(tmp_path):
     video_io.write_clip(cvpath, frames[:3], 30.0)
     with pytest.raises(_lib.MdvtError):
         ffv1_gpu.GpuFfv1Reader(cvpath, device=DEV)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_cli_stereo_rerender_gpu_writer_torchrun_two_ranks(tmp_path):
+    """--gpu_ffv1 under torchrun: every rank codes its GOP-aligned frame range into a segment, rank 0 joins the segments at
+    packet level; the joined files hold the frames of the single-process run."""
+    import subprocess
+    import sys
+
+    import stereo_rerender
+    from metric_depth_video_toolbox_b200 import video_io
+    from metric_depth_video_toolbox_b200.synth import SyntheticClip
+
+    w, h, n = 192, 108, 29            # 29 frames: ranges [0, 12) and [12, 29) with GOP-aligned starts
+    depth, colour = SyntheticClip(w, h, n).frames()
+    dpath, cpath = str(tmp_path / "depth.mkv"), str(tmp_path / "colour.mkv")
+    video_io.write_clip(dpath, depth, 24.0)
+    video_io.write_clip(cpath, colour, 24.0)
+    base = ["--depth_video", dpath, "--color_video", cpath, "--xfov", "60", "--infill_mask", "--green_and_black_infill_mask",
+            "--dont_place_points_in_edges", "--gpu_ffv1"]
+    names = [dpath + "_stereo.mkv", dpath + "_stereo.mkv_infillmask.mkv"]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port",
+           "29531", os.path.join(ROOT, "stereo_rerender.py")] + base
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    sharded = [video_io.read_clip(p) for p in names]
+    assert not [f for f in os.listdir(tmp_path) if ".rank" in f or f.endswith(".plan.json")]
+    for p in names:
+        os.remove(p)
+    assert stereo_rerender.main(base) == 0
+    for p, got in zip(names, sharded):
+        want = video_io.read_clip(p)
+        assert got.shape == want.shape and got.shape[0] == n and np.array_equal(got, want), p
+
+
+# ---- context model 1 (63 contexts): same kernels instantiated with the 5-level quantiser ------------------------------------
+@pytest.mark.parametrize("w,h,slices,alpha,rgb", [(256, 144, (16, 9), False, True), (200, 120, (7, 5), True, False)])
+def test_small_context_model_packets_equal_host_stepped_coder(host_coder, w, h, slices, alpha, rgb):
+    test_packets_equal_host_stepped_coder(host_coder, w, h, slices, alpha, rgb, 1)
+
+
+def test_small_context_model_files_decode_bit_exactly_in_opencv(tmp_path):
+    test_writer_files_decode_bit_exactly_in_opencv(tmp_path, 640, 360, 9, 1)
+
+
+@pytest.mark.parametrize("w,h,slices,alpha,rgb", [(256, 144, (16, 9), False, True), (200, 120, (7, 5), True, False)])
+def test_small_context_model_decoder_mirrors_encoder(w, h, slices, alpha, rgb):
+    test_device_decoder_mirrors_encoder(w, h, slices, alpha, rgb, 1)
+
+
+def test_cli_stereo_rerender_with_gpu_writer_device_hand_off(tmp_path):
+    """Without --create_sbs_depth_video the plain stereo mode hands the row kernel's device tensors to the coder."""
+    test_cli_stereo_rerender_with_gpu_writer_equals_default_writer(tmp_path, depth_video=False)
 
 
 def test_view_depthfile_and_save_depth_video_with_gpu_writer_equal_default_writers(tmp_path, monkeypatch):
@@ -213,36 +263,3 @@ def mkv_packets_all_key(path):
         return all(key for _, _, key in pk.packets)
     finally:
         pk.close()
-
-
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_cli_stereo_rerender_gpu_writer_torchrun_two_ranks(tmp_path):
-    """--gpu_ffv1 under torchrun: every rank codes its GOP-aligned frame range into a segment, rank 0 joins the segments at
-    packet level; the joined files hold the frames of the single-process run."""
-    import subprocess
-    import sys
-
-    import stereo_rerender
-    from metric_depth_video_toolbox_b200 import video_io
-    from metric_depth_video_toolbox_b200.synth import SyntheticClip
-
-    w, h, n = 192, 108, 29            # 29 frames: ranges [0, 12) and [12, 29) with GOP-aligned starts
-    depth, colour = SyntheticClip(w, h, n).frames()
-    dpath, cpath = str(tmp_path / "depth.mkv"), str(tmp_path / "colour.mkv")
-    video_io.write_clip(dpath, depth, 24.0)
-    video_io.write_clip(cpath, colour, 24.0)
-    base = ["--depth_video", dpath, "--color_video", cpath, "--xfov", "60", "--infill_mask", "--green_and_black_infill_mask",
-            "--dont_place_points_in_edges", "--gpu_ffv1"]
-    names = [dpath + "_stereo.mkv", dpath + "_stereo.mkv_infillmask.mkv"]
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port",
-           "29531", os.path.join(ROOT, "stereo_rerender.py")] + base
-    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
-    assert proc.returncode == 0, proc.stderr[-2000:]
-    sharded = [video_io.read_clip(p) for p in names]
-    assert not [f for f in os.listdir(tmp_path) if ".rank" in f or f.endswith(".plan.json")]
-    for p in names:
-        os.remove(p)
-    assert stereo_rerender.main(base) == 0
-    for p, got in zip(names, sharded):
-        want = video_io.read_clip(p)
-        assert got.shape == want.shape and got.shape[0] == n and np.array_equal(got, want), p
