@@ -41,6 +41,7 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--cv_frames", type=int, default=2)
     ap.add_argument("--context_model", type=int, default=0, help="0: libavcodec's 666 contexts, 1: 63 contexts")
+    ap.add_argument("--decode", action="store_true", help="also time Ffv1Decoder.decode on the packets (H2D of the packets + kernels + status read)")
     ap.add_argument("--encode_only", action="store_true", help="skip the cv2.VideoWriter and file legs")
     ap.add_argument("--grids", default="auto,32x32,16x16", help="slice grids to time: auto or NHxNV, comma separated")
     a = ap.parse_args()
@@ -69,6 +70,19 @@ def main():
                           "batch": a.batch, "device_ms_per_frame": ms / a.frames, "device_frames_per_s": 1000.0 * a.frames / ms,
                           "with_d2h_frames_per_s": a.frames / host_s, "bytes_per_frame": nbytes / a.frames,
                           "bits_per_pixel": 8.0 * nbytes / a.frames / (a.width * a.height)}), flush=True)
+        if a.decode:
+            packets = enc.encode(d[: a.batch])
+            dec = ffv1_gpu.Ffv1Decoder.for_config(enc.config, a.width, a.height, dev, max_frames=a.batch)
+            out = torch.empty((len(packets), a.height, a.width, 3), dtype=torch.uint8, device=dev)
+            dec.decode(packets, out=out)          # warm-up: staging buffers
+            t0 = time.perf_counter()
+            for _ in range(a.reps):
+                dec.decode(packets, out=out)
+            dt = (time.perf_counter() - t0) / a.reps
+            print(json.dumps({"what": "device FFV1 decode (packets in host memory -> frames on the device)", "slices": [dec.nh, dec.nv],
+                              "context_model": dec.context_model, "batch": len(packets), "frames_per_s": len(packets) / dt,
+                              "ms_per_frame": 1e3 * dt / len(packets), "identical": bool(torch.equal(out, d[: a.batch]))}), flush=True)
+            del dec, out
         del enc
     if a.encode_only:
         return

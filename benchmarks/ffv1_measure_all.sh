@@ -6,7 +6,7 @@ set -u
 mkdir -p gpurun_out
 timeout 120 python -m pytest tests/test_zz_gpu_ffv1.py -q 2>&1 | tail -15 > gpurun_out/ffv1_tests.log
 for model in 0 1; do
-  timeout 60 python benchmarks/ffv1_gpu_bench.py --frames 64 --batch 64 --reps 3 --grids auto,32x16,16x16 --context_model $model --encode_only \
+  timeout 60 python benchmarks/ffv1_gpu_bench.py --frames 64 --batch 64 --reps 3 --grids auto,32x16,16x16 --context_model $model --encode_only --decode \
     > gpurun_out/ffv1_bench_model${model}.jsonl 2> gpurun_out/ffv1_bench_model${model}.err
 done
 timeout 60 python benchmarks/ffv1_gpu_bench.py --frames 16 --batch 8 --reps 3 --grids auto > gpurun_out/ffv1_bench_batch8_files.jsonl 2>&1
