@@ -16,6 +16,32 @@ from metric_depth_video_toolbox_b200 import mkv_join
 from oracle import ffv1_oracle as fo
 
 W, H = 64, 48
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ffv1_opencv.npz")
+
+
+def _golden():
+    g = np.load(GOLDEN)
+    bounds = np.concatenate([[0], np.cumsum(g["packet_sizes"])])
+    packets = [g["packets"][bounds[k]:bounds[k + 1]].tobytes() for k in range(len(g["packet_sizes"]))]
+    return g["frames_bgr"], g["config"].tobytes(), packets, [bool(k) for k in g["keys"]]
+
+
+def test_committed_golden_clip():
+    """tests/golden/ffv1_opencv.npz (oracle/make_ffv1_golden.py: cv2.VideoWriter output of OpenCV 4.13.0 / avcodec
+    62.11.100): the oracle decodes libavcodec's packets to the frames and re-encodes them byte for byte, whatever the
+    OpenCV build of the machine the tests run on writes."""
+    frames, config, packets, keys = _golden()
+    cfg = fo.parse_config(config)
+    assert fo.crc32_mpeg(config) == 0 and fo.write_config(cfg, cfg["num_h_slices"], cfg["num_v_slices"]) == config
+    assert (cfg["version"], cfg["ac"], cfg["colorspace"], cfg["transparency"], cfg["num_h_slices"], cfg["num_v_slices"]) == (3, 0, 1, 1, 2, 2)
+    assert keys == [True, False, False, False, False]
+    h, w = frames.shape[1:3]
+    dec = [fo.SliceState(cfg) for _ in range(4)]
+    enc = [fo.SliceState(cfg) for _ in range(4)]
+    for k, f in enumerate(frames):
+        out, key = fo.decode_frame(packets[k], cfg, w, h, dec)
+        assert bool(key) == keys[k] and np.array_equal(out[..., :3], f) and (out[..., 3] == 255).all()
+        assert fo.encode_frame(_bgra(f), cfg, keys[k], enc) == packets[k], f"packet {k}"
 
 
 def _frames(n, seed=0):
@@ -43,6 +69,9 @@ def cv_file(tmp_path_factory):
         wr.write(f)
     wr.release()
     pk = mkv_join.MkvPackets(path)
+    if pk.codec_private() != _golden()[1]:
+        pytest.skip("this OpenCV / libavcodec build writes other FFV1 stream parameters than the committed golden clip's; "
+                    "the byte-identity pins run against tests/golden/ffv1_opencv.npz only")
     return frames, pk, fo.parse_config(pk.codec_private())
 
 

@@ -29,7 +29,12 @@ def _cv_file(path, frames, fps=24.0):
     for f in frames:
         wr.write(f)
     wr.release()
-    return mkv_join.MkvPackets(path)
+    pk = mkv_join.MkvPackets(path)
+    golden = np.load(os.path.join(ROOT, "tests", "golden", "ffv1_opencv.npz"))["config"].tobytes()
+    if pk.codec_private() != golden:
+        pytest.skip("this OpenCV / libavcodec build writes other FFV1 stream parameters than the committed golden clip's "
+                    "(tests/golden/ffv1_opencv.npz); the byte-identity pins against libavcodec run on the golden clip only")
+    return pk
 
 
 def _content(w, h, seed=0):
@@ -64,6 +69,26 @@ def test_config_record_and_headers_match_libavcodec(tmp_path):
         assert (c["num_h_slices"], c["num_v_slices"], c["transparency"], c["ec"], c["version"], c["ac"]) == (nh, nv, int(alpha), 1, 3, 0)
         assert c["quant_tables"] == cfg["quant_tables"] and fo.crc32_mpeg(config) == 0
         assert lens.min() >= 2 and lens.max() <= 16 and headers.shape == (nh * nv, 16)
+
+
+def test_golden_clip_pins_setup_coder_and_decoder(host_coder):
+    """Against the committed libavcodec output (tests/golden/ffv1_opencv.npz, independent of the local OpenCV build): the
+    configuration record of mdvt_ffv1_stream_setup(2 x 2, alpha) is its CodecPrivate, the slice coder reproduces its key
+    frame packet, the slice decoder reads that packet and refuses the non-key frames after it."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ffv1_opencv.npz"))
+    frames, config = g["frames_bgr"], g["config"].tobytes()
+    bounds = np.concatenate([[0], np.cumsum(g["packet_sizes"])])
+    packets = [g["packets"][bounds[k]:bounds[k + 1]].tobytes() for k in range(len(bounds) - 1)]
+    h, w = frames.shape[1:3]
+    assert ffv1_gpu.stream_setup(w, h, 2, 2, True, 0)[0] == config
+    assert host_coder(frames[0], 2, 2, True, True) == packets[0]
+    assert host_coder(frames[0][..., ::-1], 2, 2, True, False) == packets[0]
+    rc, out = host_coder.decode(packets[0], w, h, 2, 2, True, True)
+    assert rc == 0 and np.array_equal(out, frames[0])
+    assert host_coder.decode(packets[1], w, h, 2, 2, True, True)[0] == -1
+    for k in range(1, len(frames)):     # every frame as a key frame of its own: what the device writer produces
+        rc, out = host_coder.decode(host_coder(frames[k], 2, 2, True, True), w, h, 2, 2, True, True)
+        assert rc == 0 and np.array_equal(out, frames[k])
 
 
 def test_packet_equals_libavcodec_key_frame(host_coder, tmp_path):
