@@ -31,7 +31,7 @@ def clip(w, h, n, distinct=4):
 
 
 which = sys.argv[1] if len(sys.argv) > 1 else "both"
-if which in ("stereo", "both"):
+if which in ("stereo", "both", "conv"):
     w, h, n = 1920, 1080, 32
     d, c = clip(w, h, n)
     rr = StereoRerenderer(StereoParams(w, h, xfov=60.0, convergence_depths=[5.0] * n, infill_mask=True), "cuda")

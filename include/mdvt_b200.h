@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MDVT_ABI_VERSION 9
+#define MDVT_ABI_VERSION 10
 
 #if defined(__GNUC__)
 #define MDVT_API __attribute__((visibility("default")))
@@ -272,6 +272,10 @@ MDVT_API int mdvt_depth_sum(const void *depth_src, int64_t n_pixels, int decoder
 MDVT_API int mdvt_edge_vertices(const void *depth_src, const mdvt_source *src_host, const double *K_host,
                        double angle_threshold_deg, uint8_t *cell_flags_scratch, uint8_t *out_flags, double *out_normals,
                        void *stream);
+/* E1 on explicit vertices: depth_map_tools.create_mesh_from_point_cloud(points, height, width, remove_edges=True, ...)
+ * (depth_map_tools.py:1186-1416) called directly with a grid-organised (H*W, 3) float64 point array. */
+MDVT_API int mdvt_edge_vertices_xyz(const double *xyz, int width, int height, double angle_threshold_deg,
+                           uint8_t *cell_flags_scratch, uint8_t *out_flags, double *out_normals, void *stream);
 /* E2.  Flagged vertices -> "edge points" (stereo_rerender.py:589-606) -> pose (12 doubles, frame -> eye camera,
  * :615-619,723-732) -> projection with the render camera (K_render_host: fx, fy, cx, cy as the float32-rounded values
  * the reference hands to cv2.projectPoints, :735) -> np.round -> z-buffered into zbuf (out_w*out_h u64, pre-cleared;
@@ -295,6 +299,18 @@ MDVT_API int mdvt_edge_resolve(uint64_t *zbuf, const void *depth_src, const mdvt
 MDVT_API int mdvt_normal_march_infill(uint8_t *image, int64_t image_pitch, const uint8_t *hole_mask, int64_t hole_pitch,
                              const uint8_t *mask_img, int64_t mask_pitch, int width, int height, int max_steps,
                              void *stream);
+
+/* The same march with the function's own signature (stereo_rerender.infill_using_normals(color_img, hole_mask, normal_map,
+ * max_steps), stereo_rerender.py:155-240, imported by basic_nomal_infill.py:10,101): normal_map is a dense (H, W, 3)
+ * float32 plane whose x, y components give the direction; a normal of exactly (0, 1, 0) marks "no normal" (:176). */
+MDVT_API int mdvt_normal_march_infill_f32(uint8_t *image, int64_t image_pitch, const uint8_t *hole_mask, int64_t hole_pitch,
+                                 const float *normal_map, int width, int height, int max_steps, void *stream);
+
+/* depth_map_tools.calculate_normals(depth, K) (depth_map_tools.py:20-60): per-pixel unit normals of a float32 depth plane
+ * from the forward differences of the unprojected points, y and z negated; float32 with NumPy's operation order.
+ * K_host: fx, fy, cx, cy doubles (rounded to float32 like NumPy rounds Python scalars).  out_normals: H*W*3 f32. */
+MDVT_API int mdvt_calculate_normals(const float *depth, int width, int height, const double *K_host, float *out_normals,
+                           void *stream);
 
 /* ---- row-local stereo fast path: ONE fused kernel, frames batched ---------------------------- */
 /* Whole stereo_rerender.py frame loop body (:512-541 decode+scale, :583 unproject, :723-738,:831-852 eye

@@ -18,7 +18,7 @@ DECODERS = {"D1": DECODE_D1, "D2": DECODE_D2, "D3": DECODE_D3, "F32": SOURCE_F32
 REDUCE_SCRATCH_DOUBLES = 4096
 FLAG_BG_COLLIDE, FLAG_RESET_ZBUF, FLAG_MASK_RGB, FLAG_ANYWIDTH = 0x1, 0x2, 0x4, 0x8
 ZBUF_EMPTY = 0xFFFFFFFFFFFFFFFF
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 
 class MdvtError(RuntimeError):
@@ -101,11 +101,14 @@ _PROTOTYPES = {
                                          C.POINTER(C.c_double), C.POINTER(LookAt), C.c_float, C.c_int, C.c_int, _u64p, _f64p, C.c_void_p, _u8p,
                                          C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PlaneLayout), C.POINTER(PlaneLayout), _stream]),
     "mdvt_edge_vertices": (C.c_int, [_u8p, C.POINTER(Source), C.POINTER(C.c_double), C.c_double, _u8p, _u8p, _f64p, _stream]),
+    "mdvt_edge_vertices_xyz": (C.c_int, [_f64p, C.c_int, C.c_int, C.c_double, _u8p, _u8p, _f64p, _stream]),
     "mdvt_edge_splat": (C.c_int, [_u8p, C.POINTER(Source), C.POINTER(C.c_double), _u8p, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                   C.c_int, C.c_int, _u64p, _stream]),
     "mdvt_edge_resolve": (C.c_int, [_u64p, _u8p, C.POINTER(Source), C.POINTER(C.c_double), _f64p, C.POINTER(C.c_double), _u8p, _u8p,
                                     C.c_int64, C.c_int, C.c_int, C.c_uint32, C.c_int, _u8p, C.c_int64, _u8p, C.c_int64, _stream]),
     "mdvt_normal_march_infill": (C.c_int, [_u8p, C.c_int64, _u8p, C.c_int64, _u8p, C.c_int64, C.c_int, C.c_int, C.c_int, _stream]),
+    "mdvt_normal_march_infill_f32": (C.c_int, [_u8p, C.c_int64, _u8p, C.c_int64, _f32p, C.c_int, C.c_int, C.c_int, _stream]),
+    "mdvt_calculate_normals": (C.c_int, [_f32p, C.c_int, C.c_int, C.POINTER(C.c_double), _f32p, _stream]),
     "mdvt_stereo_conv_rows": (C.c_int, [_u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _u8p, _u8p,
                                         _f32p, _stream]),
     "mdvt_stereo_rows": (C.c_int, [_u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32,

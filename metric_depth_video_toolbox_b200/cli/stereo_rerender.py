@@ -26,7 +26,8 @@ import torch
 
 from .. import depth_frames_helper, sharding, video_io
 from ..geometry import convergence_angle, curve_fit, fill_nan_with_closest, rebase_transformations  # noqa: F401
-from ..infill import masked_blur  # noqa: F401  (module-level helpers other reference scripts import from stereo_rerender)
+from ..depth_map_tools import timer  # noqa: F401  (stereo_rerender.py:15-20)
+from ..infill import infill_using_normals, make_infill_mask, masked_blur  # noqa: F401  (module-level helpers other reference scripts import from stereo_rerender: basic_nomal_infill.py:10)
 from ..stereo import StereoParams, StereoRerenderer
 from ..vr180 import convert_to_equirectangular  # noqa: F401
 

@@ -38,10 +38,16 @@ __device__ __forceinline__ V3 apply(const Pose12d &p, V3 v) {
             ((v.x * m[8] + v.y * m[9]) + v.z * m[10]) + m[11]};
 }
 
-// Mesh vertex (row, col): create_point_cloud_from_depth on the (optionally stretched) grid, float64.
+// Mesh vertex (row, col): create_point_cloud_from_depth on the (optionally stretched) grid, float64 -- or, DECODER ==
+// kSourceXYZ64, read from the (H*W, 3) float64 points the caller of create_mesh_from_point_cloud holds.
+constexpr int kSourceXYZ64 = 100;
 template <int DECODER, bool BIT16>
 __device__ __forceinline__ V3 vertex_at(const void *__restrict__ src, int width, int row, int col, float dec_const, float depth_scale,
                                         const Cam64 &c) {
+    if (DECODER == kSourceXYZ64) {
+        const double *p = reinterpret_cast<const double *>(src) + ((int64_t)row * width + col) * 3;
+        return {p[0], p[1], p[2]};
+    }
     const float zf = __fmul_rn(source_depth<DECODER, BIT16>(src, (int64_t)row * width + col, dec_const), depth_scale);
     const double xg = c.stretched ? (double)__fmul_rn(__int2float_rn(col), c.sx) : (double)col;
     const double yg = c.stretched ? (double)__fmul_rn(__int2float_rn(row), c.sy) : (double)row;
@@ -201,16 +207,26 @@ __global__ void __launch_bounds__(kThreads)
 // direction coded in the final mask image until it leaves the hole, then copies the colour found two / one / zero
 // steps further on (the first that is inside the frame and not a hole).  Float32, one rounding per operation, like
 // the NumPy code.  Only hole pixels are written and only non-hole pixels are read, so the image is updated in place.
+template <bool FLOAT_NORMALS>
 __global__ void __launch_bounds__(kThreads)
     normal_march_kernel(uint8_t *__restrict__ image, int64_t image_pitch, const uint8_t *__restrict__ hole, int64_t hole_pitch,
-                        const uint8_t *__restrict__ mask_img, int64_t mask_pitch, int width, int height, int max_steps) {
+                        const uint8_t *__restrict__ mask_img, int64_t mask_pitch, const float *__restrict__ normal_map, int width, int height,
+                        int max_steps) {
     const int64_t n = (int64_t)width * height;
     for (int64_t p = blockIdx.x * (int64_t)kThreads + threadIdx.x; p < n; p += (int64_t)gridDim.x * kThreads) {
         const int y = (int)(p / width), x = (int)(p - (int64_t)y * width);
         if (!hole[y * hole_pitch + x]) continue;
-        const uint8_t *m = mask_img + y * mask_pitch + (int64_t)x * 3;
-        float dx = __fsub_rn(__fmul_rn(__fdiv_rn((float)m[0], 255.0f), 2.0f), 1.0f);  // ((m / 255) * 2) - 1 (:808,811)
-        float dy = __fsub_rn(__fmul_rn(__fdiv_rn((float)m[1], 255.0f), 2.0f), 1.0f);
+        float dx, dy;
+        if (FLOAT_NORMALS) {  // the function's own signature: a float normal map; (0, 1, 0) means "no normal here" (:176)
+            const float *m = normal_map + p * 3;
+            dx = m[0];
+            dy = m[1];
+            if (dx == 0.0f && dy == 1.0f && m[2] == 0.0f) continue;
+        } else {
+            const uint8_t *m = mask_img + y * mask_pitch + (int64_t)x * 3;
+            dx = __fsub_rn(__fmul_rn(__fdiv_rn((float)m[0], 255.0f), 2.0f), 1.0f);  // ((m / 255) * 2) - 1 (:808,811)
+            dy = __fsub_rn(__fmul_rn(__fdiv_rn((float)m[1], 255.0f), 2.0f), 1.0f);
+        }
         const float norm = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
         if (!(norm > 1e-6f)) continue;
         dx = __fdiv_rn(dx, norm);
@@ -276,6 +292,21 @@ extern "C" int mdvt_edge_vertices(const void *depth_src, const mdvt_source *src,
     return MDVT_OK;
 }
 
+extern "C" int mdvt_edge_vertices_xyz(const double *xyz, int width, int height, double angle_threshold_deg, uint8_t *cell_flags_scratch,
+                                      uint8_t *out_flags, double *out_normals, void *stream) {
+    MDVT_REQUIRE(width >= 2 && height >= 2, "the edge test needs at least a 2x2 grid");
+    MDVT_REQUIRE(xyz && cell_flags_scratch && out_flags, "NULL buffer");
+    const Cam64 cam{1.0, 1.0, 0.0, 0.0, 1.0f, 1.0f, 0};
+    const double cos_limit = cos(angle_threshold_deg * (3.14159265358979323846 / 180.0));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t cells = (int64_t)(width - 1) * (height - 1), n = (int64_t)width * height;
+    edge_cells_kernel<kSourceXYZ64, true><<<grid_for(cells), kThreads, 0, st>>>(xyz, width, height, 0.0f, 1.0f, cam, cos_limit, cell_flags_scratch);
+    edge_vertices_kernel<kSourceXYZ64, true><<<grid_for(n), kThreads, 0, st>>>(xyz, width, height, 0.0f, 1.0f, cam, cell_flags_scratch, out_flags,
+                                                                              out_normals);
+    MDVT_CUDA_TRY(cudaGetLastError());
+    return MDVT_OK;
+}
+
 extern "C" int mdvt_edge_splat(const void *depth_src, const mdvt_source *src, const double *K_host, const uint8_t *flags,
                                const double *pose_host, const double *K_render_host, int out_w, int out_h, uint64_t *zbuf, void *stream) {
     if (int rc = check_source(src)) return rc;
@@ -330,8 +361,20 @@ extern "C" int mdvt_normal_march_infill(uint8_t *image, int64_t image_pitch, con
     MDVT_REQUIRE(image && hole_mask && mask_img, "NULL buffer");
     MDVT_REQUIRE(image_pitch >= (int64_t)width * 3 && mask_pitch >= (int64_t)width * 3 && hole_pitch >= width, "pitch too small");
     MDVT_REQUIRE(max_steps >= 0, "negative step count");
-    normal_march_kernel<<<grid_for((int64_t)width * height), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        image, image_pitch, hole_mask, hole_pitch, mask_img, mask_pitch, width, height, max_steps);
+    normal_march_kernel<false><<<grid_for((int64_t)width * height), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        image, image_pitch, hole_mask, hole_pitch, mask_img, mask_pitch, nullptr, width, height, max_steps);
+    MDVT_CUDA_TRY(cudaGetLastError());
+    return MDVT_OK;
+}
+
+extern "C" int mdvt_normal_march_infill_f32(uint8_t *image, int64_t image_pitch, const uint8_t *hole_mask, int64_t hole_pitch,
+                                            const float *normal_map, int width, int height, int max_steps, void *stream) {
+    MDVT_REQUIRE(width > 0 && height > 0, "bad frame size %dx%d", width, height);
+    MDVT_REQUIRE(image && hole_mask && normal_map, "NULL buffer");
+    MDVT_REQUIRE(image_pitch >= (int64_t)width * 3 && hole_pitch >= width, "pitch too small");
+    MDVT_REQUIRE(max_steps >= 0, "negative step count");
+    normal_march_kernel<true><<<grid_for((int64_t)width * height), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        image, image_pitch, hole_mask, hole_pitch, nullptr, 0, normal_map, width, height, max_steps);
     MDVT_CUDA_TRY(cudaGetLastError());
     return MDVT_OK;
 }

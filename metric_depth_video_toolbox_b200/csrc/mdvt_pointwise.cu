@@ -215,6 +215,39 @@ __global__ void __launch_bounds__(kThreads) codes_to_pixels_kernel(const uint32_
     }
 }
 
+// depth_map_tools.calculate_normals (depth_map_tools.py:20-60) for a float32 depth plane, float32 like NumPy computes it
+// there (float32 arrays against Python scalars stay float32): P = ((u - cx)/fx * z, (cy - v)/fy * z, z), forward
+// differences to the right / lower neighbour (the last column / row repeats itself: a zero difference), their cross
+// product (multiply, multiply, subtract per component), divided by sqrt((n0^2 + n1^2) + n2^2) + 1e-8, then y and z
+// negated ("DirectX conversion").
+__global__ void __launch_bounds__(kThreads)
+    calculate_normals_kernel(const float *__restrict__ depth, int width, int height, float fx, float fy, float cx, float cy,
+                             float *__restrict__ out) {
+    const int64_t n = (int64_t)width * height;
+    for (int64_t p = blockIdx.x * (int64_t)kThreads + threadIdx.x; p < n; p += (int64_t)gridDim.x * kThreads) {
+        const int row = (int)(p / width), col = (int)(p - (int64_t)row * width);
+        auto point = [&](int c, int r, float &X, float &Y, float &Z) {
+            Z = __ldg(depth + (int64_t)r * width + c);
+            X = __fmul_rn(__fdiv_rn(__fsub_rn((float)c, cx), fx), Z);
+            Y = __fmul_rn(__fdiv_rn(__fsub_rn(cy, (float)r), fy), Z);
+        };
+        float x0, y0, z0, xr, yr, zr, xd, yd, zd;
+        point(col, row, x0, y0, z0);
+        point(min(col + 1, width - 1), row, xr, yr, zr);
+        point(col, min(row + 1, height - 1), xd, yd, zd);
+        const float ax = __fsub_rn(xr, x0), ay = __fsub_rn(yr, y0), az = __fsub_rn(zr, z0);
+        const float bx = __fsub_rn(xd, x0), by = __fsub_rn(yd, y0), bz = __fsub_rn(zd, z0);
+        const float n0 = __fsub_rn(__fmul_rn(ay, bz), __fmul_rn(az, by));
+        const float n1 = __fsub_rn(__fmul_rn(az, bx), __fmul_rn(ax, bz));
+        const float n2 = __fsub_rn(__fmul_rn(ax, by), __fmul_rn(ay, bx));
+        const float len = __fadd_rn(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(n0, n0), __fmul_rn(n1, n1)), __fmul_rn(n2, n2))), 1e-8f);
+        float *o = out + p * 3;
+        o[0] = __fdiv_rn(n0, len);
+        o[1] = -__fdiv_rn(n1, len);
+        o[2] = -__fdiv_rn(n2, len);
+    }
+}
+
 }  // namespace mdvt
 
 using namespace mdvt;
@@ -333,6 +366,17 @@ extern "C" int mdvt_project_points_f64(const double *xyz, int64_t n_points, cons
     MDVT_REQUIRE(xyz && out_uv, "NULL buffer");
     project_points_f64_kernel<<<grid_for(n_points), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(xyz, n_points, K_host[0], K_host[1],
                                                                                                       K_host[2], K_host[3], out_uv);
+    MDVT_CUDA_TRY(cudaGetLastError());
+    return MDVT_OK;
+}
+
+extern "C" int mdvt_calculate_normals(const float *depth, int width, int height, const double *K_host, float *out_normals, void *stream) {
+    MDVT_REQUIRE(width > 0 && height > 0, "bad frame size %dx%d", width, height);
+    MDVT_REQUIRE(depth && K_host && out_normals, "NULL buffer");
+    // the reference reads K through float(): Python doubles against float32 arrays -> NumPy computes in float32 with the
+    // scalar rounded to float32
+    calculate_normals_kernel<<<grid_for((int64_t)width * height), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        depth, width, height, (float)K_host[0], (float)K_host[1], (float)K_host[2], (float)K_host[3], out_normals);
     MDVT_CUDA_TRY(cudaGetLastError());
     return MDVT_OK;
 }

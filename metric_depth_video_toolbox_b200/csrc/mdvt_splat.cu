@@ -26,35 +26,37 @@ struct ViewPack {
     mdvt_view v[kMaxViews];
     int n;
 };
+struct RayPack {  // the views of one frame in ray form (mdvt_common.cuh)
+    RayView v[kMaxViews];
+    int n;
+};
 
-// One source pixel through every view.  Divisions are correctly rounded (== the float32 model's `/`): the
-// reciprocals of fx, fy are refined once per thread, the one of Zv once per view and shared by u and v.
-// All index arithmetic is 32-bit (the entry point checks that source and target planes have < 2^31 pixels).
+// One source pixel through every view in ray form.  cj[k][c] = fma(A_c, col, C_c) is hoisted per column by the caller,
+// fi = float(row).  Divisions are correctly rounded (== the float32 model's `/`): the reciprocal of Zv is refined once
+// per view and shared by u and v.  All index arithmetic is 32-bit (the entry point checks that source and target
+// planes have < 2^31 pixels).
 template <bool UVZ, bool TOUCHED>
-__device__ __forceinline__ void splat_pixel(uint32_t p, float xc, int row, float z, const SourceCam &cam, float rfx, float rfy,
-                                            const ViewPack &views, float near_plane, int out_w, uint32_t out_n, uint32_t out_h,
-                                            uint32_t id_offset, uint32_t n, unsigned long long *__restrict__ zbuf, float *__restrict__ out_uvz,
-                                            uint64_t keep, uint8_t *__restrict__ touched) {
-    const float yg = __fmul_rn(__int2float_rn(row), cam.sy);
-    const float X = div_rn_by(__fmul_rn(xc, z), cam.fx, rfx);  // xc = fl(fl(col * sx) - cx), hoisted by the caller
-    const float Y = div_rn_by(__fmul_rn(__fsub_rn(yg, cam.cy), z), cam.fy, rfy);
+__device__ __forceinline__ void splat_pixel(uint32_t p, const float (&cj)[kMaxViews][3], float fi, float z, const RayPack &rays,
+                                            float near_plane, int out_w, uint32_t out_n, uint32_t out_h, uint32_t id_offset, uint32_t n,
+                                            unsigned long long *__restrict__ zbuf, float *__restrict__ out_uvz, uint64_t keep,
+                                            uint8_t *__restrict__ touched) {
 #pragma unroll
     for (int k = 0; k < kMaxViews; ++k) {
-        if (k < views.n) {
-            const mdvt_view &vw = views.v[k];
-            const float Xv = affine_row(vw.M, X, Y, z);
-            const float Yv = affine_row(vw.M + 4, X, Y, z);
-            const float Zv = affine_row(vw.M + 8, X, Y, z);
+        if (k < rays.n) {
+            const RayView &rv = rays.v[k];
+            const float nu = __fmaf_rn(z, __fmaf_rn(rv.B[0], fi, cj[k][0]), rv.T[0]);
+            const float nv = __fmaf_rn(z, __fmaf_rn(rv.B[1], fi, cj[k][1]), rv.T[1]);
+            const float Zv = __fmaf_rn(z, __fmaf_rn(rv.B[2], fi, cj[k][2]), rv.T[2]);
             float u, v;
             if (UVZ) {  // parity output: IEEE division also where Zv is zero / negative / tiny
-                u = __fadd_rn(__fdiv_rn(__fmul_rn(vw.fx, Xv), Zv), vw.cx);
-                v = __fadd_rn(__fdiv_rn(__fmul_rn(vw.fy, Yv), Zv), vw.cy);
+                u = __fdiv_rn(nu, Zv);
+                v = __fdiv_rn(nv, Zv);
                 float *o = out_uvz + ((int64_t)k * n + p) * 3;
                 o[0] = u; o[1] = v; o[2] = Zv;
             } else {
                 const float rz = rcp_refined(Zv);
-                u = __fadd_rn(div_rn_by(__fmul_rn(vw.fx, Xv), Zv, rz), vw.cx);
-                v = __fadd_rn(div_rn_by(__fmul_rn(vw.fy, Yv), Zv, rz), vw.cy);
+                u = div_rn_by(nu, Zv, rz);
+                v = div_rn_by(nv, Zv, rz);
             }
             // Round half to even, like np.round, and test the bounds without FRND / F2I and with two compares: adding
             // 1.5 * 2^23 rounds to an integer (the sum's ulp is 1) for |u| < 2^22 and leaves rint(u) in the mantissa, so
@@ -81,29 +83,35 @@ __device__ __forceinline__ void splat_pixel(uint32_t p, float xc, int row, float
 // cameras (ncu v1: the kernel sat on the scoreboard of its own byte loads at 53 % issue-active), and the grid is sized
 // from the occupancy API so that every CTA is resident (v1 launched 2370 CTAs onto 1924 slots: a second, mostly
 // empty wave).  DEVVIEW: the single camera is read from device memory (written by the look-at kernel of the same
-// stream, mdvt_novel_view_frames) instead of the kernel parameters.
+// stream, mdvt_novel_view_frames) instead of the kernel parameters, and brought into ray form by every thread.
 constexpr int kSplatRows = 4;
 
 template <int DECODER, bool BIT16, bool DEVVIEW>
 __global__ void __launch_bounds__(kSplatThreads)
     project_splat_kernel(const void *__restrict__ rgb, int width, int height, float dec_const, float depth_scale, SourceCam cam,
-                         ViewPack views_param, const mdvt_view *__restrict__ view_dev, float near_plane, int out_w, int out_h,
+                         RayPack rays_param, const mdvt_view *__restrict__ view_dev, float near_plane, int out_w, int out_h,
                          uint32_t id_offset, unsigned long long *__restrict__ zbuf, float *__restrict__ out_uvz,
                          uint8_t *__restrict__ touched) {
     const uint32_t out_n = (uint32_t)out_w * (uint32_t)out_h, n = (uint32_t)width * (uint32_t)height;
-    const float rfx = rcp_refined(cam.fx), rfy = rcp_refined(cam.fy);
     const int col = blockIdx.x * kSplatThreads + threadIdx.x;
     if (col >= width) return;
-    ViewPack local;
+    RayPack local;
     if (DEVVIEW) {
         local.n = 1;
+        mdvt_view vw;
         const float4 *v4 = reinterpret_cast<const float4 *>(view_dev);
-        float4 *l4 = reinterpret_cast<float4 *>(&local.v[0]);
+        float4 *l4 = reinterpret_cast<float4 *>(&vw);
 #pragma unroll
         for (int k = 0; k < 4; ++k) l4[k] = __ldg(v4 + k);
+        local.v[0] = make_ray_view(cam.fx, cam.fy, cam.cx, cam.cy, cam.sx, cam.sy, vw.M, vw.fx, vw.fy, vw.cx, vw.cy);
     }
-    const ViewPack &views = DEVVIEW ? local : views_param;
-    const float xc = __fsub_rn(__fmul_rn(__int2float_rn(col), cam.sx), cam.cx);
+    const RayPack &rays = DEVVIEW ? local : rays_param;
+    float cj[kMaxViews][3];
+    const float fj = __int2float_rn(col);
+#pragma unroll
+    for (int k = 0; k < kMaxViews; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) cj[k][c] = k < rays.n ? __fmaf_rn(rays.v[k].A[c], fj, rays.v[k].C[c]) : 0.0f;
     const uint64_t keep = l2_keep_policy();
     const int stride = gridDim.y;
     for (int row0 = blockIdx.y; row0 < height; row0 += stride * kSplatRows) {
@@ -119,17 +127,17 @@ __global__ void __launch_bounds__(kSplatThreads)
             const int row = row0 + k * stride;
             if (row < height) {
                 const uint32_t p = (uint32_t)row * (uint32_t)width + (uint32_t)col;
-                const float zs = __fmul_rn(z[k], depth_scale);
+                const float zs = __fmul_rn(z[k], depth_scale), fi = __int2float_rn(row);
                 // DEVVIEW: the novel-view frame loop -- touched flags always on, never a (u, v, z) dump
                 if (DEVVIEW)
-                    splat_pixel<false, true>(p, xc, row, zs, cam, rfx, rfy, views, near_plane, out_w, out_n, (uint32_t)out_h, id_offset, n, zbuf,
-                                             nullptr, keep, touched);
+                    splat_pixel<false, true>(p, cj, fi, zs, rays, near_plane, out_w, out_n, (uint32_t)out_h, id_offset, n, zbuf, nullptr, keep,
+                                             touched);
                 else if (out_uvz)
-                    splat_pixel<true, false>(p, xc, row, zs, cam, rfx, rfy, views, near_plane, out_w, out_n, (uint32_t)out_h, id_offset, n, zbuf,
-                                             out_uvz, keep, nullptr);
+                    splat_pixel<true, false>(p, cj, fi, zs, rays, near_plane, out_w, out_n, (uint32_t)out_h, id_offset, n, zbuf, out_uvz, keep,
+                                             nullptr);
                 else
-                    splat_pixel<false, false>(p, xc, row, zs, cam, rfx, rfy, views, near_plane, out_w, out_n, (uint32_t)out_h, id_offset, n, zbuf,
-                                              nullptr, keep, nullptr);
+                    splat_pixel<false, false>(p, cj, fi, zs, rays, near_plane, out_w, out_n, (uint32_t)out_h, id_offset, n, zbuf, nullptr, keep,
+                                              nullptr);
             }
         }
     }
@@ -544,6 +552,12 @@ static int launch_project_splat(const void *depth_src, const mdvt_source *src, c
     MDVT_REQUIRE((int64_t)src->width * src->height < 0x7FFFFFFFll && (int64_t)out_w * out_h * pack.n < 0x7FFFFFFFll,
                  "source / target planes must hold fewer than 2^31 pixels");
     SourceCam cam{src->fx, src->fy, src->cx, src->cy, src->grid_sx, src->grid_sy};
+    RayPack rays{};
+    rays.n = pack.n;
+    if (!view_dev)
+        for (int k = 0; k < pack.n; ++k)
+            rays.v[k] = make_ray_view(cam.fx, cam.fy, cam.cx, cam.cy, cam.sx, cam.sy, pack.v[k].M, pack.v[k].fx, pack.v[k].fy, pack.v[k].cx,
+                                      pack.v[k].cy);
     const int col_blocks = (src->width + kSplatThreads - 1) / kSplatThreads;
 #define CALL(D, B)                                                                                                                   \
     do {                                                                                                                             \
@@ -555,7 +569,7 @@ static int launch_project_splat(const void *depth_src, const mdvt_source *src, c
         if (row_blocks < 1) row_blocks = 1;                                                                                          \
         if (row_blocks > src->height) row_blocks = src->height;                                                                      \
         kernel<<<dim3(col_blocks, row_blocks), kSplatThreads, 0, st>>>(depth_src, src->width, src->height, src->dec_const, src->depth_scale, cam, \
-                                                                     pack, view_dev, near_plane, out_w, out_h, id_offset, zb, out_uvz, touched); \
+                                                                     rays, view_dev, near_plane, out_w, out_h, id_offset, zb, out_uvz, touched); \
     } while (0)
     MDVT_DISPATCH_SOURCE(src->decoder, src->bit16, CALL);
 #undef CALL

@@ -1,14 +1,14 @@
 // Stereo with a convergence rotation (stereo_rerender.py:704-725,831-836 with --convergence_file, the way movie_2_3D
 // drives it): ONE fused kernel per batch of frames, no global z-buffer.
 //
-// Each eye pose is a rotation about the camera's y axis followed by a shift along x.  A rotation about the optical
-// centre moves a pixel's ROW by an amount that does not depend on its depth:
-//     v' - cy' = (fy'/fy) * (i - cy) / g(j),     g(j) = M[8] * (j - cx)/fx + M[10]     (= Zv / z)
-// so the source pixels that land in target row r are, per source column j, the one or two rows next to
-//     i* = cy + (r - cy') * g(j) * fy/fy'.
-// A CTA therefore owns one TARGET row (of both eyes) at a time: for every source column it takes the three candidate
-// rows around i*, rejects those whose predicted v' is not within 0.505 of r, and runs the exact float32 arithmetic of
-// the generic path (mdvt_splat.cu: unproject, 3x4 affine, refined-reciprocal divisions, rintf) on the rest.  A
+// Each eye pose is a rotation about the camera's y axis followed by a shift along x.  In ray form (mdvt_common.cuh)
+// that leaves B_u = B_z = T_v = T_z = 0: Zv = z * r_z(j) and v' = r_v(i, j) / r_z(j) -- a pixel's target ROW does not
+// depend on its depth.  The source pixels that land in target row r are therefore, per source column j, the one or
+// two rows next to
+//     i* = (r * r_z(j) - C_v(j)) / B_v.
+// A CTA owns one TARGET row (of both eyes) at a time: for every source column and eye it takes the row nearest to i*,
+// queues the neighbour when the prediction says it can also round into r, and runs the exact float32 arithmetic of
+// the generic path (mdvt_splat.cu: 6 FFMA, refined-reciprocal divisions, magic-number rounding) on the candidates.  A
 // candidate whose exact rint(v') equals r goes into a shared-memory z-buffer with a 64-bit atomicMin on
 // (float_bits(Zv) << 32 | source row offset << 12 | column) -- the same order as the generic path's
 // (Zv, source index), so the result is bit-identical to mdvt_project_splat + mdvt_resolve, which the tests assert.
@@ -24,34 +24,36 @@ namespace mdvt {
 constexpr unsigned long long kEmpty64 = MDVT_ZBUF_EMPTY;
 
 struct ConvSmemLayout {
-    int zbuf_off, out_off, mask_off, queue_off, queue_cap, total;
+    int ray_off, zbuf_off, out_off, mask_off, queue_off, queue_cap, total;
 };
 
 __host__ __device__ inline ConvSmemLayout conv_smem_layout(int width, int mask_bpp) {
     ConvSmemLayout L;
     int off = 16;
+    L.ray_off = off;  off += 2 * (int)sizeof(RayView);   // both eyes' coefficients of the current frame
     L.zbuf_off = off; off += 2 * width * 8;          // per eye: W 64-bit slots
     L.out_off = off;  off += 2 * width * 3;          // left | right RGB row
     off = (off + 15) & ~15;
     L.mask_off = off; off += 2 * width * mask_bpp;
     off = (off + 15) & ~15;
-    L.queue_cap = width;                             // second candidates: at most one per column (typically a few per cent)
+    L.queue_cap = (width + 1) / 2;                   // second candidates (typically a few per cent of 2W); overflow is evaluated in place
     L.queue_off = off; off += 4 * L.queue_cap;
     L.total = (off + 15) & ~15;
     return L;
 }
 
-// a / b for the PREDICTION side only (which candidate rows to look at): a couple of ulp off is absorbed by the window.
-__device__ __forceinline__ float approx_div(float a, float b) {
+__device__ __forceinline__ float rcp_approx(float b) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
-    return __fmul_rn(a, r);
+    return r;
 }
 
 // Half-width of the |predicted v' - r| window inside which a candidate row goes through the exact arithmetic.  The
-// prediction and the exact float32 path differ by < 1e-3 pixel (a few ulp of a coordinate below 4096), so 0.5 + 0.005
+// prediction and the exact float32 path differ by < 2e-3 pixel (a few ulp of a coordinate below 4096), so 0.5 + 0.005
 // cannot lose a pixel whose exact rint(v') is r; the narrower the window, the fewer second candidates.
 constexpr float kRowWindow = 0.505f;
+constexpr float kConvMagic = 12582912.0f;  // 1.5 * 2^23
+constexpr int kConvMagicBits = 0x4B400000;
 
 // MASK_MODE: 0 none, 1 u8 {0,255}, 2 u8x3 (bg colour / black)
 template <int MASK_MODE, int kConvThreads, int U>
@@ -63,6 +65,7 @@ __global__ void __launch_bounds__(kConvThreads)
     constexpr int mask_bpp = MASK_MODE == 2 ? 3 : 1;
     const ConvSmemLayout L = conv_smem_layout(width, mask_bpp);
     unsigned long long *s_z = reinterpret_cast<unsigned long long *>(smem + L.zbuf_off);  // [2][width]
+    RayView *s_ray = reinterpret_cast<RayView *>(smem + L.ray_off);
     uint8_t *s_out = smem + L.out_off;
     uint8_t *s_mask = smem + L.mask_off;
     uint32_t *s_queue = reinterpret_cast<uint32_t *>(smem + L.queue_off);
@@ -78,118 +81,153 @@ __global__ void __launch_bounds__(kConvThreads)
     // come out of L1 instead of L2.
     const int per_cta = (n_units + gridDim.x - 1) / gridDim.x;
     const int unit_end = min(n_units, (int)(blockIdx.x + 1) * per_cta);
+    int ray_frame = -1;
     for (int unit = blockIdx.x * per_cta; unit < unit_end; ++unit) {
         const int frame = unit / height, r = unit - frame * height;
         const mdvt_conv_frame *fc = frames + frame;
+        if (frame != ray_frame) {  // a few times per CTA: both eyes' ray coefficients, float64 -> float32 (make_ray_view)
+            __syncthreads();       // nobody still reads the previous frame's coefficients
+            if (tid < 2) {
+                const mdvt_view *vw = &fc->view[tid];
+                float M[12];
+#pragma unroll
+                for (int k = 0; k < 12; ++k) M[k] = __ldg(&vw->M[k]);
+                s_ray[tid] = make_ray_view(__ldg(&fc->fx), __ldg(&fc->fy), __ldg(&fc->cx), __ldg(&fc->cy), 1.0f, 1.0f, M, __ldg(&vw->fx),
+                                           __ldg(&vw->fy), __ldg(&vw->cx), __ldg(&vw->cy));
+            }
+            ray_frame = frame;
+            __syncthreads();
+        }
         const float dec_const = __ldg(&fc->dec_const), depth_scale = __ldg(&fc->depth_scale), near_plane = __ldg(&fc->near_plane);
-        const float sfx = __ldg(&fc->fx), sfy = __ldg(&fc->fy), scx = __ldg(&fc->cx), scy = __ldg(&fc->cy);
-        const float rfx = rcp_refined(sfx), rfy = rcp_refined(sfy);
         const uint8_t *dframe = depth_rgb + (int64_t)frame * height * row_bytes;
         const float fr = (float)r;
+        // the pose is Ry + x-shift: B_u = B_z = T_v = T_z = 0 exactly (P's second column is (0, fy', 0), its last (fx' m3, 0, 0)),
+        // so r_u = C_u(j), r_z = C_z(j) and the FFMAs that would add an exact 0 are left out: same float32 results
+        float Au[2], Av[2], Az[2], Cu[2], Cv[2], Cz[2], Bv[2], Tu[2], inv_Bv[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            Au[e] = s_ray[e].A[0]; Av[e] = s_ray[e].A[1]; Az[e] = s_ray[e].A[2];
+            Cu[e] = s_ray[e].C[0]; Cv[e] = s_ray[e].C[1]; Cz[e] = s_ray[e].C[2];
+            Bv[e] = s_ray[e].B[1]; Tu[e] = s_ray[e].T[0];
+            inv_Bv[e] = rcp_approx(Bv[e]);
+        }
 
-        // lowest source row any column of either eye can ask for (g is linear in j: its extremes sit at the borders)
+        // lowest source row any column of either eye can ask for (i* is monotone in j: its extremes sit at the borders)
         int i_base = height;
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            const float m8 = __ldg(&fc->view[e].M[8]), m10 = __ldg(&fc->view[e].M[10]);
-            const float inv_ratio = approx_div(sfy, __ldg(&fc->view[e].fy)), vcy = __ldg(&fc->view[e].cy);
 #pragma unroll
             for (int side = 0; side < 2; ++side) {
-                const float g = m8 * approx_div((side ? (float)(width - 1) : 0.0f) - scx, sfx) + m10;
-                i_base = min(i_base, (int)floorf(scy + (fr - vcy) * g * inv_ratio) - 3);
+                const float fj = side ? (float)(width - 1) : 0.0f;
+                const float istar = (fr * (Az[e] * fj + Cz[e]) - (Av[e] * fj + Cv[e])) * inv_Bv[e];
+                i_base = min(i_base, (int)floorf(istar) - 3);
             }
         }
         i_base = max(i_base, 0);
 
+        // exact path: the float32 arithmetic of splat_pixel() in mdvt_splat.cu for source pixel (i, j) and eye e
+        auto evaluate = [&](int e, int i, int j, float cju, float cjv, float cjz, uint32_t red, uint32_t blue) {
+            const float z = __fmul_rn(depth_of<MDVT_DECODE_D1>(code_of<MDVT_DECODE_D1, true>(red, 0u, blue), dec_const), depth_scale);
+            const float nu = __fmaf_rn(z, cju, Tu[e]);
+            const float nv = __fmaf_rn(z, __fmaf_rn(Bv[e], (float)i, cjv), 0.0f);
+            const float Zv = __fmaf_rn(z, cjz, 0.0f);
+            const float rz = rcp_refined(Zv);
+            const float u = div_rn_by(nu, Zv, rz);
+            const float v = div_rn_by(nv, Zv, rz);
+            // rint + bounds as in splat_pixel(): the integer sits in the mantissa of u + 1.5 * 2^23; anything out of
+            // range, infinite or NaN becomes a huge unsigned value
+            const uint32_t ui = (uint32_t)(__float_as_int(__fadd_rn(u, kConvMagic)) - kConvMagicBits);
+            const int vi = __float_as_int(__fadd_rn(v, kConvMagic)) - kConvMagicBits;
+            if (Zv > near_plane && vi == r && ui < (uint32_t)width) {
+                const unsigned long long key =
+                    ((unsigned long long)__float_as_uint(Zv) << 32) | ((uint32_t)(i - i_base) << 12) | (uint32_t)j;
+                atomicMin(&s_z[e * width + ui], key);
+            }
+        };
+
         // ---- phase A: candidate source pixels of this target row -> shared-memory z-buffers --------
-        // Per source column the row nearest to i* always goes through the exact arithmetic; its neighbour on the other
-        // side of i* can also round into row r when i* sits close to a half (a few per cent of the columns).  Those
+        // Per source column and eye the row nearest to i* always goes through the exact arithmetic; its neighbour on the
+        // other side of i* can also round into row r when i* sits close to a half (a few per cent of the columns).  Those
         // second candidates are queued in shared memory and evaluated densely afterwards instead of diverging here.
-#pragma unroll 1
-        for (int e = 0; e < 2; ++e) {
-            const mdvt_view *vw = &fc->view[e];
-            // the pose is Ry + x-shift: M = [m0 0 m2 m3; 0 1 0 0; m8 0 m10 0].  Dropping the terms that multiply an exact 0
-            // or add an exact 0 leaves every finite result as the full 3x4 affine of the generic path computes it.
-            const float m0 = __ldg(&vw->M[0]), m2 = __ldg(&vw->M[2]), m3 = __ldg(&vw->M[3]), m8 = __ldg(&vw->M[8]), m10 = __ldg(&vw->M[10]);
-            const float vfx = __ldg(&vw->fx), vfy = __ldg(&vw->fy), vcx = __ldg(&vw->cx), vcy = __ldg(&vw->cy);
-            const float ratio = approx_div(vfy, sfy), inv_ratio = approx_div(sfy, vfy), inv_sfx = approx_div(1.0f, sfx);
-            const float dr = (fr - vcy) * inv_ratio;
-            unsigned long long *zb = s_z + e * width;
-            // exact path: the float32 arithmetic of splat_pixel() in mdvt_splat.cu for source pixel (i, j)
-            auto evaluate = [&](int i, int j, uint32_t red, uint32_t blue) {
-                const float z = __fmul_rn(depth_of<MDVT_DECODE_D1>(code_of<MDVT_DECODE_D1, true>(red, 0u, blue), dec_const), depth_scale);
-                const float X = div_rn_by(__fmul_rn(__fsub_rn((float)j, scx), z), sfx, rfx);
-                const float Y = div_rn_by(__fmul_rn(__fsub_rn((float)i, scy), z), sfy, rfy);
-                const float Xv = __fadd_rn(__fadd_rn(__fmul_rn(m0, X), __fmul_rn(m2, z)), m3);
-                const float Zv = __fadd_rn(__fmul_rn(m8, X), __fmul_rn(m10, z));
-                const float rz = rcp_refined(Zv);
-                const float u = __fadd_rn(div_rn_by(__fmul_rn(vfx, Xv), Zv, rz), vcx);
-                const float v = __fadd_rn(div_rn_by(__fmul_rn(vfy, Y), Zv, rz), vcy);
-                // rint + bounds as in splat_pixel(): the integer sits in the mantissa of u + 1.5 * 2^23; anything out of
-                // range, infinite or NaN becomes a huge unsigned value
-                const uint32_t ui = (uint32_t)(__float_as_int(__fadd_rn(u, 12582912.0f)) - 0x4B400000);
-                const int vi = __float_as_int(__fadd_rn(v, 12582912.0f)) - 0x4B400000;
-                if (Zv > near_plane && vi == r && ui < (uint32_t)width) {
-                    const unsigned long long key =
-                        ((unsigned long long)__float_as_uint(Zv) << 32) | ((uint32_t)(i - i_base) << 12) | (uint32_t)j;
-                    atomicMin(&zb[ui], key);
-                }
-            };
-            if (tid == 0) *s_qcount = 0;
-            __syncthreads();
-            // U columns per thread and pass: all 2U byte loads are issued before the first is used
-            for (int jb = tid; jb < width; jb += U * kConvThreads) {
-                int i0[U], i1[U];   // nearest source row; neighbour row that may also round into r (-1: none)
-                uint32_t red[U], blue[U];
-                bool in0[U];
-                // (1) predictions of all U columns: pure arithmetic, nothing long-latency in between
+        if (tid == 0) *s_qcount = 0;
+        __syncthreads();
+        // U columns per thread and pass, both eyes: all 4U byte loads are issued before the first is used
+        for (int jb = tid; jb < width; jb += U * kConvThreads) {
+            int i0[U][2];
+            uint32_t red[U][2], blue[U][2], second[U][2];  // second: queue entry of the neighbour row, 0xFFFFFFFF = none
+            float cju[U][2], cjv[U][2], cjz[U][2];
+            bool in0[U][2];
+            // (1) predictions of all columns and eyes: pure arithmetic, nothing long-latency in between
 #pragma unroll
-                for (int k = 0; k < U; ++k) {
-                    const int j = jb + k * kConvThreads;
-                    in0[k] = false;
-                    i1[k] = -1;
+            for (int k = 0; k < U; ++k) {
+                const int j = jb + k * kConvThreads;
+                const float fj = (float)j;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    in0[k][e] = false;
+                    second[k][e] = 0xFFFFFFFFu;
                     if (j >= width) continue;
-                    // prediction (approximate on purpose; the window below absorbs its error): g = Zv / z of this column
-                    const float g = __fmaf_rn(m8, __fmul_rn(__fsub_rn((float)j, scx), inv_sfx), m10);
-                    i0[k] = __float2int_rn(__fmaf_rn(dr, g, scy));
-                    float inv_g;
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_g) : "f"(g));
-                    const float step = __fmul_rn(ratio, inv_g);                                            // d v' / d i
-                    const float v0 = __fsub_rn(__fmaf_rn(__fsub_rn((float)i0[k], scy), step, vcy), fr);    // predicted v' - r of row i0
-                    in0[k] = (uint32_t)i0[k] < (uint32_t)height;
+                    cju[k][e] = __fmaf_rn(Au[e], fj, Cu[e]);
+                    cjv[k][e] = __fmaf_rn(Av[e], fj, Cv[e]);
+                    cjz[k][e] = __fmaf_rn(Az[e], fj, Cz[e]);
+                    // prediction (approximate on purpose; the window below absorbs its error)
+                    const float g1 = __fmul_rn(cjz[k][e], inv_Bv[e]);                           // d i* / d r  (= 1 / step)
+                    const float t = __fmaf_rn(fr, g1, -__fmul_rn(cjv[k][e], inv_Bv[e]));        // i*
+                    const float tm = __fadd_rn(t, kConvMagic);
+                    i0[k][e] = __float_as_int(tm) - kConvMagicBits;                             // rint(i*)
+                    const float step = rcp_approx(g1);                                          // d v' / d i
+                    const float v0 = __fmul_rn(__fsub_rn(__fsub_rn(tm, kConvMagic), t), step);  // predicted v' - r of row i0
+                    in0[k][e] = (uint32_t)i0[k][e] < (uint32_t)height;
                     if (fabsf(v0) >= __fsub_rn(step, kRowWindow)) {  // the neighbour's predicted v' is within the window of r too
-                        const int cand = v0 < 0.0f ? i0[k] + 1 : i0[k] - 1;
-                        if ((uint32_t)cand < (uint32_t)height) i1[k] = cand;
+                        const int cand = v0 < 0.0f ? i0[k][e] + 1 : i0[k][e] - 1;
+                        if ((uint32_t)cand < (uint32_t)height) second[k][e] = ((uint32_t)e << 31) | ((uint32_t)(cand - i_base) << 12) | (uint32_t)j;
                     }
                 }
-                // (2) all 2U byte loads back to back (v3 interleaved them with the queue's warp-aggregated atomics and ncu
-                //     showed every column's prediction waiting on the previous column's loads: 27 % of the stall samples)
+            }
+            // (2) all byte loads back to back
 #pragma unroll
-                for (int k = 0; k < U; ++k) {
-                    if (in0[k]) {
-                        const uint8_t *px = dframe + ((uint32_t)i0[k] * (uint32_t)width + (uint32_t)(jb + k * kConvThreads)) * 3u;
-                        red[k] = __ldg(px);
-                        blue[k] = __ldg(px + 2);
+            for (int k = 0; k < U; ++k)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    if (in0[k][e]) {
+                        const uint8_t *px = dframe + ((uint32_t)i0[k][e] * (uint32_t)width + (uint32_t)(jb + k * kConvThreads)) * 3u;
+                        red[k][e] = __ldg(px);
+                        blue[k][e] = __ldg(px + 2);
                     }
-                }
-                // (3) second candidates -> queue (<= one per column)
+            // (3) second candidates -> queue (<= one per column and eye)
 #pragma unroll
-                for (int k = 0; k < U; ++k)
-                    if (i1[k] >= 0) s_queue[atomicAdd(s_qcount, 1u)] = ((uint32_t)(i1[k] - i_base) << 12) | (uint32_t)(jb + k * kConvThreads);
-                // (4) exact arithmetic
+            for (int k = 0; k < U; ++k)
 #pragma unroll
-                for (int k = 0; k < U; ++k)
-                    if (in0[k]) evaluate(i0[k], jb + k * kConvThreads, red[k], blue[k]);
-            }
-            __syncthreads();
-            const int queued = min((int)*s_qcount, L.queue_cap);
-            for (int q = tid; q < queued; q += kConvThreads) {
-                const uint32_t ent = s_queue[q];
-                const int i = i_base + (int)(ent >> 12), j = (int)(ent & 0xFFFu);
-                const uint32_t off = ((uint32_t)i * (uint32_t)width + (uint32_t)j) * 3u;
-                evaluate(i, j, __ldg(dframe + off), __ldg(dframe + off + 2));
-            }
-            __syncthreads();  // the queue is reused by the other eye
+                for (int e = 0; e < 2; ++e)
+                    if (second[k][e] != 0xFFFFFFFFu) {
+                        const uint32_t slot = atomicAdd(s_qcount, 1u);
+                        if (slot < (uint32_t)L.queue_cap) {
+                            s_queue[slot] = second[k][e];
+                        } else {  // queue full (extreme convergence angles only): the candidate is evaluated here, divergently
+                            const int i = i_base + (int)((second[k][e] >> 12) & 0x7FFFFu), j = jb + k * kConvThreads;
+                            const uint8_t *px = dframe + ((uint32_t)i * (uint32_t)width + (uint32_t)j) * 3u;
+                            evaluate(e, i, j, cju[k][e], cjv[k][e], cjz[k][e], __ldg(px), __ldg(px + 2));
+                        }
+                    }
+            // (4) exact arithmetic
+#pragma unroll
+            for (int k = 0; k < U; ++k)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    if (in0[k][e]) evaluate(e, i0[k][e], jb + k * kConvThreads, cju[k][e], cjv[k][e], cjz[k][e], red[k][e], blue[k][e]);
+        }
+        __syncthreads();
+        const int queued = min((int)*s_qcount, L.queue_cap);
+        for (int q = tid; q < queued; q += kConvThreads) {
+            const uint32_t ent = s_queue[q];
+            const int e = (int)(ent >> 31), i = i_base + (int)((ent >> 12) & 0x7FFFFu), j = (int)(ent & 0xFFFu);
+            const uint32_t off = ((uint32_t)i * (uint32_t)width + (uint32_t)j) * 3u;
+            const float fj = (float)j;
+            const float a_u = e ? Au[1] : Au[0], a_v = e ? Av[1] : Av[0], a_z = e ? Az[1] : Az[0];
+            const float c_u = e ? Cu[1] : Cu[0], c_v = e ? Cv[1] : Cv[0], c_z = e ? Cz[1] : Cz[0];
+            const uint32_t red = __ldg(dframe + off), blue = __ldg(dframe + off + 2);
+            if (e) evaluate(1, i, j, __fmaf_rn(a_u, fj, c_u), __fmaf_rn(a_v, fj, c_v), __fmaf_rn(a_z, fj, c_z), red, blue);
+            else evaluate(0, i, j, __fmaf_rn(a_u, fj, c_u), __fmaf_rn(a_v, fj, c_v), __fmaf_rn(a_z, fj, c_z), red, blue);
         }
         if (bulk && tid == 0) bulk_wait_read<0>();  // the previous row's staged output has left shared memory
         __syncthreads();
@@ -325,15 +363,21 @@ extern "C" int mdvt_stereo_conv_rows(const uint8_t *depth_rgb, const uint8_t *co
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // 256 threads per CTA (4 CTAs/SM at 1080p): measured 30.5 us/frame; 128 -> 44.9, 160 -> 39.0, 320 -> 31.9.  Unlike the
     // row-local kernel this one is bound by instruction issue and global-load latency, so it wants the warps.
-    static int conv_u = 0;  // columns in flight per thread: MDVT_CONV_U = 4 | 8 (development switch)
-    if (!conv_u) {
+    static int conv_u = 0, conv_t = 0;  // development switches: MDVT_CONV_U = 1 | 2 columns in flight per thread (both eyes each),
+    if (!conv_u) {                       // MDVT_CONV_THREADS = 128 | 256 | 384 | 512
         const char *e = getenv("MDVT_CONV_U");
-        conv_u = (e && atoi(e) == 8) ? 8 : 4;  // measured equal (30.6 vs 30.7 us per 1080p frame): loads in flight are not the limiter
+        conv_u = (e && atoi(e) == 2) ? 2 : 1;
+        const char *t = getenv("MDVT_CONV_THREADS");
+        conv_t = t ? atoi(t) : 256;
+        if (conv_t != 128 && conv_t != 384 && conv_t != 512) conv_t = 256;
     }
-#define LAUNCH(M)                     \
-    do {                              \
-        if (conv_u == 4) LAUNCH_T(M, 256, 4); \
-        else LAUNCH_T(M, 256, 8);     \
+#define LAUNCH(M)                                              \
+    do {                                                       \
+        if (conv_u == 2) LAUNCH_T(M, 256, 2);                  \
+        else if (conv_t == 128) LAUNCH_T(M, 128, 1);           \
+        else if (conv_t == 384) LAUNCH_T(M, 384, 1);           \
+        else if (conv_t == 512) LAUNCH_T(M, 512, 1);           \
+        else LAUNCH_T(M, 256, 1);                              \
     } while (0)
 #define LAUNCH_T(M, kConvThreads, UU)                                                                                                   \
     do {                                                                                                                            \

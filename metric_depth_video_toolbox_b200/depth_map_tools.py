@@ -17,7 +17,9 @@ Array arguments may be NumPy arrays or CUDA tensors; NumPy in -> NumPy out.  No 
 """
 from __future__ import annotations
 
+import contextlib
 import math
+import time
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -30,6 +32,21 @@ from .geometry import compute_camera_matrix, fov_from_camera_matrix  # noqa: F40
 
 NEAR_PLANE = geo.NEAR_PLANE
 zero_identity_matrix = np.identity(4)  # depth_map_tools.py:1185
+# module globals of the reference's render() (depth_map_tools.py:1417-1421): kept so that `depth_map_tools.vis` etc. resolve;
+# the splat renderer holds no window / visualiser state
+vis = None
+v_h = None
+v_w = None
+rend = None
+use_ofscreen = True
+
+
+@contextlib.contextmanager
+def timer(name='not named'):
+    """depth_map_tools.py:13-18."""
+    start = time.perf_counter()
+    yield
+    print(f"{name}: {time.perf_counter() - start:.6f} seconds")
 
 
 # ---------------------------------------------------------------------------------------------
@@ -56,6 +73,33 @@ def convergence_angle(distance, pupillary_distance):
 def cam_look_at(cam_pos, target, up=np.array([0.0, 1.0, 0.0])):
     """depth_map_tools.py:1618-1638."""
     return geo.cam_look_at(cam_pos, target, up)
+
+
+def gl_look_at(eye, target, up):
+    """depth_map_tools.py:1599-1616."""
+    return geo.gl_look_at(eye, target, up)
+
+
+def get_cam_view(side_offset, convergence_angle_rad=0.0, reverse=False):
+    """depth_map_tools.py:226-245."""
+    return geo.get_cam_view(side_offset, convergence_angle_rad, reverse)
+
+
+def open_cv_w2c_to_gl_view(transform_to_ref):
+    """depth_map_tools.py:62-75."""
+    return geo.open_cv_w2c_to_gl_view(transform_to_ref)
+
+
+def reject_outliers(data, m=1):
+    """depth_map_tools.py:1037-1038."""
+    return abs(data - np.mean(data)) < m * np.std(data)
+
+
+def apply_side_view_to_paralax_mask(parallax_mask, normals, right):
+    """depth_map_tools.py:195-207: keep the mask where the normal's x component looks towards (right) / away from the side."""
+    right_dot = normals[..., 0]
+    cos_threshold = np.cos(np.deg2rad(90.0))
+    return parallax_mask & ((right_dot > cos_threshold) if right else (right_dot < cos_threshold))
 
 
 def get_rotation_matrix_from_xyz(angles):
@@ -183,6 +227,20 @@ class PointCloud(_Posed):
         return self.points_device().mean(dim=0).cpu().numpy() if len(self) else np.zeros(3)
 
 
+class PointMesh(PointCloud):
+    """create_mesh_from_point_cloud result: explicit grid-organised vertices (`grid` = (H, W)); drawn by render() as
+    its vertices (the splat replaces triangle rasterisation)."""
+    grid = None
+
+    @property
+    def vertices(self) -> np.ndarray:
+        return self.points
+
+    @property
+    def vertex_colors(self):
+        return self.colors
+
+
 # ---------------------------------------------------------------------------------------------
 # module functions (signatures as in the reference)
 # ---------------------------------------------------------------------------------------------
@@ -215,6 +273,49 @@ def get_mesh_from_depth_map(depth_map, cam_mat, color_frame=None, inp_mesh=None,
         unused, normals = edges.edge_vertices(mesh)
         if return_normals_of_removed:
             return mesh, unused, normals
+        used = np.ones(n, dtype=bool)
+        used[unused] = False
+        return mesh, np.where(used)[0]
+    if return_normals_of_removed:
+        return mesh, np.zeros(0, dtype=np.int64), []
+    return mesh, np.arange(n)
+
+
+def calculate_normals(depth, K):
+    """depth_map_tools.py:20-60 -> (H, W, 3) float32 unit normals (y, z flipped), one kernel.  The reference computes in
+    the depth array's float32 (its only caller hands it a float32 plane, :282); other dtypes are converted first."""
+    d, as_np = _up(depth, torch.float32)
+    return _down(ops.calculate_normals(d.contiguous(), np.asarray(K, dtype=np.float64)), as_np)
+
+
+def create_mesh_from_point_cloud(points, height, width, image_frame=None, inp_mesh=None, remove_edges=False, mask=None,
+                                 angle_threshold_deg=89.0, invalid_color=None, background_edge_mask_expandansions=0,
+                                 return_normals_of_removed=False):
+    """depth_map_tools.py:1186-1416 for grid-organised points (what create_point_cloud_from_depth returns).  The mesh handle
+    is a `PointMesh` (vertices + colours + pose: render() splats it like a point cloud); the edge test
+    (`remove_edges`, 89 degrees by default) runs on the GPU and the results come back in the reference's shapes:
+    (mesh, used_indices) or, with return_normals_of_removed, (mesh, unused_indices, normals_of_removed)."""
+    if mask is not None or invalid_color is not None or background_edge_mask_expandansions:
+        raise NotImplementedError("mask / invalid_color / background_edge_mask_expandansions belong to the mesh-cell filter, which the point "
+                                  "splat does not have")
+    pts, _ = _up(np.asarray(points).reshape(-1, 3) if not isinstance(points, torch.Tensor) else points.reshape(-1, 3), torch.float64)
+    height, width = int(height), int(width)
+    if pts.shape[0] != height * width:
+        raise ValueError(f"{pts.shape[0]} points do not form a {height}x{width} grid")
+    colors = None if image_frame is None else np.asarray(image_frame).reshape(-1, 3) / 255.0
+    if isinstance(inp_mesh, PointMesh) and len(inp_mesh) == pts.shape[0]:
+        mesh = inp_mesh
+        mesh.__init__(pts, colors)
+    else:
+        mesh = PointMesh(pts, colors)
+    mesh.grid = (height, width)
+    n = pts.shape[0]
+    if remove_edges:
+        flags, normals = ops.edge_vertices_xyz(pts.contiguous(), height, width, True, angle_threshold_deg)
+        idx = torch.nonzero(flags.reshape(-1), as_tuple=False).reshape(-1)
+        unused = idx.cpu().numpy().astype(np.int64)
+        if return_normals_of_removed:
+            return mesh, unused, normals.reshape(-1, 3)[idx].cpu().numpy()
         used = np.ones(n, dtype=bool)
         used[unused] = False
         return mesh, np.where(used)[0]
@@ -316,3 +417,36 @@ def render(objects, cam_mat, depth=False, w=None, h=None, extrinsic_matric=np.ey
     if depth == -2:
         return image, z.cpu().numpy()
     return image
+
+
+# ---------------------------------------------------------------------------------------------
+# names of the reference module that are outside the dense per-frame path: importable, refuse with the reason
+# ---------------------------------------------------------------------------------------------
+def _outside_the_path(name: str, where: str, why: str):
+    def refuse(*_args, **_kwargs):
+        raise NotImplementedError(f"depth_map_tools.{name} ({where}) is not part of the GPU per-frame path: {why}")
+
+    refuse.__name__ = name
+    refuse.__doc__ = f"{where}: {why} (refuses when called)."
+    return refuse
+
+
+_GL = "the reference's own OpenGL rasteriser pipeline, unused by stereo_rerender / 3d_view_depthfile / convert_...; render() is the splat"
+_SPARSE = "sparse host-side tracking / registration maths on a few hundred points (SciPy / OpenCV solvers), not per-pixel work"
+_O3D = "an Open3D-only utility (voxel down-sampling / interactive window)"
+mesh_from_depth_and_rgb = _outside_the_path("mesh_from_depth_and_rgb", "depth_map_tools.py:265-466", _GL)
+mesh_maker_helper_make_corner_unclamped = _outside_the_path("mesh_maker_helper_make_corner_unclamped", "depth_map_tools.py:468-470", _GL)
+mesh_maker_helper_make_corner_with_mask = _outside_the_path("mesh_maker_helper_make_corner_with_mask", "depth_map_tools.py:472-485", _GL)
+remap_ids_to_img = _outside_the_path("remap_ids_to_img", "depth_map_tools.py:487-539", _GL)
+steep_disparity_lr = _outside_the_path("steep_disparity_lr", "depth_map_tools.py:541-571", _GL)
+steep_mask_disparity = _outside_the_path("steep_mask_disparity", "depth_map_tools.py:573-609", _GL)
+generate_normal_bg_image = _outside_the_path("generate_normal_bg_image", "depth_map_tools.py:611-656", _GL)
+gl_render = _outside_the_path("gl_render", "depth_map_tools.py:660-865", _GL)
+open_gl_projection_from_camera_matrix = _outside_the_path("open_gl_projection_from_camera_matrix", "depth_map_tools.py:867-900", _GL)
+frustum_planes = _outside_the_path("frustum_planes", "depth_map_tools.py:82-134", _SPARSE)
+frusta_intersect = _outside_the_path("frusta_intersect", "depth_map_tools.py:136-193", _SPARSE)
+svd = _outside_the_path("svd", "depth_map_tools.py:937-975", _SPARSE)
+pnpSolve_ransac = _outside_the_path("pnpSolve_ransac", "depth_map_tools.py:1006-1035", _SPARSE)
+project_2d_points_to_3d = _outside_the_path("project_2d_points_to_3d", "depth_map_tools.py:1062-1084", _SPARSE)
+perspective_aware_down_sample = _outside_the_path("perspective_aware_down_sample", "depth_map_tools.py:1136-1183", _O3D)
+draw = _outside_the_path("draw", "depth_map_tools.py:1652-1658", _O3D)

@@ -76,6 +76,45 @@ def cam_look_at(cam_pos, target, up=np.array([0.0, 1.0, 0.0])) -> np.ndarray:
     ], dtype=float)
 
 
+def gl_look_at(eye, target, up) -> np.ndarray:
+    """depth_map_tools.py:1599-1616: OpenGL view matrix (float32) looking from `eye` at `target`."""
+    f = np.asarray(target) - np.asarray(eye)
+    f = f / np.linalg.norm(f)
+    s = np.cross(f, up)
+    s = s / np.linalg.norm(s)
+    u = np.cross(s, f)
+    M = np.eye(4, dtype=np.float32)
+    M[0, :3], M[1, :3], M[2, :3] = s, u, -f
+    T = np.eye(4, dtype=np.float32)
+    T[:3, 3] = -np.asarray(eye)
+    return M @ T
+
+
+def get_cam_view(side_offset, convergence_angle_rad=0.0, reverse=False) -> np.ndarray:
+    """depth_map_tools.py:226-245: eye view matrix = Ry(angle) @ T(offset) @ look-down-(-z) (or its reverse order)."""
+    def rot_y(a):
+        c, s = np.cos(a), np.sin(a)
+        return np.array([[c, 0, s, 0], [0, 1, 0, 0], [-s, 0, c, 0], [0, 0, 0, 1]], dtype=np.float32)
+
+    def shift_x(x):
+        T = np.eye(4, dtype=np.float32)
+        T[:3, 3] = [x, 0, 0]
+        return T
+
+    eye = np.array([0, 0, 0], dtype=np.float32)
+    base = gl_look_at(eye, eye + np.array([0, 0, -1], dtype=np.float32), np.array([0, 1, 0], dtype=np.float32))
+    if not reverse:
+        return rot_y(convergence_angle_rad) @ shift_x(side_offset) @ base
+    return shift_x(-side_offset) @ rot_y(-convergence_angle_rad) @ base
+
+
+def open_cv_w2c_to_gl_view(transform_to_ref) -> np.ndarray:
+    """depth_map_tools.py:62-75: OpenCV camera-to-reference pose -> OpenGL view matrix (y and z axes flipped)."""
+    w2c = np.linalg.inv(transform_to_ref)
+    A = np.diag([1, -1, -1, 1]).astype(np.float32)
+    return np.linalg.inv(A @ w2c @ A)
+
+
 def rebase_transformations(transformations, lock_frame: int):
     """stereo_rerender.py:369-373: T_i <- T_i @ inv(T_lock) when a lock frame other than 0 is given."""
     mats = [np.asarray(t, dtype=np.float64) for t in transformations]

@@ -36,6 +36,28 @@ def masked_blur(img: np.ndarray, ksize=(6, 6), sigma=0) -> np.ndarray:
     return np.clip(out, 0, 255).astype(np.uint8)
 
 
+def infill_using_normals(color_img, hole_mask, normal_map, max_steps=400):
+    """stereo_rerender.infill_using_normals (:155-240; imported by basic_nomal_infill.py:10 and
+    stereo_dissoclusion_net_infill.py:10): every hole pixel marches along the x, y direction its normal codes until it
+    leaves the hole and copies the colour it finds there.  color_img (H, W, 3) u8, hole_mask (H, W) bool / u8,
+    normal_map (H, W, 3) float in [-1, 1].  NumPy in -> NumPy out, CUDA tensors in -> CUDA tensor out; the input
+    image is not modified (the reference works on a copy)."""
+    from .depth_frames_helper import _down, _up
+
+    img, as_np = _up(color_img, torch.uint8)
+    if not as_np:
+        img = img.clone()
+    hole = hole_mask.to(torch.uint8) if isinstance(hole_mask, torch.Tensor) else np.asarray(hole_mask).astype(np.uint8)
+    hole, _ = _up(hole, torch.uint8)
+    normals, _ = _up(normal_map, torch.float32)
+    return _down(ops.normal_march_infill_f32(img, hole, normals.contiguous(), max_steps), as_np)
+
+
+def make_infill_mask(boolean_mask, normals):
+    """stereo_rerender.make_infill_mask (:89-91): a placeholder that returns None in the reference, kept importable."""
+    return None
+
+
 def telea_fill_holes(mask_u8: np.ndarray, green: np.ndarray, area: np.ndarray) -> np.ndarray:
     """`cv2.inpaint(mask, area, 3, INPAINT_TELEA)` as far as the GREEN (hole) pixels are concerned -- the only pixels of
     the result the reference keeps (stereo_rerender.py:805-807).  The reference's inpaint area is everything that is not

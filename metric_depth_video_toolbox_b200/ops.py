@@ -556,6 +556,20 @@ def edge_vertices(depth_src: torch.Tensor, source: _lib.Source, K: np.ndarray, w
     return flags, normals
 
 
+def edge_vertices_xyz(xyz: torch.Tensor, height: int, width: int, want_normals: bool = True, angle_threshold_deg: float = EDGE_ANGLE_DEG):
+    """The same edge test on explicit grid-organised vertices (H*W, 3) float64 (create_mesh_from_point_cloud's input)."""
+    _need(xyz, torch.float64, "xyz")
+    if xyz.numel() != height * width * 3:
+        raise ValueError(f"xyz must hold {height}x{width} points")
+    dev = xyz.device
+    flags = torch.empty((height, width), dtype=torch.uint8, device=dev)
+    normals = torch.empty((height, width, 3), dtype=torch.float64, device=dev) if want_normals else None
+    scratch = torch.empty(((height - 1) * (width - 1),), dtype=torch.uint8, device=dev)
+    _lib.check(_lib.load().mdvt_edge_vertices_xyz(_ptr(xyz), int(width), int(height), float(angle_threshold_deg), _ptr(scratch), _ptr(flags),
+                                                  _ptr(normals), _stream()))
+    return flags, normals
+
+
 def edge_splat(depth_src: torch.Tensor, source: _lib.Source, K: np.ndarray, flags: torch.Tensor, pose, K_render: np.ndarray,
                out_w: int, out_h: int, zbuf: torch.Tensor):
     """Flagged vertices -> edge points -> eye camera (`pose`, 4x4 float64) -> z-buffer (out_h, out_w) int64."""
@@ -602,6 +616,34 @@ def normal_march_infill(image: torch.Tensor, hole_mask: torch.Tensor, mask_img: 
     _lib.check(_lib.load().mdvt_normal_march_infill(_ptr(image), image.stride(0), _ptr(hole_mask), hole_mask.stride(0), _ptr(mask_img),
                                                     mask_img.stride(0), w, h, int(max_steps), _stream()))
     return image
+
+
+def normal_march_infill_f32(image: torch.Tensor, hole_mask: torch.Tensor, normal_map: torch.Tensor, max_steps: int = 400) -> torch.Tensor:
+    """stereo_rerender.infill_using_normals(color_img, hole_mask, normal_map, max_steps) (:155-240) in place on `image`
+    (H, W, 3) u8; hole_mask (H, W) u8 (non-zero = hole); normal_map (H, W, 3) float32, dense."""
+    h, w = hole_mask.shape
+    for t, ch, name in ((image, 3, "image"), (hole_mask, 1, "hole_mask")):
+        ok = t.dtype == torch.uint8 and t.is_cuda and t.shape[0] == h and t.shape[1] == w and t.stride(-1) == 1
+        ok = ok and ((ch == 1 and t.dim() == 2) or (ch == 3 and t.dim() == 3 and t.shape[2] == 3 and t.stride(1) == 3))
+        if not ok:
+            raise ValueError(f"{name} must be a ({h}, {w}{', 3' if ch == 3 else ''}) u8 CUDA view with dense rows")
+    _need(normal_map, torch.float32, "normal_map")
+    if tuple(normal_map.shape) != (h, w, 3):
+        raise ValueError(f"normal_map must be ({h}, {w}, 3)")
+    _lib.check(_lib.load().mdvt_normal_march_infill_f32(_ptr(image), image.stride(0), _ptr(hole_mask), hole_mask.stride(0), _ptr(normal_map),
+                                                        w, h, int(max_steps), _stream()))
+    return image
+
+
+def calculate_normals(depth: torch.Tensor, K) -> torch.Tensor:
+    """depth_map_tools.calculate_normals (:20-60): (H, W) float32 depth -> (H, W, 3) float32 unit normals."""
+    _need(depth, torch.float32, "depth")
+    if depth.dim() != 2:
+        raise ValueError("depth must be (H, W)")
+    h, w = depth.shape
+    out = torch.empty((h, w, 3), dtype=torch.float32, device=depth.device)
+    _lib.check(_lib.load().mdvt_calculate_normals(_ptr(depth), w, h, _k4(K), _ptr(out), _stream()))
+    return out
 
 
 # ---------------------------------------------------------------------------------------------

@@ -1,9 +1,10 @@
 """float32, operation-for-operation NumPy model of the CUDA kernels' arithmetic.
 
 TEST INFRASTRUCTURE ONLY (see oracle/mdvt_oracle.py).  The product computes geometry in float32
-(one IEEE rounding per written operation, no FMA contraction: csrc is compiled with --fmad=false
-and spells every operation with __fmul_rn/__fadd_rn/__fdiv_rn).  NumPy float32 +,-,*,/ round the
-same way, so this model predicts the kernels' (u', v', z') *bit for bit*; feeding its output to
+with every operation spelled as an explicit intrinsic (__fmul_rn / __fadd_rn / __fdiv_rn / __fmaf_rn;
+csrc is compiled with --fmad=false, so nothing is contracted behind the source's back).  NumPy
+float32 +,-,*,/ round the same way and `fma32` below is an exact float32 fused multiply-add,
+so this model predicts the kernels' (u', v', z') *bit for bit*; feeding its output to
 the oracle's integer stage (`mdvt_oracle.splat_ids` / `resolve`) then predicts every output
 byte.  Tests use it in two directions:
 
@@ -49,22 +50,69 @@ def unproject_f32(depth_rgb, src, bit16=True):
 
 
 def affine_row(m, X, Y, Z):
-    """((m0*X + m1*Y) + m2*Z) + m3 in float32."""
+    """((m0*X + m1*Y) + m2*Z) + m3 in float32 (unproject_f32_kernel's optional pose; splat_points_kernel)."""
     return ((m[0] * X + m[1] * Y) + m[2] * Z) + m[3]
 
 
+def fma32(a, b, c):
+    """fmaf(a, b, c): the exactly rounded float32 of a*b + c, element-wise (what __fmaf_rn / FFMA computes).
+
+    a*b is exact in float64 (24 + 24 significant bits).  The float64 sum p + c rounds once more, which could
+    double-round at a float32 tie, so the sum is rounded TO ODD instead (TwoSum gives the exact rounding error;
+    an inexact sum with an even last bit moves to its odd neighbour on the error's side): rounding a
+    round-to-odd float64 (53 bits >= 24 + 2) to float32 equals rounding the exact value."""
+    a, b, c = (np.asarray(x, dtype=np.float32) for x in (a, b, c))
+    p = a.astype(np.float64) * b.astype(np.float64)
+    c64 = c.astype(np.float64)
+    with np.errstate(invalid="ignore", over="ignore"):
+        s = p + c64
+        bb = s - p
+        err = (p - (s - bb)) + (c64 - bb)
+    bits = np.atleast_1d(s).view(np.int64).copy()
+    fix = np.atleast_1d(np.isfinite(s) & (err != 0) & np.isfinite(err)) & ((bits & 1) == 0)
+    away = np.atleast_1d((err > 0) == (s > 0))   # the exact value lies further from zero than s
+    bits[fix & away] += 1                          # sign-magnitude: +1 grows the magnitude
+    bits[fix & ~away] -= 1
+    out = bits.view(np.float64).reshape(np.shape(s))
+    with np.errstate(over="ignore", invalid="ignore"):
+        return out.astype(np.float32)
+
+
+def ray_view(src, M, K_out):
+    """make_ray_view (csrc/mdvt_common.cuh): the twelve float32 coefficients of one view, evaluated in float64 with
+    the same operations in the same order.  M: 3x4 / 4x4 (rounded to float32 first, like ViewSpec.to_c);
+    K_out = (fx', fy', cx', cy')."""
+    f64 = np.float64
+    m = np.asarray(M, dtype=f64)[:3, :4].astype(f32).astype(f64)
+    kfx, kfy, kcx, kcy = (f64(f32(v)) for v in K_out)
+    fx, fy, cx, cy, sx, sy = (f64(src[k]) for k in ("fx", "fy", "cx", "cy", "sx", "sy"))
+    ax, bx, ay, by = sx / fx, -cx / fx, sy / fy, -cy / fy
+    P = np.stack([kfx * m[0] + kcx * m[2], kfy * m[1] + kcy * m[2], m[2]])
+    A = (P[:, 0] * ax).astype(f32)
+    B = (P[:, 1] * ay).astype(f32)
+    C = ((P[:, 0] * bx + P[:, 1] * by) + P[:, 2]).astype(f32)
+    T = P[:, 3].astype(f32)
+    return A, B, C, T
+
+
 def view_uvz_f32(depth_rgb, src, M, K_out, bit16=True):
-    """project_splat_kernel's per-pixel arithmetic for one view; M is 3x4/4x4 float64 (rounded to float32
-    like ViewSpec.to_c), K_out = (fx, fy, cx, cy)."""
-    X, Y, Z = unproject_f32(depth_rgb, src, bit16)
-    m = np.asarray(M, dtype=np.float64)[:3, :4].astype(f32)
-    fx, fy, cx, cy = (f32(v) for v in K_out)
+    """project_splat_kernel's / stereo_conv_rows_kernel's per-pixel arithmetic for one view (ray form):
+    r_c = fma(B_c, row, fma(A_c, col, C_c)); N_c = fma(z, r_c, T_c); u = N_u / Zv, v = N_v / Zv, Zv = N_z."""
+    h, w = src["height"], src["width"]
+    z = depth_f32(depth_rgb, src, bit16).reshape(h, w)
+    A, B, C, T = ray_view(src, M, K_out)
+    col = np.arange(w, dtype=f32)[None, :]
+    row = np.arange(h, dtype=f32)[:, None]
+    n = []
+    for c in range(3):
+        cj = fma32(A[c], col, C[c])
+        r = fma32(B[c], row, np.broadcast_to(cj, (h, w)))
+        n.append(fma32(z, r, T[c]))
     with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
-        Xv, Yv, Zv = affine_row(m[0], X, Y, Z), affine_row(m[1], X, Y, Z), affine_row(m[2], X, Y, Z)
-        u = (fx * Xv) / Zv + cx
-        v = (fy * Yv) / Zv + cy
-    assert u.dtype == f32 and v.dtype == f32 and Zv.dtype == f32
-    return u, v, Zv
+        u = n[0] / n[2]
+        v = n[1] / n[2]
+    assert u.dtype == f32 and v.dtype == f32 and n[2].dtype == f32
+    return u.reshape(-1), v.reshape(-1), n[2].reshape(-1)
 
 
 def splat_ids_f32(u, v, z, out_w, out_h, near=orc.NEAR_PLANE):

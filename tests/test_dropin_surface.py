@@ -1,0 +1,141 @@
+"""The drop-in surface the reference's OTHER scripts import ("signatures stay importable"): every
+`def` of the reference's depth_map_tools (names extracted from the reference with `ast` into the list below by
+oracle/make_dropin_golden.py's author; 37 of them), the module-level helpers of stereo_rerender that
+basic_nomal_infill.py:10 / stereo_dissoclusion_net_infill.py:10 import, and the small host-side matrix helpers against
+values produced by RUNNING the reference (tests/golden/dropin_helpers.npz).  The GPU half checks the per-pixel ones
+(calculate_normals, infill_using_normals, create_mesh_from_point_cloud) bit for bit."""
+import inspect
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import depth_map_tools as dmt
+import stereo_rerender as sr
+
+# every top-level `def` of /root/reference/depth_map_tools.py (:14-1658), in file order
+DEPTH_MAP_TOOLS_DEFS = [
+    "timer", "calculate_normals", "open_cv_w2c_to_gl_view", "frustum_planes", "frusta_intersect", "apply_side_view_to_paralax_mask",
+    "rotation_y", "translation_matrix", "get_cam_view", "convergence_angle", "mesh_from_depth_and_rgb",
+    "mesh_maker_helper_make_corner_unclamped", "mesh_maker_helper_make_corner_with_mask", "remap_ids_to_img", "steep_disparity_lr",
+    "steep_mask_disparity", "generate_normal_bg_image", "gl_render", "open_gl_projection_from_camera_matrix", "compute_camera_matrix", "svd",
+    "transform_points", "pnpSolve_ransac", "reject_outliers", "pts_2_pcd", "project_3d_points_to_2d", "project_2d_points_to_3d",
+    "convert_mesh_to_pcd", "get_mesh_from_depth_map", "create_point_cloud_from_depth", "perspective_aware_down_sample",
+    "create_mesh_from_point_cloud", "render", "gl_look_at", "cam_look_at", "fov_from_camera_matrix", "draw"]
+DEPTH_MAP_TOOLS_GLOBALS = ["vis", "v_h", "v_w", "rend", "use_ofscreen", "zero_identity_matrix"]
+STEREO_RERENDER_DEFS = ["timer", "convert_to_equirectangular", "make_infill_mask", "convergence_angle", "masked_blur", "infill_using_normals",
+                        "fill_nan_with_closest", "curve_fit"]
+OUTSIDE_THE_PATH = ["mesh_from_depth_and_rgb", "mesh_maker_helper_make_corner_unclamped", "mesh_maker_helper_make_corner_with_mask",
+                    "remap_ids_to_img", "steep_disparity_lr", "steep_mask_disparity", "generate_normal_bg_image", "gl_render",
+                    "open_gl_projection_from_camera_matrix", "frustum_planes", "frusta_intersect", "svd", "pnpSolve_ransac",
+                    "project_2d_points_to_3d", "perspective_aware_down_sample", "draw"]
+
+
+def test_depth_map_tools_name_coverage_37_of_37():
+    assert len(DEPTH_MAP_TOOLS_DEFS) == 37
+    missing = [n for n in DEPTH_MAP_TOOLS_DEFS if not callable(getattr(dmt, n, None))]
+    assert missing == []
+    assert [n for n in DEPTH_MAP_TOOLS_GLOBALS if not hasattr(dmt, n)] == []
+
+
+def test_reference_def_list_is_current():
+    """Where the reference checkout is reachable (this container, not the GPU box) the list above is re-derived from it."""
+    from oracle import ref_bridge
+
+    if not ref_bridge.available():
+        pytest.skip("no reference checkout")
+    import ast
+
+    tree = ast.parse(open(os.path.join(ref_bridge.REFERENCE_ROOT, "depth_map_tools.py")).read())
+    assert [n.name for n in tree.body if isinstance(n, ast.FunctionDef)] == DEPTH_MAP_TOOLS_DEFS
+    tree = ast.parse(open(os.path.join(ref_bridge.REFERENCE_ROOT, "stereo_rerender.py")).read())
+    assert [n.name for n in tree.body if isinstance(n, ast.FunctionDef)] == STEREO_RERENDER_DEFS
+    # argument names / defaults of the functions this round added
+    ref = ref_bridge.load("depth_map_tools")
+    def params(fn):  # (name, default) per parameter: annotations are not part of the calling convention
+        return [(p.name, p.default) for p in inspect.signature(fn).parameters.values()]
+
+    for name in ("calculate_normals", "get_cam_view", "create_mesh_from_point_cloud", "gl_look_at", "open_cv_w2c_to_gl_view", "reject_outliers",
+                 "apply_side_view_to_paralax_mask"):
+        assert params(getattr(dmt, name)) == params(getattr(ref, name)), name
+    ref_sr = ref_bridge.load("stereo_rerender")
+    for name in ("infill_using_normals", "make_infill_mask", "masked_blur"):
+        assert params(getattr(sr, name)) == params(getattr(ref_sr, name)), name
+
+
+def test_imports_of_the_reference_infill_scripts_resolve():
+    from stereo_rerender import infill_using_normals, masked_blur  # basic_nomal_infill.py:10, stereo_dissoclusion_net_infill.py:10
+
+    assert callable(infill_using_normals) and callable(masked_blur)
+    assert [n for n in STEREO_RERENDER_DEFS if not callable(getattr(sr, n, None))] == []
+    assert sr.make_infill_mask(np.zeros((2, 2), bool), None) is None  # the reference's placeholder returns None (:89-91)
+
+
+def test_names_outside_the_path_refuse_with_a_reason():
+    for name in OUTSIDE_THE_PATH:
+        with pytest.raises(NotImplementedError, match="not part of the GPU per-frame path"):
+            getattr(dmt, name)()
+
+
+def test_host_matrix_helpers_match_reference_outputs(golden_dir, capsys):
+    g = np.load(os.path.join(golden_dir, "dropin_helpers.npz"))
+    for got, want in ((dmt.get_cam_view(0.0315, 0.0063), g["cam_view_fwd"]), (dmt.get_cam_view(-0.0315, 0.02, reverse=True), g["cam_view_rev"]),
+                      (dmt.gl_look_at(np.array([1.0, 2.0, 3.0], dtype=np.float32), np.array([0.5, -1.0, -4.0], dtype=np.float32),
+                                      np.array([0.0, 1.0, 0.0], dtype=np.float32)), g["gl_look_at"]),
+                      (dmt.open_cv_w2c_to_gl_view(g["w2c_in"]), g["w2c_gl"])):
+        assert got.dtype == want.dtype and np.array_equal(got, want)
+    assert np.array_equal(dmt.reject_outliers(g["outlier_in"], 1.5), g["outlier_mask"])
+    assert np.array_equal(dmt.apply_side_view_to_paralax_mask(g["side_pm"], g["side_n"], True), g["side_right"])
+    assert np.array_equal(dmt.apply_side_view_to_paralax_mask(g["side_pm"], g["side_n"], False), g["side_left"])
+    with dmt.timer("block"):
+        pass
+    assert capsys.readouterr().out.startswith("block: ")
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU: the per-pixel ones
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_calculate_normals_bit_exact(golden_dir):
+    g = np.load(os.path.join(golden_dir, "dropin_helpers.npz"))
+    for d, k, n in (("cn_depth", "cn_K", "cn_normals"), ("cn_depth2", "cn_K2", "cn_normals2")):
+        got = dmt.calculate_normals(g[d], g[k])
+        assert got.dtype == np.float32 and got.shape == g[n].shape
+        assert np.array_equal(got.view(np.uint32), g[n].view(np.uint32))
+    dev = dmt.calculate_normals(torch.from_numpy(g["cn_depth"]).cuda(), g["cn_K"])  # CUDA in -> CUDA out
+    assert dev.is_cuda and np.array_equal(dev.cpu().numpy().view(np.uint32), g["cn_normals"].view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_infill_using_normals_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "dropin_helpers.npz"))
+    img = g["iun_img"].copy()
+    got = sr.infill_using_normals(img, g["iun_hole"], g["iun_normals"])
+    assert np.array_equal(got, g["iun_out"]) and np.array_equal(img, g["iun_img"])   # result equal, input untouched
+    assert (got != g["iun_img"]).any()
+    assert np.array_equal(sr.infill_using_normals(img, g["iun_hole"], g["iun_normals"], max_steps=12), g["iun_out_12"])
+    t = sr.infill_using_normals(torch.from_numpy(img).cuda(), torch.from_numpy(g["iun_hole"]).cuda(), torch.from_numpy(g["iun_normals"]).cuda())
+    assert t.is_cuda and np.array_equal(t.cpu().numpy(), g["iun_out"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["plain", "posed"])
+def test_create_mesh_from_point_cloud_matches_reference_mesh_builder(golden_dir, tag):
+    """create_mesh_from_point_cloud on the points create_point_cloud_from_depth returns == what the reference's own mesh
+    builder returned for that frame (tests/golden/infill_mask.npz, made by oracle/make_infill_golden.py)."""
+    from oracle import mdvt_oracle as orc
+
+    g = np.load(os.path.join(golden_dir, "infill_mask.npz"))
+    w, h, xfov, _ = g[tag + "_params"]
+    w, h = int(w), int(h)
+    K = orc.camera_matrix(xfov, None, w, h)
+    depth = orc.apply_depth_scale(orc.decode_rgb_depth_frame(g[tag + "_depth_rgb"], 100, True), orc.master_fov_depth_scale(45.0, xfov))
+    points, hh, ww = dmt.create_point_cloud_from_depth(depth, K, True)
+    mesh, unused, removed = dmt.create_mesh_from_point_cloud(points, hh, ww, g[tag + "_colour"], None, True, return_normals_of_removed=True)
+    assert np.array_equal(unused, g[tag + "_unused"]) and np.abs(removed - g[tag + "_removed_normals"]).max() < 1e-14
+    assert np.array_equal(mesh.vertices, points) and mesh.vertex_colors.shape == (w * h, 3)
+    mesh2, used = dmt.create_mesh_from_point_cloud(points, hh, ww, remove_edges=True)
+    assert np.array_equal(np.setdiff1d(np.arange(w * h), used), g[tag + "_unused"])
+    mesh3, used3 = dmt.create_mesh_from_point_cloud(points, hh, ww)
+    assert np.array_equal(used3, np.arange(w * h))
