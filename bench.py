@@ -142,33 +142,76 @@ def cpu_baseline(n_frames: int):
                       f"{total:.1f} s of CPU work"}
 
 
+def _pin_worker(cpus, counter):
+    """Pool initializer: every worker takes one host core of its own (no migration, no two workers on one core)."""
+    with counter.get_lock():
+        k = counter.value
+        counter.value += 1
+    try:
+        os.sched_setaffinity(0, {cpus[k % len(cpus)]})
+    except (AttributeError, OSError):
+        pass
+
+
+def workload_config(world: int, n_frames: int, distinct: int):
+    """The `config` object of both arms (the reference arm runs bounded samples of the same workload)."""
+    return {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "frames_per_gpu_per_step": n_frames,
+            "distinct_frames_per_gpu": distinct, "xfov": XFOV, "max_depth": MAX_DEPTH, "pupillary_distance_mm": IPD_MM,
+            "master_xfov": MASTER_XFOV, "sharding": f"frames, {world} rank(s), no data-path collective"}
+
+
 def run_reference(args):
     """The reference's CPU path (NumPy oracle port) on all host cores: frames are independent, so they are
-    fanned over a process pool exactly like movie_2_3D.py --parallel fans scenes (movie_2_3D.py:422-452)."""
+    fanned over a process pool exactly like movie_2_3D.py --parallel fans scenes (movie_2_3D.py:422-452).
+    One worker per core, pinned; frames stream through the pool with a window of tasks always outstanding (no barrier
+    between steps: a "step" is every `4 x cores` completed frames); warm-up runs until two consecutive steps agree within
+    5 %, at least --warmup steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
+    from collections import deque
 
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    per_step = cores  # one frame per core per step
-    _prepare_cpu_frames(min(cores, 16))
+    cpus = sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else list(range(os.cpu_count() or 1))
+    cores = len(cpus)
+    per_step = 4 * cores
+    _prepare_cpu_frames(16)
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
-        for _ in range(args.warmup):
-            pool.map(_oracle_stereo_frame, range(per_step), chunksize=1)
+    counter = ctx.Value("i", 0)
+    with ctx.Pool(cores, initializer=_pin_worker, initargs=(cpus, counter)) as pool:
+        inflight, submitted = deque(), 0
+
+        def run_step():
+            nonlocal submitted
+            done = 0
+            while done < per_step:
+                while len(inflight) < 3 * cores:
+                    inflight.append(pool.apply_async(_oracle_stereo_frame, (submitted,)))
+                    submitted += 1
+                inflight.popleft().get()
+                done += 1
+
+        warm, t_prev = [], time.perf_counter()
+        while len(warm) < max(2, args.warmup) or (abs(warm[-1] - warm[-2]) > 0.05 * warm[-1] and len(warm) < args.warmup + 8):
+            run_step()
+            now = time.perf_counter()
+            warm.append(now - t_prev)
+            t_prev = now
         t0 = time.perf_counter()
-        for s in range(args.steps):
-            pool.map(_oracle_stereo_frame, [s * per_step + k for k in range(per_step)], chunksize=1)
+        for _ in range(args.steps):
+            run_step()
         elapsed = time.perf_counter() - t0
+        for r in inflight:  # drain the window (outside the timed region)
+            r.get()
     value = args.steps * per_step / elapsed
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": len(warm), "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "xfov": XFOV, "max_depth": MAX_DEPTH,
-                       "pupillary_distance_mm": IPD_MM, "master_xfov": MASTER_XFOV, "frames_per_step": per_step},
+            "config": workload_config(int(os.environ.get("WORLD_SIZE", "1")), args.frames, max(1, min(args.distinct_frames, args.frames))),
             "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
-                             "sample": f"{per_step} frames per step ({args.steps} steps) of the same clip, one frame per core, NumPy float64 oracle port"},
+                             "sample": f"{per_step} frames per step ({args.steps} timed steps after {len(warm)} warm-up steps) of the same clip, streamed "
+                                       f"through {cores} pinned single-threaded workers without a barrier between steps; NumPy float64 oracle port "
+                                       f"(oracle/mdvt_oracle.stereo_frame, both eyes + masks)"},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -377,6 +420,17 @@ def run_ours(args):
 
 def main():
     args = parse_args()
+    # the CPU legs are one NumPy process per core: BLAS / OpenMP pools of their own would only oversubscribe the cores
+    if args.impl == "reference":
+        for var in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+            os.environ.setdefault(var, "1")
+        if os.environ.get("MDVT_BENCH_MALLOC") != "1" and int(os.environ.get("RANK", "0")) == 0:
+            # NumPy's 16 MB float64 temporaries otherwise go through mmap / munmap on every operation (measured here: 30 s of
+            # system time per 3 min of user time, -17 % throughput); glibc reads these at start-up, so the arm re-executes itself
+            env = dict(os.environ, MDVT_BENCH_MALLOC="1", MALLOC_MMAP_THRESHOLD_="33554432", MALLOC_TRIM_THRESHOLD_="2000000000",
+                       MALLOC_TOP_PAD_="268435456")
+            sys.stdout.flush()
+            os.execve(sys.executable, [sys.executable] + sys.argv, env)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -41,7 +41,7 @@ if which in ("stereo", "both", "conv"):
     px = w * h * n
     print(f"generic stereo (convergence) 1080p: {ms / n * 1e3:.1f} us/frame  {n / ms * 1e3:.0f} frames/s  {px * 14 / ms / 1e6:.0f} GB/s algorithmic "
           f"({px * 14 / ms / 1e6 / 6454:.3f} of HBM peak)  holes {float((mask == 255).float().mean()):.4f}")
-if which in ("stereo", "both"):
+if which in ("stereo", "both", "posed"):
     w, h, n = 1920, 1080, 32
     d, c = clip(w, h, n)
     rr = StereoRerenderer(StereoParams(w, h, xfov=60.0, convergence_depths=[5.0] * n, infill_mask=True, force_generic=True), "cuda")

@@ -114,6 +114,12 @@ MDVT_API int mdvt_decode_depth(const uint8_t *rgb, int64_t n_pixels, int decoder
 MDVT_API int mdvt_encode_depth(const float *depth, int64_t n_pixels, double max_depth, int bit16, int bgr_order,
                       uint32_t *out_codes, uint8_t *out_pix, void *stream);
 
+/* The same for a float64 depth array: the reference clips in the array's own dtype and multiplies float64(depth), so a
+ * float64 input must not be rounded to float32 first (its codes differ in the low bits and, at truncation boundaries, in
+ * the 16-bit wire bytes). */
+MDVT_API int mdvt_encode_depth_f64(const double *depth, int64_t n_pixels, double max_depth, int bit16, int bgr_order,
+                          uint32_t *out_codes, uint8_t *out_pix, void *stream);
+
 /* decode_uint32_as_depth (depth_frames_helper.py:13-24) on a plane of codes the caller holds: D1 multiplies by
  * dec_const, D2/D3 divide by it. */
 MDVT_API int mdvt_codes_to_depth(const uint32_t *codes, int64_t n_pixels, int decoder, float dec_const, float *out_depth,

@@ -73,6 +73,7 @@ _PROTOTYPES = {
     "mdvt_device_info": (C.c_int, [C.POINTER(C.c_int)] * 5),
     "mdvt_decode_depth": (C.c_int, [_u8p, C.c_int64, C.c_int, C.c_int, C.c_float, _u32p, _f32p, _stream]),
     "mdvt_encode_depth": (C.c_int, [_f32p, C.c_int64, C.c_double, C.c_int, C.c_int, _u32p, _u8p, _stream]),
+    "mdvt_encode_depth_f64": (C.c_int, [_f64p, C.c_int64, C.c_double, C.c_int, C.c_int, _u32p, _u8p, _stream]),
     "mdvt_unproject_f32": (C.c_int, [_u8p, C.POINTER(Source), C.POINTER(C.c_float), _f32p, _stream]),
     "mdvt_unproject_f64": (C.c_int, [_u8p, C.POINTER(Source), C.POINTER(C.c_double), C.POINTER(C.c_double), _f64p, _stream]),
     "mdvt_depth_to_grey": (C.c_int, [_u8p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, _stream]),

@@ -23,18 +23,28 @@ def build_parser() -> argparse.ArgumentParser:
 
 
 def convergence_depths(depth_video: str, mask_video: Optional[str], max_depth, device, chunk: int = 12) -> List[float]:
-    """find_convergence_depth.py:46-80.  A mask video shorter than the depth video ends the analysis there
-    (ChunkReader reads in lock step), frames without any selected pixel give NaN."""
+    """find_convergence_depth.py:46-80: one value per frame of the DEPTH video.  Where the mask video has run out (or
+    there is none) the mean is taken over the whole frame (:63-74, `mesured_pixels = depth`); frames whose mask selects
+    no pixel give NaN.  The mean is the float64 sum / count rounded to float32 (the reference's float32 `.mean()`
+    agrees with it to float32 rounding)."""
+    import numpy as np
+
     out: List[float] = []
     sums = torch.empty((chunk, 4 + _lib.REDUCE_SCRATCH_DOUBLES), dtype=torch.float64, device=device)
-    for n, (depth_rgb, mask) in video_io.ChunkReader([depth_video, mask_video], chunk=chunk, grey=[False, True], decoders=video_io.default_decoders()):
-        d = depth_rgb.to(device, non_blocking=True)
-        m = None if mask is None else mask.to(device, non_blocking=True)
-        for k in range(n):
-            ops.depth_sums(d[k], max_depth, "D3", True, None if m is None else m[k], 240, out=sums[k])
-        host = sums[:n, :2].cpu()
-        for s, cnt in host.tolist():
-            out.append(s / cnt if cnt > 0 else float("nan"))
+
+    def analyse(paths, start):
+        for n, (depth_rgb, mask) in video_io.ChunkReader(paths, start, None, chunk=chunk, grey=[False, True], decoders=video_io.default_decoders()):
+            d = depth_rgb.to(device, non_blocking=True)
+            m = None if mask is None else mask.to(device, non_blocking=True)
+            for k in range(n):
+                ops.depth_sums(d[k], max_depth, "D3", True, None if m is None else m[k], 240, out=sums[k])
+            host = sums[:n, :2].cpu()
+            for s, cnt in host.tolist():
+                out.append(float(np.float32(s / cnt)) if cnt > 0 else float("nan"))
+
+    analyse([depth_video, mask_video], 0)
+    if mask_video is not None:  # the mask video ended first: the remaining frames are measured whole ("Failed to read mask video frame")
+        analyse([depth_video, None], len(out))
     return out
 
 

@@ -84,8 +84,11 @@ def _require_file(path: Optional[str], what: str, exc=FileNotFoundError):
         raise exc(f"{what} not found: {path}")
 
 
-def load_clip_parameters(args, frame_width: int, frame_height: int, n_frames: int) -> StereoParams:
-    """Everything of stereo_rerender.py:343-373,402-404 that spans the whole clip (rank 0 only under torchrun)."""
+def load_clip_parameters(args, frame_width: int, frame_height: int, n_frames: int, rendered_frames: Optional[int] = None) -> StereoParams:
+    """Everything of stereo_rerender.py:343-373,402-404 that spans the whole clip (rank 0 only under torchrun).
+    n_frames: frames of the clip; rendered_frames: frames this job renders (--max_frames): the per-frame lists of a
+    convergence / transformation file only have to cover those, as in the reference, which indexes them by frame."""
+    rendered_frames = n_frames if rendered_frames is None else rendered_frames
     convergence = None
     if args.convergence_file:
         _require_file(args.convergence_file, "Convergence file")
@@ -107,12 +110,16 @@ def load_clip_parameters(args, frame_width: int, frame_height: int, n_frames: in
         with open(args.transformation_file) as fh:
             transformations = rebase_transformations(json.load(fh), args.transformation_lock_frame)
     for name, seq in (("convergence", convergence), ("transformation", transformations)):
-        if seq is not None and len(seq) < n_frames:
-            raise ValueError(f"{name} file has {len(seq)} entries, the clip has {n_frames} frames")
+        if seq is not None and len(seq) < rendered_frames:
+            raise ValueError(f"{name} file has {len(seq)} entries, the job renders {rendered_frames} frames")
+    def whole_clip(seq):  # per-frame list cut / padded (last entry repeated; never rendered) to the clip's length: fixed broadcast format
+        seq = list(seq)[:n_frames]
+        return seq + [seq[-1]] * (n_frames - len(seq))
+
     return StereoParams(frame_width, frame_height, xfov=args.xfov, yfov=args.yfov, xfovs=xfovs, max_depth=args.max_depth,
                         pupillary_distance=args.pupillary_distance, master_xfov=args.master_xfov,
-                        convergence_depths=None if convergence is None else list(convergence)[:n_frames],
-                        transformations=None if transformations is None else transformations[:n_frames],
+                        convergence_depths=None if convergence is None else whole_clip(convergence),
+                        transformations=None if transformations is None else whole_clip(transformations),
                         infill_mask=bool(args.infill_mask), mask_rgb=True)
 
 
@@ -153,7 +160,12 @@ def run(args, keep_process_group: bool = False) -> int:
     total_frames = total if args.max_frames < 0 else min(total, args.max_frames)
 
     # whole-clip parameters: built once on rank 0, broadcast (the only inter-GPU traffic of the job)
-    params = load_clip_parameters(args, frame_width, frame_height, total) if rank == 0 else None
+    params = None
+    if rank == 0:
+        try:
+            params = load_clip_parameters(args, frame_width, frame_height, total, total_frames)
+        except Exception as exc:  # travels to the other ranks as a failure marker: nobody is left waiting in a broadcast
+            params = exc
     params, _ = sharding.broadcast_params(params, total)
     # GOP-aligned ranges when every rank still gets work: range starts are key frames of the input files
     align = video_io.GOP if total_frames >= world_size * video_io.GOP else 1

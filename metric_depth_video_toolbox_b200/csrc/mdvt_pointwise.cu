@@ -61,14 +61,16 @@ __global__ void __launch_bounds__(kThreads) decode_kernel(const uint8_t *__restr
 
 // ---------------------------------------------------------------------------------------------
 // depth_frames_helper.py:5-11: np.clip in float32, float64 multiply, truncating cast; :48-61 bytes.
-__global__ void __launch_bounds__(kThreads) encode_kernel(const float *__restrict__ depth, int64_t n, float max_depth_f32,
+// T = the array's own dtype: np.clip works in it (float32 depth: max_depth rounded to float32; float64 depth: exact).
+template <typename T>
+__global__ void __launch_bounds__(kThreads) encode_kernel(const T *__restrict__ depth, int64_t n, T max_depth_t,
                                                           double multiplier, int bit16, int bgr_order,
                                                           uint32_t *__restrict__ out_codes, uint8_t *__restrict__ out_pix) {
     for (int64_t p = blockIdx.x * (int64_t)kThreads + threadIdx.x; p < n; p += (int64_t)gridDim.x * kThreads) {
-        float d = depth[p];
+        T d = depth[p];
         // np.clip == minimum(maximum(d, 0), max): NaN propagates; a NaN code is written as 0
-        d = d < 0.0f ? 0.0f : d;
-        d = d > max_depth_f32 ? max_depth_f32 : d;
+        d = d < (T)0 ? (T)0 : d;
+        d = d > max_depth_t ? max_depth_t : d;
         const double scaled = __dmul_rn(multiplier, (double)d);
         const uint32_t code = (d == d) ? __double2uint_rz(scaled) : 0u;
         if (out_codes) out_codes[p] = code;
@@ -275,8 +277,20 @@ extern "C" int mdvt_encode_depth(const float *depth, int64_t n_pixels, double ma
     if (n_pixels == 0 || (!out_codes && !out_pix)) return MDVT_OK;
     MDVT_REQUIRE(depth != nullptr, "depth is NULL");
     const double multiplier = 4228250625.0 / max_depth;  // 255**4 / float(max_depth)
-    encode_kernel<<<grid_for(n_pixels), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+    encode_kernel<float><<<grid_for(n_pixels), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         depth, n_pixels, (float)max_depth, multiplier, bit16, bgr_order, out_codes, out_pix);
+    MDVT_CUDA_TRY(cudaGetLastError());
+    return MDVT_OK;
+}
+
+extern "C" int mdvt_encode_depth_f64(const double *depth, int64_t n_pixels, double max_depth, int bit16, int bgr_order,
+                                     uint32_t *out_codes, uint8_t *out_pix, void *stream) {
+    MDVT_REQUIRE(n_pixels >= 0, "negative pixel count");
+    MDVT_REQUIRE(max_depth > 0, "max_depth must be positive");
+    if (n_pixels == 0 || (!out_codes && !out_pix)) return MDVT_OK;
+    MDVT_REQUIRE(depth != nullptr, "depth is NULL");
+    encode_kernel<double><<<grid_for(n_pixels), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        depth, n_pixels, max_depth, 4228250625.0 / max_depth, bit16, bgr_order, out_codes, out_pix);
     MDVT_CUDA_TRY(cudaGetLastError());
     return MDVT_OK;
 }

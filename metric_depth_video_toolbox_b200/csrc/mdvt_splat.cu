@@ -6,6 +6,7 @@
 // lowest source index" deterministically.  1080p stereo = 33 MB: resident in the 126 MB L2 (ncu: 0.5 MB of DRAM reads
 // per splat).  One 4K view = 66 MB does NOT stay resident next to the streams (ncu: 43 % L2 hit rate; the two-die L2
 // holds about half of its nominal size for one working set), which is what the touched-segment flags below are for.
+#include <cstdlib>
 #include <mutex>
 
 #include "mdvt_common.cuh"
@@ -37,7 +38,7 @@ struct RayPack {  // the views of one frame in ray form (mdvt_common.cuh)
 // planes have < 2^31 pixels).
 template <bool UVZ, bool TOUCHED>
 __device__ __forceinline__ void splat_pixel(uint32_t p, const float (&cj)[kMaxViews][3], float fi, float z, const RayPack &rays,
-                                            float near_plane, int out_w, uint32_t out_n, uint32_t out_h, uint32_t id_offset, uint32_t n,
+                                            float near_plane, int out_w, uint32_t out_n, uint32_t out_h, uint32_t payload, uint32_t n,
                                             unsigned long long *__restrict__ zbuf, float *__restrict__ out_uvz, uint64_t keep,
                                             uint8_t *__restrict__ touched) {
 #pragma unroll
@@ -67,7 +68,7 @@ __device__ __forceinline__ void splat_pixel(uint32_t p, const float (&cj)[kMaxVi
             const uint32_t vi = (uint32_t)(__float_as_int(__fadd_rn(v, kRoundMagic)) - kRoundMagicBits);
             if (Zv > near_plane && ui < (uint32_t)out_w && vi < out_h) {
                 const uint32_t t = (uint32_t)k * out_n + vi * (uint32_t)out_w + ui;
-                const unsigned long long key = ((unsigned long long)__float_as_uint(Zv) << 32) | (id_offset + p);
+                const unsigned long long key = ((unsigned long long)__float_as_uint(Zv) << 32) | payload;
                 red_min_u64_keep(zbuf + t, key, keep);
                 if (TOUCHED) touched[t >> kSegShift] = 1;  // flat 64-slot segments of the plane (single view: t < out_n)
             }
@@ -86,11 +87,15 @@ __device__ __forceinline__ void splat_pixel(uint32_t p, const float (&cj)[kMaxVi
 // stream, mdvt_novel_view_frames) instead of the kernel parameters, and brought into ray form by every thread.
 constexpr int kSplatRows = 4;
 
-template <int DECODER, bool BIT16, bool DEVVIEW>
+// CKEY: the low key word is the source pixel's COLOUR (0x00BBGGRR) instead of its index -- the frame loops
+// (mdvt_render_views, mdvt_novel_view_frames): the z-buffer then IS the image and the resolve is a streaming pass with
+// no gather.  Nearest Zv still wins; among candidates with bit-identical Zv the smallest packed colour wins (the
+// index-keyed primitives take the lowest source index; the reference leaves ties to an unstable argsort).
+template <int DECODER, bool BIT16, bool DEVVIEW, bool CKEY>
 __global__ void __launch_bounds__(kSplatThreads)
-    project_splat_kernel(const void *__restrict__ rgb, int width, int height, float dec_const, float depth_scale, SourceCam cam,
-                         RayPack rays_param, const mdvt_view *__restrict__ view_dev, float near_plane, int out_w, int out_h,
-                         uint32_t id_offset, unsigned long long *__restrict__ zbuf, float *__restrict__ out_uvz,
+    project_splat_kernel(const void *__restrict__ rgb, const uint8_t *__restrict__ colour, int width, int height, float dec_const,
+                         float depth_scale, SourceCam cam, RayPack rays_param, const mdvt_view *__restrict__ view_dev, float near_plane,
+                         int out_w, int out_h, uint32_t id_offset, unsigned long long *__restrict__ zbuf, float *__restrict__ out_uvz,
                          uint8_t *__restrict__ touched) {
     const uint32_t out_n = (uint32_t)out_w * (uint32_t)out_h, n = (uint32_t)width * (uint32_t)height;
     const int col = blockIdx.x * kSplatThreads + threadIdx.x;
@@ -116,11 +121,22 @@ __global__ void __launch_bounds__(kSplatThreads)
     const int stride = gridDim.y;
     for (int row0 = blockIdx.y; row0 < height; row0 += stride * kSplatRows) {
         float z[kSplatRows];
+        uint32_t pay[kSplatRows];
 #pragma unroll
         for (int k = 0; k < kSplatRows; ++k) {
             const int row = row0 + k * stride;
             z[k] = 0.0f;
-            if (row < height) z[k] = source_depth<DECODER, BIT16>(rgb, (uint32_t)row * (uint32_t)width + (uint32_t)col, dec_const);
+            pay[k] = 0u;
+            if (row < height) {
+                const uint32_t p = (uint32_t)row * (uint32_t)width + (uint32_t)col;
+                z[k] = source_depth<DECODER, BIT16>(rgb, p, dec_const);
+                if (CKEY) {
+                    const uint8_t *c = colour + (size_t)p * 3;
+                    pay[k] = (uint32_t)__ldg(c) | ((uint32_t)__ldg(c + 1) << 8) | ((uint32_t)__ldg(c + 2) << 16);
+                } else {
+                    pay[k] = id_offset + p;
+                }
+            }
         }
 #pragma unroll
         for (int k = 0; k < kSplatRows; ++k) {
@@ -130,13 +146,13 @@ __global__ void __launch_bounds__(kSplatThreads)
                 const float zs = __fmul_rn(z[k], depth_scale), fi = __int2float_rn(row);
                 // DEVVIEW: the novel-view frame loop -- touched flags always on, never a (u, v, z) dump
                 if (DEVVIEW)
-                    splat_pixel<false, true>(p, cj, fi, zs, rays, near_plane, out_w, out_n, (uint32_t)out_h, id_offset, n, zbuf, nullptr, keep,
+                    splat_pixel<false, true>(p, cj, fi, zs, rays, near_plane, out_w, out_n, (uint32_t)out_h, pay[k], n, zbuf, nullptr, keep,
                                              touched);
-                else if (out_uvz)
-                    splat_pixel<true, false>(p, cj, fi, zs, rays, near_plane, out_w, out_n, (uint32_t)out_h, id_offset, n, zbuf, out_uvz, keep,
+                else if (!CKEY && out_uvz)
+                    splat_pixel<true, false>(p, cj, fi, zs, rays, near_plane, out_w, out_n, (uint32_t)out_h, pay[k], n, zbuf, out_uvz, keep,
                                              nullptr);
                 else
-                    splat_pixel<false, false>(p, cj, fi, zs, rays, near_plane, out_w, out_n, (uint32_t)out_h, id_offset, n, zbuf, nullptr, keep,
+                    splat_pixel<false, false>(p, cj, fi, zs, rays, near_plane, out_w, out_n, (uint32_t)out_h, pay[k], n, zbuf, nullptr, keep,
                                               nullptr);
             }
         }
@@ -431,6 +447,122 @@ __global__ void __launch_bounds__(kRowResolveThreads)
     }
 }
 
+// K3 for colour-keyed z-buffers (the frame loops): the low key word already is the winner's colour, so this is a
+// streaming pass -- 2 x LDG.128 of keys per 4 target pixels, PRMT packing, word stores -- with no dependent gather.
+// Same row form as resolve_rows_kernel (blockIdx.x tiles the 4-pixel groups of a row, blockIdx.y strides over row
+// pairs, blockIdx.z = view) and the same per-segment touched flags.  VEC = 1: any width / alignment, one pixel per thread.
+template <bool DEPTH, int VEC>
+__global__ void __launch_bounds__(kRowResolveThreads)
+    resolve_ckey_kernel(unsigned long long *__restrict__ zbuf, int out_w, int out_h, uint32_t bg_rgb, uint32_t fill_rgb, uint32_t flags,
+                        uint8_t *__restrict__ out_rgb, int64_t rgb_pitch, uint8_t *__restrict__ out_mask, int64_t mask_pitch,
+                        float *__restrict__ out_depth, int64_t depth_pitch, const uint8_t *__restrict__ touched,
+                        uint8_t *__restrict__ touched_clear, ViewStrides vs) {
+    const int g = blockIdx.x * kRowResolveThreads + threadIdx.x;
+    if (g >= (out_w + VEC - 1) / VEC) return;
+    if (blockIdx.z) {
+        const int64_t v = blockIdx.z;
+        zbuf += v * vs.zbuf;
+        if (out_rgb) out_rgb += v * vs.rgb;
+        if (out_mask) out_mask += v * vs.mask;
+        if (DEPTH) out_depth += v * vs.depth;
+    }
+    const int col0 = g * VEC;
+    const bool collide = flags & MDVT_FLAG_BG_COLLIDE, reset = flags & MDVT_FLAG_RESET_ZBUF, mask_rgb = flags & MDVT_FLAG_MASK_RGB;
+    const uint64_t keep = l2_keep_policy();
+    const int stride = gridDim.y;
+    for (int row0 = blockIdx.y; row0 < out_h; row0 += 2 * stride) {
+        uint32_t hi[2][VEC], lo[2][VEC];
+        bool on[2], live[2];
+        uint32_t t0[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int row = row0 + j * stride;
+            on[j] = row < out_h;
+            t0[j] = (uint32_t)row * (uint32_t)out_w + (uint32_t)col0;
+            live[j] = on[j];
+            if (on[j] && touched) live[j] = touched[t0[j] >> kSegShift] != 0;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (on[j] && touched && (t0[j] & ((1u << kSegShift) - 1)) == 0) touched_clear[t0[j] >> kSegShift] = 0;  // the OTHER plane: next frame's
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) hi[j][k] = 0xFFFFFFFFu, lo[j][k] = 0xFFFFFFFFu;
+            if (live[j]) {
+                if (VEC == 4) {
+                    const ulonglong2 a = ld_u64x2_keep(zbuf + t0[j], keep);
+                    const ulonglong2 b = ld_u64x2_keep(zbuf + t0[j] + 2, keep);
+                    hi[j][0] = (uint32_t)(a.x >> 32); lo[j][0] = (uint32_t)a.x;
+                    hi[j][1] = (uint32_t)(a.y >> 32); lo[j][1] = (uint32_t)a.y;
+                    hi[j][2] = (uint32_t)(b.x >> 32); lo[j][2] = (uint32_t)b.x;
+                    hi[j][3] = (uint32_t)(b.y >> 32); lo[j][3] = (uint32_t)b.y;
+                } else {
+                    const unsigned long long a = ld_u64_keep(zbuf + t0[j], keep);
+                    hi[j][0] = (uint32_t)(a >> 32); lo[j][0] = (uint32_t)a;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (!on[j]) continue;
+            const int row = row0 + j * stride;
+            uint32_t px[VEC], holes = 0;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                const bool hole = hi[j][k] == 0xFFFFFFFFu || (collide && lo[j][k] == bg_rgb);  // a filled slot holds positive finite float bits there
+                px[k] = hole ? fill_rgb : lo[j][k];
+                holes |= hole ? (1u << k) : 0u;
+            }
+            if (live[j] && reset) {
+                unsigned long long *z = zbuf + t0[j];
+                if (VEC == 4) {
+                    const ulonglong2 e = make_ulonglong2(MDVT_ZBUF_EMPTY, MDVT_ZBUF_EMPTY);
+                    st_u64x2_keep(z, e, keep);
+                    st_u64x2_keep(z + 2, e, keep);
+                } else {
+                    st_u64_keep(z, MDVT_ZBUF_EMPTY, keep);
+                }
+            }
+            if (DEPTH) {
+                float *o = out_depth + row * depth_pitch + col0;
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) o[k] = hi[j][k] == 0xFFFFFFFFu ? 0.0f : __uint_as_float(hi[j][k]);
+            }
+            if (out_rgb) {
+                uint8_t *o = out_rgb + row * rgb_pitch + (int64_t)col0 * 3;
+                if (VEC == 4) {
+                    uint32_t *ow = reinterpret_cast<uint32_t *>(o);
+                    __stcs(ow, px[0] | (px[1] << 24));
+                    __stcs(ow + 1, (px[1] >> 8) | (px[2] << 16));
+                    __stcs(ow + 2, (px[2] >> 16) | (px[3] << 8));
+                } else {
+                    o[0] = (uint8_t)px[0]; o[1] = (uint8_t)(px[0] >> 8); o[2] = (uint8_t)(px[0] >> 16);
+                }
+            }
+            if (out_mask) {
+                if (mask_rgb) {
+                    uint32_t m[VEC];
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) m[k] = (holes >> k) & 1 ? bg_rgb : 0u;
+                    uint8_t *o = out_mask + row * mask_pitch + (int64_t)col0 * 3;
+                    if (VEC == 4) {
+                        uint32_t *ow = reinterpret_cast<uint32_t *>(o);
+                        __stcs(ow, m[0] | (m[1] << 24));
+                        __stcs(ow + 1, (m[1] >> 8) | (m[2] << 16));
+                        __stcs(ow + 2, (m[2] >> 16) | (m[3] << 8));
+                    } else {
+                        o[0] = (uint8_t)m[0]; o[1] = (uint8_t)(m[0] >> 8); o[2] = (uint8_t)(m[0] >> 16);
+                    }
+                } else if (VEC == 4) {
+                    const uint32_t spread = ((holes & 1) | ((holes & 2) << 7) | ((holes & 4) << 14) | ((holes & 8) << 21)) * 0xFFu;
+                    __stcs(reinterpret_cast<uint32_t *>(out_mask + row * mask_pitch + col0), spread);
+                } else {
+                    out_mask[row * mask_pitch + col0] = holes ? 255 : 0;
+                }
+            }
+        }
+    }
+}
+
 static int grid_for(int64_t work_items) {
     const int64_t blocks = (work_items + kThreads - 1) / kThreads;
     const int64_t cap = (int64_t)sm_count() * 8;
@@ -453,7 +585,7 @@ extern "C" int mdvt_zbuf_clear(uint64_t *zbuf, int64_t n_slots, void *stream) {
 
 static int launch_project_splat(const void *depth_src, const mdvt_source *src, const ViewPack &pack, const mdvt_view *view_dev, float near_plane,
                                 int out_w, int out_h, uint32_t id_offset, unsigned long long *zb, float *out_uvz, cudaStream_t st,
-                                uint8_t *touched = nullptr);
+                                uint8_t *touched = nullptr, const uint8_t *colour_key = nullptr);
 
 static int pack_views(const mdvt_view *views_host, int n_views, ViewPack &pack) {
     MDVT_REQUIRE(n_views >= 1 && n_views <= kMaxViews, "n_views must be 1..%d", kMaxViews);
@@ -544,9 +676,48 @@ static int launch_resolve(unsigned long long *zb, const uint8_t *colour_rgb, int
     return MDVT_OK;
 }
 
+// colour-keyed planes -> image / mask / depth, all views of a frame in one launch
+static int launch_resolve_ckey(unsigned long long *zb, int out_w, int out_h, uint32_t bg_rgb, uint32_t fill_rgb, uint32_t flags, uint8_t *out_rgb,
+                               int64_t rgb_pitch, uint8_t *out_mask, int64_t mask_pitch, float *out_depth, int64_t depth_pitch, cudaStream_t st,
+                               const uint8_t *touched, uint8_t *touched_clear, int n_views, ViewStrides vs) {
+    const int mask_bpp = (flags & MDVT_FLAG_MASK_RGB) ? 3 : 1;
+    MDVT_REQUIRE(!out_rgb || rgb_pitch >= (int64_t)out_w * 3, "rgb_pitch %lld too small", (long long)rgb_pitch);
+    MDVT_REQUIRE(!out_mask || mask_pitch >= (int64_t)out_w * mask_bpp, "mask_pitch %lld too small", (long long)mask_pitch);
+    if (depth_pitch == 0) depth_pitch = out_w;
+    MDVT_REQUIRE(!out_depth || depth_pitch >= out_w, "depth_pitch %lld too small", (long long)depth_pitch);
+    MDVT_REQUIRE((int64_t)out_w * out_h < 0x7FFFFFFFll, "target plane must hold fewer than 2^31 pixels");
+    auto word_ok = [](const void *p, int64_t a, int64_t b) { return (reinterpret_cast<uintptr_t>(p) % 4 == 0) && a % 4 == 0 && b % 4 == 0; };
+    const bool vec4 = out_w % 4 == 0 && reinterpret_cast<uintptr_t>(zb) % 16 == 0 && (vs.zbuf % 2 == 0) &&
+                      (!out_rgb || word_ok(out_rgb, rgb_pitch, vs.rgb)) && (!out_mask || word_ok(out_mask, mask_pitch, vs.mask));
+    bg_rgb &= 0xFFFFFF;
+    fill_rgb &= 0xFFFFFF;
+    static int per_sm_of[2][2] = {{0, 0}, {0, 0}};
+    int &per_sm = per_sm_of[out_depth ? 1 : 0][vec4 ? 1 : 0];
+#define PICK(D, V) resolve_ckey_kernel<D, V>
+    if (!per_sm) {
+        if (out_depth) per_sm = vec4 ? resident_ctas(PICK(true, 4), kRowResolveThreads) : resident_ctas(PICK(true, 1), kRowResolveThreads);
+        else per_sm = vec4 ? resident_ctas(PICK(false, 4), kRowResolveThreads) : resident_ctas(PICK(false, 1), kRowResolveThreads);
+    }
+    const int vec = vec4 ? 4 : 1;
+    const int col_blocks = ((out_w + vec - 1) / vec + kRowResolveThreads - 1) / kRowResolveThreads;
+    int row_blocks = sm_count() * per_sm / (col_blocks * n_views);
+    if (row_blocks < 1) row_blocks = 1;
+    if (row_blocks > (out_h + 1) / 2) row_blocks = (out_h + 1) / 2;
+    const dim3 grid(col_blocks, row_blocks, n_views);
+#define GO(D, V)                                                                                                                             \
+    PICK(D, V)<<<grid, kRowResolveThreads, 0, st>>>(zb, out_w, out_h, bg_rgb, fill_rgb, flags, out_rgb, rgb_pitch, out_mask, mask_pitch, out_depth, \
+                                                    depth_pitch, touched, touched_clear, vs)
+    if (out_depth) { if (vec4) GO(true, 4); else GO(true, 1); }
+    else { if (vec4) GO(false, 4); else GO(false, 1); }
+#undef GO
+#undef PICK
+    MDVT_CUDA_TRY(cudaGetLastError());
+    return MDVT_OK;
+}
+
 static int launch_project_splat(const void *depth_src, const mdvt_source *src, const ViewPack &pack, const mdvt_view *view_dev, float near_plane,
                                 int out_w, int out_h, uint32_t id_offset, unsigned long long *zb, float *out_uvz, cudaStream_t st,
-                                uint8_t *touched) {
+                                uint8_t *touched, const uint8_t *colour_key) {
     MDVT_REQUIRE((touched != nullptr) == (view_dev != nullptr), "touched flags go with the device-resident single view");
     MDVT_REQUIRE(out_w < (1 << 22) && out_h < (1 << 22), "target sides must be below 2^22 pixels");
     MDVT_REQUIRE((int64_t)src->width * src->height < 0x7FFFFFFFll && (int64_t)out_w * out_h * pack.n < 0x7FFFFFFFll,
@@ -559,16 +730,19 @@ static int launch_project_splat(const void *depth_src, const mdvt_source *src, c
             rays.v[k] = make_ray_view(cam.fx, cam.fy, cam.cx, cam.cy, cam.sx, cam.sy, pack.v[k].M, pack.v[k].fx, pack.v[k].fy, pack.v[k].cx,
                                       pack.v[k].cy);
     const int col_blocks = (src->width + kSplatThreads - 1) / kSplatThreads;
+    MDVT_REQUIRE(!view_dev || colour_key, "the device-resident view goes with colour keys");
+    MDVT_REQUIRE(!(colour_key && out_uvz), "no (u, v, z) dump in colour-key mode");
 #define CALL(D, B)                                                                                                                   \
     do {                                                                                                                             \
-        auto kernel = view_dev ? project_splat_kernel<D, B, true> : project_splat_kernel<D, B, false>;                               \
-        static int per_sm_of[2] = {0, 0};                                                                                            \
-        int &per_sm = per_sm_of[view_dev ? 1 : 0];                                                                                   \
+        auto kernel = view_dev ? project_splat_kernel<D, B, true, true>                                                              \
+                               : (colour_key ? project_splat_kernel<D, B, false, true> : project_splat_kernel<D, B, false, false>);   \
+        static int per_sm_of[3] = {0, 0, 0};                                                                                         \
+        int &per_sm = per_sm_of[view_dev ? 2 : (colour_key ? 1 : 0)];                                                                \
         if (!per_sm) per_sm = resident_ctas(kernel, kSplatThreads);                                                                   \
         int row_blocks = sm_count() * per_sm / col_blocks; /* every CTA resident: no second wave */                                  \
         if (row_blocks < 1) row_blocks = 1;                                                                                          \
         if (row_blocks > src->height) row_blocks = src->height;                                                                      \
-        kernel<<<dim3(col_blocks, row_blocks), kSplatThreads, 0, st>>>(depth_src, src->width, src->height, src->dec_const, src->depth_scale, cam, \
+        kernel<<<dim3(col_blocks, row_blocks), kSplatThreads, 0, st>>>(depth_src, colour_key, src->width, src->height, src->dec_const, src->depth_scale, cam, \
                                                                      rays, view_dev, near_plane, out_w, out_h, id_offset, zb, out_uvz, touched); \
     } while (0)
     MDVT_DISPATCH_SOURCE(src->decoder, src->bit16, CALL);
@@ -600,6 +774,7 @@ extern "C" int mdvt_render_views(const void *depth_src, int64_t depth_frame_stri
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     unsigned long long *zb = reinterpret_cast<unsigned long long *>(zbuf);
     const int64_t out_n = (int64_t)out_w * out_h;
+    static const int dbg = getenv("MDVT_DEBUG") ? atoi(getenv("MDVT_DEBUG")) : 0;  // timing aid: 1 no splat, 2 no resolve, 4 no re-arm
     for (int f = 0; f < n_frames; ++f) {
         const mdvt_source *src = sources_host + (per_frame_source ? f : 0);
         if (int rc = check_source(src)) return rc;
@@ -607,32 +782,21 @@ extern "C" int mdvt_render_views(const void *depth_src, int64_t depth_frame_stri
         ViewPack pack{};
         if (int rc = pack_views(views_host + (int64_t)f * n_views, n_views, pack)) return rc;
         const uint8_t *dsrc = static_cast<const uint8_t *>(depth_src) + f * depth_frame_stride;
-        if (int rc = launch_project_splat(dsrc, src, pack, nullptr, near_plane, out_w, out_h, 0, zb, nullptr, st)) return rc;
+        const uint8_t *colour_f = colour_rgb + f * colour_frame_stride;
+        if (!(dbg & 1))
+            if (int rc = launch_project_splat(dsrc, src, pack, nullptr, near_plane, out_w, out_h, 0, zb, nullptr, st, nullptr, colour_f)) return rc;
+        if (dbg & 2) continue;
         auto at = [&](const mdvt_plane_layout *L, int v) -> uint8_t * {
             return (L && L->base) ? static_cast<uint8_t *>(L->base) + f * L->frame_stride + v * L->view_stride : nullptr;
         };
-        const uint8_t *colour_f = colour_rgb + f * colour_frame_stride;
         const int64_t mask_pitch = mask_out ? mask_out->row_pitch : 0, depth_pitch = depth_out ? depth_out->row_pitch / 4 : 0;
-        // all views in ONE launch (blockIdx.z) when every plane qualifies for the row form of the resolve
-        auto word_ok = [](const void *p, int64_t a, int64_t b) { return (reinterpret_cast<uintptr_t>(p) % 4 == 0) && a % 4 == 0 && b % 4 == 0; };
-        const bool one_launch = n_views > 1 && out_w % 4 == 0 && reinterpret_cast<uintptr_t>(zb) % 16 == 0 && out_n % 2 == 0 &&
-                                word_ok(at(rgb_out, 0), rgb_out->row_pitch, rgb_out->view_stride) &&
-                                (!at(mask_out, 0) || word_ok(at(mask_out, 0), mask_pitch, mask_out->view_stride)) &&
-                                (!at(depth_out, 0) || word_ok(at(depth_out, 0), 0, depth_out->view_stride));
-        if (one_launch) {
-            const ViewStrides vs{out_n, rgb_out->view_stride, mask_out ? mask_out->view_stride : 0, depth_out ? depth_out->view_stride / 4 : 0};
-            if (int rc = launch_resolve(zb, colour_f, out_w, out_h, bg_rgb, fill_rgb, flags | MDVT_FLAG_RESET_ZBUF, at(rgb_out, 0),
-                                        rgb_out->row_pitch, at(mask_out, 0), mask_pitch, reinterpret_cast<float *>(at(depth_out, 0)), depth_pitch,
-                                        nullptr, st, nullptr, nullptr, n_views, vs))
-                return rc;
-        } else {
-            for (int v = 0; v < n_views; ++v) {
-                if (int rc = launch_resolve(zb + v * out_n, colour_f, out_w, out_h, bg_rgb, fill_rgb, flags | MDVT_FLAG_RESET_ZBUF, at(rgb_out, v),
-                                            rgb_out->row_pitch, at(mask_out, v), mask_pitch, reinterpret_cast<float *>(at(depth_out, v)),
-                                            depth_pitch, nullptr, st))
-                    return rc;
-            }
-        }
+        // all views in ONE launch (blockIdx.z); the kernel falls back to one pixel per thread for odd widths / alignments
+        const ViewStrides vs{out_n, rgb_out->view_stride, mask_out ? mask_out->view_stride : 0, depth_out ? depth_out->view_stride / 4 : 0};
+        MDVT_REQUIRE(!at(depth_out, 0) || (depth_out->view_stride % 4 == 0 && depth_out->row_pitch % 4 == 0), "depth planes must be float aligned");
+        if (int rc = launch_resolve_ckey(zb, out_w, out_h, bg_rgb, fill_rgb, (dbg & 4) ? flags : (flags | MDVT_FLAG_RESET_ZBUF), at(rgb_out, 0),
+                                         rgb_out->row_pitch, at(mask_out, 0), mask_pitch, reinterpret_cast<float *>(at(depth_out, 0)), depth_pitch, st,
+                                         nullptr, nullptr, n_views, vs))
+            return rc;
     }
     return MDVT_OK;
 }
@@ -718,13 +882,14 @@ extern "C" int mdvt_novel_view_frames(const void *depth_src, int64_t depth_frame
         if (int rc = centroid_of(f)) return rc;
         MDVT_CUDA_TRY(cudaStreamWaitEvent(st, aux->centroid_done[f % kRing], 0));
         uint8_t *cur = touched + (f & 1) * plane, *other = touched + ((f + 1) & 1) * plane;
-        if (int rc = launch_project_splat(dsrc, src, pack, views_dev + f, near_plane, out_w, out_h, 0, zb, nullptr, st, cur)) return rc;
+        if (int rc = launch_project_splat(dsrc, src, pack, views_dev + f, near_plane, out_w, out_h, 0, zb, nullptr, st, cur,
+                                          colour_rgb + f * colour_frame_stride))
+            return rc;
         auto at = [&](const mdvt_plane_layout *L) -> uint8_t * {
             return (L && L->base) ? static_cast<uint8_t *>(L->base) + f * L->frame_stride : nullptr;
         };
-        if (int rc = launch_resolve(zb, colour_rgb + f * colour_frame_stride, out_w, out_h, bg_rgb, fill_rgb, flags | MDVT_FLAG_RESET_ZBUF,
-                                    at(rgb_out), rgb_out->row_pitch, at(mask_out), mask_out ? mask_out->row_pitch : 0, nullptr, 0, nullptr, st,
-                                    cur, other))
+        if (int rc = launch_resolve_ckey(zb, out_w, out_h, bg_rgb, fill_rgb, flags | MDVT_FLAG_RESET_ZBUF, at(rgb_out), rgb_out->row_pitch,
+                                         at(mask_out), mask_out ? mask_out->row_pitch : 0, nullptr, 0, st, cur, other, 1, ViewStrides{0, 0, 0, 0}))
             return rc;
         MDVT_CUDA_TRY(cudaEventRecord(aux->frame_done[f % kRing], st));
     }

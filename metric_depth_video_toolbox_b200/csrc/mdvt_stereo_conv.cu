@@ -10,10 +10,10 @@
 // queues the neighbour when the prediction says it can also round into r, and runs the exact float32 arithmetic of
 // the generic path (mdvt_splat.cu: 6 FFMA, refined-reciprocal divisions, magic-number rounding) on the candidates.  A
 // candidate whose exact rint(v') equals r goes into a shared-memory z-buffer with a 64-bit atomicMin on
-// (float_bits(Zv) << 32 | source row offset << 12 | column) -- the same order as the generic path's
-// (Zv, source index), so the result is bit-identical to mdvt_project_splat + mdvt_resolve, which the tests assert.
-// Phase B gathers the winners' colours straight from global memory (the few source rows involved are L1/L2 hot),
-// packs RGB / mask bytes into a staging row and hands it to a TMA bulk store, like the row-local kernel.
+// (float_bits(Zv) << 32 | colour) -- the colour-keyed order of the generic frame loop (nearest Zv, then the smallest
+// packed colour), so the result is bit-identical to mdvt_render_views with the same cameras, which the tests assert.
+// Phase B needs no gather: it unpacks the keys into RGB / mask bytes in a staging row and hands that to a TMA bulk
+// store, like the row-local kernel.
 // HBM traffic is the algorithmic 14 B/px; the 33 MB z-buffer planes and their read / re-arm passes are gone.
 #include <cstdlib>
 
@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(kConvThreads)
         }
         const float dec_const = __ldg(&fc->dec_const), depth_scale = __ldg(&fc->depth_scale), near_plane = __ldg(&fc->near_plane);
         const uint8_t *dframe = depth_rgb + (int64_t)frame * height * row_bytes;
+        const uint8_t *cframe = colour_rgb + (int64_t)frame * height * row_bytes;
         const float fr = (float)r;
         // the pose is Ry + x-shift: B_u = B_z = T_v = T_z = 0 exactly (P's second column is (0, fy', 0), its last (fx' m3, 0, 0)),
         // so r_u = C_u(j), r_z = C_z(j) and the FFMAs that would add an exact 0 are left out: same float32 results
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(kConvThreads)
         i_base = max(i_base, 0);
 
         // exact path: the float32 arithmetic of splat_pixel() in mdvt_splat.cu for source pixel (i, j) and eye e
-        auto evaluate = [&](int e, int i, int j, float cju, float cjv, float cjz, uint32_t red, uint32_t blue) {
+        auto evaluate = [&](int e, int i, float cju, float cjv, float cjz, uint32_t red, uint32_t blue, uint32_t rgb) {
             const float z = __fmul_rn(depth_of<MDVT_DECODE_D1>(code_of<MDVT_DECODE_D1, true>(red, 0u, blue), dec_const), depth_scale);
             const float nu = __fmaf_rn(z, cju, Tu[e]);
             const float nv = __fmaf_rn(z, __fmaf_rn(Bv[e], (float)i, cjv), 0.0f);
@@ -139,9 +140,8 @@ __global__ void __launch_bounds__(kConvThreads)
             const uint32_t ui = (uint32_t)(__float_as_int(__fadd_rn(u, kConvMagic)) - kConvMagicBits);
             const int vi = __float_as_int(__fadd_rn(v, kConvMagic)) - kConvMagicBits;
             if (Zv > near_plane && vi == r && ui < (uint32_t)width) {
-                const unsigned long long key =
-                    ((unsigned long long)__float_as_uint(Zv) << 32) | ((uint32_t)(i - i_base) << 12) | (uint32_t)j;
-                atomicMin(&s_z[e * width + ui], key);
+                // colour-keyed like the generic frame loop (mdvt_splat.cu, CKEY): nearest Zv, then the smallest packed colour
+                atomicMin(&s_z[e * width + ui], ((unsigned long long)__float_as_uint(Zv) << 32) | rgb);
             }
         };
 
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(kConvThreads)
         // U columns per thread and pass, both eyes: all 4U byte loads are issued before the first is used
         for (int jb = tid; jb < width; jb += U * kConvThreads) {
             int i0[U][2];
-            uint32_t red[U][2], blue[U][2], second[U][2];  // second: queue entry of the neighbour row, 0xFFFFFFFF = none
+            uint32_t red[U][2], blue[U][2], c0[U][2], c1[U][2], c2[U][2], second[U][2];  // second: queue entry of the neighbour row, 0xFFFFFFFF = none
             float cju[U][2], cjv[U][2], cjz[U][2];
             bool in0[U][2];
             // (1) predictions of all columns and eyes: pure arithmetic, nothing long-latency in between
@@ -190,9 +190,12 @@ __global__ void __launch_bounds__(kConvThreads)
 #pragma unroll
                 for (int e = 0; e < 2; ++e)
                     if (in0[k][e]) {
-                        const uint8_t *px = dframe + ((uint32_t)i0[k][e] * (uint32_t)width + (uint32_t)(jb + k * kConvThreads)) * 3u;
-                        red[k][e] = __ldg(px);
-                        blue[k][e] = __ldg(px + 2);
+                        const uint32_t off = ((uint32_t)i0[k][e] * (uint32_t)width + (uint32_t)(jb + k * kConvThreads)) * 3u;
+                        red[k][e] = __ldg(dframe + off);
+                        blue[k][e] = __ldg(dframe + off + 2);
+                        c0[k][e] = __ldg(cframe + off);
+                        c1[k][e] = __ldg(cframe + off + 1);
+                        c2[k][e] = __ldg(cframe + off + 2);
                     }
             // (3) second candidates -> queue (<= one per column and eye)
 #pragma unroll
@@ -205,8 +208,9 @@ __global__ void __launch_bounds__(kConvThreads)
                             s_queue[slot] = second[k][e];
                         } else {  // queue full (extreme convergence angles only): the candidate is evaluated here, divergently
                             const int i = i_base + (int)((second[k][e] >> 12) & 0x7FFFFu), j = jb + k * kConvThreads;
-                            const uint8_t *px = dframe + ((uint32_t)i * (uint32_t)width + (uint32_t)j) * 3u;
-                            evaluate(e, i, j, cju[k][e], cjv[k][e], cjz[k][e], __ldg(px), __ldg(px + 2));
+                            const uint32_t off = ((uint32_t)i * (uint32_t)width + (uint32_t)j) * 3u;
+                            evaluate(e, i, cju[k][e], cjv[k][e], cjz[k][e], __ldg(dframe + off), __ldg(dframe + off + 2),
+                                     (uint32_t)__ldg(cframe + off) | ((uint32_t)__ldg(cframe + off + 1) << 8) | ((uint32_t)__ldg(cframe + off + 2) << 16));
                         }
                     }
             // (4) exact arithmetic
@@ -214,7 +218,8 @@ __global__ void __launch_bounds__(kConvThreads)
             for (int k = 0; k < U; ++k)
 #pragma unroll
                 for (int e = 0; e < 2; ++e)
-                    if (in0[k][e]) evaluate(e, i0[k][e], jb + k * kConvThreads, cju[k][e], cjv[k][e], cjz[k][e], red[k][e], blue[k][e]);
+                    if (in0[k][e])
+                        evaluate(e, i0[k][e], cju[k][e], cjv[k][e], cjz[k][e], red[k][e], blue[k][e], c0[k][e] | (c1[k][e] << 8) | (c2[k][e] << 16));
         }
         __syncthreads();
         const int queued = min((int)*s_qcount, L.queue_cap);
@@ -226,27 +231,18 @@ __global__ void __launch_bounds__(kConvThreads)
             const float a_u = e ? Au[1] : Au[0], a_v = e ? Av[1] : Av[0], a_z = e ? Az[1] : Az[0];
             const float c_u = e ? Cu[1] : Cu[0], c_v = e ? Cv[1] : Cv[0], c_z = e ? Cz[1] : Cz[0];
             const uint32_t red = __ldg(dframe + off), blue = __ldg(dframe + off + 2);
-            if (e) evaluate(1, i, j, __fmaf_rn(a_u, fj, c_u), __fmaf_rn(a_v, fj, c_v), __fmaf_rn(a_z, fj, c_z), red, blue);
-            else evaluate(0, i, j, __fmaf_rn(a_u, fj, c_u), __fmaf_rn(a_v, fj, c_v), __fmaf_rn(a_z, fj, c_z), red, blue);
+            const uint32_t rgb = (uint32_t)__ldg(cframe + off) | ((uint32_t)__ldg(cframe + off + 1) << 8) | ((uint32_t)__ldg(cframe + off + 2) << 16);
+            if (e) evaluate(1, i, __fmaf_rn(a_u, fj, c_u), __fmaf_rn(a_v, fj, c_v), __fmaf_rn(a_z, fj, c_z), red, blue, rgb);
+            else evaluate(0, i, __fmaf_rn(a_u, fj, c_u), __fmaf_rn(a_v, fj, c_v), __fmaf_rn(a_z, fj, c_z), red, blue, rgb);
         }
         if (bulk && tid == 0) bulk_wait_read<0>();  // the previous row's staged output has left shared memory
         __syncthreads();
 
-        // ---- phase B: winners -> colours, hole mask, depth; z-buffers re-armed -------------------------
-        const uint8_t *cframe = colour_rgb + (int64_t)frame * height * row_bytes;
-        // byte offset of the winner's colour inside the frame (holes read pixel 0: a harmless, always valid address)
-        auto colour_offset = [&](unsigned long long key) -> uint32_t {
-            const uint32_t payload = (uint32_t)key;
-            // an occupied slot never has an all-ones payload (column <= 4095, row offset < 2^20): one 32-bit test
-            return payload == 0xFFFFFFFFu ? 0u : ((uint32_t)(i_base + (int)(payload >> 12)) * (uint32_t)width + (payload & 0xFFFu)) * 3u;
-        };
-        auto finish_colour = [&](unsigned long long key, uint32_t c, bool &hole) -> uint32_t {
-            hole = (uint32_t)key == 0xFFFFFFFFu || (collide && c == bg_rgb);
+        // ---- phase B: z-buffers -> colours, hole mask, depth; z-buffers re-armed (the low key word IS the colour) -----
+        auto finish_colour = [&](unsigned long long key, bool &hole) -> uint32_t {
+            const uint32_t c = (uint32_t)key;  // an occupied slot holds 0x00BBGGRR there, the empty one all ones
+            hole = c == 0xFFFFFFFFu || (collide && c == bg_rgb);
             return hole ? fill_rgb : c;
-        };
-        auto colour_of = [&](unsigned long long key, bool &hole) -> uint32_t {
-            const uint8_t *sc = cframe + colour_offset(key);
-            return finish_colour(key, (uint32_t)__ldg(sc) | ((uint32_t)__ldg(sc + 1) << 8) | ((uint32_t)__ldg(sc + 2) << 16), hole);
         };
         if (vec4) {  // 4 consecutive target pixels per thread: 2 x LDS.128 keys, word stores into the staging rows
             for (int g4 = tid; g4 < 2 * width / 4; g4 += kConvThreads) {
@@ -257,14 +253,9 @@ __global__ void __launch_bounds__(kConvThreads)
                 zq[1] = empty2;
                 const unsigned long long key[4] = {ka.x, ka.y, kb.x, kb.y};
                 bool hole[4];
-                uint32_t c[4], b0[4], b1[4], b2[4];
+                uint32_t c[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {  // all twelve byte loads in flight before any is used
-                    const uint8_t *sc = cframe + colour_offset(key[k]);
-                    b0[k] = __ldg(sc); b1[k] = __ldg(sc + 1); b2[k] = __ldg(sc + 2);
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) c[k] = finish_colour(key[k], b0[k] | (b1[k] << 8) | (b2[k] << 16), hole[k]);
+                for (int k = 0; k < 4; ++k) c[k] = finish_colour(key[k], hole[k]);
                 uint32_t *ow = reinterpret_cast<uint32_t *>(s_out) + 3 * g4;
                 ow[0] = c[0] | (c[1] << 24);
                 ow[1] = (c[1] >> 8) | (c[2] << 16);
@@ -295,7 +286,7 @@ __global__ void __launch_bounds__(kConvThreads)
                 const unsigned long long key = s_z[t];
                 s_z[t] = kEmpty64;
                 bool hole;
-                const uint32_t c = colour_of(key, hole);
+                const uint32_t c = finish_colour(key, hole);
                 uint8_t *o = s_out + 3 * t;
                 o[0] = (uint8_t)c; o[1] = (uint8_t)(c >> 8); o[2] = (uint8_t)(c >> 16);
                 if (MASK_MODE == 1) {

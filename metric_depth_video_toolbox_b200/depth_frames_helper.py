@@ -56,9 +56,14 @@ def _down(t: torch.Tensor, as_numpy: bool):
 # ---------------------------------------------------------------------------------------------
 # linear codec (depth_frames_helper.py:5-24, 48-75, 99-103)
 # ---------------------------------------------------------------------------------------------
+def _is_f64(a) -> bool:
+    return (a.dtype == torch.float64) if isinstance(a, torch.Tensor) else (np.asarray(a).dtype == np.float64)
+
+
 def encode_depth_as_uint32(depth, max_depth):
-    """clip to [0, max_depth]; (255**4 / max_depth * float64(depth)) truncated to uint32."""
-    d, as_np = _up(depth, torch.float32)
+    """clip to [0, max_depth] in the array's own dtype; (255**4 / max_depth * float64(depth)) truncated to uint32.
+    float64 depth stays float64 (the reference never rounds it to float32); everything else is computed as float32."""
+    d, as_np = _up(depth, torch.float64 if _is_f64(depth) else torch.float32)
     _, codes = ops.encode_depth(d, max_depth, True, True, want_codes=True)
     return _down(codes, as_np)
 
@@ -170,7 +175,7 @@ def save_depth_video(frames, output_video_path, fps, max_depth_arg, rescale_widt
             depth = np.asarray(frames[i])
             if rescale_width != width or rescale_height != height:
                 depth = cv2.resize(depth, (rescale_width, rescale_height), interpolation=cv2.INTER_LINEAR)
-            chunk.append(np.ascontiguousarray(depth, dtype=np.float32))
+            chunk.append(np.ascontiguousarray(depth, dtype=np.float64 if depth.dtype == np.float64 else np.float32))
         dev = torch.from_numpy(np.stack(chunk)).to(_device())
         coded = ops.encode_depth(dev, max_depth_arg, True, True)  # B, G, R like encode_data_as_BGR
         out.write(coded if on_device else coded.cpu().numpy(), rgb=False)

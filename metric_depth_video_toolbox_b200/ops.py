@@ -73,14 +73,18 @@ def decode_depth(rgb: torch.Tensor, max_depth, bit16: bool = True, decoder: str 
 
 
 def encode_depth(depth: torch.Tensor, max_depth, bit16: bool = True, bgr_order: bool = True, want_codes: bool = False):
-    """float32 metres -> (..., 3) u8 (B,G,R by default, as the reference hands to cv2)."""
-    _need(depth, torch.float32, "depth")
+    """float32 (or float64: clipped and scaled in float64 like the reference does for such an array) metres -> (..., 3) u8
+    (B,G,R by default, as the reference hands to cv2)."""
+    if depth.dtype != torch.float64:
+        _need(depth, torch.float32, "depth")
+    else:
+        _need(depth, torch.float64, "depth")
     n = depth.numel()
     pix = torch.empty(depth.shape + (3,), dtype=torch.uint8, device=depth.device)
     codes = torch.empty(depth.shape, dtype=torch.uint32, device=depth.device) if want_codes else None
     lib = _lib.load()
-    _lib.check(lib.mdvt_encode_depth(_ptr(depth), n, float(max_depth), int(bool(bit16)), int(bool(bgr_order)), _ptr(codes),
-                                     _ptr(pix), _stream()))
+    fn = lib.mdvt_encode_depth_f64 if depth.dtype == torch.float64 else lib.mdvt_encode_depth
+    _lib.check(fn(_ptr(depth), n, float(max_depth), int(bool(bit16)), int(bool(bgr_order)), _ptr(codes), _ptr(pix), _stream()))
     return (pix, codes) if want_codes else pix
 
 
@@ -266,6 +270,39 @@ class ViewSpec:
         return v
 
 
+SOURCE_DTYPE = np.dtype([("width", "<i4"), ("height", "<i4"), ("decoder", "<i4"), ("bit16", "<i4"), ("dec_const", "<f4"),
+                         ("depth_scale", "<f4"), ("fx", "<f4"), ("fy", "<f4"), ("cx", "<f4"), ("cy", "<f4"), ("grid_sx", "<f4"),
+                         ("grid_sy", "<f4")])   # mdvt_source, field for field
+
+
+def pack_views(M, fx, fy, cx, cy) -> np.ndarray:
+    """Cameras as rows of mdvt_view without a Python object per camera: M (..., 3|4, 4) float64 poses, intrinsics
+    broadcastable to M's leading shape -> (..., 16) float32 [M row-major 3x4, fx, fy, cx, cy] (what ViewSpec.to_c writes)."""
+    M = np.asarray(M, dtype=np.float64)[..., :3, :4]
+    lead = M.shape[:-2]
+    out = np.empty(lead + (16,), dtype=np.float32)
+    out[..., :12] = M.reshape(lead + (12,)).astype(np.float32)
+    for k, v in enumerate((fx, fy, cx, cy)):
+        out[..., 12 + k] = np.asarray(v, dtype=np.float64).astype(np.float32)
+    return out
+
+
+def pack_sources(width: int, height: int, fx, fy, cx, cy, max_depth=100, decoder: str = "D1", bit16: bool = True, depth_scale=1.0,
+                 of_by_one: bool = False) -> np.ndarray:
+    """n mdvt_source records at once (make_source for per-frame intrinsics / depth scales): fx, fy, cx, cy, depth_scale are
+    scalars or (n,) arrays -> structured array of SOURCE_DTYPE."""
+    n = int(np.broadcast(fx, fy, cx, cy, depth_scale).size)
+    out = np.zeros(n, dtype=SOURCE_DTYPE)
+    out["width"], out["height"], out["decoder"], out["bit16"] = int(width), int(height), DECODERS[decoder], int(bool(bit16))
+    out["dec_const"] = 1.0 if decoder == "F32" else dec_const(max_depth, decoder)
+    out["depth_scale"] = np.asarray(depth_scale, dtype=np.float64).astype(np.float32)
+    for k, v in (("fx", fx), ("fy", fy), ("cx", cx), ("cy", cy)):
+        out[k] = np.asarray(v, dtype=np.float64).astype(np.float32)
+    out["grid_sx"] = np.float32((width + 1) / width) if of_by_one else 1.0
+    out["grid_sy"] = np.float32((height + 1) / height) if of_by_one else 1.0
+    return out
+
+
 def new_zbuf(n_views: int, out_w: int, out_h: int, device) -> torch.Tensor:
     z = torch.empty((n_views, out_h, out_w), dtype=torch.int64, device=device)
     zbuf_clear(z)
@@ -312,25 +349,45 @@ def render_views(depth_src: torch.Tensor, colour: torch.Tensor, sources: Sequenc
     Views are laid side by side: out_rgb (n, out_h, n_views*out_w, 3) u8, out_mask (n, out_h, n_views*out_w[, 3]) u8,
     out_depth (n, out_h, n_views*out_w) f32.  The z-buffer (n_views, out_h, out_w) must be empty and is left empty."""
     n = depth_src.shape[0]
-    n_views = len(views[0])
-    if len(views) != n or any(len(v) != n_views for v in views):
-        raise ValueError("views must hold the same number of cameras for each of the n frames")
+    packed = isinstance(views, np.ndarray)   # (n, n_views, 16) float32 from pack_views + SOURCE_DTYPE records from pack_sources
+    if packed:
+        if views.dtype != np.float32 or views.ndim != 3 or views.shape[0] != n or views.shape[2] != 16 or not isinstance(sources, np.ndarray) \
+                or sources.dtype != SOURCE_DTYPE:
+            raise ValueError("packed cameras: views (n, n_views, 16) float32 and sources as SOURCE_DTYPE records")
+        n_views = views.shape[1]
+    else:
+        n_views = len(views[0])
+        if len(views) != n or any(len(v) != n_views for v in views):
+            raise ValueError("views must hold the same number of cameras for each of the n frames")
     if len(sources) not in (1, n):
         raise ValueError("sources must hold one entry or one per frame")
     _need(colour, torch.uint8, "colour")
     _need(zbuf, torch.int64, "zbuf")
     if tuple(zbuf.shape) != (n_views, out_h, out_w):
         raise ValueError(f"zbuf shape {tuple(zbuf.shape)} != ({n_views}, {out_h}, {out_w})")
-    for k, src in enumerate(sources):
-        _need_source(depth_src[k], src)
-    if colour.shape[0] != n or colour.shape[1] * colour.shape[2] != sources[0].width * sources[0].height:
+    if packed:
+        src_w, src_h = int(sources["width"][0]), int(sources["height"][0])
+        f32_src = int(sources["decoder"][0]) == _lib.SOURCE_F32
+        _need(depth_src, torch.float32 if f32_src else torch.uint8, "depth_src")
+        if tuple(depth_src.shape[1:3]) != (src_h, src_w) or not depth_src[0].is_contiguous():
+            raise ValueError(f"depth_src frames must be dense ({src_h}, {src_w}) planes")
+    else:
+        for k, src in enumerate(sources):
+            _need_source(depth_src[k], src)
+        src_w, src_h = sources[0].width, sources[0].height
+    if colour.shape[0] != n or colour.shape[1] * colour.shape[2] != src_w * src_h:
         raise ValueError("colour must hold one (H, W, 3) frame per depth frame")
     mask_ch = 3 if flags & FLAG_MASK_RGB else 1
     rgb_l = _plane_layout(_need(out_rgb, torch.uint8, "out_rgb"), n, n_views, out_h, out_w, 3, "out_rgb")
     mask_l = _plane_layout(None if out_mask is None else _need(out_mask, torch.uint8, "out_mask"), n, n_views, out_h, out_w, mask_ch, "out_mask")
     depth_l = _plane_layout(None if out_depth is None else _need(out_depth, torch.float32, "out_depth"), n, n_views, out_h, out_w, 1, "out_depth")
-    src_arr = (_lib.Source * len(sources))(*sources)
-    view_arr = (_lib.View * (n * n_views))(*[v.to_c() for fv in views for v in fv])
+    if packed:
+        views_c, sources_c = np.ascontiguousarray(views), np.ascontiguousarray(sources)
+        src_arr = (_lib.Source * len(sources_c)).from_buffer(sources_c)
+        view_arr = (_lib.View * (n * n_views)).from_buffer(views_c)
+    else:
+        src_arr = (_lib.Source * len(sources))(*sources)
+        view_arr = (_lib.View * (n * n_views))(*[v.to_c() for fv in views for v in fv])
     opt = lambda l: None if l is None else C.byref(l)  # noqa: E731
     _lib.check(_lib.load().mdvt_render_views(_ptr(depth_src), depth_src.stride(0) * depth_src.element_size(), _ptr(colour),
                                              colour.stride(0), n, src_arr, int(len(sources) == n and n > 1), view_arr, n_views,
@@ -672,6 +729,23 @@ def conv_frames(sources: Sequence[_lib.Source], views: Sequence[Sequence[ViewSpe
                 raise ValueError("camera pose is not a y-rotation plus an x-shift")
             f.view[e] = c
     return np.frombuffer(bytes(arr), dtype=np.float32).reshape(n, C.sizeof(_lib.ConvFrame) // 4).copy()
+
+
+def conv_frames_packed(sources: np.ndarray, views: np.ndarray, near: float = NEAR_PLANE) -> np.ndarray:
+    """conv_frames from packed cameras (pack_sources records, pack_views rows (n, 2, 16)): (n, 40) float32, vectorised."""
+    n = views.shape[0]
+    if views.shape[1:] != (2, 16) or len(sources) not in (1, n):
+        raise ValueError("two cameras (left, right) per frame; one source or one per frame")
+    src = sources if len(sources) == n else np.repeat(sources, n)
+    if np.any(src["decoder"] != _lib.DECODE_D1) or np.any(src["bit16"] == 0) or np.any(src["grid_sx"] != 1.0) or np.any(src["grid_sy"] != 1.0):
+        raise ValueError("the fused convergence kernel takes 16-bit D1 wire-format frames on the exact pixel grid")
+    if np.any(views[:, :, [1, 4, 6, 7, 9, 11]] != 0.0) or np.any(views[:, :, 5] != 1.0):
+        raise ValueError("camera pose is not a y-rotation plus an x-shift")
+    out = np.zeros((n, C.sizeof(_lib.ConvFrame) // 4), dtype=np.float32)
+    out[:, 0], out[:, 1], out[:, 2] = src["dec_const"], src["depth_scale"], np.float32(near)
+    out[:, 4], out[:, 5], out[:, 6], out[:, 7] = src["fx"], src["fy"], src["cx"], src["cy"]
+    out[:, 8:] = views.reshape(n, 32)
+    return out
 
 
 def stereo_conv_rows(depth_rgb: torch.Tensor, colour: torch.Tensor, frames: torch.Tensor, bg_rgb=(0, 0, 0), fill_rgb=(0, 0, 0),

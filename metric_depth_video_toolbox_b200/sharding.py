@@ -114,11 +114,16 @@ def unpack_params(vec: np.ndarray) -> Tuple[StereoParams, int]:
     return StereoParams(**kw), n
 
 
-def broadcast_params(p: Optional[StereoParams], n_frames: int = 0, src: int = 0, device: Optional[torch.device] = None):
+def broadcast_params(p, n_frames: int = 0, src: int = 0, device: Optional[torch.device] = None):
     """Rank `src` passes the clip's parameters; every rank returns (StereoParams, n_frames).  Two broadcasts:
-    the vector length, then the vector (a few KB; at most ~140 B per frame with a pose file)."""
+    the vector length, then the vector (a few KB; at most ~140 B per frame with a pose file).
+    `p` may also be the EXCEPTION rank `src` caught while building the parameters (a missing file, a bad list): the
+    length travels as -1, every other rank raises too instead of waiting in the second broadcast until the NCCL
+    timeout, and rank `src` re-raises the original."""
     rank, world_size = world()
     if world_size == 1:
+        if isinstance(p, BaseException):
+            raise p
         if p is None:
             raise ValueError("the source rank must supply the parameters")
         return p, n_frames
@@ -126,12 +131,19 @@ def broadcast_params(p: Optional[StereoParams], n_frames: int = 0, src: int = 0,
         device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
     if rank == src:
         if p is None:
-            raise ValueError("the source rank must supply the parameters")
-        vec = torch.from_numpy(pack_params(p, n_frames)).to(device)
-        size = torch.tensor([vec.numel()], dtype=torch.int64, device=device)
+            p = ValueError("the source rank must supply the parameters")
+        if isinstance(p, BaseException):
+            size = torch.tensor([-1], dtype=torch.int64, device=device)
+        else:
+            vec = torch.from_numpy(pack_params(p, n_frames)).to(device)
+            size = torch.tensor([vec.numel()], dtype=torch.int64, device=device)
     else:
         size = torch.zeros(1, dtype=torch.int64, device=device)
     dist.broadcast(size, src=src)
+    if int(size.item()) < 0:
+        if rank == src:
+            raise p
+        raise RuntimeError(f"rank {src} could not build the clip parameters (its exception carries the reason)")
     if rank != src:
         vec = torch.empty(int(size.item()), dtype=torch.float64, device=device)
     dist.broadcast(vec, src=src)

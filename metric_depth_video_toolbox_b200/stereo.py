@@ -106,6 +106,51 @@ class StereoRerenderer:
         T = np.eye(4) if p.transformations is None else np.asarray(p.transformations[frame], dtype=np.float64)
         return [ops.ViewSpec(geo.stereo_eye_pose(eye, ipd, theta) @ T, K[0, 0], K[1, 1], K[0, 2], K[1, 2]) for eye in ("left", "right")]
 
+    def packed_cameras(self, start: int, count: int):
+        """The cameras of frames start .. start+count-1 for the generic path as packed arrays (ops.pack_sources /
+        ops.pack_views): the same numbers as `views_of` / `ops.make_source` per frame, built with a handful of vectorised
+        NumPy operations instead of ~40 us of Python per frame (which was 3/4 of the generic path's time per frame)."""
+        import math
+
+        p = self.p
+        w, h = p.width, p.height
+        frames = range(start, start + count)
+        if p.xfovs is not None:
+            Ks = [geo.compute_camera_matrix(p.xfov_of(f), None, w, h) for f in frames]
+            scales = np.array([geo.master_fov_depth_scale(p.master_xfov, p.xfov_of(f)) for f in frames])
+            fx, fy = np.array([K[0, 0] for K in Ks]), np.array([K[1, 1] for K in Ks])
+            cx, cy = Ks[0][0, 2], Ks[0][1, 2]
+        else:
+            K = geo.compute_camera_matrix(p.xfov_of(start), p.yfov, w, h)
+            fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+            scales = np.full(count, geo.master_fov_depth_scale(p.master_xfov, p.xfov_of(start)))
+        ipd = p.pupillary_distance / 1000
+        theta = np.zeros(count)
+        if p.convergence_depths is not None:
+            for k, f in enumerate(frames):
+                conv = float(p.convergence_depths[f])
+                if conv != 0:  # "Convergence distance is zero, skipping convergence" (:711-713)
+                    theta[k] = geo.convergence_angle(conv * float(scales[k]), ipd)
+        T = None if p.transformations is None else np.asarray([p.transformations[f] for f in frames], dtype=np.float64)
+        M = np.zeros((count, 2, 3, 4))
+        for e, sign in enumerate((1.0, -1.0)):   # left: Ry(-theta), +ipd/2; right: Ry(+theta), -ipd/2 (geo.stereo_eye_pose)
+            ang = -sign * theta
+            c = np.array([math.cos(a) if a else 1.0 for a in ang])[:, None]
+            s = np.array([math.sin(a) if a else 0.0 for a in ang])[:, None]
+            tx = sign * ipd / 2
+            if T is None:
+                M[:, e, 0, 0], M[:, e, 0, 2], M[:, e, 0, 3] = c[:, 0], s[:, 0], tx
+                M[:, e, 1, 1] = 1.0
+                M[:, e, 2, 0], M[:, e, 2, 2] = 0.0 - s[:, 0], c[:, 0]   # 0 - s: +0 where there is no rotation, like np.eye
+            else:   # E @ T, summed in matmul's order; the terms that multiply an exact 0 are left out
+                M[:, e, 0] = c * T[:, 0] + s * T[:, 2] + tx * T[:, 3]
+                M[:, e, 1] = T[:, 1]
+                M[:, e, 2] = -s * T[:, 0] + c * T[:, 2]
+        bc = (lambda v: np.asarray(v)[:, None]) if p.xfovs is not None else (lambda v: v)
+        views = ops.pack_views(M, bc(fx), bc(fy), cx, cy)
+        sources = ops.pack_sources(w, h, fx, fy, cx, cy, p.max_depth, "D1", True, scales if p.xfovs is not None else scales[:1])
+        return sources, views
+
     # ---- device-resident ------------------------------------------------------------------------------
     def render_device(self, depth_rgb: torch.Tensor, colour: torch.Tensor, start_frame: int = 0,
                       out_sbs: Optional[torch.Tensor] = None, out_mask: Optional[torch.Tensor] = None,
@@ -125,24 +170,16 @@ class StereoRerenderer:
             out_sbs = torch.empty((n, h, 2 * w, 3), dtype=torch.uint8, device=depth_rgb.device)
         if out_mask is None and p.infill_mask:
             out_mask = torch.empty((n, h, 2 * w) + ((3,) if mask_rgb else ()), dtype=torch.uint8, device=depth_rgb.device)
-        def cameras():
-            sources = []
-            for f in (range(start_frame, start_frame + n) if p.xfovs is not None else [start_frame]):
-                xf = p.xfov_of(f)
-                K = geo.compute_camera_matrix(xf, None if p.xfovs is not None else p.yfov, w, h)
-                sources.append(ops.make_source(w, h, K, p.max_depth, "D1", True, geo.master_fov_depth_scale(p.master_xfov, xf), False))
-            return sources, [self.views_of(f) for f in range(start_frame, start_frame + n)]
-
         if p.conv_local():  # convergence only: fused target-row kernel, no global z-buffer
             key = ("conv", start_frame, n)
             if key not in self._consts_cache:
                 if len(self._consts_cache) > 64:
                     self._consts_cache.clear()
-                self._consts_cache[key] = torch.from_numpy(ops.conv_frames(*cameras(), p.near)).to(self.device)
+                self._consts_cache[key] = torch.from_numpy(ops.conv_frames_packed(*self.packed_cameras(start_frame, n), p.near)).to(self.device)
             return ops.stereo_conv_rows(depth_rgb, colour, self._consts_cache[key], p.bg_rgb, (0, 0, 0), flags, out_sbs, out_mask,
                                         want_mask=False, out_depth=out_depth)
-        sources, views = cameras()
-        # generic path: per frame K1+K2 into a persistent 2-view z-buffer, K3 per eye straight into the SBS halves
+        sources, views = self.packed_cameras(start_frame, n)
+        # generic path: per frame K1+K2 into a persistent 2-view z-buffer, K3 for both eyes straight into the SBS halves
         zkey = torch.cuda.current_stream(depth_rgb.device).cuda_stream
         zbuf = self._zbufs.get(zkey)
         if zbuf is None or tuple(zbuf.shape) != (2, h, w) or zbuf.device != depth_rgb.device:
@@ -154,7 +191,8 @@ class StereoRerenderer:
     def render_host(self, depth_rgb, colour, out_sbs=None, out_mask=None, start_frame: int = 0, chunk_frames: int = 8):
         """depth_rgb / colour: (n, H, W, 3) u8 host arrays (NumPy or CPU tensors; pinned memory makes the
         copies asynchronous).  Frames stream through `chunk_frames`-sized device staging buffers on two
-        CUDA streams so H2D, the kernels and D2H overlap.  Returns host tensors (sbs, mask)."""
+        CUDA streams so H2D, the kernels and D2H overlap.  Returns host tensors (sbs, mask); it waits for the last copy,
+        so the returned buffers are complete."""
         p = self.p
         d_host = torch.as_tensor(depth_rgb)
         c_host = torch.as_tensor(colour)
@@ -183,6 +221,7 @@ class StereoRerenderer:
                     out_mask_t[f0:f0 + cnt].copy_(s["mask"][:cnt], non_blocking=True)
         for s in slots:
             caller.wait_stream(s["stream"])
+            s["stream"].synchronize()   # "returns host tensors": the asynchronous D2H copies have landed when this returns
         return out_sbs, out_mask
 
     def _host_pipeline_slots(self, n_slots, chunk, h, w):

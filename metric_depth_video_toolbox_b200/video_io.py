@@ -195,6 +195,8 @@ class ChunkReader:
         for _ in range(depth + 1 + self.decoders):   # pinned: 300 MB per 12-frame 4K chunk, keep the ring short
             self._free.put(self._alloc())
         self._tickets: "queue.Queue" = queue.Queue(maxsize=max(1, depth) + self.decoders)
+        self._stop, self._tickets_done, self._finished = threading.Event(), threading.Event(), threading.Event()
+        self._q_end: list = []   # the exception the collector ended with, if any
         self._threads = [threading.Thread(target=self._dispatch, daemon=True), threading.Thread(target=self._collect, daemon=True)]
         for t in self._threads:
             t.start()
@@ -206,26 +208,52 @@ class ChunkReader:
             bufs.append(None if p is None else torch.empty(shape, dtype=torch.uint8, pin_memory=self.pin))
         return bufs
 
+    # blocking queue operations poll, so that close() (early `break`, an exception in the consumer, interpreter exit) can
+    # always get the background threads out of them
+    def _get(self, q: "queue.Queue"):
+        while not self._stop.is_set():
+            try:
+                return q.get(timeout=0.05)
+            except queue.Empty:
+                continue
+        return None
+
+    def _put(self, q: "queue.Queue", item) -> bool:
+        while not self._stop.is_set():
+            try:
+                q.put(item, timeout=0.05)
+                return True
+            except queue.Full:
+                continue
+        return False
+
     def _dispatch(self):
         c = 0
         pos = self.start
         try:
-            while pos < self.stop:
-                bufs = self._free.get()
+            while pos < self.stop and not self._stop.is_set():
+                bufs = self._get(self._free)
+                if bufs is None:
+                    break
                 count = min(self.chunk, self.stop - pos)
                 tickets = [None if w is None else w[c % self.decoders].submit(b, pos, count) for w, b in zip(self._workers, bufs)]
-                self._tickets.put((count, bufs, tickets))
+                if not self._put(self._tickets, (count, bufs, tickets)):
+                    break
                 pos += count
                 c += 1
         finally:
-            self._tickets.put(None)
+            self._tickets_done.set()
 
     def _collect(self):
+        end = None
         try:
             while True:
-                item = self._tickets.get()
-                if item is None:
-                    break
+                try:
+                    item = self._tickets.get(timeout=0.05)
+                except queue.Empty:
+                    if self._stop.is_set() or self._tickets_done.is_set():
+                        break
+                    continue
                 count, bufs, tickets = item
                 n = count
                 for t in tickets:
@@ -235,28 +263,65 @@ class ChunkReader:
                     if t["err"] is not None:
                         raise t["err"]
                     n = min(n, t["n"])
-                if n:
-                    self._q.put((n, bufs))
+                if n and not self._put(self._q, (n, bufs)):
+                    break
                 if n < count:   # a video ended early: stop here for all of them
                     break
         except BaseException as exc:  # surfaced on the consumer side
-            self._q.put(exc)
+            end = exc
         finally:
-            self._q.put(None)
-            for ws in self._workers:
-                for w in ws or ():
-                    w.tasks.put(None)
+            # the decoders are stopped and JOINED before the end marker is published: the consumer (and with it the process)
+            # may finish right after it, and a worker still inside cv2.VideoCapture.release() then aborts the interpreter
+            self._stop_workers()
+            if end is not None:
+                self._q_end.append(end)
+            self._finished.set()
+
+    def _stop_workers(self):
+        for ws in self._workers:
+            for w in ws or ():
+                w.tasks.put(None)
+        for ws in self._workers:
+            for w in ws or ():
+                w.join()
+
+    def close(self):
+        """Stops and joins every background thread.  Called when the iteration ends for whatever reason (exhausted, `break`,
+        exception); safe to call twice."""
+        self._stop.set()
+        for t in self._threads:
+            if t is not threading.current_thread():
+                t.join()
+        self._stop_workers()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def __iter__(self):
-        while True:
-            item = self._q.get()
-            if item is None:
-                return
-            if isinstance(item, BaseException):
-                raise item
-            n, bufs = item
-            yield n, [None if b is None else b[:n] for b in bufs]
-            self._free.put(bufs)  # the consumer is done with the previous chunk when it asks for the next
+        try:
+            while True:
+                try:
+                    item = self._q.get(timeout=0.05)
+                except queue.Empty:
+                    if self._finished.is_set() and self._q.empty():
+                        if self._q_end:
+                            raise self._q_end[0]
+                        return
+                    continue
+                n, bufs = item
+                yield n, [None if b is None else b[:n] for b in bufs]
+                self._free.put(bufs)  # the consumer is done with the previous chunk when it asks for the next
+        finally:
+            self.close()
 
 
 class ChunkWriter:

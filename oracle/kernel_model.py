@@ -115,10 +115,28 @@ def view_uvz_f32(depth_rgb, src, M, K_out, bit16=True):
     return u.reshape(-1), v.reshape(-1), n[2].reshape(-1)
 
 
-def splat_ids_f32(u, v, z, out_w, out_h, near=orc.NEAR_PLANE):
+def splat_ids_f32(u, v, z, out_w, out_h, near=orc.NEAR_PLANE, tie=None):
     """The kernel's cull / round / bounds / atomicMin rule on float32 inputs == the oracle's rule
-    (rintf is round-half-even; the float32 comparisons promote exactly)."""
-    return orc.splat_ids(u.astype(np.float64), v.astype(np.float64), z.astype(np.float64), out_w, out_h, float(f32(near)))
+    (rintf is round-half-even; the float32 comparisons promote exactly).  tie: the packed colours for the
+    colour-keyed frame loops (key = Zv bits << 32 | 0x00BBGGRR), None for the index-keyed primitives."""
+    return orc.splat_ids(u.astype(np.float64), v.astype(np.float64), z.astype(np.float64), out_w, out_h, float(f32(near)), tie)
+
+
+def render_views_f32(depth_rgb, colour, src, views, out_w, out_h, bg_rgb=(0, 0, 0), fill_rgb=(0, 0, 0), bg_collide=False, near=orc.NEAR_PLANE):
+    """mdvt_render_views / mdvt_stereo_conv_rows / mdvt_novel_view_frames for one frame: every output byte and the float32
+    depth planes.  views: [(M, (fx, fy, cx, cy)), ...].  Returns (image (out_h, n*out_w, 3) u8, mask (out_h, n*out_w) u8,
+    depth (out_h, n*out_w) f32, [ids per view])."""
+    imgs, masks, depths, idl = [], [], [], []
+    tie = orc.pack_colour(colour)
+    for M, K_out in views:
+        u, v, z = view_uvz_f32(depth_rgb, src, M, K_out)
+        ids = splat_ids_f32(u, v, z, out_w, out_h, near, tie)
+        img, mask = orc.resolve(ids, colour, bg_rgb, fill_rgb, bg_collide)
+        imgs.append(img)
+        masks.append(mask)
+        depths.append(orc.zbuffer_depth(ids, z))
+        idl.append(ids)
+    return np.concatenate(imgs, axis=1), np.concatenate(masks, axis=1), np.concatenate(depths, axis=1), idl
 
 
 def stereo_rows_f32(depth_rgb, colour, consts, bg_rgb=(0, 0, 0), fill_rgb=(0, 0, 0), bg_collide=False):

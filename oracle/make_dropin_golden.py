@@ -74,6 +74,16 @@ def main():
     out["iun_img"], out["iun_hole"], out["iun_normals"] = img, hole, normal_map
     out["iun_out"] = sr.infill_using_normals(img, hole, normal_map)
     out["iun_out_12"] = sr.infill_using_normals(img, hole, normal_map, max_steps=12)
+    # ---- encode_depth_as_uint32 on a float64 depth array (clip and scale stay float64 in the reference) ----------
+    d64 = rng.uniform(0, 100, size=(32, 48))
+    d64[0, :6] = [0.0, 100.0, 100.0000001, -1e-12, 99.99999999, 50.0]
+    d64[1, :4] = [100.0 * k / 65535.0 for k in (1, 2, 65534, 65535)]
+    d64[2, :8] = np.nextafter(np.float32(37.5), np.float32(40)).astype(np.float64) - 1e-9   # values float32 would round across a code
+    out["enc64_depth"] = d64
+    for md in (100, 20):
+        codes = dfh.encode_depth_as_uint32(d64, md)
+        out[f"enc64_codes_md{md}"] = codes
+        out[f"enc64_bgr16_md{md}"] = dfh.encode_data_as_BGR(codes, 48, 32, bit16=True)
     np.savez_compressed(os.path.join(OUT, "dropin_helpers.npz"), **out)
     print("wrote", os.path.join(OUT, "dropin_helpers.npz"), {k: np.asarray(v).shape for k, v in out.items()})
 

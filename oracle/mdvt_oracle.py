@@ -224,13 +224,20 @@ def look_at_extrinsic(cam_pos, target, up=(0.0, 1.0, 0.0)) -> np.ndarray:
 # --------------------------------------------------------------------------------------
 # visibility (z-buffered point splat) + hole mask
 # --------------------------------------------------------------------------------------
-def splat_ids(u, v, z, out_w: int, out_h: int, near: float = NEAR_PLANE) -> np.ndarray:
+def pack_colour(colour) -> np.ndarray:
+    """(N, 3) / (H, W, 3) u8 RGB -> flat uint32 0x00BBGGRR (the low key word of the colour-keyed z-buffers)."""
+    c = np.asarray(colour, dtype=np.uint8).reshape(-1, 3).astype(np.uint32)
+    return c[:, 0] | (c[:, 1] << 8) | (c[:, 2] << 16)
+
+
+def splat_ids(u, v, z, out_w: int, out_h: int, near: float = NEAR_PLANE, tie=None) -> np.ndarray:
     """Forward point splat -> id buffer (out_h, out_w) int64, -1 = hole.
 
     Rule (stereo_rerender.py:746-755,814): target = round-half-even(u, v); keep 0<=x<W,
     0<=y<H; nearest z wins.  The reference's tie order is an unstable argsort (undefined);
-    here ties go to the lowest source index.  Points with z <= near (GL near plane,
-    depth_map_tools.py:1520) or non-finite coordinates are culled before rounding.
+    here ties go to the lowest source index, or -- `tie` = one integer per source, the packed
+    colour in the product's frame loops -- to the smallest tie value first.  Points with z <= near
+    (GL near plane, depth_map_tools.py:1520) or non-finite coordinates are culled before rounding.
     """
     u = np.asarray(u, dtype=np.float64)
     v = np.asarray(v, dtype=np.float64)
@@ -241,7 +248,10 @@ def splat_ids(u, v, z, out_w: int, out_h: int, near: float = NEAR_PLANE) -> np.n
         ok = (z > near) & (ur >= 0) & (ur <= out_w - 1) & (vr >= 0) & (vr <= out_h - 1)
     src = np.flatnonzero(ok)
     tgt = vr[src].astype(np.int64) * out_w + ur[src].astype(np.int64)
-    order = np.lexsort((src, z[src], tgt))  # primary tgt, then z, then source id
+    if tie is None:
+        order = np.lexsort((src, z[src], tgt))  # primary tgt, then z, then source id
+    else:
+        order = np.lexsort((src, np.asarray(tie).reshape(-1)[src], z[src], tgt))  # tgt, z, tie value, source id
     tgt_s = tgt[order]
     first = np.ones(len(order), dtype=bool)
     first[1:] = tgt_s[1:] != tgt_s[:-1]
@@ -299,21 +309,23 @@ def view_uvz(depth_rgb, max_depth, K, M, depth_scale=None, K_out=None, bit16=Tru
 
 
 def render_view(depth_rgb, colour, max_depth, K, M, depth_scale=None, K_out=None, out_size=None,
-                bg_rgb=(0, 0, 0), hole_fill=(0, 0, 0), **kw):
-    """One novel view: returns (image, mask, ids)."""
+                bg_rgb=(0, 0, 0), hole_fill=(0, 0, 0), tie_colour=False, **kw):
+    """One novel view: returns (image, mask, ids).  tie_colour: equal z -> smallest packed colour (frame loops)."""
     h, w = depth_rgb.shape[:2]
     ow, oh = (w, h) if out_size is None else out_size
     u, v, z = view_uvz(depth_rgb, max_depth, K, M, depth_scale, K_out, **kw)
-    ids = splat_ids(u, v, z, ow, oh)
+    ids = splat_ids(u, v, z, ow, oh, tie=pack_colour(colour) if tie_colour else None)
     img, mask = resolve(ids, colour, bg_rgb, hole_fill)
     return img, mask, ids
 
 
 def stereo_frame(depth_rgb, colour, xfov, yfov=None, max_depth=100, pupillary_distance_mm=63,
-                 master_xfov=45.0, convergence_depth=None, transform=None, infill_mask=True):
+                 master_xfov=45.0, convergence_depth=None, transform=None, infill_mask=True, tie_colour=False):
     """One iteration of the stereo_rerender.py frame loop (:489-941) in point-splat form.
 
     Returns (sbs image (H,2W,3) u8, sbs hole mask (H,2W) u8, (ids_left, ids_right)).
+    tie_colour: candidates with equal z' are ordered by packed colour instead of source index (the rule of the
+    product's colour-keyed frame loops; the reference leaves ties undefined).
     """
     h, w = depth_rgb.shape[:2]
     K = camera_matrix(xfov, yfov, w, h)
@@ -327,7 +339,7 @@ def stereo_frame(depth_rgb, colour, xfov, yfov=None, max_depth=100, pupillary_di
     imgs, masks, idl = [], [], []
     for eye in ("left", "right"):
         M = eye_pose(eye, ipd, theta) @ T
-        img, mask, ids = render_view(depth_rgb, colour, max_depth, K, M, depth_scale=scale, bg_rgb=bg)
+        img, mask, ids = render_view(depth_rgb, colour, max_depth, K, M, depth_scale=scale, bg_rgb=bg, tie_colour=tie_colour)
         imgs.append(img)
         masks.append(mask)
         idl.append(ids)
@@ -335,7 +347,7 @@ def stereo_frame(depth_rgb, colour, xfov, yfov=None, max_depth=100, pupillary_di
 
 
 def novel_view_frame(depth_rgb, colour, xfov, yfov=None, max_depth=100, cam_pos=(2.0, 2.0, -4.0),
-                     target=None, transform=None, center_of_by_one=False):
+                     target=None, transform=None, center_of_by_one=False, tie_colour=False):
     """One iteration of `3d_view_depthfile.py --render` (:133-255) in point-splat form:
     target defaults to the vertex mean (:231; the mesh's vertices sit on the stretched grid
     unless --render_as_pointcloud, :178-182 -> `center_of_by_one`), white background (:254).
@@ -360,7 +372,7 @@ def novel_view_frame(depth_rgb, colour, xfov, yfov=None, max_depth=100, cam_pos=
     pts = apply_pose(pts, ext)
     K_r = np.array([[K[0][0], 0, K[0][2]], [0, K[0][0], K[1][2]], [0, 0, 1.0]])
     u, v, z = project(pts, K_r)
-    ids = splat_ids(u, v, z, w, h)
+    ids = splat_ids(u, v, z, w, h, tie=pack_colour(colour) if tie_colour else None)
     img, mask = resolve(ids, colour, bg_rgb=(255, 255, 255), hole_fill=(255, 255, 255))
     return img, mask, ids, ext
 

@@ -139,3 +139,19 @@ def test_create_mesh_from_point_cloud_matches_reference_mesh_builder(golden_dir,
     assert np.array_equal(np.setdiff1d(np.arange(w * h), used), g[tag + "_unused"])
     mesh3, used3 = dmt.create_mesh_from_point_cloud(points, hh, ww)
     assert np.array_equal(used3, np.arange(w * h))
+
+
+@pytest.mark.gpu
+def test_encode_depth_float64_input_matches_reference(golden_dir):
+    """a float64 depth array must be clipped and scaled in float64 (no early float32 rounding)."""
+    import depth_frames_helper as dfh
+
+    g = np.load(os.path.join(golden_dir, "dropin_helpers.npz"))
+    d64 = g["enc64_depth"]
+    differs = 0
+    for md in (100, 20):
+        codes = dfh.encode_depth_as_uint32(d64, md)
+        assert codes.dtype == np.uint32 and np.array_equal(codes, g[f"enc64_codes_md{md}"])
+        assert np.array_equal(dfh.encode_data_as_BGR(codes, 48, 32, bit16=True), g[f"enc64_bgr16_md{md}"])
+        differs += int((dfh.encode_depth_as_uint32(d64.astype(np.float32), md) != codes).sum())
+    assert differs > 0   # the float32 route really gives other codes: the test distinguishes the two

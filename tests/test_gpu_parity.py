@@ -404,6 +404,24 @@ def test_stereo_conv_rows_bit_identical_to_generic_path(size, conv, yfov, mask_r
     assert torch.equal(sa, sb) and torch.equal(ma, mb)
     assert torch.equal(da.view(torch.int32), db.view(torch.int32))
     assert bool((ma != 0).any()) and bool((da > 0).any())
-    # and, through the generic path's own oracle check, against the float64 reference restatement
-    want, _, _ = orc.stereo_frame(depth[2], colour[2], 60.0, yfov, convergence_depth=convs[2], infill_mask=True)
-    assert (sa[2].cpu().numpy() != want).any(axis=-1).mean() < 3e-3
+    # both against the float32 model of the frame loops, every byte and every depth bit (frames 0 and 2: with / without rotation)
+    scale = orc.master_fov_depth_scale(45.0, 60.0)
+    K = orc.camera_matrix(60.0, yfov, w, h)
+    msrc = km.source_constants(w, h, K, 100, "D1", scale)
+    for f in (0, 1, 2):
+        theta = None if convs[f] == 0 else orc.convergence_angle(convs[f] * scale, 0.063)
+        views = [(orc.eye_pose(e, 0.063, theta), (K[0, 0], K[1, 1], K[0, 2], K[1, 2])) for e in ("left", "right")]
+        img, mask, zplane, ids32 = km.render_views_f32(depth[f], colour[f], msrc, views, w, h, (0, 255, 0), (0, 0, 0), True)
+        assert np.array_equal(sa[f].cpu().numpy(), img)
+        got_mask = ma[f].cpu().numpy()
+        assert np.array_equal(got_mask if not mask_rgb else (got_mask != 0).any(axis=-1).astype(np.uint8) * 255, mask)
+        assert np.array_equal(bits(da[f].cpu().numpy()), bits(zplane))
+    # and against the float64 reference restatement: winners differ only where a rounding boundary / z tie explains it
+    _, _, ids64 = orc.stereo_frame(depth[2], colour[2], 60.0, yfov, convergence_depth=convs[2], infill_mask=True, tie_colour=True)
+    n_total = 0
+    for k, eye in enumerate(("left", "right")):
+        u64, v64, z64 = orc.view_uvz(depth[2], 100, K, views[k][0], depth_scale=scale)
+        n_diff, unexplained = boundary_explained(u64, v64, z64, ids32[k], ids64[k], w, h)
+        assert unexplained == 0
+        n_total += n_diff
+    assert n_total <= max(4, int(3e-3 * w * h))
