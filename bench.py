@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--cpu-frames", type=int, default=24, help="frames of the bounded CPU-baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-paths", action="store_true", help="skip the `paths` sections (convergence / posed stereo at 1080p, 4K novel view)")
     return ap.parse_args()
 
 
@@ -157,7 +158,9 @@ def workload_config(world: int, n_frames: int, distinct: int):
     """The `config` object of both arms (the reference arm runs bounded samples of the same workload)."""
     return {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "frames_per_gpu_per_step": n_frames,
             "distinct_frames_per_gpu": distinct, "xfov": XFOV, "max_depth": MAX_DEPTH, "pupillary_distance_mm": IPD_MM,
-            "master_xfov": MASTER_XFOV, "sharding": f"frames, {world} rank(s), no data-path collective"}
+            "master_xfov": MASTER_XFOV, "sharding": f"frames, {world} rank(s), no data-path collective",
+            "l2": f"inputs {2 * n_frames * HEIGHT * WIDTH * 3 / 1e9:.2f} GB + outputs {n_frames * HEIGHT * 2 * WIDTH * 4 / 1e9:.2f} GB per GPU per step "
+                  f">> 126 MB L2 (no flush needed)"}
 
 
 def run_reference(args):
@@ -237,6 +240,102 @@ def ncu_traffic_per_frame():
     return None
 
 
+def measure_paths(dev, peak: float, frames_1080: int = 32, frames_4k: int = 16, reps: int = 5):
+    """The other kernels of the path at BASELINE.json's sizes, outside `value` (N = 1): convergence stereo (what
+    movie_2_3D runs: --convergence_file), stereo with a pose file (--transformation_file), and configs[2] (3840x2160 novel
+    view, camera (2, 2, -4) aimed at the frame's vertex centroid).  Each: CUDA-event time per frame on device-resident
+    frames, the roofline fraction from SURVEY.md 8(d)'s algorithmic bytes (14 / 14 / 10 B/px), and the same frames through
+    the host API with pinned host buffers (H2D + kernels + D2H inside the timed region)."""
+    import math
+
+    import numpy as np
+    import torch
+
+    from metric_depth_video_toolbox_b200.novel_view import NovelViewParams, NovelViewRenderer
+    from metric_depth_video_toolbox_b200.stereo import StereoParams, StereoRerenderer
+    from metric_depth_video_toolbox_b200.synth import SyntheticClip
+
+    def clip(w, h, n, distinct=4):
+        d, c = SyntheticClip(w, h, n).frames(0, distinct)
+        reps_ = (n + distinct - 1) // distinct
+        hd = torch.from_numpy(np.concatenate([d] * reps_)[:n]).pin_memory()
+        hc = torch.from_numpy(np.concatenate([c] * reps_)[:n]).pin_memory()
+        return hd, hc
+
+    def timed(fn, n_frames):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (reps * n_frames)   # ms per frame
+
+    def wall(fn, n_frames, steps=2):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) * 1e3 / (steps * n_frames)
+
+    def entry(ms_frame, e2e_ms_frame, w, h, bpp, kernel, h2d, d2h, note):
+        achieved = bpp * w * h / (ms_frame / 1e3) / 1e9
+        return {"ms_per_frame": ms_frame, "frames_per_s": 1e3 / ms_frame, "kernel": kernel, "workload": note,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "algorithmic_bytes_per_frame": bpp * w * h, "traffic": None},
+                "e2e": {"value": 1e3 / e2e_ms_frame, "unit": "frames/s", "ms_per_frame": e2e_ms_frame, "h2d_bytes_per_frame": h2d,
+                        "d2h_bytes_per_frame": d2h}}
+
+    out = {}
+    w, h, n = WIDTH, HEIGHT, frames_1080
+    hd, hc = clip(w, h, n)
+    d, c = hd.to(dev), hc.to(dev)
+    sbs = torch.empty((n, h, 2 * w, 3), dtype=torch.uint8, device=dev)
+    mask = torch.empty((n, h, 2 * w), dtype=torch.uint8, device=dev)
+    h_sbs = torch.empty((n, h, 2 * w, 3), dtype=torch.uint8, pin_memory=True)
+    h_mask = torch.empty((n, h, 2 * w), dtype=torch.uint8, pin_memory=True)
+    poses = []
+    for f in range(n):   # a small hand-held camera path: a few milliradians of rotation, centimetres of translation
+        a, b = 0.01 * math.sin(0.21 * f), 0.004 * math.cos(0.13 * f)
+        ry = np.array([[math.cos(a), 0, math.sin(a)], [0, 1, 0], [-math.sin(a), 0, math.cos(a)]])
+        rx = np.array([[1, 0, 0], [0, math.cos(b), -math.sin(b)], [0, math.sin(b), math.cos(b)]])
+        T = np.eye(4)
+        T[:3, :3] = ry @ rx
+        T[:3, 3] = (0.05 * math.sin(0.17 * f), -0.02 * math.cos(0.11 * f), 0.1 * math.sin(0.07 * f))
+        poses.append(T)
+    common = dict(xfov=XFOV, max_depth=MAX_DEPTH, pupillary_distance=IPD_MM, master_xfov=MASTER_XFOV, infill_mask=True)
+    for key, extra, kernel, note in (
+            ("convergence_1080p", dict(convergence_depths=[5.0 + 0.02 * f for f in range(n)]), "mdvt::stereo_conv_rows_kernel",
+             f"{w}x{h} x {n} frames, stereo pair + hole masks with a per-frame convergence rotation (stereo_rerender --convergence_file)"),
+            ("posed_1080p", dict(transformations=poses), "mdvt::project_splat_kernel + mdvt::resolve_ckey_kernel",
+             f"{w}x{h} x {n} frames, stereo pair + hole masks with a per-frame 4x4 camera pose (stereo_rerender --transformation_file)")):
+        rr = StereoRerenderer(StereoParams(w, h, **common, **extra), dev)
+        ms = timed(lambda: rr.render_device(d, c, 0, sbs, mask), n)
+        e2e_ms = wall(lambda: rr.render_host(hd, hc, h_sbs, h_mask), n)
+        out[key] = entry(ms, e2e_ms, w, h, 14, kernel, 2 * w * h * 3, 2 * w * h * 4, note)
+        out[key]["holes"] = float((mask == 255).float().mean().item())
+    del d, c, sbs, mask, h_sbs, h_mask, hd, hc
+    w, h, n = 3840, 2160, frames_4k
+    hd, hc = clip(w, h, n)
+    d, c = hd.to(dev), hc.to(dev)
+    nv = NovelViewRenderer(NovelViewParams(w, h, XFOV, None, MAX_DEPTH), dev)
+    rgb = torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
+    msk = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
+    h_rgb = torch.empty((n, h, w, 3), dtype=torch.uint8, pin_memory=True)
+    ms = timed(lambda: nv.render_device(d, c, 0, rgb, msk), n)
+    e2e_ms = wall(lambda: nv.render_host(hd, hc, h_rgb), n)
+    out["novel_view_4k"] = entry(ms, e2e_ms, w, h, 10, "mdvt::centroid_partial_kernel + mdvt::project_splat_kernel + mdvt::resolve_ckey_kernel",
+                                 2 * w * h * 3, w * h * 3,
+                                 f"configs[2]: {w}x{h} x {n} frames, 3d_view_depthfile --render, camera (2, 2, -4) aimed at the vertex centroid, white background")
+    out["novel_view_4k"]["holes"] = float((msk == 255).float().mean().item())
+    return out
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -253,6 +352,9 @@ def run_ours(args):
         raise SystemExit("bench.py --impl ours needs a CUDA device: there is no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # host threads and the pinned buffers they first touch go next to this rank's GPU where the box exposes a topology
+    from metric_depth_video_toolbox_b200 import sharding
+    host_locality = sharding.bind_host_to_gpu(local_rank, world)
     saved_stdout = None
     if world > 1:
         # stdout carries exactly ONE JSON line (the contract): NCCL prints its version banner to fd 1 when the box sets
@@ -326,32 +428,45 @@ def run_ours(args):
     if not args.no_e2e:
         host_sbs = torch.empty((distinct, HEIGHT, 2 * WIDTH, 3), dtype=torch.uint8, pin_memory=True)
         host_mask = torch.empty((distinct, HEIGHT, 2 * WIDTH), dtype=torch.uint8, pin_memory=True)
+        host_bits = torch.empty((distinct, HEIGHT, 2 * WIDTH // 8), dtype=torch.uint8, pin_memory=True)
         segments = [(f0, min(distinct, n_frames - f0)) for f0 in range(0, n_frames, distinct)]
 
-        def e2e_step():
-            for f0, cnt in segments:
-                rr.render_host(host_d[:cnt], host_c[:cnt], host_sbs[:cnt], host_mask[:cnt], start_frame=f0)
+        def e2e_run(mask_format):
+            out_mask_host = host_bits if mask_format == "bits" else host_mask
 
-        e2e_step()  # warm-up: allocates the device staging buffers
-        sync_all()
-        t0 = time.perf_counter()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.e2e_steps):
-            e2e_step()
-        e1.record()
-        sync_all()
-        wall_ms = (time.perf_counter() - t0) * 1e3
-        t = torch.tensor([max(e0.elapsed_time(e1), wall_ms)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_value = world * n_frames * args.e2e_steps / (float(t.item()) / 1e3)
-        checksum = int(host_mask[::17].sum().item())  # the step's result is read on the host
+            def e2e_step():
+                for f0, cnt in segments:
+                    rr.render_host(host_d[:cnt], host_c[:cnt], host_sbs[:cnt], out_mask_host[:cnt], start_frame=f0, mask_format=mask_format)
+
+            e2e_step()  # warm-up: allocates the device staging buffers
+            sync_all()
+            t0 = time.perf_counter()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.e2e_steps):
+                e2e_step()
+            e1.record()
+            sync_all()
+            wall_ms = (time.perf_counter() - t0) * 1e3
+            t = torch.tensor([max(e0.elapsed_time(e1), wall_ms)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return world * n_frames * args.e2e_steps / (float(t.item()) / 1e3), int(out_mask_host[::17].to(torch.int64).sum().item())
+
+        # the API's default (one byte per mask pixel) and its packed form (one bit per pixel: same information, the mask's
+        # share of the device-to-host bytes drops from 25 % to 4 %); the packed form is the headline, both are reported
+        u8_value, u8_checksum = e2e_run("u8")
+        bits_value, bits_checksum = e2e_run("bits")
         per_frame_in = 2 * HEIGHT * WIDTH * 3
-        per_frame_out = HEIGHT * 2 * WIDTH * 4
-        e2e = {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(per_frame_in * n_frames * world),
+        per_frame_out = HEIGHT * 2 * WIDTH * 3 + HEIGHT * 2 * WIDTH // 8
+        e2e = {"value": bits_value, "unit": "frames/s", "h2d_bytes_per_step": int(per_frame_in * n_frames * world),
                "d2h_bytes_per_step": int(per_frame_out * n_frames * world), "steps": args.e2e_steps,
-               "api": "StereoRerenderer.render_host (pinned host ring, 2-stream chunked H2D/kernel/D2H)", "mask_checksum": checksum}
+               "api": "StereoRerenderer.render_host(mask_format='bits') (pinned host ring, 2-stream chunked H2D/kernel/D2H; hole mask shipped as "
+                      "one bit per pixel, ops.unpack_mask_bits restores the u8 plane)",
+               "mask_checksum": bits_checksum,
+               "u8_mask": {"value": u8_value, "unit": "frames/s", "d2h_bytes_per_step": int(HEIGHT * 2 * WIDTH * 4 * n_frames * world),
+                           "api": "StereoRerenderer.render_host() (default: one byte per mask pixel)", "mask_checksum": u8_checksum},
+               "host": host_locality}
 
     # ---- informational: the result codec on the device (N=1 only; outside every timed region above) ----------
     # The side-by-side frames the timed kernel just wrote, through mdvt_ffv1_encode_frames (FFV1 as the reference's result
@@ -386,6 +501,14 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     peak, peak_kind = measured_peak()
+    paths = None
+    if world == 1 and not args.no_paths:
+        dev_d = dev_c = out_sbs = out_mask = None   # the 8.7 GB of the headline step make room for the 4K frames
+        torch.cuda.empty_cache()
+        try:
+            paths = measure_paths(dev, peak)
+        except Exception as exc:  # noqa: BLE001 - informational leg: never costs the bench line
+            paths = {"error": f"{type(exc).__name__}: {exc}"}
     mean_launch_ms = sum(launch_ms) / len(launch_ms)
     algorithmic = BYTES_PER_PX * WIDTH * HEIGHT * n_frames
     achieved = algorithmic / (mean_launch_ms / 1e3) / 1e9
@@ -398,11 +521,10 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "frames_per_gpu_per_step": n_frames,
-                       "distinct_frames_per_gpu": distinct, "xfov": XFOV, "max_depth": MAX_DEPTH, "pupillary_distance_mm": IPD_MM,
-                       "master_xfov": MASTER_XFOV, "sharding": f"frames, {world} rank(s), no data-path collective",
-                       "l2": f"inputs {(dev_d.numel() + dev_c.numel()) / 1e9:.2f} GB + outputs {(out_sbs.numel() + out_mask.numel()) / 1e9:.2f} GB per step >> 126 MB L2 (no flush needed)"},
+            "config": workload_config(world, n_frames, distinct),
             "roofline": roofline, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks.summary()}
+    if paths is not None:
+        line["paths"] = paths
     if result_codec is not None:
         line["result_codec"] = result_codec
     if not args.no_cpu and world == 1:

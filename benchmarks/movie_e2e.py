@@ -32,11 +32,18 @@ if rank == 0:
     os.makedirs(tmp)
 paths = {k: os.path.join(tmp, k + ".mkv") for k in ("depth", "colour", "mask")}
 t_gen = time.time()
+host_inputs = "--host-inputs" in sys.argv   # inputs as the REFERENCE's tools write them (cv2.VideoWriter: 2 x 2 slices, GOP 12): host decode
 if rank == 0:
     depth, colour = SyntheticClip(w, h, n).frames()
     for key, frames in (("depth", depth), ("colour", colour), ("mask", np.full((n, h, w, 3), 255, np.uint8))):
-        pw = video_io.ParallelWriter(paths[key], 24.0, (w, h), lanes=os.cpu_count(), block=12)   # OpenCV's files, GOP 12, on all cores
-        pw.write(frames, rgb=True)
+        if host_inputs:
+            pw = video_io.ParallelWriter(paths[key], 24.0, (w, h), lanes=os.cpu_count(), block=12)   # OpenCV's files, GOP 12, on all cores
+        else:   # inputs as THIS package's writers leave them (save_depth_video, the result writers): decoded on the device
+            from metric_depth_video_toolbox_b200 import ffv1_gpu
+
+            pw = ffv1_gpu.GpuFfv1Writer(paths[key], 24.0, (w, h), device=torch.device("cuda", local))
+        for a in range(0, n, 8):
+            pw.write(frames[a:a + 8], rgb=True)
         pw.close()
 if world > 1:
     torch.distributed.barrier()
@@ -58,6 +65,8 @@ if rank == 0:
     assert os.path.isfile(out) and os.path.isfile(out + "_infillmask.mkv"), os.listdir(tmp)
     print(json.dumps({"workload": f"movie_2_3D steps 4+5, {w}x{h} x {n} frames, FFV1 in/out, {'green/black' if green else 'normals-coded + TELEA'} infill mask",
                       "n_gpus": world, "host_cores": os.cpu_count(),
-                      "result_writer": "gpu (mdvt_ffv1_encode_frames)" if os.environ.get("MDVT_FFV1_WRITER") == "gpu" else "host lanes (cv2.VideoWriter x cores)", "synthetic_clip_write_s": round(t_gen, 2),
+                      "inputs": "cv2.VideoWriter files (host decode)" if host_inputs else "GpuFfv1Writer files (device decode, mdvt_ffv1_decode_frames)",
+                      "result_writer": "gpu (mdvt_ffv1_encode_frames)" if video_io.gpu_ffv1_requested() else "host lanes (cv2.VideoWriter x cores)",
+                      "synthetic_clip_write_s": round(t_gen, 2),
                       "step4_s": round(t4, 2), "step4_frames_per_s": round(n / t4, 1), "step5_s": round(t5, 2),
                       "step5_frames_per_s": round(n / t5, 1), "frames_per_s": round(n / (t4 + t5), 2)}))

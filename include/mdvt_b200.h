@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MDVT_ABI_VERSION 10
+#define MDVT_ABI_VERSION 11
 
 #if defined(__GNUC__)
 #define MDVT_API __attribute__((visibility("default")))
@@ -144,6 +144,12 @@ MDVT_API int mdvt_touchly_depth(const void *depth_src, int width, int height, in
                        float depth_scale, float touchly_min, float touchly_max, float gain, int zero_is_far,
                        uint8_t *out_rgb, int64_t out_pitch, void *stream);
 
+/* Hole mask plane u8 {0, non-zero} -> one bit per pixel, most significant bit first (numpy.packbits order), (n_pixels + 7) / 8
+ * bytes: the form in which the host API ships masks over PCIe when asked to (StereoRerenderer.render_host(mask_format="bits");
+ * the reference's mask is the u8 / green-black image of stereo_rerender.py:787-793, recovered with numpy.unpackbits).
+ * mask: 16-byte aligned, bits: 2-byte aligned. */
+MDVT_API int mdvt_pack_mask_bits(const uint8_t *mask, int64_t n_pixels, uint8_t *bits, void *stream);
+
 /* cv2.remap(src, map_x, map_y, INTER_LINEAR, BORDER_CONSTANT, border_rgb) for u8x3 images and float32 maps
  * (dst_w*dst_h each), bit-exact with OpenCV's fixed-point bilinear (1/32-pixel coordinates, 15-bit weights): the
  * per-pixel part of stereo_rerender.convert_to_equirectangular (stereo_rerender.py:25-86), used for --vr180 /
@@ -215,13 +221,19 @@ typedef struct mdvt_plane_layout {
 
 /* The generic frame loop in one call (stereo_rerender.py:471-941 with a pose file / convergence rotation;
  * 3d_view_depthfile.py:133-255): for each of n_frames frames, K1+K2 of all n_views cameras
- * (views_host[f*n_views + v]) into `zbuf` (n_views planes, left empty again), then K3 per view into the planes
- * described by rgb_out / mask_out (optional) / depth_out (optional, f32).  sources_host: one mdvt_source per
- * frame (per_frame_source = 1) or one for all.  depth_src / colour_rgb: frame f at + f*frame_stride bytes. */
+ * (views_host[f*n_views + v]) into `zbuf`, then K3 of all views into the planes described by rgb_out / mask_out
+ * (optional) / depth_out (optional, f32).  sources_host: one mdvt_source per frame (per_frame_source = 1) or one for
+ * all.  depth_src / colour_rgb: frame f at + f*frame_stride bytes.
+ * zbuf: zbuf_sets * n_views planes of out_w*out_h slots, all ones on entry (mdvt_zbuf_clear) and on return.  Inside the
+ * call a slot holds epoch << 56 | float_bits(z') << 25 | 0x00BBGGRR of the nearest point: the colour rides in the key (no
+ * gather in K3; candidates with bit-identical z' are ordered by colour, where the index-keyed mdvt_project_splat takes the
+ * lowest source index and the reference an unstable argsort), and the epoch byte counts down from frame to frame, so
+ * planes are not re-armed between frames.  zbuf_sets = 2 lets the call run odd frames on an internal second stream
+ * (forked from / joined to `stream` with events) next to the even ones. */
 MDVT_API int mdvt_render_views(const void *depth_src, int64_t depth_frame_stride, const uint8_t *colour_rgb,
                       int64_t colour_frame_stride, int n_frames, const mdvt_source *sources_host, int per_frame_source,
                       const mdvt_view *views_host, int n_views, float near_plane, int out_w, int out_h, uint64_t *zbuf,
-                      uint32_t bg_rgb, uint32_t fill_rgb, uint32_t flags, const mdvt_plane_layout *rgb_out,
+                      int zbuf_sets, uint32_t bg_rgb, uint32_t fill_rgb, uint32_t flags, const mdvt_plane_layout *rgb_out,
                       const mdvt_plane_layout *mask_out, const mdvt_plane_layout *depth_out, void *stream);
 
 /* The camera of `3d_view_depthfile.py --render` (3d_view_depthfile.py:231-241, depth_map_tools.py:1618-1638,1528-1552):
@@ -241,15 +253,16 @@ typedef struct mdvt_lookat {
  * the frame (pixel grid `src_host`) through that camera, K3 into the planes of rgb_out / mask_out (optional).
  * poses_host: n_frames x 16 doubles (row-major 4x4, the frame's transformation) or NULL.  sums_dev: n_frames x
  * (4 + MDVT_REDUCE_SCRATCH_DOUBLES) doubles (results {sum X, sum Y, sum Z, n} first); views_dev: n_frames
- * mdvt_view, 16-byte aligned; both stay valid for the caller to read back.  zbuf: one out_w x out_h plane, empty on
- * entry, left empty.  touched: mdvt_touched_bytes(out_w, out_h) bytes of scratch (per-segment "something was drawn
- * here" flags that let K3 skip the z-buffer traffic of empty regions).  The centroid kernels run on an internal second
- * stream forked from / joined to `stream` with events. */
+ * mdvt_view, 16-byte aligned; both stay valid for the caller to read back.  zbuf: zbuf_sets (1 or 2) planes of out_w x
+ * out_h slots, all ones on entry and on return (colour-keyed and epoch-tagged inside the call, see mdvt_render_views).
+ * touched: zbuf_sets * mdvt_touched_bytes(out_w, out_h) bytes of scratch (per-segment "something was drawn here" flags that
+ * let K3 skip the z-buffer traffic of empty regions).  With zbuf_sets = 2 the odd frames run on an internal second stream
+ * (forked from / joined to `stream` with events) next to the even ones. */
 MDVT_API int64_t mdvt_touched_bytes(int out_w, int out_h);
 MDVT_API int mdvt_novel_view_frames(const void *depth_src, int64_t depth_frame_stride, const uint8_t *colour_rgb,
                            int64_t colour_frame_stride, int n_frames, const mdvt_source *centroid_src_host,
                            const mdvt_source *src_host, const double *K_host, const double *poses_host,
-                           const mdvt_lookat *look_host, float near_plane, int out_w, int out_h, uint64_t *zbuf,
+                           const mdvt_lookat *look_host, float near_plane, int out_w, int out_h, uint64_t *zbuf, int zbuf_sets,
                            double *sums_dev, mdvt_view *views_dev, uint8_t *touched, uint32_t bg_rgb, uint32_t fill_rgb,
                            uint32_t flags, const mdvt_plane_layout *rgb_out, const mdvt_plane_layout *mask_out,
                            void *stream);

@@ -18,7 +18,7 @@ DECODERS = {"D1": DECODE_D1, "D2": DECODE_D2, "D3": DECODE_D3, "F32": SOURCE_F32
 REDUCE_SCRATCH_DOUBLES = 4096
 FLAG_BG_COLLIDE, FLAG_RESET_ZBUF, FLAG_MASK_RGB, FLAG_ANYWIDTH = 0x1, 0x2, 0x4, 0x8
 ZBUF_EMPTY = 0xFFFFFFFFFFFFFFFF
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 
 class MdvtError(RuntimeError):
@@ -77,6 +77,7 @@ _PROTOTYPES = {
     "mdvt_unproject_f32": (C.c_int, [_u8p, C.POINTER(Source), C.POINTER(C.c_float), _f32p, _stream]),
     "mdvt_unproject_f64": (C.c_int, [_u8p, C.POINTER(Source), C.POINTER(C.c_double), C.POINTER(C.c_double), _f64p, _stream]),
     "mdvt_depth_to_grey": (C.c_int, [_u8p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, _stream]),
+    "mdvt_pack_mask_bits": (C.c_int, [_u8p, C.c_int64, _u8p, _stream]),
     "mdvt_touchly_depth": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                      C.c_int, _u8p, C.c_int64, _stream]),
     "mdvt_remap_bilinear_u8x3": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int64, _f32p, _f32p, C.c_int, C.c_int, C.c_uint32, _u8p, C.c_int64,
@@ -95,11 +96,11 @@ _PROTOTYPES = {
     "mdvt_resolve": (C.c_int, [_u64p, _u8p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, _u8p, C.c_int64,
                                _u8p, C.c_int64, _f32p, C.c_int64, _i32p, _stream]),
     "mdvt_render_views": (C.c_int, [_u8p, C.c_int64, _u8p, C.c_int64, C.c_int, C.POINTER(Source), C.c_int, C.POINTER(View), C.c_int,
-                                    C.c_float, C.c_int, C.c_int, _u64p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PlaneLayout),
+                                    C.c_float, C.c_int, C.c_int, _u64p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PlaneLayout),
                                     C.POINTER(PlaneLayout), C.POINTER(PlaneLayout), _stream]),
     "mdvt_touched_bytes": (C.c_int64, [C.c_int, C.c_int]),
     "mdvt_novel_view_frames": (C.c_int, [_u8p, C.c_int64, _u8p, C.c_int64, C.c_int, C.POINTER(Source), C.POINTER(Source), C.POINTER(C.c_double),
-                                         C.POINTER(C.c_double), C.POINTER(LookAt), C.c_float, C.c_int, C.c_int, _u64p, _f64p, C.c_void_p, _u8p,
+                                         C.POINTER(C.c_double), C.POINTER(LookAt), C.c_float, C.c_int, C.c_int, _u64p, C.c_int, _f64p, C.c_void_p, _u8p,
                                          C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PlaneLayout), C.POINTER(PlaneLayout), _stream]),
     "mdvt_edge_vertices": (C.c_int, [_u8p, C.POINTER(Source), C.POINTER(C.c_double), C.c_double, _u8p, _u8p, _f64p, _stream]),
     "mdvt_edge_vertices_xyz": (C.c_int, [_f64p, C.c_int, C.c_int, C.c_double, _u8p, _u8p, _f64p, _stream]),

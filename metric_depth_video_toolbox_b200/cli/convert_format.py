@@ -93,7 +93,7 @@ def main(argv: Optional[List[str]] = None) -> int:
             grey = cv2.VideoWriter(out_path, cv2.VideoWriter_fourcc(*"FFV1"), fps, (w, h))
     src = None if cam_matrix is None else ops.make_source(w, h, cam_matrix, args.max_depth, "D2", True, 1.0, True)
     frame_n = first
-    for n, (depth_rgb, colour) in video_io.ChunkReader([args.depth_video, args.color_video], first, last, chunk=4):
+    for n, (depth_rgb, colour) in video_io.open_chunk_reader([args.depth_video, args.color_video], first, last, chunk=4):
         d = depth_rgb.to(device, non_blocking=True)
         if grey is not None:
             for frame in ops.depth_to_grey(d, args.max_depth, 16 if args.bit16 else 8, "D2").cpu().numpy():
@@ -103,7 +103,7 @@ def main(argv: Optional[List[str]] = None) -> int:
             if args.save_ply is not None:
                 pose = None if transformations is None else transformations[frame_n]
                 xyz = ops.unproject(d[k], src, pose, torch.float64, cam_matrix).cpu().numpy()
-                rgb = (depth_rgb if colour is None else colour)[k].numpy().reshape(-1, 3)
+                rgb = (depth_rgb if colour is None else colour)[k].cpu().numpy().reshape(-1, 3)
                 ply.write_point_cloud(os.path.join(args.save_ply, f"{frame_n:07d}.ply"), xyz, rgb)
             frame_n += 1
     if grey is not None:

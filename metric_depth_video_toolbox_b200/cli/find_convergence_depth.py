@@ -33,7 +33,7 @@ def convergence_depths(depth_video: str, mask_video: Optional[str], max_depth, d
     sums = torch.empty((chunk, 4 + _lib.REDUCE_SCRATCH_DOUBLES), dtype=torch.float64, device=device)
 
     def analyse(paths, start):
-        for n, (depth_rgb, mask) in video_io.ChunkReader(paths, start, None, chunk=chunk, grey=[False, True], decoders=video_io.default_decoders()):
+        for n, (depth_rgb, mask) in video_io.open_chunk_reader(paths, start, None, chunk=chunk, grey=[False, True], decoders=video_io.default_decoders(), device=device):
             d = depth_rgb.to(device, non_blocking=True)
             m = None if mask is None else mask.to(device, non_blocking=True)
             for k in range(n):

@@ -14,9 +14,10 @@ from ..stereo import StereoParams, StereoRerenderer
 class StereoJob:
     """One clip shard -> chunks of output frames on the host.
 
-    render_chunk(depth_rgb, colour, first_frame) takes pinned host tensors (n, H, W, 3) u8 RGB and returns
-    {"main": (n, oh, ow, 3) u8 RGB, "mask": ... RGB (with --infill_mask), "depth": ... BGR wire format (with
-    --create_sbs_depth_video)} host tensors that stay valid until the next call.
+    render_chunk(depth_rgb, colour, first_frame) takes (n, H, W, 3) u8 RGB tensors -- pinned host chunks of video_io.ChunkReader
+    or device chunks of video_io.DeviceChunkReader -- and returns {"main": (n, oh, ow, 3) u8 RGB, "mask": ... RGB (with
+    --infill_mask), "depth": ... BGR wire format (with --create_sbs_depth_video)}: host tensors, or with `device_outputs` (the
+    result videos are coded on the device) device tensors wherever no host pass remains; valid until the next call.
 
     Modes (stereo_rerender.py:406-422):
       stereo    left | right side by side (:910-918), green/black hole mask (:787-793,921-928), optional SBS depth
@@ -110,6 +111,14 @@ class StereoJob:
             # with --do_basic_infill the holes are filled by the normal march instead of the edge colours (:810-814); the
             # edge points still contribute their normals to the mask
             self.infill.render_device(d, c, first_frame, dsbs, dmask, self.code_normals, self.paint_edges and not self.basic_infill, ddepth)
+            if self.device_outputs and not self.code_normals:
+                # nothing left to do on the host (no TELEA pass): the frames go to the device coder as they are
+                out = {"main": dsbs}
+                if ddepth is not None:
+                    out["depth"] = ops.encode_depth(ddepth, self.params.max_depth, True, True)
+                if mask is not None:
+                    out["mask"] = dmask
+                return out
             if not self.basic_infill:
                 sbs.copy_(dsbs, non_blocking=True)
             out = {"main": sbs}
@@ -141,6 +150,11 @@ class StereoJob:
             ddepth = self._dev_buf("depth", (n, self.h, 2 * self.w), torch.float32)
             self.renderer.render_device(d, c, first_frame, dsbs, dmask, ddepth)
             coded = ops.encode_depth(ddepth, self.params.max_depth, True, True)  # B, G, R like encode_data_as_BGR (:932-936)
+            if self.device_outputs:
+                out = {"main": dsbs, "depth": coded}
+                if dmask is not None:
+                    out["mask"] = dmask
+                return out
             sbs.copy_(dsbs, non_blocking=True)
             if mask is not None:
                 mask.copy_(dmask, non_blocking=True)
@@ -184,6 +198,8 @@ class StereoJob:
             out[:, :self.h].copy_(rgb)
             for k in range(n):
                 ops.touchly_depth(depth[k], a.touchly_min_depth, a.touchly_max_depth, True, decoder="F32", out=out[k, self.h:])
+        if self.device_outputs:
+            return {"main": out}
         host = self._host_buf("main", out.shape)
         host.copy_(out, non_blocking=True)
         return {"main": host}
@@ -238,6 +254,8 @@ class StereoJob:
             if self.touchly0:
                 ops.touchly_depth(depth[k, :, :side].contiguous(), a.touchly_min_depth, a.touchly_max_depth, True, decoder="F32", out=tdepth)
                 ops.remap_bilinear(tdepth, mx, my, out=out[k, :, 2 * side:])
+        if self.device_outputs:
+            return {"main": out}
         host = self._host_buf("main", out.shape)
         host.copy_(out, non_blocking=True)
         return {"main": host}

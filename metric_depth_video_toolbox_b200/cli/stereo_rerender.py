@@ -200,14 +200,18 @@ def run(args, keep_process_group: bool = False) -> int:
     if job.has_depth_output:
         writers["depth"] = open_writer(output_tmp_file + "_depth.mkv", "FFV1")
 
-    reader = video_io.ChunkReader([args.depth_video, args.color_video], start, stop, chunk=args.chunk_frames,
+    reader = video_io.open_chunk_reader([args.depth_video, args.color_video], start, stop, chunk=args.chunk_frames, device=device,
                                   decoders=video_io.default_decoders(world_size))
     t0 = time.time()
     done = 0
     deferred = {}
+    stage = {"read": 0.0, "render": 0.0, "write": 0.0}   # MDVT_PROFILE_LOOP=1: where the frame loop's wall time goes
+    t_prev = time.perf_counter()
     for n, (depth_rgb, colour) in reader:
+        t_a = time.perf_counter()
         outputs = job.render_chunk(depth_rgb, depth_rgb if colour is None else colour, start + done)
-        torch.cuda.synchronize(device)  # results are on the host, the reader may recycle its buffers
+        torch.cuda.synchronize(device)  # results are complete, the reader may recycle its buffers
+        t_b = time.perf_counter()
         for key, pending in list(deferred.items()):   # last chunk's host-finished frames (TELEA tail of the mask)
             writers[key].write(pending.result(), rgb=(key != "depth"))
             del deferred[key]
@@ -217,13 +221,23 @@ def run(args, keep_process_group: bool = False) -> int:
             else:
                 w.write(outputs[key], rgb=(key != "depth"))
         done += n
+        t_c = time.perf_counter()
+        stage["read"] += t_a - t_prev
+        stage["render"] += t_b - t_a
+        stage["write"] += t_c - t_b
+        t_prev = t_c
         if rank == 0:
             pct = 100.0 * done / max(1, stop - start)
             print(f"[{pct:5.1f}%] Frame #{done:4d}/{stop - start}  {done / max(1e-9, time.time() - t0):7.1f} frames/s", end="\r", file=sys.stderr)
     for key, pending in deferred.items():
         writers[key].write(pending.result(), rgb=(key != "depth"))
+    t_close = time.perf_counter()
     for w in writers.values():
         w.close()
+    if os.environ.get("MDVT_PROFILE_LOOP") == "1":
+        print(f"\n[frame loop, rank {rank}] {done} frames: waiting for the reader {stage['read']:.2f} s, render + sync {stage['render']:.2f} s, "
+              f"handing to the writers {stage['write']:.2f} s, closing the writers {time.perf_counter() - t_close:.2f} s "
+              f"({type(reader).__name__}, {', '.join(type(w).__name__ for w in writers.values())})", file=sys.stderr)
     total_done = sharding.gather_counts(done)
 
     if world_size > 1:

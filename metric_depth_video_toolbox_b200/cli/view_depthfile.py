@@ -98,7 +98,7 @@ def main(argv: Optional[List[str]] = None) -> int:
             video_io.ChunkWriter(output_file, fourcc, fps, (w, h))
     done = 0
     host_out = None
-    for n, (depth_rgb, colour) in video_io.ChunkReader([args.depth_video, args.color_video], 0, total_frames, chunk=args.chunk_frames,
+    for n, (depth_rgb, colour) in video_io.open_chunk_reader([args.depth_video, args.color_video], 0, total_frames, chunk=args.chunk_frames,
                                                           decoders=video_io.default_decoders()):
         d = depth_rgb.to(device, non_blocking=True)
         c = d if colour is None else colour.to(device, non_blocking=True)

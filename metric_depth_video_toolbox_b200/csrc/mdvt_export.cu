@@ -44,9 +44,51 @@ __global__ void __launch_bounds__(kThreads)
     }
 }
 
+// Hole mask u8 {0, non-zero} -> 1 bit per pixel, most significant bit first (np.packbits order): what crosses PCIe when
+// the host API is asked for packed masks (a 1080p stereo mask shrinks from 4.1 MB to 0.5 MB per frame).  16 pixels per
+// thread: one 16-byte load, the top bit of every byte (0xFF / 0x00 masks; any non-zero byte counts) gathered by a
+// multiply, one 2-byte store.
+__global__ void __launch_bounds__(kThreads) pack_mask_bits_kernel(const uint8_t *__restrict__ mask, int64_t n_groups16, int64_t n_pixels,
+                                                                  uint8_t *__restrict__ bits) {
+    for (int64_t g = blockIdx.x * (int64_t)kThreads + threadIdx.x; g < n_groups16; g += (int64_t)gridDim.x * kThreads) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if ((g + 1) * 16 <= n_pixels) {
+            const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(mask) + g);
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        } else {
+            for (int k = 0; k < 16 && g * 16 + k < n_pixels; ++k) w[k >> 2] |= (uint32_t)mask[g * 16 + k] << (8 * (k & 3));
+        }
+        uint32_t out = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            // non-zero byte -> its top bit set: (x | (x + 0x7F7F7F7F per byte without carry across bytes)) & 0x80
+            const uint32_t x = w[q];
+            const uint32_t nz = (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+            // bytes 0..3 (pixels 4q .. 4q+3) -> bits 3..0 of a nibble, first pixel most significant
+            const uint32_t nib = ((nz >> 7) * 0x08040201u >> 24) & 0xFu;   // byte0 -> bit 3, byte1 -> bit 2, byte2 -> bit 1, byte3 -> bit 0
+            out |= nib << (4 * ((q & 1) ? 0 : 1) + 8 * (q >> 1));
+        }
+        const int64_t b = g * 2;
+        const int64_t n_bytes = (n_pixels + 7) >> 3;
+        if (b + 1 < n_bytes) *reinterpret_cast<uint16_t *>(bits + b) = (uint16_t)out;
+        else if (b < n_bytes) bits[b] = (uint8_t)out;
+    }
+}
+
 }  // namespace mdvt
 
 using namespace mdvt;
+
+extern "C" int mdvt_pack_mask_bits(const uint8_t *mask, int64_t n_pixels, uint8_t *bits, void *stream) {
+    MDVT_REQUIRE(n_pixels >= 0, "negative pixel count");
+    if (n_pixels == 0) return MDVT_OK;
+    MDVT_REQUIRE(mask && bits, "NULL buffer");
+    MDVT_REQUIRE((reinterpret_cast<uintptr_t>(mask) & 15) == 0 && (reinterpret_cast<uintptr_t>(bits) & 1) == 0, "mask must be 16-byte, bits 2-byte aligned");
+    const int64_t groups = (n_pixels + 15) / 16;
+    pack_mask_bits_kernel<<<grid_for(groups), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(mask, groups, n_pixels, bits);
+    MDVT_CUDA_TRY(cudaGetLastError());
+    return MDVT_OK;
+}
 
 extern "C" int mdvt_depth_to_grey(const void *depth_src, int64_t n_pixels, int decoder, int bit16, float dec_const, float factor,
                                   int out_bits, int channels, void *out, void *stream) {

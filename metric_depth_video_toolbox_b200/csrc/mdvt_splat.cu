@@ -23,6 +23,11 @@ constexpr int kRoundMagicBits = 0x4B400000;
 // camera, z-buffer traffic drops from 2 x 66 MB to 2 x 25 MB per 4K frame and the touched part stays L2-resident.
 constexpr int kSegShift = 6;
 
+static int g_grid_pct() {  // development switch: MDVT_GRID_PCT = share of the resident CTA slots a frame-loop kernel asks for (default 100)
+    static const int pct = getenv("MDVT_GRID_PCT") ? atoi(getenv("MDVT_GRID_PCT")) : 100;
+    return pct < 10 ? 10 : (pct > 100 ? 100 : pct);
+}
+
 struct ViewPack {
     mdvt_view v[kMaxViews];
     int n;
@@ -36,11 +41,15 @@ struct RayPack {  // the views of one frame in ray form (mdvt_common.cuh)
 // fi = float(row).  Divisions are correctly rounded (== the float32 model's `/`): the reciprocal of Zv is refined once
 // per view and shared by u and v.  All index arithmetic is 32-bit (the entry point checks that source and target
 // planes have < 2^31 pixels).
-template <bool UVZ, bool TOUCHED>
+// EPOCH (the colour-keyed frame loops): key = epoch << 56 | float_bits(Zv) << 25 | colour.  Frames count the epoch DOWN, so
+// a key written for the current frame is smaller than anything an earlier frame left in the plane: stale slots lose every
+// atomicMin and the resolve recognises them by their epoch byte -- the z-buffer is never re-armed between frames (that
+// pass wrote 8 bytes per target pixel and view; the planes are cleared once per call instead).
+template <bool UVZ, bool TOUCHED, bool EPOCH>
 __device__ __forceinline__ void splat_pixel(uint32_t p, const float (&cj)[kMaxViews][3], float fi, float z, const RayPack &rays,
                                             float near_plane, int out_w, uint32_t out_n, uint32_t out_h, uint32_t payload, uint32_t n,
                                             unsigned long long *__restrict__ zbuf, float *__restrict__ out_uvz, uint64_t keep,
-                                            uint8_t *__restrict__ touched) {
+                                            uint8_t *__restrict__ touched, uint32_t epoch_hi, uint32_t lanes) {
 #pragma unroll
     for (int k = 0; k < kMaxViews; ++k) {
         if (k < rays.n) {
@@ -66,9 +75,15 @@ __device__ __forceinline__ void splat_pixel(uint32_t p, const float (&cj)[kMaxVi
             // (out_w, out_h < 2^22 is checked at the entry points).  Zv > near is false for NaN.
             const uint32_t ui = (uint32_t)(__float_as_int(__fadd_rn(u, kRoundMagic)) - kRoundMagicBits);
             const uint32_t vi = (uint32_t)(__float_as_int(__fadd_rn(v, kRoundMagic)) - kRoundMagicBits);
-            if (Zv > near_plane && ui < (uint32_t)out_w && vi < out_h) {
-                const uint32_t t = (uint32_t)k * out_n + vi * (uint32_t)out_w + ui;
-                const unsigned long long key = ((unsigned long long)__float_as_uint(Zv) << 32) | payload;
+            const bool ok = Zv > near_plane && ui < (uint32_t)out_w && vi < out_h;
+            const uint32_t t = (uint32_t)k * out_n + vi * (uint32_t)out_w + ui;
+            const uint32_t zb = __float_as_uint(Zv);  // positive, finite: < 2^31 where ok
+            const unsigned long long key = EPOCH ? (((unsigned long long)(epoch_hi | (zb >> 7)) << 32) | ((zb << 25) | payload))
+                                                 : (((unsigned long long)zb << 32) | payload);
+            // (measured and dropped: letting a lane stay silent when a neighbouring lane holds a smaller key for the same slot -- the
+            //  novel view folds 2.6 source pixels onto a drawn target pixel -- costs 17 instructions per pixel and buys nothing: the
+            //  L2 processes a warp's REDs per sector, 40.4 vs 41.0 us per 4K frame, profiles/r02_novel_4k_v7_dedup_brief.txt)
+            if (ok) {
                 red_min_u64_keep(zbuf + t, key, keep);
                 if (TOUCHED) touched[t >> kSegShift] = 1;  // flat 64-slot segments of the plane (single view: t < out_n)
             }
@@ -96,10 +111,11 @@ __global__ void __launch_bounds__(kSplatThreads)
     project_splat_kernel(const void *__restrict__ rgb, const uint8_t *__restrict__ colour, int width, int height, float dec_const,
                          float depth_scale, SourceCam cam, RayPack rays_param, const mdvt_view *__restrict__ view_dev, float near_plane,
                          int out_w, int out_h, uint32_t id_offset, unsigned long long *__restrict__ zbuf, float *__restrict__ out_uvz,
-                         uint8_t *__restrict__ touched) {
+                         uint8_t *__restrict__ touched, uint32_t epoch_hi) {
     const uint32_t out_n = (uint32_t)out_w * (uint32_t)out_h, n = (uint32_t)width * (uint32_t)height;
     const int col = blockIdx.x * kSplatThreads + threadIdx.x;
     if (col >= width) return;
+    const uint32_t lanes = __activemask();  // the lanes of this warp that own a column (all 32 except in the last column block)
     RayPack local;
     if (DEVVIEW) {
         local.n = 1;
@@ -146,14 +162,14 @@ __global__ void __launch_bounds__(kSplatThreads)
                 const float zs = __fmul_rn(z[k], depth_scale), fi = __int2float_rn(row);
                 // DEVVIEW: the novel-view frame loop -- touched flags always on, never a (u, v, z) dump
                 if (DEVVIEW)
-                    splat_pixel<false, true>(p, cj, fi, zs, rays, near_plane, out_w, out_n, (uint32_t)out_h, pay[k], n, zbuf, nullptr, keep,
-                                             touched);
+                    splat_pixel<false, true, true>(p, cj, fi, zs, rays, near_plane, out_w, out_n, (uint32_t)out_h, pay[k], n, zbuf, nullptr, keep,
+                                                   touched, epoch_hi, lanes);
                 else if (!CKEY && out_uvz)
-                    splat_pixel<true, false>(p, cj, fi, zs, rays, near_plane, out_w, out_n, (uint32_t)out_h, pay[k], n, zbuf, out_uvz, keep,
-                                             nullptr);
+                    splat_pixel<true, false, false>(p, cj, fi, zs, rays, near_plane, out_w, out_n, (uint32_t)out_h, pay[k], n, zbuf, out_uvz, keep,
+                                                    nullptr, 0u, lanes);
                 else
-                    splat_pixel<false, false>(p, cj, fi, zs, rays, near_plane, out_w, out_n, (uint32_t)out_h, pay[k], n, zbuf, nullptr, keep,
-                                              nullptr);
+                    splat_pixel<false, false, CKEY>(p, cj, fi, zs, rays, near_plane, out_w, out_n, (uint32_t)out_h, pay[k], n, zbuf, nullptr, keep,
+                                                    nullptr, epoch_hi, lanes);
             }
         }
     }
@@ -456,7 +472,7 @@ __global__ void __launch_bounds__(kRowResolveThreads)
     resolve_ckey_kernel(unsigned long long *__restrict__ zbuf, int out_w, int out_h, uint32_t bg_rgb, uint32_t fill_rgb, uint32_t flags,
                         uint8_t *__restrict__ out_rgb, int64_t rgb_pitch, uint8_t *__restrict__ out_mask, int64_t mask_pitch,
                         float *__restrict__ out_depth, int64_t depth_pitch, const uint8_t *__restrict__ touched,
-                        uint8_t *__restrict__ touched_clear, ViewStrides vs) {
+                        uint8_t *__restrict__ touched_clear, ViewStrides vs, uint32_t epoch) {
     const int g = blockIdx.x * kRowResolveThreads + threadIdx.x;
     if (g >= (out_w + VEC - 1) / VEC) return;
     if (blockIdx.z) {
@@ -467,7 +483,7 @@ __global__ void __launch_bounds__(kRowResolveThreads)
         if (DEPTH) out_depth += v * vs.depth;
     }
     const int col0 = g * VEC;
-    const bool collide = flags & MDVT_FLAG_BG_COLLIDE, reset = flags & MDVT_FLAG_RESET_ZBUF, mask_rgb = flags & MDVT_FLAG_MASK_RGB;
+    const bool collide = flags & MDVT_FLAG_BG_COLLIDE, mask_rgb = flags & MDVT_FLAG_MASK_RGB;
     const uint64_t keep = l2_keep_policy();
     const int stride = gridDim.y;
     for (int row0 = blockIdx.y; row0 < out_h; row0 += 2 * stride) {
@@ -508,24 +524,17 @@ __global__ void __launch_bounds__(kRowResolveThreads)
             uint32_t px[VEC], holes = 0;
 #pragma unroll
             for (int k = 0; k < VEC; ++k) {
-                const bool hole = hi[j][k] == 0xFFFFFFFFu || (collide && lo[j][k] == bg_rgb);  // a filled slot holds positive finite float bits there
-                px[k] = hole ? fill_rgb : lo[j][k];
+                const uint32_t rgb = lo[j][k] & 0xFFFFFFu;
+                const bool drawn = (hi[j][k] >> 24) == epoch;   // anything else is an older frame's key or the cleared plane
+                const bool hole = !drawn || (collide && rgb == bg_rgb);
+                px[k] = hole ? fill_rgb : rgb;
                 holes |= hole ? (1u << k) : 0u;
-            }
-            if (live[j] && reset) {
-                unsigned long long *z = zbuf + t0[j];
-                if (VEC == 4) {
-                    const ulonglong2 e = make_ulonglong2(MDVT_ZBUF_EMPTY, MDVT_ZBUF_EMPTY);
-                    st_u64x2_keep(z, e, keep);
-                    st_u64x2_keep(z + 2, e, keep);
-                } else {
-                    st_u64_keep(z, MDVT_ZBUF_EMPTY, keep);
-                }
             }
             if (DEPTH) {
                 float *o = out_depth + row * depth_pitch + col0;
 #pragma unroll
-                for (int k = 0; k < VEC; ++k) o[k] = hi[j][k] == 0xFFFFFFFFu ? 0.0f : __uint_as_float(hi[j][k]);
+                for (int k = 0; k < VEC; ++k)
+                    o[k] = (hi[j][k] >> 24) == epoch ? __uint_as_float(((hi[j][k] & 0xFFFFFFu) << 7) | (lo[j][k] >> 25)) : 0.0f;
             }
             if (out_rgb) {
                 uint8_t *o = out_rgb + row * rgb_pitch + (int64_t)col0 * 3;
@@ -585,7 +594,7 @@ extern "C" int mdvt_zbuf_clear(uint64_t *zbuf, int64_t n_slots, void *stream) {
 
 static int launch_project_splat(const void *depth_src, const mdvt_source *src, const ViewPack &pack, const mdvt_view *view_dev, float near_plane,
                                 int out_w, int out_h, uint32_t id_offset, unsigned long long *zb, float *out_uvz, cudaStream_t st,
-                                uint8_t *touched = nullptr, const uint8_t *colour_key = nullptr);
+                                uint8_t *touched = nullptr, const uint8_t *colour_key = nullptr, uint32_t epoch = 0);
 
 static int pack_views(const mdvt_view *views_host, int n_views, ViewPack &pack) {
     MDVT_REQUIRE(n_views >= 1 && n_views <= kMaxViews, "n_views must be 1..%d", kMaxViews);
@@ -679,7 +688,7 @@ static int launch_resolve(unsigned long long *zb, const uint8_t *colour_rgb, int
 // colour-keyed planes -> image / mask / depth, all views of a frame in one launch
 static int launch_resolve_ckey(unsigned long long *zb, int out_w, int out_h, uint32_t bg_rgb, uint32_t fill_rgb, uint32_t flags, uint8_t *out_rgb,
                                int64_t rgb_pitch, uint8_t *out_mask, int64_t mask_pitch, float *out_depth, int64_t depth_pitch, cudaStream_t st,
-                               const uint8_t *touched, uint8_t *touched_clear, int n_views, ViewStrides vs) {
+                               const uint8_t *touched, uint8_t *touched_clear, int n_views, ViewStrides vs, uint32_t epoch) {
     const int mask_bpp = (flags & MDVT_FLAG_MASK_RGB) ? 3 : 1;
     MDVT_REQUIRE(!out_rgb || rgb_pitch >= (int64_t)out_w * 3, "rgb_pitch %lld too small", (long long)rgb_pitch);
     MDVT_REQUIRE(!out_mask || mask_pitch >= (int64_t)out_w * mask_bpp, "mask_pitch %lld too small", (long long)mask_pitch);
@@ -700,13 +709,13 @@ static int launch_resolve_ckey(unsigned long long *zb, int out_w, int out_h, uin
     }
     const int vec = vec4 ? 4 : 1;
     const int col_blocks = ((out_w + vec - 1) / vec + kRowResolveThreads - 1) / kRowResolveThreads;
-    int row_blocks = sm_count() * per_sm / (col_blocks * n_views);
+    int row_blocks = sm_count() * per_sm * g_grid_pct() / 100 / (col_blocks * n_views);
     if (row_blocks < 1) row_blocks = 1;
     if (row_blocks > (out_h + 1) / 2) row_blocks = (out_h + 1) / 2;
     const dim3 grid(col_blocks, row_blocks, n_views);
 #define GO(D, V)                                                                                                                             \
     PICK(D, V)<<<grid, kRowResolveThreads, 0, st>>>(zb, out_w, out_h, bg_rgb, fill_rgb, flags, out_rgb, rgb_pitch, out_mask, mask_pitch, out_depth, \
-                                                    depth_pitch, touched, touched_clear, vs)
+                                                    depth_pitch, touched, touched_clear, vs, epoch)
     if (out_depth) { if (vec4) GO(true, 4); else GO(true, 1); }
     else { if (vec4) GO(false, 4); else GO(false, 1); }
 #undef GO
@@ -717,7 +726,7 @@ static int launch_resolve_ckey(unsigned long long *zb, int out_w, int out_h, uin
 
 static int launch_project_splat(const void *depth_src, const mdvt_source *src, const ViewPack &pack, const mdvt_view *view_dev, float near_plane,
                                 int out_w, int out_h, uint32_t id_offset, unsigned long long *zb, float *out_uvz, cudaStream_t st,
-                                uint8_t *touched, const uint8_t *colour_key) {
+                                uint8_t *touched, const uint8_t *colour_key, uint32_t epoch) {
     MDVT_REQUIRE((touched != nullptr) == (view_dev != nullptr), "touched flags go with the device-resident single view");
     MDVT_REQUIRE(out_w < (1 << 22) && out_h < (1 << 22), "target sides must be below 2^22 pixels");
     MDVT_REQUIRE((int64_t)src->width * src->height < 0x7FFFFFFFll && (int64_t)out_w * out_h * pack.n < 0x7FFFFFFFll,
@@ -739,11 +748,11 @@ static int launch_project_splat(const void *depth_src, const mdvt_source *src, c
         static int per_sm_of[3] = {0, 0, 0};                                                                                         \
         int &per_sm = per_sm_of[view_dev ? 2 : (colour_key ? 1 : 0)];                                                                \
         if (!per_sm) per_sm = resident_ctas(kernel, kSplatThreads);                                                                   \
-        int row_blocks = sm_count() * per_sm / col_blocks; /* every CTA resident: no second wave */                                  \
+        int row_blocks = sm_count() * per_sm * (colour_key ? g_grid_pct() : 100) / 100 / col_blocks; /* every CTA resident: no second wave */ \
         if (row_blocks < 1) row_blocks = 1;                                                                                          \
         if (row_blocks > src->height) row_blocks = src->height;                                                                      \
         kernel<<<dim3(col_blocks, row_blocks), kSplatThreads, 0, st>>>(depth_src, colour_key, src->width, src->height, src->dec_const, src->depth_scale, cam, \
-                                                                     rays, view_dev, near_plane, out_w, out_h, id_offset, zb, out_uvz, touched); \
+                                                                     rays, view_dev, near_plane, out_w, out_h, id_offset, zb, out_uvz, touched, epoch << 24); \
     } while (0)
     MDVT_DISPATCH_SOURCE(src->decoder, src->bit16, CALL);
 #undef CALL
@@ -760,57 +769,14 @@ extern "C" int mdvt_resolve(uint64_t *zbuf, const uint8_t *colour_rgb, int out_w
                           out_mask, mask_pitch, out_depth, depth_pitch, out_ids, static_cast<cudaStream_t>(stream));
 }
 
-// Frame loop of the generic path in one call: per frame K1+K2 for all views, then K3 per view.
-extern "C" int mdvt_render_views(const void *depth_src, int64_t depth_frame_stride, const uint8_t *colour_rgb, int64_t colour_frame_stride,
-                                 int n_frames, const mdvt_source *sources_host, int per_frame_source, const mdvt_view *views_host,
-                                 int n_views, float near_plane, int out_w, int out_h, uint64_t *zbuf, uint32_t bg_rgb, uint32_t fill_rgb,
-                                 uint32_t flags, const mdvt_plane_layout *rgb_out, const mdvt_plane_layout *mask_out,
-                                 const mdvt_plane_layout *depth_out, void *stream) {
-    MDVT_REQUIRE(n_frames >= 0, "negative frame count");
-    MDVT_REQUIRE(n_views >= 1 && n_views <= kMaxViews, "n_views must be 1..%d", kMaxViews);
-    MDVT_REQUIRE(out_w > 0 && out_h > 0, "bad output size %dx%d", out_w, out_h);
-    if (n_frames == 0) return MDVT_OK;
-    MDVT_REQUIRE(depth_src && colour_rgb && sources_host && views_host && zbuf && rgb_out && rgb_out->base, "NULL buffer");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    unsigned long long *zb = reinterpret_cast<unsigned long long *>(zbuf);
-    const int64_t out_n = (int64_t)out_w * out_h;
-    static const int dbg = getenv("MDVT_DEBUG") ? atoi(getenv("MDVT_DEBUG")) : 0;  // timing aid: 1 no splat, 2 no resolve, 4 no re-arm
-    for (int f = 0; f < n_frames; ++f) {
-        const mdvt_source *src = sources_host + (per_frame_source ? f : 0);
-        if (int rc = check_source(src)) return rc;
-        MDVT_REQUIRE((int64_t)src->width * src->height <= 0xFFFFFFFFll, "source frame has more than 2^32 pixels");
-        ViewPack pack{};
-        if (int rc = pack_views(views_host + (int64_t)f * n_views, n_views, pack)) return rc;
-        const uint8_t *dsrc = static_cast<const uint8_t *>(depth_src) + f * depth_frame_stride;
-        const uint8_t *colour_f = colour_rgb + f * colour_frame_stride;
-        if (!(dbg & 1))
-            if (int rc = launch_project_splat(dsrc, src, pack, nullptr, near_plane, out_w, out_h, 0, zb, nullptr, st, nullptr, colour_f)) return rc;
-        if (dbg & 2) continue;
-        auto at = [&](const mdvt_plane_layout *L, int v) -> uint8_t * {
-            return (L && L->base) ? static_cast<uint8_t *>(L->base) + f * L->frame_stride + v * L->view_stride : nullptr;
-        };
-        const int64_t mask_pitch = mask_out ? mask_out->row_pitch : 0, depth_pitch = depth_out ? depth_out->row_pitch / 4 : 0;
-        // all views in ONE launch (blockIdx.z); the kernel falls back to one pixel per thread for odd widths / alignments
-        const ViewStrides vs{out_n, rgb_out->view_stride, mask_out ? mask_out->view_stride : 0, depth_out ? depth_out->view_stride / 4 : 0};
-        MDVT_REQUIRE(!at(depth_out, 0) || (depth_out->view_stride % 4 == 0 && depth_out->row_pitch % 4 == 0), "depth planes must be float aligned");
-        if (int rc = launch_resolve_ckey(zb, out_w, out_h, bg_rgb, fill_rgb, (dbg & 4) ? flags : (flags | MDVT_FLAG_RESET_ZBUF), at(rgb_out, 0),
-                                         rgb_out->row_pitch, at(mask_out, 0), mask_pitch, reinterpret_cast<float *>(at(depth_out, 0)), depth_pitch, st,
-                                         nullptr, nullptr, n_views, vs))
-            return rc;
-    }
-    return MDVT_OK;
-}
-
-// 3d_view_depthfile.py --render, whole chunk, no host synchronisation: centroid -> device look-at -> splat -> resolve.
-// The centroid (+ look-at) of frame f+1 does not depend on frame f, is latency-bound and small, so it runs on an
-// internal second stream underneath the splat / resolve of the frames before it (fork / join with events; at most
-// kAhead frames ahead so that its input is still in L2 when the splat reads it again).
+// An internal second stream (process-wide, one device per process) with its fork / join events: the frame loops below run
+// independent work next to the caller's stream on it.
 namespace {
 constexpr int kAhead = 2, kRing = 4;
 struct AuxStream {
     int device = -1;
     cudaStream_t stream = nullptr;
-    cudaEvent_t fork = nullptr, centroid_done[kRing] = {}, frame_done[kRing] = {};
+    cudaEvent_t fork = nullptr, join = nullptr, centroid_done[kRing] = {}, frame_done[kRing] = {};
 };
 int aux_for_current_device(AuxStream **out) {
     static AuxStream aux;
@@ -820,6 +786,7 @@ int aux_for_current_device(AuxStream **out) {
         MDVT_REQUIRE(aux.device == -1, "one process drives one GPU: the library was first used on device %d, now on %d", aux.device, dev);
         MDVT_CUDA_TRY(cudaStreamCreateWithFlags(&aux.stream, cudaStreamNonBlocking));
         MDVT_CUDA_TRY(cudaEventCreateWithFlags(&aux.fork, cudaEventDisableTiming));
+        MDVT_CUDA_TRY(cudaEventCreateWithFlags(&aux.join, cudaEventDisableTiming));
         for (int k = 0; k < kRing; ++k) {
             MDVT_CUDA_TRY(cudaEventCreateWithFlags(&aux.centroid_done[k], cudaEventDisableTiming));
             MDVT_CUDA_TRY(cudaEventCreateWithFlags(&aux.frame_done[k], cudaEventDisableTiming));
@@ -829,8 +796,79 @@ int aux_for_current_device(AuxStream **out) {
     *out = &aux;
     return MDVT_OK;
 }
+std::mutex g_aux_mutex;  // the internal stream and its events are process-wide: calls from several host threads enqueue one after the other
 }  // namespace
 
+
+// Frame loop of the generic path in one call: per frame K1+K2 for all views (colour-keyed, epoch-tagged), then K3 for all
+// views in one launch.  zbuf_sets = 2: `zbuf` holds two sets of n_views planes and the frames alternate between the caller's
+// stream (set 0) and the internal second stream (set 1), so that one frame's splat (atomic-rate bound) runs next to the
+// other frame's resolve (bandwidth bound).  The planes are cleared once at the end of the call (and every 254 uses of a set).
+extern "C" int mdvt_render_views(const void *depth_src, int64_t depth_frame_stride, const uint8_t *colour_rgb, int64_t colour_frame_stride,
+                                 int n_frames, const mdvt_source *sources_host, int per_frame_source, const mdvt_view *views_host,
+                                 int n_views, float near_plane, int out_w, int out_h, uint64_t *zbuf, int zbuf_sets, uint32_t bg_rgb,
+                                 uint32_t fill_rgb, uint32_t flags, const mdvt_plane_layout *rgb_out, const mdvt_plane_layout *mask_out,
+                                 const mdvt_plane_layout *depth_out, void *stream) {
+    MDVT_REQUIRE(n_frames >= 0, "negative frame count");
+    MDVT_REQUIRE(n_views >= 1 && n_views <= kMaxViews, "n_views must be 1..%d", kMaxViews);
+    MDVT_REQUIRE(out_w > 0 && out_h > 0, "bad output size %dx%d", out_w, out_h);
+    MDVT_REQUIRE(zbuf_sets == 1 || zbuf_sets == 2, "zbuf_sets must be 1 or 2");
+    if (n_frames == 0) return MDVT_OK;
+    MDVT_REQUIRE(depth_src && colour_rgb && sources_host && views_host && zbuf && rgb_out && rgb_out->base, "NULL buffer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t out_n = (int64_t)out_w * out_h;
+    static const int dbg = getenv("MDVT_DEBUG") ? atoi(getenv("MDVT_DEBUG")) : 0;  // timing aid: 1 no splat, 2 no resolve
+    const int sets = n_frames > 1 ? zbuf_sets : 1;
+    std::unique_lock<std::mutex> aux_lock(g_aux_mutex, std::defer_lock);
+    AuxStream *aux = nullptr;
+    cudaStream_t lane[2] = {st, st};
+    if (sets == 2) {
+        aux_lock.lock();
+        if (int rc = aux_for_current_device(&aux)) return rc;
+        lane[1] = aux->stream;
+        MDVT_CUDA_TRY(cudaEventRecord(aux->fork, st));
+        MDVT_CUDA_TRY(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
+    }
+    for (int f = 0; f < n_frames; ++f) {
+        const mdvt_source *src = sources_host + (per_frame_source ? f : 0);
+        if (int rc = check_source(src)) return rc;
+        MDVT_REQUIRE((int64_t)src->width * src->height <= 0xFFFFFFFFll, "source frame has more than 2^32 pixels");
+        ViewPack pack{};
+        if (int rc = pack_views(views_host + (int64_t)f * n_views, n_views, pack)) return rc;
+        const int set = f % sets, use = f / sets;
+        cudaStream_t ls = lane[set];
+        unsigned long long *zb = reinterpret_cast<unsigned long long *>(zbuf) + (int64_t)set * n_views * out_n;
+        const uint32_t epoch = 254u - (uint32_t)(use % 254);
+        const uint8_t *dsrc = static_cast<const uint8_t *>(depth_src) + f * depth_frame_stride;
+        const uint8_t *colour_f = colour_rgb + f * colour_frame_stride;
+        if (!(dbg & 1))
+            if (int rc = launch_project_splat(dsrc, src, pack, nullptr, near_plane, out_w, out_h, 0, zb, nullptr, ls, nullptr, colour_f, epoch)) return rc;
+        auto at = [&](const mdvt_plane_layout *L, int v) -> uint8_t * {
+            return (L && L->base) ? static_cast<uint8_t *>(L->base) + f * L->frame_stride + v * L->view_stride : nullptr;
+        };
+        const int64_t mask_pitch = mask_out ? mask_out->row_pitch : 0, depth_pitch = depth_out ? depth_out->row_pitch / 4 : 0;
+        // all views in ONE launch (blockIdx.z); the kernel falls back to one pixel per thread for odd widths / alignments
+        const ViewStrides vs{out_n, rgb_out->view_stride, mask_out ? mask_out->view_stride : 0, depth_out ? depth_out->view_stride / 4 : 0};
+        MDVT_REQUIRE(!at(depth_out, 0) || (depth_out->view_stride % 4 == 0 && depth_out->row_pitch % 4 == 0), "depth planes must be float aligned");
+        if (!(dbg & 2))
+            if (int rc = launch_resolve_ckey(zb, out_w, out_h, bg_rgb, fill_rgb, flags, at(rgb_out, 0), rgb_out->row_pitch, at(mask_out, 0), mask_pitch,
+                                             reinterpret_cast<float *>(at(depth_out, 0)), depth_pitch, ls, nullptr, nullptr, n_views, vs, epoch))
+                return rc;
+        // the epoch byte is used up (or this was the set's last frame): back to the all-ones plane
+        if (use % 254 == 253 || f + sets >= n_frames)
+            if (int rc = mdvt_zbuf_clear(reinterpret_cast<uint64_t *>(zb), (int64_t)n_views * out_n, ls)) return rc;
+    }
+    if (sets == 2) {
+        MDVT_CUDA_TRY(cudaEventRecord(aux->join, aux->stream));
+        MDVT_CUDA_TRY(cudaStreamWaitEvent(st, aux->join, 0));
+    }
+    return MDVT_OK;
+}
+
+// 3d_view_depthfile.py --render, whole chunk, no host synchronisation: centroid -> device look-at -> splat -> resolve.
+// The centroid (+ look-at) of frame f+1 does not depend on frame f, is latency-bound and small, so it runs on an
+// internal second stream underneath the splat / resolve of the frames before it (fork / join with events; at most
+// kAhead frames ahead so that its input is still in L2 when the splat reads it again).
 extern "C" int64_t mdvt_touched_bytes(int out_w, int out_h) {
     if (out_w <= 0 || out_h <= 0) return 0;
     return 2 * (((int64_t)out_h * out_w + (1 << kSegShift) - 1) >> kSegShift);
@@ -839,11 +877,12 @@ extern "C" int64_t mdvt_touched_bytes(int out_w, int out_h) {
 extern "C" int mdvt_novel_view_frames(const void *depth_src, int64_t depth_frame_stride, const uint8_t *colour_rgb, int64_t colour_frame_stride,
                                       int n_frames, const mdvt_source *centroid_src, const mdvt_source *src, const double *K_host,
                                       const double *poses_host, const mdvt_lookat *look, float near_plane, int out_w, int out_h,
-                                      uint64_t *zbuf, double *sums_dev, mdvt_view *views_dev, uint8_t *touched, uint32_t bg_rgb,
+                                      uint64_t *zbuf, int zbuf_sets, double *sums_dev, mdvt_view *views_dev, uint8_t *touched, uint32_t bg_rgb,
                                       uint32_t fill_rgb, uint32_t flags, const mdvt_plane_layout *rgb_out, const mdvt_plane_layout *mask_out,
                                       void *stream) {
     MDVT_REQUIRE(n_frames >= 0, "negative frame count");
     MDVT_REQUIRE(out_w > 0 && out_h > 0, "bad output size %dx%d", out_w, out_h);
+    MDVT_REQUIRE(zbuf_sets == 1 || zbuf_sets == 2, "zbuf_sets must be 1 or 2");
     if (int rc = check_source(centroid_src)) return rc;
     if (int rc = check_source(src)) return rc;
     if (n_frames == 0) return MDVT_OK;
@@ -852,46 +891,55 @@ extern "C" int mdvt_novel_view_frames(const void *depth_src, int64_t depth_frame
     MDVT_REQUIRE(reinterpret_cast<uintptr_t>(views_dev) % 16 == 0, "views_dev must be 16-byte aligned");
     MDVT_REQUIRE(centroid_src->width == src->width && centroid_src->height == src->height, "the two source descriptions differ in size");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // the internal stream and its event ring are process-wide: calls from several host threads enqueue one after the other
-    static std::mutex aux_mutex;
-    std::lock_guard<std::mutex> aux_lock(aux_mutex);
+    // Two lanes: even frames on the caller's stream, odd frames on the internal one, each with its own z-buffer plane and
+    // pair of touched-flag planes.  A lane runs centroid + look-at -> splat -> resolve of its frames back to back; the
+    // latency-bound reduction and the bandwidth-bound resolve of one lane fill in under the atomic-rate-bound splat of the
+    // other.
+    const int sets = n_frames > 1 ? zbuf_sets : 1;
+    std::unique_lock<std::mutex> aux_lock(g_aux_mutex, std::defer_lock);
     AuxStream *aux = nullptr;
-    if (int rc = aux_for_current_device(&aux)) return rc;
-    unsigned long long *zb = reinterpret_cast<unsigned long long *>(zbuf);
+    cudaStream_t lane[2] = {st, st};
     ViewPack pack{};
     pack.n = 1;
     const int64_t sums_stride = 4 + MDVT_REDUCE_SCRATCH_DOUBLES;
-    const int64_t plane = mdvt_touched_bytes(out_w, out_h) / 2;
-    // the "last CTA finishes" counters of the centroid kernels (last scratch double of every frame) and both planes of
-    // touched flags: zeroed on the caller's stream before the fork
+    const int64_t plane = mdvt_touched_bytes(out_w, out_h) / 2, out_n = (int64_t)out_w * out_h;
+    // the "last CTA finishes" counters of the centroid kernels (last scratch double of every frame) and the touched flags:
+    // zeroed on the caller's stream before the fork
     MDVT_CUDA_TRY(cudaMemset2DAsync(sums_dev + sums_stride - 1, sums_stride * sizeof(double), 0, sizeof(double), n_frames, st));
-    MDVT_CUDA_TRY(cudaMemsetAsync(touched, 0, 2 * plane, st));
-    MDVT_CUDA_TRY(cudaEventRecord(aux->fork, st));
-    MDVT_CUDA_TRY(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
-    auto centroid_of = [&](int f) -> int {
-        const uint8_t *dsrc = static_cast<const uint8_t *>(depth_src) + f * depth_frame_stride;
-        if (f >= kAhead) MDVT_CUDA_TRY(cudaStreamWaitEvent(aux->stream, aux->frame_done[(f - kAhead) % kRing], 0));
-        if (int rc = launch_centroid_lookat(dsrc, centroid_src, K_host, poses_host ? poses_host + 16 * (int64_t)f : nullptr, look,
-                                            sums_dev + f * sums_stride, views_dev + f, aux->stream))
-            return rc;
-        MDVT_CUDA_TRY(cudaEventRecord(aux->centroid_done[f % kRing], aux->stream));
-        return MDVT_OK;
-    };
+    MDVT_CUDA_TRY(cudaMemsetAsync(touched, 0, 2 * plane * sets, st));
+    if (sets == 2) {
+        aux_lock.lock();
+        if (int rc = aux_for_current_device(&aux)) return rc;
+        lane[1] = aux->stream;
+        MDVT_CUDA_TRY(cudaEventRecord(aux->fork, st));
+        MDVT_CUDA_TRY(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
+    }
     for (int f = 0; f < n_frames; ++f) {
+        const int set = f % sets, use = f / sets;
+        cudaStream_t ls = lane[set];
         const uint8_t *dsrc = static_cast<const uint8_t *>(depth_src) + f * depth_frame_stride;
-        if (int rc = centroid_of(f)) return rc;
-        MDVT_CUDA_TRY(cudaStreamWaitEvent(st, aux->centroid_done[f % kRing], 0));
-        uint8_t *cur = touched + (f & 1) * plane, *other = touched + ((f + 1) & 1) * plane;
-        if (int rc = launch_project_splat(dsrc, src, pack, views_dev + f, near_plane, out_w, out_h, 0, zb, nullptr, st, cur,
-                                          colour_rgb + f * colour_frame_stride))
+        unsigned long long *zb = reinterpret_cast<unsigned long long *>(zbuf) + (int64_t)set * out_n;
+        if (int rc = launch_centroid_lookat(dsrc, centroid_src, K_host, poses_host ? poses_host + 16 * (int64_t)f : nullptr, look,
+                                            sums_dev + f * sums_stride, views_dev + f, ls))
+            return rc;
+        uint8_t *lane_touched = touched + (int64_t)set * 2 * plane;
+        uint8_t *cur = lane_touched + (use & 1) * plane, *other = lane_touched + ((use + 1) & 1) * plane;
+        const uint32_t epoch = 254u - (uint32_t)(use % 254);
+        if (int rc = launch_project_splat(dsrc, src, pack, views_dev + f, near_plane, out_w, out_h, 0, zb, nullptr, ls, cur,
+                                          colour_rgb + f * colour_frame_stride, epoch))
             return rc;
         auto at = [&](const mdvt_plane_layout *L) -> uint8_t * {
             return (L && L->base) ? static_cast<uint8_t *>(L->base) + f * L->frame_stride : nullptr;
         };
-        if (int rc = launch_resolve_ckey(zb, out_w, out_h, bg_rgb, fill_rgb, flags | MDVT_FLAG_RESET_ZBUF, at(rgb_out), rgb_out->row_pitch,
-                                         at(mask_out), mask_out ? mask_out->row_pitch : 0, nullptr, 0, st, cur, other, 1, ViewStrides{0, 0, 0, 0}))
+        if (int rc = launch_resolve_ckey(zb, out_w, out_h, bg_rgb, fill_rgb, flags, at(rgb_out), rgb_out->row_pitch, at(mask_out),
+                                         mask_out ? mask_out->row_pitch : 0, nullptr, 0, ls, cur, other, 1, ViewStrides{0, 0, 0, 0}, epoch))
             return rc;
-        MDVT_CUDA_TRY(cudaEventRecord(aux->frame_done[f % kRing], st));
+        if (use % 254 == 253 || f + sets >= n_frames)  // epoch byte used up / the lane's last frame: the plane goes back to all ones
+            if (int rc = mdvt_zbuf_clear(reinterpret_cast<uint64_t *>(zb), out_n, ls)) return rc;
+    }
+    if (sets == 2) {
+        MDVT_CUDA_TRY(cudaEventRecord(aux->join, aux->stream));
+        MDVT_CUDA_TRY(cudaStreamWaitEvent(st, aux->join, 0));
     }
     return MDVT_OK;
 }

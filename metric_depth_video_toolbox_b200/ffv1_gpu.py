@@ -259,8 +259,11 @@ class GpuFfv1Writer:
 
     def __init__(self, path: str, fps: float, size: Tuple[int, int], device=None, batch: int = 8,
                  slices: Optional[Tuple[int, int]] = None, alpha: bool = False, join_on_close: bool = True, depth: int = 2,
-                 context_model: int = 0):
-        """join_on_close=False: `path` is one rank's segment of a torchrun job; close() leaves `<path>.plan.json` next to
+                 context_model: int = 1):
+        """context_model 1 (default): the 63-context quant table -- 1 KB instead of 10.6 KB of coder state per slice thread,
+        ~40 % more frames/s on the B200 and files within -0.5 .. +1 % of the 666-context ones (the tables travel in the
+        configuration record: any FFV1 decoder reads either); 0: libavcodec's own tables.
+        join_on_close=False: `path` is one rank's segment of a torchrun job; close() leaves `<path>.plan.json` next to
         it in video_io.ParallelWriter's format, and rank 0 stitches the segments at packet level (video_io.join_plans)."""
         import queue
         import threading

@@ -10,6 +10,7 @@ one small D2H copy, NumPy look-at matrices, splat + resolve per frame) kept as t
 camera."""
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
@@ -90,8 +91,9 @@ class NovelViewRenderer:
             out_rgb = torch.empty((n, h, w, 3), dtype=torch.uint8, device=dev)
         if out_mask is None:
             out_mask = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
-        if self._zbuf is None or tuple(self._zbuf.shape) != (1, h, w) or self._zbuf.device != dev:
-            self._zbuf = ops.new_zbuf(1, w, h, dev)
+        sets = 1 if os.environ.get("MDVT_ZBUF_SETS", "2") == "1" else 2   # two planes: frames alternate between two streams
+        if self._zbuf is None or tuple(self._zbuf.shape) != (sets, h, w) or self._zbuf.device != dev:
+            self._zbuf = ops.new_zbuf(sets, w, h, dev)
         return n, h, w, out_rgb, out_mask
 
     def render_device(self, depth_rgb: torch.Tensor, colour: torch.Tensor, start_frame: int = 0, out_rgb: Optional[torch.Tensor] = None,
@@ -104,7 +106,7 @@ class NovelViewRenderer:
         if self._sums is None or self._sums.shape[0] < n or self._sums.device != depth_rgb.device:
             self._sums = torch.empty((n, stride), dtype=torch.float64, device=depth_rgb.device)
             self._views = torch.empty((n, 16), dtype=torch.float32, device=depth_rgb.device)
-            self._touched = torch.empty(int(_lib.load().mdvt_touched_bytes(w, h)), dtype=torch.uint8, device=depth_rgb.device)
+            self._touched = torch.empty(2 * int(_lib.load().mdvt_touched_bytes(w, h)), dtype=torch.uint8, device=depth_rgb.device)
         src_c = ops.make_source(w, h, self.K, p.max_depth, "D1", True, 1.0, p.of_by_one)
         src = ops.make_source(w, h, self.K, p.max_depth, "D1", True, 1.0, False)
         poses = None if p.transformations is None else np.stack([self._pose(start_frame + k) for k in range(n)])
@@ -121,7 +123,7 @@ class NovelViewRenderer:
         centres = self.centroids(depth_rgb, start_frame)
         src = ops.make_source(w, h, self.K, p.max_depth, "D1", True, 1.0, False)
         views = [[self.view_of(start_frame + k, centres[k])] for k in range(n)]
-        ops.render_views(depth_rgb, colour, [src], views, w, h, self._zbuf, out_rgb, out_mask, None, p.bg_rgb, p.bg_rgb, 0, p.near)
+        ops.render_views(depth_rgb, colour, [src], views, w, h, self._zbuf[:1], out_rgb, out_mask, None, p.bg_rgb, p.bg_rgb, 0, p.near)
         return out_rgb, out_mask
 
     def render_host(self, depth_rgb, colour, out_rgb=None):

@@ -347,7 +347,8 @@ def render_views(depth_src: torch.Tensor, colour: torch.Tensor, sources: Sequenc
     """The generic frame loop in ONE library call: frames (n, H, W, 3) u8 (or (n, H, W) f32 for F32 sources),
     `sources` one per frame or a single one, `views[f]` the cameras of frame f (same count for every frame).
     Views are laid side by side: out_rgb (n, out_h, n_views*out_w, 3) u8, out_mask (n, out_h, n_views*out_w[, 3]) u8,
-    out_depth (n, out_h, n_views*out_w) f32.  The z-buffer (n_views, out_h, out_w) must be empty and is left empty."""
+    out_depth (n, out_h, n_views*out_w) f32.  The z-buffer (n_views or 2*n_views, out_h, out_w) must be empty and is left
+    empty; with two sets of planes the odd frames run on the library's second stream next to the even ones."""
     n = depth_src.shape[0]
     packed = isinstance(views, np.ndarray)   # (n, n_views, 16) float32 from pack_views + SOURCE_DTYPE records from pack_sources
     if packed:
@@ -363,8 +364,9 @@ def render_views(depth_src: torch.Tensor, colour: torch.Tensor, sources: Sequenc
         raise ValueError("sources must hold one entry or one per frame")
     _need(colour, torch.uint8, "colour")
     _need(zbuf, torch.int64, "zbuf")
-    if tuple(zbuf.shape) != (n_views, out_h, out_w):
-        raise ValueError(f"zbuf shape {tuple(zbuf.shape)} != ({n_views}, {out_h}, {out_w})")
+    if tuple(zbuf.shape) not in ((n_views, out_h, out_w), (2 * n_views, out_h, out_w)):
+        raise ValueError(f"zbuf shape {tuple(zbuf.shape)} != ({n_views} or {2 * n_views}, {out_h}, {out_w})")
+    zbuf_sets = zbuf.shape[0] // n_views   # two sets: odd frames run on the library's second stream next to the even ones
     if packed:
         src_w, src_h = int(sources["width"][0]), int(sources["height"][0])
         f32_src = int(sources["decoder"][0]) == _lib.SOURCE_F32
@@ -391,7 +393,7 @@ def render_views(depth_src: torch.Tensor, colour: torch.Tensor, sources: Sequenc
     opt = lambda l: None if l is None else C.byref(l)  # noqa: E731
     _lib.check(_lib.load().mdvt_render_views(_ptr(depth_src), depth_src.stride(0) * depth_src.element_size(), _ptr(colour),
                                              colour.stride(0), n, src_arr, int(len(sources) == n and n > 1), view_arr, n_views,
-                                             float(np.float32(near)), int(out_w), int(out_h), _ptr(zbuf), pack_rgb(bg_rgb), pack_rgb(fill_rgb),
+                                             float(np.float32(near)), int(out_w), int(out_h), _ptr(zbuf), int(zbuf_sets), pack_rgb(bg_rgb), pack_rgb(fill_rgb),
                                              flags, C.byref(rgb_l), opt(mask_l), opt(depth_l), _stream()))
     return out_rgb, out_mask, out_depth
 
@@ -412,8 +414,9 @@ def novel_view_frames(depth_src: torch.Tensor, colour: torch.Tensor, centroid_so
         raise ValueError("depth_src must be contiguous")
     _need(colour, torch.uint8, "colour")
     _need(zbuf, torch.int64, "zbuf")
-    if tuple(zbuf.shape) != (1, h, w):
-        raise ValueError(f"zbuf shape {tuple(zbuf.shape)} != (1, {h}, {w})")
+    if tuple(zbuf.shape) not in ((1, h, w), (2, h, w)):
+        raise ValueError(f"zbuf shape {tuple(zbuf.shape)} != (1 or 2, {h}, {w})")
+    zbuf_sets = zbuf.shape[0]   # two planes: odd frames run on the library's second stream next to the even ones
     if colour.shape[0] != n or colour.shape[1] * colour.shape[2] != w * h:
         raise ValueError("colour must hold one (H, W, 3) frame per depth frame")
     dev = depth_src.device
@@ -424,7 +427,7 @@ def novel_view_frames(depth_src: torch.Tensor, colour: torch.Tensor, centroid_so
         views_dev = torch.empty((n, 16), dtype=torch.float32, device=dev)
     if tuple(_need(sums, torch.float64, "sums").shape) != (n, stride) or tuple(_need(views_dev, torch.float32, "views_dev").shape) != (n, 16):
         raise ValueError("sums must be (n, 4 + scratch) float64 and views_dev (n, 16) float32")
-    need = int(_lib.load().mdvt_touched_bytes(w, h))
+    need = zbuf_sets * int(_lib.load().mdvt_touched_bytes(w, h))
     if touched is None:
         touched = torch.empty(need, dtype=torch.uint8, device=dev)
     if _need(touched, torch.uint8, "touched").numel() < need:
@@ -448,7 +451,7 @@ def novel_view_frames(depth_src: torch.Tensor, colour: torch.Tensor, centroid_so
     mask_l = _plane_layout(None if out_mask is None else _need(out_mask, torch.uint8, "out_mask"), n, 1, h, w, mask_ch, "out_mask")
     _lib.check(_lib.load().mdvt_novel_view_frames(_ptr(depth_src), depth_src.stride(0) * depth_src.element_size(), _ptr(colour), colour.stride(0),
                                                   n, C.byref(centroid_source), C.byref(source), _k4(K), pose_arr, C.byref(look),
-                                                  float(np.float32(near)), w, h, _ptr(zbuf), _ptr(sums), _ptr(views_dev), _ptr(touched), pack_rgb(bg_rgb),
+                                                  float(np.float32(near)), w, h, _ptr(zbuf), int(zbuf_sets), _ptr(sums), _ptr(views_dev), _ptr(touched), pack_rgb(bg_rgb),
                                                   pack_rgb(fill_rgb), flags, C.byref(rgb_l), None if mask_l is None else C.byref(mask_l),
                                                   _stream()))
     return out_rgb, out_mask, sums, views_dev
@@ -673,6 +676,30 @@ def normal_march_infill(image: torch.Tensor, hole_mask: torch.Tensor, mask_img: 
     _lib.check(_lib.load().mdvt_normal_march_infill(_ptr(image), image.stride(0), _ptr(hole_mask), hole_mask.stride(0), _ptr(mask_img),
                                                     mask_img.stride(0), w, h, int(max_steps), _stream()))
     return image
+
+
+def pack_mask_bits(mask: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(..., W) u8 hole mask {0, 255} -> (..., W / 8) u8, one bit per pixel, most significant bit first (np.packbits order).
+    W must be a multiple of 8 so that rows stay byte aligned."""
+    _need(mask, torch.uint8, "mask")
+    if mask.shape[-1] % 8:
+        raise ValueError("the mask width must be a multiple of 8")
+    shape = tuple(mask.shape[:-1]) + (mask.shape[-1] // 8,)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.uint8, device=mask.device)
+    if tuple(_need(out, torch.uint8, "out").shape) != shape:
+        raise ValueError(f"out must be {shape}")
+    _lib.check(_lib.load().mdvt_pack_mask_bits(_ptr(mask), mask.numel(), _ptr(out), _stream()))
+    return out
+
+
+def unpack_mask_bits(bits, width: Optional[int] = None) -> np.ndarray:
+    """Host side of pack_mask_bits: (..., W / 8) u8 (NumPy array or CPU tensor) -> (..., W) u8 {0, 255}."""
+    arr = bits.numpy() if isinstance(bits, torch.Tensor) else np.asarray(bits)
+    out = np.unpackbits(arr, axis=-1)
+    if width is not None:
+        out = out[..., :width]
+    return out * np.uint8(255)
 
 
 def normal_march_infill_f32(image: torch.Tensor, hole_mask: torch.Tensor, normal_map: torch.Tensor, max_steps: int = 400) -> torch.Tensor:

@@ -49,6 +49,45 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
     return rank, world_size, local_rank
 
 
+def bind_host_to_gpu(local_rank: int, local_world: int = 1) -> dict:
+    """Best-effort host locality for one-process-per-GPU jobs: the calling process is restricted to the CPU cores NVML
+    reports as local to GPU `local_rank` (its PCIe root's socket), so that the pinned staging buffers it allocates
+    afterwards are first touched -- and therefore placed -- on that socket's memory.  When NVML reports the same core
+    set for every GPU (one NUMA node visible, as inside a VM) and several ranks share the box, the cores are split evenly
+    between the ranks instead, so that the ranks' copy threads do not migrate over each other.  Returns what was done
+    (reported by bench.py); never raises."""
+    info = {"cores_before": None, "cores_after": None, "source": "unchanged"}
+    try:
+        before = sorted(os.sched_getaffinity(0))
+        info["cores_before"] = len(before)
+        local = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            handle = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            words = pynvml.nvmlDeviceGetCpuAffinity(handle, (max(before) // 64) + 1)
+            local = [c for c in before if (words[c // 64] >> (c % 64)) & 1]
+            try:
+                info["numa_node"] = int(pynvml.nvmlDeviceGetNumaNodeId(handle))
+            except Exception:  # older drivers / VMs
+                pass
+        except Exception as exc:  # NVML not usable: keep the inherited mask
+            info["nvml"] = f"{type(exc).__name__}"
+        chosen, source = before, "unchanged"
+        if local and len(local) < len(before):
+            chosen, source = local, "nvml cpu affinity of the GPU"
+        elif local_world > 1 and len(before) >= 2 * local_world:
+            per = len(before) // local_world
+            chosen, source = before[local_rank * per:(local_rank + 1) * per], "even split of the visible cores (no topology exposed)"
+        if chosen != before:
+            os.sched_setaffinity(0, set(chosen))
+        info.update(cores_after=len(chosen), source=source)
+    except Exception as exc:  # noqa: BLE001
+        info["error"] = f"{type(exc).__name__}: {exc}"
+    return info
+
+
 def frame_range(n_frames: int, rank: Optional[int] = None, world_size: Optional[int] = None, align: int = 1) -> Tuple[int, int]:
     """Contiguous [start, stop) of `rank`: ranges differ by at most one frame (one block of `align` frames), concatenate
     in rank order to [0, n_frames), and are empty only when there are fewer frames (blocks) than ranks.  align > 1 puts

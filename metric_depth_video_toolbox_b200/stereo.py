@@ -13,6 +13,7 @@ double-buffered H2D -> kernel -> D2H pipeline (`render_host`).  There is no CPU 
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
 
@@ -182,25 +183,33 @@ class StereoRerenderer:
         # generic path: per frame K1+K2 into a persistent 2-view z-buffer, K3 for both eyes straight into the SBS halves
         zkey = torch.cuda.current_stream(depth_rgb.device).cuda_stream
         zbuf = self._zbufs.get(zkey)
-        if zbuf is None or tuple(zbuf.shape) != (2, h, w) or zbuf.device != depth_rgb.device:
-            zbuf = self._zbufs[zkey] = ops.new_zbuf(2, w, h, depth_rgb.device)
+        sets = 1 if os.environ.get("MDVT_ZBUF_SETS", "2") == "1" else 2   # two sets of planes: frames alternate between two streams
+        if zbuf is None or tuple(zbuf.shape) != (2 * sets, h, w) or zbuf.device != depth_rgb.device:
+            zbuf = self._zbufs[zkey] = ops.new_zbuf(2 * sets, w, h, depth_rgb.device)
         ops.render_views(depth_rgb, colour, sources, views, w, h, zbuf, out_sbs, out_mask, out_depth, p.bg_rgb, (0, 0, 0), flags, p.near)
         return out_sbs, out_mask
 
     # ---- host arrays, pipelined -----------------------------------------------------------------------
-    def render_host(self, depth_rgb, colour, out_sbs=None, out_mask=None, start_frame: int = 0, chunk_frames: int = 8):
+    def render_host(self, depth_rgb, colour, out_sbs=None, out_mask=None, start_frame: int = 0, chunk_frames: int = 8,
+                    mask_format: str = "u8"):
         """depth_rgb / colour: (n, H, W, 3) u8 host arrays (NumPy or CPU tensors; pinned memory makes the
         copies asynchronous).  Frames stream through `chunk_frames`-sized device staging buffers on two
         CUDA streams so H2D, the kernels and D2H overlap.  Returns host tensors (sbs, mask); it waits for the last copy,
-        so the returned buffers are complete."""
+        so the returned buffers are complete.
+        mask_format "bits": the hole mask crosses PCIe as one bit per pixel -- (n, H, 2W/8) u8, most significant bit
+        first; `ops.unpack_mask_bits` (numpy.unpackbits) gives the u8 {0, 255} plane back.  It takes the mask's share of the
+        device-to-host bytes from 25 % to 4 % (the host link, not the kernel, bounds this call); plain u8 masks only."""
         p = self.p
         d_host = torch.as_tensor(depth_rgb)
         c_host = torch.as_tensor(colour)
         n, h, w, _ = d_host.shape
+        bits = mask_format == "bits"
+        if mask_format not in ("u8", "bits") or (bits and (p.mask_rgb or not p.infill_mask or (2 * w) % 8)):
+            raise ValueError("mask_format is 'u8' or 'bits' (bits: u8 masks of a width that is a multiple of 8)")
         if out_sbs is None:
             out_sbs = torch.empty((n, h, 2 * w, 3), dtype=torch.uint8, pin_memory=True)
         if out_mask is None and p.infill_mask:
-            out_mask = torch.empty((n, h, 2 * w) + ((3,) if p.mask_rgb else ()), dtype=torch.uint8, pin_memory=True)
+            out_mask = torch.empty((n, h, 2 * w // 8) if bits else (n, h, 2 * w) + ((3,) if p.mask_rgb else ()), dtype=torch.uint8, pin_memory=True)
         out_sbs_t, out_mask_t = torch.as_tensor(out_sbs), (None if out_mask is None else torch.as_tensor(out_mask))
         chunk = max(1, min(chunk_frames, n))
         n_slots = 2
@@ -217,7 +226,11 @@ class StereoRerenderer:
                 self.render_device(s["d"][:cnt], s["c"][:cnt], start_frame + f0, s["sbs"][:cnt],
                                    None if s["mask"] is None else s["mask"][:cnt])
                 out_sbs_t[f0:f0 + cnt].copy_(s["sbs"][:cnt], non_blocking=True)
-                if out_mask_t is not None:
+                if out_mask_t is not None and bits:
+                    if s.get("bits") is None:
+                        s["bits"] = torch.empty((chunk, h, 2 * w // 8), dtype=torch.uint8, device=self.device)
+                    out_mask_t[f0:f0 + cnt].copy_(ops.pack_mask_bits(s["mask"][:cnt], s["bits"][:cnt]), non_blocking=True)
+                elif out_mask_t is not None:
                     out_mask_t[f0:f0 + cnt].copy_(s["mask"][:cnt], non_blocking=True)
         for s in slots:
             caller.wait_stream(s["stream"])

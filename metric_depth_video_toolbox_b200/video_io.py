@@ -324,6 +324,115 @@ class ChunkReader:
             self.close()
 
 
+class DeviceChunkReader:
+    """ChunkReader for clips this package wrote (ffv1_gpu.GpuFfv1Writer: FFV1 v3, every frame a key frame, ~1000 slices):
+    the packets go from the file to the device and are decoded there, one thread per slice (`mdvt_ffv1_decode_frames`), so
+    no decoded pixel ever exists on the host.  Same iteration protocol as ChunkReader -- (n, [tensor or None per path]) --
+    but the tensors are CUDA tensors (n, H, W, 3) u8 RGB, or (n, H, W) grey for `grey` inputs (OpenCV's 8-bit BGR2GRAY,
+    computed on the device).  A background thread stays `depth` chunks ahead on its own stream; a yielded chunk is
+    complete and stays valid until the next one is asked for.  Raises `_lib.MdvtError` from `probe` / the constructor when
+    a file is not such a stream (callers fall back to ChunkReader: open_chunk_reader)."""
+
+    def __init__(self, paths: Sequence[Optional[str]], start: int = 0, stop: Optional[int] = None, chunk: int = 8, depth: int = 2,
+                 grey: Sequence[bool] = (), device=None):
+        from . import ffv1_gpu
+
+        self.paths = list(paths)
+        self.grey = list(grey) + [False] * (len(self.paths) - len(grey))
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.chunk = max(1, chunk)
+        self._readers = [None if p is None else ffv1_gpu.GpuFfv1Reader(p, self.device, batch=self.chunk, rgb=True) for p in self.paths]
+        first = next(r for r in self._readers if r is not None)
+        self.width, self.height = first.width, first.height
+        total = min(r.frames for r in self._readers if r is not None)
+        self.start, self.stop = start, total if stop is None else min(stop, total)
+        self._q: "queue.Queue" = queue.Queue(maxsize=max(1, depth))
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, name="mdvt-device-reader", daemon=True)
+        self._thread.start()
+
+    @staticmethod
+    def _to_grey(rgb: torch.Tensor) -> torch.Tensor:
+        """cv2.cvtColor(BGR2GRAY) of 8-bit frames: (R*9798 + G*19235 + B*3735 + 2^14) >> 15, OpenCV's 15-bit fixed-point
+        weights (checked against cv2 4.13 on every third value of each channel: identical)."""
+        x = rgb.to(torch.int32)
+        return ((x[..., 0] * 9798 + x[..., 1] * 19235 + x[..., 2] * 3735 + 16384) >> 15).to(torch.uint8)
+
+    def _run(self):
+        try:
+            torch.cuda.set_device(self.device)
+            stream = torch.cuda.Stream(device=self.device)
+            with torch.cuda.stream(stream):
+                for a in range(self.start, self.stop, self.chunk):
+                    if self._stop.is_set():
+                        return
+                    b = min(a + self.chunk, self.stop)
+                    bufs = []
+                    for r, g in zip(self._readers, self.grey):
+                        if r is None:
+                            bufs.append(None)
+                            continue
+                        frames = r.dec.decode([r._pk.payload(k) for k in range(a, b)], rgb=True)   # a fresh tensor, complete on return
+                        bufs.append(self._to_grey(frames) if g else frames)
+                    stream.synchronize()
+                    while not self._stop.is_set():
+                        try:
+                            self._q.put((b - a, bufs), timeout=0.05)
+                            break
+                        except queue.Full:
+                            continue
+            self._q_put_end(None)
+        except BaseException as exc:  # surfaced on the consumer side
+            self._q_put_end(exc)
+
+    def _q_put_end(self, item):
+        while not self._stop.is_set():
+            try:
+                self._q.put(("end", item), timeout=0.05)
+                return
+            except queue.Full:
+                continue
+
+    def close(self):
+        self._stop.set()
+        if self._thread is not threading.current_thread():
+            self._thread.join()
+        for r in self._readers:
+            if r is not None:
+                r.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __iter__(self):
+        try:
+            while True:
+                n, bufs = self._q.get()
+                if n == "end":
+                    if bufs is not None:
+                        raise bufs
+                    return
+                yield n, bufs
+        finally:
+            self.close()
+
+
+def open_chunk_reader(paths: Sequence[Optional[str]], start: int = 0, stop: Optional[int] = None, chunk: int = 8, depth: int = 3,
+                      pin: bool = True, grey: Sequence[bool] = (), decoders: int = 1, device=None):
+    """The reader of the script front ends: DeviceChunkReader when every input is an all-key-frame FFV1 stream of this
+    package (the frames then never touch host memory), ChunkReader (cv2.VideoCapture threads, pinned host chunks) for
+    everything else -- files written by the reference's tools included.  MDVT_FFV1_READER=host forces the latter."""
+    if torch.cuda.is_available() and os.environ.get("MDVT_FFV1_READER", "") != "host":
+        try:
+            return DeviceChunkReader(paths, start, stop, chunk=chunk, depth=min(depth, 2), grey=grey, device=device)
+        except Exception:  # noqa: BLE001 - not (all) device-decodable streams (another container, codec, slice layout, GOP > 1):
+            pass           # the host reader takes over and reports whatever is really wrong with the files
+    return ChunkReader(paths, start, stop, chunk=chunk, depth=depth, pin=pin, grey=grey, decoders=decoders)
+
+
 class ChunkWriter:
     """cv2.VideoWriter on a background thread.  `write(frames_rgb)` takes a (n, H, W, 3) uint8 host tensor /
     array in RGB order (or BGR with rgb=False, as the depth encoder produces) and returns immediately; the
@@ -375,9 +484,13 @@ GOP = 12  # key-frame interval of OpenCV's FFmpeg writer (AVCodecContext.gop_siz
 
 
 def gpu_ffv1_requested(flag: bool = False) -> bool:
-    """FFV1 result videos coded on the device (ffv1_gpu.GpuFfv1Writer) instead of by cv2.VideoWriter lanes: asked for by a
-    front end's --gpu_ffv1 or by MDVT_FFV1_WRITER=gpu in the environment."""
-    return bool(flag) or os.environ.get("MDVT_FFV1_WRITER", "") == "gpu"
+    """FFV1 result videos coded on the device (ffv1_gpu.GpuFfv1Writer) instead of by cv2.VideoWriter lanes on host cores: the
+    default wherever a CUDA device is present (the rendered frames then leave the device as packets only); a front end's
+    --gpu_ffv1 or MDVT_FFV1_WRITER=gpu asks for it explicitly, MDVT_FFV1_WRITER=host keeps the host lanes."""
+    env = os.environ.get("MDVT_FFV1_WRITER", "")
+    if env == "host":
+        return False
+    return bool(flag) or env == "gpu" or torch.cuda.is_available()
 
 
 def default_lanes(world_size: int = 1) -> int:

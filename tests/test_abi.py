@@ -84,8 +84,9 @@ def test_argument_validation_without_a_device():
     assert lib.mdvt_project_points_f64(None, 5, None, None, None) == -1
     assert lib.mdvt_depth_sum(None, 16, 9, 1, 1.0, None, 240, None, None) == -1  # unknown decoder
     assert lib.mdvt_centroid(None, C.byref(src), None, None, None, None) == -1
-    assert lib.mdvt_render_views(None, 0, None, 0, 0, None, 0, None, 2, 1e-4, 4, 4, None, 0, 0, 0, None, None, None, None) == 0
-    assert lib.mdvt_render_views(None, 0, None, 0, 1, None, 0, None, 9, 1e-4, 4, 4, None, 0, 0, 0, None, None, None, None) == -1
+    assert lib.mdvt_render_views(None, 0, None, 0, 0, None, 0, None, 2, 1e-4, 4, 4, None, 1, 0, 0, 0, None, None, None, None) == 0
+    assert lib.mdvt_render_views(None, 0, None, 0, 1, None, 0, None, 2, 1e-4, 4, 4, None, 3, 0, 0, 0, None, None, None, None) == -1  # zbuf_sets
+    assert lib.mdvt_render_views(None, 0, None, 0, 1, None, 0, None, 9, 1e-4, 4, 4, None, 1, 0, 0, 0, None, None, None, None) == -1
     assert lib.mdvt_resolve(None, None, 4, 4, 0, 0, 0, None, 0, None, 0, None, 0, None, None) == -1
     assert lib.mdvt_stereo_conv_rows(None, None, 1, 5000, 4, None, 0, 0, 0, None, None, None, None) == -2  # column does not fit 12 bits
     assert lib.mdvt_stereo_conv_rows(None, None, 0, 64, 4, None, 0, 0, 0, None, None, None, None) == 0

@@ -99,3 +99,36 @@ def test_stereo_rows_key_order_equals_z_order():
         c16 = np.arange(65536, dtype=np.uint32)
         z = ((c16 << 16).astype(np.float32) * np.float32(dec)) * np.float32(scale)
         assert np.all(np.diff(z.astype(np.float64)) > 0)
+
+
+@pytest.mark.parametrize("size,band", [((1920, 1080), None), ((3840, 2160), (1000, 1128))])
+def test_generic_view_model_vs_oracle_at_full_size(size, band):
+    """VERDICT r1 #8a: the float32 model of the generic path against the float64 oracle at BASELINE's sizes -- the whole
+    1080p frame and a 128-row band of the 4K frame (the band's rows carry their true row numbers), posed stereo camera.
+    Coordinates within 1e-4 relative; every differing winner explained by a rounding boundary / z tie."""
+    w, h = size
+    depth_rgb, _ = SyntheticClip(w, h, 4, zero_fraction=0.005).frame(2)
+    K = orc.camera_matrix(60.0, None, w, h)
+    scale = orc.master_fov_depth_scale(45.0, 60.0)
+    T = np.eye(4)
+    T[:3, :3] = orc.rot_y(0.01)
+    T[:3, 3] = (0.05, -0.02, 0.1)
+    M = orc.eye_pose("left", 0.063, 0.008) @ T
+    u64, v64, z64 = orc.view_uvz(depth_rgb, 100, K, M, depth_scale=scale)
+    src = km.source_constants(w, h, K, 100, depth_scale=scale)
+    u32, v32, z32 = km.view_uvz_f32(depth_rgb, src, M, (K[0, 0], K[1, 1], K[0, 2], K[1, 2]))
+    if band is not None:   # keep the rows of the band only (as sources): targets still span the whole frame
+        keep = np.zeros((h, w), bool)
+        keep[band[0]:band[1]] = True
+        keep = keep.reshape(-1)
+        z64 = np.where(keep, z64, 0.0)
+        z32 = np.where(keep, z32, np.float32(0.0))
+    ok = z64 > orc.NEAR_PLANE
+    assert rel_err(z32[ok], z64[ok], 1e-6).max() < REL_TOL
+    assert rel_err(u32[ok], u64[ok], 1.0).max() < REL_TOL and rel_err(v32[ok], v64[ok], 1.0).max() < REL_TOL
+    assert np.abs(u32[ok] - u64[ok]).max() < 1e-3 and np.abs(v32[ok] - v64[ok]).max() < 1e-3   # absolute: a thousandth of a pixel
+    ids64 = orc.splat_ids(u64, v64, z64, w, h)
+    ids32 = km.splat_ids_f32(u32, v32, z32, w, h)
+    n_diff, unexplained = boundary_explained(u64, v64, z64, ids32, ids64, w, h)
+    assert unexplained == 0
+    assert n_diff <= max(4, int(2e-3 * int(ok.sum())))

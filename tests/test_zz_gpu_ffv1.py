@@ -94,7 +94,8 @@ def test_rejects_host_tensors_and_bad_sizes():
 
 
 def test_cli_stereo_rerender_with_gpu_writer_equals_default_writer(tmp_path, depth_video=True):
-    """stereo_rerender --gpu_ffv1 writes the same frames (main, mask and SBS depth video) as the default host writers.
+    """stereo_rerender (result videos coded on the device: the default) writes the same frames (main, mask and SBS depth
+    video) as with the host writers (MDVT_FFV1_WRITER=host).
     Without --create_sbs_depth_video the front end hands the device tensors of the row kernel straight to the coder."""
     import stereo_rerender   # the root-level launcher
     from metric_depth_video_toolbox_b200 import video_io
@@ -108,11 +109,17 @@ def test_cli_stereo_rerender_with_gpu_writer_equals_default_writer(tmp_path, dep
     argv = ["--depth_video", dpath, "--color_video", cpath, "--xfov", "60", "--infill_mask", "--green_and_black_infill_mask",
             "--dont_place_points_in_edges", "--chunk_frames", "3"] + (["--create_sbs_depth_video"] if depth_video else [])
     names = [dpath + "_stereo.mkv", dpath + "_stereo.mkv_infillmask.mkv"] + ([dpath + "_stereo.mkv_depth.mkv"] if depth_video else [])
-    assert stereo_rerender.main(argv) == 0
+    os.environ["MDVT_FFV1_WRITER"] = "host"   # the reference's writers (cv2.VideoWriter lanes); the device coder is the default
+    try:
+        assert stereo_rerender.main(argv) == 0
+    finally:
+        os.environ.pop("MDVT_FFV1_WRITER", None)
     want = [video_io.read_clip(p) for p in names]
+    assert not mkv_packets_all_key(names[0])
     for p in names:
         os.remove(p)
-    assert stereo_rerender.main(argv + ["--gpu_ffv1"]) == 0
+    assert stereo_rerender.main(argv) == 0     # default: coded on the device
+    assert mkv_packets_all_key(names[0])
     for p, ref in zip(names, want):
         got = video_io.read_clip(p)
         assert ref.shape[0] == n and got.shape == ref.shape and np.array_equal(got, ref), p
@@ -235,7 +242,9 @@ def test_view_depthfile_and_save_depth_video_with_gpu_writer_equal_default_write
     video_io.write_clip(cpath, colour, 24.0)
     view = importlib.import_module("3d_view_depthfile")
     argv = ["--depth_video", dpath, "--color_video", cpath, "--xfov", "60", "--render", "--chunk_frames", "3"]
+    monkeypatch.setenv("MDVT_FFV1_WRITER", "host")
     assert view.main(argv) == 0
+    monkeypatch.delenv("MDVT_FFV1_WRITER")
     want = video_io.read_clip(dpath + "_render.mkv")
     os.remove(dpath + "_render.mkv")
     assert view.main(argv + ["--gpu_ffv1"]) == 0
@@ -245,10 +254,10 @@ def test_view_depthfile_and_save_depth_video_with_gpu_writer_equal_default_write
     rng = np.random.default_rng(5)
     metres = rng.uniform(0.2, 60, (n, 48, 64)).astype(np.float32)
     a, b = str(tmp_path / "host.mkv"), str(tmp_path / "gpu.mkv")
+    monkeypatch.setenv("MDVT_FFV1_WRITER", "host")
     dfh.save_depth_video(metres, a, 24.0, 100, 64, 48)
-    monkeypatch.setenv("MDVT_FFV1_WRITER", "gpu")
-    dfh.save_depth_video(metres, b, 24.0, 100, 64, 48)
     monkeypatch.delenv("MDVT_FFV1_WRITER")
+    dfh.save_depth_video(metres, b, 24.0, 100, 64, 48)   # default with a device: coded there
     fa, fb = video_io.read_clip(a), video_io.read_clip(b)
     assert fa.shape == (n, 48, 64, 3) and np.array_equal(fa, fb)
     assert mkv_packets_all_key(b) and not mkv_packets_all_key(a)
@@ -263,3 +272,114 @@ def mkv_packets_all_key(path):
         return all(key for _, _, key in pk.packets)
     finally:
         pk.close()
+
+
+def test_device_chunk_reader_yields_the_written_frames_and_falls_back_for_opencv_files(tmp_path):
+    """video_io.open_chunk_reader: inputs written by this package's writer are decoded on the device (CUDA chunks, never a
+    host pixel), in lock step over several inputs, with start / stop / chunking and the device BGR2GRAY; files written by
+    cv2.VideoWriter (what the reference's tools produce) go through the host reader with the same frames."""
+    from metric_depth_video_toolbox_b200 import video_io
+
+    w, h, n = 320, 192, 11
+    a, b = content(w, h, n, 1), content(w, h, n, 2)
+    pa, pb, pc = (str(tmp_path / f"{k}.mkv") for k in "abc")
+    for path, frames in ((pa, a), (pb, b)):
+        wr = ffv1_gpu.GpuFfv1Writer(path, 24.0, (w, h), device=DEV, batch=4)
+        wr.write(torch.from_numpy(frames).to(DEV))
+        assert wr.close() == n
+    rd = video_io.open_chunk_reader([pa, pb, None], 2, 10, chunk=3, grey=[False, True, False])
+    assert isinstance(rd, video_io.DeviceChunkReader)
+    got_a, got_b = [], []
+    for cnt, (ca, cb, none) in rd:
+        assert none is None and ca.is_cuda and cb.is_cuda and ca.shape[0] == cnt == cb.shape[0] and cb.dim() == 3
+        got_a.append(ca.cpu().numpy())
+        got_b.append(cb.cpu().numpy())
+    assert np.array_equal(np.concatenate(got_a), a[2:10])
+    want_grey = np.stack([cv2.cvtColor(cv2.cvtColor(f, cv2.COLOR_RGB2BGR), cv2.COLOR_BGR2GRAY) for f in b[2:10]])
+    assert np.array_equal(np.concatenate(got_b), want_grey)
+    # early exit: the background thread is stopped and joined by the generator's finally
+    rd = video_io.open_chunk_reader([pa], chunk=2)
+    for cnt, (ca,) in rd:
+        break
+    assert not rd._thread.is_alive()
+    # a file from cv2.VideoWriter: host reader, same frames
+    cvw = cv2.VideoWriter(pc, cv2.VideoWriter_fourcc(*"FFV1"), 24.0, (w, h))
+    for f in a:
+        cvw.write(cv2.cvtColor(f, cv2.COLOR_RGB2BGR))
+    cvw.release()
+    rd = video_io.open_chunk_reader([pc, pa], chunk=4)   # mixed inputs: everything goes through the host reader
+    assert isinstance(rd, video_io.ChunkReader)
+    host = np.concatenate([c0.numpy().copy() for _, (c0, c1) in rd])
+    assert np.array_equal(host, a)
+
+
+def test_movie_steps_4_and_5_files_in_files_out_on_the_device(tmp_path):
+    """movie_2_3D steps 4 + 5 on clips this package wrote: device decode -> render -> device encode (packets are the only
+    pixels-related bytes on the host), and the results decode in OpenCV to exactly the frames of the host-I/O run."""
+    import json
+
+    from metric_depth_video_toolbox_b200 import movie_steps, video_io
+    from metric_depth_video_toolbox_b200.cli import stereo_rerender
+    from metric_depth_video_toolbox_b200.synth import SyntheticClip
+
+    w, h, n = 320, 192, 14
+    depth, colour = SyntheticClip(w, h, n, zero_fraction=0.003).frames()
+    mask = np.zeros((n, h, w, 3), np.uint8)
+    mask[:, 40:150, 60:260] = 255
+    results = {}
+    for mode in ("device", "host"):
+        d = tmp_path / mode
+        d.mkdir()
+        paths = {k: str(d / f"{k}.mkv") for k in ("depth", "colour", "mask")}
+        for key, frames in (("depth", depth), ("colour", colour), ("mask", mask)):
+            if mode == "device":
+                wr = ffv1_gpu.GpuFfv1Writer(paths[key], 24.0, (w, h), device=DEV, batch=4)
+            else:
+                wr = video_io.ChunkWriter(paths[key], "FFV1", 24.0, (w, h))
+            wr.write(torch.from_numpy(frames), rgb=True)
+            wr.close()
+        os.environ["MDVT_FFV1_WRITER"] = "gpu" if mode == "device" else "host"
+        try:
+            scene = {"finished": False, "scene_video_file": paths["colour"], "depth_video_file": paths["depth"], "mask_video_file": paths["mask"],
+                     "xfov": 60.0, "sbs": str(d / "sbs.mkv")}
+            movie_steps.step4_find_convergence([scene])
+            argv = movie_steps.stereo_rerender_argv(scene) + ["--green_and_black_infill_mask", "--create_sbs_depth_video"]
+            stereo_rerender.run(stereo_rerender.build_parser().parse_args(argv), keep_process_group=True)
+        finally:
+            os.environ.pop("MDVT_FFV1_WRITER", None)
+        conv = json.load(open(paths["depth"] + "_convergence_depths.json"))
+        out = paths["depth"] + "_stereo.mkv"
+        frames = {}
+        for suffix in ("", "_infillmask.mkv", "_depth.mkv"):
+            cap = cv2.VideoCapture(out + suffix)
+            got = []
+            while True:
+                ok, f = cap.read()
+                if not ok:
+                    break
+                got.append(f)
+            cap.release()
+            frames[suffix] = np.stack(got)
+        results[mode] = (conv, frames)
+    assert results["device"][0] == results["host"][0] and len(results["host"][0]) == n
+    for suffix in ("", "_infillmask.mkv", "_depth.mkv"):
+        assert results["device"][1][suffix].shape[0] == n
+        assert np.array_equal(results["device"][1][suffix], results["host"][1][suffix]), suffix
+
+
+@pytest.mark.parametrize("w,h,nh,nv,alpha,model", [(64, 48, 8, 8, False, 0), (70, 33, 5, 7, True, 0), (64, 48, 16, 12, False, 1), (48, 32, 1, 1, False, 1)])
+def test_device_decoder_decodes_oracle_written_streams(w, h, nh, nv, alpha, model):
+    """an anchor for the device DECODER that does not involve the device (or host-stepped) encoder: the
+    packets come from oracle/ffv1_oracle.py's plain-Python encoder (pinned byte for byte on libavcodec), many slices, both
+    context models, with and without the alpha plane, both channel orders."""
+    from oracle import ffv1_oracle as fo
+
+    base = fo.parse_config(ffv1_gpu.stream_setup(w, h, nh, nv, alpha, model)[0])
+    frames = content(w, h, 4, seed=21)          # RGB-order test content; the oracle codes B, G, R, A planes
+    packets = []
+    for f in frames:
+        bgra = np.dstack([f[..., ::-1], np.full((h, w), 255, np.uint8)])
+        packets.append(fo.encode_frame(bgra, base, True, [fo.SliceState(base) for _ in range(nh * nv)]))
+    dec = ffv1_gpu.Ffv1Decoder(w, h, DEV, max_frames=4, slices=(nh, nv), alpha=alpha, context_model=model)
+    assert np.array_equal(dec.decode(packets, rgb=True).cpu().numpy(), frames)
+    assert np.array_equal(dec.decode(packets[:2], rgb=False).cpu().numpy(), frames[:2, ..., ::-1])
