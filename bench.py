@@ -310,8 +310,10 @@ def measure_paths(dev, peak: float, frames_1080: int = 32, frames_4k: int = 16, 
         poses.append(T)
     common = dict(xfov=XFOV, max_depth=MAX_DEPTH, pupillary_distance=IPD_MM, master_xfov=MASTER_XFOV, infill_mask=True)
     for key, extra, kernel, note in (
-            ("convergence_1080p", dict(convergence_depths=[5.0 + 0.02 * f for f in range(n)]), "mdvt::stereo_conv_rows_kernel",
+            ("convergence_1080p", dict(convergence_depths=[5.0 + 0.02 * f for f in range(n)]), "mdvt::project_splat_kernel + mdvt::resolve_ckey_kernel",
              f"{w}x{h} x {n} frames, stereo pair + hole masks with a per-frame convergence rotation (stereo_rerender --convergence_file)"),
+            ("convergence_1080p_fused_row_kernel", dict(convergence_depths=[5.0 + 0.02 * f for f in range(n)], conv_kernel=True),
+             "mdvt::stereo_conv_rows_kernel", f"the same frames through the fused target-row kernel (no global z-buffer; StereoParams.conv_kernel)"),
             ("posed_1080p", dict(transformations=poses), "mdvt::project_splat_kernel + mdvt::resolve_ckey_kernel",
              f"{w}x{h} x {n} frames, stereo pair + hole masks with a per-frame 4x4 camera pose (stereo_rerender --transformation_file)")):
         rr = StereoRerenderer(StereoParams(w, h, **common, **extra), dev)

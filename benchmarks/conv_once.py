@@ -7,7 +7,7 @@ from metric_depth_video_toolbox_b200.synth import SyntheticClip
 w, h, n = 1920, 1080, 8
 d, c = SyntheticClip(w, h, n).frames(0, n)
 d, c = torch.from_numpy(d).cuda(), torch.from_numpy(c).cuda()
-rr = StereoRerenderer(StereoParams(w, h, xfov=60.0, convergence_depths=[5.0] * n, infill_mask=True), "cuda")
+rr = StereoRerenderer(StereoParams(w, h, xfov=60.0, convergence_depths=[5.0] * n, infill_mask=True, conv_kernel=True), "cuda")
 for _ in range(2):
     sbs, mask = rr.render_device(d, c)
 torch.cuda.synchronize()

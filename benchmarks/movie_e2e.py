@@ -56,6 +56,8 @@ t4 = time.time() - t0
 t0 = time.time()
 if green:
     argv = movie_steps.stereo_rerender_argv(scene) + ["--green_and_black_infill_mask"]
+    if os.environ.get("MDVT_E2E_CHUNK"):
+        argv += ["--chunk_frames", os.environ["MDVT_E2E_CHUNK"]]
     stereo_rerender.run(stereo_rerender.build_parser().parse_args(argv), keep_process_group=True)
 else:
     movie_steps.step5_render_sbs(None, [scene])

@@ -18,17 +18,25 @@ from metric_depth_video_toolbox_b200 import video_io
 from metric_depth_video_toolbox_b200.cli import view_depthfile
 from metric_depth_video_toolbox_b200.synth import SyntheticClip
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 36
-w = int(sys.argv[2]) if len(sys.argv) > 2 else 3840
-h = int(sys.argv[3]) if len(sys.argv) > 3 else 2160
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+n = int(args[0]) if len(args) > 0 else 36
+w = int(args[1]) if len(args) > 1 else 3840
+h = int(args[2]) if len(args) > 2 else 2160
 tmp = os.path.join(tempfile.gettempdir(), f"mdvt_novel_e2e_{n}_{w}")
 shutil.rmtree(tmp, ignore_errors=True)
 os.makedirs(tmp)
 t0 = time.time()
 depth, colour = SyntheticClip(w, h, n).frames()
-for name, frames in (("depth.mkv", depth), ("colour.mkv", colour)):   # OpenCV's files (GOP 12), written on all cores
-    pw = video_io.ParallelWriter(os.path.join(tmp, name), 24.0, (w, h), lanes=os.cpu_count(), block=12)
-    pw.write(frames, rgb=True)
+host_inputs = "--host-inputs" in sys.argv
+for name, frames in (("depth.mkv", depth), ("colour.mkv", colour)):
+    if host_inputs:   # OpenCV's files (GOP 12, what the reference's tools write), on all cores: decoded on host threads
+        pw = video_io.ParallelWriter(os.path.join(tmp, name), 24.0, (w, h), lanes=os.cpu_count(), block=12)
+    else:             # this package's writer (what save_depth_video / the result writers leave): decoded on the device
+        from metric_depth_video_toolbox_b200 import ffv1_gpu
+
+        pw = ffv1_gpu.GpuFfv1Writer(os.path.join(tmp, name), 24.0, (w, h))
+    for a in range(0, n, 4):
+        pw.write(frames[a:a + 4], rgb=True)
     pw.close()
 t_gen = time.time() - t0
 del depth, colour
@@ -39,6 +47,7 @@ t = time.time() - t0
 out = os.path.join(tmp, "depth.mkv_render.mkv")
 assert video_io.video_info(out)[3] == n
 print(json.dumps({"workload": f"3d_view_depthfile.py --render, {w}x{h} x {n} frames, FFV1 in/out", "host_cores": os.cpu_count(),
-                  "result_writer": "gpu (mdvt_ffv1_encode_frames)" if os.environ.get("MDVT_FFV1_WRITER") == "gpu" else "host lanes (cv2.VideoWriter x cores)",
+                  "inputs": "cv2.VideoWriter files (host decode)" if host_inputs else "GpuFfv1Writer files (device decode)",
+                  "result_writer": "gpu (mdvt_ffv1_encode_frames)" if video_io.gpu_ffv1_requested() else "host lanes (cv2.VideoWriter x cores)",
                   "synthetic_clip_write_s": round(t_gen, 2), "render_s": round(t, 2), "frames_per_s": round(n / t, 2)}))
 shutil.rmtree(tmp, ignore_errors=True)

@@ -34,12 +34,12 @@ which = sys.argv[1] if len(sys.argv) > 1 else "both"
 if which in ("stereo", "both", "conv"):
     w, h, n = 1920, 1080, 32
     d, c = clip(w, h, n)
-    rr = StereoRerenderer(StereoParams(w, h, xfov=60.0, convergence_depths=[5.0] * n, infill_mask=True), "cuda")
+    rr = StereoRerenderer(StereoParams(w, h, xfov=60.0, convergence_depths=[5.0] * n, infill_mask=True, conv_kernel=True), "cuda")
     sbs = torch.empty((n, h, 2 * w, 3), dtype=torch.uint8, device="cuda")
     mask = torch.empty((n, h, 2 * w), dtype=torch.uint8, device="cuda")
     ms = timed(lambda: rr.render_device(d, c, 0, sbs, mask), 3)
     px = w * h * n
-    print(f"generic stereo (convergence) 1080p: {ms / n * 1e3:.1f} us/frame  {n / ms * 1e3:.0f} frames/s  {px * 14 / ms / 1e6:.0f} GB/s algorithmic "
+    print(f"convergence stereo, fused target-row kernel, 1080p: {ms / n * 1e3:.1f} us/frame  {n / ms * 1e3:.0f} frames/s  {px * 14 / ms / 1e6:.0f} GB/s algorithmic "
           f"({px * 14 / ms / 1e6 / 6454:.3f} of HBM peak)  holes {float((mask == 255).float().mean()):.4f}")
 if which in ("stereo", "both", "posed"):
     w, h, n = 1920, 1080, 32

@@ -188,7 +188,7 @@ def run(args, keep_process_group: bool = False) -> int:
         if gpu_ffv1 and cc == "FFV1":   # entropy coding on the device; ranks leave segments + plans for the packet-level join
             from .. import ffv1_gpu
 
-            return ffv1_gpu.GpuFfv1Writer(seg(path), frame_rate, job.out_size, device=device, batch=min(8, max(1, args.chunk_frames)),
+            return ffv1_gpu.GpuFfv1Writer(seg(path), frame_rate, job.out_size, device=device, batch=min(16, max(1, args.chunk_frames)),
                                           join_on_close=(world_size == 1))
         if parallel and cc == "FFV1":
             return video_io.ParallelWriter(seg(path), frame_rate, job.out_size, lanes=lanes, join_on_close=(world_size == 1))
@@ -202,6 +202,11 @@ def run(args, keep_process_group: bool = False) -> int:
 
     reader = video_io.open_chunk_reader([args.depth_video, args.color_video], start, stop, chunk=args.chunk_frames, device=device,
                                   decoders=video_io.default_decoders(world_size))
+    # The loop shares the interpreter with the reader's and the writers' threads (packet copies, muxing).  With CPython's
+    # default 5 ms switch interval every GIL hand-back costs this thread up to 5 ms -- measured: 4-7 ms of "render" per frame
+    # for 0.2 ms of kernels -- so the interval is shortened for the duration of the job.
+    switch_interval = sys.getswitchinterval()
+    sys.setswitchinterval(1e-4)
     t0 = time.time()
     done = 0
     deferred = {}
@@ -210,7 +215,10 @@ def run(args, keep_process_group: bool = False) -> int:
     for n, (depth_rgb, colour) in reader:
         t_a = time.perf_counter()
         outputs = job.render_chunk(depth_rgb, depth_rgb if colour is None else colour, start + done)
-        torch.cuda.synchronize(device)  # results are complete, the reader may recycle its buffers
+        # results are complete and the reader may recycle its buffers once THIS stream is done (the renderer's second stream
+        # is joined to it by an event); a device-wide synchronize would also wait for the writers' encodes and the reader's
+        # decodes of other chunks, which run on streams of their own precisely so that they overlap this loop
+        torch.cuda.current_stream(device).synchronize()
         t_b = time.perf_counter()
         for key, pending in list(deferred.items()):   # last chunk's host-finished frames (TELEA tail of the mask)
             writers[key].write(pending.result(), rgb=(key != "depth"))
@@ -234,6 +242,7 @@ def run(args, keep_process_group: bool = False) -> int:
     t_close = time.perf_counter()
     for w in writers.values():
         w.close()
+    sys.setswitchinterval(switch_interval)
     if os.environ.get("MDVT_PROFILE_LOOP") == "1":
         print(f"\n[frame loop, rank {rank}] {done} frames: waiting for the reader {stage['read']:.2f} s, render + sync {stage['render']:.2f} s, "
               f"handing to the writers {stage['write']:.2f} s, closing the writers {time.perf_counter() - t_close:.2f} s "

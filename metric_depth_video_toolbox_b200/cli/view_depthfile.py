@@ -92,7 +92,7 @@ def main(argv: Optional[List[str]] = None) -> int:
     if on_device:
         from .. import ffv1_gpu
 
-        writer = ffv1_gpu.GpuFfv1Writer(output_file, fps, (w, h), device=device, batch=min(8, max(1, args.chunk_frames)))
+        writer = ffv1_gpu.GpuFfv1Writer(output_file, fps, (w, h), device=device, batch=min(16, max(1, args.chunk_frames)))
     else:
         writer = video_io.ParallelWriter(output_file, fps, (w, h), lanes=lanes) if (fourcc == "FFV1" and lanes > 1) else \
             video_io.ChunkWriter(output_file, fourcc, fps, (w, h))
@@ -105,14 +105,14 @@ def main(argv: Optional[List[str]] = None) -> int:
         rgb, _ = renderer.render_device(d, c, done)
         if on_device:   # the writer takes its own device copy: no raw frame crosses PCIe
             writer.write(rgb[:n])
-            torch.cuda.synchronize(device)   # as below: the reader may recycle its buffers, the renderer's second stream is idle
+            torch.cuda.current_stream(device).synchronize()   # this stream only (the renderer's second stream is joined to it): the writer's and the reader's streams keep running
             done += n
             print(f"Frame: {done} {done / fps}s", end="\r", file=sys.stderr)
             continue
         if host_out is None:
             host_out = torch.empty((args.chunk_frames, h, w, 3), dtype=torch.uint8, pin_memory=True)
         host_out[:n].copy_(rgb, non_blocking=True)
-        torch.cuda.synchronize(device)
+        torch.cuda.current_stream(device).synchronize()
         writer.write(host_out[:n])
         done += n
         print(f"Frame: {done} {done / fps}s", end="\r", file=sys.stderr)

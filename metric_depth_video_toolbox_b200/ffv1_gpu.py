@@ -284,6 +284,10 @@ class GpuFfv1Writer:
 
     def _run(self):
         torch.cuda.set_device(self.device)
+        # a stream of its own: on the (legacy) default stream the encode launches of this thread would queue behind -- and
+        # hold up -- the renderer's kernels and the other writers' encodes, and the coder, a latency-bound kernel with one
+        # thread per slice, is exactly the kind of work that should run underneath them
+        stream = torch.cuda.Stream(device=self.device)
         while True:
             item = self._queue.get()
             if item is None:
@@ -292,10 +296,11 @@ class GpuFfv1Writer:
                 continue   # keep draining so the producer never blocks
             t, rgb = item
             try:
-                for a in range(0, int(t.shape[0]), self.enc.max_frames):
-                    for pkt in self.enc.encode(t[a:a + self.enc.max_frames], rgb):
-                        self._mux.add(pkt, True)
-                        self.bytes += len(pkt)
+                with torch.cuda.stream(stream):
+                    for a in range(0, int(t.shape[0]), self.enc.max_frames):
+                        for pkt in self.enc.encode(t[a:a + self.enc.max_frames], rgb):
+                            self._mux.add(pkt, True)
+                            self.bytes += len(pkt)
             except BaseException as e:   # surfaced by the next write() / close()
                 self._error = e
 

@@ -6,7 +6,9 @@ list, max_depth, pupillary distance, master FOV, optional smoothed convergence l
 camera poses) into per-frame constant blocks, picks the kernel path per clip
 
   * row-local fused kernel (`ops.stereo_rows`)      -- no pose file, no convergence rotation
-  * generic path (`ops.project_splat` + `ops.resolve`) -- anything else
+  * generic frame loop (`ops.render_views`: colour-keyed splat + streaming resolve, two frames in flight on two streams)
+    -- anything else; convergence without a pose file can also go through the fused target-row kernel
+    (`ops.stereo_conv_rows`, `StereoParams.conv_kernel`), which needs no global z-buffer but is slower on the B200
 
 and runs it either on device-resident tensors (`render_device`) or on host arrays through a chunked,
 double-buffered H2D -> kernel -> D2H pipeline (`render_host`).  There is no CPU implementation.
@@ -41,6 +43,8 @@ class StereoParams:
     mask_rgb: bool = False                # mask as the reference's green/black u8x3 image instead of u8
     near: float = geo.NEAR_PLANE
     force_generic: bool = False           # test / comparison aid: always take the K1+K2+K3 path
+    conv_kernel: bool = False             # convergence without a pose file through the fused target-row kernel (no global z-buffer)
+                                          # instead of the two-lane generic path: same bytes, 23.0 vs 18.9 us per 1080p frame on the B200
 
     def __post_init__(self):
         if self.xfov is None and self.yfov is None and self.xfovs is None:
@@ -64,7 +68,8 @@ class StereoParams:
     def conv_local(self) -> bool:
         """True when the eye poses are `rotation about y + shift along x` (convergence without a pose file): the row
         displacement is then depth independent and the fused target-row kernel applies."""
-        return self.transformations is None and self.convergence_depths is not None and not self.force_generic and self.width <= 4096
+        return (self.conv_kernel and self.transformations is None and self.convergence_depths is not None and not self.force_generic
+                and self.width <= 4096)
 
 
 class StereoRerenderer:

@@ -359,22 +359,32 @@ class DeviceChunkReader:
         return ((x[..., 0] * 9798 + x[..., 1] * 19235 + x[..., 2] * 3735 + 16384) >> 15).to(torch.uint8)
 
     def _run(self):
-        try:
+        from concurrent.futures import ThreadPoolExecutor
+
+        streams = {}
+
+        def decode_one(idx: int, a: int, b: int):
+            """Frames [a, b) of input idx on that input's own stream: the inputs of a chunk are decoded side by side (the
+            decoder is a latency-bound kernel with one thread per slice, two of them overlap almost perfectly)."""
+            r, g = self._readers[idx], self.grey[idx]
             torch.cuda.set_device(self.device)
-            stream = torch.cuda.Stream(device=self.device)
-            with torch.cuda.stream(stream):
+            if idx not in streams:
+                streams[idx] = torch.cuda.Stream(device=self.device)
+            with torch.cuda.stream(streams[idx]):
+                frames = r.dec.decode([r._pk.payload(k) for k in range(a, b)], rgb=True)   # a fresh tensor, complete on return
+                out = self._to_grey(frames) if g else frames
+                streams[idx].synchronize()
+            return out
+
+        try:
+            live = [k for k, r in enumerate(self._readers) if r is not None]
+            with ThreadPoolExecutor(max_workers=max(1, len(live)), thread_name_prefix="mdvt-device-decode") as pool:
                 for a in range(self.start, self.stop, self.chunk):
                     if self._stop.is_set():
                         return
                     b = min(a + self.chunk, self.stop)
-                    bufs = []
-                    for r, g in zip(self._readers, self.grey):
-                        if r is None:
-                            bufs.append(None)
-                            continue
-                        frames = r.dec.decode([r._pk.payload(k) for k in range(a, b)], rgb=True)   # a fresh tensor, complete on return
-                        bufs.append(self._to_grey(frames) if g else frames)
-                    stream.synchronize()
+                    futures = {k: pool.submit(decode_one, k, a, b) for k in live}
+                    bufs = [futures[k].result() if k in futures else None for k in range(len(self._readers))]
                     while not self._stop.is_set():
                         try:
                             self._q.put((b - a, bufs), timeout=0.05)

@@ -412,7 +412,7 @@ def test_stereo_conv_rows_bit_identical_to_generic_path(size, conv, yfov, mask_r
     convs = [conv, 0.0, conv * 1.7]  # 0 -> "skipping convergence" for that frame (stereo_rerender.py:710-712)
     outs = []
     for force in (False, True):
-        p = StereoParams(w, h, xfov=60.0, yfov=yfov, convergence_depths=convs, infill_mask=True, mask_rgb=mask_rgb, force_generic=force)
+        p = StereoParams(w, h, xfov=60.0, yfov=yfov, convergence_depths=convs, infill_mask=True, mask_rgb=mask_rgb, force_generic=force, conv_kernel=True)
         assert p.conv_local() != force
         rr = StereoRerenderer(p, DEV)
         out_depth = torch.full((n, h, 2 * w), -1.0, dtype=torch.float32, device=DEV)
