@@ -232,12 +232,22 @@ def measured_peak():
 
 
 def ncu_traffic_per_frame():
-    """DRAM bytes per frame of the fused kernel from the committed ncu capture (profiles/), if any."""
+    """DRAM bytes per frame of the fused kernel from the committed ncu capture (profiles/), if any, with the kernel name ncu
+    reported and whether the capture was taken from the kernel source that is in the tree now (benchmarks/make_traffic_json.py
+    stores the SHA-256 of the kernel's source files)."""
     path = os.path.join(ROOT, "profiles", "stereo_rows_traffic.json")
-    if os.path.exists(path):
-        with open(path) as fh:
-            return json.load(fh)
-    return None
+    if not os.path.exists(path):
+        return None
+    with open(path) as fh:
+        traffic = json.load(fh)
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
+        from make_traffic_json import source_sha256
+
+        traffic["matches_current_source"] = traffic.get("kernel_source_sha256") == source_sha256()
+    except Exception:  # noqa: BLE001
+        traffic["matches_current_source"] = None
+    return traffic
 
 
 def measure_paths(dev, peak: float, frames_1080: int = 32, frames_4k: int = 16, reps: int = 5):
@@ -478,7 +488,7 @@ def run_ours(args):
         try:
             from metric_depth_video_toolbox_b200 import ffv1_gpu
 
-            batch = min(32, n_frames)
+            batch = min(128, n_frames)   # one thread per slice: the coder needs ~100 k slices in flight to fill the machine (32 frames: 10 % occupancy)
             result_codec = {"what": "FFV1 v3 entropy coding of the SBS result on the device (mdvt_ffv1_encode_frames), not part of `value`",
                             "frame": f"{2 * WIDTH}x{HEIGHT}", "batch": batch}
             for model, key in ((0, "libavcodec_tables_666_contexts"), (1, "small_tables_63_contexts")):
@@ -517,9 +527,10 @@ def run_ours(args):
     traffic = ncu_traffic_per_frame()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (traffic["dram_bytes_per_frame"] * n_frames) if traffic else None,
-                "kernel": "mdvt::stereo_rows_w32_kernel<1,true,160,4>", "algorithmic_bytes_per_launch": algorithmic,
+                "kernel": (traffic or {}).get("kernel") or "mdvt::stereo_rows_w32_kernel<1,true,160,4>", "algorithmic_bytes_per_launch": algorithmic,
                 "launch_ms": mean_launch_ms, "peak_source": peak_kind,
-                "traffic_source": traffic.get("source") if traffic else None}
+                "traffic_source": traffic.get("source") if traffic else None,
+                "traffic_capture_matches_kernel_source": traffic.get("matches_current_source") if traffic else None}
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
