@@ -61,29 +61,89 @@ def parse_args():
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in this process (a thread polling every 2 ms --
+    the headline region is ~30 ms long, too short for a freshly started nvidia-smi to report from), nvidia-smi -lms as the
+    fallback where pynvml is missing."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
-        self.samples, self.proc, self.gpu = [], None, gpu_index
+        self.samples, self.proc, self.gpu, self.source = [], None, gpu_index, None   # samples: (sm MHz, [reason, ...])
+        self.sm_max, self._stop, self.thread = 0.0, threading.Event(), None
+
+    def _nvml_handle(self):
+        import pynvml
+
+        pynvml.nvmlInit()
+        try:   # CUDA ordinal -> NVML device through the UUID (CUDA_VISIBLE_DEVICES may renumber)
+            import torch
+
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(self.gpu).uuid)
+            try:
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except TypeError:
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        except Exception:  # noqa: BLE001
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+
+    def _poll_nvml(self, pynvml, handle):
+        masks = (("hw_slowdown", pynvml.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", pynvml.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", pynvml.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", pynvml.nvmlClocksEventReasonSwPowerCap))
+        while not self._stop.is_set():
+            try:
+                mhz = float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM))
+                try:
+                    bits = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle))
+                except Exception:  # noqa: BLE001 - older bindings
+                    bits = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(handle))
+                self.samples.append((mhz, [name for name, bit in masks if bits & bit]))
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.002)
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            pynvml, handle = self._nvml_handle()
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll_nvml, args=(pynvml, handle), daemon=True)
             self.thread.start()
+            return self
+        except Exception:  # noqa: BLE001 - no NVML binding / no permission: ask nvidia-smi
+            self.source = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
+            self.thread.start()
+            deadline = time.time() + 3.0   # nvidia-smi needs a few hundred ms before its first line
+            while not self.samples and time.time() < deadline:
+                time.sleep(0.01)
+            self.samples.clear()
         except OSError:
             self.proc = None
         return self
 
-    def _read(self):
+    def _read_smi(self):
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            parts = [x.strip() for x in line.strip().split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                mhz = float(parts[0])
+                self.sm_max = max(self.sm_max, float(parts[1]))
+            except ValueError:
+                continue
+            self.samples.append((mhz, [n for n, v in zip(names, parts[3:7]) if v.lower().startswith("active")]))
 
     def __exit__(self, *exc):
-        if self.proc is not None:
-            time.sleep(0.12)
+        if self.source == "nvml":
+            self._stop.set()
+            self.thread.join(timeout=1)
+        elif self.proc is not None:
+            time.sleep(0.05)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
@@ -91,22 +151,10 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm, sm_max, reasons = [], 0, set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for line in self.samples:
-            parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                sm_max = max(sm_max, float(parts[1]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": sm_max or None, "reasons": sorted(reasons), "samples": len(sm)}
+        sm = sorted(m for m, _ in self.samples)
+        reasons = sorted({r for _, rs in self.samples for r in rs})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max or None, "reasons": reasons, "samples": len(sm),
+                "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -41,6 +41,17 @@ if which in ("stereo", "both", "conv"):
     px = w * h * n
     print(f"convergence stereo, fused target-row kernel, 1080p: {ms / n * 1e3:.1f} us/frame  {n / ms * 1e3:.0f} frames/s  {px * 14 / ms / 1e6:.0f} GB/s algorithmic "
           f"({px * 14 / ms / 1e6 / 6454:.3f} of HBM peak)  holes {float((mask == 255).float().mean()):.4f}")
+if which in ("stereo", "both", "conv", "vrows"):
+    w, h, n = 1920, 1080, 32
+    d, c = clip(w, h, n)
+    sbs = torch.empty((n, h, 2 * w, 3), dtype=torch.uint8, device="cuda")
+    mask = torch.empty((n, h, 2 * w), dtype=torch.uint8, device="cuda")
+    for conv in (5.0, 2.0, 1.0):
+        rr = StereoRerenderer(StereoParams(w, h, xfov=60.0, convergence_depths=[conv + 0.02 * f for f in range(n)], infill_mask=True, conv_kernel="vrows"), "cuda")
+        ms = timed(lambda: rr.render_device(d, c, 0, sbs, mask), 5)
+        px = w * h * n
+        print(f"convergence stereo at {conv} m, virtual-source-row kernel, 1080p: {ms / n * 1e3:.2f} us/frame  {n / ms * 1e3:.0f} frames/s  "
+              f"{px * 14 / ms / 1e6:.0f} GB/s algorithmic ({px * 14 / ms / 1e6 / 6454:.3f} of HBM peak)  holes {float((mask == 255).float().mean()):.4f}")
 if which in ("stereo", "both", "posed"):
     w, h, n = 1920, 1080, 32
     d, c = clip(w, h, n)

@@ -361,6 +361,23 @@ MDVT_API int mdvt_stereo_conv_rows(const uint8_t *depth_rgb, const uint8_t *colo
                           const mdvt_conv_frame *frames_dev, uint32_t bg_rgb, uint32_t fill_rgb, uint32_t flags,
                           uint8_t *out_sbs, uint8_t *out_mask, float *out_depth, void *stream);
 
+/* The same job in "virtual source row" form (csrc/mdvt_stereo_vrows.cu): along a target row the source row index is a
+ * staircase in the source column, so the TMA engine assembles one virtual source row per eye in shared memory and the
+ * row is processed like a row of mdvt_stereo_rows, with two 32-bit shared-memory atomic passes (Zv, then colour) standing
+ * in for the 64-bit key.  Bit-identical to mdvt_render_views / mdvt_stereo_conv_rows (nearest Zv wins, candidates with
+ * bit-identical Zv are ordered by packed colour).  Requires W % 32 == 0, W <= 3840, 16-byte aligned buffers and poses inside
+ * the limits mdvt_stereo_conv_vrows_supported checks (else MDVT_ERR_UNSUPPORTED / undefined rows flagged in status_dev).
+ * status_dev: optional n_frames int32 (DEVICE), set to 1 for a frame whose geometry left the limits (never for frames the
+ * host check accepted); zero it before the call. */
+MDVT_API int mdvt_stereo_conv_vrows(const uint8_t *depth_rgb, const uint8_t *colour_rgb, int n_frames, int width, int height,
+                           const mdvt_conv_frame *frames_dev, uint32_t bg_rgb, uint32_t fill_rgb, uint32_t flags,
+                           uint8_t *out_sbs, uint8_t *out_mask, float *out_depth, int32_t *status_dev, void *stream);
+
+/* Host-side check (no CUDA call): 1 when every frame of frames_host (HOST array) is a pose mdvt_stereo_conv_vrows handles
+ * at this size -- y-rotation + x-shift, row step within [0.9, 1.12], staircase slope below 0.4 rows per 15 columns
+ * (convergence distances down to ~0.6 m at 1080p) -- else 0 (use mdvt_render_views). */
+MDVT_API int mdvt_stereo_conv_vrows_supported(const mdvt_conv_frame *frames_host, int n_frames, int width, int height);
+
 /* ---- FFV1 result-video encoder -----------------------------------------------------------------------------------------
  * Replaces the entropy coder behind the reference's cv2.VideoWriter(fourcc "FFV1") result writers
  * (stereo_rerender.py:420-442,941; depth_frames_helper.py:125-161; 3d_view_depthfile.py:118-127), i.e. libavcodec's FFV1

@@ -113,6 +113,9 @@ _PROTOTYPES = {
     "mdvt_calculate_normals": (C.c_int, [_f32p, C.c_int, C.c_int, C.POINTER(C.c_double), _f32p, _stream]),
     "mdvt_stereo_conv_rows": (C.c_int, [_u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _u8p, _u8p,
                                         _f32p, _stream]),
+    "mdvt_stereo_conv_vrows": (C.c_int, [_u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, _u8p, _u8p,
+                                         _f32p, _i32p, _stream]),
+    "mdvt_stereo_conv_vrows_supported": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "mdvt_stereo_rows": (C.c_int, [_u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32,
                                    C.c_uint32, _u8p, _u8p, _f32p, _stream]),
     "mdvt_ffv1_stream_setup": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int),

@@ -15,7 +15,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIB_PATH = os.path.join(PKG_DIR, "libmdvt_b200.so")
 
-SOURCES = ["mdvt_abi.cu", "mdvt_pointwise.cu", "mdvt_splat.cu", "mdvt_reduce.cu", "mdvt_export.cu", "mdvt_edges.cu", "mdvt_remap.cu", "mdvt_stereo_rows.cu", "mdvt_stereo_conv.cu", "mdvt_ffv1.cu"]
+SOURCES = ["mdvt_abi.cu", "mdvt_pointwise.cu", "mdvt_splat.cu", "mdvt_reduce.cu", "mdvt_export.cu", "mdvt_edges.cu", "mdvt_remap.cu", "mdvt_stereo_rows.cu", "mdvt_stereo_conv.cu", "mdvt_stereo_vrows.cu", "mdvt_ffv1.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

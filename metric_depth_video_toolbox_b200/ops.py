@@ -775,11 +775,26 @@ def conv_frames_packed(sources: np.ndarray, views: np.ndarray, near: float = NEA
     return out
 
 
+def conv_vrows_supported(frames_host: np.ndarray, width: int, height: int) -> bool:
+    """True when every frame of the HOST array `frames_host` ((n, 40) float32 rows of mdvt_conv_frame) is a pose the
+    virtual-row kernel handles at this size (mdvt_stereo_conv_vrows_supported: no CUDA call)."""
+    arr = np.ascontiguousarray(frames_host, dtype=np.float32)
+    if arr.ndim != 2 or arr.shape[1] != C.sizeof(_lib.ConvFrame) // 4:
+        raise ValueError("frames_host must be (n, 40) float32 rows of mdvt_conv_frame")
+    return bool(_lib.load().mdvt_stereo_conv_vrows_supported(arr.ctypes.data, arr.shape[0], int(width), int(height)))
+
+
 def stereo_conv_rows(depth_rgb: torch.Tensor, colour: torch.Tensor, frames: torch.Tensor, bg_rgb=(0, 0, 0), fill_rgb=(0, 0, 0),
                      flags: int = 0, out_sbs: Optional[torch.Tensor] = None, out_mask: Optional[torch.Tensor] = None,
-                     want_mask: bool = True, out_depth: Optional[torch.Tensor] = None):
+                     want_mask: bool = True, out_depth: Optional[torch.Tensor] = None, kernel: str = "rows",
+                     status: Optional[torch.Tensor] = None):
     """Fused convergence-stereo kernel over a batch: depth_rgb / colour (n, H, W, 3) u8, frames (n, 40) float32 CUDA
-    tensor from conv_frames().  Same outputs as stereo_rows; bit-identical to project_splat + resolve."""
+    tensor from conv_frames().  Same outputs as stereo_rows; bit-identical to project_splat + resolve.
+    kernel "vrows": the virtual-source-row kernel (mdvt_stereo_conv_vrows; poses must pass conv_vrows_supported), `status`
+    an optional zeroed (n,) int32 CUDA tensor that receives 1 for frames whose geometry left the kernel's limits;
+    kernel "rows": the target-row kernel with per-column source-row prediction (mdvt_stereo_conv_rows, any width)."""
+    if kernel not in ("rows", "vrows"):
+        raise ValueError("kernel is 'rows' or 'vrows'")
     _need(depth_rgb, torch.uint8, "depth_rgb")
     _need(colour, torch.uint8, "colour")
     _need(frames, torch.float32, "frames")
@@ -805,6 +820,14 @@ def stereo_conv_rows(depth_rgb: torch.Tensor, colour: torch.Tensor, frames: torc
         _need(out_depth, torch.float32, "out_depth")
         if out_depth.numel() != n * h * 2 * w:
             raise ValueError("out_depth must be (n, H, 2W) float32")
+    if kernel == "vrows":
+        if status is not None:
+            _need(status, torch.int32, "status")
+            if status.numel() != n:
+                raise ValueError("status must hold one int32 per frame")
+        _lib.check(_lib.load().mdvt_stereo_conv_vrows(_ptr(depth_rgb), _ptr(colour), n, w, h, _ptr(frames), pack_rgb(bg_rgb), pack_rgb(fill_rgb),
+                                                      flags, _ptr(out_sbs), _ptr(out_mask), _ptr(out_depth), _ptr(status), _stream()))
+        return out_sbs, out_mask
     _lib.check(_lib.load().mdvt_stereo_conv_rows(_ptr(depth_rgb), _ptr(colour), n, w, h, _ptr(frames), pack_rgb(bg_rgb), pack_rgb(fill_rgb),
                                                  flags, _ptr(out_sbs), _ptr(out_mask), _ptr(out_depth), _stream()))
     return out_sbs, out_mask

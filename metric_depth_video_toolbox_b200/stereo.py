@@ -43,8 +43,10 @@ class StereoParams:
     mask_rgb: bool = False                # mask as the reference's green/black u8x3 image instead of u8
     near: float = geo.NEAR_PLANE
     force_generic: bool = False           # test / comparison aid: always take the K1+K2+K3 path
-    conv_kernel: bool = False             # convergence without a pose file through the fused target-row kernel (no global z-buffer)
-                                          # instead of the two-lane generic path: same bytes, 23.0 vs 18.9 us per 1080p frame on the B200
+    conv_kernel: object = "auto"          # convergence without a pose file: "auto" = the virtual-source-row kernel (ops.stereo_conv_rows
+                                          # kernel="vrows", no global z-buffer) where the poses and the frame size allow it, else the
+                                          # two-lane generic loop; "vrows" = insist on it; True / "rows" = round 1's target-row kernel;
+                                          # False / "generic" = always the generic loop.  Every choice writes the same bytes.
 
     def __post_init__(self):
         if self.xfov is None and self.yfov is None and self.xfovs is None:
@@ -65,11 +67,26 @@ class StereoParams:
         """True when every frame is a pure +-ipd/2 shift: v' == v, one fused kernel does it all."""
         return self.transformations is None and self.convergence_depths is None and not self.force_generic
 
+    def conv_mode(self) -> str:
+        """Which fused convergence kernel may run: "off" (pose file, no convergence list, force_generic), else "auto" | "vrows" |
+        "rows" | "generic" (conv_kernel)."""
+        if self.transformations is not None or self.convergence_depths is None or self.force_generic:
+            return "off"
+        ck = self.conv_kernel
+        if ck is True:
+            ck = "rows"
+        if ck is False or ck is None:
+            ck = "generic"
+        if ck not in ("auto", "vrows", "rows", "generic"):
+            raise ValueError("conv_kernel is 'auto', 'vrows', 'rows' / True or 'generic' / False")
+        if ck == "rows" and self.width > 4096:
+            ck = "generic"
+        return ck
+
     def conv_local(self) -> bool:
-        """True when the eye poses are `rotation about y + shift along x` (convergence without a pose file): the row
-        displacement is then depth independent and the fused target-row kernel applies."""
-        return (self.conv_kernel and self.transformations is None and self.convergence_depths is not None and not self.force_generic
-                and self.width <= 4096)
+        """True when the eye poses are `rotation about y + shift along x` (convergence without a pose file) and a fused
+        convergence kernel is allowed: the row displacement is then depth independent."""
+        return self.conv_mode() in ("auto", "vrows", "rows")
 
 
 class StereoRerenderer:
@@ -176,14 +193,24 @@ class StereoRerenderer:
             out_sbs = torch.empty((n, h, 2 * w, 3), dtype=torch.uint8, device=depth_rgb.device)
         if out_mask is None and p.infill_mask:
             out_mask = torch.empty((n, h, 2 * w) + ((3,) if mask_rgb else ()), dtype=torch.uint8, device=depth_rgb.device)
-        if p.conv_local():  # convergence only: fused target-row kernel, no global z-buffer
+        mode = p.conv_mode()
+        if mode in ("auto", "vrows", "rows"):  # convergence only: fused kernels without a global z-buffer
             key = ("conv", start_frame, n)
             if key not in self._consts_cache:
                 if len(self._consts_cache) > 64:
                     self._consts_cache.clear()
-                self._consts_cache[key] = torch.from_numpy(ops.conv_frames_packed(*self.packed_cameras(start_frame, n), p.near)).to(self.device)
-            return ops.stereo_conv_rows(depth_rgb, colour, self._consts_cache[key], p.bg_rgb, (0, 0, 0), flags, out_sbs, out_mask,
-                                        want_mask=False, out_depth=out_depth)
+                host = ops.conv_frames_packed(*self.packed_cameras(start_frame, n), p.near)
+                self._consts_cache[key] = (torch.from_numpy(host).to(self.device), ops.conv_vrows_supported(host, w, h))
+            frames_dev, vrows_ok = self._consts_cache[key]
+            aligned = all(t is None or t.data_ptr() % 16 == 0 for t in (depth_rgb, colour, out_sbs, out_mask, out_depth))
+            if mode == "vrows" and not (vrows_ok and aligned):
+                raise ValueError("conv_kernel='vrows': the poses / frame size / buffer alignment are outside the virtual-row kernel's limits")
+            if mode != "rows" and vrows_ok and aligned:
+                return ops.stereo_conv_rows(depth_rgb, colour, frames_dev, p.bg_rgb, (0, 0, 0), flags, out_sbs, out_mask,
+                                            want_mask=False, out_depth=out_depth, kernel="vrows")
+            if mode == "rows":
+                return ops.stereo_conv_rows(depth_rgb, colour, frames_dev, p.bg_rgb, (0, 0, 0), flags, out_sbs, out_mask,
+                                            want_mask=False, out_depth=out_depth)
         sources, views = self.packed_cameras(start_frame, n)
         # generic path: per frame K1+K2 into a persistent 2-view z-buffer, K3 for both eyes straight into the SBS halves
         zkey = torch.cuda.current_stream(depth_rgb.device).cuda_stream

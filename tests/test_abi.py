@@ -90,6 +90,10 @@ def test_argument_validation_without_a_device():
     assert lib.mdvt_resolve(None, None, 4, 4, 0, 0, 0, None, 0, None, 0, None, 0, None, None) == -1
     assert lib.mdvt_stereo_conv_rows(None, None, 1, 5000, 4, None, 0, 0, 0, None, None, None, None) == -2  # column does not fit 12 bits
     assert lib.mdvt_stereo_conv_rows(None, None, 0, 64, 4, None, 0, 0, 0, None, None, None, None) == 0
+    assert lib.mdvt_stereo_conv_vrows(None, None, 1, 70, 4, None, 0, 0, 0, None, None, None, None, None) == -2  # width not a multiple of 32
+    assert b"multiples of 32" in lib.mdvt_last_error()
+    assert lib.mdvt_stereo_conv_vrows(None, None, 0, 64, 4, None, 0, 0, 0, None, None, None, None, None) == 0
+    assert lib.mdvt_stereo_conv_vrows_supported(None, 1, 64, 4) == 0
     assert lib.mdvt_remap_bilinear_u8x3(None, 4, 4, 12, None, None, 4, 4, 0, None, 12, None) == -1
     assert lib.mdvt_normal_march_infill(None, 12, None, 4, None, 12, 4, 4, 400, None) == -1
     assert lib.mdvt_edge_vertices(None, C.byref(src), None, 89.0, None, None, None, None) == -1

@@ -445,6 +445,76 @@ def test_stereo_conv_rows_bit_identical_to_generic_path(size, conv, yfov, mask_r
     assert n_total <= max(4, int(3e-3 * w * h))
 
 
+@pytest.mark.parametrize("size,convs,yfov,mask_rgb", [
+    ((64, 48), [5.0, 0.0, 8.5], None, False),
+    ((640, 480), [2.0, 0.0, 3.4], None, True),
+    ((640, 480), [0.9, 1.3, 40.0], 50.0, False),
+    ((1920, 24), [1.0, 0.0, 1.7], None, False),
+    ((1920, 1080), [5.0, 1.1, 0.75], None, False),      # strong rotations: dozens of staircase steps per row, alternates beyond the staged slots
+    ((3840, 2160), [4.0, 1.5], None, False),
+    ((1280, 720), [3.0, 2.0, 1.0], None, True),
+])
+def test_stereo_conv_vrows_bit_identical_to_generic_path(size, convs, yfov, mask_rgb):
+    """The virtual-source-row kernel (TMA-assembled rows, two 32-bit shared-memory atomic passes) against the generic frame
+    loop with the same cameras: every output byte, the hole masks and the float32 depth planes are identical, no frame
+    reports geometry outside its limits; small sizes also against the float32 model of the frame loops."""
+    from metric_depth_video_toolbox_b200.stereo import StereoParams, StereoRerenderer
+
+    w, h = size
+    n = len(convs)
+    depth, colour = SyntheticClip(w, h, n, zero_fraction=0.01).frames()
+    colour[:, 1, 2] = (0, 255, 0)
+    outs = []
+    for kernel in ("vrows", "generic"):
+        p = StereoParams(w, h, xfov=60.0, yfov=yfov, convergence_depths=convs, infill_mask=True, mask_rgb=mask_rgb, conv_kernel=kernel)
+        rr = StereoRerenderer(p, DEV)
+        out_depth = torch.full((n, h, 2 * w), -1.0, dtype=torch.float32, device=DEV)
+        sbs, mask = rr.render_device(cu(depth), cu(colour), out_depth=out_depth)
+        outs.append((sbs, mask, out_depth))
+    (sa, ma, da), (sb, mb, db) = outs
+    assert torch.equal(sa, sb) and torch.equal(ma, mb)
+    assert torch.equal(da.view(torch.int32), db.view(torch.int32))
+    assert bool((ma != 0).any()) and bool((da > 0).any())
+    # the kernel's own geometry guard stayed silent, also when called through ops with a status plane
+    rr = StereoRerenderer(StereoParams(w, h, xfov=60.0, yfov=yfov, convergence_depths=convs, infill_mask=True, mask_rgb=mask_rgb), DEV)
+    host = ops.conv_frames_packed(*rr.packed_cameras(0, n), rr.p.near)
+    assert ops.conv_vrows_supported(host, w, h)
+    status = torch.zeros(n, dtype=torch.int32, device=DEV)
+    s2, m2 = ops.stereo_conv_rows(cu(depth), cu(colour), cu(host), rr.p.bg_rgb, (0, 0, 0),
+                                  ops.FLAG_BG_COLLIDE | (ops.FLAG_MASK_RGB if mask_rgb else 0), kernel="vrows", status=status)
+    assert int(status.sum().item()) == 0 and torch.equal(s2, sa) and torch.equal(m2.view(ma.shape), ma)
+    if w * h <= 640 * 480:
+        scale = orc.master_fov_depth_scale(45.0, 60.0)
+        K = orc.camera_matrix(60.0, yfov, w, h)
+        msrc = km.source_constants(w, h, K, 100, "D1", scale)
+        for f in range(n):
+            theta = None if convs[f] == 0 else orc.convergence_angle(convs[f] * scale, 0.063)
+            views = [(orc.eye_pose(e, 0.063, theta), (K[0, 0], K[1, 1], K[0, 2], K[1, 2])) for e in ("left", "right")]
+            img, mask, zplane, _ = km.render_views_f32(depth[f], colour[f], msrc, views, w, h, (0, 255, 0), (0, 0, 0), True)
+            assert np.array_equal(sa[f].cpu().numpy(), img)
+            got_mask = ma[f].cpu().numpy()
+            assert np.array_equal(got_mask if not mask_rgb else (got_mask != 0).any(axis=-1).astype(np.uint8) * 255, mask)
+            assert np.array_equal(bits(da[f].cpu().numpy()), bits(zplane))
+
+
+def test_stereo_conv_vrows_limits_send_extreme_poses_to_the_generic_loop():
+    """Outside the virtual-row kernel's limits (width not a multiple of 32, convergence so close that the staircase is steeper
+    than 0.4 rows per 15 columns) "auto" renders through the generic loop -- same bytes as asking for it -- and "vrows" refuses."""
+    from metric_depth_video_toolbox_b200.stereo import StereoParams, StereoRerenderer
+
+    for (w, h), conv in (((70, 33), 3.0), ((640, 480), 0.05)):
+        depth, colour = SyntheticClip(w, h, 2).frames()
+        outs = []
+        for kernel in ("auto", "generic"):
+            rr = StereoRerenderer(StereoParams(w, h, xfov=60.0, convergence_depths=[conv, conv], conv_kernel=kernel), DEV)
+            outs.append(rr.render_device(cu(depth), cu(colour)))
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+        host = ops.conv_frames_packed(*rr.packed_cameras(0, 2), rr.p.near)
+        assert not ops.conv_vrows_supported(host, w, h)
+        with pytest.raises(ValueError):
+            StereoRerenderer(StereoParams(w, h, xfov=60.0, convergence_depths=[conv, conv], conv_kernel="vrows"), DEV).render_device(cu(depth), cu(colour))
+
+
 def test_pack_mask_bits_equals_numpy_packbits_and_host_api():
     """One bit per mask pixel (what render_host(mask_format="bits") ships over PCIe): np.packbits order, any non-zero byte
     counts as set, ragged tails, and the host API's packed masks unpack to exactly its u8 masks."""

@@ -351,3 +351,28 @@ def test_infill_finish_async_equals_finish_per_eye():
     for k in range(3):
         for e in range(2):
             assert np.array_equal(out[k, :, e * 128:(e + 1) * 128], infill.finish_mask(frames_before[k, :, e * 128:(e + 1) * 128]))
+
+
+def test_conv_vrows_limits_check_runs_on_the_host():
+    """mdvt_stereo_conv_vrows_supported makes no CUDA call: typical convergence distances pass at the sizes the kernel is built
+    for, a width that is not a multiple of 32, a pose that is not `y rotation + x shift`, and a convergence distance of a few
+    centimetres (staircase steeper than 0.4 rows per 15 columns) do not."""
+    import numpy as np
+
+    from metric_depth_video_toolbox_b200 import ops
+    from metric_depth_video_toolbox_b200.stereo import StereoParams, StereoRerenderer
+
+    def frames(w, h, convs):
+        rr = StereoRerenderer(StereoParams(w, h, xfov=60.0, convergence_depths=convs), "cpu")
+        return ops.conv_frames_packed(*rr.packed_cameras(0, len(convs)), rr.p.near)
+
+    assert ops.conv_vrows_supported(frames(1920, 1080, [5.0, 1.1, 0.75, 0.0]), 1920, 1080)
+    assert ops.conv_vrows_supported(frames(3840, 2160, [4.0, 1.5]), 3840, 2160)
+    assert not ops.conv_vrows_supported(frames(640, 480, [0.05]), 640, 480)
+    assert not ops.conv_vrows_supported(frames(70, 33, [3.0]), 70, 33)
+    assert not ops.conv_vrows_supported(frames(4096, 64, [3.0]), 4096, 64)
+    tilted = frames(640, 480, [3.0])
+    tilted[0, 8 + 9] = 1e-3  # M[9] of the left eye: a rotation about x sneaks in (the target row would depend on the depth)
+    assert not ops.conv_vrows_supported(tilted, 640, 480)
+    with pytest.raises(ValueError):
+        ops.conv_vrows_supported(np.zeros((2, 7), dtype=np.float32), 640, 480)
