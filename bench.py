@@ -367,11 +367,15 @@ def measure_paths(dev, peak: float, frames_1080: int = 32, frames_4k: int = 16, 
         T[:3, 3] = (0.05 * math.sin(0.17 * f), -0.02 * math.cos(0.11 * f), 0.1 * math.sin(0.07 * f))
         poses.append(T)
     common = dict(xfov=XFOV, max_depth=MAX_DEPTH, pupillary_distance=IPD_MM, master_xfov=MASTER_XFOV, infill_mask=True)
+    conv_list = [5.0 + 0.02 * f for f in range(n)]
     for key, extra, kernel, note in (
-            ("convergence_1080p", dict(convergence_depths=[5.0 + 0.02 * f for f in range(n)]), "mdvt::project_splat_kernel + mdvt::resolve_ckey_kernel",
-             f"{w}x{h} x {n} frames, stereo pair + hole masks with a per-frame convergence rotation (stereo_rerender --convergence_file)"),
-            ("convergence_1080p_fused_row_kernel", dict(convergence_depths=[5.0 + 0.02 * f for f in range(n)], conv_kernel=True),
-             "mdvt::stereo_conv_rows_kernel", f"the same frames through the fused target-row kernel (no global z-buffer; StereoParams.conv_kernel)"),
+            ("convergence_1080p", dict(convergence_depths=conv_list), "mdvt::stereo_conv_vrows_kernel",
+             f"{w}x{h} x {n} frames, stereo pair + hole masks with a per-frame convergence rotation (stereo_rerender --convergence_file, what movie_2_3D "
+             f"runs), default dispatch: the virtual-source-row kernel (TMA-assembled rows, shared-memory z-buffer, no global planes)"),
+            ("convergence_1080p_generic_loop", dict(convergence_depths=conv_list, conv_kernel="generic"),
+             "mdvt::project_splat_kernel + mdvt::resolve_ckey_kernel", "the same frames through the two-lane generic loop (global 64-bit z-buffer planes; the bytes are identical)"),
+            ("convergence_1080p_fused_row_kernel", dict(convergence_depths=conv_list, conv_kernel="rows"),
+             "mdvt::stereo_conv_rows_kernel", "the same frames through round 1's target-row kernel (per-column source-row prediction, byte gathers)"),
             ("posed_1080p", dict(transformations=poses), "mdvt::project_splat_kernel + mdvt::resolve_ckey_kernel",
              f"{w}x{h} x {n} frames, stereo pair + hole masks with a per-frame 4x4 camera pose (stereo_rerender --transformation_file)")):
         rr = StereoRerenderer(StereoParams(w, h, **common, **extra), dev)

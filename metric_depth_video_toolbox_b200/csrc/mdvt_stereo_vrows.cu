@@ -6,29 +6,34 @@
 // that leaves B_u = B_z = T_v = T_z = 0: Zv = z * r_z(j), u' = (z r_u(j) + T_u) / Zv, and v' = r_v(i, j) / r_z(j) does
 // not depend on the depth.  The source row that lands in target row r is, per source column j,
 //     i*(j) = ((r A_z - A_v) j + (r C_z - C_v)) / B_v            -- LINEAR in j, |slope| ~ sin(theta) |r - cy| / fx,
-// so along a target row the source row index is a staircase with a handful of steps.  A CTA owns one target row of both
-// eyes at a time.  Its producer warp evaluates the staircase per 16-pixel sub-block and eye in float64 and has the TMA
-// engine assemble, per eye, a VIRTUAL SOURCE ROW in shared memory: for each run of sub-blocks with the same source row
-// one cp.async.bulk of that row's depth bytes and one of its colour bytes, at the columns' natural offsets.  The compute
-// warps then treat the virtual row like the row-local kernel treats a real one: lane-strided columns, word loads, decode,
-// the exact float32 arithmetic of the generic path for Zv and u' (mdvt_splat.cu: FFMA chain, refined reciprocal, correctly
-// rounded quotient, magic-number rounding), conflict-free shared-memory atomics.
-//   * Where the float64 prediction says |v' - r| < 0.495 for every column of a sub-block, rint(v') == r is certain (the
-//     float32 chain is within 1e-3 px of the prediction) and v' is not even computed.  Otherwise (sub-blocks next to a
-//     step of the staircase, ~1 % of the pixels) the candidate goes through the exact v' arithmetic and must round to r,
-//     and the neighbouring source row that can also round into r is fetched as an ALTERNATE sub-block (48 + 48 bytes)
-//     and evaluated the same way.
+// so along a target row the source row index is a staircase with a handful of steps.
+//   * A unit of work is one target row of ONE eye.  CTAs of 5 compute warps + 1 producer warp, 4 per SM at 1080p, each
+//     walking a contiguous block of units.
+//   * The PRODUCER warp (one lane per staircase step, float64) has the TMA engine assemble the unit's VIRTUAL SOURCE ROW in
+//     shared memory: for every stretch of columns whose source row is certain, one cp.async.bulk of that row's depth bytes and
+//     one of its colour bytes at the columns' natural offsets (16-pixel sub-blocks of 48 bytes are the granularity).  "Certain"
+//     means the prediction |v' - r| < 0.494 holds with a margin the float32 chain cannot eat (it is within 2e-3 px of the
+//     prediction).  The narrow zones around the steps of the staircase -- about 1 % of the pixels at a convergence distance of
+//     5 m -- get zero depth bytes in the virtual row instead, and both source rows that can round into r there go on a list
+//     of ALTERNATE sub-blocks (48 + 48 bytes each, also fetched by TMA).  The producer runs two units ahead of the compute
+//     warps, so a unit's loads are issued a full unit time before their first use.
+//   * The COMPUTE warps treat the virtual row like the row-local kernel treats a real one: lane-strided columns, word loads,
+//     decode, the exact float32 arithmetic of the generic path for Zv and u' (mdvt_splat.cu: FFMA chain, refined reciprocal,
+//     correctly rounded quotient, magic-number rounding; v' is not computed at all for certain columns), conflict-free
+//     shared-memory reductions.  Alternates additionally go through the exact v' arithmetic and must round to r.
 //   * Visibility: nearest Zv wins, candidates with bit-identical Zv are ordered by packed colour -- the colour-keyed order
 //     of the generic frame loop (mdvt_render_views), so the results are bit-identical to it (asserted by the tests on every
 //     byte, mask and depth plane).  Shared memory has no 64-bit atomic min, so the 55-bit key is split over two 32-bit
 //     planes and two passes: (1) every candidate: ATOMS.MIN of float_bits(Zv) into the z plane; barrier; (2) every
 //     candidate whose Zv is the slot's minimum: ATOMS.MIN of its colour into the colour plane.  A thread keeps its
-//     candidates (slot, Zv bits, colour) in registers between the passes.
-//   * Phase B reads the colour plane four pixels at a time, re-arms both planes, packs RGB / mask bytes into the dead raw
-//     buffer of the row; the producer warp hands that to a TMA bulk store and meanwhile has loaded the next row.
+//     candidates (slot address, Zv bits) in registers between the passes and reads the colour in pass 2.
+//   * Phase B reads the colour plane four pixels at a time (an empty slot already holds the flagged fill colour), re-arms both
+//     planes and packs RGB / mask bytes into a staging row that leaves through a TMA bulk store.
 // HBM traffic is the algorithmic 14 B/px (each source row is read by ~2-3 neighbouring target rows of the same CTA and by
 // both eyes: L2 hits).  Geometry outside the limits below (checked on the host by mdvt_stereo_conv_vrows_supported) goes
 // through the generic frame loop instead.
+// Measured on the B200 (1080p, 32 frames per launch): 13.3 us per frame at a convergence distance of 5 m, 14.9 at 2 m, 18.1
+// at 1 m (generic two-lane loop: 18.9; round 1's target-row kernel: 23.0); profiles/r02_vrows_*.
 #include <cmath>
 #include <cstdlib>
 
@@ -37,35 +42,33 @@
 namespace mdvt {
 
 constexpr int kSub = 16;            // pixels per sub-block: 48 bytes of u8x3, the TMA granularity of the assembly
-constexpr int kAltSlots = 48;       // alternate sub-blocks with their data staged in shared memory (more are read from global memory)
+constexpr int kAltSlots = 24;       // alternate sub-blocks with their data staged in shared memory (more are read from global memory)
 constexpr uint32_t kEmpty32 = 0xFFFFFFFFu;
 constexpr float kVMagic = 12582912.0f;  // 1.5 * 2^23
 constexpr int kVMagicBits = 0x4B400000;
 constexpr float kVMagicInt = 8388608.0f;
-// (prediction windows, in pixels, sit next to their use in the producer: the float32 chain and the prediction of v' differ by
-// < 2e-3 px for coordinates < 8192)
 constexpr double kStepMin = 0.9, kStepMax = 1.12, kMaxSubSpan = 0.4;
 
 struct VrowSmem {
-    int alt_off, alt_stride;      // [2 buffers][1 + 4 nsub] u32: count, then eye << 31 | sub-block << 16 | source row
+    int alt_off, alt_stride;      // [2 buffers][1 + 4 nsub] u32: count, then sub-block << 16 | source row
     int altdata_off, altdata_stride;  // [2 buffers][kAltSlots][96]: depth 48 | colour 48
-    int raw_off, raw_stride;      // [2 buffers][2 eyes][depth 3W | colour 3W]
-    int zp_off, cp_off;           // [2 eyes][W + 4] u32 each
-    int out_off, mask_off, total; // staging of the left | right output row and of its mask row
+    int raw_off, raw_stride;      // [2 buffers][depth 3W | colour 3W]: the virtual source row of one eye
+    int zp_off, cp_off;           // [W + 4] u32 each
+    int out_off, mask_off, total; // staging of the eye's half of the output row and of its mask row
 };
 
 __host__ __device__ inline VrowSmem vrow_smem_layout(int width, int mask_bpp) {
     VrowSmem L;
     const int nsub = width / kSub;
-    int off = 64 + 2 * 96;  // [0,16): two mbarriers; [64, 256): two StairFrame slots
+    int off = 64 + 2 * 96 + 64;  // [0,16): two mbarriers; [64, 256): two StairFrame slots; [256, 320): both eyes' EyeConsts
     L.alt_off = off;  L.alt_stride = (1 + 4 * nsub) * 4;       off += 2 * L.alt_stride;
     off = (off + 15) & ~15;
     L.altdata_off = off; L.altdata_stride = kAltSlots * 96;    off += 2 * L.altdata_stride;
-    L.raw_off = off;  L.raw_stride = 12 * width;               off += 2 * L.raw_stride;
-    L.zp_off = off;   off += 2 * (width + 4) * 4;
-    L.cp_off = off;   off += 2 * (width + 4) * 4;
-    L.out_off = off;  off += 6 * width;
-    L.mask_off = off; off += 2 * width * mask_bpp;
+    L.raw_off = off;  L.raw_stride = 6 * width;                off += 2 * L.raw_stride;
+    L.zp_off = off;   off += (width + 4) * 4;
+    L.cp_off = off;   off += (width + 4) * 4;
+    L.out_off = off;  off += 3 * width;
+    L.mask_off = off; off += width * mask_bpp;
     L.total = (off + 15) & ~15;
     return L;
 }
@@ -156,15 +159,15 @@ __device__ __forceinline__ void named_barrier(int id, int count) { asm volatile(
 // alpha j + beta with alpha = r k1 - k0, beta = r c1 - c0 (k1 = A_z / B_v, k0 = A_v / B_v, c1 = C_z / B_v, c0 = C_v / B_v, float64),
 // and the row step |B_v / r_z(j)| lies in [smin, smax] for every row.
 struct StairFrame {
-    double k1[2], k0[2], c1[2], c0[2];
-    float smin[2], smax[2];
+    double k1[2], k0[2], c1[2], c0[2], m[2];
     int frame, pad;
 };
 
-// MASK_MODE: 0 none, 1 u8 {0,255}, 2 u8x3 (bg colour / black).  T threads; every thread owns the columns tid + n T, n < CPT.
-// GUARD: W < T * CPT (columns past the row are culled).
+// MASK_MODE: 0 none, 1 u8 {0,255}, 2 u8x3 (bg colour / black).  A unit of work is one target row of ONE eye (both eyes of a
+// row are consecutive units of the same CTA); T threads, every thread owns the columns tid + n T, n < CPT.  GUARD: W < T * CPT
+// (columns past the row are culled).
 template <int MASK_MODE, int T, int CPT, bool GUARD>
-__global__ void __launch_bounds__(T, T <= 384 ? 2 : 1)
+__global__ void __launch_bounds__(T + 32, T <= 160 ? 4 : 2)
     stereo_conv_vrows_kernel(const uint8_t *__restrict__ depth_rgb, const uint8_t *__restrict__ colour_rgb, int n_units, int width, int height,
                              const mdvt_conv_frame *__restrict__ frames, uint32_t bg_rgb, uint32_t fill_rgb, int collide,
                              uint8_t *__restrict__ out_sbs, uint8_t *__restrict__ out_mask, float *__restrict__ out_depth,
@@ -175,243 +178,266 @@ __global__ void __launch_bounds__(T, T <= 384 ? 2 : 1)
     const VrowSmem L = vrow_smem_layout(width, mask_bpp);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);  // bar[0], bar[1]: the two sets of row buffers
     StairFrame *s_stair = reinterpret_cast<StairFrame *>(smem + 64);  // [2]
-    const int tid = threadIdx.x, lane = tid & 31;
+    EyeConsts *s_eye = reinterpret_cast<EyeConsts *>(smem + 256);     // [2]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool producer = tid >= T;  // the last warp prepares rows (staircase, TMA loads), the others compute
     const int nsub = width / kSub;
-    const int n_items = 2 * ((nsub + 31) / 32);  // (eye, chunk of 32 sub-blocks): the units of the row preparation, one warp each
     const uint32_t row_bytes = 3u * width;
-    const int plane = width + 4;  // slots per eye (W + the dummy slot, padded to 16 bytes)
+    const uint32_t sm = smem_addr(smem);
 
     if (tid == 0) {
-        mbar_init(&bar[0], (uint32_t)n_items);
-        mbar_init(&bar[1], (uint32_t)n_items);
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
         mbar_fence_init();
         s_stair[0].frame = s_stair[1].frame = -1;
         *reinterpret_cast<uint32_t *>(smem + L.alt_off) = 0u;
         *reinterpret_cast<uint32_t *>(smem + L.alt_off + L.alt_stride) = 0u;
     }
-    {   // z planes: all ones; colour planes: the flagged fill colour (any real colour, < 2^24, beats it; a hole reads as the fill)
+    {   // z plane: all ones; colour plane: the flagged fill colour (any real colour, < 2^24, beats it; a hole reads as the fill)
         uint32_t *zp = reinterpret_cast<uint32_t *>(smem + L.zp_off), *cp = reinterpret_cast<uint32_t *>(smem + L.cp_off);
-        for (int k = tid; k < 2 * plane; k += T) {
+        for (int k = tid; k < width + 4; k += T + 32) {
             zp[k] = kEmpty32;
             cp[k] = fill_rgb | 0xFF000000u;
         }
     }
     __syncthreads();
 
-    // contiguous block of target rows per CTA: successive rows need almost the same source rows (L2 / TMA locality) and the
-    // frame constants change once or twice per CTA
-    const int per_cta = (n_units + gridDim.x - 1) / gridDim.x;
+    // contiguous block of units per CTA (an even number, so both eyes of a row stay together): successive rows need almost the
+    // same source rows (L2 / TMA locality) and the frame constants change once or twice per CTA
+    const int per_cta = (((n_units + gridDim.x - 1) / gridDim.x) + 1) & ~1;
     const int unit_begin = blockIdx.x * per_cta, unit_end = min(n_units, unit_begin + per_cta);
     if (unit_begin >= unit_end) return;
-    int frame = unit_begin / height, r = unit_begin - frame * height;  // the row being processed
-    int frame2 = frame, r2 = r;                                        // the row being prepared (two ahead in the steady state)
-    const int warp = tid >> 5;
+    // unit -> (frame, row, eye); tracked incrementally for the unit being processed and the unit being prepared (two ahead)
+    int frame = (unit_begin >> 1) / height, r = (unit_begin >> 1) - frame * height, eye = unit_begin & 1;
+    int frame2 = frame, r2 = r, eye2 = eye;
+    auto advance = [&](int &f, int &row, int &e) {
+        if (e == 0) { e = 1; return; }
+        e = 0;
+        if (++row == height) { row = 0; ++f; }
+    };
 
-    // ---- row preparation: one (eye, chunk) item per warp --------------------------------------------------------
-    // Sub-blocks whose source row is CERTAIN for every column go into the virtual row: runs of sub-blocks with one source row ->
-    // one bulk copy per array (a lane finds the end of its run in the ballot of the run starts).  Every other sub-block gets
-    // zero depth bytes (code 0 never passes Zv > near >= 0) and its candidates -- the predicted row where it is not certain,
-    // the neighbouring row where that one can round into r too -- go on the list of alternates, which are evaluated with the
-    // exact row test.  Per row the warp forms alpha and beta - r in float64 and rounds them to float32: the sub-block
-    // arithmetic runs on delta(j) = i*(j) - r, a number of a few tens at most (absolute error < 1e-5 rows against the 5e-3
-    // margin of the windows).  Every item arrives once on the row's mbarrier with its own transaction bytes.
-    auto prepare_items = [&](int buf) {  // row (frame2, r2) -> buffers `buf`
-        constexpr float kCertainF = 0.494f, kPossibleF = 0.506f;
-        for (int item = warp; item < n_items; item += kWarps) {
-            const int e = item & 1, s = (item >> 1) * 32 + lane;
-            StairFrame *sf = &s_stair[frame2 & 1];
-            double k1, k0, c1, c0;
-            float smin, smax;
-            if (sf->frame == frame2) {
-                k1 = sf->k1[e]; k0 = sf->k0[e]; c1 = sf->c1[e]; c0 = sf->c0[e]; smin = sf->smin[e]; smax = sf->smax[e];
-            } else {  // first row of a frame in this CTA: every preparing warp evaluates the constants itself, the eye-0 warp of chunk 0 publishes them
+    // ---- row preparation (producer warp): one lane per step of the staircase --------------------------------------------
+    // delta(j) = i*(j) - r = alpha j + beta' is linear in the column.  Around an integer k, for delta in (k - m, k + m) with
+    //     m = min(0.494 / smax, 1 - 0.506 / smin),
+    // source row r + k is CERTAIN to round into target row r and no neighbour can (the float32 chain is within 2e-3 px of this
+    // prediction; [smin, smax] bounds the row step |B_v / r_z(j)|).  Between those clean stretches lie the ZONES
+    // [k + m, k + 1 - m]: there rows r + k and r + k + 1 are both candidates and both get the exact row test.  So the producer
+    // enumerates the zones that meet the row -- lane c takes zone c in column order -- turns each into a range of sub-blocks
+    // (conservatively: +- 0.25 px), and
+    //   * the clean stretch before zone c (lane c; lane K the one after the last zone) becomes ONE bulk copy per array of
+    //     source row r + k into the virtual row (zero depth bytes where that row is outside the frame: code 0 never passes
+    //     Zv > near >= 0);
+    //   * every sub-block of a zone gets zero depth bytes in the virtual row and two entries on the list of alternates.
+    // alpha, beta' and the zone borders are evaluated in float64 (a handful of operations per lane).  The warp arrives once on
+    // the unit's mbarrier with the sum of its transaction bytes (posted after the copies are issued: the phase cannot complete
+    // before that arrival, and tx-counts may run negative meanwhile).
+    auto prepare_items = [&](int buf) {  // unit (frame2, r2, eye2) -> buffers `buf`
+        const int e = eye2;
+        StairFrame *sf = &s_stair[frame2 & 1];
+        if (sf->frame != frame2) {  // first unit of a frame in this CTA (always eye 0 or the CTA's very first unit): both eyes at once
+            __syncwarp();
+            if (lane < 2) {
                 const mdvt_conv_frame *fc = frames + frame2;
                 float M[12];
 #pragma unroll
-                for (int k = 0; k < 12; ++k) M[k] = __ldg(&fc->view[e].M[k]);
-                const RayView rv = make_ray_view(__ldg(&fc->fx), __ldg(&fc->fy), __ldg(&fc->cx), __ldg(&fc->cy), 1.0f, 1.0f, M, __ldg(&fc->view[e].fx),
-                                                 __ldg(&fc->view[e].fy), __ldg(&fc->view[e].cx), __ldg(&fc->view[e].cy));
+                for (int k = 0; k < 12; ++k) M[k] = __ldg(&fc->view[lane].M[k]);
+                const RayView rv = make_ray_view(__ldg(&fc->fx), __ldg(&fc->fy), __ldg(&fc->cx), __ldg(&fc->cy), 1.0f, 1.0f, M,
+                                                 __ldg(&fc->view[lane].fx), __ldg(&fc->view[lane].fy), __ldg(&fc->view[lane].cx), __ldg(&fc->view[lane].cy));
                 const double Bv = rv.B[1];
-                k1 = (double)rv.A[2] / Bv; k0 = (double)rv.A[1] / Bv; c1 = (double)rv.C[2] / Bv; c0 = (double)rv.C[1] / Bv;
-                const Staircase top = staircase_of(rv, 0, width), bottom = staircase_of(rv, height - 1, width);
-                smin = (float)top.smin * 0.999999f; smax = (float)top.smax * 1.000001f;  // the step does not depend on the row
-                const bool bad = !staircase_ok(top) || !staircase_ok(bottom) || rv.B[0] != 0.0f || rv.B[2] != 0.0f || rv.T[1] != 0.0f || rv.T[2] != 0.0f;
-                if (bad && status && lane == 0) status[frame2] = 1;
-                if (item < 2 && lane == 0) {  // items 0 / 1: eye 0 / 1 of the first chunk (always present)
-                    sf->k1[e] = k1; sf->k0[e] = k0; sf->c1[e] = c1; sf->c0[e] = c0; sf->smin[e] = smin; sf->smax[e] = smax;
-                }
-            }
-            const double rd = (double)r2;
-            const float alpha = (float)(rd * k1 - k0), beta = (float)((rd * c1 - c0) - rd);
-            const bool in = s < nsub;
-            const float da = __fmaf_rn(alpha, (float)(s * kSub), beta), db = __fmaf_rn(alpha, (float)(s * kSub + kSub - 1), beta);
-            const float dlo = fminf(da, db), dhi = fmaxf(da, db);
-            const float ipd = rintf(0.5f * (da + db));
-            const bool certain = fmaxf(fabsf(ipd - da), fabsf(ipd - db)) * smax < kCertainF;
-            const bool up = (ipd + 1.0f - dhi) * smin <= kPossibleF;    // row ip + 1 can round into r somewhere in the sub-block
-            const bool down = (dlo - (ipd - 1.0f)) * smin <= kPossibleF;
-            const int ip = r2 + (int)ipd;
-            const bool ip_ok = ip >= 0 && ip < height;
-            const int prim = !in ? -2 : ((ip_ok && certain) ? ip : -1);   // source row of the virtual row, -1: none
-            if (in && up && down && status) status[frame2] = 1;  // cannot happen inside the limits (kMaxSubSpan)
-            uint8_t *raw = smem + L.raw_off + buf * L.raw_stride;
-            uint8_t *vd = raw + e * 2 * row_bytes, *vc = vd + row_bytes;
-            const uint8_t *dframe = depth_rgb + (int64_t)frame2 * height * row_bytes;
-            const uint8_t *cframe = colour_rgb + (int64_t)frame2 * height * row_bytes;
-            // alternates: the uncertain predicted row, then the neighbour; slots through one shared-memory atomic per item
-            uint32_t *alt = reinterpret_cast<uint32_t *>(smem + L.alt_off + buf * L.alt_stride);
-            uint8_t *altdata = smem + L.altdata_off + buf * L.altdata_stride;
-            const int ia = ip + (up ? 1 : -1);
-            const bool alt_p = in && ip_ok && !certain, alt_n = in && (up || down) && ia >= 0 && ia < height;
-            const uint32_t mp = __ballot_sync(0xFFFFFFFFu, alt_p), mn = __ballot_sync(0xFFFFFFFFu, alt_n);
-            int n_staged = 0;
-            if (mp | mn) {
-                uint32_t base = 0;
-                if (lane == 0) base = atoms_add(smem_addr(alt), (uint32_t)(__popc(mp) + __popc(mn)));
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                const uint32_t below = (1u << lane) - 1u;
-                const uint32_t slot_p = base + __popc(mp & below), slot_n = base + __popc(mp) + __popc(mn & below);
-                auto add = [&](uint32_t slot, int row) {
-                    alt[1 + slot] = ((uint32_t)e << 31) | ((uint32_t)s << 16) | (uint32_t)row;
-                    if (slot < (uint32_t)kAltSlots) {
-                        const int64_t goff = ((int64_t)row * width + (int64_t)s * kSub) * 3;
-                        bulk_load(altdata + 96 * slot, dframe + goff, 48u, &bar[buf]);
-                        bulk_load(altdata + 96 * slot + 48, cframe + goff, 48u, &bar[buf]);
-                    }
-                };
-                if (alt_p) add(slot_p, ip);
-                if (alt_n) add(slot_n, ia);
-                const int total = __popc(mp) + __popc(mn);
-                n_staged = max(0, min((int)base + total, kAltSlots) - min((int)base, kAltSlots));
-            }
-            // runs
-            int prev = __shfl_up_sync(0xFFFFFFFFu, prim, 1);
-            if (lane == 0) prev = -3;
-            const uint32_t starts = __ballot_sync(0xFFFFFFFFu, in && prim != prev);
-            const int n_loaded = __popc(__ballot_sync(0xFFFFFFFFu, prim >= 0));
-            if (prim == -1) {
-                uint4 *z4 = reinterpret_cast<uint4 *>(vd + 48 * s);
-                z4[0] = z4[1] = z4[2] = make_uint4(0u, 0u, 0u, 0u);
-            } else if (prim >= 0 && prim != prev) {
-                const uint32_t above = lane == 31 ? 0u : (starts >> (lane + 1));
-                int len = above ? __ffs(above) : 32 - lane;
-                len = min(len, nsub - s);
-                const int64_t goff = ((int64_t)prim * width + (int64_t)s * kSub) * 3;
-                bulk_load(vd + 48 * s, dframe + goff, 48u * (uint32_t)len, &bar[buf]);
-                bulk_load(vc + 48 * s, cframe + goff, 48u * (uint32_t)len, &bar[buf]);
+                sf->k1[lane] = (double)rv.A[2] / Bv; sf->k0[lane] = (double)rv.A[1] / Bv;
+                sf->c1[lane] = (double)rv.C[2] / Bv; sf->c0[lane] = (double)rv.C[1] / Bv;
+                const Staircase top = staircase_of(rv, 0, width), bottom = staircase_of(rv, height - 1, width);  // the step does not depend on the row
+                const double m = fmin(0.494 / (top.smax * 1.000001), 1.0 - 0.506 / (top.smin * 0.999999));
+                sf->m[lane] = m;
+                const bool bad = !staircase_ok(top) || !staircase_ok(bottom) || rv.B[0] != 0.0f || rv.B[2] != 0.0f || rv.T[1] != 0.0f || rv.T[2] != 0.0f ||
+                                 !(m > 0.4);
+                if (bad && status) status[frame2] = 1;
             }
             __syncwarp();
-            if (lane == 0) mbar_expect_tx(&bar[buf], 96u * (uint32_t)(n_loaded + n_staged));
+            if (lane == 0) sf->frame = frame2;
+            __syncwarp();
         }
+        const double rd = (double)r2, m = sf->m[e];
+        const double alpha = rd * sf->k1[e] - sf->k0[e], beta = (rd * sf->c1[e] - sf->c0[e]) - rd;
+        const double d0 = beta, d1 = alpha * (double)(width - 1) + beta;
+        const double dmin = fmin(d0, d1), dmax = fmax(d0, d1);
+        const int kA = (int)ceil(dmin - 1.0 + m), kB = (int)floor(dmax - m);   // zones kA .. kB meet the row
+        const int K = max(0, kB - kA + 1);
+        const bool rising = alpha >= 0.0;
+        const bool flat = fabs(alpha) < 1e-12;
+        const double inv_alpha = flat ? 0.0 : 1.0 / alpha;
+        uint8_t *vd = smem + L.raw_off + buf * L.raw_stride, *vc = vd + row_bytes;
+        const uint8_t *dframe = depth_rgb + (int64_t)frame2 * height * row_bytes;
+        const uint8_t *cframe = colour_rgb + (int64_t)frame2 * height * row_bytes;
+        uint32_t *alt = reinterpret_cast<uint32_t *>(smem + L.alt_off + buf * L.alt_stride);
+        uint8_t *altdata = smem + L.altdata_off + buf * L.altdata_stride;
+        const uint32_t alt_count_a = sm + L.alt_off + buf * L.alt_stride;
+        const int k_clean = (int)rint(0.5 * (d0 + d1));  // the one clean row when no zone meets the row
+        int tx = 0;            // sub-blocks (48 + 48 bytes) this lane has bulk copies in flight for
+        int carry_sb = -1;     // last sub-block of the previous zone (in column order)
+        for (int c0 = 0; c0 <= K; c0 += 32) {
+            const int c = c0 + lane;
+            // zone c (c < K): its index k, its sub-block range [sa, sb]; lane K carries the sentinel sa = nsub
+            const int k = rising ? kA + c : kB - c;
+            int sa = nsub, sb = nsub;
+            if (c < K) {
+                if (flat) {
+                    sa = 0; sb = nsub - 1;
+                } else {
+                    const double ja = ((double)k + m - beta) * inv_alpha, jb = ((double)k + 1.0 - m - beta) * inv_alpha;
+                    const double jlo = fmin(ja, jb) - 0.25, jhi = fmax(ja, jb) + 0.25;
+                    // (a zone that numerically just misses the row is clamped onto the edge sub-block: testing that one exactly is harmless)
+                    sa = (int)fmin(fmax(floor(jlo * (1.0 / kSub)), 0.0), (double)(nsub - 1));
+                    sb = (int)fmin(fmax(floor(jhi * (1.0 / kSub)), (double)sa), (double)(nsub - 1));
+                }
+            }
+            int prev_sb = __shfl_up_sync(0xFFFFFFFFu, sb, 1);
+            if (lane == 0) prev_sb = carry_sb;
+            carry_sb = __shfl_sync(0xFFFFFFFFu, sb, 31);
+            if (c <= K) {
+                // clean stretch before zone c (after the last zone for c == K)
+                const int s_first = prev_sb + 1, s_last = sa - 1;
+                if (s_last >= s_first) {
+                    const int krow = K == 0 ? k_clean : (c < K ? (rising ? k : k + 1) : (rising ? kB + 1 : kA));
+                    const int row = r2 + krow;
+                    if (row >= 0 && row < height) {
+                        const int64_t goff = ((int64_t)row * width + (int64_t)s_first * kSub) * 3;
+                        const uint32_t bytes = 48u * (uint32_t)(s_last - s_first + 1);
+                        bulk_load(vd + 48 * s_first, dframe + goff, bytes, &bar[buf]);
+                        bulk_load(vc + 48 * s_first, cframe + goff, bytes, &bar[buf]);
+                        tx += s_last - s_first + 1;
+                    } else {
+                        for (int s = s_first; s <= s_last; ++s) {
+                            uint4 *z4 = reinterpret_cast<uint4 *>(vd + 48 * s);
+                            z4[0] = z4[1] = z4[2] = make_uint4(0u, 0u, 0u, 0u);
+                        }
+                    }
+                }
+                // the zone itself
+                if (c < K) {
+                    for (int s = sa; s <= sb; ++s) {
+                        uint4 *z4 = reinterpret_cast<uint4 *>(vd + 48 * s);
+                        z4[0] = z4[1] = z4[2] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                        for (int up = 0; up < 2; ++up) {
+                            const int row = r2 + k + up;
+                            if (row < 0 || row >= height) continue;
+                            const uint32_t slot = atoms_add(alt_count_a, 1u);
+                            alt[1 + slot] = ((uint32_t)s << 16) | (uint32_t)row;
+                            if (slot < (uint32_t)kAltSlots) {
+                                const int64_t goff = ((int64_t)row * width + (int64_t)s * kSub) * 3;
+                                bulk_load(altdata + 96 * slot, dframe + goff, 48u, &bar[buf]);
+                                bulk_load(altdata + 96 * slot + 48, cframe + goff, 48u, &bar[buf]);
+                                ++tx;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        tx = __reduce_add_sync(0xFFFFFFFFu, tx);
+        __syncwarp();  // every lane's zero bytes and list entries are in place before the arrival that publishes them
+        if (lane == 0) mbar_expect_tx(&bar[buf], 96u * (uint32_t)tx);
     };
-    auto publish_frame = [&]() {  // after the items of a row: the constants of its frame are in place for the following rows
-        if (tid == 0) s_stair[frame2 & 1].frame = frame2;
-    };
-
-    // prologue: the first two rows
-    prepare_items(0);
-    __syncthreads();
-    publish_frame();
-    __syncthreads();
-    if (unit_begin + 1 < unit_end) {
-        if (++r2 == height) { r2 = 0; ++frame2; }
-        prepare_items(1);
-        __syncthreads();
-        publish_frame();
+    if (producer) {
+        // Two units ahead of the compute warps: the buffers of unit u (virtual row, alternates) are free once every compute warp
+        // has passed barrier (B) of unit u -- the producer joins that barrier and then prepares unit u + 2 into them, so a unit's
+        // loads are issued a full unit time before their first use.
+        prepare_items(0);
+        if (unit_begin + 1 < unit_end) {
+            advance(frame2, r2, eye2);
+            prepare_items(1);
+        }
+        int it = 0;
+        for (int unit = unit_begin; unit < unit_end; ++unit, ++it) {
+            named_barrier(2, T + 32);  // (B) of this unit
+            if (unit + 2 < unit_end) {
+                advance(frame2, r2, eye2);
+                prepare_items(it & 1);
+            }
+        }
+        return;
     }
-    __syncthreads();
 
-    const uint32_t sm = smem_addr(smem);
     const uint32_t byte0 = 3u * tid;
     const uint32_t shift = (byte0 & 3u) * 8u;  // loop-invariant: the column step T moves 3T bytes, a multiple of 4
     const uint32_t dp_off = byte0 & ~3u;
     const uint32_t flagged_fill = fill_rgb | 0xFF000000u;
     const uint32_t bg_match = (collide & 1) ? bg_rgb : kEmpty32;
-    const int dbg = collide >> 8;  // development switch (MDVT_VROWS_SKIP): 1 = no pass 2, 2 = no phase B, 4 = no pass 1 reductions
     const uint4 empty4 = make_uint4(kEmpty32, kEmpty32, kEmpty32, kEmpty32), fill4 = make_uint4(flagged_fill, flagged_fill, flagged_fill, flagged_fill);
-    const uint32_t zp_a = sm + L.zp_off;                       // z plane of eye 0; eye 1 at + 4 plane
+    const uint32_t zp_a = sm + L.zp_off;
     const uint32_t cp_delta = (uint32_t)(L.cp_off - L.zp_off);  // colour plane of the same slot
-    const uint32_t eye_stride = 4u * (uint32_t)plane;
     const uint32_t w32 = (uint32_t)width;
     const uint32_t bar_a = sm;  // the two mbarriers
     const uint32_t out_a = sm + L.out_off, mask_a = sm + L.mask_off;
     const float fj0 = __int2float_rn(tid);
     int ray_frame = -1;
-    EyeConsts ec[2];
     float dec16 = 0.0f, neg_bias = 0.0f, depth_scale = 0.0f, near_plane = 0.0f;
 
     int it = 0;
     for (int unit = unit_begin; unit < unit_end; ++unit, ++it) {
         const int buf = it & 1;
-        if (frame != ray_frame) {  // once or twice per CTA: every thread evaluates both eyes' coefficients itself (float64, ~200 instructions)
+        if (frame != ray_frame) {  // once or twice per CTA: both eyes' float32 coefficients (float64 inside make_ray_view) -> shared memory
             const mdvt_conv_frame *fc = frames + frame;
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                float M[12];
-#pragma unroll
-                for (int k = 0; k < 12; ++k) M[k] = __ldg(&fc->view[e].M[k]);
-                const RayView rv = make_ray_view(__ldg(&fc->fx), __ldg(&fc->fy), __ldg(&fc->cx), __ldg(&fc->cy), 1.0f, 1.0f, M,
-                                                 __ldg(&fc->view[e].fx), __ldg(&fc->view[e].fy), __ldg(&fc->view[e].cx), __ldg(&fc->view[e].cy));
-                ec[e].Au = rv.A[0]; ec[e].Av = rv.A[1]; ec[e].Az = rv.A[2];
-                ec[e].Cu = rv.C[0]; ec[e].Cv = rv.C[1]; ec[e].Cz = rv.C[2];
-                ec[e].Bv = rv.B[1]; ec[e].Tu = rv.T[0];
-            }
             dec16 = __fmul_rn(__ldg(&fc->dec_const), 65536.0f);  // exact: fl32(c16 << 16) * dec == fl32(c16) * dec16
             neg_bias = -__fmul_rn(kVMagicInt, dec16);
             depth_scale = __ldg(&fc->depth_scale);
             near_plane = __ldg(&fc->near_plane);
+            named_barrier(1, T);  // nobody still reads the previous frame's coefficients
+            if (tid < 2) {
+                float M[12];
+#pragma unroll
+                for (int k = 0; k < 12; ++k) M[k] = __ldg(&fc->view[tid].M[k]);
+                const RayView rv = make_ray_view(__ldg(&fc->fx), __ldg(&fc->fy), __ldg(&fc->cx), __ldg(&fc->cy), 1.0f, 1.0f, M, __ldg(&fc->view[tid].fx),
+                                                 __ldg(&fc->view[tid].fy), __ldg(&fc->view[tid].cx), __ldg(&fc->view[tid].cy));
+                EyeConsts k;
+                k.Au = rv.A[0]; k.Av = rv.A[1]; k.Az = rv.A[2];
+                k.Cu = rv.C[0]; k.Cv = rv.C[1]; k.Cz = rv.C[2];
+                k.Bv = rv.B[1]; k.Tu = rv.T[0];
+                s_eye[tid] = k;
+            }
+            named_barrier(1, T);
             ray_frame = frame;
         }
+        const EyeConsts ec = s_eye[eye];
         const uint32_t raw_a = sm + L.raw_off + buf * L.raw_stride;
-        const uint32_t bd0 = raw_a + dp_off, bd1 = bd0 + 2u * row_bytes;   // this thread's first pixel in the depth rows of eye 0 / 1
+        const uint32_t bd = raw_a + dp_off;   // this thread's first pixel in the depth row
         const uint32_t alt_a = sm + L.alt_off + buf * L.alt_stride;
         const uint8_t *altdata = smem + L.altdata_off + buf * L.altdata_stride;
         mbar_wait_a(bar_a + 8u * (uint32_t)buf, (uint32_t)((it >> 1) & 1));
 
         // ---- pass 1: every candidate -> z plane ------------------------------------------------------------
-        uint32_t c_addr[CPT][2], c_z[CPT][2];  // byte address of the candidate's z-plane slot, key bits of its Zv
-        auto decode_z = [&](uint32_t lo, uint32_t hi) {
-            const uint32_t px = __funnelshift_r(lo, hi, shift);           // [R, G, B, next]
-            const uint32_t t = __byte_perm(px, 0x4B000000u, 0x7402);      // 0x4B00RRBB: float value 2^23 + code16
-            return __fmul_rn(__fmaf_rn(__uint_as_float(t), dec16, neg_bias), depth_scale);
-        };
-        constexpr int NB = CPT % 3 == 0 ? 3 : (CPT % 2 == 0 ? 2 : CPT);  // columns per batch: all shared-memory loads first, reductions last
+        uint32_t c_addr[CPT], c_z[CPT];  // byte address of the candidate's z-plane slot, key bits of its Zv
+        constexpr int NB = CPT % 4 == 0 ? 4 : (CPT % 3 == 0 ? 3 : (CPT % 2 == 0 ? 2 : 1));  // columns per batch: loads first, reductions last
 #pragma unroll
         for (int n0 = 0; n0 < CPT; n0 += NB) {
-            uint32_t dlo[NB][2], dhi[NB][2];
+            uint32_t dlo[NB], dhi[NB];
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
                 const uint32_t o = (uint32_t)((n0 + b) * 3 * T);
-                dlo[b][0] = lds32(bd0 + o); dhi[b][0] = lds32(bd0 + o + 4u);
-                dlo[b][1] = lds32(bd1 + o); dhi[b][1] = lds32(bd1 + o + 4u);
+                dlo[b] = lds32(bd + o); dhi[b] = lds32(bd + o + 4u);
             }
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
                 const int n = n0 + b;
                 const float fj = __fadd_rn(fj0, (float)(n * T));  // exact
+                const uint32_t px = __funnelshift_r(dlo[b], dhi[b], shift);           // [R, G, B, next]
+                const uint32_t t = __byte_perm(px, 0x4B000000u, 0x7402);              // 0x4B00RRBB: float value 2^23 + code16
+                const float z = __fmul_rn(__fmaf_rn(__uint_as_float(t), dec16, neg_bias), depth_scale);
+                float Zv, rz;
+                uint32_t slot = vrow_project(z, fj, ec, near_plane, w32, c_z[n], Zv, rz);
+                if (GUARD) slot = (tid + n * T < width) ? slot : w32;
+                c_addr[n] = zp_a + 4u * slot;
+            }
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const float z = decode_z(dlo[b][e], dhi[b][e]);
-                    float Zv, rz;
-                    uint32_t slot = vrow_project(z, fj, ec[e], near_plane, w32, c_z[n][e], Zv, rz);
-                    if (GUARD) slot = (tid + n * T < width) ? slot : w32;
-                    c_addr[n][e] = zp_a + (uint32_t)e * eye_stride + 4u * slot;
-                }
-            }
-            if (!(dbg & 4)) {
-#pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                reds_min(c_addr[n0 + b][0], c_z[n0 + b][0]);
-                reds_min(c_addr[n0 + b][1], c_z[n0 + b][1]);
-            }
-            }
+            for (int b = 0; b < NB; ++b) reds_min(c_addr[n0 + b], c_z[n0 + b]);
         }
         // alternates: half a warp per sub-block and source row, with the exact row test; the first kAltSlots from shared
         // memory, the rest (strong rotations only) from global memory
         const int n_alt = (int)lds32(alt_a);
         auto alternate = [&](int a, uint32_t &addr, uint32_t &zb, uint32_t &col) {
             const uint32_t ent = lds32(alt_a + 4u + 4u * (uint32_t)a);
-            const int e = (int)(ent >> 31), s = (int)((ent >> 16) & 0x7FFFu), ia = (int)(ent & 0xFFFFu);
+            const int s = (int)(ent >> 16), ia = (int)(ent & 0xFFFFu);
             const int j = s * kSub + (lane & 15);
             uint32_t red, blue;
             if (a < kAltSlots) {
@@ -425,12 +451,11 @@ __global__ void __launch_bounds__(T, T <= 384 ? 2 : 1)
             }
             const uint32_t t = 0x4B000000u | (red << 8) | blue;
             const float z = __fmul_rn(__fmaf_rn(__uint_as_float(t), dec16, neg_bias), depth_scale);
-            const EyeConsts &k = e ? ec[1] : ec[0];
             const float fj = __int2float_rn(j);
             float Zv, rz;
-            uint32_t slot = vrow_project(z, fj, k, near_plane, w32, zb, Zv, rz);
-            if (vrow_target_row(z, fj, k, (float)ia, Zv, rz) != r) slot = w32;
-            addr = zp_a + (uint32_t)e * eye_stride + 4u * slot;
+            uint32_t slot = vrow_project(z, fj, ec, near_plane, w32, zb, Zv, rz);
+            if (vrow_target_row(z, fj, ec, (float)ia, Zv, rz) != r) slot = w32;
+            addr = zp_a + 4u * slot;
         };
         const int a0 = 2 * warp + (lane >> 4);  // this half-warp's first alternate stays in registers for pass 2, later ones are re-evaluated
         uint32_t a0_addr = zp_a + 4u * w32, a0_z = kEmpty32, a0_col = kEmpty32;
@@ -443,33 +468,28 @@ __global__ void __launch_bounds__(T, T <= 384 ? 2 : 1)
             alternate(a, addr, zb, col);
             reds_min(addr, zb);
         }
-        named_barrier(1, T);  // (A) the z planes hold the nearest Zv of every slot
+        named_barrier(1, T);  // (A) the z plane holds the nearest Zv of every slot
         if (tid == 0) {
-            sts32(alt_a, 0u);      // everybody has read this row's alternate count: the list is free for the row after next
-            sts32(sm + 48u, 0u);   // phase B's work counter
+            sts32(alt_a, 0u);      // everybody has read this unit's alternate count: the list is free for the unit after next
         }
 
         // ---- pass 2: the candidates that hold a slot's minimum -> colour plane ------------------------------------
         // (the colours are read here, not in pass 1: fewer registers live across the barrier; a candidate parked on the dummy
         //  slot may write its colour there, nobody reads it)
-        if (!(dbg & 1))
 #pragma unroll
         for (int n0 = 0; n0 < CPT; n0 += NB) {
-            uint32_t zwin[NB][2], clo[NB][2], chi[NB][2];
+            uint32_t zwin[NB], clo[NB], chi[NB];
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
                 const uint32_t o = (uint32_t)((n0 + b) * 3 * T) + row_bytes;
-                zwin[b][0] = lds32(c_addr[n0 + b][0]); zwin[b][1] = lds32(c_addr[n0 + b][1]);
-                clo[b][0] = lds32(bd0 + o); chi[b][0] = lds32(bd0 + o + 4u);
-                clo[b][1] = lds32(bd1 + o); chi[b][1] = lds32(bd1 + o + 4u);
+                zwin[b] = lds32(c_addr[n0 + b]);
+                clo[b] = lds32(bd + o); chi[b] = lds32(bd + o + 4u);
             }
 #pragma unroll
-            for (int b = 0; b < NB; ++b)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const uint32_t col = __funnelshift_r(clo[b][e], chi[b][e], shift) & 0xFFFFFFu;
-                    reds_min(c_addr[n0 + b][e] + cp_delta, zwin[b][e] == c_z[n0 + b][e] ? col : kEmpty32);
-                }
+            for (int b = 0; b < NB; ++b) {
+                const uint32_t col = __funnelshift_r(clo[b], chi[b], shift) & 0xFFFFFFu;
+                reds_min(c_addr[n0 + b] + cp_delta, zwin[b] == c_z[n0 + b] ? col : kEmpty32);
+            }
         }
         if (a0 < n_alt && lds32(a0_addr) == a0_z) reds_min(a0_addr + cp_delta, a0_col);
         for (int a = a0 + 2 * kWarps; a < n_alt; a += 2 * kWarps) {
@@ -477,26 +497,16 @@ __global__ void __launch_bounds__(T, T <= 384 ? 2 : 1)
             alternate(a, addr, zb, col);
             if (lds32(addr) == zb) reds_min(addr + cp_delta, col);
         }
-        if (tid == 0) bulk_wait_read<0>();  // the previous row's staged output has left shared memory (its store was issued a row ago)
-        named_barrier(1, T);  // (B) both planes final; this row's virtual rows and alternates are dead
-        if (unit + 2 < unit_end) {  // ... so the row after next is prepared into the same buffers: its loads have a full row time
-            if (++r2 == height) { r2 = 0; ++frame2; }
-            prepare_items(buf);
-        }
+        if (tid == 0) bulk_wait_read<0>();  // the previous unit's staged output has left shared memory (its store was issued a unit ago)
+        named_barrier(2, T + 32);  // (B) both planes final; this unit's virtual row and alternates are dead: the producer reloads them
 
         // ---- phase B: planes -> colours, hole mask, depth; planes re-armed ---------------------------------------------
+        const int row_unit = unit >> 1;  // frame * height + r
         {
-            const int groups = width / 4;  // per eye; item k < 2 groups: eye e = k / groups, 4 consecutive target pixels
+            const int groups = width / 4;  // 4 consecutive target pixels each
             constexpr int mwpg = MASK_MODE == 2 ? 3 : 1;
-            // 32 groups at a time, handed out through a shared-memory counter: the warps that prepared a row item above join later
-            for (; !(dbg & 2);) {
-                int k = 0;
-                if (lane == 0) k = (int)atoms_add(sm + 48u, 32u);
-                k = __shfl_sync(0xFFFFFFFFu, k, 0) + lane;
-                if (k - lane >= 2 * groups) break;
-                if (k >= 2 * groups) continue;
-                const int e = k >= groups;
-                const uint32_t za = zp_a + 16u * (uint32_t)k + (e ? 16u : 0u);  // eye 1's plane starts 4 slots (the dummy tail) later
+            for (int k = tid; k < groups; k += T) {
+                const uint32_t za = zp_a + 16u * (uint32_t)k;
                 const uint4 c4 = lds128(za + cp_delta);
                 if (out_depth) {
                     const uint4 z4 = lds128(za);
@@ -505,7 +515,7 @@ __global__ void __launch_bounds__(T, T <= 384 ? 2 : 1)
                     d.y = z4.y == kEmpty32 ? 0.0f : __uint_as_float(z4.y);
                     d.z = z4.z == kEmpty32 ? 0.0f : __uint_as_float(z4.z);
                     d.w = z4.w == kEmpty32 ? 0.0f : __uint_as_float(z4.w);
-                    reinterpret_cast<float4 *>(out_depth + (int64_t)unit * 2 * width)[k] = d;
+                    reinterpret_cast<float4 *>(out_depth + ((int64_t)row_unit * 2 + eye) * width)[k] = d;
                 }
                 sts128(za + cp_delta, fill4);
                 sts128(za, empty4);
@@ -513,7 +523,7 @@ __global__ void __launch_bounds__(T, T <= 384 ? 2 : 1)
                 const uint32_t p1 = c4.y == bg_match ? flagged_fill : c4.y;
                 const uint32_t p2 = c4.z == bg_match ? flagged_fill : c4.z;
                 const uint32_t p3 = c4.w == bg_match ? flagged_fill : c4.w;
-                const uint32_t oa = out_a + 12u * (uint32_t)k;  // left | right output row
+                const uint32_t oa = out_a + 12u * (uint32_t)k;
                 sts32(oa, __byte_perm(p0, p1, 0x4210));
                 sts32(oa + 4u, __byte_perm(p1, p2, 0x5421));
                 sts32(oa + 8u, __byte_perm(p2, p3, 0x6542));
@@ -529,14 +539,13 @@ __global__ void __launch_bounds__(T, T <= 384 ? 2 : 1)
             }
         }
         fence_async_smem();
-        named_barrier(1, T);  // (C) staged row complete
-        if (unit + 2 < unit_end) publish_frame();
-        if (tid == 0) {
-            bulk_store(out_sbs + (int64_t)unit * 2 * row_bytes, smem + L.out_off, 2 * row_bytes);
-            if (MASK_MODE != 0) bulk_store(out_mask + (int64_t)unit * 2 * width * mask_bpp, smem + L.mask_off, 2 * width * mask_bpp);
+        named_barrier(1, T);  // (C) staged half row complete
+        if (tid == 0) {  // this eye's half of the side-by-side row and of its mask row
+            bulk_store(out_sbs + ((int64_t)row_unit * 2 + eye) * row_bytes, smem + L.out_off, row_bytes);
+            if (MASK_MODE != 0) bulk_store(out_mask + ((int64_t)row_unit * 2 + eye) * width * mask_bpp, smem + L.mask_off, width * mask_bpp);
             bulk_commit();
         }
-        if (++r == height) { r = 0; ++frame; }
+        advance(frame, r, eye);
     }
     if (tid == 0) bulk_wait_all<0>();
 }
@@ -563,15 +572,6 @@ extern "C" int mdvt_stereo_conv_vrows_supported(const mdvt_conv_frame *frames_ho
     return 1;
 }
 
-static int vrows_dbg() {
-    static const int v = getenv("MDVT_VROWS_SKIP") ? atoi(getenv("MDVT_VROWS_SKIP")) : 0;
-    return v;
-}
-static bool vrows_t384() {  // development switch: MDVT_VROWS_T=384 -> 384 threads x 5 columns instead of 320 x 6 at widths up to 1920
-    static const bool v = getenv("MDVT_VROWS_T") && atoi(getenv("MDVT_VROWS_T")) == 384;
-    return v;
-}
-
 extern "C" int mdvt_stereo_conv_vrows(const uint8_t *depth_rgb, const uint8_t *colour_rgb, int n_frames, int width, int height,
                                       const mdvt_conv_frame *frames_dev, uint32_t bg_rgb, uint32_t fill_rgb, uint32_t flags, uint8_t *out_sbs,
                                       uint8_t *out_mask, float *out_depth, int32_t *status_dev, void *stream) {
@@ -583,7 +583,7 @@ extern "C" int mdvt_stereo_conv_vrows(const uint8_t *depth_rgb, const uint8_t *c
     }
     if (n_frames == 0) return MDVT_OK;
     MDVT_REQUIRE(depth_rgb && colour_rgb && frames_dev && out_sbs, "NULL buffer");
-    MDVT_REQUIRE((int64_t)n_frames * height <= 0x7FFFFFFFll, "too many rows in one batch");
+    MDVT_REQUIRE((int64_t)n_frames * height * 2 <= 0x7FFFFFFFll, "too many rows in one batch");
     auto aligned16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     if (!aligned16(depth_rgb) || !aligned16(colour_rgb) || !aligned16(out_sbs) || (out_mask && !aligned16(out_mask)) ||
         (out_depth && !aligned16(out_depth))) {
@@ -599,21 +599,21 @@ extern "C" int mdvt_stereo_conv_vrows(const uint8_t *depth_rgb, const uint8_t *c
         set_error("row of width %d needs %d bytes of shared memory, device offers %d", width, L.total, smem_optin);
         return MDVT_ERR_UNSUPPORTED;
     }
-    const int n_units = n_frames * height;
+    const int n_units = n_frames * height * 2;  // (row, eye)
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define LAUNCH_TC(M, TT, CC, GG)                                                                                                          \
     do {                                                                                                                              \
         auto kernel = stereo_conv_vrows_kernel<M, TT, CC, GG>;                                                                            \
         MDVT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));                            \
         int ctas = 0;                                                                                                                 \
-        MDVT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kernel, TT, L.total));                                \
+        MDVT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kernel, TT + 32, L.total));                                \
         if (ctas < 1) ctas = 1;                                                                                                       \
         int grid = sm_count() * ctas;                                                                                                 \
         if (grid > n_units) grid = n_units;                                                                                           \
-        const int per = (n_units + grid - 1) / grid;                                                                                  \
+        const int per = (((n_units + grid - 1) / grid) + 1) & ~1; /* both eyes of a row in one CTA */                                 \
         grid = (n_units + per - 1) / per; /* no empty CTAs */                                                                         \
-        kernel<<<grid, TT, L.total, st>>>(depth_rgb, colour_rgb, n_units, width, height, frames_dev, bg_rgb & 0xFFFFFF,          \
-                                               fill_rgb & 0xFFFFFF, ((flags & MDVT_FLAG_BG_COLLIDE) ? 1 : 0) | (vrows_dbg() << 8), out_sbs, out_mask, out_depth, \
+        kernel<<<grid, TT + 32, L.total, st>>>(depth_rgb, colour_rgb, n_units, width, height, frames_dev, bg_rgb & 0xFFFFFF,          \
+                                               fill_rgb & 0xFFFFFF, (flags & MDVT_FLAG_BG_COLLIDE) ? 1 : 0, out_sbs, out_mask, out_depth, \
                                                status_dev);                                                                           \
     } while (0)
 #define LAUNCH_G(M, TT, CC)                                           \
@@ -623,11 +623,11 @@ extern "C" int mdvt_stereo_conv_vrows(const uint8_t *depth_rgb, const uint8_t *c
     } while (0)
 #define LAUNCH_M(M)                                                   \
     do {                                                              \
-        if (width <= 640) LAUNCH_G(M, 320, 2);                        \
-        else if (width <= 1280) LAUNCH_G(M, 320, 4);                  \
-        else if (width <= 1920 && vrows_t384()) LAUNCH_G(M, 384, 5);  \
-        else if (width <= 1920) LAUNCH_G(M, 320, 6);                  \
-        else LAUNCH_G(M, 640, 6);                                     \
+        if (width <= 320) LAUNCH_G(M, 160, 2);                        \
+        else if (width <= 640) LAUNCH_G(M, 160, 4);                   \
+        else if (width <= 1280) LAUNCH_G(M, 160, 8);                  \
+        else if (width <= 1920) LAUNCH_G(M, 160, 12);                 \
+        else LAUNCH_G(M, 320, 12);                                    \
     } while (0)
     if (mode == 0) LAUNCH_M(0);
     else if (mode == 1) LAUNCH_M(1);
