@@ -397,7 +397,29 @@ def measure_paths(dev, peak: float, frames_1080: int = 32, frames_4k: int = 16, 
                                  2 * w * h * 3, w * h * 3,
                                  f"configs[2]: {w}x{h} x {n} frames, 3d_view_depthfile --render, camera (2, 2, -4) aimed at the vertex centroid, white background")
     out["novel_view_4k"]["holes"] = float((msk == 255).float().mean().item())
+    del d, c, rgb, msk, h_rgb, hd, hc, nv
+    torch.cuda.empty_cache()
+    out["movie_2_3D_steps_4_5_1080p"] = measure_movie_pipeline()
     return out
+
+
+def measure_movie_pipeline(frames: int = 192):
+    """BASELINE configs[4] end to end, files in -> files out: movie_2_3D step 4 (convergence list from the depth + focus-mask
+    videos) and step 5 (stereo_rerender with the flags movie_2_3D passes, SBS + infill-mask videos) on a synthetic 1920x1080
+    FFV1 clip in a temporary directory, through benchmarks/movie_e2e.py in a child process (wall clock, codecs included: the
+    inputs are decoded and the results coded by the device FFV1 codec; green/black infill mask, i.e. without the host TELEA
+    step of the normals-coded mask).  Informational: never costs the bench line."""
+    script = os.path.join(ROOT, "benchmarks", "movie_e2e.py")
+    try:
+        proc = subprocess.run([sys.executable, script, str(frames), "--green"], capture_output=True, text=True, timeout=600)
+        for line in reversed(proc.stdout.splitlines()):
+            if line.startswith("{"):
+                res = json.loads(line)
+                res["frames"] = frames
+                return res
+        return {"error": (proc.stderr or proc.stdout)[-400:]}
+    except Exception as exc:  # noqa: BLE001
+        return {"error": f"{type(exc).__name__}: {exc}"}
 
 
 def run_ours(args):

@@ -146,7 +146,7 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
-        path = _build.LIB_PATH
+        path = os.environ.get("MDVT_B200_LIB") or _build.LIB_PATH   # MDVT_B200_LIB: a differently built copy of the library (kernel tuning experiments)
         if not os.path.exists(path):
             _build.build()  # raises if nvcc is missing: there is no other implementation to fall back to
         lib = C.CDLL(path)

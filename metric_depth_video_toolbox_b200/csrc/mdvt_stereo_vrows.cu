@@ -39,6 +39,10 @@
 
 #include "mdvt_common.cuh"
 
+#ifndef MDVT_VROWS_NB
+#define MDVT_VROWS_NB 4
+#endif
+
 namespace mdvt {
 
 constexpr int kSub = 16;            // pixels per sub-block: 48 bytes of u8x3, the TMA granularity of the assembly
@@ -408,7 +412,7 @@ __global__ void __launch_bounds__(T + 32, T <= 160 ? 4 : 2)
 
         // ---- pass 1: every candidate -> z plane ------------------------------------------------------------
         uint32_t c_addr[CPT], c_z[CPT];  // byte address of the candidate's z-plane slot, key bits of its Zv
-        constexpr int NB = CPT % 4 == 0 ? 4 : (CPT % 3 == 0 ? 3 : (CPT % 2 == 0 ? 2 : 1));  // columns per batch: loads first, reductions last
+        constexpr int NB = CPT % MDVT_VROWS_NB == 0 ? MDVT_VROWS_NB : (CPT % 4 == 0 ? 4 : (CPT % 3 == 0 ? 3 : (CPT % 2 == 0 ? 2 : 1)));  // columns per batch: loads first, reductions last
 #pragma unroll
         for (int n0 = 0; n0 < CPT; n0 += NB) {
             uint32_t dlo[NB], dhi[NB];

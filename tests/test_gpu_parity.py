@@ -497,6 +497,23 @@ def test_stereo_conv_vrows_bit_identical_to_generic_path(size, convs, yfov, mask
             assert np.array_equal(bits(da[f].cpu().numpy()), bits(zplane))
 
 
+def test_stereo_conv_vrows_without_mask_and_with_guard_columns():
+    """No hole mask (infill_mask off: black background, no collision rule) and widths that do not fill the thread grid
+    (96, 352, 1600: the guard instantiations) -- still byte for byte the generic loop."""
+    from metric_depth_video_toolbox_b200.stereo import StereoParams, StereoRerenderer
+
+    for (w, h), conv in (((96, 40), 2.0), ((352, 64), 1.5), ((1600, 48), 3.0)):
+        depth, colour = SyntheticClip(w, h, 2, zero_fraction=0.02).frames()
+        outs = []
+        for kernel in ("vrows", "generic"):
+            rr = StereoRerenderer(StereoParams(w, h, xfov=70.0, convergence_depths=[conv, conv * 2], infill_mask=False, conv_kernel=kernel), DEV)
+            sbs, mask = rr.render_device(cu(depth), cu(colour))
+            assert mask is None
+            outs.append(sbs)
+        assert torch.equal(outs[0], outs[1])
+        assert bool((outs[0] != 0).any())
+
+
 def test_stereo_conv_vrows_limits_send_extreme_poses_to_the_generic_loop():
     """Outside the virtual-row kernel's limits (width not a multiple of 32, convergence so close that the staircase is steeper
     than 0.4 rows per 15 columns) "auto" renders through the generic loop -- same bytes as asking for it -- and "vrows" refuses."""
