@@ -36,6 +36,7 @@
 // at 1 m (generic two-lane loop: 18.9; round 1's target-row kernel: 23.0); profiles/r02_vrows_*.
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 
 #include "mdvt_common.cuh"
 
@@ -125,6 +126,7 @@ __device__ __forceinline__ void reds_min(uint32_t addr, uint32_t v) { asm volati
 // One candidate through the exact float32 arithmetic of splat_pixel() (mdvt_splat.cu), with the additions that are exact
 // zeros left out: target column (>= width when culled or out of range) and the key bits of Zv; Zv and its refined
 // reciprocal are handed on for the row test of the alternates.
+template <bool CULL = true>
 __device__ __forceinline__ uint32_t vrow_project(float z, float fj, const EyeConsts &k, float near_plane, uint32_t width, uint32_t &zbits,
                                                  float &Zv, float &rz) {
     const float cju = __fmaf_rn(k.Au, fj, k.Cu), cjz = __fmaf_rn(k.Az, fj, k.Cz);
@@ -134,7 +136,9 @@ __device__ __forceinline__ uint32_t vrow_project(float z, float fj, const EyeCon
     const float u = div_rn_by(nu, Zv, rz);
     const uint32_t ui = (uint32_t)(__float_as_int(__fadd_rn(u, kVMagic)) - kVMagicBits);
     zbits = __float_as_uint(Zv);
-    return min(Zv > near_plane ? ui : 0xFFFFFFFFu, width);
+    // CULL = false (rows whose near plane lies below the depth of code 1 for every column): only code 0 could fail Zv > near,
+    // and that one already leaves the row -- z = 0 makes the reciprocal infinite and u a NaN, whose "integer" is >= width
+    return CULL ? min(Zv > near_plane ? ui : 0xFFFFFFFFu, width) : min(ui, width);
 }
 // rint(v') of the same candidate when it comes from source row `frow_src` (only where the prediction is not certain)
 __device__ __forceinline__ int vrow_target_row(float z, float fj, const EyeConsts &k, float frow_src, float Zv, float rz) {
@@ -171,7 +175,7 @@ struct StairFrame {
 // row are consecutive units of the same CTA); T threads, every thread owns the columns tid + n T, n < CPT.  GUARD: W < T * CPT
 // (columns past the row are culled).
 template <int MASK_MODE, int T, int CPT, bool GUARD>
-__global__ void __launch_bounds__(T + 32, T <= 160 ? 4 : 2)
+__global__ void __launch_bounds__(T + 32, T <= 192 ? 4 : 2)
     stereo_conv_vrows_kernel(const uint8_t *__restrict__ depth_rgb, const uint8_t *__restrict__ colour_rgb, int n_units, int width, int height,
                              const mdvt_conv_frame *__restrict__ frames, uint32_t bg_rgb, uint32_t fill_rgb, int collide,
                              uint8_t *__restrict__ out_sbs, uint8_t *__restrict__ out_mask, float *__restrict__ out_depth,
@@ -413,29 +417,37 @@ __global__ void __launch_bounds__(T + 32, T <= 160 ? 4 : 2)
         // ---- pass 1: every candidate -> z plane ------------------------------------------------------------
         uint32_t c_addr[CPT], c_z[CPT];  // byte address of the candidate's z-plane slot, key bits of its Zv
         constexpr int NB = CPT % MDVT_VROWS_NB == 0 ? MDVT_VROWS_NB : (CPT % 4 == 0 ? 4 : (CPT % 3 == 0 ? 3 : (CPT % 2 == 0 ? 2 : 1)));  // columns per batch: loads first, reductions last
+        auto pass1 = [&](auto cull_tag) {
+            constexpr bool CULL = decltype(cull_tag)::value;
 #pragma unroll
-        for (int n0 = 0; n0 < CPT; n0 += NB) {
-            uint32_t dlo[NB], dhi[NB];
+            for (int n0 = 0; n0 < CPT; n0 += NB) {
+                uint32_t dlo[NB], dhi[NB];
 #pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                const uint32_t o = (uint32_t)((n0 + b) * 3 * T);
-                dlo[b] = lds32(bd + o); dhi[b] = lds32(bd + o + 4u);
+                for (int b = 0; b < NB; ++b) {
+                    const uint32_t o = (uint32_t)((n0 + b) * 3 * T);
+                    dlo[b] = lds32(bd + o); dhi[b] = lds32(bd + o + 4u);
+                }
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    const int n = n0 + b;
+                    const float fj = __fadd_rn(fj0, (float)(n * T));  // exact
+                    const uint32_t px = __funnelshift_r(dlo[b], dhi[b], shift);           // [R, G, B, next]
+                    const uint32_t t = __byte_perm(px, 0x4B000000u, 0x7402);              // 0x4B00RRBB: float value 2^23 + code16
+                    const float z = __fmul_rn(__fmaf_rn(__uint_as_float(t), dec16, neg_bias), depth_scale);
+                    float Zv, rz;
+                    uint32_t slot = vrow_project<CULL>(z, fj, ec, near_plane, w32, c_z[n], Zv, rz);
+                    if (GUARD) slot = (tid + n * T < width) ? slot : w32;
+                    c_addr[n] = zp_a + 4u * slot;
+                }
+#pragma unroll
+                for (int b = 0; b < NB; ++b) reds_min(c_addr[n0 + b], c_z[n0 + b]);
             }
-#pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                const int n = n0 + b;
-                const float fj = __fadd_rn(fj0, (float)(n * T));  // exact
-                const uint32_t px = __funnelshift_r(dlo[b], dhi[b], shift);           // [R, G, B, next]
-                const uint32_t t = __byte_perm(px, 0x4B000000u, 0x7402);              // 0x4B00RRBB: float value 2^23 + code16
-                const float z = __fmul_rn(__fmaf_rn(__uint_as_float(t), dec16, neg_bias), depth_scale);
-                float Zv, rz;
-                uint32_t slot = vrow_project(z, fj, ec, near_plane, w32, c_z[n], Zv, rz);
-                if (GUARD) slot = (tid + n * T < width) ? slot : w32;
-                c_addr[n] = zp_a + 4u * slot;
-            }
-#pragma unroll
-            for (int b = 0; b < NB; ++b) reds_min(c_addr[n0 + b], c_z[n0 + b]);
-        }
+        };
+        // the cull test is needed only when some non-zero code can lie at or below the near plane: r_z(j) is linear in j, so
+        // its minimum over the row sits at an end column; the depth of code 1 is dec16 * depth_scale
+        const float rz_min = fminf(ec.Cz, __fmaf_rn(ec.Az, (float)(width - 1), ec.Cz));
+        if (near_plane < __fmul_rn(__fmul_rn(dec16, depth_scale), rz_min) * 0.999f) pass1(std::false_type{});
+        else pass1(std::true_type{});
         // alternates: half a warp per sub-block and source row, with the exact row test; the first kAltSlots from shared
         // memory, the rest (strong rotations only) from global memory
         const int n_alt = (int)lds32(alt_a);
@@ -509,17 +521,19 @@ __global__ void __launch_bounds__(T + 32, T <= 160 ? 4 : 2)
         {
             const int groups = width / 4;  // 4 consecutive target pixels each
             constexpr int mwpg = MASK_MODE == 2 ? 3 : 1;
+            float4 *drow = out_depth ? reinterpret_cast<float4 *>(out_depth + ((int64_t)row_unit * 2 + eye) * width) : nullptr;
+#pragma unroll 3
             for (int k = tid; k < groups; k += T) {
                 const uint32_t za = zp_a + 16u * (uint32_t)k;
                 const uint4 c4 = lds128(za + cp_delta);
-                if (out_depth) {
+                if (drow) {
                     const uint4 z4 = lds128(za);
                     float4 d;
                     d.x = z4.x == kEmpty32 ? 0.0f : __uint_as_float(z4.x);
                     d.y = z4.y == kEmpty32 ? 0.0f : __uint_as_float(z4.y);
                     d.z = z4.z == kEmpty32 ? 0.0f : __uint_as_float(z4.z);
                     d.w = z4.w == kEmpty32 ? 0.0f : __uint_as_float(z4.w);
-                    reinterpret_cast<float4 *>(out_depth + ((int64_t)row_unit * 2 + eye) * width)[k] = d;
+                    drow[k] = d;
                 }
                 sts128(za + cp_delta, fill4);
                 sts128(za, empty4);
@@ -576,6 +590,11 @@ extern "C" int mdvt_stereo_conv_vrows_supported(const mdvt_conv_frame *frames_ho
     return 1;
 }
 
+static bool vrows_t192() {  // development switch: MDVT_VROWS_T=192 -> 6 compute warps x 10 columns instead of 5 x 12 at 1920
+    static const bool v = getenv("MDVT_VROWS_T") && atoi(getenv("MDVT_VROWS_T")) == 192;
+    return v;
+}
+
 extern "C" int mdvt_stereo_conv_vrows(const uint8_t *depth_rgb, const uint8_t *colour_rgb, int n_frames, int width, int height,
                                       const mdvt_conv_frame *frames_dev, uint32_t bg_rgb, uint32_t fill_rgb, uint32_t flags, uint8_t *out_sbs,
                                       uint8_t *out_mask, float *out_depth, int32_t *status_dev, void *stream) {
@@ -630,6 +649,7 @@ extern "C" int mdvt_stereo_conv_vrows(const uint8_t *depth_rgb, const uint8_t *c
         if (width <= 320) LAUNCH_G(M, 160, 2);                        \
         else if (width <= 640) LAUNCH_G(M, 160, 4);                   \
         else if (width <= 1280) LAUNCH_G(M, 160, 8);                  \
+        else if (width == 1920 && vrows_t192()) LAUNCH_TC(M, 192, 10, false); \
         else if (width <= 1920) LAUNCH_G(M, 160, 12);                 \
         else LAUNCH_G(M, 320, 12);                                    \
     } while (0)
