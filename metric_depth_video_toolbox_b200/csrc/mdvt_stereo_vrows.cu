@@ -161,7 +161,12 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity) 
         "r"(parity)
         : "memory");
 }
-__device__ __forceinline__ void named_barrier(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+// bar.sync is the ALIGNED barrier: every thread of a warp must arrive together, so the warp reconverges first (the loops over
+// the alternates leave half-warps on different paths)
+__device__ __forceinline__ void named_barrier(int id, int count) {
+    __syncwarp();
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
 
 // Per-frame constants of the staircase (shared memory, two slots keyed by frame parity): i*(j) of target row r is
 // alpha j + beta with alpha = r k1 - k0, beta = r c1 - c0 (k1 = A_z / B_v, k0 = A_v / B_v, c1 = C_z / B_v, c0 = C_v / B_v, float64),
@@ -425,7 +430,10 @@ __global__ void __launch_bounds__(T + 32, T <= 192 ? 4 : 2)
 #pragma unroll
                 for (int b = 0; b < NB; ++b) {
                     const uint32_t o = (uint32_t)((n0 + b) * 3 * T);
-                    dlo[b] = lds32(bd + o); dhi[b] = lds32(bd + o + 4u);
+                    dlo[b] = dhi[b] = 0u;
+                    if (!GUARD || tid + (n0 + b) * T < width) {  // columns past the row: nothing to read (their bytes would lie outside the row buffers)
+                        dlo[b] = lds32(bd + o); dhi[b] = lds32(bd + o + 4u);
+                    }
                 }
 #pragma unroll
                 for (int b = 0; b < NB; ++b) {
@@ -499,7 +507,10 @@ __global__ void __launch_bounds__(T + 32, T <= 192 ? 4 : 2)
             for (int b = 0; b < NB; ++b) {
                 const uint32_t o = (uint32_t)((n0 + b) * 3 * T) + row_bytes;
                 zwin[b] = lds32(c_addr[n0 + b]);
-                clo[b] = lds32(bd + o); chi[b] = lds32(bd + o + 4u);
+                clo[b] = chi[b] = 0u;
+                if (!GUARD || tid + (n0 + b) * T < width) {
+                    clo[b] = lds32(bd + o); chi[b] = lds32(bd + o + 4u);
+                }
             }
 #pragma unroll
             for (int b = 0; b < NB; ++b) {

@@ -514,6 +514,47 @@ def test_stereo_conv_vrows_without_mask_and_with_guard_columns():
         assert bool((outs[0] != 0).any())
 
 
+def test_stereo_conv_vrows_random_geometries_equal_the_generic_loop():
+    """Thirty random geometries (frame size, field of view on both axes, pupillary distance, master FOV, per-frame convergence
+    distances from 0.6 m to 60 m, background-collision on/off): wherever the host check accepts the poses, the virtual-row
+    kernel writes the generic loop's bytes, masks and depth bits, and its own geometry guard stays silent."""
+    from metric_depth_video_toolbox_b200.stereo import StereoParams, StereoRerenderer
+
+    rng = np.random.default_rng(20260)
+    taken = 0
+    for case in range(30):
+        w = 32 * int(rng.integers(1, 17))
+        h = int(rng.integers(9, 120))
+        n = int(rng.integers(1, 4))
+        xfov = float(rng.uniform(35.0, 105.0))
+        yfov = None if rng.random() < 0.5 else float(rng.uniform(30.0, 90.0))
+        convs = [float(np.exp(rng.uniform(np.log(0.6), np.log(60.0)))) for _ in range(n)]
+        ipd = float(rng.uniform(50.0, 75.0))
+        infill = bool(rng.random() < 0.7)
+        depth, colour = SyntheticClip(w, h, n, seed=100 + case, zero_fraction=0.01, n_rects=4).frames()
+        common = dict(xfov=xfov, yfov=yfov, convergence_depths=convs, pupillary_distance=ipd, master_xfov=float(rng.uniform(40.0, 60.0)), infill_mask=infill)
+        probe = StereoRerenderer(StereoParams(w, h, **common), DEV)
+        host = ops.conv_frames_packed(*probe.packed_cameras(0, n), probe.p.near)
+        if not ops.conv_vrows_supported(host, w, h):
+            continue
+        taken += 1
+        outs = []
+        for kernel in ("vrows", "generic"):
+            rr = StereoRerenderer(StereoParams(w, h, conv_kernel=kernel, **common), DEV)
+            out_depth = torch.full((n, h, 2 * w), -1.0, dtype=torch.float32, device=DEV)
+            sbs, mask = rr.render_device(cu(depth), cu(colour), out_depth=out_depth)
+            outs.append((sbs, mask, out_depth))
+        (sa, ma, da), (sb, mb, db) = outs
+        assert torch.equal(sa, sb), (case, w, h, xfov, yfov, convs)
+        assert (ma is None and mb is None) or torch.equal(ma, mb), (case, w, h)
+        assert torch.equal(da.view(torch.int32), db.view(torch.int32)), (case, w, h)
+        status = torch.zeros(n, dtype=torch.int32, device=DEV)
+        ops.stereo_conv_rows(cu(depth), cu(colour), cu(host), probe.p.bg_rgb, (0, 0, 0), ops.FLAG_BG_COLLIDE if infill else 0, kernel="vrows",
+                             status=status, want_mask=infill)
+        assert int(status.sum().item()) == 0
+    assert taken >= 20
+
+
 def test_stereo_conv_vrows_limits_send_extreme_poses_to_the_generic_loop():
     """Outside the virtual-row kernel's limits (width not a multiple of 32, convergence so close that the staircase is steeper
     than 0.4 rows per 15 columns) "auto" renders through the generic loop -- same bytes as asking for it -- and "vrows" refuses."""
