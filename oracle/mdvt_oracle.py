@@ -346,8 +346,23 @@ def stereo_frame(depth_rgb, colour, xfov, yfov=None, max_depth=100, pupillary_di
     return np.concatenate(imgs, axis=1), np.concatenate(masks, axis=1), tuple(idl)
 
 
+def stereo_frame_uvz(depth_rgb, xfov, yfov=None, max_depth=100, pupillary_distance_mm=63, master_xfov=45.0, convergence_depth=None,
+                     transform=None):
+    """(u', v', z') of every source pixel in the left and in the right eye, exactly as stereo_frame projects them (the tests use
+    them to tell which target pixels a float32 evaluation may legitimately paint differently: rounding boundaries, z ties)."""
+    h, w = depth_rgb.shape[:2]
+    K = camera_matrix(xfov, yfov, w, h)
+    scale = master_fov_depth_scale(master_xfov, xfov)
+    ipd = pupillary_distance_mm / 1000
+    theta = None
+    if convergence_depth is not None and float(convergence_depth) != 0:
+        theta = convergence_angle(float(convergence_depth) * scale, ipd)
+    T = np.eye(4) if transform is None else np.asarray(transform, dtype=np.float64)
+    return [view_uvz(depth_rgb, max_depth, K, eye_pose(eye, ipd, theta) @ T, scale) for eye in ("left", "right")]
+
+
 def novel_view_frame(depth_rgb, colour, xfov, yfov=None, max_depth=100, cam_pos=(2.0, 2.0, -4.0),
-                     target=None, transform=None, center_of_by_one=False, tie_colour=False):
+                     target=None, transform=None, center_of_by_one=False, tie_colour=False, want_uvz=False):
     """One iteration of `3d_view_depthfile.py --render` (:133-255) in point-splat form:
     target defaults to the vertex mean (:231; the mesh's vertices sit on the stretched grid
     unless --render_as_pointcloud, :178-182 -> `center_of_by_one`), white background (:254).
@@ -374,6 +389,8 @@ def novel_view_frame(depth_rgb, colour, xfov, yfov=None, max_depth=100, cam_pos=
     u, v, z = project(pts, K_r)
     ids = splat_ids(u, v, z, w, h, tie=pack_colour(colour) if tie_colour else None)
     img, mask = resolve(ids, colour, bg_rgb=(255, 255, 255), hole_fill=(255, 255, 255))
+    if want_uvz:
+        return img, mask, ids, ext, (u, v, z)
     return img, mask, ids, ext
 
 
