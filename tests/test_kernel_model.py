@@ -6,6 +6,7 @@ import pytest
 
 from oracle import kernel_model as km
 from oracle import mdvt_oracle as orc
+from oracle.checks import assert_differs_only_where_explained, explained_map  # noqa: F401  (re-exported to the GPU tests)
 from metric_depth_video_toolbox_b200.synth import SyntheticClip
 
 REL_TOL = 1e-4  # BASELINE.json north_star: "within 1e-4 relative on the float unproject/reproject"
@@ -35,57 +36,6 @@ def boundary_explained(u64, v64, z64, ids_a, ids_b, w, h):
             ok = bool(near.any())
         unexplained += 0 if ok else 1
     return len(diff), unexplained
-
-
-def explained_map(u64, v64, z64, w, h, near_plane=None):
-    """(h, w) bool: the target pixels a float32 evaluation of the same projection may legitimately paint differently from the
-    float64 oracle -- a source whose float64 (u', v') lies within 1e-3 px of a .5 rounding boundary rounds into the pixel or
-    one of its 8 neighbours, or the pixel's two nearest candidates differ by less than 1e-5 relative in z' (the
-    same criteria as boundary_explained, for comparisons of final images where no winner ids are at hand)."""
-    near_plane = orc.NEAR_PLANE if near_plane is None else near_plane
-    u64, v64, z64 = (np.asarray(a, dtype=np.float64).reshape(-1) for a in (u64, v64, z64))
-    valid = np.isfinite(u64) & np.isfinite(v64) & (z64 > near_plane)
-    with np.errstate(invalid="ignore"):
-        near_half = valid & ((np.abs((u64 - np.floor(u64)) - 0.5) < 1e-3) | (np.abs((v64 - np.floor(v64)) - 0.5) < 1e-3))
-    pad = np.zeros((h + 2, w + 2), dtype=bool)
-    ur, vr = np.rint(u64[near_half]), np.rint(v64[near_half])
-    keep = (ur >= -1) & (ur <= w) & (vr >= -1) & (vr <= h)
-    ur, vr = ur[keep].astype(np.int64), vr[keep].astype(np.int64)
-    for dy in (-1, 0, 1):
-        for dx in (-1, 0, 1):
-            rr, cc = vr + dy, ur + dx
-            ok = (rr >= 0) & (rr < h) & (cc >= 0) & (cc < w)
-            pad[rr[ok] + 1, cc[ok] + 1] = True
-    out = pad[1:-1, 1:-1].copy()
-    with np.errstate(invalid="ignore"):
-        ui, vi = np.rint(u64), np.rint(v64)
-        inside = valid & (ui >= 0) & (ui < w) & (vi >= 0) & (vi < h)
-    t = (vi[inside] * w + ui[inside]).astype(np.int64)
-    z = z64[inside]
-    order = np.lexsort((z, t))
-    t, z = t[order], z[order]
-    if len(t) > 1:
-        first = np.flatnonzero(np.r_[True, t[1:] != t[:-1]])
-        second = first + 1
-        has2 = second < len(t)
-        has2[has2] &= t[second[has2]] == t[first[has2]]
-        za, zb = z[first[has2]], z[second[has2]]
-        tie = np.abs(za - zb) <= 1e-5 * np.maximum(np.abs(za), np.abs(zb))
-        out.reshape(-1)[t[first[has2]][tie]] = True
-    return out
-
-
-def assert_differs_only_where_explained(got, want, maps, max_fraction=2e-3):
-    """Final images (h, W[, 3]) of a float32 path and of the float64 oracle: every differing pixel lies in the explained map
-    (one map per view, side by side like the images), and they are few."""
-    diff = (np.asarray(got) != np.asarray(want))
-    if diff.ndim == 3:
-        diff = diff.any(axis=-1)
-    explained = np.concatenate(list(maps), axis=1) if isinstance(maps, (list, tuple)) else maps
-    assert explained.shape == diff.shape, (explained.shape, diff.shape)
-    bad = diff & ~explained
-    assert not bad.any(), f"{int(bad.sum())} differing pixels are not next to a rounding boundary or a z tie, e.g. {np.argwhere(bad)[:5].tolist()}"
-    assert diff.mean() <= max_fraction, f"{diff.mean():.2e} of the pixels differ"
 
 
 @pytest.mark.parametrize("size", [(64, 48), (640, 480)])
@@ -183,3 +133,28 @@ def test_generic_view_model_vs_oracle_at_full_size(size, band):
     n_diff, unexplained = boundary_explained(u64, v64, z64, ids32, ids64, w, h)
     assert unexplained == 0
     assert n_diff <= max(4, int(2e-3 * int(ok.sum())))
+
+
+def test_explained_map_marks_rounding_boundaries_and_z_ties_only():
+    """The image-level parity criterion itself: a source next to a .5 boundary explains its 3x3 neighbourhood, two nearest
+    candidates within 1e-5 relative explain their pixel, everything else is unexplained; culled / non-finite sources do not count."""
+    w, h = 16, 8
+    u = np.array([3.2, 7.4995, 12.1, 12.3, 5.0, 9.5004, np.nan, 1.0])
+    v = np.array([2.1, 4.2, 6.0, 6.2, 1.0, 7.0, 3.0, 0.5002])
+    z = np.array([1.0, 2.0, 3.0, 3.00002, 2.0, 0.00001, 1.0, 4.0])   # source 5 is behind the near plane, source 6 is not finite
+    m = explained_map(u, v, z, w, h)
+    want = np.zeros((h, w), dtype=bool)
+    want[3:6, 6:9] = True        # source 1: u = 7.4995 rounds to 7, row 4
+    want[6, 12] = True           # sources 2 and 3 meet on (6, 12) with z' 3.0 / 3.00002
+    want[0:2, 0:3] = True        # source 7: v = 0.5002 rounds to 1 -> rows 0..2 clipped to the frame... (rint(0.5002) = 1)
+    want[2, 0:3] = True
+    assert np.array_equal(m, want)
+    a = np.zeros((h, w, 3), dtype=np.uint8)
+    b = a.copy()
+    b[4, 7] = 9
+    assert_differs_only_where_explained(a, b, m, max_fraction=0.01)
+    with pytest.raises(AssertionError):
+        assert_differs_only_where_explained(a, b, m)   # explained, but more than the default 2e-3 of this tiny frame
+    b[0, 15] = 1
+    with pytest.raises(AssertionError):
+        assert_differs_only_where_explained(a, b, m, max_fraction=1.0)
