@@ -403,7 +403,7 @@ def measure_paths(dev, peak: float, frames_1080: int = 32, frames_4k: int = 16, 
     return out
 
 
-def measure_movie_pipeline(frames: int = 192):
+def measure_movie_pipeline(frames: int = 480):
     """BASELINE configs[4] end to end, files in -> files out: movie_2_3D step 4 (convergence list from the depth + focus-mask
     videos) and step 5 (stereo_rerender with the flags movie_2_3D passes, SBS + infill-mask videos) on a synthetic 1920x1080
     FFV1 clip in a temporary directory, through benchmarks/movie_e2e.py in a child process (wall clock, codecs included: the
