@@ -96,7 +96,7 @@ class StereoJob:
                 out["mask"] = dmask
             return out
         if not self.has_depth_output and self.infill is None:  # the pipelined two-stream path
-            self.renderer.render_host(depth_rgb, colour, sbs, mask, start_frame=first_frame, chunk_frames=max(1, min(n, 8)))
+            self.renderer.render_host(depth_rgb, colour, sbs, mask, start_frame=first_frame, chunk_frames=max(1, min(n, 4)))
             out = {"main": sbs}
         elif self.infill is not None:  # edge points painted into the holes, normals-coded (or green/black) mask image
             from .. import ops

@@ -126,12 +126,61 @@ class NovelViewRenderer:
         ops.render_views(depth_rgb, colour, [src], views, w, h, self._zbuf[:1], out_rgb, out_mask, None, p.bg_rgb, p.bg_rgb, 0, p.near)
         return out_rgb, out_mask
 
-    def render_host(self, depth_rgb, colour, out_rgb=None):
-        """Host arrays in, pinned host tensor out (one chunk: H2D, kernels, D2H on the current stream)."""
-        d = torch.as_tensor(depth_rgb).to(self.device, non_blocking=True)
-        c = torch.as_tensor(colour).to(self.device, non_blocking=True)
-        rgb, _ = self.render_device(d, c)
+    def render_host(self, depth_rgb, colour, out_rgb=None, start_frame: int = 0, chunk_frames: int = 2):
+        """Host arrays in ((n, H, W, 3) u8, pinned memory makes the copies asynchronous), pinned host tensor out; the returned
+        buffer is complete.  Three streams: the uploads of chunk i + 1 and the download of chunk i - 1 run next to the kernels of
+        chunk i (the kernels themselves stay on the caller's stream: the frame loop keeps per-renderer state and an internal
+        second stream), through two sets of device staging buffers of `chunk_frames` frames."""
+        d_host, c_host = torch.as_tensor(depth_rgb), torch.as_tensor(colour)
+        n, h, w, _ = d_host.shape
         if out_rgb is None:
-            out_rgb = torch.empty(rgb.shape, dtype=torch.uint8, pin_memory=True)
-        torch.as_tensor(out_rgb).copy_(rgb, non_blocking=True)
+            out_rgb = torch.empty((n, h, w, 3), dtype=torch.uint8, pin_memory=True)
+        out_t = torch.as_tensor(out_rgb)
+        chunk = max(1, min(int(os.environ.get("MDVT_HOST_CHUNK", chunk_frames)), n))
+        dev = self.device
+        key = (chunk, h, w)
+        if getattr(self, "_host_key", None) != key:
+            self._host = dict(up=torch.cuda.Stream(device=dev), down=torch.cuda.Stream(device=dev),
+                              slots=[dict(d=torch.empty((chunk, h, w, 3), dtype=torch.uint8, device=dev),
+                                          c=torch.empty((chunk, h, w, 3), dtype=torch.uint8, device=dev),
+                                          rgb=torch.empty((chunk, h, w, 3), dtype=torch.uint8, device=dev),
+                                          mask=torch.empty((chunk, h, w), dtype=torch.uint8, device=dev)) for _ in range(2)])
+            self._host_key = key
+        hp = self._host
+        main = torch.cuda.current_stream(dev)
+        hp["up"].wait_stream(main)
+        hp["down"].wait_stream(main)
+        starts = list(range(0, n, chunk))
+        uploaded = [torch.cuda.Event() for _ in starts]
+        rendered = [torch.cuda.Event() for _ in starts]
+        downloaded = [torch.cuda.Event() for _ in starts]
+
+        def upload(i):
+            f0 = starts[i]
+            cnt = min(chunk, n - f0)
+            slot = hp["slots"][i % 2]
+            with torch.cuda.stream(hp["up"]):
+                if i >= 2:
+                    hp["up"].wait_event(rendered[i - 2])   # the kernels that read this slot's inputs are done
+                slot["d"][:cnt].copy_(d_host[f0:f0 + cnt], non_blocking=True)
+                slot["c"][:cnt].copy_(c_host[f0:f0 + cnt], non_blocking=True)
+                uploaded[i].record(hp["up"])
+
+        upload(0)
+        for i, f0 in enumerate(starts):
+            cnt = min(chunk, n - f0)
+            slot = hp["slots"][i % 2]
+            if i + 1 < len(starts):
+                upload(i + 1)
+            main.wait_event(uploaded[i])
+            if i >= 2:
+                main.wait_event(downloaded[i - 2])        # this slot's previous result has left the device
+            self.render_device(slot["d"][:cnt], slot["c"][:cnt], start_frame + f0, slot["rgb"][:cnt], slot["mask"][:cnt])
+            rendered[i].record(main)
+            with torch.cuda.stream(hp["down"]):
+                hp["down"].wait_event(rendered[i])
+                out_t[f0:f0 + cnt].copy_(slot["rgb"][:cnt], non_blocking=True)
+                downloaded[i].record(hp["down"])
+        main.wait_stream(hp["down"])
+        hp["down"].synchronize()
         return out_rgb

@@ -246,6 +246,24 @@ def test_novel_view_renderer_vs_oracle(of_by_one, yfov):
         assert_differs_only_where_explained(mask[k].cpu().numpy(), want_mask, explained, 3e-3)
 
 
+def test_novel_view_render_host_pipeline_equals_render_device():
+    """The three-stream host API of the novel view (uploads, kernels and downloads of neighbouring chunks overlap) returns
+    complete buffers with exactly the frames of one device-resident call, for ragged chunkings and a start frame."""
+    w, h, n = 96, 64, 7
+    depth, colour = SyntheticClip(w, h, n, zero_fraction=0.005).frames()
+    T = np.tile(np.eye(4), (n + 3, 1, 1))
+    T[:, 0, 3] = np.linspace(0.0, 0.3, n + 3)
+    nv = NovelViewRenderer(NovelViewParams(w, h, 60, None, 100, (2.0, 2.0, -4.0), (None, None, None), T), DEV)
+    want, _ = nv.render_device(cu(depth), cu(colour), 3)
+    want = want.cpu().numpy()
+    for chunk in (1, 2, 3, 7, 16):
+        got = nv.render_host(depth, colour, start_frame=3, chunk_frames=chunk)
+        assert np.array_equal(np.asarray(got), want), chunk
+    pinned = torch.empty((n, h, w, 3), dtype=torch.uint8, pin_memory=True)
+    assert nv.render_host(torch.from_numpy(depth).pin_memory(), torch.from_numpy(colour).pin_memory(), pinned, start_frame=3) is pinned
+    assert np.array_equal(pinned.numpy(), want)
+
+
 @pytest.mark.parametrize("of_by_one,yfov,posed,size", [(True, None, True, (160, 120)), (False, 50.0, False, (160, 120)),
                                                        (True, 40.0, True, (160, 120)), (True, None, False, (70, 33)),
                                                        (False, None, True, (132, 50))])
