@@ -547,7 +547,7 @@ def run_ours(args):
         per_frame_out = HEIGHT * 2 * WIDTH * 3 + HEIGHT * 2 * WIDTH // 8
         e2e = {"value": bits_value, "unit": "frames/s", "h2d_bytes_per_step": int(per_frame_in * n_frames * world),
                "d2h_bytes_per_step": int(per_frame_out * n_frames * world), "steps": args.e2e_steps,
-               "api": "StereoRerenderer.render_host(mask_format='bits') (pinned host ring, 2-stream chunked H2D/kernel/D2H; hole mask shipped as "
+               "api": "StereoRerenderer.render_host(mask_format='bits') (pinned host ring, 3 staging buffers with a stream each: chunked H2D/kernel/D2H; hole mask shipped as "
                       "one bit per pixel, ops.unpack_mask_bits restores the u8 plane)",
                "mask_checksum": bits_checksum,
                "u8_mask": {"value": u8_value, "unit": "frames/s", "d2h_bytes_per_step": int(HEIGHT * 2 * WIDTH * 4 * n_frames * world),

@@ -225,9 +225,10 @@ class StereoRerenderer:
     def render_host(self, depth_rgb, colour, out_sbs=None, out_mask=None, start_frame: int = 0, chunk_frames: int = 4,
                     mask_format: str = "u8"):
         """depth_rgb / colour: (n, H, W, 3) u8 host arrays (NumPy or CPU tensors; pinned memory makes the
-        copies asynchronous).  Frames stream through `chunk_frames`-sized device staging buffers on two
-        CUDA streams so H2D, the kernels and D2H overlap (4 frames per buffer measured best on the B200: 3.3 k frames/s at 1080p
-        against 3.07 k with 8 and 2.7 k with 16, profiles/r02_host_pipeline_sweep*.txt).  Returns host tensors (sbs, mask); it waits for the last copy,
+        copies asynchronous).  Frames stream through three `chunk_frames`-sized device staging buffers, each with a CUDA stream
+        of its own, so H2D, the kernels and D2H overlap (4 frames per buffer measured best on the B200: 3.3-3.4 k frames/s at
+        1080p against 3.07 k with 8 and 2.7 k with 16; a separate upload / kernel / download stream design measured the same:
+        profiles/r02_host_pipeline_sweep*.txt).  Returns host tensors (sbs, mask); it waits for the last copy,
         so the returned buffers are complete.
         mask_format "bits": the hole mask crosses PCIe as one bit per pixel -- (n, H, 2W/8) u8, most significant bit
         first; `ops.unpack_mask_bits` (numpy.unpackbits) gives the u8 {0, 255} plane back.  It takes the mask's share of the
@@ -245,7 +246,7 @@ class StereoRerenderer:
             out_mask = torch.empty((n, h, 2 * w // 8) if bits else (n, h, 2 * w) + ((3,) if p.mask_rgb else ()), dtype=torch.uint8, pin_memory=True)
         out_sbs_t, out_mask_t = torch.as_tensor(out_sbs), (None if out_mask is None else torch.as_tensor(out_mask))
         chunk = max(1, min(int(os.environ.get("MDVT_HOST_CHUNK", chunk_frames)), n))   # tuning aids: frames per staging buffer,
-        n_slots = max(2, int(os.environ.get("MDVT_HOST_SLOTS", "2")))                     # staging buffers / streams in flight
+        n_slots = max(2, int(os.environ.get("MDVT_HOST_SLOTS", "3")))                     # staging buffers / streams in flight
         slots = self._host_pipeline_slots(n_slots, chunk, h, w)
         caller = torch.cuda.current_stream(self.device)
         for s in slots:
