@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(T + 32, T <= 192 ? 4 : 2)
 
         // ---- pass 1: every candidate -> z plane ------------------------------------------------------------
         uint32_t c_addr[CPT], c_z[CPT];  // byte address of the candidate's z-plane slot, key bits of its Zv
-        constexpr int NB = CPT % MDVT_VROWS_NB == 0 ? MDVT_VROWS_NB : (CPT % 4 == 0 ? 4 : (CPT % 3 == 0 ? 3 : (CPT % 2 == 0 ? 2 : 1)));  // columns per batch: loads first, reductions last
+        constexpr int NB = CPT % MDVT_VROWS_NB == 0 ? MDVT_VROWS_NB : (CPT % 4 == 0 ? 4 : (CPT % 5 == 0 ? 5 : (CPT % 3 == 0 ? 3 : (CPT % 2 == 0 ? 2 : 1))));  // columns per batch: loads first, reductions last
         auto pass1 = [&](auto cull_tag) {
             constexpr bool CULL = decltype(cull_tag)::value;
 #pragma unroll
@@ -601,8 +601,8 @@ extern "C" int mdvt_stereo_conv_vrows_supported(const mdvt_conv_frame *frames_ho
     return 1;
 }
 
-static bool vrows_t192() {  // development switch: MDVT_VROWS_T=192 -> 6 compute warps x 10 columns instead of 5 x 12 at 1920
-    static const bool v = getenv("MDVT_VROWS_T") && atoi(getenv("MDVT_VROWS_T")) == 192;
+static int vrows_t() {  // development switch: MDVT_VROWS_T=192 | 128 -> 6 compute warps x 10 columns / 4 x 15 instead of 5 x 12 at 1920
+    static const int v = getenv("MDVT_VROWS_T") ? atoi(getenv("MDVT_VROWS_T")) : 0;
     return v;
 }
 
@@ -660,7 +660,8 @@ extern "C" int mdvt_stereo_conv_vrows(const uint8_t *depth_rgb, const uint8_t *c
         if (width <= 320) LAUNCH_G(M, 160, 2);                        \
         else if (width <= 640) LAUNCH_G(M, 160, 4);                   \
         else if (width <= 1280) LAUNCH_G(M, 160, 8);                  \
-        else if (width == 1920 && vrows_t192()) LAUNCH_TC(M, 192, 10, false); \
+        else if (width == 1920 && vrows_t() == 192) LAUNCH_TC(M, 192, 10, false); \
+        else if (width == 1920 && vrows_t() == 128) LAUNCH_TC(M, 128, 15, false); \
         else if (width <= 1920) LAUNCH_G(M, 160, 12);                 \
         else LAUNCH_G(M, 320, 12);                                    \
     } while (0)
