@@ -17,16 +17,7 @@ from . import sharding
 from .cli import find_convergence_depth, stereo_rerender
 
 
-def is_valid_video(file_path: str) -> bool:
-    """movie_2_3D.py:62-68."""
-    import cv2
-
-    if not os.path.exists(file_path):
-        return False
-    cap = cv2.VideoCapture(file_path)
-    ok = cap.isOpened() and int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) > 0
-    cap.release()
-    return ok
+from .movie_plan import is_valid_video  # noqa: E402,F401  (movie_2_3D.py:62-67: exists and holds at least 2 KB)
 
 
 def _barrier():

@@ -155,3 +155,153 @@ def test_encode_depth_float64_input_matches_reference(golden_dir):
         assert np.array_equal(dfh.encode_data_as_BGR(codes, 48, 32, bit16=True), g[f"enc64_bgr16_md{md}"])
         differs += int((dfh.encode_depth_as_uint32(d64.astype(np.float32), md) != codes).sum())
     assert differs > 0   # the float32 route really gives other codes: the test distinguishes the two
+
+
+# ---------------------------------------------------------------------------------------------
+# movie_2_3D: the module surface MDVT_gui.py:1290-1320 loads by path
+# ---------------------------------------------------------------------------------------------
+# every top-level `def` of /root/reference/movie_2_3D.py, in file order
+MOVIE_2_3D_DEFS = [
+    "write_frames_to_file", "wait_for_first", "is_valid_video", "validate_video_lengths", "_seconds_to_timecode", "split_scenes", "parse_args",
+    "ensure_output_dir", "ensure_scene_file", "open_input_video", "load_and_split_scenes", "plan_scene_files", "step1_create_scene_videos",
+    "step2_estimate_depth", "step3_generate_masks", "step4_find_convergence", "step5_render_sbs", "step6_infill_and_collect",
+    "step6_normal_infill_render_sbs", "step6_m2svid_infill_and_collect", "step6_inspatio_world_infill_and_collect",
+    "step6_stereocrafter_infill_and_collect", "step6_stereo_dissoclusion_net_infill_and_collect", "step7_concat_and_mux", "main"]
+
+
+def _movie_golden():
+    import json
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "movie_2_3D.json")) as fh:
+        return json.load(fh)
+
+
+def test_movie_2_3D_name_coverage_and_signatures():
+    import movie_2_3D as m
+
+    assert len(MOVIE_2_3D_DEFS) == 25
+    assert [n for n in MOVIE_2_3D_DEFS if not callable(getattr(m, n, None))] == []
+    from oracle import ref_bridge
+
+    if ref_bridge.available():   # this container only: names, parameter names and defaults re-derived from the reference
+        import ast
+
+        tree = ast.parse(open(os.path.join(ref_bridge.REFERENCE_ROOT, "movie_2_3D.py")).read())
+        defs = [n for n in tree.body if isinstance(n, ast.FunctionDef)]
+        assert [n.name for n in defs] == MOVIE_2_3D_DEFS
+        for node in defs:
+            want = [a.arg for a in node.args.args]
+            got = list(inspect.signature(getattr(m, node.name)).parameters)
+            assert got == want, (node.name, got, want)
+            want_defaults = [ast.literal_eval(d) for d in node.args.defaults]
+            got_defaults = [p.default for p in inspect.signature(getattr(m, node.name)).parameters.values() if p.default is not inspect.Parameter.empty]
+            assert got_defaults == want_defaults, node.name
+
+
+def test_movie_2_3D_planning_helpers_equal_the_reference_outputs(tmp_path):
+    """Time codes, scene splitting, the csv loader and the per-scene file plan against the outputs of the reference's own
+    functions (tests/golden/movie_2_3D.json, oracle/make_movie_golden.py)."""
+    import copy
+
+    import movie_2_3D as m
+
+    g = _movie_golden()
+    for text, want in g["timecodes"].items():
+        assert m._seconds_to_timecode(float(text)) == want, text
+    for max_frames, want in g["split"].items():
+        scenes = copy.deepcopy(g["scenes"])
+        assert m.split_scenes(scenes, max_scene_frames=int(max_frames)) == want
+        assert scenes == g["scenes"]   # the input rows are not modified
+    assert m.split_scenes(copy.deepcopy(g["scenes"])) == g["split"]["1500"]   # default max_scene_frames
+    csv_path = tmp_path / "scenes.csv"
+    csv_path.write_text(g["csv_text"], newline="")
+    for max_frames, want in g["csv"].items():
+        assert m.load_and_split_scenes(str(csv_path), ",", int(max_frames)) == want
+    out_dir = str(tmp_path / "out")
+    for end_scene, want in g["plan"].items():
+        planned = m.plan_scene_files(m.split_scenes(copy.deepcopy(g["scenes"]), 1500), out_dir, int(end_scene))
+        assert [{k: (v.replace(out_dir, "<OUT>") if isinstance(v, str) else v) for k, v in s.items()} for s in planned] == want
+    # 'finished' follows the files on disk
+    m.ensure_output_dir(out_dir)
+    m.ensure_output_dir(out_dir)
+    scenes = m.split_scenes(copy.deepcopy(g["scenes"]), 1500)
+    open(os.path.join(out_dir, "scene_2.mkv_depth.mkv_stereo.mkv"), "wb").close()
+    assert [s["finished"] for s in m.plan_scene_files(scenes, out_dir, -1)] == [False, True, False, False, False, False]
+
+
+def test_movie_2_3D_flag_table_equals_the_reference(monkeypatch):
+    import ast
+
+    import movie_2_3D as m
+    from metric_depth_video_toolbox_b200 import movie_plan
+
+    sys_path = os.path.abspath(movie_plan.__file__)
+    got = {}
+    for node in ast.walk(ast.parse(open(sys_path).read())):
+        if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr == "add_argument":
+            spec = {"type": None, "default": None, "action": None, "required": False}
+            for kw in node.keywords:
+                if kw.arg == "type":
+                    spec["type"] = kw.value.id
+                elif kw.arg in ("default", "action", "required"):
+                    try:
+                        spec[kw.arg] = ast.literal_eval(kw.value)
+                    except ValueError:
+                        spec[kw.arg] = "expr:" + ast.unparse(kw.value)
+            got[ast.literal_eval(node.args[0])] = spec
+    assert got == _movie_golden()["flags"]
+    monkeypatch.setattr("sys.argv", ["movie_2_3D.py"])
+    with pytest.raises(ValueError, match="need --color_video"):
+        m.parse_args()
+    monkeypatch.setattr("sys.argv", ["movie_2_3D.py", "--color_video", "in.mp4", "--end_scene", "3", "--infill_engine", "none"])
+    a = m.parse_args()
+    assert (a.color_video, a.end_scene, a.infill_engine, a.output_dir, a.max_scene_frames, a.no_render, a.gui) == ("in.mp4", 3, "none", "output", 1500, False, False)
+    assert a.parallel == int(os.cpu_count() // 2)
+
+
+def test_movie_2_3D_step1_copies_the_scene_frames_and_the_model_steps_refuse(tmp_path):
+    import cv2
+
+    import movie_2_3D as m
+    from metric_depth_video_toolbox_b200 import video_io
+    from metric_depth_video_toolbox_b200.movie_plan import OutOfScope
+
+    rng = np.random.default_rng(5)
+    frames = rng.integers(0, 256, size=(9, 32, 48, 3), dtype=np.uint8)
+    src = str(tmp_path / "movie.mkv")
+    video_io.write_clip(src, frames, 24.0)
+    assert m.is_valid_video(src) and not m.is_valid_video(str(tmp_path / "nothing.mkv"))
+    small = tmp_path / "small.mkv"
+    small.write_bytes(b"x" * 2047)
+    assert not m.is_valid_video(str(small))
+    scenes = [{"Scene Number": "1", "Length (frames)": "4", "finished": False, "scene_video_file": str(tmp_path / "scene_1.mkv")},
+              {"Scene Number": "2", "Length (frames)": "2", "finished": True, "scene_video_file": str(tmp_path / "scene_2.mkv")},
+              {"Scene Number": "3", "Length (frames)": "3", "finished": False, "scene_video_file": str(tmp_path / "scene_3.mkv")}]
+    cap, w, h, fps = m.open_input_video(src)
+    assert (w, h) == (48, 32) and abs(fps - 24.0) < 1e-6
+    m.step1_create_scene_videos(cap, scenes, fps, w, h)
+    cap.release()
+    assert np.array_equal(video_io.read_clip(scenes[0]["scene_video_file"]), frames[0:4])
+    assert not os.path.exists(scenes[1]["scene_video_file"])                      # finished scenes are only read past
+    assert np.array_equal(video_io.read_clip(scenes[2]["scene_video_file"]), frames[6:9])
+    assert not os.path.exists(scenes[0]["scene_video_file"] + "_tmp.mkv")
+    for s in scenes:
+        s["infilled"] = s["scene_video_file"]
+    assert m.validate_video_lengths([scenes[0], scenes[2]]) and not m.validate_video_lengths(scenes)
+    args = type("A", (), {"infill_engine": "stereocrafter", "parallel": 1})()
+    for call in (lambda: m.step2_estimate_depth(args, scenes), lambda: m.step3_generate_masks(args, scenes),
+                 lambda: m.step6_infill_and_collect(args, scenes), lambda: m.step6_normal_infill_render_sbs(args, scenes),
+                 lambda: m.step7_concat_and_mux(args, []), m.main):
+        with pytest.raises(OutOfScope, match="outside the dense per-frame path"):
+            call()
+    args.infill_engine = "magic"
+    with pytest.raises(Exception, match="unknown infill engine: magic"):
+        m.step6_infill_and_collect(args, scenes)
+    import subprocess
+    import sys
+
+    procs = [subprocess.Popen([sys.executable, "-c", "import time; time.sleep(%s)" % t]) for t in ("5", "0")]
+    left = m.wait_for_first(procs)
+    assert left == [procs[0]] and m.wait_for_first([]) == []
+    procs[0].kill()
+    procs[0].wait()
