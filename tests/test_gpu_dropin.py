@@ -670,6 +670,9 @@ def test_movie_2_3d_steps_4_and_5(clip_files, tmp_path):
     w, h, n = c["w"], c["h"], c["n"]
     focus = np.zeros((n, h, w, 3), dtype=np.uint8)
     focus[:, h // 4: h // 2, w // 4: w // 2] = 255
+    # a speckled rim: the reference accepts a mask video only from 2 KB on (movie_2_3D.py:62-67), which a clean rectangle does not fill
+    speckle = np.random.default_rng(3).integers(0, 2, size=(n, h, w), dtype=np.uint8) * 255
+    focus[:, : h // 8] = speckle[:, : h // 8, :, None]
     video_io.write_clip(str(work / "mask.mkv"), focus, 24.0)
     scene = {"finished": False, "scene_video_file": str(work / "colour.mkv"), "depth_video_file": str(work / "depth.mkv"),
              "mask_video_file": str(work / "mask.mkv"), "xfov": 60.0, "sbs": str(work / "depth.mkv") + "_stereo.mkv"}
