@@ -88,5 +88,28 @@ def main():
     print("wrote", os.path.join(OUT, "dropin_helpers.npz"), {k: np.asarray(v).shape for k, v in out.items()})
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--convert-helpers" not in sys.argv:
     main()
+
+
+def convert_helpers_golden():
+    """tests/golden/convert_helpers.npz: the two NumPy helpers of convert_metric_depth_video_to_other_format.py on seeded inputs."""
+    import numpy as np
+
+    from oracle import ref_bridge
+
+    ref = ref_bridge.load("convert_metric_depth_video_to_other_format")
+    rng = np.random.default_rng(77)
+    img = np.concatenate([rng.uniform(-1.0, 14.0, size=(6, 9)), np.array([[0.0, 1e-5, 1e-4, 10.0, 9.99999, 1e9, 2.5, 0.3, 7.0]])]).astype(np.float32)
+    depth = rng.uniform(0.0, 6.0, size=400)
+    depth[::17] = 0.0
+    target = 1.0 / (0.83 * (1.0 / np.where(depth > 0, depth, 1.0)) + 0.021) + rng.normal(0, 1e-3, size=400)
+    target[5::23] = -1.0
+    s, t = ref.estimate_scale_shift(depth, target)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "convert_helpers.npz"), img=img, bytes_default=ref.float_image_to_byte_image(img),
+                        bytes_custom=ref.float_image_to_byte_image(img, max_value=5.0, scale=200, log_scale=2), depth=depth, target=target,
+                        scale_shift=np.array([s, t]))
+
+
+if __name__ == "__main__" and "--convert-helpers" in sys.argv:
+    convert_helpers_golden()

@@ -305,3 +305,38 @@ def test_movie_2_3D_step1_copies_the_scene_frames_and_the_model_steps_refuse(tmp
     assert left == [procs[0]] and m.wait_for_first([]) == []
     procs[0].kill()
     procs[0].wait()
+
+
+# ---------------------------------------------------------------------------------------------
+# convert_metric_depth_video_to_other_format: module-level helpers
+# ---------------------------------------------------------------------------------------------
+CONVERT_DEFS = ["float_image_to_byte_image", "compute_weights_chunked", "best_intersection_point_vectorized_weighted", "find_nearby_points",
+                "merge_global_points", "add_open3d_mesh", "add_point_cloud", "assign_vertex_color_material", "create_camera_alembic",
+                "estimate_scale_shift"]
+
+
+def test_convert_script_helpers_importable_and_the_numpy_ones_equal_the_reference(golden_dir):
+    import convert_metric_depth_video_to_other_format as conv
+    from metric_depth_video_toolbox_b200.convert_helpers import OutOfScope
+
+    assert [n for n in CONVERT_DEFS if not callable(getattr(conv, n, None))] == [] and callable(conv.main)
+    g = np.load(os.path.join(golden_dir, "convert_helpers.npz"))
+    assert np.array_equal(conv.float_image_to_byte_image(g["img"]), g["bytes_default"])
+    assert np.array_equal(conv.float_image_to_byte_image(g["img"], max_value=5.0, scale=200, log_scale=2), g["bytes_custom"])
+    np.testing.assert_allclose(conv.estimate_scale_shift(g["depth"], g["target"]), g["scale_shift"], rtol=1e-12)
+    for call in (lambda: conv.compute_weights_chunked(np.zeros((2, 3))), lambda: conv.merge_global_points([], []),
+                 lambda: conv.create_camera_alembic([], "x.abc"), lambda: conv.add_point_cloud(np.zeros((1, 3)))):
+        with pytest.raises(OutOfScope, match="outside the dense per-frame path"):
+            call()
+    from oracle import ref_bridge
+
+    if ref_bridge.available():   # this container only: names, parameter names and defaults re-derived from the reference
+        import ast
+
+        tree = ast.parse(open(os.path.join(ref_bridge.REFERENCE_ROOT, "convert_metric_depth_video_to_other_format.py")).read())
+        defs = [n for n in tree.body if isinstance(n, ast.FunctionDef)]
+        assert [n.name for n in defs] == CONVERT_DEFS
+        for node in defs:
+            assert list(inspect.signature(getattr(conv, node.name)).parameters) == [a.arg for a in node.args.args], node.name
+            got_defaults = [p.default for p in inspect.signature(getattr(conv, node.name)).parameters.values() if p.default is not inspect.Parameter.empty]
+            assert got_defaults == [ast.literal_eval(d) for d in node.args.defaults], node.name
