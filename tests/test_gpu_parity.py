@@ -533,6 +533,8 @@ def test_stereo_conv_vrows_random_geometries_equal_the_generic_loop():
         infill = bool(rng.random() < 0.7)
         depth, colour = SyntheticClip(w, h, n, seed=100 + case, zero_fraction=0.01, n_rects=4).frames()
         common = dict(xfov=xfov, yfov=yfov, convergence_depths=convs, pupillary_distance=ipd, master_xfov=float(rng.uniform(40.0, 60.0)), infill_mask=infill)
+        if rng.random() < 0.3:   # --xfov_file: a field of view per frame (the intrinsics change inside one launch)
+            common.update(xfov=None, yfov=None, xfovs=[float(xfov + 3.0 * k) for k in range(n)])
         probe = StereoRerenderer(StereoParams(w, h, **common), DEV)
         host = ops.conv_frames_packed(*probe.packed_cameras(0, n), probe.p.near)
         if not ops.conv_vrows_supported(host, w, h):
