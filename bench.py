@@ -409,9 +409,14 @@ def measure_movie_pipeline(frames: int = 480):
     FFV1 clip in a temporary directory, through benchmarks/movie_e2e.py in a child process (wall clock, codecs included: the
     inputs are decoded and the results coded by the device FFV1 codec; green/black infill mask, i.e. without the host TELEA
     step of the normals-coded mask).  Informational: never costs the bench line."""
+    import shutil
+    import tempfile
+
     script = os.path.join(ROOT, "benchmarks", "movie_e2e.py")
+    work = tempfile.mkdtemp(prefix="mdvt_bench_movie_")   # a few GB of FFV1 clips (the synthetic colour is incompressible): removed afterwards
     try:
-        proc = subprocess.run([sys.executable, script, str(frames), "--green"], capture_output=True, text=True, timeout=600)
+        proc = subprocess.run([sys.executable, script, str(frames), "--green"], capture_output=True, text=True, timeout=600,
+                              env=dict(os.environ, MDVT_E2E_DIR=os.path.join(work, "clip")))
         for line in reversed(proc.stdout.splitlines()):
             if line.startswith("{"):
                 res = json.loads(line)
@@ -420,6 +425,8 @@ def measure_movie_pipeline(frames: int = 480):
         return {"error": (proc.stderr or proc.stdout)[-400:]}
     except Exception as exc:  # noqa: BLE001
         return {"error": f"{type(exc).__name__}: {exc}"}
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
 
 
 def run_ours(args):
