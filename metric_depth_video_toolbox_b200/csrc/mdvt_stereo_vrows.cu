@@ -43,6 +43,9 @@
 #ifndef MDVT_VROWS_NB
 #define MDVT_VROWS_NB 4
 #endif
+#ifndef MDVT_VROWS_MINB
+#define MDVT_VROWS_MINB 4   // resident CTAs per SM the register allocation aims at (tuning aid)
+#endif
 
 namespace mdvt {
 
@@ -180,7 +183,7 @@ struct StairFrame {
 // row are consecutive units of the same CTA); T threads, every thread owns the columns tid + n T, n < CPT.  GUARD: W < T * CPT
 // (columns past the row are culled).
 template <int MASK_MODE, int T, int CPT, bool GUARD>
-__global__ void __launch_bounds__(T + 32, T <= 192 ? 4 : 2)
+__global__ void __launch_bounds__(T + 32, T <= 192 ? MDVT_VROWS_MINB : 2)
     stereo_conv_vrows_kernel(const uint8_t *__restrict__ depth_rgb, const uint8_t *__restrict__ colour_rgb, int n_units, int width, int height,
                              const mdvt_conv_frame *__restrict__ frames, uint32_t bg_rgb, uint32_t fill_rgb, int collide,
                              uint8_t *__restrict__ out_sbs, uint8_t *__restrict__ out_mask, float *__restrict__ out_depth,
