@@ -298,6 +298,21 @@ def ncu_traffic_per_frame():
     return traffic
 
 
+def vrows_traffic_per_frame():
+    """DRAM bytes per 1080p frame of the virtual-source-row kernel from its committed ncu capture, or None (also None when the
+    kernel's source has changed since the capture)."""
+    path = os.path.join(ROOT, "profiles", "stereo_vrows_traffic.json")
+    try:
+        with open(path) as fh:
+            t = json.load(fh)
+        sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
+        from make_traffic_json import VROWS_SOURCES, source_sha256
+
+        return float(t["dram_bytes_per_frame"]) if t.get("kernel_source_sha256") == source_sha256(VROWS_SOURCES) else None
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def measure_paths(dev, peak: float, frames_1080: int = 32, frames_4k: int = 16, reps: int = 5):
     """The other kernels of the path at BASELINE.json's sizes, outside `value` (N = 1): convergence stereo (what
     movie_2_3D runs: --convergence_file), stereo with a pose file (--transformation_file), and configs[2] (3840x2160 novel
@@ -383,6 +398,8 @@ def measure_paths(dev, peak: float, frames_1080: int = 32, frames_4k: int = 16, 
         e2e_ms = wall(lambda: rr.render_host(hd, hc, h_sbs, h_mask), n)
         out[key] = entry(ms, e2e_ms, w, h, 14, kernel, 2 * w * h * 3, 2 * w * h * 4, note)
         out[key]["holes"] = float((mask == 255).float().mean().item())
+        if key == "convergence_1080p":
+            out[key]["roofline"]["traffic"] = vrows_traffic_per_frame()   # per frame, like algorithmic_bytes_per_frame
     del d, c, sbs, mask, h_sbs, h_mask, hd, hc
     w, h, n = 3840, 2160, frames_4k
     hd, hc = clip(w, h, n)

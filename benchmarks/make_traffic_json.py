@@ -11,9 +11,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 KERNEL_SOURCES = ["metric_depth_video_toolbox_b200/csrc/mdvt_stereo_rows.cu", "metric_depth_video_toolbox_b200/csrc/mdvt_common.cuh"]
 
 
-def source_sha256() -> str:
+VROWS_SOURCES = ["metric_depth_video_toolbox_b200/csrc/mdvt_stereo_vrows.cu", "metric_depth_video_toolbox_b200/csrc/mdvt_common.cuh"]
+
+
+def source_sha256(sources=None) -> str:
     h = hashlib.sha256()
-    for rel in KERNEL_SOURCES:
+    for rel in (sources or KERNEL_SOURCES):
         with open(os.path.join(ROOT, rel), "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()
@@ -22,6 +25,8 @@ def source_sha256() -> str:
 if __name__ == "__main__":
     rep, frames = sys.argv[1], int(sys.argv[2])
     label = sys.argv[3] if len(sys.argv) > 3 else rep
+    if "--vrows" in sys.argv:   # the capture is of the virtual-source-row kernel (profiles/stereo_vrows_traffic.json)
+        KERNEL_SOURCES[:] = VROWS_SOURCES
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, vals = rows[0], rows[1], rows[2]
