@@ -6,12 +6,13 @@ list, max_depth, pupillary distance, master FOV, optional smoothed convergence l
 camera poses) into per-frame constant blocks, picks the kernel path per clip
 
   * row-local fused kernel (`ops.stereo_rows`)      -- no pose file, no convergence rotation
+  * virtual-source-row kernel (`ops.stereo_conv_rows(kernel="vrows")`) -- a convergence rotation without a pose file (what
+    movie_2_3D runs), where the poses and the frame size pass the kernel's host-side limits check (`StereoParams.conv_kernel`)
   * generic frame loop (`ops.render_views`: colour-keyed splat + streaming resolve, two frames in flight on two streams)
-    -- anything else; convergence without a pose file can also go through the fused target-row kernel
-    (`ops.stereo_conv_rows`, `StereoParams.conv_kernel`), which needs no global z-buffer but is slower on the B200
+    -- anything else (pose files, extreme convergence angles, widths that are not multiples of 32)
 
 and runs it either on device-resident tensors (`render_device`) or on host arrays through a chunked,
-double-buffered H2D -> kernel -> D2H pipeline (`render_host`).  There is no CPU implementation.
+triple-buffered H2D -> kernel -> D2H pipeline (`render_host`).  Every path writes the same bytes.  There is no CPU implementation.
 """
 from __future__ import annotations
 
