@@ -355,8 +355,9 @@ typedef struct mdvt_conv_frame {
     mdvt_view view[2];
 } mdvt_conv_frame;
 
-/* Same inputs / outputs / flags as mdvt_stereo_rows; results are bit-identical to mdvt_project_splat + mdvt_resolve with
- * the same cameras (nearest Zv wins, ties -> lowest source index), without the global z-buffer.  Requires W <= 4096. */
+/* Same inputs / outputs / flags as mdvt_stereo_rows; results are bit-identical to mdvt_render_views with the same cameras
+ * (nearest Zv wins, candidates with bit-identical Zv are ordered by packed colour: the rule of the colour-keyed frame loops),
+ * without the global z-buffer.  Round 1's target-row kernel (per-column source-row prediction); any width up to 4096. */
 MDVT_API int mdvt_stereo_conv_rows(const uint8_t *depth_rgb, const uint8_t *colour_rgb, int n_frames, int width, int height,
                           const mdvt_conv_frame *frames_dev, uint32_t bg_rgb, uint32_t fill_rgb, uint32_t flags,
                           uint8_t *out_sbs, uint8_t *out_mask, float *out_depth, void *stream);
