@@ -603,6 +603,26 @@ def run_ours(args):
                 result_codec[key] = {"frames_per_s": 1e3 * batch / ms, "ms_per_frame": ms / batch, "slices_per_frame": enc.per_frame,
                                      "bytes_per_frame": int(offsets[-1].item()) / batch}
                 del enc
+            # the same coder on film-like content (a blurred texture that pans, sensor noise in the low bits, a flat patch and a
+            # black band: benchmarks/ffv1_gpu_bench.frames_like) -- the rendered synthetic clip above is i.i.d. colour noise, which
+            # no lossless coder compresses (13.8 MB of packets per 12.4 MB frame) and which takes the long escape codes everywhere
+            sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
+            from ffv1_gpu_bench import frames_like
+
+            film = torch.from_numpy(frames_like(2 * WIDTH, HEIGHT, 64)).to(dev)
+            enc = ffv1_gpu.Ffv1Encoder(2 * WIDTH, HEIGHT, dev, max_frames=64, context_model=1)
+            enc.encode_device(film)
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(3):
+                _, offsets = enc.encode_device(film)
+            c1.record()
+            torch.cuda.synchronize()
+            ms = c0.elapsed_time(c1) / 3
+            result_codec["film_like_content_63_contexts"] = {"frames_per_s": 1e3 * 64 / ms, "ms_per_frame": ms / 64, "batch": 64,
+                                                             "bytes_per_frame": int(offsets[-1].item()) / 64}
+            del enc, film
         except Exception as exc:  # noqa: BLE001 - informational leg only
             result_codec = {"error": f"{type(exc).__name__}: {exc}"}
 
