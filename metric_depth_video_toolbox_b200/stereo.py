@@ -69,11 +69,13 @@ class StereoParams:
         return self.transformations is None and self.convergence_depths is None and not self.force_generic
 
     def conv_mode(self) -> str:
-        """Which fused convergence kernel may run: "off" (pose file, no convergence list, force_generic), else "auto" | "vrows" |
-        "rows" | "generic" (conv_kernel)."""
-        if self.transformations is not None or self.convergence_depths is None or self.force_generic:
+        """Which fused convergence kernel may run: "off" (force_generic; neither a convergence list nor a pose file: the row-local
+        kernel's case; a pose file with anything but conv_kernel "auto"), else "auto" | "vrows" | "rows" | "generic" (conv_kernel)."""
+        if self.force_generic or (self.transformations is None and self.convergence_depths is None):
             return "off"
         ck = self.conv_kernel
+        if self.transformations is not None and ck != "auto":
+            return "off"   # a pose file: only "auto" tries the virtual-row kernel (poses that are y-rotations + x-shifts qualify)
         if ck is True:
             ck = "rows"
         if ck is False or ck is None:
@@ -200,8 +202,13 @@ class StereoRerenderer:
             if key not in self._consts_cache:
                 if len(self._consts_cache) > 64:
                     self._consts_cache.clear()
-                host = ops.conv_frames_packed(*self.packed_cameras(start_frame, n), p.near)
-                self._consts_cache[key] = (torch.from_numpy(host).to(self.device), ops.conv_vrows_supported(host, w, h))
+                try:
+                    host = ops.conv_frames_packed(*self.packed_cameras(start_frame, n), p.near)
+                    self._consts_cache[key] = (torch.from_numpy(host).to(self.device), ops.conv_vrows_supported(host, w, h))
+                except ValueError:   # a pose of the chunk is not `y rotation + x shift` (pose files): the generic loop
+                    if p.transformations is None:
+                        raise
+                    self._consts_cache[key] = (None, False)
             frames_dev, vrows_ok = self._consts_cache[key]
             aligned = all(t is None or t.data_ptr() % 16 == 0 for t in (depth_rgb, colour, out_sbs, out_mask, out_depth))
             if mode == "vrows" and not (vrows_ok and aligned):

@@ -557,6 +557,36 @@ def test_stereo_conv_vrows_random_geometries_equal_the_generic_loop():
     assert taken >= 20
 
 
+def test_pose_file_of_pans_takes_the_virtual_row_kernel_and_other_poses_the_generic_loop():
+    """--transformation_file: a camera that only pans (rotation about y) keeps every eye pose a `y rotation + x shift`, so "auto"
+    renders it with the virtual-row kernel; one frame with a tilt -- or any translation, which the convergence rotation turns
+    into a shift along z -- sends the chunk through the generic loop.  Either way the bytes are the generic loop's."""
+    from metric_depth_video_toolbox_b200.stereo import StereoParams, StereoRerenderer
+
+    w, h, n = 256, 72, 3
+    depth, colour = SyntheticClip(w, h, n, zero_fraction=0.01).frames()
+
+    def pan(angle, tx):
+        T = np.eye(4)
+        T[:3, :3] = orc.rot_y(angle)
+        T[0, 3] = tx
+        return T
+
+    pans = [pan(0.004 * k, 0.0) for k in range(n)]
+    slides = [pan(0.004 * k, 0.03 * k) for k in range(n)]
+    tilted = [T.copy() for T in pans]
+    tilted[1][:3, :3] = tilted[1][:3, :3] @ np.array([[1, 0, 0], [0, np.cos(0.002), -np.sin(0.002)], [0, np.sin(0.002), np.cos(0.002)]])
+    for poses, expect_vrows in ((pans, True), (tilted, False), (slides, False)):
+        outs = []
+        for kernel in ("auto", "generic"):
+            rr = StereoRerenderer(StereoParams(w, h, xfov=60.0, convergence_depths=[3.0] * n, transformations=poses, conv_kernel=kernel), DEV)
+            sbs, mask = rr.render_device(cu(depth), cu(colour))
+            if kernel == "auto":
+                assert rr._consts_cache[("conv", 0, n)][1] == expect_vrows
+            outs.append((sbs, mask))
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 def test_stereo_conv_vrows_limits_send_extreme_poses_to_the_generic_loop():
     """Outside the virtual-row kernel's limits (width not a multiple of 32, convergence so close that the staircase is steeper
     than 0.4 rows per 15 columns) "auto" renders through the generic loop -- same bytes as asking for it -- and "vrows" refuses."""
