@@ -7,9 +7,10 @@
 // not depend on the depth.  The source row that lands in target row r is, per source column j,
 //     i*(j) = ((r A_z - A_v) j + (r C_z - C_v)) / B_v            -- LINEAR in j, |slope| ~ sin(theta) |r - cy| / fx,
 // so along a target row the source row index is a staircase with a handful of steps.
-//   * A unit of work is one target row of ONE eye.  CTAs of 5 compute warps + 1 producer warp, 4 per SM at 1080p, each
+//   * A unit of work is one target row of ONE eye.  CTAs of 5 compute warps + 2 producer warps, 4 per SM at 1080p, each
 //     walking a contiguous block of units.
-//   * The PRODUCER warp (one lane per staircase step, float64) has the TMA engine assemble the unit's VIRTUAL SOURCE ROW in
+//   * A PRODUCER warp (one lane per staircase step, float64; one warp per eye, because assembling a row of many steps takes
+//     a single warp longer than the compute warps need for it) has the TMA engine assemble the unit's VIRTUAL SOURCE ROW in
 //     shared memory: for every stretch of columns whose source row is certain, one cp.async.bulk of that row's depth bytes and
 //     one of its colour bytes at the columns' natural offsets (16-pixel sub-blocks of 48 bytes are the granularity).  "Certain"
 //     means the prediction |v' - r| < 0.494 holds with a margin the float32 chain cannot eat (it is within 2e-3 px of the
@@ -32,8 +33,8 @@
 // HBM traffic is the algorithmic 14 B/px (each source row is read by ~2-3 neighbouring target rows of the same CTA and by
 // both eyes: L2 hits).  Geometry outside the limits below (checked on the host by mdvt_stereo_conv_vrows_supported) goes
 // through the generic frame loop instead.
-// Measured on the B200 (1080p, 32 frames per launch): 13.3 us per frame at a convergence distance of 5 m, 14.9 at 2 m, 18.1
-// at 1 m (generic two-lane loop: 18.9; round 1's target-row kernel: 23.0); profiles/r02_vrows_*.
+// Measured on the B200 (32 frames per launch): 1080p 12.5 us per frame at a convergence distance of 5 m, 14.2 at 2 m, 17.6 at
+// 1 m (generic two-lane loop: 17.4; round 1's target-row kernel: 22.6); 4K 51.6 us (generic loop 89.3); profiles/r02_vrows_*.
 #include <cmath>
 #include <cstdlib>
 #include <type_traits>
@@ -43,6 +44,9 @@
 #ifndef MDVT_VROWS_NB
 #define MDVT_VROWS_NB 4
 #endif
+#ifndef MDVT_VROWS_NP
+#define MDVT_VROWS_NP 2     // producer warps per CTA (1 or 2)
+#endif
 #ifndef MDVT_VROWS_MINB
 #define MDVT_VROWS_MINB 4   // resident CTAs per SM the register allocation aims at (tuning aid)
 #endif
@@ -50,7 +54,10 @@
 namespace mdvt {
 
 constexpr int kSub = 16;            // pixels per sub-block: 48 bytes of u8x3, the TMA granularity of the assembly
-constexpr int kAltSlots = 24;       // alternate sub-blocks with their data staged in shared memory (more are read from global memory)
+#ifndef MDVT_VROWS_ALTSLOTS
+#define MDVT_VROWS_ALTSLOTS 24
+#endif
+constexpr int kAltSlots = MDVT_VROWS_ALTSLOTS;       // alternate sub-blocks with their data staged in shared memory (more are read from global memory)
 constexpr uint32_t kEmpty32 = 0xFFFFFFFFu;
 constexpr float kVMagic = 12582912.0f;  // 1.5 * 2^23
 constexpr int kVMagicBits = 0x4B400000;
@@ -68,7 +75,7 @@ struct VrowSmem {
 __host__ __device__ inline VrowSmem vrow_smem_layout(int width, int mask_bpp) {
     VrowSmem L;
     const int nsub = width / kSub;
-    int off = 64 + 2 * 96 + 64;  // [0,16): two mbarriers; [64, 256): two StairFrame slots; [256, 320): both eyes' EyeConsts
+    int off = 64 + 4 * 96 + 64;  // [0,16): two mbarriers; [64, 448): two StairFrame slots per producer warp; [448, 512): both eyes' EyeConsts
     L.alt_off = off;  L.alt_stride = (1 + 4 * nsub) * 4;       off += 2 * L.alt_stride;
     off = (off + 15) & ~15;
     L.altdata_off = off; L.altdata_stride = kAltSlots * 96;    off += 2 * L.altdata_stride;
@@ -179,11 +186,97 @@ struct StairFrame {
     int frame, pad;
 };
 
+// The virtual source row of one unit (target row r2 of eye e), assembled by ONE warp: see "row preparation" in the kernel below.
+// vd: the unit's row buffer (depth bytes, then colour bytes); alt / alt_count_a: its list of alternates (generic pointer /
+// shared address of the count, which must be 0 on entry); bar: the unit's mbarrier (one arrival, with the transaction bytes).
+template <int SLOTS>
+__device__ __forceinline__ void vrow_assemble(const StairFrame *sf, int e, int r2, int width, int height, const uint8_t *dframe, const uint8_t *cframe,
+                                              uint8_t *vd, uint32_t *alt, uint32_t alt_count_a, uint8_t *altdata, uint64_t *bar, int lane) {
+    const int nsub = width / kSub;
+    const uint32_t row_bytes = 3u * width;
+    const double rd = (double)r2, m = sf->m[e];
+    const double alpha = rd * sf->k1[e] - sf->k0[e], beta = (rd * sf->c1[e] - sf->c0[e]) - rd;
+    const double d0 = beta, d1 = alpha * (double)(width - 1) + beta;
+    const double dmin = fmin(d0, d1), dmax = fmax(d0, d1);
+    const int kA = (int)ceil(dmin - 1.0 + m), kB = (int)floor(dmax - m);   // zones kA .. kB meet the row
+    const int K = max(0, kB - kA + 1);
+    const bool rising = alpha >= 0.0;
+    const bool flat = fabs(alpha) < 1e-12;
+    const double inv_alpha = flat ? 0.0 : 1.0 / alpha;
+    uint8_t *vc = vd + row_bytes;
+    const int k_clean = (int)rint(0.5 * (d0 + d1));  // the one clean row when no zone meets the row
+    int tx = 0;            // sub-blocks (48 + 48 bytes) this lane has bulk copies in flight for
+    int carry_sb = -1;     // last sub-block of the previous zone (in column order)
+    for (int c0 = 0; c0 <= K; c0 += 32) {
+        const int c = c0 + lane;
+        // zone c (c < K): its index k, its sub-block range [sa, sb]; lane K carries the sentinel sa = nsub
+        const int k = rising ? kA + c : kB - c;
+        int sa = nsub, sb = nsub;
+        if (c < K) {
+            if (flat) {
+                sa = 0; sb = nsub - 1;
+            } else {
+                const double ja = ((double)k + m - beta) * inv_alpha, jb = ((double)k + 1.0 - m - beta) * inv_alpha;
+                const double jlo = fmin(ja, jb) - 0.25, jhi = fmax(ja, jb) + 0.25;
+                // (a zone that numerically just misses the row is clamped onto the edge sub-block: testing that one exactly is harmless)
+                sa = (int)fmin(fmax(floor(jlo * (1.0 / kSub)), 0.0), (double)(nsub - 1));
+                sb = (int)fmin(fmax(floor(jhi * (1.0 / kSub)), (double)sa), (double)(nsub - 1));
+            }
+        }
+        int prev_sb = __shfl_up_sync(0xFFFFFFFFu, sb, 1);
+        if (lane == 0) prev_sb = carry_sb;
+        carry_sb = __shfl_sync(0xFFFFFFFFu, sb, 31);
+        if (c <= K) {
+            // clean stretch before zone c (after the last zone for c == K)
+            const int s_first = prev_sb + 1, s_last = sa - 1;
+            if (s_last >= s_first) {
+                const int krow = K == 0 ? k_clean : (c < K ? (rising ? k : k + 1) : (rising ? kB + 1 : kA));
+                const int row = r2 + krow;
+                if (row >= 0 && row < height) {
+                    const int64_t goff = ((int64_t)row * width + (int64_t)s_first * kSub) * 3;
+                    const uint32_t bytes = 48u * (uint32_t)(s_last - s_first + 1);
+                    bulk_load(vd + 48 * s_first, dframe + goff, bytes, bar);
+                    bulk_load(vc + 48 * s_first, cframe + goff, bytes, bar);
+                    tx += s_last - s_first + 1;
+                } else {
+                    for (int s = s_first; s <= s_last; ++s) {
+                        uint4 *z4 = reinterpret_cast<uint4 *>(vd + 48 * s);
+                        z4[0] = z4[1] = z4[2] = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                }
+            }
+            // the zone itself
+            if (c < K) {
+                for (int s = sa; s <= sb; ++s) {
+                    uint4 *z4 = reinterpret_cast<uint4 *>(vd + 48 * s);
+                    z4[0] = z4[1] = z4[2] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                    for (int up = 0; up < 2; ++up) {
+                        const int row = r2 + k + up;
+                        if (row < 0 || row >= height) continue;
+                        const uint32_t slot = atoms_add(alt_count_a, 1u);
+                        alt[1 + slot] = ((uint32_t)s << 16) | (uint32_t)row;
+                        if (slot < (uint32_t)SLOTS) {
+                            const int64_t goff = ((int64_t)row * width + (int64_t)s * kSub) * 3;
+                            bulk_load(altdata + 96 * slot, dframe + goff, 48u, bar);
+                            bulk_load(altdata + 96 * slot + 48, cframe + goff, 48u, bar);
+                            ++tx;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tx = __reduce_add_sync(0xFFFFFFFFu, tx);
+    __syncwarp();  // every lane's zero bytes and list entries are in place before the arrival that publishes them
+    if (lane == 0) mbar_expect_tx(bar, 96u * (uint32_t)tx);
+}
+
 // MASK_MODE: 0 none, 1 u8 {0,255}, 2 u8x3 (bg colour / black).  A unit of work is one target row of ONE eye (both eyes of a
 // row are consecutive units of the same CTA); T threads, every thread owns the columns tid + n T, n < CPT.  GUARD: W < T * CPT
 // (columns past the row are culled).
 template <int MASK_MODE, int T, int CPT, bool GUARD>
-__global__ void __launch_bounds__(T + 32, T <= 192 ? MDVT_VROWS_MINB : 2)
+__global__ void __launch_bounds__(T + 32 * MDVT_VROWS_NP, T <= 192 ? MDVT_VROWS_MINB : 2)
     stereo_conv_vrows_kernel(const uint8_t *__restrict__ depth_rgb, const uint8_t *__restrict__ colour_rgb, int n_units, int width, int height,
                              const mdvt_conv_frame *__restrict__ frames, uint32_t bg_rgb, uint32_t fill_rgb, int collide,
                              uint8_t *__restrict__ out_sbs, uint8_t *__restrict__ out_mask, float *__restrict__ out_depth,
@@ -193,11 +286,11 @@ __global__ void __launch_bounds__(T + 32, T <= 192 ? MDVT_VROWS_MINB : 2)
     constexpr int kWarps = T / 32;
     const VrowSmem L = vrow_smem_layout(width, mask_bpp);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);  // bar[0], bar[1]: the two sets of row buffers
-    StairFrame *s_stair = reinterpret_cast<StairFrame *>(smem + 64);  // [2]
-    EyeConsts *s_eye = reinterpret_cast<EyeConsts *>(smem + 256);     // [2]
+    StairFrame *s_stair = reinterpret_cast<StairFrame *>(smem + 64);  // [producer warp][frame parity]
+    EyeConsts *s_eye = reinterpret_cast<EyeConsts *>(smem + 448);     // [2]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool producer = tid >= T;  // the last warp prepares rows (staircase, TMA loads), the others compute
-    const int nsub = width / kSub;
+    constexpr int NP = MDVT_VROWS_NP;
+    const bool producer = tid >= T;  // the last NP warps prepare rows (staircase, TMA loads), the others compute
     const uint32_t row_bytes = 3u * width;
     const uint32_t sm = smem_addr(smem);
 
@@ -205,13 +298,13 @@ __global__ void __launch_bounds__(T + 32, T <= 192 ? MDVT_VROWS_MINB : 2)
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
         mbar_fence_init();
-        s_stair[0].frame = s_stair[1].frame = -1;
+        s_stair[0].frame = s_stair[1].frame = s_stair[2].frame = s_stair[3].frame = -1;
         *reinterpret_cast<uint32_t *>(smem + L.alt_off) = 0u;
         *reinterpret_cast<uint32_t *>(smem + L.alt_off + L.alt_stride) = 0u;
     }
     {   // z plane: all ones; colour plane: the flagged fill colour (any real colour, < 2^24, beats it; a hole reads as the fill)
         uint32_t *zp = reinterpret_cast<uint32_t *>(smem + L.zp_off), *cp = reinterpret_cast<uint32_t *>(smem + L.cp_off);
-        for (int k = tid; k < width + 4; k += T + 32) {
+        for (int k = tid; k < width + 4; k += T + 32 * NP) {
             zp[k] = kEmpty32;
             cp[k] = fill_rgb | 0xFF000000u;
         }
@@ -249,7 +342,7 @@ __global__ void __launch_bounds__(T + 32, T <= 192 ? MDVT_VROWS_MINB : 2)
     // before that arrival, and tx-counts may run negative meanwhile).
     auto prepare_items = [&](int buf) {  // unit (frame2, r2, eye2) -> buffers `buf`
         const int e = eye2;
-        StairFrame *sf = &s_stair[frame2 & 1];
+        StairFrame *sf = &s_stair[2 * (warp - kWarps) + (frame2 & 1)];
         if (sf->frame != frame2) {  // first unit of a frame in this CTA (always eye 0 or the CTA's very first unit): both eyes at once
             __syncwarp();
             if (lane < 2) {
@@ -273,92 +366,34 @@ __global__ void __launch_bounds__(T + 32, T <= 192 ? MDVT_VROWS_MINB : 2)
             if (lane == 0) sf->frame = frame2;
             __syncwarp();
         }
-        const double rd = (double)r2, m = sf->m[e];
-        const double alpha = rd * sf->k1[e] - sf->k0[e], beta = (rd * sf->c1[e] - sf->c0[e]) - rd;
-        const double d0 = beta, d1 = alpha * (double)(width - 1) + beta;
-        const double dmin = fmin(d0, d1), dmax = fmax(d0, d1);
-        const int kA = (int)ceil(dmin - 1.0 + m), kB = (int)floor(dmax - m);   // zones kA .. kB meet the row
-        const int K = max(0, kB - kA + 1);
-        const bool rising = alpha >= 0.0;
-        const bool flat = fabs(alpha) < 1e-12;
-        const double inv_alpha = flat ? 0.0 : 1.0 / alpha;
-        uint8_t *vd = smem + L.raw_off + buf * L.raw_stride, *vc = vd + row_bytes;
-        const uint8_t *dframe = depth_rgb + (int64_t)frame2 * height * row_bytes;
-        const uint8_t *cframe = colour_rgb + (int64_t)frame2 * height * row_bytes;
-        uint32_t *alt = reinterpret_cast<uint32_t *>(smem + L.alt_off + buf * L.alt_stride);
-        uint8_t *altdata = smem + L.altdata_off + buf * L.altdata_stride;
-        const uint32_t alt_count_a = sm + L.alt_off + buf * L.alt_stride;
-        const int k_clean = (int)rint(0.5 * (d0 + d1));  // the one clean row when no zone meets the row
-        int tx = 0;            // sub-blocks (48 + 48 bytes) this lane has bulk copies in flight for
-        int carry_sb = -1;     // last sub-block of the previous zone (in column order)
-        for (int c0 = 0; c0 <= K; c0 += 32) {
-            const int c = c0 + lane;
-            // zone c (c < K): its index k, its sub-block range [sa, sb]; lane K carries the sentinel sa = nsub
-            const int k = rising ? kA + c : kB - c;
-            int sa = nsub, sb = nsub;
-            if (c < K) {
-                if (flat) {
-                    sa = 0; sb = nsub - 1;
-                } else {
-                    const double ja = ((double)k + m - beta) * inv_alpha, jb = ((double)k + 1.0 - m - beta) * inv_alpha;
-                    const double jlo = fmin(ja, jb) - 0.25, jhi = fmax(ja, jb) + 0.25;
-                    // (a zone that numerically just misses the row is clamped onto the edge sub-block: testing that one exactly is harmless)
-                    sa = (int)fmin(fmax(floor(jlo * (1.0 / kSub)), 0.0), (double)(nsub - 1));
-                    sb = (int)fmin(fmax(floor(jhi * (1.0 / kSub)), (double)sa), (double)(nsub - 1));
-                }
-            }
-            int prev_sb = __shfl_up_sync(0xFFFFFFFFu, sb, 1);
-            if (lane == 0) prev_sb = carry_sb;
-            carry_sb = __shfl_sync(0xFFFFFFFFu, sb, 31);
-            if (c <= K) {
-                // clean stretch before zone c (after the last zone for c == K)
-                const int s_first = prev_sb + 1, s_last = sa - 1;
-                if (s_last >= s_first) {
-                    const int krow = K == 0 ? k_clean : (c < K ? (rising ? k : k + 1) : (rising ? kB + 1 : kA));
-                    const int row = r2 + krow;
-                    if (row >= 0 && row < height) {
-                        const int64_t goff = ((int64_t)row * width + (int64_t)s_first * kSub) * 3;
-                        const uint32_t bytes = 48u * (uint32_t)(s_last - s_first + 1);
-                        bulk_load(vd + 48 * s_first, dframe + goff, bytes, &bar[buf]);
-                        bulk_load(vc + 48 * s_first, cframe + goff, bytes, &bar[buf]);
-                        tx += s_last - s_first + 1;
-                    } else {
-                        for (int s = s_first; s <= s_last; ++s) {
-                            uint4 *z4 = reinterpret_cast<uint4 *>(vd + 48 * s);
-                            z4[0] = z4[1] = z4[2] = make_uint4(0u, 0u, 0u, 0u);
-                        }
-                    }
-                }
-                // the zone itself
-                if (c < K) {
-                    for (int s = sa; s <= sb; ++s) {
-                        uint4 *z4 = reinterpret_cast<uint4 *>(vd + 48 * s);
-                        z4[0] = z4[1] = z4[2] = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-                        for (int up = 0; up < 2; ++up) {
-                            const int row = r2 + k + up;
-                            if (row < 0 || row >= height) continue;
-                            const uint32_t slot = atoms_add(alt_count_a, 1u);
-                            alt[1 + slot] = ((uint32_t)s << 16) | (uint32_t)row;
-                            if (slot < (uint32_t)kAltSlots) {
-                                const int64_t goff = ((int64_t)row * width + (int64_t)s * kSub) * 3;
-                                bulk_load(altdata + 96 * slot, dframe + goff, 48u, &bar[buf]);
-                                bulk_load(altdata + 96 * slot + 48, cframe + goff, 48u, &bar[buf]);
-                                ++tx;
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        tx = __reduce_add_sync(0xFFFFFFFFu, tx);
-        __syncwarp();  // every lane's zero bytes and list entries are in place before the arrival that publishes them
-        if (lane == 0) mbar_expect_tx(&bar[buf], 96u * (uint32_t)tx);
+        vrow_assemble<kAltSlots>(sf, e, r2, width, height, depth_rgb + (int64_t)frame2 * height * row_bytes, colour_rgb + (int64_t)frame2 * height * row_bytes,
+                      smem + L.raw_off + buf * L.raw_stride, reinterpret_cast<uint32_t *>(smem + L.alt_off + buf * L.alt_stride),
+                      sm + L.alt_off + buf * L.alt_stride, smem + L.altdata_off + buf * L.altdata_stride, &bar[buf], lane);
     };
     if (producer) {
         // Two units ahead of the compute warps: the buffers of unit u (virtual row, alternates) are free once every compute warp
-        // has passed barrier (B) of unit u -- the producer joins that barrier and then prepares unit u + 2 into them, so a unit's
-        // loads are issued a full unit time before their first use.
+        // has passed barrier (B) of unit u, and the unit's loads are issued a full unit time before their first use.  With two
+        // producer warps, warp pw owns buffer set pw = the units of eye pw (unit_begin is even) and joins only their barrier (B)
+        // -- the compute warps alternate between two barrier ids -- so it has two unit times per row; assembling a row of many
+        // steps takes one warp longer than the compute warps need for it.
+        const int pw = warp - kWarps;
+        if (NP == 2) {
+            if (pw == 1) {
+                if (unit_begin + 1 >= unit_end) return;
+                advance(frame2, r2, eye2);
+            }
+            prepare_items(pw);
+            for (int unit = unit_begin + pw; unit < unit_end; unit += 2) {
+                if (pw) named_barrier(3, T + 32);  // (B) of this unit
+                else named_barrier(2, T + 32);
+                if (unit + 2 < unit_end) {
+                    advance(frame2, r2, eye2);
+                    advance(frame2, r2, eye2);
+                    prepare_items(pw);
+                }
+            }
+            return;
+        }
         prepare_items(0);
         if (unit_begin + 1 < unit_end) {
             advance(frame2, r2, eye2);
@@ -421,6 +456,27 @@ __global__ void __launch_bounds__(T + 32, T <= 192 ? MDVT_VROWS_MINB : 2)
         const uint32_t alt_a = sm + L.alt_off + buf * L.alt_stride;
         const uint8_t *altdata = smem + L.altdata_off + buf * L.altdata_stride;
         mbar_wait_a(bar_a + 8u * (uint32_t)buf, (uint32_t)((it >> 1) & 1));
+        // The unit's alternates (sub-block << 16 | source row): the first kAltSlots have their bytes staged in shared memory, the
+        // rest come from global memory (L2: the rows were just copied for the neighbouring units).  Each half-warp fetches its
+        // first alternate HERE, ahead of pass 1, so that the latency hides behind the main columns, and keeps it in registers for
+        // pass 2; later ones (strong rotations only) are re-evaluated there.
+        const int n_alt = (int)lds32(alt_a);
+        auto alt_fetch = [&](int a, uint32_t &ent, uint32_t &red, uint32_t &blue, uint32_t &col) {
+            ent = lds32(alt_a + 4u + 4u * (uint32_t)a);
+            if (a < kAltSlots) {
+                const uint8_t *d = altdata + 96 * a + 3 * (lane & 15);
+                red = d[0]; blue = d[2];
+                col = (uint32_t)d[48] | ((uint32_t)d[49] << 8) | ((uint32_t)d[50] << 16);
+            } else {
+                const int s = (int)(ent >> 16), ia = (int)(ent & 0xFFFFu);
+                const int64_t off = ((int64_t)frame * height * width + (int64_t)ia * width + s * kSub + (lane & 15)) * 3;
+                red = __ldg(depth_rgb + off); blue = __ldg(depth_rgb + off + 2);
+                col = (uint32_t)__ldg(colour_rgb + off) | ((uint32_t)__ldg(colour_rgb + off + 1) << 8) | ((uint32_t)__ldg(colour_rgb + off + 2) << 16);
+            }
+        };
+        const int a0 = 2 * warp + (lane >> 4);
+        uint32_t a0_ent = 0u, a0_red = 0u, a0_blue = 0u, a0_col = kEmpty32;
+        if (a0 < n_alt) alt_fetch(a0, a0_ent, a0_red, a0_blue, a0_col);
 
         // ---- pass 1: every candidate -> z plane ------------------------------------------------------------
         uint32_t c_addr[CPT], c_z[CPT];  // byte address of the candidate's z-plane slot, key bits of its Zv
@@ -459,23 +515,10 @@ __global__ void __launch_bounds__(T + 32, T <= 192 ? MDVT_VROWS_MINB : 2)
         const float rz_min = fminf(ec.Cz, __fmaf_rn(ec.Az, (float)(width - 1), ec.Cz));
         if (near_plane < __fmul_rn(__fmul_rn(dec16, depth_scale), rz_min) * 0.999f) pass1(std::false_type{});
         else pass1(std::true_type{});
-        // alternates: half a warp per sub-block and source row, with the exact row test; the first kAltSlots from shared
-        // memory, the rest (strong rotations only) from global memory
-        const int n_alt = (int)lds32(alt_a);
-        auto alternate = [&](int a, uint32_t &addr, uint32_t &zb, uint32_t &col) {
-            const uint32_t ent = lds32(alt_a + 4u + 4u * (uint32_t)a);
+        // alternates: half a warp per sub-block and source row, with the exact row test
+        auto alt_project = [&](uint32_t ent, uint32_t red, uint32_t blue, uint32_t &addr, uint32_t &zb) {
             const int s = (int)(ent >> 16), ia = (int)(ent & 0xFFFFu);
             const int j = s * kSub + (lane & 15);
-            uint32_t red, blue;
-            if (a < kAltSlots) {
-                const uint8_t *d = altdata + 96 * a + 3 * (lane & 15);
-                red = d[0]; blue = d[2];
-                col = (uint32_t)d[48] | ((uint32_t)d[49] << 8) | ((uint32_t)d[50] << 16);
-            } else {
-                const int64_t off = ((int64_t)frame * height * width + (int64_t)ia * width + j) * 3;
-                red = __ldg(depth_rgb + off); blue = __ldg(depth_rgb + off + 2);
-                col = (uint32_t)__ldg(colour_rgb + off) | ((uint32_t)__ldg(colour_rgb + off + 1) << 8) | ((uint32_t)__ldg(colour_rgb + off + 2) << 16);
-            }
             const uint32_t t = 0x4B000000u | (red << 8) | blue;
             const float z = __fmul_rn(__fmaf_rn(__uint_as_float(t), dec16, neg_bias), depth_scale);
             const float fj = __int2float_rn(j);
@@ -484,15 +527,15 @@ __global__ void __launch_bounds__(T + 32, T <= 192 ? MDVT_VROWS_MINB : 2)
             if (vrow_target_row(z, fj, ec, (float)ia, Zv, rz) != r) slot = w32;
             addr = zp_a + 4u * slot;
         };
-        const int a0 = 2 * warp + (lane >> 4);  // this half-warp's first alternate stays in registers for pass 2, later ones are re-evaluated
-        uint32_t a0_addr = zp_a + 4u * w32, a0_z = kEmpty32, a0_col = kEmpty32;
+        uint32_t a0_addr = zp_a + 4u * w32, a0_z = kEmpty32;
         if (a0 < n_alt) {
-            alternate(a0, a0_addr, a0_z, a0_col);
+            alt_project(a0_ent, a0_red, a0_blue, a0_addr, a0_z);
             reds_min(a0_addr, a0_z);
         }
         for (int a = a0 + 2 * kWarps; a < n_alt; a += 2 * kWarps) {
-            uint32_t addr, zb, col;
-            alternate(a, addr, zb, col);
+            uint32_t ent, red, blue, col, addr, zb;
+            alt_fetch(a, ent, red, blue, col);
+            alt_project(ent, red, blue, addr, zb);
             reds_min(addr, zb);
         }
         named_barrier(1, T);  // (A) the z plane holds the nearest Zv of every slot
@@ -523,12 +566,15 @@ __global__ void __launch_bounds__(T + 32, T <= 192 ? MDVT_VROWS_MINB : 2)
         }
         if (a0 < n_alt && lds32(a0_addr) == a0_z) reds_min(a0_addr + cp_delta, a0_col);
         for (int a = a0 + 2 * kWarps; a < n_alt; a += 2 * kWarps) {
-            uint32_t addr, zb, col;
-            alternate(a, addr, zb, col);
+            uint32_t ent, red, blue, col, addr, zb;
+            alt_fetch(a, ent, red, blue, col);
+            alt_project(ent, red, blue, addr, zb);
             if (lds32(addr) == zb) reds_min(addr + cp_delta, col);
         }
         if (tid == 0) bulk_wait_read<0>();  // the previous unit's staged output has left shared memory (its store was issued a unit ago)
-        named_barrier(2, T + 32);  // (B) both planes final; this unit's virtual row and alternates are dead: the producer reloads them
+        // (B) both planes final; this unit's virtual row and alternates are dead: its producer reloads them
+        if (NP == 2 && buf) named_barrier(3, T + 32);
+        else named_barrier(2, T + 32);
 
         // ---- phase B: planes -> colours, hole mask, depth; planes re-armed ---------------------------------------------
         const int row_unit = unit >> 1;  // frame * height + r
@@ -643,13 +689,13 @@ extern "C" int mdvt_stereo_conv_vrows(const uint8_t *depth_rgb, const uint8_t *c
         auto kernel = stereo_conv_vrows_kernel<M, TT, CC, GG>;                                                                            \
         MDVT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));                            \
         int ctas = 0;                                                                                                                 \
-        MDVT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kernel, TT + 32, L.total));                                \
+        MDVT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kernel, TT + 32 * MDVT_VROWS_NP, L.total));                \
         if (ctas < 1) ctas = 1;                                                                                                       \
         int grid = sm_count() * ctas;                                                                                                 \
         if (grid > n_units) grid = n_units;                                                                                           \
         const int per = (((n_units + grid - 1) / grid) + 1) & ~1; /* both eyes of a row in one CTA */                                 \
         grid = (n_units + per - 1) / per; /* no empty CTAs */                                                                         \
-        kernel<<<grid, TT + 32, L.total, st>>>(depth_rgb, colour_rgb, n_units, width, height, frames_dev, bg_rgb & 0xFFFFFF,          \
+        kernel<<<grid, TT + 32 * MDVT_VROWS_NP, L.total, st>>>(depth_rgb, colour_rgb, n_units, width, height, frames_dev, bg_rgb & 0xFFFFFF,          \
                                                fill_rgb & 0xFFFFFF, (flags & MDVT_FLAG_BG_COLLIDE) ? 1 : 0, out_sbs, out_mask, out_depth, \
                                                status_dev);                                                                           \
     } while (0)
