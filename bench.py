@@ -586,7 +586,7 @@ def run_ours(args):
         try:
             from metric_depth_video_toolbox_b200 import ffv1_gpu
 
-            batch = min(128, n_frames)   # one thread per slice: the coder needs ~100 k slices in flight to fill the machine (32 frames: 10 % occupancy)
+            batch = min(64, n_frames)    # one thread per slice with 1 KB of coder state each: 64 frames is the sweet spot (3 840 x 1 080, film-like content: 4.30 k frames/s at 64, 3.36 k at 128 and 256 -- the states of 128 k slices no longer fit the L2; profiles/r02_ffv1_gpu_bench_batch_sweep.jsonl)
             result_codec = {"what": "FFV1 v3 entropy coding of the SBS result on the device (mdvt_ffv1_encode_frames), not part of `value`",
                             "frame": f"{2 * WIDTH}x{HEIGHT}", "batch": batch}
             for model, key in ((0, "libavcodec_tables_666_contexts"), (1, "small_tables_63_contexts")):
