@@ -589,40 +589,35 @@ def run_ours(args):
             batch = min(64, n_frames)    # one thread per slice with 1 KB of coder state each: 64 frames is the sweet spot (3 840 x 1 080, film-like content: 4.30 k frames/s at 64, 3.36 k at 128 and 256 -- the states of 128 k slices no longer fit the L2; profiles/r02_ffv1_gpu_bench_batch_sweep.jsonl)
             result_codec = {"what": "FFV1 v3 entropy coding of the SBS result on the device (mdvt_ffv1_encode_frames), not part of `value`",
                             "frame": f"{2 * WIDTH}x{HEIGHT}", "batch": batch}
-            for model, key in ((0, "libavcodec_tables_666_contexts"), (1, "small_tables_63_contexts")):
-                enc = ffv1_gpu.Ffv1Encoder(2 * WIDTH, HEIGHT, dev, max_frames=batch, context_model=model)
-                enc.encode_device(out_sbs[:batch])
+
+            def time_encoder(frames_dev, model, frames_per_launch):
+                enc = ffv1_gpu.Ffv1Encoder(2 * WIDTH, HEIGHT, dev, max_frames=frames_per_launch, context_model=model)
+                enc.encode_device(frames_dev[:frames_per_launch])
                 torch.cuda.synchronize()
                 c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 c0.record()
                 for _ in range(3):
-                    _, offsets = enc.encode_device(out_sbs[:batch])
+                    _, offsets = enc.encode_device(frames_dev[:frames_per_launch])
                 c1.record()
                 torch.cuda.synchronize()
                 ms = c0.elapsed_time(c1) / 3
-                result_codec[key] = {"frames_per_s": 1e3 * batch / ms, "ms_per_frame": ms / batch, "slices_per_frame": enc.per_frame,
-                                     "bytes_per_frame": int(offsets[-1].item()) / batch}
-                del enc
+                return {"frames_per_s": 1e3 * frames_per_launch / ms, "ms_per_frame": ms / frames_per_launch, "batch": frames_per_launch,
+                        "slices_per_frame": enc.per_frame, "bytes_per_frame": int(offsets[-1].item()) / frames_per_launch}
+
+            # model 2 keeps its 224 bytes of state per slice in shared memory and wants more slices in flight (128 frames per launch)
+            for model, key, per_launch in ((0, "libavcodec_tables_666_contexts", batch), (1, "small_tables_63_contexts", batch),
+                                           (2, "tiny_tables_14_contexts", min(128, n_frames))):
+                result_codec[key] = time_encoder(out_sbs, model, per_launch)
             # the same coder on film-like content (a blurred texture that pans, sensor noise in the low bits, a flat patch and a
             # black band: benchmarks/ffv1_gpu_bench.frames_like) -- the rendered synthetic clip above is i.i.d. colour noise, which
             # no lossless coder compresses (13.8 MB of packets per 12.4 MB frame) and which takes the long escape codes everywhere
             sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
             from ffv1_gpu_bench import frames_like
 
-            film = torch.from_numpy(frames_like(2 * WIDTH, HEIGHT, 64)).to(dev)
-            enc = ffv1_gpu.Ffv1Encoder(2 * WIDTH, HEIGHT, dev, max_frames=64, context_model=1)
-            enc.encode_device(film)
-            torch.cuda.synchronize()
-            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            c0.record()
-            for _ in range(3):
-                _, offsets = enc.encode_device(film)
-            c1.record()
-            torch.cuda.synchronize()
-            ms = c0.elapsed_time(c1) / 3
-            result_codec["film_like_content_63_contexts"] = {"frames_per_s": 1e3 * 64 / ms, "ms_per_frame": ms / 64, "batch": 64,
-                                                             "bytes_per_frame": int(offsets[-1].item()) / 64}
-            del enc, film
+            film = torch.from_numpy(frames_like(2 * WIDTH, HEIGHT, 128)).to(dev)
+            result_codec["film_like_content_63_contexts"] = time_encoder(film, 1, 64)
+            result_codec["film_like_content_14_contexts"] = time_encoder(film, 2, 128)
+            del film
         except Exception as exc:  # noqa: BLE001 - informational leg only
             result_codec = {"error": f"{type(exc).__name__}: {exc}"}
 

@@ -40,7 +40,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--cv_frames", type=int, default=2)
-    ap.add_argument("--context_model", type=int, default=0, help="0: libavcodec's 666 contexts, 1: 63 contexts")
+    ap.add_argument("--context_model", type=int, default=0, help="0: libavcodec's 666 contexts, 1: 63 contexts, 2: 14 contexts (coder states in shared memory)")
     ap.add_argument("--decode", action="store_true", help="also time Ffv1Decoder.decode on the packets (H2D of the packets + kernels + status read)")
     ap.add_argument("--encode_only", action="store_true", help="skip the cv2.VideoWriter and file legs")
     ap.add_argument("--grids", default="auto,32x32,16x16", help="slice grids to time: auto or NHxNV, comma separated")

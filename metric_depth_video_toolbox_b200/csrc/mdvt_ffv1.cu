@@ -200,7 +200,7 @@ int check_stream(int width, int height, int nh, int nv, int alpha) {
 }
 
 int check_model(int context_model) {
-    MDVT_REQUIRE(context_model == 0 || context_model == 1, "context_model must be 0 (libavcodec's 666 contexts) or 1 (63 contexts)");
+    MDVT_REQUIRE(context_model >= 0 && context_model <= 2, "context_model must be 0 (libavcodec's 666 contexts), 1 (63 contexts) or 2 (14 contexts)");
     return MDVT_OK;
 }
 
@@ -252,7 +252,44 @@ __global__ void __launch_bounds__(64) ffv1_encode_kernel(const uint8_t *__restri
     job.states = states + t * (int64_t)((n_planes > 3 ? 3 : 2) * mdvt_ffv1::contexts_of(model));
     job.out = out + t * capacity;
     job.crc_table = crc_s;
-    sizes[t] = (int32_t)(model ? mdvt_ffv1::encode_slice<true>(job) : mdvt_ffv1::encode_slice<false>(job));
+    sizes[t] = (int32_t)(model == 2 ? mdvt_ffv1::encode_slice<2>(job) : (model ? mdvt_ffv1::encode_slice<1>(job) : mdvt_ffv1::encode_slice<0>(job)));
+}
+
+// Context model 2 without the alpha plane: the 2 x 14 states of a slice (224 bytes) live in SHARED memory, context-major and
+// interleaved over the CTA's threads (state of context c of thread t at [c * TPB + t]: the threads of a warp that sit in the
+// same context hit consecutive banks).  14.3 KB per 64 slices: the register file, not the shared memory, bounds the resident
+// warps, and a state access costs a shared-memory round trip instead of an L1 / L2 one (with 1 KB per slice, model 1, the same
+// layout leaves 6 warps per SM and buys nothing: profiles/r02_ffv1_state_experiments.txt).
+template <int TPB>
+__global__ void __launch_bounds__(TPB) ffv1_encode_tiny_kernel(const uint8_t *__restrict__ frames, int64_t frame_stride, int64_t row_pitch,
+                                                               int n_frames, int width, int height, int nh, int nv, int ib, int ir,
+                                                               const uint8_t *__restrict__ headers, const int32_t *__restrict__ header_len,
+                                                               uint8_t *out, int64_t capacity, int32_t *sizes) {
+    __shared__ uint32_t crc_s[1024];
+    __shared__ mdvt_ffv1::VlcState state_s[2 * mdvt_ffv1::kContextsTiny * TPB];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) crc_s[i] = g_crc_table[i];
+    __syncthreads();
+    const int per_frame = nh * nv;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)n_frames * per_frame) return;
+    const int f = (int)(t / per_frame), si = (int)(t - (int64_t)f * per_frame);
+    const int sy = si / nh, sx = si - sy * nh;
+    const int x0 = (int)((int64_t)sx * width / nh), x1 = (int)((int64_t)(sx + 1) * width / nh);
+    const int y0 = (int)((int64_t)sy * height / nv), y1 = (int)((int64_t)(sy + 1) * height / nv);
+    mdvt_ffv1::SliceJob job;
+    job.frame = frames + f * frame_stride + y0 * row_pitch + 3 * (int64_t)x0;
+    job.row_pitch = row_pitch;
+    job.w = x1 - x0;
+    job.h = y1 - y0;
+    job.n_planes = 3;
+    job.ib = ib;
+    job.ir = ir;
+    job.header = headers + si * mdvt_ffv1::kHeaderStride;
+    job.header_len = header_len[si];
+    job.states = state_s + threadIdx.x;
+    job.out = out + t * capacity;
+    job.crc_table = crc_s;
+    sizes[t] = (int32_t)mdvt_ffv1::encode_slice<2, TPB>(job);
 }
 
 // ---- decoder ----------------------------------------------------------------------------------------------------------
@@ -315,7 +352,46 @@ __global__ void __launch_bounds__(64, 12) ffv1_decode_kernel(const uint8_t *__re
     in.ir = ir;
     in.states = states + t * (int64_t)((n_planes > 3 ? 3 : 2) * mdvt_ffv1::contexts_of(model));
     in.crc_table = crc_s;
-    const int code = model ? mdvt_ffv1::decode_slice<true>(in) : mdvt_ffv1::decode_slice<false>(in);
+    const int code = model == 2 ? mdvt_ffv1::decode_slice<2>(in) : (model ? mdvt_ffv1::decode_slice<1>(in) : mdvt_ffv1::decode_slice<0>(in));
+    if (code < 0) atomicMin(&status[f], code - 2);   // -3: foreign slice header, -4: slice size, -5: bit stream overrun, -6: CRC
+}
+
+// The decoder for context model 2 without the alpha plane, coder states in shared memory (see ffv1_encode_tiny_kernel).
+template <int TPB>
+__global__ void __launch_bounds__(TPB, 12) ffv1_decode_tiny_kernel(const uint8_t *__restrict__ packets, const int64_t *__restrict__ packet_offsets,
+                                                                   const int64_t *__restrict__ slice_offsets, int n_frames, int width, int height,
+                                                                   int nh, int nv, int ib, int ir, const uint8_t *__restrict__ headers,
+                                                                   const int32_t *__restrict__ header_len, uint8_t *frames, int64_t frame_stride,
+                                                                   int64_t row_pitch, int32_t *status) {
+    __shared__ uint32_t crc_s[256];
+    __shared__ mdvt_ffv1::VlcState state_s[2 * mdvt_ffv1::kContextsTiny * TPB];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) crc_s[i] = g_crc_table[i];
+    __syncthreads();
+    const int per_frame = nh * nv;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)n_frames * per_frame) return;
+    const int f = (int)(t / per_frame), si = (int)(t - (int64_t)f * per_frame);
+    if (status[f] == -2) return;   // the index kernel could not split this packet
+    const int sy = si / nh, sx = si - sy * nh;
+    const int x0 = (int)((int64_t)sx * width / nh), x1 = (int)((int64_t)(sx + 1) * width / nh);
+    const int y0 = (int)((int64_t)sy * height / nv), y1 = (int)((int64_t)(sy + 1) * height / nv);
+    const int64_t begin = slice_offsets[t];
+    const int64_t end = si + 1 < per_frame ? slice_offsets[t + 1] : packet_offsets[f + 1];
+    mdvt_ffv1::SliceInput in;
+    in.data = packets + begin;
+    in.size = (uint32_t)(end - begin);
+    in.header = headers + si * mdvt_ffv1::kHeaderStride;
+    in.header_len = header_len[si];
+    in.frame = frames + f * frame_stride + y0 * row_pitch + 3 * (int64_t)x0;
+    in.row_pitch = row_pitch;
+    in.w = x1 - x0;
+    in.h = y1 - y0;
+    in.n_planes = 3;
+    in.ib = ib;
+    in.ir = ir;
+    in.states = state_s + threadIdx.x;
+    in.crc_table = crc_s;
+    const int code = mdvt_ffv1::decode_slice<2, TPB>(in);
     if (code < 0) atomicMin(&status[f], code - 2);   // -3: foreign slice header, -4: slice size, -5: bit stream overrun, -6: CRC
 }
 
@@ -392,7 +468,7 @@ extern "C" int64_t mdvt_ffv1_slice_capacity(int width, int height, int nh, int n
 }
 
 extern "C" int64_t mdvt_ffv1_state_bytes(int n_frames, int nh, int nv, int alpha, int context_model) {
-    if (n_frames < 0 || nh < 1 || nv < 1 || nh * nv > 1024 || (context_model != 0 && context_model != 1)) return -1;
+    if (n_frames < 0 || nh < 1 || nv < 1 || nh * nv > 1024 || context_model < 0 || context_model > 2) return -1;
     return (int64_t)n_frames * nh * nv * (alpha ? 3 : 2) * mdvt_ffv1::contexts_of(context_model) * (int64_t)sizeof(mdvt_ffv1::VlcState);
 }
 
@@ -402,9 +478,9 @@ extern "C" int mdvt_ffv1_stream_setup(int width, int height, int nh, int nv, int
     if (int rc = mdvt::check_stream(width, height, nh, nv, alpha)) return rc;
     if (int rc = mdvt::check_model(context_model)) return rc;
     MDVT_REQUIRE(config_host && config_len && headers_host && header_len_host, "NULL output");
-    static const int q11[] = {1, 1, 3, 7, 23, 93}, q5[] = {1, 3, 124}, q0[] = {128};
+    static const int q11[] = {1, 1, 3, 7, 23, 93}, q5[] = {1, 3, 124}, q3[] = {1, 127}, q0[] = {128};
     {   // ffv1enc.c write_extradata: version 3.4, Golomb-Rice, RGB, 8 bit; model 0: both of libavcodec's quant-table sets
-        // (as its encoder writes them), model 1: one set, the 5-level table on three inputs
+        // (as its encoder writes them), model 1: one set, the 5-level table on three inputs, model 2: one set, the 3-level table
         RangeCoder rc;
         uint8_t st[32];
         memset(st, 128, sizeof st);
@@ -434,7 +510,10 @@ extern "C" int mdvt_ffv1_stream_setup(int width, int height, int nh, int nv, int
             rc.put_rac(st, 0);
         } else {
             rc.put_symbol(st, 1, false);
-            for (int k = 0; k < 3; ++k) mdvt::write_run_table(rc, q5, 3);
+            for (int k = 0; k < 3; ++k) {
+                if (context_model == 1) mdvt::write_run_table(rc, q5, 3);
+                else mdvt::write_run_table(rc, q3, 2);
+            }
             for (int k = 3; k < 5; ++k) mdvt::write_run_table(rc, q0, 1);
             rc.put_rac(st, 0);
         }
@@ -492,9 +571,14 @@ extern "C" int mdvt_ffv1_encode_frames(const uint8_t *frames, int64_t frame_stri
     MDVT_REQUIRE(total < (1LL << 30), "too many slices in one call");
     mdvt::ffv1_crc_table_kernel<<<1, 256, 0, s>>>();
     const int threads = 64;
-    mdvt::ffv1_encode_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(
-        frames, frame_stride, row_pitch, n_frames, width, height, nh, nv, 3 + alpha, bgr_order ? 0 : 2, bgr_order ? 2 : 0, context_model,
-        headers, header_len, static_cast<mdvt_ffv1::VlcState *>(states), slices, capacity, sizes);
+    if (context_model == 2 && !alpha)
+        mdvt::ffv1_encode_tiny_kernel<64><<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(
+            frames, frame_stride, row_pitch, n_frames, width, height, nh, nv, bgr_order ? 0 : 2, bgr_order ? 2 : 0, headers, header_len, slices,
+            capacity, sizes);
+    else
+        mdvt::ffv1_encode_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(
+            frames, frame_stride, row_pitch, n_frames, width, height, nh, nv, 3 + alpha, bgr_order ? 0 : 2, bgr_order ? 2 : 0, context_model,
+            headers, header_len, static_cast<mdvt_ffv1::VlcState *>(states), slices, capacity, sizes);
     mdvt::ffv1_offsets_kernel<<<1, 1024, 0, s>>>(sizes, n_frames, per_frame, offsets);
     mdvt::ffv1_pack_kernel<<<(unsigned)total, 128, 0, s>>>(slices, capacity, sizes, offsets, packed);
     MDVT_CUDA_TRY(cudaGetLastError());
@@ -511,7 +595,7 @@ extern "C" int mdvt_ffv1_parse_config(const uint8_t *config_host, int config_len
     const int bits = rr.get_symbol(st), chroma = rr.get_rac(st), hshift = rr.get_symbol(st), vshift = rr.get_symbol(st);
     const int transparency = rr.get_rac(st);
     const int h_slices = 1 + rr.get_symbol(st), v_slices = 1 + rr.get_symbol(st);
-    const int model = rr.get_symbol(st) == 1 ? 1 : 0;   // quant table sets: 1 = this library's small model, 2 = libavcodec's
+    const int table_sets = rr.get_symbol(st);           // quant table sets: 1 = one of this library's small models, 2 = libavcodec's
     (void)micro, (void)bits, (void)chroma, (void)hshift, (void)vshift;
     if (rr.bad || version != 3 || coder != 0 || colourspace != 1) {
         mdvt::set_error("not an FFV1 version 3 Golomb-Rice RGB stream (version %d, coder %d, colourspace %d)", version, coder, colourspace);
@@ -523,9 +607,14 @@ extern "C" int mdvt_ffv1_parse_config(const uint8_t *config_host, int config_len
     int own_len = 0;
     std::vector<uint8_t> headers((size_t)h_slices * v_slices * mdvt_ffv1::kHeaderStride);
     std::vector<int32_t> lens((size_t)h_slices * v_slices);
-    if (int rc = mdvt_ffv1_stream_setup(width, height, h_slices, v_slices, transparency, model, own, 64, &own_len, headers.data(),
-                                        lens.data()))
-        return rc;
+    int model = table_sets == 1 ? 1 : 0;
+    for (;;) {
+        if (int rc = mdvt_ffv1_stream_setup(width, height, h_slices, v_slices, transparency, model, own, 64, &own_len, headers.data(),
+                                            lens.data()))
+            return rc;
+        if ((own_len == config_len && memcmp(own, config_host, (size_t)own_len) == 0) || model != 1) break;
+        model = 2;   // one table set that is not model 1's: the record must then be model 2's
+    }
     if (own_len != config_len || memcmp(own, config_host, (size_t)own_len) != 0) {
         mdvt::set_error("FFV1 stream parameters differ from the ones this library writes (8 bit, its quant tables, CRC)");
         return MDVT_ERR_UNSUPPORTED;
@@ -554,9 +643,14 @@ extern "C" int mdvt_ffv1_decode_frames(const uint8_t *packets, const int64_t *pa
     mdvt::ffv1_crc_table_kernel<<<1, 256, 0, s>>>();
     mdvt::ffv1_index_kernel<<<(n_frames + 31) / 32, 32, 0, s>>>(packets, packet_offsets, n_frames, per_frame, slice_offsets, status);
     const int threads = 64;
-    mdvt::ffv1_decode_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(
-        packets, packet_offsets, slice_offsets, n_frames, width, height, nh, nv, 3 + alpha, bgr_order ? 0 : 2, bgr_order ? 2 : 0, context_model,
-        headers, header_len, static_cast<mdvt_ffv1::VlcState *>(states), frames, frame_stride, row_pitch, status);
+    if (context_model == 2 && !alpha)
+        mdvt::ffv1_decode_tiny_kernel<64><<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(
+            packets, packet_offsets, slice_offsets, n_frames, width, height, nh, nv, bgr_order ? 0 : 2, bgr_order ? 2 : 0, headers, header_len, frames,
+            frame_stride, row_pitch, status);
+    else
+        mdvt::ffv1_decode_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(
+            packets, packet_offsets, slice_offsets, n_frames, width, height, nh, nv, 3 + alpha, bgr_order ? 0 : 2, bgr_order ? 2 : 0, context_model,
+            headers, header_len, static_cast<mdvt_ffv1::VlcState *>(states), frames, frame_stride, row_pitch, status);
     MDVT_CUDA_TRY(cudaGetLastError());
     return MDVT_OK;
 }

@@ -23,10 +23,13 @@ namespace mdvt_ffv1 {
 //   0  libavcodec's set 0 for <= 8-bit content: quant11 on three differences, (11*11*11 + 1) / 2 = 666 contexts per plane
 //      context -- what cv2.VideoWriter's files use; packets are byte-identical to libavcodec's at equal slice layout;
 //   1  a 5-level table on the same three differences, (5*5*5 + 1) / 2 = 63 contexts: 1 KB of coder state per slice instead
-//      of 10.6 KB, and less context dilution for slices of a few thousand samples.
+//      of 10.6 KB, and less context dilution for slices of a few thousand samples;
+//   2  a 3-level table (the sign of each difference), (3*3*3 + 1) / 2 = 14 contexts: 224 bytes of coder state per slice, which
+//      the device encoder keeps in shared memory; ~1 % larger files than model 1 on film-like content.
 constexpr int kContexts = 666;        // per plane context, model 0
 constexpr int kContextsSmall = 63;
-MDVT_FFV1_HD inline int contexts_of(int model) { return model ? kContextsSmall : kContexts; }
+constexpr int kContextsTiny = 14;
+MDVT_FFV1_HD inline int contexts_of(int model) { return model == 2 ? kContextsTiny : (model ? kContextsSmall : kContexts); }
 constexpr int kHeaderStride = 16;     // bytes reserved per precomputed range-coded slice header
 constexpr int kFooterBytes = 8;       // 3-byte size, error-status byte, CRC-32
 
@@ -93,13 +96,13 @@ struct BitSink {
 };
 
 // The quantiser of a neighbour difference as arithmetic.  Model 0: libavcodec's quant11[] (levels change at 1, 2, 5, 12,
-// 35); model 1: 5 levels (changes at 1 and 4, the shape of libavcodec's quant5[]).
-template <bool SMALL>
+// 35); model 1: 5 levels (changes at 1 and 4, the shape of libavcodec's quant5[]); model 2: 3 levels (the sign).
+template <int SMALL>
 MDVT_FFV1_HD inline int quant(int d) {
     d &= 0xFF;
     const int neg = d >= 128;
     const int m = neg ? 256 - d : d;
-    const int q = SMALL ? (m >= 1) + (m >= 4) : (m >= 1) + (m >= 2) + (m >= 5) + (m >= 12) + (m >= 35);
+    const int q = SMALL == 2 ? (m >= 1) : (SMALL ? (m >= 1) + (m >= 4) : (m >= 1) + (m >= 2) + (m >= 5) + (m >= 12) + (m >= 35));
     return neg ? -q : q;
 }
 
@@ -182,10 +185,10 @@ MDVT_FFV1_HD inline int eval_raw(const Raw &v) {
 
 // Context and prediction residual of one sample from its neighbours (ffv1.h get_context / predict, sign folded as in
 // encode_line).  q_lt_t = quant(LT - T) comes from the previous sample (it was its quant(T - RT)).
-template <bool SMALL>
+template <int SMALL>
 MDVT_FFV1_HD inline void context_and_residual(int L, int LT, int T, int RT, int C, int q_lt_t, int &q_t_rt, int &ctx, int &diff) {
     q_t_rt = quant<SMALL>(T - RT);
-    ctx = quant<SMALL>(L - LT) + (SMALL ? 5 : 11) * q_lt_t + (SMALL ? 25 : 121) * q_t_rt;
+    ctx = quant<SMALL>(L - LT) + (SMALL == 2 ? 3 : (SMALL ? 5 : 11)) * q_lt_t + (SMALL == 2 ? 9 : (SMALL ? 25 : 121)) * q_t_rt;
     diff = C - median3(L, L + T - LT, T);
     if (ctx < 0) {
         ctx = -ctx;
@@ -213,7 +216,9 @@ struct SliceJob {
 // then the state is forwarded in registers.  first1 / first2: sample 0 of rows y-1 / y-2 (the format's left border:
 // ffv1enc.c encode_rgb_frame sets sample[p][0][-1] = sample[p][1][0] and sample[p][1][w] = sample[p][1][w-1]; rows above
 // the slice read as 0).
-template <int PL, bool SMALL>
+// STRIDE: distance, in states, between consecutive contexts of this slice (1: a contiguous block per slice; > 1: the states of
+// several slices interleaved, e.g. in shared memory with one slice per thread).
+template <int PL, int SMALL, int STRIDE = 1>
 MDVT_FFV1_HD inline void encode_line(BitSink &bs, VlcState *states, const uint8_t *row, const uint8_t *up, bool has_up, int w, int ib,
                                      int ir, int &run_index, int &first1, int &first2) {
     const uint8_t *upper = has_up ? up : row;   // a readable address either way; the value is dropped without a row above
@@ -225,7 +230,7 @@ MDVT_FFV1_HD inline void encode_line(BitSink &bs, VlcState *states, const uint8_
     context_and_residual<SMALL>(first1, first2, T, RT, C, quant<SMALL>(first2 - T), q, ctx, diff);
     first2 = first1;
     first1 = C;
-    VlcState *sp = states + ctx;
+    VlcState *sp = states + ctx * STRIDE;
     VlcState st = *sp;
     // bytes of sample 1 (current row x = 1, upper row x = 2)
     Raw rc_n = load_raw<PL>(row + 3 * (last < 1 ? last : 1), ib, ir);
@@ -249,7 +254,7 @@ MDVT_FFV1_HD inline void encode_line(BitSink &bs, VlcState *states, const uint8_
             T = RT;
             RT = RTn;
             C = Cn;
-            sp_n = states + ctx_n;
+            sp_n = states + ctx_n * STRIDE;
             st_n = *sp_n;
         }
         // sample x
@@ -293,9 +298,9 @@ MDVT_FFV1_HD inline void encode_line(BitSink &bs, VlcState *states, const uint8_
 }
 
 // Codes one slice; returns its size in the packet (body + footer).
-template <bool SMALL>
+template <int SMALL, int STRIDE = 1>
 MDVT_FFV1_HD inline uint32_t encode_slice(const SliceJob &job) {
-    constexpr int NC = SMALL ? kContextsSmall : kContexts;
+    constexpr int NC = SMALL == 2 ? kContextsTiny : (SMALL ? kContextsSmall : kContexts);
     BitSink bs;
     bs.out = job.out;
     bs.pos = 0;
@@ -306,7 +311,7 @@ MDVT_FFV1_HD inline uint32_t encode_slice(const SliceJob &job) {
     for (int i = 0; i < job.header_len; ++i) bs.put(8, job.header[i]);
 
     const int n_pc = job.n_planes > 3 ? 3 : 2;   // plane contexts: G | B,R | alpha
-    for (int i = 0; i < n_pc * NC; ++i) job.states[i] = kVlcInit;
+    for (int i = 0; i < n_pc * NC; ++i) job.states[i * STRIDE] = kVlcInit;
 
     int run_index = 0;
     int f1_0 = 0, f1_1 = 0, f1_2 = 0, f1_3 = 0, f2_0 = 0, f2_1 = 0, f2_2 = 0, f2_3 = 0;   // sample 0 of rows y-1, y-2 per plane
@@ -314,10 +319,10 @@ MDVT_FFV1_HD inline uint32_t encode_slice(const SliceJob &job) {
         const uint8_t *row = job.frame + (int64_t)y * job.row_pitch;
         const uint8_t *up = row - job.row_pitch;
         const bool has_up = y > 0;
-        encode_line<0, SMALL>(bs, job.states, row, up, has_up, job.w, job.ib, job.ir, run_index, f1_0, f2_0);
-        encode_line<1, SMALL>(bs, job.states + NC, row, up, has_up, job.w, job.ib, job.ir, run_index, f1_1, f2_1);
-        encode_line<2, SMALL>(bs, job.states + NC, row, up, has_up, job.w, job.ib, job.ir, run_index, f1_2, f2_2);
-        if (job.n_planes > 3) encode_line<3, SMALL>(bs, job.states + 2 * NC, row, up, has_up, job.w, job.ib, job.ir, run_index, f1_3, f2_3);
+        encode_line<0, SMALL, STRIDE>(bs, job.states, row, up, has_up, job.w, job.ib, job.ir, run_index, f1_0, f2_0);
+        encode_line<1, SMALL, STRIDE>(bs, job.states + NC * STRIDE, row, up, has_up, job.w, job.ib, job.ir, run_index, f1_1, f2_1);
+        encode_line<2, SMALL, STRIDE>(bs, job.states + NC * STRIDE, row, up, has_up, job.w, job.ib, job.ir, run_index, f1_2, f2_2);
+        if (job.n_planes > 3) encode_line<3, SMALL, STRIDE>(bs, job.states + 2 * NC * STRIDE, row, up, has_up, job.w, job.ib, job.ir, run_index, f1_3, f2_3);
     }
     bs.flush();
     const uint32_t body = bs.pos;
@@ -440,7 +445,7 @@ struct SliceInput {
 // One line of one plane.  Plane 0 / 1 leave their samples in the output row as scratch (G' in the green byte; the low 8
 // bits of B' in the blue byte and its ninth bit in the red byte); plane 2 turns the three into the final pixel (inverse
 // RCT); plane 3 (alpha) is decoded and dropped.  Neighbours of the row above are recomputed from its final pixels.
-template <int PL, bool SMALL>
+template <int PL, int SMALL, int STRIDE = 1>
 MDVT_FFV1_HD inline void decode_line(BitSource &bs, VlcState *states, uint8_t *row, const uint8_t *up, bool has_up, int w, int ib, int ir,
                                      int &run_index, int &first1, int &first2) {
     const int last = w - 1;
@@ -454,7 +459,7 @@ MDVT_FFV1_HD inline void decode_line(BitSource &bs, VlcState *states, uint8_t *r
         const int xr = x + 2 < last ? x + 2 : last;
         const int RT_next = has_up ? plane_of_pixel<PL>(up + 3 * xr, ib, ir) : 0;
         const int q_t_rt = quant<SMALL>(T - RT);
-        int ctx = quant<SMALL>(L - LT) + (SMALL ? 5 : 11) * q_lt_t + (SMALL ? 25 : 121) * q_t_rt;
+        int ctx = quant<SMALL>(L - LT) + (SMALL == 2 ? 3 : (SMALL ? 5 : 11)) * q_lt_t + (SMALL == 2 ? 9 : (SMALL ? 25 : 121)) * q_t_rt;
         const bool sign = ctx < 0;
         if (sign) ctx = -ctx;
         int diff;
@@ -474,13 +479,13 @@ MDVT_FFV1_HD inline void decode_line(BitSource &bs, VlcState *states, uint8_t *r
             if (run_count < 0) {
                 run_mode = 0;
                 run_count = 0;
-                diff = get_vlc(bs, states[ctx]);
+                diff = get_vlc(bs, states[ctx * STRIDE]);
                 if (diff >= 0) ++diff;
             } else {
                 diff = 0;
             }
         } else {
-            diff = get_vlc(bs, states[ctx]);
+            diff = get_vlc(bs, states[ctx * STRIDE]);
         }
         if (sign) diff = -diff;
         const int cur = (median3(L, L + T - LT, T) + diff) & 511;
@@ -511,9 +516,9 @@ MDVT_FFV1_HD inline void decode_line(BitSource &bs, VlcState *states, uint8_t *r
 // Decodes one slice into the frame; returns 0, or a negative code: -1 the header is not the expected one, -2 the size in
 // the footer does not match, -3 the bit stream ran past the slice, -4 the slice's CRC-32 is wrong (checked first: a damaged
 // slice is reported, not decoded -- ffv1dec.c decode_frame does the same check on every slice when ec is set).
-template <bool SMALL>
+template <int SMALL, int STRIDE = 1>
 MDVT_FFV1_HD inline int decode_slice(const SliceInput &in) {
-    constexpr int NC = SMALL ? kContextsSmall : kContexts;
+    constexpr int NC = SMALL == 2 ? kContextsTiny : (SMALL ? kContextsSmall : kContexts);
     if (in.size < (uint32_t)(in.header_len + kFooterBytes)) return -2;
     for (int i = 0; i < in.header_len; ++i)
         if (in.data[i] != in.header[i]) return -1;
@@ -529,17 +534,17 @@ MDVT_FFV1_HD inline int decode_slice(const SliceInput &in) {
     bs.acc = 0;
     bs.nbits = 0;
     const int n_pc = in.n_planes > 3 ? 3 : 2;
-    for (int i = 0; i < n_pc * NC; ++i) in.states[i] = kVlcInit;
+    for (int i = 0; i < n_pc * NC; ++i) in.states[i * STRIDE] = kVlcInit;
     int run_index = 0;
     int f1_0 = 0, f1_1 = 0, f1_2 = 0, f1_3 = 0, f2_0 = 0, f2_1 = 0, f2_2 = 0, f2_3 = 0;
     for (int y = 0; y < in.h; ++y) {
         uint8_t *row = in.frame + (int64_t)y * in.row_pitch;
         const uint8_t *up = row - in.row_pitch;
         const bool has_up = y > 0;
-        decode_line<0, SMALL>(bs, in.states, row, up, has_up, in.w, in.ib, in.ir, run_index, f1_0, f2_0);
-        decode_line<1, SMALL>(bs, in.states + NC, row, up, has_up, in.w, in.ib, in.ir, run_index, f1_1, f2_1);
-        decode_line<2, SMALL>(bs, in.states + NC, row, up, has_up, in.w, in.ib, in.ir, run_index, f1_2, f2_2);
-        if (in.n_planes > 3) decode_line<3, SMALL>(bs, in.states + 2 * NC, row, up, has_up, in.w, in.ib, in.ir, run_index, f1_3, f2_3);
+        decode_line<0, SMALL, STRIDE>(bs, in.states, row, up, has_up, in.w, in.ib, in.ir, run_index, f1_0, f2_0);
+        decode_line<1, SMALL, STRIDE>(bs, in.states + NC * STRIDE, row, up, has_up, in.w, in.ib, in.ir, run_index, f1_1, f2_1);
+        decode_line<2, SMALL, STRIDE>(bs, in.states + NC * STRIDE, row, up, has_up, in.w, in.ib, in.ir, run_index, f1_2, f2_2);
+        if (in.n_planes > 3) decode_line<3, SMALL, STRIDE>(bs, in.states + 2 * NC * STRIDE, row, up, has_up, in.w, in.ib, in.ir, run_index, f1_3, f2_3);
     }
     // bits consumed must lie inside the body (the window holds bytes read ahead)
     const int64_t consumed_bits = (int64_t)(bs.p - (in.data + in.header_len)) * 8 - bs.nbits;

@@ -37,7 +37,8 @@ def slice_grid(width: int, height: int, target_pixels: int = 4096) -> Tuple[int,
 
 def stream_setup(width: int, height: int, nh: int, nv: int, alpha: bool = False, context_model: int = 0):
     """(configuration record bytes, slice headers (S, 16) uint8, header lengths (S,) int32) -- host arrays.
-    context_model 0: libavcodec's quant tables (666 contexts), 1: the 5-level table (63 contexts)."""
+    context_model 0: libavcodec's quant tables (666 contexts), 1: the 5-level table (63 contexts), 2: the 3-level table (14 contexts:
+    the device encoder keeps the coder states in shared memory; ~1 % larger files than model 1)."""
     lib = _lib.load()
     config = (C.c_uint8 * 64)()
     n = C.c_int(0)

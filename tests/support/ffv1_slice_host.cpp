@@ -48,7 +48,7 @@ extern "C" long long ffv1_host_encode_frame(const uint8_t *frame, long long row_
             }
             job.out = packet + pos;
             job.crc_table = g_crc;
-            pos += context_model ? mdvt_ffv1::encode_slice<true>(job) : mdvt_ffv1::encode_slice<false>(job);
+            pos += context_model == 2 ? mdvt_ffv1::encode_slice<2>(job) : (context_model ? mdvt_ffv1::encode_slice<1>(job) : mdvt_ffv1::encode_slice<0>(job));
         }
     free(states);
     return pos;
@@ -103,7 +103,7 @@ extern "C" int ffv1_host_decode_frame(const uint8_t *packet, long long packet_le
             in.states = states;
             init_crc();
             in.crc_table = g_crc;
-            rc = context_model ? mdvt_ffv1::decode_slice<true>(in) : mdvt_ffv1::decode_slice<false>(in);
+            rc = context_model == 2 ? mdvt_ffv1::decode_slice<2>(in) : (context_model ? mdvt_ffv1::decode_slice<1>(in) : mdvt_ffv1::decode_slice<0>(in));
         }
     free(states);
     free(starts);

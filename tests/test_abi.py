@@ -125,11 +125,13 @@ def test_ffv1_argument_validation_without_a_device():
     assert lib.mdvt_ffv1_stream_setup(64, 48, 33, 32, 0, 0, cfg, 64, C.byref(n), hdr, lens) == -1
     assert b"1024" in lib.mdvt_last_error()
     assert lib.mdvt_ffv1_stream_setup(64, 48, 65, 1, 0, 0, cfg, 64, C.byref(n), hdr, lens) == -1                       # more slices than columns
-    assert lib.mdvt_ffv1_stream_setup(64, 48, 2, 2, 0, 2, cfg, 64, C.byref(n), hdr, lens) == -1                        # unknown context model
+    assert lib.mdvt_ffv1_stream_setup(64, 48, 2, 2, 0, 2, cfg, 64, C.byref(n), hdr, lens) == 0 and 0 < n.value < 42   # the 14-context tables
+    assert lib.mdvt_ffv1_stream_setup(64, 48, 2, 2, 0, 3, cfg, 64, C.byref(n), hdr, lens) == -1                        # unknown context model
     assert lib.mdvt_ffv1_slice_capacity(3840, 1080, 59, 17, 0) % 16 == 0 and lib.mdvt_ffv1_slice_capacity(3840, 1080, 59, 17, 0) > 66 * 64 * 3
     assert lib.mdvt_ffv1_slice_capacity(0, 1080, 1, 1, 0) == -1
     assert lib.mdvt_ffv1_state_bytes(2, 59, 17, 0, 0) == 2 * 1003 * 2 * 666 * 8
     assert lib.mdvt_ffv1_state_bytes(2, 59, 17, 1, 1) == 2 * 1003 * 3 * 63 * 8
+    assert lib.mdvt_ffv1_state_bytes(2, 59, 17, 0, 2) == 2 * 1003 * 2 * 14 * 8
     assert lib.mdvt_ffv1_state_bytes(2, 59, 17, 0, 3) == -1
     assert lib.mdvt_ffv1_encode_frames(None, 0, 0, 0, 64, 48, 2, 2, 0, 0, 0, None, None, None, None, 0, None, None, None, None) == 0  # no frames
     assert lib.mdvt_ffv1_encode_frames(None, 0, 0, 1, 64, 48, 2, 2, 0, 0, 0, None, None, None, None, 16, None, None, None, None) == -1

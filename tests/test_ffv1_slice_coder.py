@@ -103,12 +103,13 @@ def test_packet_equals_libavcodec_key_frame(host_coder, tmp_path):
 
 @pytest.mark.parametrize("w,h,nh,nv,alpha,model", [(64, 48, 8, 8, False, 0), (64, 48, 16, 12, True, 0), (70, 33, 5, 7, False, 0),
                                                    (33, 17, 33, 17, False, 0), (48, 32, 1, 1, False, 0), (64, 48, 8, 8, False, 1),
-                                                   (70, 33, 5, 7, True, 1), (48, 32, 1, 1, False, 1)])
+                                                   (70, 33, 5, 7, True, 1), (48, 32, 1, 1, False, 1), (64, 48, 8, 8, False, 2),
+                                                   (70, 33, 5, 7, True, 2), (48, 32, 1, 1, False, 2)])
 def test_packet_equals_oracle(host_coder, w, h, nh, nv, alpha, model):
     """The oracle codes with whatever quant tables the configuration record carries: model 0 = libavcodec's (666
-    contexts), model 1 = the 5-level table (63 contexts)."""
+    contexts), model 1 = the 5-level table (63 contexts), model 2 = the 3-level table (14 contexts)."""
     base = fo.parse_config(ffv1_gpu.stream_setup(w, h, nh, nv, alpha, model)[0])
-    assert base["context_count"][0] == (63 if model else 666) and base["quant_table_count"] == (1 if model else 2)
+    assert base["context_count"][0] == (666, 63, 14)[model] and base["quant_table_count"] == (1 if model else 2)
     for k, f in enumerate(_content(w, h, seed=5)):
         ss = [fo.SliceState(base) for _ in range(nh * nv)]
         want = fo.encode_frame(np.dstack([f, np.full((h, w), 255, np.uint8)]), base, True, ss)
@@ -116,7 +117,8 @@ def test_packet_equals_oracle(host_coder, w, h, nh, nv, alpha, model):
 
 
 @pytest.mark.parametrize("w,h,nh,nv,alpha,model", [(256, 144, 16, 9, False, 0), (256, 144, 32, 32, False, 0), (200, 120, 7, 5, True, 0),
-                                                   (256, 144, 16, 9, False, 1), (200, 120, 7, 5, True, 1)])
+                                                   (256, 144, 16, 9, False, 1), (200, 120, 7, 5, True, 1), (256, 144, 16, 9, False, 2),
+                                                   (200, 120, 7, 5, True, 2)])
 def test_stream_decodes_in_opencv(host_coder, tmp_path, w, h, nh, nv, alpha, model):
     """Packets of the slice coder + this library's configuration record + mkv_join's muxer -> OpenCV returns the frames."""
     frames = _content(w, h, seed=9)
@@ -138,7 +140,8 @@ def test_stream_decodes_in_opencv(host_coder, tmp_path, w, h, nh, nv, alpha, mod
 
 @pytest.mark.parametrize("w,h,nh,nv,alpha,model", [(64, 48, 8, 8, False, 0), (70, 33, 5, 7, True, 0), (33, 17, 33, 17, False, 0),
                                                    (48, 32, 1, 1, False, 0), (256, 144, 16, 9, False, 0), (64, 48, 8, 8, False, 1),
-                                                   (70, 33, 5, 7, True, 1), (256, 144, 16, 9, False, 1)])
+                                                   (70, 33, 5, 7, True, 1), (256, 144, 16, 9, False, 1), (64, 48, 8, 8, False, 2),
+                                                   (70, 33, 5, 7, True, 2), (256, 144, 16, 9, False, 2)])
 def test_decoder_mirrors_encoder_and_oracle(host_coder, w, h, nh, nv, alpha, model):
     """The slice decoder the device runs (host-stepped): packets of the slice coder and of the oracle's encoder decode
     to the source frames in either channel order; damaged packets are reported, not decoded."""
@@ -148,7 +151,7 @@ def test_decoder_mirrors_encoder_and_oracle(host_coder, w, h, nh, nv, alpha, mod
         rc, out = host_coder.decode(packet, w, h, nh, nv, alpha, True, model)
         assert rc == 0 and np.array_equal(out, f), f"content {k}"
         if k == 0 and 16 * nh * nv <= w * h <= 64 * 48 * 2:      # the other model's decoder must not reproduce the frame
-            assert not np.array_equal(host_coder.decode(packet, w, h, nh, nv, alpha, True, 1 - model)[1], f)
+            assert not np.array_equal(host_coder.decode(packet, w, h, nh, nv, alpha, True, (model + 1) % 3)[1], f)
         rc, out = host_coder.decode(packet, w, h, nh, nv, alpha, False, model)     # RGB-order output of a BGR-order source
         assert rc == 0 and np.array_equal(out, f[..., ::-1]), f"content {k} (channel order)"
         if w * h <= 64 * 48:
@@ -182,7 +185,7 @@ def test_parse_config_accepts_only_this_librarys_streams(tmp_path):
 
     lib = _lib.load()
     nh, nv, alpha, model = C.c_int(), C.c_int(), C.c_int(), C.c_int()
-    for grid in ((59, 17, 0, 0), (2, 2, 1, 0), (1, 1, 0, 0), (59, 17, 0, 1), (4, 3, 1, 1)):
+    for grid in ((59, 17, 0, 0), (2, 2, 1, 0), (1, 1, 0, 0), (59, 17, 0, 1), (4, 3, 1, 1), (59, 17, 0, 2), (4, 3, 1, 2)):
         cfg = ffv1_gpu.stream_setup(3840, 1080, grid[0], grid[1], bool(grid[2]), grid[3])[0]
         assert lib.mdvt_ffv1_parse_config(cfg, len(cfg), 3840, 1080, C.byref(nh), C.byref(nv), C.byref(alpha), C.byref(model)) == 0
         assert (nh.value, nv.value, alpha.value, model.value) == grid
@@ -237,7 +240,7 @@ def test_round_trip_property(host_coder):
     from hypothesis import strategies as st
 
     @settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
-    @given(w=st.integers(1, 96), h=st.integers(1, 40), fx=st.integers(1, 12), fy=st.integers(1, 12), alpha=st.booleans(), model=st.integers(0, 1),
+    @given(w=st.integers(1, 96), h=st.integers(1, 40), fx=st.integers(1, 12), fy=st.integers(1, 12), alpha=st.booleans(), model=st.integers(0, 2),
            bgr=st.booleans(), kind=st.integers(0, 4), seed=st.integers(0, 2**31 - 1))
     def check(w, h, fx, fy, alpha, model, bgr, kind, seed):
         nh, nv = min(fx, w), min(fy, h)

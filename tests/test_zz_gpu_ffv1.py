@@ -221,6 +221,24 @@ def test_small_context_model_decoder_mirrors_encoder(w, h, slices, alpha, rgb):
     test_device_decoder_mirrors_encoder(w, h, slices, alpha, rgb, 1)
 
 
+# ---- context model 2 (14 contexts): the encoder keeps the coder states in shared memory (ffv1_encode_tiny_kernel; with the alpha
+# plane the global-state kernel codes it) -------------------------------------------------------------------------------------
+@pytest.mark.parametrize("w,h,slices,alpha,rgb", [(256, 144, (16, 9), False, True), (200, 120, (7, 5), True, False), (3840, 1080, None, False, True)])
+def test_tiny_context_model_packets_equal_host_stepped_coder(host_coder, w, h, slices, alpha, rgb):
+    if slices is None:
+        slices = ffv1_gpu.slice_grid(w, h)
+    test_packets_equal_host_stepped_coder(host_coder, w, h, slices, alpha, rgb, 2)
+
+
+def test_tiny_context_model_files_decode_bit_exactly_in_opencv(tmp_path):
+    test_writer_files_decode_bit_exactly_in_opencv(tmp_path, 640, 360, 9, 2)
+
+
+@pytest.mark.parametrize("w,h,slices,alpha,rgb", [(256, 144, (16, 9), False, True), (200, 120, (7, 5), True, False)])
+def test_tiny_context_model_decoder_mirrors_encoder(w, h, slices, alpha, rgb):
+    test_device_decoder_mirrors_encoder(w, h, slices, alpha, rgb, 2)
+
+
 def test_cli_stereo_rerender_with_gpu_writer_device_hand_off(tmp_path):
     """Without --create_sbs_depth_video the plain stereo mode hands the row kernel's device tensors to the coder."""
     test_cli_stereo_rerender_with_gpu_writer_equals_default_writer(tmp_path, depth_video=False)
