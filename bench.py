@@ -604,9 +604,9 @@ def run_ours(args):
                 return {"frames_per_s": 1e3 * frames_per_launch / ms, "ms_per_frame": ms / frames_per_launch, "batch": frames_per_launch,
                         "slices_per_frame": enc.per_frame, "bytes_per_frame": int(offsets[-1].item()) / frames_per_launch}
 
-            # model 2 keeps its 224 bytes of state per slice in shared memory and wants more slices in flight (128 frames per launch)
+            # model 2 keeps its 224 bytes of state per slice in shared memory and wants more slices in flight (256 frames per launch)
             for model, key, per_launch in ((0, "libavcodec_tables_666_contexts", batch), (1, "small_tables_63_contexts", batch),
-                                           (2, "tiny_tables_14_contexts", min(128, n_frames))):
+                                           (2, "tiny_tables_14_contexts", min(256, n_frames))):
                 result_codec[key] = time_encoder(out_sbs, model, per_launch)
             # the same coder on film-like content (a blurred texture that pans, sensor noise in the low bits, a flat patch and a
             # black band: benchmarks/ffv1_gpu_bench.frames_like) -- the rendered synthetic clip above is i.i.d. colour noise, which
@@ -614,9 +614,9 @@ def run_ours(args):
             sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
             from ffv1_gpu_bench import frames_like
 
-            film = torch.from_numpy(frames_like(2 * WIDTH, HEIGHT, 128)).to(dev)
+            film = torch.from_numpy(frames_like(2 * WIDTH, HEIGHT, 256)).to(dev)
             result_codec["film_like_content_63_contexts"] = time_encoder(film, 1, 64)
-            result_codec["film_like_content_14_contexts"] = time_encoder(film, 2, 128)
+            result_codec["film_like_content_14_contexts"] = time_encoder(film, 2, 256)
             del film
         except Exception as exc:  # noqa: BLE001 - informational leg only
             result_codec = {"error": f"{type(exc).__name__}: {exc}"}

@@ -390,7 +390,7 @@ MDVT_API int mdvt_stereo_conv_vrows_supported(const mdvt_conv_frame *frames_host
  * carry: at OpenCV's 2 x 2 slices + alpha the key-frame packets are byte-identical to libavcodec's); context_model = 1
  * writes a 5-level table instead (63 contexts: a tenth of the coder state per slice; the tables travel in the
  * configuration record, so any FFV1 decoder follows); context_model = 2 writes a 3-level table (14 contexts, 224 bytes of
- * coder state per slice, which the device coder then keeps in shared memory: ~1.5 x the encoder throughput of model 1 for ~1 %
+ * coder state per slice, which the device coder then keeps in shared memory: ~1.8 x the encoder throughput of model 1 for ~1 %
  * larger files on film-like content; the `states` buffer is not touched in that case unless alpha = 1). */
 
 /* HOST function, no device needed.  Writes the codec configuration record (Matroska CodecPrivate; <= 64 bytes) and the

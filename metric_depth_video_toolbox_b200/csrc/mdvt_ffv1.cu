@@ -6,6 +6,7 @@
 //
 // Host side (no device needed): the range coder of rangecoder.c for the configuration record (ffv1enc.c
 // write_extradata) and the per-slice headers (encode_slice_header); tests pin both byte-for-byte against OpenCV's files.
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -571,6 +572,14 @@ extern "C" int mdvt_ffv1_encode_frames(const uint8_t *frames, int64_t frame_stri
     MDVT_REQUIRE(total < (1LL << 30), "too many slices in one call");
     mdvt::ffv1_crc_table_kernel<<<1, 256, 0, s>>>();
     const int threads = 64;
+    if (context_model == 2 && !alpha) {
+        // The coder reads its pixels byte by byte through the L1 (60 M sector look-ups per 3840x1080 frame), so the L1 matters as
+        // much as the resident warps: with the default carve-out 10 CTAs per SM leave it 60 KB (6.5 k frames/s), 12 CTAs 23 KB
+        // (2.8 k); asking for half of the array (132 KB of shared memory = 7 CTAs, 124 KB of L1) gives 7.9-8.3 k
+        // (profiles/r02_ffv1_state_experiments.txt).  MDVT_FFV1_CARVEOUT=<percent> overrides (tuning aid).
+        static const int carve = getenv("MDVT_FFV1_CARVEOUT") ? atoi(getenv("MDVT_FFV1_CARVEOUT")) : 52;
+        MDVT_CUDA_TRY(cudaFuncSetAttribute(mdvt::ffv1_encode_tiny_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    }
     if (context_model == 2 && !alpha)
         mdvt::ffv1_encode_tiny_kernel<64><<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(
             frames, frame_stride, row_pitch, n_frames, width, height, nh, nv, bgr_order ? 0 : 2, bgr_order ? 2 : 0, headers, header_len, slices,
