@@ -575,7 +575,7 @@ extern "C" int mdvt_ffv1_encode_frames(const uint8_t *frames, int64_t frame_stri
     if (context_model == 2 && !alpha) {
         // The coder reads its pixels byte by byte through the L1 (60 M sector look-ups per 3840x1080 frame), so the L1 matters as
         // much as the resident warps: with the default carve-out 10 CTAs per SM leave it 60 KB (6.5 k frames/s), 12 CTAs 23 KB
-        // (2.8 k); asking for half of the array (132 KB of shared memory = 7 CTAs, 124 KB of L1) gives 7.9-8.3 k
+        // (2.8 k); asking for half of the array (132 KB of shared memory = 6 CTAs, 121 KB of L1) gives 7.9-8.3 k
         // (profiles/r02_ffv1_state_experiments.txt).  MDVT_FFV1_CARVEOUT=<percent> overrides (tuning aid).
         static const int carve = getenv("MDVT_FFV1_CARVEOUT") ? atoi(getenv("MDVT_FFV1_CARVEOUT")) : 52;
         MDVT_CUDA_TRY(cudaFuncSetAttribute(mdvt::ffv1_encode_tiny_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
