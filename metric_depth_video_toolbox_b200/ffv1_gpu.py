@@ -252,6 +252,16 @@ def _make_container_template(width: int, height: int, fps: float):
             os.remove(path)
 
 
+def default_context_model() -> int:
+    """The writers' context model: 1 (63 contexts) unless MDVT_FFV1_CONTEXT_MODEL names 0, 1 or 2."""
+    v = os.environ.get("MDVT_FFV1_CONTEXT_MODEL", "").strip()
+    if not v:
+        return 1
+    if v not in ("0", "1", "2"):
+        raise ValueError(f"MDVT_FFV1_CONTEXT_MODEL must be 0, 1 or 2, not {v!r}")
+    return int(v)
+
+
 class GpuFfv1Writer:
     """`cv2.VideoWriter(path, FFV1, fps, size)` for frames that live on the device.  write() takes (n, H, W, 3) uint8
     tensors (device; host tensors / arrays are uploaded before it returns, so the caller may recycle its buffer), RGB by
@@ -260,10 +270,12 @@ class GpuFfv1Writer:
 
     def __init__(self, path: str, fps: float, size: Tuple[int, int], device=None, batch: int = 8,
                  slices: Optional[Tuple[int, int]] = None, alpha: bool = False, join_on_close: bool = True, depth: int = 2,
-                 context_model: int = 1):
-        """context_model 1 (default): the 63-context quant table -- 1 KB instead of 10.6 KB of coder state per slice thread,
-        ~40 % more frames/s on the B200 and files within -0.5 .. +1 % of the 666-context ones (the tables travel in the
-        configuration record: any FFV1 decoder reads either); 0: libavcodec's own tables.
+                 context_model: Optional[int] = None):
+        """context_model 1 (the default, or what MDVT_FFV1_CONTEXT_MODEL says): the 63-context quant table -- 1 KB instead of
+        10.6 KB of coder state per slice thread, ~40 % more frames/s on the B200 and files within -0.5 .. +1 % of the
+        666-context ones (the tables travel in the configuration record: any FFV1 decoder reads either); 0: libavcodec's
+        own tables; 2: the 14-context table whose coder states the kernels keep in shared memory (~1.9 x the encoder
+        throughput of model 1 for ~1 % larger files).
         join_on_close=False: `path` is one rank's segment of a torchrun job; close() leaves `<path>.plan.json` next to
         it in video_io.ParallelWriter's format, and rank 0 stitches the segments at packet level (video_io.join_plans)."""
         import queue
@@ -273,7 +285,7 @@ class GpuFfv1Writer:
         self.join_on_close = join_on_close
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.enc = Ffv1Encoder(self.size[0], self.size[1], self.device, max_frames=batch, slices=slices, alpha=alpha,
-                               context_model=context_model)
+                               context_model=default_context_model() if context_model is None else context_model)
         header, tracks = container_template(self.size[0], self.size[1], fps)
         self._mux = mkv_join.StreamWriter(path, header, mkv_join.replace_codec_private(tracks, self.enc.config), fps)
         self.frames = 0

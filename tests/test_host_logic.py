@@ -376,3 +376,17 @@ def test_conv_vrows_limits_check_runs_on_the_host():
     assert not ops.conv_vrows_supported(tilted, 640, 480)
     with pytest.raises(ValueError):
         ops.conv_vrows_supported(np.zeros((2, 7), dtype=np.float32), 640, 480)
+
+
+def test_writer_context_model_comes_from_the_environment(monkeypatch):
+    """MDVT_FFV1_CONTEXT_MODEL picks the device writers' quant tables (default 1; 2 = the 14-context tables); anything else is refused."""
+    from metric_depth_video_toolbox_b200 import ffv1_gpu
+
+    monkeypatch.delenv("MDVT_FFV1_CONTEXT_MODEL", raising=False)
+    assert ffv1_gpu.default_context_model() == 1
+    for v in ("0", "1", "2"):
+        monkeypatch.setenv("MDVT_FFV1_CONTEXT_MODEL", v)
+        assert ffv1_gpu.default_context_model() == int(v)
+    monkeypatch.setenv("MDVT_FFV1_CONTEXT_MODEL", "3")
+    with pytest.raises(ValueError):
+        ffv1_gpu.default_context_model()
